@@ -1,0 +1,47 @@
+// C-ABI surface of libmdiff: error handling, launch accounting and the op-level entry points.
+#include "host.h"
+
+#include <stdarg.h>
+#include <stdio.h>
+#include <atomic>
+
+namespace md {
+
+static thread_local char g_err[1024] = "";
+static std::atomic<long long> g_launches{0};
+
+int set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return -1;
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+}  // namespace md
+
+extern "C" {
+
+int md_version(void) { return 100; }
+const char* md_last_error(void) { return md::g_err; }
+long long md_launch_count(void) { return md::g_launches.load(); }
+void md_reset_launch_count(void) { md::g_launches.store(0); }
+
+int md_op_conv_gemm(const md_conv_gemm_args* args, void* stream) {
+  if (!args) return md::set_error("md_op_conv_gemm: null args");
+  return md::launch_conv_gemm(*args, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,146 @@
+// Host launcher for the tcgen05 implicit-GEMM kernel: builds the TMA tensor maps and picks the tile shape.
+#include "conv_gemm.cuh"
+#include "host.h"
+
+#include <mutex>
+
+namespace md {
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+    if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = reinterpret_cast<PFN_encodeTiled>(p);
+  });
+  return fn;
+}
+
+static int pow2_floor(int v) {
+  int p = 1;
+  while (p * 2 <= v) p *= 2;
+  return p;
+}
+
+template <int BN, int STAGES>
+static int launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p, int grid,
+                       cudaStream_t stream) {
+  using S = ConvGemmSmem<BN, STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         S::kTotal);
+    if (e != cudaSuccess) return set_error("cudaFuncSetAttribute(conv_gemm): %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  conv_gemm_kernel<BN, STAGES><<<grid, 192, S::kTotal, stream>>>(tmA, tmB, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error("conv_gemm launch: %s", cudaGetErrorString(e));
+  count_launch();
+  return 0;
+}
+
+int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+  if (a.Cin % kBlockK != 0) return set_error("conv_gemm: Cin=%d must be a multiple of 64", a.Cin);
+  if (a.N % 8 != 0) return set_error("conv_gemm: N=%d must be a multiple of 8", a.N);
+  if (a.ntaps < 1 || a.ntaps > kMaxTaps) return set_error("conv_gemm: bad tap count %d", a.ntaps);
+  if ((reinterpret_cast<uintptr_t>(a.A) & 15) || (reinterpret_cast<uintptr_t>(a.Wt) & 15))
+    return set_error("conv_gemm: operands must be 16-byte aligned");
+  const int Cpitch = a.Cpitch ? a.Cpitch : a.Cin;
+  if (Cpitch % 8 != 0) return set_error("conv_gemm: channel pitch %d must be a multiple of 8", Cpitch);
+
+  ConvGemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.W = a.W; p.H = a.H; p.D = a.D; p.B = a.B;
+  int rem = kBlockM;
+  p.bw = std::min(pow2_floor(a.W), rem); rem /= p.bw;
+  p.bh = std::min(pow2_floor(a.H), rem); rem /= p.bh;
+  p.bd = std::min(pow2_floor(a.D), rem); rem /= p.bd;
+  p.bb = rem;
+  p.nxb = (a.W + p.bw - 1) / p.bw;
+  p.nyb = (a.H + p.bh - 1) / p.bh;
+  p.nzb = (a.D + p.bd - 1) / p.bd;
+  p.nbb = (a.B + p.bb - 1) / p.bb;
+  p.m_tiles = p.nxb * p.nyb * p.nzb * p.nbb;
+  p.kblocks_per_tap = a.Cin / kBlockK;
+  p.ntaps = a.ntaps;
+  for (int t = 0; t < a.ntaps; ++t) {
+    p.tdx[t] = static_cast<int8_t>(a.tap[t][0]);
+    p.tdy[t] = static_cast<int8_t>(a.tap[t][1]);
+    p.tdz[t] = static_cast<int8_t>(a.tap[t][2]);
+  }
+  p.N = a.N;
+  p.OW = a.OW ? a.OW : a.W; p.OH = a.OH ? a.OH : a.H; p.OD = a.OD ? a.OD : a.D;
+  p.osx = a.os[0] ? a.os[0] : 1; p.osy = a.os[1] ? a.os[1] : 1; p.osz = a.os[2] ? a.os[2] : 1;
+  p.opx = a.op[0]; p.opy = a.op[1]; p.opz = a.op[2];
+  p.act = a.act;
+  const int n_out = (a.act == ACT_GEGLU) ? a.N / 2 : a.N;
+  p.ldo = a.ldo ? a.ldo : n_out;
+  p.bias = a.bias; p.rowvec = a.rowvec; p.rowvec_ld = a.rowvec_ld ? a.rowvec_ld : a.N;
+  p.res_f32 = a.res_f32; p.res_bf16 = static_cast<const __nv_bfloat16*>(a.res_bf16);
+  p.out_f32 = a.out_f32; p.out_bf16 = static_cast<__nv_bfloat16*>(a.out_bf16);
+  p.out_scale = a.out_scale == 0.f ? 1.f : a.out_scale;
+  if (p.ldo % 8 != 0) return set_error("conv_gemm: ldo=%d must be a multiple of 8", p.ldo);
+  if (a.act == ACT_GEGLU && !a.out_bf16) return set_error("conv_gemm: GEGLU epilogue writes bf16 only");
+
+  // ---- tile N selection
+  int BN = a.BN;
+  if (BN == 0) {
+    if (a.act == ACT_GEGLU) BN = 128;
+    else if (a.N % 160 == 0 && a.N % 256 != 0 && (long long)p.m_tiles * (a.N / 160) >= 120) BN = 160;
+    else if (a.N >= 256 && (long long)p.m_tiles * ((a.N + 255) / 256) >= 148) BN = 256;
+    else if (a.N >= 128 && (long long)p.m_tiles * ((a.N + 127) / 128) >= 100) BN = 128;
+    else if (a.N > 64 && a.N % 160 == 0 && a.N % 128 != 0) BN = 160;
+    else BN = (a.N <= 64) ? 64 : ((a.N % 128 == 0 && (long long)p.m_tiles * (a.N / 128) >= 64) ? 128 : 64);
+  }
+  if (a.act == ACT_GEGLU && BN != 128) return set_error("conv_gemm: GEGLU requires BN=128");
+  p.n_tiles = (a.N + BN - 1) / BN;
+
+  // ---- tensor maps
+  CUtensorMap tmA, tmB;
+  {
+    cuuint64_t dims[5] = {(cuuint64_t)a.Cin, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.D, (cuuint64_t)a.B};
+    cuuint64_t strides[4] = {(cuuint64_t)Cpitch * 2, (cuuint64_t)Cpitch * 2 * a.W,
+                             (cuuint64_t)Cpitch * 2 * a.W * a.H, (cuuint64_t)Cpitch * 2 * a.W * a.H * a.D};
+    cuuint32_t box[5] = {(cuuint32_t)kBlockK, (cuuint32_t)p.bw, (cuuint32_t)p.bh, (cuuint32_t)p.bd,
+                         (cuuint32_t)p.bb};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(a.A), dims, strides, box,
+                     es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error("cuTensorMapEncodeTiled(A) failed: %d (W=%d H=%d D=%d B=%d C=%d)", (int)r,
+                                            a.W, a.H, a.D, a.B, a.Cin);
+  }
+  {
+    const cuuint64_t Ktot = (cuuint64_t)a.ntaps * a.Cin;
+    cuuint64_t dims[2] = {Ktot, (cuuint64_t)a.N};
+    cuuint64_t strides[1] = {Ktot * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)BN};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(a.Wt), dims, strides, box,
+                     es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error("cuTensorMapEncodeTiled(B) failed: %d (K=%llu N=%d)", (int)r,
+                                            (unsigned long long)Ktot, a.N);
+  }
+
+  const int total = p.m_tiles * p.n_tiles;
+  const int grid = std::min(total, num_sms());
+  switch (BN) {
+    case 64:  return launch_impl<64, 8>(tmA, tmB, p, grid, stream);
+    case 128: return launch_impl<128, 6>(tmA, tmB, p, grid, stream);
+    case 160: return launch_impl<160, 5>(tmA, tmB, p, grid, stream);
+    case 256: return launch_impl<256, 4>(tmA, tmB, p, grid, stream);
+    default:  return set_error("conv_gemm: unsupported BN=%d", BN);
+  }
+}
+
+}  // namespace md

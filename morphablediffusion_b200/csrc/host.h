@@ -1,0 +1,40 @@
+// Host-side helpers shared by all translation units of libmdiff.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <string.h>
+#include <algorithm>
+
+#include "../../include/mdiff.h"
+
+namespace md {
+
+typedef md_conv_gemm_args ConvGemmArgs;
+
+int set_error(const char* fmt, ...);  // stores the message, returns -1
+void count_launch(int n = 1);
+int num_sms();
+
+int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream);
+
+#define MD_CHECK(expr)                 \
+  do {                                 \
+    int _rc = (expr);                  \
+    if (_rc != 0) return _rc;          \
+  } while (0)
+
+#define MD_CUDA(expr)                                                                   \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess) return md::set_error("%s: %s", #expr, cudaGetErrorString(_e)); \
+  } while (0)
+
+inline int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error("%s launch: %s", what, cudaGetErrorString(e));
+  count_launch();
+  return 0;
+}
+
+}  // namespace md

@@ -1,0 +1,574 @@
+"""ORACLE (test infrastructure — never imported by the product path).
+
+CPU fp32 restatement, in functional torch, of the reference's multi-view denoise step
+(`SyncDDIMSampler.denoise_apply`, /root/reference/ldm/models/diffusion/morphable_diffusion.py:701-739) and of
+everything it calls.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this file.  Every function cites the reference lines it restates.  Parameters are addressed by the
+reference's state-dict keys so the same seeded state dict drives the reference modules, this oracle and the CUDA
+path.
+
+Pinning: `oracle/make_golden.py` runs the *real* reference modules (imported from /root/reference in the build
+container) on seeded inputs and stores their outputs under tests/golden/; tests/test_oracle_golden.py checks this
+restatement against those vectors.  The one place the reference itself cannot be run is spconv's SparseConvNet
+(spconv is not installed / not vendored): `sparse_conv_net` below restates spconv-2.x semantics on a dense grid and
+is therefore "parity unpinned" at that boundary.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+# ----------------------------------------------------------------------------- small helpers
+
+
+def _w(sd, key):
+    return sd[key].float()
+
+
+def timestep_embedding(t, dim, max_period=10000):
+    """ldm/modules/diffusionmodules/util.py:151-171."""
+    half = dim // 2
+    freqs = torch.exp(-math.log(max_period) * torch.arange(half, dtype=torch.float32) / half)
+    args = t[:, None].float() * freqs[None]
+    return torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
+
+
+def group_norm(x, sd, key, groups, eps=1e-5):
+    return F.group_norm(x, groups, _w(sd, key + ".weight"), _w(sd, key + ".bias"), eps)
+
+
+def conv(x, sd, key, stride=1, padding=0):
+    w = _w(sd, key + ".weight")
+    b = sd.get(key + ".bias")
+    b = None if b is None else b.float()
+    if w.dim() == 4:
+        return F.conv2d(x, w, b, stride=stride, padding=padding)
+    return F.conv3d(x, w, b, stride=stride, padding=padding)
+
+
+def linear(x, sd, key):
+    b = sd.get(key + ".bias")
+    return F.linear(x, _w(sd, key + ".weight"), None if b is None else b.float())
+
+
+# ----------------------------------------------------------------------------- UNet (K10-K13)
+
+
+def res_block(x, emb, sd, p):
+    """ResBlock._forward, ldm/modules/diffusionmodules/openaimodel.py:256-276 (no up/down, no scale-shift)."""
+    h = conv(F.silu(group_norm(x, sd, p + "in_layers.0", 32)), sd, p + "in_layers.2", padding=1)
+    e = linear(F.silu(emb), sd, p + "emb_layers.1")
+    h = h + e[:, :, None, None]
+    h = conv(F.silu(group_norm(h, sd, p + "out_layers.0", 32)), sd, p + "out_layers.3", padding=1)
+    if (p + "skip_connection.weight") in sd:
+        x = conv(x, sd, p + "skip_connection")
+    return x + h
+
+
+def cross_attention(x, ctx, sd, p, heads):
+    """CrossAttention.forward, ldm/modules/attention.py:179-203."""
+    q = linear(x, sd, p + "to_q")
+    ctx = x if ctx is None else ctx
+    k = linear(ctx, sd, p + "to_k")
+    v = linear(ctx, sd, p + "to_v")
+    b, n, c = q.shape
+    d = c // heads
+
+    def split(t):
+        return t.view(b, -1, heads, d).permute(0, 2, 1, 3)
+
+    q, k, v = split(q), split(k), split(v)
+    sim = torch.matmul(q, k.transpose(-1, -2)) * (d ** -0.5)
+    attn = sim.softmax(dim=-1)
+    out = torch.matmul(attn, v).permute(0, 2, 1, 3).reshape(b, n, c)
+    return linear(out, sd, p + "to_out.0")
+
+
+def transformer_block(x, ctx, sd, p, heads):
+    """BasicTransformerBlock._forward, ldm/modules/attention.py:265-269 (+ GEGLU :42-44, FeedForward :72-73)."""
+    c = x.shape[-1]
+    ln = lambda t, k: F.layer_norm(t, (c,), _w(sd, p + k + ".weight"), _w(sd, p + k + ".bias"), 1e-5)
+    x = cross_attention(ln(x, "norm1"), None, sd, p + "attn1.", heads) + x
+    x = cross_attention(ln(x, "norm2"), ctx, sd, p + "attn2.", heads) + x
+    y = linear(ln(x, "norm3"), sd, p + "ff.net.0.proj")
+    a, gate = y.chunk(2, dim=-1)
+    x = linear(a * F.gelu(gate), sd, p + "ff.net.2") + x
+    return x
+
+
+def spatial_transformer(x, ctx, sd, p, heads):
+    """SpatialTransformer.forward, ldm/modules/attention.py:325-336 (GroupNorm eps 1e-6, :85-86)."""
+    b, c, h, w = x.shape
+    x_in = x
+    x = group_norm(x, sd, p + "norm", 32, eps=1e-6)
+    x = conv(x, sd, p + "proj_in")
+    x = x.permute(0, 2, 3, 1).reshape(b, h * w, c)
+    x = transformer_block(x, ctx, sd, p + "transformer_blocks.0.", heads)
+    x = x.reshape(b, h, w, c).permute(0, 3, 1, 2)
+    x = conv(x, sd, p + "proj_out")
+    return x + x_in
+
+
+def depth_transformer(x, context, sd, p, heads=4):
+    """DepthTransformer._forward + DepthAttention.forward, ldm/models/diffusion/attention.py:78-84,26-47."""
+    x_in = x
+    x = F.silu(group_norm(conv(x, sd, p + "proj_in.0"), sd, p + "proj_in.1", 8))
+    context = F.relu(group_norm(conv(context, sd, p + "proj_context.0"), sd, p + "proj_context.1", 8))
+    q = conv(x, sd, p + "depth_attn.to_q")
+    k = conv(context, sd, p + "depth_attn.to_k")
+    v = conv(context, sd, p + "depth_attn.to_v")
+    b, inner, h, w = q.shape
+    d = context.shape[2]
+    hd = inner // heads
+    q = q.reshape(b, heads, hd, h, w)
+    k = k.reshape(b, heads, hd, d, h, w)
+    v = v.reshape(b, heads, hd, d, h, w)
+    sim = (q.unsqueeze(3) * k).sum(2) * (hd ** -0.5)
+    attn = sim.softmax(dim=2)
+    out = (v * attn.unsqueeze(2)).sum(3).reshape(b, inner, h, w)
+    x = conv(out, sd, p + "depth_attn.to_out")
+    y = conv(F.relu(group_norm(x, sd, p + "proj_out.0", 8)), sd, p + "proj_out.2", padding=1)
+    y = conv(F.relu(group_norm(y, sd, p + "proj_out.3", 8)), sd, p + "proj_out.5", padding=1)
+    return y + x_in
+
+
+class UNetSpec:
+    """Topology of DepthWiseAttention ⊂ UNetModel as built from configs/facescape.yaml:26-42
+    (openaimodel.py:537-721, ldm/models/diffusion/attention.py:87-115)."""
+
+    def __init__(self, model_channels=320, channel_mult=(1, 2, 4, 4), num_res_blocks=2,
+                 attention_resolutions=(4, 2, 1), num_heads=8, in_channels=8, out_channels=4):
+        self.model_channels = model_channels
+        self.num_heads = num_heads
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        # input blocks: list of (kind, ...) per TimestepEmbedSequential
+        self.input_blocks = [[("conv",)]]
+        ds = 1
+        for level, mult in enumerate(channel_mult):
+            for _ in range(num_res_blocks):
+                layers = [("res",)]
+                if ds in attention_resolutions:
+                    layers.append(("st",))
+                self.input_blocks.append(layers)
+            if level != len(channel_mult) - 1:
+                self.input_blocks.append([("down",)])
+                ds *= 2
+        self.output_blocks = []
+        for level, mult in list(enumerate(channel_mult))[::-1]:
+            for i in range(num_res_blocks + 1):
+                layers = [("res",)]
+                if ds in attention_resolutions:
+                    layers.append(("st",))
+                if level and i == num_res_blocks:
+                    layers.append(("up",))
+                    ds //= 2
+                self.output_blocks.append(layers)
+        self.output_b2c = {3: 0, 4: 1, 5: 2, 6: 3, 7: 4, 8: 5, 9: 6, 10: 7, 11: 8}
+
+
+def unet_forward(sd, x, timesteps, context, source_dict, spec=None, prefix=""):
+    """DepthWiseAttention.forward, ldm/models/diffusion/attention.py:117-138."""
+    spec = spec or UNetSpec()
+    P = prefix
+    emb = timestep_embedding(timesteps, spec.model_channels)
+    emb = linear(F.silu(linear(emb, sd, P + "time_embed.0")), sd, P + "time_embed.2")
+    heads = spec.num_heads
+
+    def run_block(h, layers, p):
+        for li, layer in enumerate(layers):
+            lp = f"{p}{li}."
+            if layer[0] == "conv":
+                h = conv(h, sd, lp[:-1], padding=1)
+            elif layer[0] == "res":
+                h = res_block(h, emb, sd, lp)
+            elif layer[0] == "st":
+                h = spatial_transformer(h, context, sd, lp, heads)
+            elif layer[0] == "down":
+                h = conv(h, sd, lp + "op", stride=2, padding=1)  # Downsample, openaimodel.py:159-161
+            elif layer[0] == "up":
+                h = F.interpolate(h, scale_factor=2, mode="nearest")  # Upsample, openaimodel.py:110-120
+                h = conv(h, sd, lp + "conv", padding=1)
+        return h
+
+    hs = []
+    h = x.float()
+    for bi, layers in enumerate(spec.input_blocks):
+        h = run_block(h, layers, f"{P}input_blocks.{bi}.")
+        hs.append(h)
+    h = res_block(h, emb, sd, P + "middle_block.0.")
+    h = spatial_transformer(h, context, sd, P + "middle_block.1.", heads)
+    h = res_block(h, emb, sd, P + "middle_block.2.")
+    h = depth_transformer(h, source_dict[h.shape[-1]], sd, P + "middle_conditions.")
+    for bi, layers in enumerate(spec.output_blocks):
+        h = torch.cat([h, hs.pop()], dim=1)
+        h = run_block(h, layers, f"{P}output_blocks.{bi}.")
+        if bi in spec.output_b2c:
+            h = depth_transformer(h, source_dict[h.shape[-1]], sd, f"{P}output_conditions.{spec.output_b2c[bi]}.")
+    h = F.silu(group_norm(h, sd, P + "out.0", 32))
+    return conv(h, sd, P + "out.2", padding=1)
+
+
+def predict_with_unconditional_scale(sd, x, t, clip_embed, volume_feats, x_concat, scale, prefix="model.diffusion_model."):
+    """UNetWrapper.predict_with_unconditional_scale, morphable_diffusion.py:132-149."""
+    x_ = torch.cat([x, x], 0)
+    t_ = torch.cat([t, t], 0)
+    clip_ = torch.cat([clip_embed, torch.zeros_like(clip_embed)], 0)
+    v_ = {k: torch.cat([v, torch.zeros_like(v)], 0) for k, v in volume_feats.items()}
+    xc = torch.cat([x_concat, torch.zeros_like(x_concat)], 0).clone()
+    xc[:, :4] = xc[:, :4] / 0.18215
+    s, s_uc = unet_forward(sd, torch.cat([x_, xc], 1), t_, clip_, v_, prefix=prefix).chunk(2)
+    return s_uc + scale * (s - s_uc)
+
+
+# ----------------------------------------------------------------------------- conditioning nets (K1, K9)
+
+
+def noisy_target_view_encoder(sd, x, t, v, p="spatial_volume.target_encoder."):
+    """NoisyTargetViewEncoder.forward + Image2DResBlockWithTV, network.py:163-207."""
+    t4 = t[:, :, None, None]
+    v4 = v[:, :, None, None]
+    x = conv(x, sd, p + "init_conv", padding=1)
+    for name in ("out_conv0.", "out_conv1.", "out_conv2."):
+        q = p + name
+        y = x + conv(t4, sd, q + "time_embed") + conv(v4, sd, q + "view_embed")
+        y = conv(F.silu(group_norm(y, sd, q + "conv.0", 8)), sd, q + "conv.2", padding=1)
+        y = conv(F.silu(group_norm(y, sd, q + "conv.3", 8)), sd, q + "conv.5", padding=1)
+        x = x + y
+    return conv(F.silu(group_norm(x, sd, p + "final_out.0", 8)), sd, p + "final_out.2", padding=1)
+
+
+def frustum_tv3d_net(sd, x, t, v, p="spatial_volume.frustum_volume_feats."):
+    """FrustumTV3DNet.forward, FrustumTVBlock, FrustumTVUpBlock — network.py:285-347."""
+    t5 = t[:, :, None, None, None]
+    v5 = v[:, :, None, None, None]
+
+    def block(h, name, stride):
+        q = p + name + "."
+        h = h + conv(t5, sd, q + "t_conv") + conv(v5, sd, q + "v_conv")
+        return conv(F.silu(group_norm(h, sd, q + "bn", 8)), sd, q + "conv", stride=stride, padding=1)
+
+    def up(h, name):
+        q = p + name + "."
+        h = h + conv(t5, sd, q + "t_conv") + conv(v5, sd, q + "v_conv")
+        h = F.silu(group_norm(h, sd, q + "norm", 8))
+        return F.conv_transpose3d(h, _w(sd, q + "conv.weight"), _w(sd, q + "conv.bias"), stride=2, padding=1,
+                                  output_padding=1)
+
+    w = x.shape[-1]
+    x0 = conv(x, sd, p + "conv0", padding=1)
+    x1 = block(block(x0, "conv1", 2), "conv2", 1)
+    x2 = block(block(x1, "conv3", 2), "conv4", 1)
+    x3 = block(block(x2, "conv5", 2), "conv6", 1)
+    x2 = up(x3, "up0") + x2
+    x1 = up(x2, "up1") + x1
+    x0 = up(x1, "up2") + x0
+    return {w: x0, w // 2: x1, w // 4: x2, w // 8: x3}
+
+
+# ----------------------------------------------------------------------------- sparse conv (K5) — parity unpinned
+
+
+def _bn_relu_active(x, mask, sd, key, eps=1e-3):
+    """BatchNorm1d(eps=1e-3) in eval mode + ReLU on the active rows only (network.py:105-106,116-117)."""
+    w, b = _w(sd, key + ".weight"), _w(sd, key + ".bias")
+    rm, rv = _w(sd, key + ".running_mean"), _w(sd, key + ".running_var")
+    shp = (1, -1, 1, 1, 1)
+    y = (x - rm.view(shp)) / torch.sqrt(rv.view(shp) + eps) * w.view(shp) + b.view(shp)
+    return F.relu(y) * mask
+
+
+def _spconv_weight(sd, key):
+    # spconv 2.x stores [O, kd, kh, kw, I]; dense conv wants [O, I, kd, kh, kw]
+    return _w(sd, key + ".weight").permute(0, 4, 1, 2, 3).contiguous()
+
+
+def sparse_conv_net(sd, feats, coord, out_sh, p="spatial_volume.xyzc_net."):
+    """SparseConvTensor(feat, coord, out_sh, 1) -> SparseConvNet.forward -> .dense()
+    (morphable_diffusion.py:245-254, network.py:74-161) restated on a dense grid with spconv-2.x semantics:
+    SubMConv3d = dense conv masked to the input active set; SparseConv3d(k3,s2,p1) = dense strided conv whose
+    active set is max_pool3d(occupancy,3,2,1); BN+ReLU act on active rows only.  Duplicate voxel rows:
+    the LOWEST vertex index wins at scatter (rule fixed by this build; spconv leaves it implementation-defined).
+    feats [Nv,16], coord [Nv,3] int (d,h,w), out_sh 3 ints -> [1,64,out_sh/4...]
+    """
+    D, H, W = [int(s) for s in out_sh]
+    C = feats.shape[1]
+    grid = torch.zeros(C, D * H * W)
+    lin = (coord[:, 0].long() * H + coord[:, 1].long()) * W + coord[:, 2].long()
+    # lowest index wins: write in reverse order so the first occurrence is the last writer
+    order = torch.arange(lin.shape[0] - 1, -1, -1)
+    grid[:, lin[order]] = feats.float().t()[:, order]
+    occ = torch.zeros(D * H * W)
+    occ[lin] = 1.0
+    x = grid.view(1, C, D, H, W)
+    m = occ.view(1, 1, D, H, W)
+
+    def subm(x, m, key_conv, key_bn):
+        y = F.conv3d(x, _spconv_weight(sd, key_conv), None, padding=1) * m
+        return _bn_relu_active(y, m, sd, key_bn)
+
+    def down(x, m, key_conv, key_bn):
+        y = F.conv3d(x, _spconv_weight(sd, key_conv), None, stride=2, padding=1)
+        m2 = F.max_pool3d(m, 3, 2, 1)
+        return _bn_relu_active(y * m2, m2, sd, key_bn), m2
+
+    x = subm(x, m, p + "conv0.0", p + "conv0.1")
+    x = subm(x, m, p + "conv0.3", p + "conv0.4")
+    x, m = down(x, m, p + "down0.0", p + "down0.1")
+    x = subm(x, m, p + "conv1.0", p + "conv1.1")
+    x = subm(x, m, p + "conv1.3", p + "conv1.4")
+    x, m = down(x, m, p + "down1.0", p + "down1.1")
+    x = subm(x, m, p + "conv2.0", p + "conv2.1")
+    x = subm(x, m, p + "conv2.3", p + "conv2.4")
+    x = subm(x, m, p + "conv2.6", p + "conv2.7")
+    return x
+
+
+# ----------------------------------------------------------------------------- geometry (K2, K3, K6, K7, K8)
+
+
+def construct_project_matrix(ratio, Ks, poses, projection):
+    """ldm/models/diffusion/utils.py:46-69."""
+    n = Ks.shape[0]
+    if projection == "perspective":
+        scale = torch.diag(torch.tensor([ratio, ratio, 1.0]))
+        prj = scale[None] @ Ks[:, :3, :3] @ poses
+        pad = torch.zeros(n, 1, 4)
+        pad[:, :, 3] = 1.0
+        return torch.cat([prj, pad], 1)
+    if projection == "orthographic":
+        bottom = torch.tensor([[[0.0, 0.0, 0.0, 1.0]]]).expand(n, -1, -1)
+        return Ks @ torch.cat([poses, bottom], 1)
+    raise NotImplementedError(projection)
+
+
+def get_warp_coordinates(volume_xyz, warp_size, input_size, Ks, poses, projection):
+    """utils.py:71-76 + project_and_normalize :20-43."""
+    B, _, D, H, W = volume_xyz.shape
+    proj = construct_project_matrix(warp_size / input_size, Ks, poses, projection)
+    pts = volume_xyz.reshape(B, 3, D * H * W)
+    g = proj[:, :3, :3] @ pts + proj[:, :3, 3:]
+    if projection == "perspective":
+        z = g[:, 2:3].clone()
+        z[z < 1e-4] = 1e-4
+        g = g[:, :2] / z
+        g = g / ((warp_size - 1) / 2) - 1
+    else:
+        g = g[:, :2]
+    return g.permute(0, 2, 1).reshape(B, D, H, W, 2)
+
+
+def create_target_volume(D, size, input_size, poses, Ks, near, far, projection):
+    """utils.py:79-153. near/far: [B,1,H,W]."""
+    B = poses.shape[0]
+    H = W = size
+    depth = torch.linspace(0, 1, D).view(1, D, 1, 1) * (far - near) + near  # B,D,H,W
+    depth = depth.reshape(B, 1, D, H * W)
+    ys, xs = torch.meshgrid(torch.arange(H, dtype=torch.float32), torch.arange(W, dtype=torch.float32), indexing="ij")
+    grid = torch.stack([xs, ys], 0).reshape(1, 2, H * W).expand(B, -1, -1)  # kornia.create_meshgrid: [...,0]=x
+    ones = torch.ones(B, 1, H * W)
+    if projection == "perspective":
+        g = torch.cat([grid, ones], 1).unsqueeze(2) * depth  # B,3,D,HW
+        proj = construct_project_matrix(size / input_size, Ks, poses, projection)
+        inv = torch.inverse(proj)
+        world = inv[:, :3, :3] @ g.reshape(B, 3, D * H * W) + inv[:, :3, 3:]
+    elif projection == "orthographic":
+        g = 2 * grid / (H - 1) - 1
+        g = torch.cat([g, ones], 1).unsqueeze(2).repeat(1, 1, D, 1)
+        Kinv = torch.inverse(Ks)
+        cam = (Kinv[:, :3, :3] @ g.reshape(B, 3, D * H * W)).reshape(B, 3, D, H * W)
+        cam[:, 2] = depth[:, 0]
+        RT = construct_project_matrix(1, torch.eye(4).unsqueeze(0).repeat(B, 1, 1), poses, projection)
+        inv = torch.inverse(RT)
+        world = inv[:, :3, :3] @ cam.reshape(B, 3, D * H * W) + inv[:, :3, 3:]
+    else:
+        raise NotImplementedError(projection)
+    return world.reshape(B, 3, D, H, W), depth.reshape(B, 1, D, H, W)
+
+
+class VolumeCfg:
+    """SpatialVolumeNet constants, morphable_diffusion.py:152-180."""
+
+    def __init__(self, projection="perspective", input_image_size=256, num_views=16):
+        self.V = 32
+        self.length = 0.5
+        self.frustum_length = 0.86603
+        self.D = 48
+        self.input_image_size = input_image_size
+        self.frustum_size = input_image_size // 8
+        self.projection = projection
+        self.num_views = num_views  # SMPLFeatureExtractor.num_views (hard-coded 16 in the reference, :165-167)
+
+
+def smpl_feature_extractor(sd, feats, num_views, p="spatial_volume.smpl_feature_extractor."):
+    """SMPLFeatureExtractor.forward with filter_channels=[16,16], no_residual=False (network.py:41-72):
+    one Conv1d 1x1, no activation, then the mean over views."""
+    BN_, C, Nv = feats.shape[0] * feats.shape[1], feats.shape[2], feats.shape[3]
+    y = F.conv1d(feats.reshape(BN_, C, Nv), _w(sd, p + "conv0.weight"), _w(sd, p + "conv0.bias"))
+    return y.view(-1, num_views, y.shape[1], Nv).mean(dim=1)
+
+
+def spatial_volume_verts(V, length, B):
+    """morphable_diffusion.py:197-200: voxel centres, channel order (x,y,z) over a (z,y,x)-indexed grid."""
+    lin = torch.linspace(-length, length, V)
+    g = torch.stack(torch.meshgrid(lin, lin, lin, indexing="ij"), -1)
+    g = g.reshape(1, V ** 3, 3)[:, :, (2, 1, 0)]
+    return g.view(1, V, V, V, 3).permute(0, 4, 1, 2, 3).repeat(B, 1, 1, 1, 1)
+
+
+def construct_spatial_volume(sd, cfg, x, t_embed, v_embed, batch, return_parts=False):
+    """SpatialVolumeNet.construct_spatial_volume, morphable_diffusion.py:182-263 (use_spatial_volume=False)."""
+    B, N, _, H, W = x.shape
+    V = cfg.V
+    verts = spatial_volume_verts(V, cfg.length, B)
+    Ks, poses = batch["target_K"], batch["target_RT"]
+    per_view = []
+    for ni in range(N):
+        x_ = noisy_target_view_encoder(sd, x[:, ni], t_embed, v_embed[:, ni])
+        C = x_.shape[1]
+        coords = get_warp_coordinates(verts, x_.shape[-1], cfg.input_image_size, Ks[:, ni], poses[:, ni],
+                                      cfg.projection).view(B, V, V * V, 2)
+        un = F.grid_sample(x_, coords, mode="bilinear", padding_mode="zeros", align_corners=True)
+        per_view.append(un.view(B, C, V, V, V))
+    feats = torch.stack(per_view, 1)  # B,N,C,V,V,V
+    Nv = batch["vertices"].shape[1]
+    grid = (batch["vertices"] / cfg.length)[:, None, :, None, None, :].repeat(1, N, 1, 1, 1, 1).reshape(B * N, Nv, 1, 1, 3)
+    vert_feats = F.grid_sample(feats.reshape(B * N, -1, V, V, V), grid, mode="bilinear", padding_mode="zeros",
+                               align_corners=True)[:, :, :, 0, 0].reshape(B, N, -1, Nv)
+    smpl = smpl_feature_extractor(sd, vert_feats, cfg.num_views).permute(0, 2, 1)  # B,Nv,16
+    dhw = verts.permute(0, 2, 3, 4, 1).reshape(B, V ** 3, 3)[:, :, [2, 1, 0]]
+    min_dhw = batch["bounds"][:, 0, [2, 1, 0]].unsqueeze(1)
+    dhw = (dhw - min_dhw) / torch.tensor([0.005, 0.005, 0.005]).view(1, 1, 3)
+    dhw = dhw / batch["out_sh"].unsqueeze(1) * 2 - 1
+    grid_coords = dhw[..., [2, 1, 0]].reshape(B, V, V, V, 3)
+    outs = []
+    for bi in range(B):
+        dense = sparse_conv_net(sd, smpl[bi], batch["coord"][bi].int(), batch["out_sh"][bi].int().tolist())
+        outs.append(F.grid_sample(dense, grid_coords[bi].unsqueeze(0), mode="bilinear", padding_mode="zeros",
+                                  align_corners=True)[0])
+    vol = torch.stack(outs)
+    if return_parts:
+        return vol, {"unproj": feats, "vert_feats": vert_feats, "smpl": smpl}
+    return vol
+
+
+def construct_view_frustum_volume(sd, cfg, spatial_volume, t_embed, v_embed, target_indices, batch, return_parts=False):
+    """SpatialVolumeNet.construct_view_frustum_volume, morphable_diffusion.py:265-320."""
+    B, TN = target_indices.shape
+    H = W = cfg.frustum_size
+    D, V = cfg.D, cfg.V
+    RT = batch["target_RT"]
+    cam_pos = torch.einsum("bnij,bnjk->bnik", -RT[:, :, :3, :3].permute(0, 1, 3, 2), RT[:, :, :3, 3:])[..., 0]
+    dist = torch.linalg.norm(cam_pos, dim=-1)
+    poses_ = torch.stack([RT[b][target_indices[b]] for b in range(B)]).reshape(B * TN, 3, 4)
+    Ks_ = torch.stack([batch["target_K"][b][target_indices[b]] for b in range(B)]).reshape(B * TN, 4, 4)
+    dist_ = torch.stack([dist[b][target_indices[b]] for b in range(B)]).reshape(B * TN, 1)
+    near = torch.ones(B * TN, 1, H, W) * dist_[:, :, None, None] - cfg.frustum_length
+    far = torch.ones(B * TN, 1, H, W) * dist_[:, :, None, None] + cfg.frustum_length
+    xyz, depth = create_target_volume(D, cfg.frustum_size, cfg.input_image_size, poses_, Ks_, near, far, cfg.projection)
+    g = (xyz / cfg.length).permute(0, 2, 3, 4, 1)
+    vol_ = spatial_volume.unsqueeze(1).repeat(1, TN, 1, 1, 1, 1).view(B * TN, -1, V, V, V)
+    feats = F.grid_sample(vol_, g, mode="bilinear", padding_mode="zeros", align_corners=True)
+    v_ = v_embed[torch.arange(B)[:, None], target_indices].view(B * TN, -1)
+    t_ = t_embed.unsqueeze(1).repeat(1, TN, 1).view(B * TN, -1)
+    out = frustum_tv3d_net(sd, feats, t_, v_)
+    if return_parts:
+        return out, depth, {"frustum_xyz": xyz, "frustum_in": feats}
+    return out, depth
+
+
+# ----------------------------------------------------------------------------- schedule + step (a2-a4, a11)
+
+
+def make_schedule(ddim_num_steps=50, eta=1.0, num_timesteps=1000):
+    """_init_schedule (morphable_diffusion.py:428-450), make_ddim_timesteps (diffusionmodules/util.py:46-60),
+    SyncDDIMSampler._make_schedule (:658-672)."""
+    betas = torch.linspace(0.00085 ** 0.5, 0.0120 ** 0.5, num_timesteps, dtype=torch.float32) ** 2
+    alphas_cumprod = torch.cumprod(1.0 - betas, dim=0).float()
+    c = num_timesteps // ddim_num_steps
+    ts = torch.arange(0, num_timesteps, c) + 1
+    a = alphas_cumprod[ts].double()
+    a_prev = torch.cat([alphas_cumprod[0:1], alphas_cumprod[ts[:-1]]], 0)
+    sig = eta * torch.sqrt((1 - a_prev) / (1 - a) * (1 - a / a_prev))
+    return {"timesteps": ts, "alphas": a.float(), "alphas_prev": a_prev.float(), "sigmas": sig.float(),
+            "sqrt_one_minus_alphas": torch.sqrt(1.0 - a.float()).float()}
+
+
+def get_viewpoint_embedding(batch):
+    """morphable_diffusion.py:383-397."""
+    d_e = torch.deg2rad(batch["target_elevation"]) - torch.deg2rad(batch["input_elevation"])
+    d_a = torch.deg2rad(batch["target_azimuth"]) - torch.deg2rad(batch["input_azimuth"])
+    return torch.stack([d_e, torch.sin(d_a), torch.cos(d_a), torch.zeros_like(d_a)], -1)
+
+
+def embed_time(sd, t, dim=256):
+    """morphable_diffusion.py:491-494, 452-458."""
+    e = timestep_embedding(t, dim)
+    return linear(F.silu(linear(e, sd, "time_embed.0")), sd, "time_embed.2")
+
+
+def ddim_update(sched, x, index, eps, noise=None):
+    """SyncDDIMSampler.denoise_apply_impl, morphable_diffusion.py:675-698. `noise` None <=> is_step0."""
+    a_t = sched["alphas"][index]
+    a_prev = sched["alphas_prev"][index]
+    s1m = sched["sqrt_one_minus_alphas"][index]
+    sigma = sched["sigmas"][index]
+    pred_x0 = (x - s1m * eps) / a_t.sqrt()
+    dir_xt = torch.clamp(1.0 - a_prev - sigma ** 2, min=1e-7).sqrt() * eps
+    x_prev = a_prev.sqrt() * pred_x0 + dir_xt
+    if noise is not None:
+        x_prev = x_prev + sigma * noise
+    return x_prev
+
+
+def denoise_eps(sd, cfg, x_t, x_input, clip_embed, time_steps, cfg_scale, batch, batch_view_num=4, return_parts=False):
+    """The ε-prediction half of SyncDDIMSampler.denoise_apply, morphable_diffusion.py:701-737."""
+    B, N, C, H, W = x_t.shape
+    v_embed = get_viewpoint_embedding(batch)
+    t_embed = embed_time(sd, time_steps)
+    vol = construct_spatial_volume(sd, cfg, x_t, t_embed, v_embed, batch)
+    e_t = []
+    parts = {"spatial_volume": vol}
+    for ni in range(0, N, batch_view_num):
+        xs = x_t[:, ni:ni + batch_view_num]
+        VN = xs.shape[1]
+        xs = xs.reshape(B * VN, C, H, W)
+        ts = time_steps.view(B, 1).repeat(1, VN).view(B * VN)
+        idx = torch.arange(N)[ni:ni + batch_view_num].unsqueeze(0).repeat(B, 1)
+        feats, _ = construct_view_frustum_volume(sd, cfg, vol, t_embed, v_embed, idx, batch)
+        clip_ = clip_embed.unsqueeze(1).repeat(1, VN, 1, 1).view(B * VN, 1, 768)
+        xin_ = x_input.unsqueeze(1).repeat(1, VN, 1, 1, 1).view(B * VN, 4, H, W)
+        if cfg_scale != 1.0:
+            e = predict_with_unconditional_scale(sd, xs, ts, clip_, feats, xin_, cfg_scale)
+        else:
+            xc = xin_.clone()
+            xc[:, :4] = xc[:, :4] / 0.18215
+            e = unet_forward(sd, torch.cat([xs, xc], 1), ts, clip_, feats, prefix="model.diffusion_model.")
+        e_t.append(e.view(B, VN, 4, H, W))
+    eps = torch.cat(e_t, 1)
+    if return_parts:
+        return eps, parts
+    return eps
+
+
+def denoise_apply(sd, cfg, sched, x_t, x_input, clip_embed, time_steps, index, cfg_scale, batch, noise=None,
+                  batch_view_num=4):
+    """SyncDDIMSampler.denoise_apply, morphable_diffusion.py:701-739 (noise supplied by the caller)."""
+    eps = denoise_eps(sd, cfg, x_t, x_input, clip_embed, time_steps, cfg_scale, batch, batch_view_num)
+    return ddim_update(sched, x_t, index, eps, noise)
+
+
+def voxelize(vertices):
+    """CPU voxelisation rule, generate_face.py:214-225 == ldm/data/facescape.py:165-175.
+    vertices [Nv,3] f32 -> coord [Nv,3] i32 (d,h,w), out_sh [3] i32, bounds [2,3] f32."""
+    min_xyz = torch.min(vertices, dim=0).values
+    max_xyz = torch.max(vertices, dim=0).values
+    bounds = torch.stack([min_xyz, max_xyz], 0)
+    dhw = vertices[:, [2, 1, 0]]
+    min_dhw = min_xyz[[2, 1, 0]]
+    max_dhw = max_xyz[[2, 1, 0]]
+    voxel = torch.tensor([0.005, 0.005, 0.005])
+    coord = torch.round((dhw - min_dhw) / voxel).int()
+    out_sh = torch.ceil((max_dhw - min_dhw) / voxel).int()
+    out_sh = (out_sh | 3) + 1
+    return coord, out_sh, bounds
