@@ -62,6 +62,85 @@ typedef struct md_conv_gemm_args {
 
 MD_API int md_op_conv_gemm(const md_conv_gemm_args* args, void* stream);
 
+
+/* ------------------------------------------------------------------ model context
+ * One context per GPU / rank.  It owns the packed weights, the workspace arena and the per-sample binding.
+ * Replaces the Python objects SyncMultiviewDiffusion / SpatialVolumeNet / UNetWrapper / DepthWiseAttention
+ * (ldm/models/diffusion/morphable_diffusion.py:67-151,322-359; ldm/models/diffusion/attention.py:87-138). */
+typedef struct md_ctx md_ctx;
+
+typedef struct md_config {
+  /* DepthWiseAttention / UNetModel arguments (configs/facescape.yaml:26-42) */
+  int model_channels, in_channels, out_channels, num_res_blocks, num_heads, context_dim;
+  int channel_mult[4];
+  int attn_ds[4];       /* attention at downsample rate 1,2,4,8 (attention_resolutions) */
+  int volume_dims[4];
+  /* SpatialVolumeNet constants (morphable_diffusion.py:152-180) */
+  int latent_size, image_size, spatial_volume_size, frustum_depth, time_embed_dim, view_dim;
+  float spatial_volume_length, frustum_volume_length;
+  int smpl_num_views;   /* SMPLFeatureExtractor.num_views; 0 = number of bound views (reference hard-codes 16) */
+  /* DDIM sampler (SyncDDIMSampler.__init__, morphable_diffusion.py:649-672) */
+  int ddim_steps;
+  float ddim_eta;
+  /* runtime */
+  int max_views_per_call;          /* UNet batch = 2 x this with CFG; 0 = 16 */
+  unsigned long long workspace_bytes; /* 0 = sized from max_views_per_call */
+} md_config;
+
+MD_API void md_default_config(md_config* cfg);
+MD_API int md_create(md_ctx** out, const md_config* cfg);
+MD_API void md_destroy(md_ctx* ctx);
+MD_API unsigned long long md_workspace_peak(md_ctx* ctx);
+
+/* load_state_dict (generate_face.py:75-76): n named fp32 DEVICE tensors keyed by the reference's nn.Module paths
+ * ("model.diffusion_model.input_blocks.1.0.in_layers.2.weight", "spatial_volume.xyzc_net.conv0.0.weight", ...).
+ * Torch layouts (Conv [O,I,k..], ConvTranspose3d [I,O,k,k,k], Linear [O,I], spconv [O,kd,kh,kw,I]).  The tensors
+ * are only read during the call; keys the hot path does not use are ignored (strict=False). */
+MD_API int md_load_weights(md_ctx* ctx, int n, const char* const* names, const void* const* ptrs,
+                           const long long* numels, void* stream);
+
+/* Step invariants of one sample: the `batch` dict of generate_face.py:227-241.  ALL POINTERS HERE ARE HOST
+ * pointers (camera/mesh metadata; copied).  K [n_views][4][4], RT [n_views][3][4] world->cam,
+ * v_embed [n_views][4] (get_viewpoint_embedding, morphable_diffusion.py:383-397), vertices [nv][3],
+ * coord [nv][3] int32 (d,h,w), out_sh [3], bounds [2][3].  This rank owns views [view0, view0+n_local).
+ * projection: 0 perspective, 1 orthographic (utils.py:20-69; anything else -> error like NotImplementedError). */
+MD_API int md_bind_sample(md_ctx* ctx, const float* K, const float* RT, const float* v_embed, const float* vertices,
+                          const int32_t* coord, const int32_t* out_sh, const float* bounds, int nv, int n_views,
+                          int view0, int n_local, int projection, void* stream);
+
+/* Voxelisation rule of generate_face.py:214-225 on the GPU (device pointers): coord [nv][3] i32, out_sh [3] i32,
+ * bounds [2][3] f32.  Bit-exact with torch.round((v[:, [2,1,0]] - min) / 0.005).int(). */
+MD_API int md_voxelize(const float* vertices, int nv, int32_t* coord, int32_t* out_sh, float* bounds, void* stream);
+
+/* SpatialVolumeNet.construct_spatial_volume (morphable_diffusion.py:182-263) for the bound sample.
+ * x_local [n_local][4][S][S] fp32; volume_out [64][V][V][V] fp32 (NCDHW, B = 1). With a communicator set
+ * (md_comm_init) the per-view vertex features are all-reduced over ranks inside this call. */
+MD_API int md_spatial_volume(md_ctx* ctx, const float* x_local, float timestep, float* volume_out, void* stream);
+
+/* SpatialVolumeNet.construct_view_frustum_volume (morphable_diffusion.py:265-320) for T local views starting at
+ * local index lv0.  volume [64][V][V][V]; out_levels[i] NCDHW fp32 [T][C_i][D/2^i][S/2^i][S/2^i]. */
+MD_API int md_frustum_feats(md_ctx* ctx, const float* volume, int lv0, int T, float timestep,
+                            float* const out_levels[4], void* stream);
+
+/* DepthWiseAttention.forward (ldm/models/diffusion/attention.py:117-138): x [B][8][S][S], timesteps [B] (HOST
+ * floats), context [B][context_dim] (one token per sample), source[i] NCDHW fp32 frustum volumes, out [B][4][S][S]. */
+MD_API int md_unet_forward(md_ctx* ctx, const float* x, const float* timesteps_host, const float* context,
+                           const float* const source[4], int B, float* out, void* stream);
+
+/* SyncDDIMSampler.denoise_apply (morphable_diffusion.py:701-739) for the local views:
+ * x_local [n_local][4][S][S] is replaced by x_{t-1}.  x_input [4][S][S], clip_embed [context_dim].
+ * noise: optional [n_local][4][S][S] standard-normal draws; NULL -> Philox keyed by (seed, index, global view).
+ * eps_out: optional [n_local][4][S][S] CFG-combined epsilon. index = DDIM index (49 .. 0); index 0 adds no noise. */
+MD_API int md_denoise_step(md_ctx* ctx, float* x_local, const float* x_input, const float* clip_embed, int index,
+                           float cfg_scale, const float* noise, unsigned long long seed, float* eps_out,
+                           void* stream);
+MD_API int md_ddim_timestep(md_ctx* ctx, int index);  /* 1 .. 981 */
+
+/* Multi-GPU: one process per GPU; NCCL communicator created from a 128-byte unique id distributed by the host
+ * side (torch.distributed).  The only exchange per step is an all-reduce(sum) of the [nv][16] vertex features. */
+MD_API int md_comm_unique_id(void* id128);
+MD_API int md_comm_init(md_ctx* ctx, int rank, int world, const void* id128);
+
 #ifdef __cplusplus
 }
 #endif

@@ -105,3 +105,41 @@ def conv_gemm(A, Wt, *, B, D, H, W, Cin, N, taps, bias=None, rowvec=None, res_f3
     a.out_f32 = ptr(out_f32); a.out_bf16 = ptr(out_bf16)
     a.ldo = ldo; a.act = ACT[act]; a.out_scale = out_scale; a.BN = BN
     check(lib.md_op_conv_gemm(C.byref(a), cur_stream()), "md_op_conv_gemm")
+
+
+# ----------------------------------------------------------------------------- context-level API
+class MdConfig(C.Structure):
+    _fields_ = [
+        ("model_channels", C.c_int), ("in_channels", C.c_int), ("out_channels", C.c_int),
+        ("num_res_blocks", C.c_int), ("num_heads", C.c_int), ("context_dim", C.c_int),
+        ("channel_mult", C.c_int * 4), ("attn_ds", C.c_int * 4), ("volume_dims", C.c_int * 4),
+        ("latent_size", C.c_int), ("image_size", C.c_int), ("spatial_volume_size", C.c_int),
+        ("frustum_depth", C.c_int), ("time_embed_dim", C.c_int), ("view_dim", C.c_int),
+        ("spatial_volume_length", C.c_float), ("frustum_volume_length", C.c_float),
+        ("smpl_num_views", C.c_int),
+        ("ddim_steps", C.c_int), ("ddim_eta", C.c_float),
+        ("max_views_per_call", C.c_int), ("workspace_bytes", C.c_ulonglong),
+    ]
+
+
+_vp = C.c_void_p
+lib.md_default_config.argtypes = [C.POINTER(MdConfig)]
+lib.md_default_config.restype = None
+lib.md_create.argtypes = [C.POINTER(_vp), C.POINTER(MdConfig)]
+lib.md_destroy.argtypes = [_vp]
+lib.md_destroy.restype = None
+lib.md_workspace_peak.argtypes = [_vp]
+lib.md_workspace_peak.restype = C.c_ulonglong
+lib.md_load_weights.argtypes = [_vp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(_vp), C.POINTER(C.c_longlong), _vp]
+lib.md_bind_sample.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp]
+lib.md_voxelize.argtypes = [_vp, C.c_int, _vp, _vp, _vp, _vp]
+lib.md_spatial_volume.argtypes = [_vp, _vp, C.c_float, _vp, _vp]
+lib.md_frustum_feats.argtypes = [_vp, _vp, C.c_int, C.c_int, C.c_float, C.POINTER(_vp), _vp]
+lib.md_unet_forward.argtypes = [_vp, _vp, C.POINTER(C.c_float), _vp, C.POINTER(_vp), C.c_int, _vp, _vp]
+lib.md_denoise_step.argtypes = [_vp, _vp, _vp, _vp, C.c_int, C.c_float, _vp, C.c_ulonglong, _vp, _vp]
+lib.md_ddim_timestep.argtypes = [_vp, C.c_int]
+lib.md_comm_unique_id.argtypes = [_vp]
+lib.md_comm_init.argtypes = [_vp, C.c_int, C.c_int, _vp]
+for _f in ("md_create", "md_load_weights", "md_bind_sample", "md_voxelize", "md_spatial_volume", "md_frustum_feats",
+           "md_unet_forward", "md_denoise_step", "md_ddim_timestep", "md_comm_unique_id", "md_comm_init"):
+    getattr(lib, _f).restype = C.c_int

@@ -1,0 +1,282 @@
+// Attention kernels of the UNet:
+//   * self-attention of BasicTransformerBlock.attn1 (ldm/modules/attention.py:179-203): fused flash-style kernel
+//     (QK^T -> online softmax -> PV) on bf16 mma.sync tiles, head dims 40/80/160, sequences 16..4096;
+//     the [B*heads, S, S] score tensor the reference materialises never exists.
+//   * depth attention of DepthAttention.forward (ldm/models/diffusion/attention.py:26-47): per-pixel softmax over
+//     the D depth samples of a view's frustum volume; one HBM pass over K|V.
+#include "host.h"
+#include "kernels.h"
+
+namespace md {
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
+  const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(p));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void ldsm_x2(uint32_t (&r)[2], const void* p) {
+  const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(p));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(a));
+}
+__device__ __forceinline__ void ldsm_x2_trans(uint32_t (&r)[2], const void* p) {
+  const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(p));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(a));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+constexpr int kAttBQ = 64;   // queries per CTA (4 warps x 16)
+constexpr int kAttBK = 64;   // keys per tile
+
+// DHP: head dim padded to a multiple of 16.  Row stride DHP+8 keeps ldmatrix rows on distinct banks.
+template <int DHP>
+__global__ void __launch_bounds__(128)
+self_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int S, int heads, int dh,
+                      float scale_log2e) {
+  constexpr int LD = DHP + 8;
+  extern __shared__ __align__(16) uint8_t att_smem[];
+  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(att_smem);
+  __nv_bfloat16* sK = sQ + kAttBQ * LD;
+  __nv_bfloat16* sV = sK + kAttBK * LD;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * kAttBQ;
+  const int C = heads * dh;
+  const size_t row_stride = static_cast<size_t>(3) * C;
+  const __nv_bfloat16* base = qkv + static_cast<size_t>(b) * S * row_stride + h * dh;
+  const int chunks = dh / 8;          // 16-byte chunks of real data per row
+  constexpr int chunksP = DHP / 8;    // including zero padding
+
+  auto load_tile = [&](__nv_bfloat16* dst, const __nv_bfloat16* src, int r0) {
+    for (int i = threadIdx.x; i < 64 * chunksP; i += 128) {
+      const int r = i / chunksP, c = i % chunksP;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (r0 + r < S && c < chunks)
+        v = *reinterpret_cast<const uint4*>(src + static_cast<size_t>(r0 + r) * row_stride + c * 8);
+      *reinterpret_cast<uint4*>(dst + r * LD + c * 8) = v;
+    }
+  };
+  load_tile(sQ, base, q0);
+  __syncthreads();
+
+  // Q fragments stay in registers for the whole kernel
+  uint32_t qf[DHP / 16][4];
+#pragma unroll
+  for (int kk = 0; kk < DHP / 16; ++kk) {
+    const int r = warp * 16 + (lane & 15);
+    const int c = kk * 16 + (lane >> 4) * 8;
+    ldsm_x4(qf[kk], sQ + r * LD + c);
+  }
+
+  float o[DHP / 8][4];
+#pragma unroll
+  for (int i = 0; i < DHP / 8; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+
+  for (int k0 = 0; k0 < S; k0 += kAttBK) {
+    __syncthreads();
+    load_tile(sK, base + C, k0);
+    load_tile(sV, base + 2 * C, k0);
+    __syncthreads();
+
+    float s[kAttBK / 8][4];
+#pragma unroll
+    for (int j = 0; j < kAttBK / 8; ++j) {
+      s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+#pragma unroll
+      for (int kk = 0; kk < DHP / 16; ++kk) {
+        uint32_t bf[2];
+        const int r = j * 8 + (lane & 7);
+        const int c = kk * 16 + ((lane >> 3) & 1) * 8;
+        ldsm_x2(bf, sK + r * LD + c);
+        mma_bf16_16816(s[j], qf[kk], bf);
+      }
+    }
+    // mask keys beyond the sequence
+    if (k0 + kAttBK > S) {
+#pragma unroll
+      for (int j = 0; j < kAttBK / 8; ++j) {
+        const int key = k0 + j * 8 + (lane & 3) * 2;
+        if (key >= S) { s[j][0] = -INFINITY; s[j][2] = -INFINITY; }
+        if (key + 1 >= S) { s[j][1] = -INFINITY; s[j][3] = -INFINITY; }
+      }
+    }
+    float mx0 = m0, mx1 = m1;
+#pragma unroll
+    for (int j = 0; j < kAttBK / 8; ++j) {
+      mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffff, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffff, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffff, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffff, mx1, 2));
+    const float corr0 = exp2f((m0 - mx0) * scale_log2e);
+    const float corr1 = exp2f((m1 - mx1) * scale_log2e);
+    m0 = mx0; m1 = mx1;
+    l0 *= corr0; l1 *= corr1;
+#pragma unroll
+    for (int i = 0; i < DHP / 8; ++i) { o[i][0] *= corr0; o[i][1] *= corr0; o[i][2] *= corr1; o[i][3] *= corr1; }
+    const float mb0 = m0 * scale_log2e, mb1 = m1 * scale_log2e;
+    uint32_t pf[kAttBK / 16][4];
+#pragma unroll
+    for (int j = 0; j < kAttBK / 8; ++j) {
+      const float p0 = exp2f(s[j][0] * scale_log2e - mb0);
+      const float p1 = exp2f(s[j][1] * scale_log2e - mb0);
+      const float p2 = exp2f(s[j][2] * scale_log2e - mb1);
+      const float p3 = exp2f(s[j][3] * scale_log2e - mb1);
+      l0 += p0 + p1; l1 += p2 + p3;
+      pf[j >> 1][(j & 1) * 2 + 0] = pack_bf16(p0, p1);
+      pf[j >> 1][(j & 1) * 2 + 1] = pack_bf16(p2, p3);
+    }
+#pragma unroll
+    for (int kk = 0; kk < kAttBK / 16; ++kk) {
+#pragma unroll
+      for (int i = 0; i < DHP / 8; ++i) {
+        uint32_t bf[2];
+        const int r = kk * 16 + (lane & 15);
+        ldsm_x2_trans(bf, sV + r * LD + i * 8);
+        mma_bf16_16816(o[i], pf[kk], bf);
+      }
+    }
+  }
+  l0 += __shfl_xor_sync(0xffffffff, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffff, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffff, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffff, l1, 2);
+  const float inv0 = 1.f / l0, inv1 = 1.f / l1;
+  const int r0 = q0 + warp * 16 + (lane >> 2);
+  const int r1 = r0 + 8;
+  __nv_bfloat16* ob = out + static_cast<size_t>(b) * S * C + h * dh;
+#pragma unroll
+  for (int i = 0; i < DHP / 8; ++i) {
+    const int d = i * 8 + (lane & 3) * 2;
+    if (d < dh) {
+      if (r0 < S) *reinterpret_cast<uint32_t*>(ob + static_cast<size_t>(r0) * C + d) = pack_bf16(o[i][0] * inv0, o[i][1] * inv0);
+      if (r1 < S) *reinterpret_cast<uint32_t*>(ob + static_cast<size_t>(r1) * C + d) = pack_bf16(o[i][2] * inv1, o[i][3] * inv1);
+    }
+  }
+}
+
+template <int DHP>
+static int self_attention_impl(const void* qkv, void* out, int B, int S, int heads, int dh, cudaStream_t st) {
+  constexpr int LD = DHP + 8;
+  const int smem = (kAttBQ + 2 * kAttBK) * LD * 2;
+  static bool attr = false;
+  if (!attr) {
+    MD_CUDA(cudaFuncSetAttribute(self_attention_kernel<DHP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr = true;
+  }
+  dim3 grid((S + kAttBQ - 1) / kAttBQ, heads, B);
+  const float scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(dh));
+  self_attention_kernel<DHP><<<grid, 128, smem, st>>>(static_cast<const __nv_bfloat16*>(qkv),
+                                                      static_cast<__nv_bfloat16*>(out), S, heads, dh, scale_log2e);
+  return check_launch("self_attention");
+}
+
+int launch_self_attention(const void* qkv, void* out, int B, int S, int heads, int dh, cudaStream_t st) {
+  if (dh % 8) return set_error("self_attention: head dim %d must be a multiple of 8", dh);
+  if (dh <= 48) return self_attention_impl<48>(qkv, out, B, S, heads, dh, st);
+  if (dh <= 80) return self_attention_impl<80>(qkv, out, B, S, heads, dh, st);
+  if (dh <= 160) return self_attention_impl<160>(qkv, out, B, S, heads, dh, st);
+  return set_error("self_attention: head dim %d unsupported", dh);
+}
+
+// ------------------------------------------------------------------------------------------------ depth attention
+// One warp per (sample, pixel); lane l serves head l/8 with a contiguous chunk of CH = dh/8 channels.
+template <int CH>
+__global__ void depth_attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kv,
+                                       __nv_bfloat16* __restrict__ out, int B, int D, int HW, float scale_log2e) {
+  constexpr int inner = CH * 32;
+  const int lane = threadIdx.x & 31;
+  const size_t wid = (blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x) >> 5;
+  if (wid >= static_cast<size_t>(B) * HW) return;
+  const int b = static_cast<int>(wid / HW);
+  const int p = static_cast<int>(wid % HW);
+  const int c0 = lane * CH;
+
+  float qv[CH];
+  {
+    const __nv_bfloat16* qp = q + wid * inner + c0;
+#pragma unroll
+    for (int e = 0; e < CH; e += 4) {
+      const uint2 u = *reinterpret_cast<const uint2*>(qp + e);
+      const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&u.x);
+      const __nv_bfloat162 c = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+      qv[e] = __low2float(a); qv[e + 1] = __high2float(a); qv[e + 2] = __low2float(c); qv[e + 3] = __high2float(c);
+    }
+  }
+  float acc[CH];
+#pragma unroll
+  for (int e = 0; e < CH; ++e) acc[e] = 0.f;
+  float m = -INFINITY, l = 0.f;
+  const __nv_bfloat16* kvp = kv + (static_cast<size_t>(b) * D * HW + p) * (2 * inner) + c0;
+  const size_t dstride = static_cast<size_t>(HW) * 2 * inner;
+  for (int d = 0; d < D; ++d) {
+    const __nv_bfloat16* kp = kvp + d * dstride;
+    float kf[CH], vf[CH];
+#pragma unroll
+    for (int e = 0; e < CH; e += 4) {
+      const uint2 uk = *reinterpret_cast<const uint2*>(kp + e);
+      const uint2 uv = *reinterpret_cast<const uint2*>(kp + inner + e);
+      const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&uk.x);
+      const __nv_bfloat162 c = *reinterpret_cast<const __nv_bfloat162*>(&uk.y);
+      const __nv_bfloat162 a2 = *reinterpret_cast<const __nv_bfloat162*>(&uv.x);
+      const __nv_bfloat162 c2 = *reinterpret_cast<const __nv_bfloat162*>(&uv.y);
+      kf[e] = __low2float(a); kf[e + 1] = __high2float(a); kf[e + 2] = __low2float(c); kf[e + 3] = __high2float(c);
+      vf[e] = __low2float(a2); vf[e + 1] = __high2float(a2); vf[e + 2] = __low2float(c2); vf[e + 3] = __high2float(c2);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int e = 0; e < CH; ++e) s += qv[e] * kf[e];
+    s += __shfl_xor_sync(0xffffffff, s, 1);
+    s += __shfl_xor_sync(0xffffffff, s, 2);
+    s += __shfl_xor_sync(0xffffffff, s, 4);
+    const float mn = fmaxf(m, s);
+    const float corr = exp2f((m - mn) * scale_log2e);
+    const float pe = exp2f((s - mn) * scale_log2e);
+    m = mn;
+    l = l * corr + pe;
+#pragma unroll
+    for (int e = 0; e < CH; ++e) acc[e] = acc[e] * corr + pe * vf[e];
+  }
+  const float inv = 1.f / l;
+  __nv_bfloat16* op = out + wid * inner + c0;
+#pragma unroll
+  for (int e = 0; e < CH; e += 4) {
+    uint2 u;
+    u.x = pack_bf16(acc[e] * inv, acc[e + 1] * inv);
+    u.y = pack_bf16(acc[e + 2] * inv, acc[e + 3] * inv);
+    *reinterpret_cast<uint2*>(op + e) = u;
+  }
+}
+
+int launch_depth_attention(const void* q, const void* kv, void* out, int B, int D, int HW, int heads, int dh,
+                           cudaStream_t st) {
+  if (heads != 4) return set_error("depth_attention: heads=%d (DepthTransformer always uses 4)", heads);
+  const int CH = dh / 8;
+  const float scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(dh));
+  const size_t warps = static_cast<size_t>(B) * HW;
+  const unsigned blocks = static_cast<unsigned>((warps * 32 + 127) / 128);
+  const __nv_bfloat16* qq = static_cast<const __nv_bfloat16*>(q);
+  const __nv_bfloat16* kk = static_cast<const __nv_bfloat16*>(kv);
+  __nv_bfloat16* oo = static_cast<__nv_bfloat16*>(out);
+  switch (CH) {
+    case 4: depth_attention_kernel<4><<<blocks, 128, 0, st>>>(qq, kk, oo, B, D, HW, scale_log2e); break;
+    case 8: depth_attention_kernel<8><<<blocks, 128, 0, st>>>(qq, kk, oo, B, D, HW, scale_log2e); break;
+    case 16: depth_attention_kernel<16><<<blocks, 128, 0, st>>>(qq, kk, oo, B, D, HW, scale_log2e); break;
+    case 32: depth_attention_kernel<32><<<blocks, 128, 0, st>>>(qq, kk, oo, B, D, HW, scale_log2e); break;
+    default: return set_error("depth_attention: head dim %d unsupported", dh);
+  }
+  return check_launch("depth_attention");
+}
+
+}  // namespace md

@@ -10,6 +10,7 @@
 // Warp roles: warp0 = TMA producer, warp1 = MMA issuer (+TMEM alloc), warps2..5 = epilogue.
 #pragma once
 #include "ptx.cuh"
+#include "kernels.h"
 
 namespace md {
 
@@ -17,7 +18,6 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
 constexpr int kMaxTaps = 27;
 
-enum Act : int { ACT_NONE = 0, ACT_SILU = 1, ACT_RELU = 2, ACT_GEGLU = 3, ACT_GELU = 4 };
 
 struct ConvGemmParams {
   // input (A) geometry, channels-last [B][D][H][W][C]

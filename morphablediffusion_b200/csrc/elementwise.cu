@@ -1,0 +1,598 @@
+// HBM-bound helper kernels of the denoise step: GroupNorm (column statistics -> per-(sample,channel) affine ->
+// fused activation), LayerNorm, small linear layers (time/view embeddings), small-channel direct convolutions,
+// nearest upsample, stride-2 patch gather, CFG combine + DDIM update.  All activations are channels-last.
+#include "host.h"
+#include "kernels.h"
+
+namespace md {
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
+
+__device__ __forceinline__ float4 load4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 load4(const __nv_bfloat16* p) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&u.x);
+  const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+  return make_float4(__low2float(a), __high2float(a), __low2float(b), __high2float(b));
+}
+__device__ __forceinline__ void store4(__nv_bfloat16* p, float4 v) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y);
+  __nv_bfloat162 b = __floats2bfloat162_rn(v.z, v.w);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&a);
+  u.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+__device__ __forceinline__ void store4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+// ------------------------------------------------------------------------------------------------ GroupNorm
+// Stage 1: per-(sample, channel) sum and sum of squares over the rows of a channels-last tensor.  The tensor may be
+// the channel concatenation of two sources (UNet skip connections) without materialising the concat.
+template <typename T0, typename T1>
+__global__ void colstats_kernel(const T0* __restrict__ x0, int C0, const T1* __restrict__ x1, int C1,
+                                float* __restrict__ stats, int rows, int rows_per_cta, int R) {
+  extern __shared__ float sm[];
+  const int C = C0 + C1;
+  const int CQ = C >> 2;
+  const int b = blockIdx.y;
+  const int cq = threadIdx.x % CQ;
+  const int rsub = threadIdx.x / CQ;
+  const int r0 = blockIdx.x * rows_per_cta;
+  const int r1 = min(rows, r0 + rows_per_cta);
+  const int c = cq * 4;
+  float4 s = make_float4(0, 0, 0, 0), q = make_float4(0, 0, 0, 0);
+  if (rsub < R) {
+    if (c < C0) {
+      const T0* p = x0 + (static_cast<size_t>(b) * rows) * C0 + c;
+#pragma unroll 4
+      for (int r = r0 + rsub; r < r1; r += R) {
+        const float4 v = load4(p + static_cast<size_t>(r) * C0);
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        q.x += v.x * v.x; q.y += v.y * v.y; q.z += v.z * v.z; q.w += v.w * v.w;
+      }
+    } else {
+      const T1* p = x1 + (static_cast<size_t>(b) * rows) * C1 + (c - C0);
+#pragma unroll 4
+      for (int r = r0 + rsub; r < r1; r += R) {
+        const float4 v = load4(p + static_cast<size_t>(r) * C1);
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        q.x += v.x * v.x; q.y += v.y * v.y; q.z += v.z * v.z; q.w += v.w * v.w;
+      }
+    }
+  }
+  float* my = sm + threadIdx.x * 8;
+  my[0] = s.x; my[1] = s.y; my[2] = s.z; my[3] = s.w;
+  my[4] = q.x; my[5] = q.y; my[6] = q.z; my[7] = q.w;
+  __syncthreads();
+  if (rsub == 0) {
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = my[e];
+    for (int rr = 1; rr < R; ++rr) {
+      const float* o = sm + (rr * CQ + cq) * 8;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] += o[e];
+    }
+    float* st = stats + (static_cast<size_t>(b) * C + c) * 2;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      atomicAdd(st + 2 * e, acc[e]);
+      atomicAdd(st + 2 * e + 1, acc[4 + e]);
+    }
+  }
+}
+
+// Stage 2: group statistics -> per-(sample, channel) scale/shift:  y = x*scale + shift  ==  GN(x + addvec).
+__global__ void gn_finalize_kernel(const float* __restrict__ stats, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, const float* __restrict__ addvec, int addvec_ld,
+                                   float* __restrict__ ss, int C, int G, float nrows, float eps) {
+  const int b = blockIdx.x;
+  const int cpg = C / G;
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    double s1 = 0.0, s2 = 0.0;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+      const double a = stats[(static_cast<size_t>(b) * C + c) * 2];
+      const double q = stats[(static_cast<size_t>(b) * C + c) * 2 + 1];
+      const double tv = addvec ? addvec[static_cast<size_t>(b) * addvec_ld + c] : 0.0;
+      s1 += a + nrows * tv;
+      s2 += q + 2.0 * tv * a + nrows * tv * tv;
+    }
+    const double n = static_cast<double>(nrows) * cpg;
+    const double mean = s1 / n;
+    double var = s2 / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const double rstd = 1.0 / sqrt(var + static_cast<double>(eps));
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+      const double tv = addvec ? addvec[static_cast<size_t>(b) * addvec_ld + c] : 0.0;
+      const double sc = gamma[c] * rstd;
+      ss[(static_cast<size_t>(b) * C + c) * 2] = static_cast<float>(sc);
+      ss[(static_cast<size_t>(b) * C + c) * 2 + 1] = static_cast<float>(beta[c] + (tv - mean) * sc);
+    }
+  }
+}
+
+// Stage 3: y = act(x*scale + shift) -> bf16 (and optionally the raw x as bf16, used by 1x1 skip convolutions).
+template <typename T0, typename T1>
+__global__ void affine_act_kernel(const T0* __restrict__ x0, int C0, const T1* __restrict__ x1, int C1,
+                                  const float* __restrict__ ss, __nv_bfloat16* __restrict__ out,
+                                  __nv_bfloat16* __restrict__ raw, size_t total4, int rows, int act) {
+  const int C = C0 + C1;
+  const int CQ = C >> 2;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total4;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int cq = static_cast<int>(i % CQ);
+    const size_t row = i / CQ;  // global row = b*rows + r
+    const int b = static_cast<int>(row / rows);
+    const int c = cq * 4;
+    float4 v;
+    if (c < C0) v = load4(x0 + row * C0 + c);
+    else v = load4(x1 + row * C1 + (c - C0));
+    if (raw) store4(raw + row * C + c, v);
+    const float4 s01 = *reinterpret_cast<const float4*>(ss + (static_cast<size_t>(b) * C + c) * 2);
+    const float4 s23 = *reinterpret_cast<const float4*>(ss + (static_cast<size_t>(b) * C + c) * 2 + 4);
+    float4 y = make_float4(v.x * s01.x + s01.y, v.y * s01.z + s01.w, v.z * s23.x + s23.y, v.w * s23.z + s23.w);
+    if (act == ACT_SILU) {
+      y.x = silu_f(y.x); y.y = silu_f(y.y); y.z = silu_f(y.z); y.w = silu_f(y.w);
+    } else if (act == ACT_RELU) {
+      y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f);
+    }
+    store4(out + row * C + c, y);
+  }
+}
+
+template <typename T0, typename T1>
+static int group_norm_impl(const GroupNormArgs& a, cudaStream_t st) {
+  const int C = a.C0 + a.C1;
+  if (C % 4 || a.C0 % 4) return set_error("group_norm: channels must be multiples of 4 (C0=%d C1=%d)", a.C0, a.C1);
+  if (C % a.groups) return set_error("group_norm: C=%d not divisible by groups=%d", C, a.groups);
+  const int CQ = C / 4;
+  if (CQ > 1024) return set_error("group_norm: C=%d too large", C);
+  int R = std::max(1, std::min(8, 256 / CQ));
+  const int threads = CQ * R;
+  MD_CUDA(cudaMemsetAsync(a.stats, 0, sizeof(float) * 2 * a.B * C, st));
+  // aim for >= 2 waves of CTAs
+  int rows_per_cta = std::max(R * 4, (a.rows * a.B + 295) / 296);
+  rows_per_cta = std::min(rows_per_cta, a.rows);
+  dim3 grid((a.rows + rows_per_cta - 1) / rows_per_cta, a.B);
+  colstats_kernel<T0, T1><<<grid, threads, threads * 8 * sizeof(float), st>>>(
+      static_cast<const T0*>(a.x0), a.C0, static_cast<const T1*>(a.x1), a.C1, a.stats, a.rows, rows_per_cta, R);
+  MD_CHECK(check_launch("colstats"));
+  gn_finalize_kernel<<<a.B, 32, 0, st>>>(a.stats, a.gamma, a.beta, a.addvec, a.addvec_ld, a.scale_shift, C, a.groups,
+                                         static_cast<float>(a.rows), a.eps);
+  MD_CHECK(check_launch("gn_finalize"));
+  const size_t total4 = static_cast<size_t>(a.B) * a.rows * CQ;
+  const int blocks = static_cast<int>(std::min<size_t>((total4 + 255) / 256, static_cast<size_t>(num_sms()) * 16));
+  affine_act_kernel<T0, T1><<<blocks, 256, 0, st>>>(static_cast<const T0*>(a.x0), a.C0,
+                                                    static_cast<const T1*>(a.x1), a.C1, a.scale_shift,
+                                                    static_cast<__nv_bfloat16*>(a.out),
+                                                    static_cast<__nv_bfloat16*>(a.raw_out), total4, a.rows, a.act);
+  return check_launch("affine_act");
+}
+
+int launch_group_norm(const GroupNormArgs& a, cudaStream_t st) {
+  if (a.C1 == 0) {
+    return a.x0_bf16 ? group_norm_impl<__nv_bfloat16, __nv_bfloat16>(a, st) : group_norm_impl<float, float>(a, st);
+  }
+  if (a.x0_bf16 != a.x1_bf16) return set_error("group_norm: mixed-dtype concat unsupported");
+  return a.x0_bf16 ? group_norm_impl<__nv_bfloat16, __nv_bfloat16>(a, st) : group_norm_impl<float, float>(a, st);
+}
+
+// ------------------------------------------------------------------------------------------------ LayerNorm
+// One warp per row.  Optional per-sample vector added first (and written back): x <- x + addvec[b].
+template <int MAXV>
+__global__ void layer_norm_kernel(float* __restrict__ x, const float* __restrict__ addvec, int addvec_ld,
+                                  const float* __restrict__ gamma, const float* __restrict__ beta,
+                                  __nv_bfloat16* __restrict__ out, size_t nrows, int rows_per_sample, int C, float eps) {
+  const int lane = threadIdx.x & 31;
+  const size_t row = (blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x) >> 5;
+  if (row >= nrows) return;
+  const int nv = C >> 7;  // float4 per lane (C multiple of 128) handled vector-wise; remainder scalar
+  float* xr = x + row * C;
+  const float* av = addvec ? addvec + (row / rows_per_sample) * addvec_ld : nullptr;
+  float4 v[MAXV];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k) {
+    const int c = (k * 32 + lane) * 4;
+    if (c < C) {
+      v[k] = load4(xr + c);
+      if (av) {
+        const float4 a4 = load4(av + c);
+        v[k].x += a4.x; v[k].y += a4.y; v[k].z += a4.z; v[k].w += a4.w;
+        store4(xr + c, v[k]);
+      }
+      s += v[k].x + v[k].y + v[k].z + v[k].w;
+    }
+  }
+  (void)nv;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffff, s, o);
+  const float mean = s / C;
+  float q = 0.f;
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k) {
+    const int c = (k * 32 + lane) * 4;
+    if (c < C) {
+      const float dx = v[k].x - mean, dy = v[k].y - mean, dz = v[k].z - mean, dw = v[k].w - mean;
+      q += dx * dx + dy * dy + dz * dz + dw * dw;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffff, q, o);
+  const float rstd = rsqrtf(q / C + eps);
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k) {
+    const int c = (k * 32 + lane) * 4;
+    if (c < C) {
+      const float4 g = load4(gamma + c), bt = load4(beta + c);
+      float4 y;
+      y.x = (v[k].x - mean) * rstd * g.x + bt.x;
+      y.y = (v[k].y - mean) * rstd * g.y + bt.y;
+      y.z = (v[k].z - mean) * rstd * g.z + bt.z;
+      y.w = (v[k].w - mean) * rstd * g.w + bt.w;
+      store4(out + row * C + c, y);
+    }
+  }
+}
+
+int launch_layer_norm(float* x, const float* addvec, int addvec_ld, const float* gamma, const float* beta,
+                      void* out_bf16, size_t nrows, int rows_per_sample, int C, float eps, cudaStream_t st) {
+  if (C % 4 || C > 1280) return set_error("layer_norm: unsupported C=%d", C);
+  const int threads = 256;
+  const size_t blocks = (nrows * 32 + threads - 1) / threads;
+  layer_norm_kernel<10><<<static_cast<unsigned>(blocks), threads, 0, st>>>(
+      x, addvec, addvec_ld, gamma, beta, static_cast<__nv_bfloat16*>(out_bf16), nrows, rows_per_sample, C, eps);
+  return check_launch("layer_norm");
+}
+
+// ------------------------------------------------------------------------------------------------ small linear
+// out[b][n] = act_out( bias[n] + sum_k act_in(x[b][k]) * W[n][k] );  one warp per output column n, all samples.
+__global__ void small_linear_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ W,
+                                    const float* __restrict__ bias, float* __restrict__ out, int ldo, int B, int K,
+                                    int N, int act_in, int act_out, int accumulate) {
+  const int lane = threadIdx.x & 31;
+  const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (n >= N) return;
+  const float* w = W + static_cast<size_t>(n) * K;
+  for (int b = 0; b < B; ++b) {
+    const float* xb = x + static_cast<size_t>(b) * ldx;
+    float acc = 0.f;
+    for (int k = lane; k < K; k += 32) {
+      float xv = xb[k];
+      if (act_in == ACT_SILU) xv = silu_f(xv);
+      acc += xv * __ldg(w + k);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffff, acc, o);
+    if (lane == 0) {
+      acc += bias ? bias[n] : 0.f;
+      if (act_out == ACT_SILU) acc = silu_f(acc);
+      float* o = out + static_cast<size_t>(b) * ldo + n;
+      *o = accumulate ? (*o + acc) : acc;
+    }
+  }
+}
+
+int launch_small_linear(const float* x, int ldx, const float* W, const float* bias, float* out, int ldo, int B, int K,
+                        int N, int act_in, int act_out, int accumulate, cudaStream_t st) {
+  const int threads = 128;
+  const int blocks = (N * 32 + threads - 1) / threads;
+  small_linear_kernel<<<blocks, threads, 0, st>>>(x, ldx, W, bias, out, ldo, B, K, N, act_in, act_out, accumulate);
+  return check_launch("small_linear");
+}
+
+// ------------------------------------------------------------------------------------------------ timestep embedding
+// [cos(t f_i), sin(t f_i)], f_i = exp(-ln(10000) i / half)   (ldm/modules/diffusionmodules/util.py:151-171)
+__global__ void timestep_embedding_kernel(const float* __restrict__ t, float* __restrict__ out, int B, int dim) {
+  const int half = dim / 2;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * half) return;
+  const int b = i / half, k = i % half;
+  const float f = expf(-logf(10000.f) * static_cast<float>(k) / static_cast<float>(half));
+  const float a = t[b] * f;
+  out[static_cast<size_t>(b) * dim + k] = cosf(a);
+  out[static_cast<size_t>(b) * dim + half + k] = sinf(a);
+}
+
+int launch_timestep_embedding(const float* t, float* out, int B, int dim, cudaStream_t st) {
+  const int n = B * (dim / 2);
+  timestep_embedding_kernel<<<(n + 127) / 128, 128, 0, st>>>(t, out, B, dim);
+  return check_launch("timestep_embedding");
+}
+
+// ------------------------------------------------------------------------------------------------ direct 3x3 conv
+// Small-channel Conv2d 3x3 pad 1 (UNet conv_in 8->320).  x fp32 NHWC, W fp32 [tap][Cin][Cout], out fp32 NHWC.
+__global__ void conv3x3_direct_kernel(const float* __restrict__ x, const float* __restrict__ W,
+                                      const float* __restrict__ bias, float* __restrict__ out, int B, int H, int Wd,
+                                      int Cin, int Cout) {
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  const size_t total = static_cast<size_t>(B) * H * Wd * Cout;
+  if (i >= total) return;
+  const int co = static_cast<int>(i % Cout);
+  size_t p = i / Cout;
+  const int xw = static_cast<int>(p % Wd); p /= Wd;
+  const int yh = static_cast<int>(p % H);
+  const int b = static_cast<int>(p / H);
+  float acc = bias ? bias[co] : 0.f;
+  for (int ky = 0; ky < 3; ++ky) {
+    const int yy = yh + ky - 1;
+    if (yy < 0 || yy >= H) continue;
+    for (int kx = 0; kx < 3; ++kx) {
+      const int xx = xw + kx - 1;
+      if (xx < 0 || xx >= Wd) continue;
+      const float* xp = x + ((static_cast<size_t>(b) * H + yy) * Wd + xx) * Cin;
+      const float* wp = W + static_cast<size_t>((ky * 3 + kx) * Cin) * Cout + co;
+      for (int ci = 0; ci < Cin; ++ci) acc += xp[ci] * __ldg(wp + static_cast<size_t>(ci) * Cout);
+    }
+  }
+  out[i] = acc;
+}
+
+int launch_conv3x3_direct(const float* x, const float* W, const float* bias, float* out, int B, int H, int Wd, int Cin,
+                          int Cout, cudaStream_t st) {
+  const size_t total = static_cast<size_t>(B) * H * Wd * Cout;
+  conv3x3_direct_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(x, W, bias, out, B, H, Wd, Cin,
+                                                                                    Cout);
+  return check_launch("conv3x3_direct");
+}
+
+// Final UNet conv (320 -> 4): bf16 NHWC activations, fp32 weights [tap][Cout<=4][Cin]; one warp per pixel.
+// Output is NCHW fp32 (the layout of the epsilon tensor at the API boundary).
+__global__ void conv3x3_out_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ W,
+                                   const float* __restrict__ bias, float* __restrict__ out, int B, int H, int Wd,
+                                   int Cin, int Cout) {
+  const int lane = threadIdx.x & 31;
+  const size_t pix = (blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x) >> 5;
+  if (pix >= static_cast<size_t>(B) * H * Wd) return;
+  const int xw = static_cast<int>(pix % Wd);
+  const int yh = static_cast<int>((pix / Wd) % H);
+  const int b = static_cast<int>(pix / (static_cast<size_t>(Wd) * H));
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int ky = 0; ky < 3; ++ky) {
+    const int yy = yh + ky - 1;
+    if (yy < 0 || yy >= H) continue;
+    for (int kx = 0; kx < 3; ++kx) {
+      const int xx = xw + kx - 1;
+      if (xx < 0 || xx >= Wd) continue;
+      const __nv_bfloat16* xp = x + ((static_cast<size_t>(b) * H + yy) * Wd + xx) * Cin;
+      const float* wp = W + static_cast<size_t>(ky * 3 + kx) * Cout * Cin;
+      for (int c = lane * 2; c < Cin; c += 64) {
+        const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(xp + c);
+        const float v0 = __low2float(v), v1 = __high2float(v);
+        for (int co = 0; co < Cout; ++co) {
+          acc[co] += v0 * __ldg(wp + co * Cin + c) + v1 * __ldg(wp + co * Cin + c + 1);
+        }
+      }
+    }
+  }
+  for (int co = 0; co < Cout; ++co) {
+    float a = acc[co];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffff, a, o);
+    if (lane == 0) out[((static_cast<size_t>(b) * Cout + co) * H + yh) * Wd + xw] = a + (bias ? bias[co] : 0.f);
+  }
+}
+
+int launch_conv3x3_out(const void* x_bf16, const float* W, const float* bias, float* out, int B, int H, int Wd, int Cin,
+                       int Cout, cudaStream_t st) {
+  if (Cout > 4 || Cin % 2) return set_error("conv3x3_out: unsupported Cout=%d Cin=%d", Cout, Cin);
+  const size_t warps = static_cast<size_t>(B) * H * Wd;
+  conv3x3_out_kernel<<<static_cast<unsigned>((warps * 32 + 255) / 256), 256, 0, st>>>(
+      static_cast<const __nv_bfloat16*>(x_bf16), W, bias, out, B, H, Wd, Cin, Cout);
+  return check_launch("conv3x3_out");
+}
+
+// ------------------------------------------------------------------------------------------------ layout helpers
+// UNet input assembly: NHWC fp32 [2T][H][W][8] from x_t (NCHW [T,4,H,W]) and x_concat (NCHW [1 or T,4,H,W]):
+// first T samples conditional (x_concat / 0.18215), last T unconditional (zeros)  (morphable_diffusion.py:132-146).
+__global__ void unet_input_kernel(const float* __restrict__ x, const float* __restrict__ xc, int xc_per_sample,
+                                  float* __restrict__ out, int T, int HW, int cfg) {
+  const int nb = cfg ? 2 * T : T;
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i >= static_cast<size_t>(nb) * HW * 8) return;
+  const int c = static_cast<int>(i % 8);
+  const int p = static_cast<int>((i / 8) % HW);
+  const int b = static_cast<int>(i / (8 * static_cast<size_t>(HW)));
+  const int t = b % T;
+  float v;
+  if (c < 4) v = x[(static_cast<size_t>(t) * 4 + c) * HW + p];
+  else if (b >= T) v = 0.f;
+  else v = xc[((xc_per_sample ? static_cast<size_t>(t) : 0) * 4 + (c - 4)) * HW + p] / 0.18215f;
+  out[i] = v;
+}
+
+int launch_unet_input(const float* x, const float* xc, int xc_per_sample, float* out, int T, int HW, int cfg,
+                      cudaStream_t st) {
+  const size_t total = static_cast<size_t>(cfg ? 2 * T : T) * HW * 8;
+  unet_input_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(x, xc, xc_per_sample, out, T, HW, cfg);
+  return check_launch("unet_input");
+}
+
+template <typename T>
+__global__ void cast_bf16_kernel(const T* __restrict__ x, __nv_bfloat16* __restrict__ out, size_t n4) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    store4(out + i * 4, load4(x + i * 4));
+}
+
+int launch_cast_bf16(const float* x, void* out, size_t n, cudaStream_t st) {
+  if (n % 4) return set_error("cast_bf16: n must be a multiple of 4");
+  const size_t n4 = n / 4;
+  const int blocks = static_cast<int>(std::min<size_t>((n4 + 255) / 256, static_cast<size_t>(num_sms()) * 16));
+  cast_bf16_kernel<float><<<blocks, 256, 0, st>>>(x, static_cast<__nv_bfloat16*>(out), n4);
+  return check_launch("cast_bf16");
+}
+
+// nearest x2 upsample (Upsample.forward, openaimodel.py:110-120): fp32 NHWC -> bf16 NHWC
+__global__ void upsample2x_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int B, int H, int W,
+                                  int C) {
+  const int CQ = C / 4;
+  const size_t total = static_cast<size_t>(B) * 2 * H * 2 * W * CQ;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int cq = static_cast<int>(i % CQ);
+    size_t p = i / CQ;
+    const int ox = static_cast<int>(p % (2 * W)); p /= (2 * W);
+    const int oy = static_cast<int>(p % (2 * H));
+    const int b = static_cast<int>(p / (2 * H));
+    const float4 v = load4(x + ((static_cast<size_t>(b) * H + oy / 2) * W + ox / 2) * C + cq * 4);
+    store4(out + i * 4, v);
+  }
+}
+
+int launch_upsample2x(const float* x, void* out, int B, int H, int W, int C, cudaStream_t st) {
+  const size_t total = static_cast<size_t>(B) * 4 * H * W * (C / 4);
+  const int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, static_cast<size_t>(num_sms()) * 16));
+  upsample2x_kernel<<<blocks, 256, 0, st>>>(x, static_cast<__nv_bfloat16*>(out), B, H, W, C);
+  return check_launch("upsample2x");
+}
+
+// Stride-2, pad-1, k=3 patch gather ("im2col") for the few strided convolutions:
+// in [B][D][H][W][C] -> out [B][OD][OH][OW][taps][C] with zero fill; 2-D uses D=OD=1 and 9 taps.
+template <typename T>
+__global__ void gather_s2_kernel(const T* __restrict__ x, __nv_bfloat16* __restrict__ out, int B, int D, int H, int W,
+                                 int C, int OD, int OH, int OW, int kd) {
+  const int CQ = C / 4;
+  const int taps = kd * 9;
+  const size_t total = static_cast<size_t>(B) * OD * OH * OW * taps * CQ;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int cq = static_cast<int>(i % CQ);
+    size_t p = i / CQ;
+    const int tap = static_cast<int>(p % taps); p /= taps;
+    const int ox = static_cast<int>(p % OW); p /= OW;
+    const int oy = static_cast<int>(p % OH); p /= OH;
+    const int oz = static_cast<int>(p % OD);
+    const int b = static_cast<int>(p / OD);
+    const int kx = tap % 3, ky = (tap / 3) % 3, kz = tap / 9;
+    const int ix = 2 * ox - 1 + kx, iy = 2 * oy - 1 + ky;
+    const int iz = (kd == 3) ? (2 * oz - 1 + kz) : oz;
+    float4 v = make_float4(0, 0, 0, 0);
+    if (ix >= 0 && ix < W && iy >= 0 && iy < H && iz >= 0 && iz < D)
+      v = load4(x + (((static_cast<size_t>(b) * D + iz) * H + iy) * W + ix) * C + cq * 4);
+    store4(out + i * 4, v);
+  }
+}
+
+int launch_gather_s2(const void* x, int x_is_bf16, void* out, int B, int D, int H, int W, int C, int kd,
+                     cudaStream_t st) {
+  const int OD = (kd == 3) ? (D + 1) / 2 : D, OH = (H + 1) / 2, OW = (W + 1) / 2;
+  const size_t total = static_cast<size_t>(B) * OD * OH * OW * kd * 9 * (C / 4);
+  const int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, static_cast<size_t>(num_sms()) * 16));
+  if (x_is_bf16)
+    gather_s2_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x),
+                                                            static_cast<__nv_bfloat16*>(out), B, D, H, W, C, OD, OH,
+                                                            OW, kd);
+  else
+    gather_s2_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(x), static_cast<__nv_bfloat16*>(out), B,
+                                                    D, H, W, C, OD, OH, OW, kd);
+  return check_launch("gather_s2");
+}
+
+// NCDHW fp32 -> channels-last bf16 (API-boundary transposition of caller-supplied frustum volumes)
+__global__ void ncdhw_to_cl_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int B, int C,
+                                        size_t S) {
+  const size_t total = static_cast<size_t>(B) * C * S;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    const size_t s = (i / C) % S;
+    const size_t b = i / (static_cast<size_t>(C) * S);
+    out[i] = __float2bfloat16(x[(b * C + c) * S + s]);
+  }
+}
+int launch_ncdhw_to_cl_bf16(const float* x, void* out, int B, int C, size_t S, cudaStream_t st) {
+  const size_t total = static_cast<size_t>(B) * C * S;
+  const int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, static_cast<size_t>(num_sms()) * 32));
+  ncdhw_to_cl_bf16_kernel<<<blocks, 256, 0, st>>>(x, static_cast<__nv_bfloat16*>(out), B, C, S);
+  return check_launch("ncdhw_to_cl_bf16");
+}
+
+// channels-last (bf16 or fp32) -> NCDHW fp32
+template <typename T>
+__global__ void cl_to_ncdhw_kernel(const T* __restrict__ x, float* __restrict__ out, int B, int C, size_t S) {
+  const size_t total = static_cast<size_t>(B) * C * S;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t s = i % S;
+    const int c = static_cast<int>((i / S) % C);
+    const size_t b = i / (static_cast<size_t>(C) * S);
+    out[i] = static_cast<float>(x[(b * S + s) * C + c]);
+  }
+}
+int launch_cl_to_ncdhw(const void* x, int x_is_bf16, float* out, int B, int C, size_t S, cudaStream_t st) {
+  const size_t total = static_cast<size_t>(B) * C * S;
+  const int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, static_cast<size_t>(num_sms()) * 32));
+  if (x_is_bf16)
+    cl_to_ncdhw_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), out, B, C, S);
+  else
+    cl_to_ncdhw_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(x), out, B, C, S);
+  return check_launch("cl_to_ncdhw");
+}
+
+// ------------------------------------------------------------------------------------------------ CFG + DDIM (K14)
+// Philox4x32-10 counter RNG + Box-Muller, keyed by (seed, step, global element index) => shard-invariant noise.
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t (&o)[4]) {
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = static_cast<uint64_t>(0xD2511F53u) * c0;
+    const uint64_t p1 = static_cast<uint64_t>(0xCD9E8D57u) * c2;
+    const uint32_t n0 = static_cast<uint32_t>(p1 >> 32) ^ c1 ^ k0;
+    const uint32_t n1 = static_cast<uint32_t>(p1);
+    const uint32_t n2 = static_cast<uint32_t>(p0 >> 32) ^ c3 ^ k1;
+    const uint32_t n3 = static_cast<uint32_t>(p0);
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  o[0] = c0; o[1] = c1; o[2] = c2; o[3] = c3;
+}
+
+// eps: [2T][4][HW] (cond then uncond) or [T][4][HW] when cfg == 0.  x: [T][4][HW] updated in place -> x_prev.
+__global__ void cfg_ddim_kernel(const float* __restrict__ eps, float* __restrict__ x, float* __restrict__ eps_out,
+                                const float* __restrict__ noise, int T, int n_per_view, int cfg, float cfg_scale,
+                                float a_t, float a_prev, float sigma, float sqrt_1m_at, int add_noise, uint64_t seed,
+                                uint32_t step, int view0, int do_update) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int total = T * n_per_view;
+  if (i >= total) return;
+  float e = eps[i];
+  if (cfg) {
+    const float e_uc = eps[total + i];
+    e = e_uc + cfg_scale * (e - e_uc);
+  }
+  if (eps_out) eps_out[i] = e;
+  if (!do_update) return;
+  const float xt = x[i];
+  const float pred_x0 = (xt - sqrt_1m_at * e) / sqrtf(a_t);
+  const float dir = sqrtf(fmaxf(1.f - a_prev - sigma * sigma, 1e-7f)) * e;
+  float xp = sqrtf(a_prev) * pred_x0 + dir;
+  if (add_noise) {
+    float z;
+    if (noise) {
+      z = noise[i];
+    } else {
+      const int view = view0 + i / n_per_view;
+      const uint32_t el = static_cast<uint32_t>(i % n_per_view);
+      uint32_t r[4];
+      philox4x32_10(el >> 1, static_cast<uint32_t>(view), step, 0u, static_cast<uint32_t>(seed),
+                    static_cast<uint32_t>(seed >> 32), r);
+      const float u1 = (static_cast<float>(r[(el & 1) * 2]) + 1.f) * 2.3283064365386963e-10f;  // (0,1]
+      const float u2 = static_cast<float>(r[(el & 1) * 2 + 1]) * 2.3283064365386963e-10f;
+      z = sqrtf(-2.f * logf(u1)) * cospif(2.f * u2);
+    }
+    xp += sigma * z;
+  }
+  x[i] = xp;
+}
+
+int launch_cfg_ddim(const float* eps, float* x, float* eps_out, const float* noise, int T, int n_per_view, int cfg,
+                    float cfg_scale, float a_t, float a_prev, float sigma, float sqrt_1m_at, int add_noise,
+                    uint64_t seed, uint32_t step, int view0, int do_update, cudaStream_t st) {
+  const int total = T * n_per_view;
+  cfg_ddim_kernel<<<(total + 255) / 256, 256, 0, st>>>(eps, x, eps_out, noise, T, n_per_view, cfg, cfg_scale, a_t,
+                                                       a_prev, sigma, sqrt_1m_at, add_noise, seed, step, view0,
+                                                       do_update);
+  return check_launch("cfg_ddim");
+}
+
+}  // namespace md

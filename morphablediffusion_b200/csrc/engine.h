@@ -1,0 +1,154 @@
+// Engine: model context, packed weights, workspace arena and the host-side orchestration of the denoise step.
+#pragma once
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "geometry.h"
+#include "host.h"
+#include "kernels.h"
+
+namespace md {
+
+typedef __nv_bfloat16 bf16;
+
+// ------------------------------------------------------------------ workspace arena (bump allocator, graph friendly)
+struct Arena {
+  char* base = nullptr;
+  size_t cap = 0, off = 0, peak = 0;
+  bool failed = false;
+  void* alloc(size_t bytes) {
+    const size_t a = (off + 255) & ~size_t(255);
+    if (a + bytes > cap) { failed = true; return nullptr; }
+    off = a + bytes;
+    if (off > peak) peak = off;
+    return base + a;
+  }
+  template <typename T> T* get(size_t n) { return static_cast<T*>(alloc(n * sizeof(T))); }
+  size_t mark() const { return off; }
+  void release(size_t m) { off = m; }
+};
+
+// ------------------------------------------------------------------ weights
+struct GemmW {           // bf16 [N][taps*K] packed for conv_gemm
+  bf16* w = nullptr;
+  const float* bias = nullptr;  // fp32 [N] or null
+  int N = 0, K = 0, taps = 1;
+};
+struct NormW { const float* g = nullptr; const float* b = nullptr; int C = 0; };
+
+struct ResW {
+  int cin = 0, cout = 0, emb_off = 0;
+  NormW n1, n2;
+  GemmW c1, c2, skip;
+  bool has_skip = false;
+};
+struct STW {
+  int C = 0, heads = 0;
+  NormW norm, ln1, ln2, ln3;
+  GemmW proj_in, qkv, o1, ff1, ff2, proj_out;
+  const float* wv2 = nullptr;  // fp32 [C][ctx]   attn2.to_v
+  const float* wo2 = nullptr;  // fp32 [C][C]     attn2.to_out.0
+  const float* bo2 = nullptr;
+};
+struct DepthW {
+  int dim = 0, inner = 0, ctx = 0, dhead = 0;
+  GemmW proj_in, proj_ctx, to_q, to_kv, to_out, conv1, conv2;
+  NormW gn_in, gn_ctx, gn_o1, gn_o2;
+};
+struct UNetLayer {
+  int kind = 0;  // 0 conv_in, 1 res, 2 st, 3 down, 4 up
+  ResW res; STW st; GemmW conv;
+};
+struct UNetW {
+  int model_channels = 320, in_channels = 8, out_channels = 4, heads = 8, ctx_dim = 768, emb_dim = 1280;
+  const float* te0_w = nullptr; const float* te0_b = nullptr; const float* te2_w = nullptr; const float* te2_b = nullptr;
+  float* emb_w = nullptr; float* emb_b = nullptr; int emb_total = 0;  // concatenated emb_layers.1 of all ResBlocks
+  float* conv_in_w = nullptr; const float* conv_in_b = nullptr;       // fp32 [tap][Cin][Cout]
+  std::vector<std::vector<UNetLayer>> input_blocks, output_blocks;
+  ResW mid0, mid2; STW mid1;
+  DepthW mid_cond; std::vector<DepthW> out_cond;
+  NormW out_norm; float* out_w = nullptr; const float* out_b = nullptr;  // fp32 [tap][Cout][Cin]
+};
+
+struct FrBlockW {   // FrustumTVBlock / FrustumTVUpBlock
+  int cin = 0, cout = 0, stride = 1; bool up = false;
+  const float* t_w = nullptr; const float* t_b = nullptr; const float* v_w = nullptr; const float* v_b = nullptr;
+  NormW gn;
+  GemmW conv;            // stride 1: 27 taps implicit; stride 2: [N][27*Cin] on gathered patches
+  GemmW upc[8];          // transposed conv: one packed weight per output parity class
+};
+struct FrustumW { GemmW conv0; FrBlockW blk[9]; };  // conv1..conv6, up0..up2
+
+struct SparseLayerW { float* w = nullptr; float* scale = nullptr; float* shift = nullptr; int cin = 0, cout = 0; };
+struct VolumeW {
+  EncWeightsHost enc;
+  const float* te0_w = nullptr; const float* te0_b = nullptr; const float* te2_w = nullptr; const float* te2_b = nullptr;
+  const float* smpl_w = nullptr; const float* smpl_b = nullptr;
+  SparseLayerW sp[9];   // conv0.0 conv0.3 down0 conv1.0 conv1.3 down1 conv2.0 conv2.3 conv2.6
+  FrustumW fr;
+};
+
+// ------------------------------------------------------------------ per-sample binding (step invariants)
+struct SampleBinding {
+  bool bound = false;
+  int n_views = 0, view0 = 0, n_local = 0, nv = 0, ortho = 0;
+  float* proj = nullptr;        // [N][12] projection rows used by the unproject (diag(r,r,1) K RT | K4 RT4)
+  float* cam = nullptr;         // [N][24] frustum back-projection
+  float* v_embed = nullptr;     // [N][4]
+  float* vertices = nullptr;    // [Nv][3]
+  float* pts = nullptr;         // [n_local][D*S*S][3]
+  int n0 = 0, n1 = 0, n2 = 0;   // active rows per sparse level
+  int32_t* row_vertex = nullptr;  // [n0]
+  int32_t* nbr[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // subm0, down0, subm1, down1, subm2
+  int32_t* rs_idx = nullptr; float* rs_w = nullptr;                  // [V^3][8]
+  std::vector<void*> owned;
+};
+
+struct Ctx {
+  md_config mcfg;
+  UNetW unet;
+  VolumeW vol;
+  bool weights_loaded = false;
+  std::vector<void*> weight_allocs;
+  Arena arena;
+  SampleBinding sb;
+  // DDIM schedule (host)
+  std::vector<float> alphas, alphas_prev, sigmas, sqrt_1m_alphas;
+  std::vector<int> timesteps;
+  // step state buffers
+  float* d_t = nullptr;  // [max B] timesteps as float
+  // multi-GPU
+  void* nccl_comm = nullptr;
+  int rank = 0, world = 1;
+  std::string err;
+};
+
+// activation tensor (channels-last) helpers
+struct TF32 { float* p; int B, H, W, C; size_t rows() const { return (size_t)B * H * W; } };
+
+// weights.cu
+struct NamedTensor { const float* ptr; std::vector<int64_t> shape; size_t numel; };
+typedef std::unordered_map<std::string, NamedTensor> TensorMap;
+int load_all_weights(Ctx& c, const TensorMap& tm, cudaStream_t st);
+void free_weights(Ctx& c);
+
+// unet.cu
+// x_in fp32 NHWC [B][H][W][8]; timesteps fp32 [B]; context fp32 [B][ctx_dim]; levels: bf16 channels-last frustum
+// volumes for the B samples {64@D,S,S ; 128 ; 256 ; 512}; eps_out fp32 NCHW [B][4][H][W].
+int unet_forward(Ctx& c, const float* x_in, const float* timesteps, const float* context, const bf16* const levels[4],
+                 int B, int S, int D, float* eps_out, cudaStream_t st);
+
+// volume.cu
+int bind_sample(Ctx& c, const float* K, const float* RT, const float* v_embed, const float* vertices,
+                const int32_t* coord, const int32_t* out_sh, const float* bounds, int nv, int n_views, int view0,
+                int n_local, int ortho, cudaStream_t st);
+void free_binding(Ctx& c);
+int embed_time(Ctx& c, const float* t_dev, float* t_embed, cudaStream_t st);  // [1] -> [256]
+int vertex_feature_sum(Ctx& c, const float* x_local, const float* t_embed, float* vsum, cudaStream_t st);
+int spatial_volume_from_vsum(Ctx& c, const float* vsum, float* vol, cudaStream_t st);
+int frustum_levels(Ctx& c, const float* vol, int lv0, int T, const float* t_embed, int alloc_samples, bf16* levels[4],
+                   cudaStream_t st);
+
+}  // namespace md

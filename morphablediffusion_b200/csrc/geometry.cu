@@ -1,0 +1,503 @@
+// Geometry group of the denoise step (HBM / latency bound):
+//   voxelize            mesh vertices -> voxel indices (generate_face.py:214-225), bit-exact integer rule
+//   target_encoder      NoisyTargetViewEncoder (network.py:163-207), one CTA per view, everything in shared memory
+//   unproject           per-view latent features -> 32^3 volume (utils.py:20-76 + grid_sample 2-D)
+//   vertex_features     fused unproject + trilinear gather at the mesh vertices, summed over views
+//   sparse_conv         rulebook gather-conv with folded BatchNorm + ReLU (network.py:74-161)
+//   volume_resample     sparse-conv output -> 32^3 world grid (morphable_diffusion.py:234-255)
+//   frustum_points      per-view ray sample points (utils.py:79-153)
+//   frustum_gather      trilinear gather of the spatial volume along the rays (morphable_diffusion.py:312-315)
+#include "host.h"
+#include "kernels.h"
+#include "geometry.h"
+
+namespace md {
+
+// ------------------------------------------------------------------------------------------------ voxelize (a1)
+__global__ void minmax_kernel(const float* __restrict__ v, int nv, float* __restrict__ bounds) {
+  __shared__ float smin[3][32], smax[3][32];
+  float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+  for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float a = v[i * 3 + k];
+      mn[k] = fminf(mn[k], a);
+      mx[k] = fmaxf(mx[k], a);
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    for (int o = 16; o; o >>= 1) {
+      mn[k] = fminf(mn[k], __shfl_xor_sync(0xffffffff, mn[k], o));
+      mx[k] = fmaxf(mx[k], __shfl_xor_sync(0xffffffff, mx[k], o));
+    }
+    if (lane == 0) { smin[k][warp] = mn[k]; smax[k][warp] = mx[k]; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    const int k = threadIdx.x;
+    float a = INFINITY, b = -INFINITY;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) { a = fminf(a, smin[k][w]); b = fmaxf(b, smax[k][w]); }
+    bounds[k] = a;
+    bounds[3 + k] = b;
+  }
+}
+
+__global__ void voxel_coord_kernel(const float* __restrict__ v, int nv, const float* __restrict__ bounds,
+                                   int32_t* __restrict__ coord, int32_t* __restrict__ out_sh) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const float voxel = 0.005f;
+  if (i < nv) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {  // output order d,h,w = z,y,x
+      const int src = 2 - k;
+      const float q = __fdiv_rn(__fsub_rn(v[i * 3 + src], bounds[src]), voxel);
+      coord[i * 3 + k] = static_cast<int32_t>(rintf(q));  // torch.round: half to even
+    }
+  }
+  if (i < 3) {
+    const int src = 2 - i;
+    const float q = __fdiv_rn(__fsub_rn(bounds[3 + src], bounds[src]), voxel);
+    out_sh[i] = (static_cast<int32_t>(ceilf(q)) | 3) + 1;
+  }
+}
+
+int launch_voxelize(const float* vertices, int nv, int32_t* coord, int32_t* out_sh, float* bounds, cudaStream_t st) {
+  minmax_kernel<<<1, 1024, 0, st>>>(vertices, nv, bounds);
+  MD_CHECK(check_launch("minmax"));
+  voxel_coord_kernel<<<(std::max(nv, 3) + 255) / 256, 256, 0, st>>>(vertices, nv, bounds, coord, out_sh);
+  return check_launch("voxel_coord");
+}
+
+// ------------------------------------------------------------------------------------------------ target encoder (K1)
+// One CTA (1024 threads = one thread per latent pixel) runs the whole 8-conv encoder of one view out of shared memory.
+struct EncSmem {
+  float tmp[16][32 * 32];    // conv input after GN+SiLU
+  float w[9 * 16 * 16];      // current conv weights [tap][ci][co]
+  float red[32][16];         // per-warp GN partials
+  float gstat[16];           // group mean (8) + rstd (8)
+  float tv[16];
+};
+
+__device__ void enc_group_stats(EncSmem& s, const float (&v)[16]) {
+  // 8 groups of 2 channels over 1024 pixels
+  float part[16];
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    part[g] = v[2 * g] + v[2 * g + 1];
+    part[8 + g] = v[2 * g] * v[2 * g] + v[2 * g + 1] * v[2 * g + 1];
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int e = 0; e < 16; ++e) {
+    float a = part[e];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffff, a, o);
+    if (lane == 0) s.red[warp][e] = a;
+  }
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    double s1 = 0.0, s2 = 0.0;
+    for (int w = 0; w < 32; ++w) { s1 += s.red[w][threadIdx.x]; s2 += s.red[w][8 + threadIdx.x]; }
+    const double n = 2048.0;
+    const double mean = s1 / n;
+    double var = s2 / n - mean * mean;
+    if (var < 0) var = 0;
+    s.gstat[threadIdx.x] = static_cast<float>(mean);
+    s.gstat[8 + threadIdx.x] = static_cast<float>(1.0 / sqrt(var + 1e-5));
+  }
+  __syncthreads();
+}
+
+// out[co] = bias[co] + sum_{tap,ci} w[tap][ci][co] * in[ci][pixel+tap]   (in = s.tmp, CIN input channels)
+template <int CIN>
+__device__ void enc_conv3x3(EncSmem& s, const float* __restrict__ gw, const float* __restrict__ gb, float (&acc)[16]) {
+  // stage weights: global layout is torch [co][ci][ky][kx]
+  for (int i = threadIdx.x; i < 9 * CIN * 16; i += blockDim.x) {
+    const int co = i % 16, ci = (i / 16) % CIN, tap = i / (16 * CIN);
+    s.w[i] = gw[(co * CIN + ci) * 9 + tap];
+  }
+  __syncthreads();
+  const int px = threadIdx.x & 31, py = threadIdx.x >> 5;
+#pragma unroll
+  for (int co = 0; co < 16; ++co) acc[co] = gb[co];
+  for (int ky = 0; ky < 3; ++ky) {
+    const int yy = py + ky - 1;
+    if (yy < 0 || yy >= 32) continue;
+    for (int kx = 0; kx < 3; ++kx) {
+      const int xx = px + kx - 1;
+      if (xx < 0 || xx >= 32) continue;
+      const float* wp = s.w + (ky * 3 + kx) * CIN * 16;
+#pragma unroll
+      for (int ci = 0; ci < CIN; ++ci) {
+        const float a = s.tmp[ci][yy * 32 + xx];
+        const float4* w4 = reinterpret_cast<const float4*>(wp + ci * 16);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 w = w4[q];
+          acc[4 * q + 0] += a * w.x; acc[4 * q + 1] += a * w.y; acc[4 * q + 2] += a * w.z; acc[4 * q + 3] += a * w.w;
+        }
+      }
+    }
+  }
+  __syncthreads();  // everyone done reading s.tmp / s.w
+}
+
+struct EncWeights {
+  const float* init_w; const float* init_b;
+  struct Res {
+    const float* te_w; const float* te_b; const float* ve_w; const float* ve_b;
+    const float* gn0_w; const float* gn0_b; const float* c0_w; const float* c0_b;
+    const float* gn1_w; const float* gn1_b; const float* c1_w; const float* c1_b;
+  } res[3];
+  const float* fgn_w; const float* fgn_b; const float* fc_w; const float* fc_b;
+};
+
+__device__ __forceinline__ float silu_g(float x) { return x / (1.f + __expf(-x)); }
+
+__global__ void __launch_bounds__(1024, 1)
+target_encoder_kernel(const float* __restrict__ x, const float* __restrict__ t_embed, const float* __restrict__ v_embed,
+                      EncWeights W, float* __restrict__ out, int tdim, int vdim) {
+  extern __shared__ __align__(16) uint8_t enc_raw[];
+  EncSmem& s = *reinterpret_cast<EncSmem*>(enc_raw);
+  const int view = blockIdx.x;
+  const int p = threadIdx.x;
+  float f[16], acc[16];
+
+  // init conv 4 -> 16
+  for (int c = 0; c < 4; ++c) s.tmp[c][p] = x[(static_cast<size_t>(view) * 4 + c) * 1024 + p];
+  __syncthreads();
+  enc_conv3x3<4>(s, W.init_w, W.init_b, f);
+
+  for (int rb = 0; rb < 3; ++rb) {
+    const EncWeights::Res& R = W.res[rb];
+    if (p < 16) {  // per-channel time/view bias (1x1 convs on a 1x1 map)
+      float a = R.te_b[p] + R.ve_b[p];
+      for (int k = 0; k < tdim; ++k) a += R.te_w[p * tdim + k] * t_embed[k];
+      for (int k = 0; k < vdim; ++k) a += R.ve_w[p * vdim + k] * v_embed[view * vdim + k];
+      s.tv[p] = a;
+    }
+    __syncthreads();
+    float y[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) y[c] = f[c] + s.tv[c];
+    enc_group_stats(s, y);
+#pragma unroll
+    for (int c = 0; c < 16; ++c)
+      s.tmp[c][p] = silu_g((y[c] - s.gstat[c >> 1]) * s.gstat[8 + (c >> 1)] * R.gn0_w[c] + R.gn0_b[c]);
+    __syncthreads();
+    enc_conv3x3<16>(s, R.c0_w, R.c0_b, acc);
+    enc_group_stats(s, acc);
+#pragma unroll
+    for (int c = 0; c < 16; ++c)
+      s.tmp[c][p] = silu_g((acc[c] - s.gstat[c >> 1]) * s.gstat[8 + (c >> 1)] * R.gn1_w[c] + R.gn1_b[c]);
+    __syncthreads();
+    enc_conv3x3<16>(s, R.c1_w, R.c1_b, acc);
+#pragma unroll
+    for (int c = 0; c < 16; ++c) f[c] += acc[c];
+  }
+  enc_group_stats(s, f);
+#pragma unroll
+  for (int c = 0; c < 16; ++c)
+    s.tmp[c][p] = silu_g((f[c] - s.gstat[c >> 1]) * s.gstat[8 + (c >> 1)] * W.fgn_w[c] + W.fgn_b[c]);
+  __syncthreads();
+  enc_conv3x3<16>(s, W.fc_w, W.fc_b, acc);
+  // channels-last output [view][pixel][16]
+  float4* o = reinterpret_cast<float4*>(out + (static_cast<size_t>(view) * 1024 + p) * 16);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) o[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+}
+
+int launch_target_encoder(const float* x, const float* t_embed, const float* v_embed, const EncWeightsHost& w,
+                          float* out, int n_views, int tdim, int vdim, cudaStream_t st) {
+  static bool attr = false;
+  const int smem = sizeof(EncSmem);
+  if (!attr) {
+    MD_CUDA(cudaFuncSetAttribute(target_encoder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr = true;
+  }
+  EncWeights W;
+  static_assert(sizeof(EncWeights) == sizeof(EncWeightsHost), "layout mismatch");
+  memcpy(&W, &w, sizeof(W));
+  target_encoder_kernel<<<n_views, 1024, smem, st>>>(x, t_embed, v_embed, W, out, tdim, vdim);
+  return check_launch("target_encoder");
+}
+
+// ------------------------------------------------------------------------------------------------ projection helpers
+// Projects a world point with the 3x4 matrix P (row-major) and returns pixel coordinates in the 32x32 feature map,
+// following utils.py:20-43 and grid_sample's align_corners=True un-normalisation.
+__device__ __forceinline__ void project_point(const float* __restrict__ P, int ortho, float wx, float wy, float wz,
+                                              int size, float& px, float& py) {
+  const float u = P[0] * wx + P[1] * wy + P[2] * wz + P[3];
+  const float v = P[4] * wx + P[5] * wy + P[6] * wz + P[7];
+  float gx, gy;
+  if (!ortho) {
+    float w = P[8] * wx + P[9] * wy + P[10] * wz + P[11];
+    if (w < 1e-4f) w = 1e-4f;
+    const float half = (size - 1) / 2.f;
+    gx = (u / w) / half - 1.f;
+    gy = (v / w) / half - 1.f;
+  } else {
+    gx = u;
+    gy = v;
+  }
+  px = ((gx + 1.f) / 2.f) * (size - 1);
+  py = ((gy + 1.f) / 2.f) * (size - 1);
+}
+
+// bilinear sample (zeros padding) of a channels-last [size][size][16] map; accumulates wgt * value into acc[4]
+// for channel quad cq.
+__device__ __forceinline__ void bilinear16_acc(const float* __restrict__ fmap, int size, float px, float py, int cq,
+                                               float wgt, float4& acc) {
+  const float fx = floorf(px), fy = floorf(py);
+  const int x0 = static_cast<int>(fx), y0 = static_cast<int>(fy);
+  const float ax = px - fx, ay = py - fy;
+#pragma unroll
+  for (int dy = 0; dy < 2; ++dy) {
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx) {
+      const int xx = x0 + dx, yy = y0 + dy;
+      if (xx < 0 || xx >= size || yy < 0 || yy >= size) continue;
+      const float w = wgt * (dx ? ax : 1.f - ax) * (dy ? ay : 1.f - ay);
+      const float4 v = *reinterpret_cast<const float4*>(fmap + (static_cast<size_t>(yy) * size + xx) * 16 + cq * 4);
+      acc.x += w * v.x; acc.y += w * v.y; acc.z += w * v.z; acc.w += w * v.w;
+    }
+  }
+}
+
+// linspace(-length, length, V)[i] exactly as torch computes it (start + i*step for the first half, end - (V-1-i)*step
+// for the second half).
+__device__ __forceinline__ float linspace_at(float length, int V, int i) {
+  const float step = (2.f * length) / static_cast<float>(V - 1);
+  return (i < V / 2) ? (-length + step * i) : (length - step * (V - 1 - i));
+}
+
+// ------------------------------------------------------------------------------------------------ unproject (K2)
+// feats [N][size*size][16] -> vol [N][V][V][V][16] (channels-last; index (d,h,w) <-> world (x=l[w], y=l[h], z=l[d]))
+__global__ void unproject_kernel(const float* __restrict__ feats, const float* __restrict__ proj, int ortho, int size,
+                                 int V, float length, float* __restrict__ vol, int n_views) {
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  const size_t total = static_cast<size_t>(n_views) * V * V * V * 4;
+  if (i >= total) return;
+  const int cq = static_cast<int>(i & 3);
+  size_t r = i >> 2;
+  const int w = static_cast<int>(r % V); r /= V;
+  const int h = static_cast<int>(r % V); r /= V;
+  const int d = static_cast<int>(r % V);
+  const int n = static_cast<int>(r / V);
+  float px, py;
+  project_point(proj + n * 12, ortho, linspace_at(length, V, w), linspace_at(length, V, h), linspace_at(length, V, d),
+                size, px, py);
+  float4 acc = make_float4(0, 0, 0, 0);
+  bilinear16_acc(feats + static_cast<size_t>(n) * size * size * 16, size, px, py, cq, 1.f, acc);
+  *reinterpret_cast<float4*>(vol + (i >> 2) * 16 + cq * 4) = acc;
+}
+
+int launch_unproject(const float* feats, const float* proj, int ortho, int size, int V, float length, float* vol,
+                     int n_views, cudaStream_t st) {
+  const size_t total = static_cast<size_t>(n_views) * V * V * V * 4;
+  unproject_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(feats, proj, ortho, size, V, length, vol,
+                                                                               n_views);
+  return check_launch("unproject");
+}
+
+// ------------------------------------------------------------------------------------------------ vertex features (K2+K3)
+// sum over the views [view0, view0+n_views) of the trilinear sample (at vertex/length) of each view's unprojected
+// volume.  The volume is never materialised: each of the 8 corner voxels is projected and bilinearly sampled on the fly.
+// out [Nv][16] (sum over views, not yet divided by N).
+__global__ void vertex_features_kernel(const float* __restrict__ feats, const float* __restrict__ proj, int ortho,
+                                       int size, int V, float length, const float* __restrict__ vertices, int nv,
+                                       int n_views, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nv * 4) return;
+  const int cq = i & 3, vi = i >> 2;
+  const float gx = vertices[vi * 3 + 0] / length, gy = vertices[vi * 3 + 1] / length, gz = vertices[vi * 3 + 2] / length;
+  const float ix = ((gx + 1.f) / 2.f) * (V - 1), iy = ((gy + 1.f) / 2.f) * (V - 1), iz = ((gz + 1.f) / 2.f) * (V - 1);
+  const float fx = floorf(ix), fy = floorf(iy), fz = floorf(iz);
+  const int x0 = static_cast<int>(fx), y0 = static_cast<int>(fy), z0 = static_cast<int>(fz);
+  const float ax = ix - fx, ay = iy - fy, az = iz - fz;
+  float4 acc = make_float4(0, 0, 0, 0);
+  for (int n = 0; n < n_views; ++n) {
+    const float* P = proj + n * 12;
+    const float* fm = feats + static_cast<size_t>(n) * size * size * 16;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const int dx = c & 1, dy = (c >> 1) & 1, dz = c >> 2;
+      const int xx = x0 + dx, yy = y0 + dy, zz = z0 + dz;
+      if (xx < 0 || xx >= V || yy < 0 || yy >= V || zz < 0 || zz >= V) continue;
+      const float w = (dx ? ax : 1.f - ax) * (dy ? ay : 1.f - ay) * (dz ? az : 1.f - az);
+      float px, py;
+      project_point(P, ortho, linspace_at(length, V, xx), linspace_at(length, V, yy), linspace_at(length, V, zz), size,
+                    px, py);
+      bilinear16_acc(fm, size, px, py, cq, w, acc);
+    }
+  }
+  *reinterpret_cast<float4*>(out + static_cast<size_t>(vi) * 16 + cq * 4) = acc;
+}
+
+int launch_vertex_features(const float* feats, const float* proj, int ortho, int size, int V, float length,
+                           const float* vertices, int nv, int n_views, float* out, cudaStream_t st) {
+  vertex_features_kernel<<<(nv * 4 + 127) / 128, 128, 0, st>>>(feats, proj, ortho, size, V, length, vertices, nv,
+                                                                n_views, out);
+  return check_launch("vertex_features");
+}
+
+// ------------------------------------------------------------------------------------------------ sparse conv (K4+K5)
+// SMPLFeatureExtractor (Conv1d 1x1 on the view-mean, network.py:41-72) fused with the scatter into voxel rows:
+// row r takes the features of its lowest-index vertex.
+__global__ void smpl_scatter_kernel(const float* __restrict__ vsum, float inv_views, const float* __restrict__ W,
+                                    const float* __restrict__ bias, const int32_t* __restrict__ row_vertex, int n_rows,
+                                    float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rows * 16) return;
+  const int co = i & 15, r = i >> 4;
+  const float* f = vsum + static_cast<size_t>(row_vertex[r]) * 16;
+  float a = 0.f;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) a += W[co * 16 + k] * (f[k] * inv_views);
+  out[i] = a + bias[co];
+}
+
+int launch_smpl_scatter(const float* vsum, float inv_views, const float* W, const float* bias,
+                        const int32_t* row_vertex, int n_rows, float* out, cudaStream_t st) {
+  smpl_scatter_kernel<<<(n_rows * 16 + 127) / 128, 128, 0, st>>>(vsum, inv_views, W, bias, row_vertex, n_rows, out);
+  return check_launch("smpl_scatter");
+}
+
+// out[r][co] = relu( scale[co] * sum_{k,ci} W[k][ci][co] * in[nbr[r][k]][ci] + shift[co] ),  nbr < 0 = inactive.
+__global__ void sparse_conv_kernel(const float* __restrict__ in, const int32_t* __restrict__ nbr,
+                                   const float* __restrict__ W, const float* __restrict__ scale,
+                                   const float* __restrict__ shift, float* __restrict__ out, int n_rows, int Cin,
+                                   int Cout) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rows * Cout) return;
+  const int co = i % Cout, r = i / Cout;
+  float acc = 0.f;
+  for (int k = 0; k < 27; ++k) {
+    const int j = nbr[r * 27 + k];
+    if (j < 0) continue;
+    const float* ip = in + static_cast<size_t>(j) * Cin;
+    const float* wp = W + static_cast<size_t>(k) * Cin * Cout + co;
+    for (int ci = 0; ci < Cin; ++ci) acc += ip[ci] * __ldg(wp + ci * Cout);
+  }
+  out[i] = fmaxf(acc * scale[co] + shift[co], 0.f);
+}
+
+int launch_sparse_conv(const float* in, const int32_t* nbr, const float* W, const float* scale, const float* shift,
+                       float* out, int n_rows, int Cin, int Cout, cudaStream_t st) {
+  if (n_rows == 0) return 0;
+  sparse_conv_kernel<<<(n_rows * Cout + 127) / 128, 128, 0, st>>>(in, nbr, W, scale, shift, out, n_rows, Cin, Cout);
+  return check_launch("sparse_conv");
+}
+
+// ------------------------------------------------------------------------------------------------ volume resample (K6)
+// vol[p][c] = sum_j w[p][j] * feat[idx[p][j]][c];  idx < 0 = empty voxel.  feat [n2][64], vol [V^3][64] fp32.
+__global__ void volume_resample_kernel(const float* __restrict__ feat, const int32_t* __restrict__ idx,
+                                       const float* __restrict__ wgt, float* __restrict__ vol, int npts) {
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i >= static_cast<size_t>(npts) * 16) return;
+  const int cq = static_cast<int>(i & 15);
+  const size_t p = i >> 4;
+  float4 acc = make_float4(0, 0, 0, 0);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int r = idx[p * 8 + j];
+    if (r < 0) continue;
+    const float w = wgt[p * 8 + j];
+    const float4 v = *reinterpret_cast<const float4*>(feat + static_cast<size_t>(r) * 64 + cq * 4);
+    acc.x += w * v.x; acc.y += w * v.y; acc.z += w * v.z; acc.w += w * v.w;
+  }
+  *reinterpret_cast<float4*>(vol + p * 64 + cq * 4) = acc;
+}
+
+int launch_volume_resample(const float* feat, const int32_t* idx, const float* wgt, float* vol, int npts,
+                           cudaStream_t st) {
+  const size_t total = static_cast<size_t>(npts) * 16;
+  volume_resample_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(feat, idx, wgt, vol, npts);
+  return check_launch("volume_resample");
+}
+
+// ------------------------------------------------------------------------------------------------ frustum points (K7)
+// pts[view][d][y][x] = world point / length (normalised grid_sample coordinate), utils.py:79-153.
+// persp: world = M * (x*dep, y*dep, dep) + t ;  ortho: world = M * (kx, ky, dep) + t with (kx,ky) = Kinv*(gx,gy,1).
+__global__ void frustum_points_kernel(const float* __restrict__ cam, int ortho, int D, int size, float length,
+                                      float frustum_len, float* __restrict__ pts, int n_views) {
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  const size_t per_view = static_cast<size_t>(D) * size * size;
+  if (i >= per_view * n_views) return;
+  const int view = static_cast<int>(i / per_view);
+  size_t r = i % per_view;
+  const int x = static_cast<int>(r % size); r /= size;
+  const int y = static_cast<int>(r % size);
+  const int d = static_cast<int>(r / size);
+  const float* c = cam + view * 24;  // M (9), t (3), dist (1), Kinv rows for ortho (6: k00 k01 k02 k10 k11 k12), pad
+  const float dist = c[12];
+  const float nearv = dist - frustum_len, farv = dist + frustum_len;
+  // torch.linspace(0,1,D)
+  const float lstep = 1.f / static_cast<float>(D - 1);
+  const float lin = (d < D / 2) ? (lstep * d) : (1.f - lstep * (D - 1 - d));
+  const float dep = lin * (farv - nearv) + nearv;
+  float a, b, cc;
+  if (!ortho) {
+    a = x * dep; b = y * dep; cc = dep;
+  } else {
+    const float gx = (2.f * x) / (size - 1) - 1.f, gy = (2.f * y) / (size - 1) - 1.f;
+    a = c[13] * gx + c[14] * gy + c[15];
+    b = c[16] * gx + c[17] * gy + c[18];
+    cc = dep;
+  }
+  const float wx = c[0] * a + c[1] * b + c[2] * cc + c[9];
+  const float wy = c[3] * a + c[4] * b + c[5] * cc + c[10];
+  const float wz = c[6] * a + c[7] * b + c[8] * cc + c[11];
+  pts[i * 3 + 0] = wx / length;
+  pts[i * 3 + 1] = wy / length;
+  pts[i * 3 + 2] = wz / length;
+}
+
+int launch_frustum_points(const float* cam, int ortho, int D, int size, float length, float frustum_len, float* pts,
+                          int n_views, cudaStream_t st) {
+  const size_t total = static_cast<size_t>(D) * size * size * n_views;
+  frustum_points_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(cam, ortho, D, size, length,
+                                                                                    frustum_len, pts, n_views);
+  return check_launch("frustum_points");
+}
+
+// ------------------------------------------------------------------------------------------------ frustum gather (K8)
+// One warp per sample point; lane = channel pair.  vol fp32 [V][V][V][64]; out bf16 [npts][64].
+__global__ void frustum_gather_kernel(const float* __restrict__ vol, const float* __restrict__ pts, int V,
+                                      __nv_bfloat16* __restrict__ out, size_t npts) {
+  const int lane = threadIdx.x & 31;
+  const size_t p = (blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x) >> 5;
+  if (p >= npts) return;
+  const float gx = pts[p * 3], gy = pts[p * 3 + 1], gz = pts[p * 3 + 2];
+  const float ix = ((gx + 1.f) / 2.f) * (V - 1), iy = ((gy + 1.f) / 2.f) * (V - 1), iz = ((gz + 1.f) / 2.f) * (V - 1);
+  const float fx = floorf(ix), fy = floorf(iy), fz = floorf(iz);
+  const float ax = ix - fx, ay = iy - fy, az = iz - fz;
+  // clamp before the int conversion so far-away points cannot overflow
+  const int x0 = static_cast<int>(fminf(fmaxf(fx, -2.f), static_cast<float>(V)));
+  const int y0 = static_cast<int>(fminf(fmaxf(fy, -2.f), static_cast<float>(V)));
+  const int z0 = static_cast<int>(fminf(fmaxf(fz, -2.f), static_cast<float>(V)));
+  float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const int dx = c & 1, dy = (c >> 1) & 1, dz = c >> 2;
+    const int xx = x0 + dx, yy = y0 + dy, zz = z0 + dz;
+    if (xx < 0 || xx >= V || yy < 0 || yy >= V || zz < 0 || zz >= V) continue;
+    const float w = (dx ? ax : 1.f - ax) * (dy ? ay : 1.f - ay) * (dz ? az : 1.f - az);
+    const float2 v = *reinterpret_cast<const float2*>(vol + ((static_cast<size_t>(zz) * V + yy) * V + xx) * 64 + lane * 2);
+    a0 += w * v.x;
+    a1 += w * v.y;
+  }
+  __nv_bfloat162 o = __floats2bfloat162_rn(a0, a1);
+  *reinterpret_cast<__nv_bfloat162*>(out + p * 64 + lane * 2) = o;
+}
+
+int launch_frustum_gather(const float* vol, const float* pts, int V, void* out_bf16, size_t npts, cudaStream_t st) {
+  const size_t threads = npts * 32;
+  frustum_gather_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, st>>>(
+      vol, pts, V, static_cast<__nv_bfloat16*>(out_bf16), npts);
+  return check_launch("frustum_gather");
+}
+
+}  // namespace md

@@ -1,0 +1,54 @@
+// Internal launcher declarations (host side) for every kernel of libmdiff.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+namespace md {
+
+enum Act : int { ACT_NONE = 0, ACT_SILU = 1, ACT_RELU = 2, ACT_GEGLU = 3, ACT_GELU = 4 };
+
+// ---- elementwise.cu
+struct GroupNormArgs {
+  const void* x0; int C0; int x0_bf16;   // first source  [B][rows][C0]
+  const void* x1; int C1; int x1_bf16;   // optional second source (channel concat), C1 = 0 if absent
+  int B, rows, groups;
+  float eps;
+  const float* gamma; const float* beta; // [C0+C1]
+  const float* addvec; int addvec_ld;    // optional per-sample vector added before normalising
+  float* stats;                          // workspace [B][C][2]
+  float* scale_shift;                    // workspace [B][C][2]
+  void* out;                             // bf16 [B][rows][C]
+  void* raw_out;                         // optional bf16 copy of the un-normalised input
+  int act;
+};
+int launch_group_norm(const GroupNormArgs& a, cudaStream_t st);
+int launch_layer_norm(float* x, const float* addvec, int addvec_ld, const float* gamma, const float* beta,
+                      void* out_bf16, size_t nrows, int rows_per_sample, int C, float eps, cudaStream_t st);
+int launch_small_linear(const float* x, int ldx, const float* W, const float* bias, float* out, int ldo, int B, int K,
+                        int N, int act_in, int act_out, int accumulate, cudaStream_t st);
+int launch_timestep_embedding(const float* t, float* out, int B, int dim, cudaStream_t st);
+int launch_conv3x3_direct(const float* x, const float* W, const float* bias, float* out, int B, int H, int Wd, int Cin,
+                          int Cout, cudaStream_t st);
+int launch_conv3x3_out(const void* x_bf16, const float* W, const float* bias, float* out, int B, int H, int Wd, int Cin,
+                       int Cout, cudaStream_t st);
+int launch_unet_input(const float* x, const float* xc, int xc_per_sample, float* out, int T, int HW, int cfg,
+                      cudaStream_t st);
+int launch_cast_bf16(const float* x, void* out, size_t n, cudaStream_t st);
+int launch_upsample2x(const float* x, void* out, int B, int H, int W, int C, cudaStream_t st);
+int launch_gather_s2(const void* x, int x_is_bf16, void* out, int B, int D, int H, int W, int C, int kd,
+                     cudaStream_t st);
+int launch_ncdhw_to_cl_bf16(const float* x, void* out, int B, int C, size_t S, cudaStream_t st);
+int launch_cl_to_ncdhw(const void* x, int x_is_bf16, float* out, int B, int C, size_t S, cudaStream_t st);
+int launch_cfg_ddim(const float* eps, float* x, float* eps_out, const float* noise, int T, int n_per_view, int cfg,
+                    float cfg_scale, float a_t, float a_prev, float sigma, float sqrt_1m_at, int add_noise,
+                    uint64_t seed, uint32_t step, int view0, int do_update, cudaStream_t st);
+
+// ---- attention.cu
+// Self-attention over tokens: qkv bf16 [B][S][3*C] (q | k | v, head h at columns h*dh), out bf16 [B][S][C].
+int launch_self_attention(const void* qkv, void* out, int B, int S, int heads, int dh, cudaStream_t st);
+// Depth attention: q bf16 [B][HW][inner], kv bf16 [B][D][HW][2*inner] (k | v), out bf16 [B][HW][inner].
+int launch_depth_attention(const void* q, const void* kv, void* out, int B, int D, int HW, int heads, int dh,
+                           cudaStream_t st);
+
+}  // namespace md

@@ -1,0 +1,356 @@
+// Context lifecycle, stage-level C ABI and the fused denoise step (SyncDDIMSampler.denoise_apply,
+// morphable_diffusion.py:701-739).
+#include "engine.h"
+
+#include <dlfcn.h>
+#include <math.h>
+
+struct md_ctx { md::Ctx c; };
+
+namespace md {
+
+// ------------------------------------------------------------------ tiny kernels local to the step
+__global__ void fill_kernel(float* p, float v, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+// context rows: first T = clip embedding, remaining (uncond) = 0   (morphable_diffusion.py:135)
+__global__ void make_context_kernel(const float* __restrict__ clip, float* __restrict__ out, int T, int B, int dim) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * dim) return;
+  out[i] = (i / dim < T) ? clip[i % dim] : 0.f;
+}
+__global__ void ncdhw_to_cl_f32_kernel(const float* __restrict__ x, float* __restrict__ out, int C, size_t S) {
+  const size_t total = static_cast<size_t>(C) * S;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    const size_t s = i / C;
+    out[i] = x[static_cast<size_t>(c) * S + s];
+  }
+}
+
+// ------------------------------------------------------------------ NCCL through dlopen (torch already loaded it)
+struct NcclApi {
+  void* h = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, /*ncclUniqueId by value*/ struct Id128, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+struct Id128 { char b[128]; };
+static NcclApi g_nccl;
+
+static int nccl_load() {
+  if (g_nccl.h) return 0;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) {
+    g_nccl.h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (g_nccl.h) break;
+  }
+  if (!g_nccl.h) return set_error("NCCL library not found (dlopen libnccl.so.2): %s", dlerror());
+  *reinterpret_cast<void**>(&g_nccl.GetUniqueId) = dlsym(g_nccl.h, "ncclGetUniqueId");
+  *reinterpret_cast<void**>(&g_nccl.CommInitRank) = dlsym(g_nccl.h, "ncclCommInitRank");
+  *reinterpret_cast<void**>(&g_nccl.AllReduce) = dlsym(g_nccl.h, "ncclAllReduce");
+  *reinterpret_cast<void**>(&g_nccl.AllGather) = dlsym(g_nccl.h, "ncclAllGather");
+  *reinterpret_cast<void**>(&g_nccl.CommDestroy) = dlsym(g_nccl.h, "ncclCommDestroy");
+  *reinterpret_cast<void**>(&g_nccl.GetErrorString) = dlsym(g_nccl.h, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce) return set_error("NCCL symbols missing");
+  return 0;
+}
+
+static void make_schedule(Ctx& c) {
+  // _init_schedule (morphable_diffusion.py:428-438) + make_ddim_timesteps + _make_schedule (:658-672)
+  const int T = 1000;
+  std::vector<float> acp(T);
+  const float s0 = sqrtf(0.00085f), s1 = sqrtf(0.0120f);
+  float prod = 1.f;
+  const float step = (s1 - s0) / static_cast<float>(T - 1);
+  for (int i = 0; i < T; ++i) {
+    const float b = (i < T / 2) ? (s0 + step * i) : (s1 - step * (T - 1 - i));
+    const float beta = b * b;
+    prod *= (1.f - beta);
+    acp[i] = prod;
+  }
+  const int n = c.mcfg.ddim_steps;
+  const int stride = T / n;
+  c.timesteps.clear(); c.alphas.clear(); c.alphas_prev.clear(); c.sigmas.clear(); c.sqrt_1m_alphas.clear();
+  for (int i = 0; i * stride < T; ++i) c.timesteps.push_back(i * stride + 1);
+  for (size_t i = 0; i < c.timesteps.size(); ++i) {
+    const double a = acp[c.timesteps[i]];
+    const double ap = (i == 0) ? acp[0] : acp[c.timesteps[i - 1]];
+    const double sig = c.mcfg.ddim_eta * sqrt((1.0 - ap) / (1.0 - a) * (1.0 - a / ap));
+    c.alphas.push_back(static_cast<float>(a));
+    c.alphas_prev.push_back(static_cast<float>(ap));
+    c.sigmas.push_back(static_cast<float>(sig));
+    c.sqrt_1m_alphas.push_back(sqrtf(1.f - static_cast<float>(a)));
+  }
+}
+
+static int ensure_ready(md_ctx* ctx, bool need_binding) {
+  if (!ctx) return set_error("null context");
+  if (!ctx->c.weights_loaded) return set_error("weights not loaded (md_load_weights)");
+  if (need_binding && !ctx->c.sb.bound) return set_error("no sample bound (md_bind_sample)");
+  ctx->c.arena.failed = false;
+  return 0;
+}
+
+// one denoise step for the local views (all chunks)
+static int denoise_step_impl(Ctx& c, float* x_local, const float* x_input, const float* clip, int index,
+                             float cfg_scale, const float* noise, unsigned long long seed, float* eps_out,
+                             int do_update, cudaStream_t st) {
+  const md_config& mc = c.mcfg;
+  const SampleBinding& sb = c.sb;
+  if (index < 0 || index >= static_cast<int>(c.timesteps.size())) return set_error("denoise_step: bad DDIM index %d", index);
+  const int S = mc.latent_size, V = mc.spatial_volume_size, D = mc.frustum_depth;
+  const int HW = S * S;
+  const float tval = static_cast<float>(c.timesteps[index]);
+  const int cfg = cfg_scale != 1.0f ? 1 : 0;
+  Arena& A = c.arena;
+  A.off = 0;
+  const int chunk = std::min(sb.n_local, mc.max_views_per_call > 0 ? mc.max_views_per_call : 16);
+  const int maxB = (cfg ? 2 : 1) * chunk;
+
+  float* d_t = A.get<float>(maxB);
+  float* t_embed = A.get<float>(mc.time_embed_dim);
+  float* vsum = A.get<float>(static_cast<size_t>(sb.nv) * 16);
+  float* vol = A.get<float>(static_cast<size_t>(V) * V * V * 64);
+  float* eps_all = A.get<float>(static_cast<size_t>(maxB) * 4 * HW);
+  float* ctxv = A.get<float>(static_cast<size_t>(maxB) * mc.context_dim);
+  float* x_in = A.get<float>(static_cast<size_t>(maxB) * HW * 8);
+  if (A.failed) return set_error("workspace exhausted (step)");
+  fill_kernel<<<(maxB + 63) / 64, 64, 0, st>>>(d_t, tval, maxB);
+  MD_CHECK(check_launch("fill"));
+  MD_CHECK(embed_time(c, d_t, t_embed, st));
+  MD_CHECK(vertex_feature_sum(c, x_local, t_embed, vsum, st));
+  if (c.world > 1) {
+    if (!c.nccl_comm) return set_error("denoise_step: world=%d but no communicator", c.world);
+    const int r = g_nccl.AllReduce(vsum, vsum, static_cast<size_t>(sb.nv) * 16, /*ncclFloat32*/ 7, /*ncclSum*/ 0,
+                                   c.nccl_comm, st);
+    if (r != 0) return set_error("ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+  }
+  MD_CHECK(spatial_volume_from_vsum(c, vsum, vol, st));
+
+  const size_t m = A.mark();
+  for (int lv0 = 0; lv0 < sb.n_local; lv0 += chunk) {
+    const int T = std::min(chunk, sb.n_local - lv0);
+    const int B = (cfg ? 2 : 1) * T;
+    bf16* levels[4];
+    MD_CHECK(frustum_levels(c, vol, lv0, T, t_embed, B, levels, st));
+    MD_CHECK(launch_unet_input(x_local + static_cast<size_t>(lv0) * 4 * HW, x_input, 0, x_in, T, HW, cfg, st));
+    make_context_kernel<<<(B * mc.context_dim + 255) / 256, 256, 0, st>>>(clip, ctxv, T, B, mc.context_dim);
+    MD_CHECK(check_launch("make_context"));
+    MD_CHECK(unet_forward(c, x_in, d_t, ctxv, levels, B, S, D, eps_all, st));
+    const int add_noise = (index != 0) ? 1 : 0;
+    MD_CHECK(launch_cfg_ddim(eps_all, x_local + static_cast<size_t>(lv0) * 4 * HW,
+                             eps_out ? eps_out + static_cast<size_t>(lv0) * 4 * HW : nullptr,
+                             noise ? noise + static_cast<size_t>(lv0) * 4 * HW : nullptr, T, 4 * HW, cfg, cfg_scale,
+                             c.alphas[index], c.alphas_prev[index], c.sigmas[index], c.sqrt_1m_alphas[index],
+                             add_noise, seed, static_cast<uint32_t>(index), sb.view0 + lv0, do_update, st));
+    A.release(m);
+  }
+  return 0;
+}
+
+}  // namespace md
+
+using namespace md;
+
+extern "C" {
+
+void md_default_config(md_config* cfg) {
+  memset(cfg, 0, sizeof(*cfg));
+  cfg->model_channels = 320; cfg->in_channels = 8; cfg->out_channels = 4; cfg->num_res_blocks = 2;
+  cfg->num_heads = 8; cfg->context_dim = 768;
+  const int cm[4] = {1, 2, 4, 4}, at[4] = {1, 1, 1, 0}, vd[4] = {64, 128, 256, 512};
+  for (int i = 0; i < 4; ++i) { cfg->channel_mult[i] = cm[i]; cfg->attn_ds[i] = at[i]; cfg->volume_dims[i] = vd[i]; }
+  cfg->latent_size = 32; cfg->image_size = 256; cfg->spatial_volume_size = 32; cfg->frustum_depth = 48;
+  cfg->time_embed_dim = 256; cfg->view_dim = 4;
+  cfg->spatial_volume_length = 0.5f; cfg->frustum_volume_length = 0.86603f;
+  cfg->smpl_num_views = 0;
+  cfg->ddim_steps = 50; cfg->ddim_eta = 1.0f;
+  cfg->max_views_per_call = 16; cfg->workspace_bytes = 0;
+}
+
+int md_create(md_ctx** out, const md_config* cfg) {
+  if (!out) return set_error("md_create: null out");
+  md_config c;
+  if (cfg) c = *cfg; else md_default_config(&c);
+  if (c.volume_dims[0] != 64) return set_error("md_create: volume_dims[0] must be 64 (spatial volume channels)");
+  if (c.latent_size % 8) return set_error("md_create: latent_size must be a multiple of 8");
+  md_ctx* ctx = new md_ctx();
+  ctx->c.mcfg = c;
+  make_schedule(ctx->c);
+  const int mv = c.max_views_per_call > 0 ? c.max_views_per_call : 16;
+  const double scale = (c.latent_size / 32.0) * (c.latent_size / 32.0);
+  size_t bytes = c.workspace_bytes ? static_cast<size_t>(c.workspace_bytes)
+                                   : static_cast<size_t>((1.0 + 0.45 * mv * scale) * (1ull << 30));
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&ctx->c.arena.base), bytes);
+  if (e != cudaSuccess) {
+    delete ctx;
+    return set_error("md_create: cudaMalloc(%zu) for the workspace failed: %s", bytes, cudaGetErrorString(e));
+  }
+  ctx->c.arena.cap = bytes;
+  *out = ctx;
+  return 0;
+}
+
+void md_destroy(md_ctx* ctx) {
+  if (!ctx) return;
+  cudaDeviceSynchronize();
+  free_binding(ctx->c);
+  free_weights(ctx->c);
+  if (ctx->c.nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->c.nccl_comm);
+  cudaFree(ctx->c.arena.base);
+  delete ctx;
+}
+
+unsigned long long md_workspace_peak(md_ctx* ctx) { return ctx ? ctx->c.arena.peak : 0; }
+
+int md_load_weights(md_ctx* ctx, int n, const char* const* names, const void* const* ptrs, const long long* numels,
+                    void* stream) {
+  if (!ctx) return set_error("null context");
+  TensorMap tm;
+  tm.reserve(static_cast<size_t>(n) * 2);
+  for (int i = 0; i < n; ++i) {
+    NamedTensor t;
+    t.ptr = static_cast<const float*>(ptrs[i]);
+    t.numel = static_cast<size_t>(numels[i]);
+    tm[names[i]] = t;
+  }
+  return load_all_weights(ctx->c, tm, static_cast<cudaStream_t>(stream));
+}
+
+int md_bind_sample(md_ctx* ctx, const float* K, const float* RT, const float* v_embed, const float* vertices,
+                   const int32_t* coord, const int32_t* out_sh, const float* bounds, int nv, int n_views, int view0,
+                   int n_local, int projection, void* stream) {
+  if (!ctx) return set_error("null context");
+  if (projection != 0 && projection != 1) return set_error("NotImplementedError: projection %d", projection);
+  return bind_sample(ctx->c, K, RT, v_embed, vertices, coord, out_sh, bounds, nv, n_views, view0, n_local, projection,
+                     static_cast<cudaStream_t>(stream));
+}
+
+int md_voxelize(const float* vertices, int nv, int32_t* coord, int32_t* out_sh, float* bounds, void* stream) {
+  return launch_voxelize(vertices, nv, coord, out_sh, bounds, static_cast<cudaStream_t>(stream));
+}
+
+int md_spatial_volume(md_ctx* ctx, const float* x_local, float timestep, float* volume_out, void* stream) {
+  MD_CHECK(ensure_ready(ctx, true));
+  Ctx& c = ctx->c;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const md_config& mc = c.mcfg;
+  const int V = mc.spatial_volume_size;
+  Arena& A = c.arena;
+  A.off = 0;
+  float* d_t = A.get<float>(1);
+  float* t_embed = A.get<float>(mc.time_embed_dim);
+  float* vsum = A.get<float>(static_cast<size_t>(c.sb.nv) * 16);
+  float* vol = A.get<float>(static_cast<size_t>(V) * V * V * 64);
+  if (A.failed) return set_error("workspace exhausted");
+  fill_kernel<<<1, 32, 0, st>>>(d_t, timestep, 1);
+  MD_CHECK(check_launch("fill"));
+  MD_CHECK(embed_time(c, d_t, t_embed, st));
+  MD_CHECK(vertex_feature_sum(c, x_local, t_embed, vsum, st));
+  if (c.world > 1 && c.nccl_comm) {
+    const int r = g_nccl.AllReduce(vsum, vsum, static_cast<size_t>(c.sb.nv) * 16, 7, 0, c.nccl_comm, st);
+    if (r != 0) return set_error("ncclAllReduce failed (%d)", r);
+  }
+  MD_CHECK(spatial_volume_from_vsum(c, vsum, vol, st));
+  return launch_cl_to_ncdhw(vol, 0, volume_out, 1, 64, static_cast<size_t>(V) * V * V, st);
+}
+
+int md_frustum_feats(md_ctx* ctx, const float* volume, int lv0, int T, float timestep, float* const out_levels[4],
+                     void* stream) {
+  MD_CHECK(ensure_ready(ctx, true));
+  Ctx& c = ctx->c;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const md_config& mc = c.mcfg;
+  const int V = mc.spatial_volume_size, S = mc.latent_size, D = mc.frustum_depth;
+  Arena& A = c.arena;
+  A.off = 0;
+  float* d_t = A.get<float>(1);
+  float* t_embed = A.get<float>(mc.time_embed_dim);
+  float* vol = A.get<float>(static_cast<size_t>(V) * V * V * 64);
+  if (A.failed) return set_error("workspace exhausted");
+  fill_kernel<<<1, 32, 0, st>>>(d_t, timestep, 1);
+  MD_CHECK(check_launch("fill"));
+  MD_CHECK(embed_time(c, d_t, t_embed, st));
+  ncdhw_to_cl_f32_kernel<<<148 * 8, 256, 0, st>>>(volume, vol, 64, static_cast<size_t>(V) * V * V);
+  MD_CHECK(check_launch("ncdhw_to_cl_f32"));
+  bf16* levels[4];
+  MD_CHECK(frustum_levels(c, vol, lv0, T, t_embed, T, levels, st));
+  for (int i = 0; i < 4; ++i) {
+    const size_t sp = static_cast<size_t>(D >> i) * (S >> i) * (S >> i);
+    MD_CHECK(launch_cl_to_ncdhw(levels[i], 1, out_levels[i], T, mc.volume_dims[i], sp, st));
+  }
+  return 0;
+}
+
+int md_unet_forward(md_ctx* ctx, const float* x, const float* timesteps_host, const float* context,
+                    const float* const source[4], int B, float* out, void* stream) {
+  MD_CHECK(ensure_ready(ctx, false));
+  Ctx& c = ctx->c;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const md_config& mc = c.mcfg;
+  const int S = mc.latent_size, D = mc.frustum_depth;
+  Arena& A = c.arena;
+  A.off = 0;
+  float* d_t = A.get<float>(B);
+  float* x_in = A.get<float>(static_cast<size_t>(B) * S * S * mc.in_channels);
+  bf16* levels[4];
+  for (int i = 0; i < 4; ++i) {
+    const size_t sp = static_cast<size_t>(D >> i) * (S >> i) * (S >> i);
+    levels[i] = A.get<bf16>(static_cast<size_t>(B) * sp * mc.volume_dims[i]);
+  }
+  if (A.failed) return set_error("workspace exhausted");
+  MD_CUDA(cudaMemcpyAsync(d_t, timesteps_host, sizeof(float) * B, cudaMemcpyHostToDevice, st));
+  for (int i = 0; i < 4; ++i) {
+    const size_t sp = static_cast<size_t>(D >> i) * (S >> i) * (S >> i);
+    MD_CHECK(launch_ncdhw_to_cl_bf16(source[i], levels[i], B, mc.volume_dims[i], sp, st));
+  }
+  // NCHW -> NHWC for the 8-channel input (same transposition kernel, fp32 variant per sample)
+  for (int b = 0; b < B; ++b) {
+    ncdhw_to_cl_f32_kernel<<<32, 256, 0, st>>>(x + static_cast<size_t>(b) * mc.in_channels * S * S,
+                                               x_in + static_cast<size_t>(b) * mc.in_channels * S * S, mc.in_channels,
+                                               static_cast<size_t>(S) * S);
+    MD_CHECK(check_launch("nchw_to_nhwc"));
+  }
+  return unet_forward(c, x_in, d_t, context, levels, B, S, D, out, st);
+}
+
+int md_denoise_step(md_ctx* ctx, float* x_local, const float* x_input, const float* clip_embed, int index,
+                    float cfg_scale, const float* noise, unsigned long long seed, float* eps_out, void* stream) {
+  MD_CHECK(ensure_ready(ctx, true));
+  return denoise_step_impl(ctx->c, x_local, x_input, clip_embed, index, cfg_scale, noise, seed, eps_out, 1,
+                           static_cast<cudaStream_t>(stream));
+}
+
+int md_ddim_timestep(md_ctx* ctx, int index) {
+  if (!ctx || index < 0 || index >= static_cast<int>(ctx->c.timesteps.size())) return -1;
+  return ctx->c.timesteps[index];
+}
+
+int md_comm_unique_id(void* id128) {
+  MD_CHECK(nccl_load());
+  const int r = g_nccl.GetUniqueId(id128);
+  return r == 0 ? 0 : set_error("ncclGetUniqueId failed (%d)", r);
+}
+
+int md_comm_init(md_ctx* ctx, int rank, int world, const void* id128) {
+  if (!ctx) return set_error("null context");
+  ctx->c.rank = rank;
+  ctx->c.world = world;
+  if (world <= 1) return 0;
+  MD_CHECK(nccl_load());
+  Id128 id;
+  memcpy(&id, id128, sizeof(id));
+  void* comm = nullptr;
+  const int r = g_nccl.CommInitRank(&comm, world, id, rank);
+  if (r != 0) return set_error("ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+  ctx->c.nccl_comm = comm;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,310 @@
+// Host orchestration of DepthWiseAttention.forward (ldm/models/diffusion/attention.py:117-138) on the kernels of
+// this library.  Layout: every activation is channels-last; the UNet residual stream `h` is fp32, GEMM operands are
+// bf16 produced by the fused GroupNorm/LayerNorm kernels.
+#include "engine.h"
+
+namespace md {
+
+namespace {
+
+struct Fwd {
+  Ctx& c;
+  cudaStream_t st;
+  int B;               // samples in this UNet call
+  const float* emb_all;  // [B][emb_total] per-ResBlock time-embedding projections
+  const float* context;  // [B][ctx_dim]
+  int rc = 0;
+
+  Arena& A() { return c.arena; }
+
+  static void taps2d(md_conv_gemm_args& a) {
+    a.ntaps = 9;
+    for (int ky = 0; ky < 3; ++ky)
+      for (int kx = 0; kx < 3; ++kx) {
+        a.tap[ky * 3 + kx][0] = kx - 1; a.tap[ky * 3 + kx][1] = ky - 1; a.tap[ky * 3 + kx][2] = 0;
+      }
+  }
+
+  // conv3x3 (pad 1) or 1x1 on a bf16 NHWC tensor
+  int conv(const bf16* a_in, int H, int W, const GemmW& w, const float* rowvec, int rowvec_ld, const float* res_f32,
+           float* out_f32, bf16* out_bf16, int act = ACT_NONE) {
+    md_conv_gemm_args a;
+    memset(&a, 0, sizeof(a));
+    a.A = a_in; a.B = B; a.D = 1; a.H = H; a.W = W; a.Cin = w.K; a.Wt = w.w; a.N = w.N;
+    if (w.taps == 9) taps2d(a);
+    else { a.ntaps = 1; }
+    a.bias = w.bias; a.rowvec = rowvec; a.rowvec_ld = rowvec_ld; a.res_f32 = res_f32;
+    a.out_f32 = out_f32; a.out_bf16 = out_bf16; a.act = act;
+    return launch_conv_gemm(a, st);
+  }
+  // plain GEMM over rows = B*H*W tokens
+  int gemm(const bf16* a_in, size_t rows_per_sample, const GemmW& w, const float* res_f32, float* out_f32, bf16* out_bf16,
+           int act = ACT_NONE) {
+    md_conv_gemm_args a;
+    memset(&a, 0, sizeof(a));
+    a.A = a_in; a.B = B; a.D = 1; a.H = 1; a.W = static_cast<int>(rows_per_sample); a.Cin = w.K; a.Wt = w.w; a.N = w.N;
+    a.ntaps = 1;
+    a.bias = w.bias; a.res_f32 = res_f32; a.out_f32 = out_f32; a.out_bf16 = out_bf16; a.act = act;
+    return launch_conv_gemm(a, st);
+  }
+
+  int gn(const void* x0, int C0, bool bf0, const void* x1, int C1, int rows, int groups, float eps, const NormW& n,
+         int act, bf16* out, bf16* raw, int Bn = -1) {
+    const int C = C0 + C1;
+    const int nb = Bn < 0 ? B : Bn;
+    GroupNormArgs g;
+    memset(&g, 0, sizeof(g));
+    g.x0 = x0; g.C0 = C0; g.x0_bf16 = bf0; g.x1 = x1; g.C1 = C1; g.x1_bf16 = bf0;
+    g.B = nb; g.rows = rows; g.groups = groups; g.eps = eps; g.gamma = n.g; g.beta = n.b;
+    g.stats = A().get<float>(static_cast<size_t>(nb) * C * 2);
+    g.scale_shift = A().get<float>(static_cast<size_t>(nb) * C * 2);
+    if (!g.stats || !g.scale_shift) return set_error("workspace exhausted (group norm)");
+    g.out = out; g.raw_out = raw; g.act = act;
+    return launch_group_norm(g, st);
+  }
+
+  // ResBlock._forward (openaimodel.py:256-276).  Input is (x0 | x1) channel-concatenated (x1 may be null).
+  int res_block(const ResW& r, const float* x0, int C0, const float* x1, int C1, int H, int W, float* out) {
+    const size_t rows = static_cast<size_t>(B) * H * W;
+    const size_t m = A().mark();
+    bf16* a1 = A().get<bf16>(rows * r.cin);
+    bf16* raw = r.has_skip ? A().get<bf16>(rows * r.cin) : nullptr;
+    float* h1 = A().get<float>(rows * r.cout);
+    bf16* a2 = A().get<bf16>(rows * r.cout);
+    float* skip = r.has_skip ? A().get<float>(rows * r.cout) : nullptr;
+    if (A().failed) return set_error("workspace exhausted (res block)");
+    MD_CHECK(gn(x0, C0, false, x1, C1, H * W, 32, 1e-5f, r.n1, ACT_SILU, a1, raw));
+    MD_CHECK(conv(a1, H, W, r.c1, emb_all + r.emb_off, c.unet.emb_total, nullptr, h1, nullptr));
+    MD_CHECK(gn(h1, r.cout, false, nullptr, 0, H * W, 32, 1e-5f, r.n2, ACT_SILU, a2, nullptr));
+    const float* resid = x0;
+    if (r.has_skip) {
+      MD_CHECK(conv(raw, H, W, r.skip, nullptr, 0, nullptr, skip, nullptr));
+      resid = skip;
+    } else if (C1 != 0) {
+      return set_error("res block: identity skip with concatenated input");
+    }
+    MD_CHECK(conv(a2, H, W, r.c2, nullptr, 0, resid, out, nullptr));
+    A().release(m);
+    return 0;
+  }
+
+  // SpatialTransformer.forward (ldm/modules/attention.py:325-336), depth 1, single-token context.
+  int spatial_transformer(const STW& s, const float* x_in, int H, int W, float* out) {
+    const int C = s.C;
+    const size_t S = static_cast<size_t>(H) * W;
+    const size_t rows = static_cast<size_t>(B) * S;
+    const size_t m = A().mark();
+    bf16* a = A().get<bf16>(rows * C);
+    float* x = A().get<float>(rows * C);
+    bf16* ln = A().get<bf16>(rows * C);
+    bf16* qkv = A().get<bf16>(rows * 3 * C);
+    bf16* att = A().get<bf16>(rows * C);
+    bf16* ff = A().get<bf16>(rows * 4 * C);
+    bf16* xb = A().get<bf16>(rows * C);
+    float* v2a = A().get<float>(static_cast<size_t>(B) * C);
+    float* v2 = A().get<float>(static_cast<size_t>(B) * C);
+    if (A().failed) return set_error("workspace exhausted (spatial transformer)");
+    MD_CHECK(gn(x_in, C, false, nullptr, 0, static_cast<int>(S), 32, 1e-6f, s.norm, ACT_NONE, a, nullptr));
+    MD_CHECK(gemm(a, S, s.proj_in, nullptr, x, nullptr));
+    // attn1 (self-attention)
+    MD_CHECK(launch_layer_norm(x, nullptr, 0, s.ln1.g, s.ln1.b, ln, rows, static_cast<int>(S), C, 1e-5f, st));
+    MD_CHECK(gemm(ln, S, s.qkv, nullptr, nullptr, qkv));
+    MD_CHECK(launch_self_attention(qkv, att, B, static_cast<int>(S), s.heads, C / s.heads, st));
+    MD_CHECK(gemm(att, S, s.o1, x, x, nullptr));
+    // attn2: one context token => softmax == 1 => attn2(x) = to_out(to_v(ctx)) for every query
+    MD_CHECK(launch_small_linear(context, c.unet.ctx_dim, s.wv2, nullptr, v2a, C, B, c.unet.ctx_dim, C, ACT_NONE,
+                                 ACT_NONE, 0, st));
+    MD_CHECK(launch_small_linear(v2a, C, s.wo2, s.bo2, v2, C, B, C, C, ACT_NONE, ACT_NONE, 0, st));
+    // x += v2[b]; then norm3 -> GEGLU feed-forward
+    MD_CHECK(launch_layer_norm(x, v2, C, s.ln3.g, s.ln3.b, ln, rows, static_cast<int>(S), C, 1e-5f, st));
+    MD_CHECK(gemm(ln, S, s.ff1, nullptr, nullptr, ff, ACT_GEGLU));
+    MD_CHECK(gemm(ff, S, s.ff2, x, nullptr, xb));
+    MD_CHECK(gemm(xb, S, s.proj_out, x_in, out, nullptr));
+    A().release(m);
+    return 0;
+  }
+
+  // DepthTransformer._forward + DepthAttention.forward (ldm/models/diffusion/attention.py:78-84,26-47)
+  int depth_transformer(const DepthW& d, const float* x_in, int H, int W, const bf16* ctx, int D, float* out) {
+    const size_t S = static_cast<size_t>(H) * W;
+    const size_t rows = static_cast<size_t>(B) * S;
+    const size_t crows = rows * D;
+    const size_t m = A().mark();
+    bf16* xb = A().get<bf16>(rows * d.dim);
+    float* y = A().get<float>(rows * d.inner);
+    bf16* xq = A().get<bf16>(rows * d.inner);
+    bf16* q = A().get<bf16>(rows * d.inner);
+    bf16* c1 = A().get<bf16>(crows * d.ctx);
+    bf16* c2 = A().get<bf16>(crows * d.ctx);
+    bf16* kv = A().get<bf16>(crows * 2 * d.inner);
+    bf16* att = A().get<bf16>(rows * d.inner);
+    float* y2 = A().get<float>(rows * d.inner);
+    bf16* a1 = A().get<bf16>(rows * d.inner);
+    float* y3 = A().get<float>(rows * d.inner);
+    bf16* a2 = A().get<bf16>(rows * d.inner);
+    if (A().failed) return set_error("workspace exhausted (depth transformer)");
+    MD_CHECK(launch_cast_bf16(x_in, xb, rows * d.dim, st));
+    MD_CHECK(gemm(xb, S, d.proj_in, nullptr, y, nullptr));
+    MD_CHECK(gn(y, d.inner, false, nullptr, 0, static_cast<int>(S), 8, 1e-5f, d.gn_in, ACT_SILU, xq, nullptr));
+    MD_CHECK(gemm(xq, S, d.to_q, nullptr, nullptr, q));
+    // context branch
+    MD_CHECK(gemm(ctx, S * D, d.proj_ctx, nullptr, nullptr, c1));
+    MD_CHECK(gn(c1, d.ctx, true, nullptr, 0, static_cast<int>(S * D), 8, 1e-5f, d.gn_ctx, ACT_RELU, c2, nullptr));
+    MD_CHECK(gemm(c2, S * D, d.to_kv, nullptr, nullptr, kv));
+    MD_CHECK(launch_depth_attention(q, kv, att, B, D, static_cast<int>(S), 4, d.dhead, st));
+    MD_CHECK(gemm(att, S, d.to_out, nullptr, y2, nullptr));
+    MD_CHECK(gn(y2, d.inner, false, nullptr, 0, static_cast<int>(S), 8, 1e-5f, d.gn_o1, ACT_RELU, a1, nullptr));
+    MD_CHECK(conv(a1, H, W, d.conv1, nullptr, 0, nullptr, y3, nullptr));
+    MD_CHECK(gn(y3, d.inner, false, nullptr, 0, static_cast<int>(S), 8, 1e-5f, d.gn_o2, ACT_RELU, a2, nullptr));
+    MD_CHECK(conv(a2, H, W, d.conv2, nullptr, 0, x_in, out, nullptr));
+    A().release(m);
+    return 0;
+  }
+
+  // Downsample: Conv2d 3x3 stride 2 pad 1 (openaimodel.py:159-161) via patch gather + GEMM
+  int downsample(const GemmW& w, const float* x, int H, int W, int C, float* out) {
+    const int OH = H / 2, OW = W / 2;
+    const size_t orows = static_cast<size_t>(B) * OH * OW;
+    const size_t m = A().mark();
+    bf16* patches = A().get<bf16>(orows * 9 * C);
+    if (A().failed) return set_error("workspace exhausted (downsample)");
+    MD_CHECK(launch_gather_s2(x, 0, patches, B, 1, H, W, C, 1, st));
+    md_conv_gemm_args a;
+    memset(&a, 0, sizeof(a));
+    a.A = patches; a.B = B; a.D = 1; a.H = 1; a.W = OH * OW; a.Cin = 9 * C; a.Wt = w.w; a.N = w.N; a.ntaps = 1;
+    a.bias = w.bias; a.out_f32 = out;
+    MD_CHECK(launch_conv_gemm(a, st));
+    A().release(m);
+    return 0;
+  }
+  // Upsample: nearest x2 + Conv2d 3x3 (openaimodel.py:110-120)
+  int upsample(const GemmW& w, const float* x, int H, int W, int C, float* out) {
+    const size_t orows = static_cast<size_t>(B) * 4 * H * W;
+    const size_t m = A().mark();
+    bf16* up = A().get<bf16>(orows * C);
+    if (A().failed) return set_error("workspace exhausted (upsample)");
+    MD_CHECK(launch_upsample2x(x, up, B, H, W, C, st));
+    MD_CHECK(conv(up, 2 * H, 2 * W, w, nullptr, 0, nullptr, out, nullptr));
+    A().release(m);
+    return 0;
+  }
+};
+
+}  // namespace
+
+int unet_forward(Ctx& c, const float* x_in, const float* timesteps, const float* context, const bf16* const levels[4],
+                 int B, int S, int D, float* eps_out, cudaStream_t st) {
+  if (!c.weights_loaded) return set_error("unet_forward: weights not loaded");
+  const UNetW& u = c.unet;
+  Arena& A = c.arena;
+  const size_t m0 = A.mark();
+  const int mch = u.model_channels;
+
+  // time embedding MLP + all ResBlock emb projections in three launches
+  float* temb = A.get<float>(static_cast<size_t>(B) * mch);
+  float* e1 = A.get<float>(static_cast<size_t>(B) * u.emb_dim);
+  float* emb = A.get<float>(static_cast<size_t>(B) * u.emb_dim);
+  float* emb_all = A.get<float>(static_cast<size_t>(B) * u.emb_total);
+  if (A.failed) return set_error("workspace exhausted (unet embeddings)");
+  MD_CHECK(launch_timestep_embedding(timesteps, temb, B, mch, st));
+  MD_CHECK(launch_small_linear(temb, mch, u.te0_w, u.te0_b, e1, u.emb_dim, B, mch, u.emb_dim, ACT_NONE, ACT_SILU, 0, st));
+  MD_CHECK(launch_small_linear(e1, u.emb_dim, u.te2_w, u.te2_b, emb, u.emb_dim, B, u.emb_dim, u.emb_dim, ACT_NONE, ACT_NONE, 0, st));
+  MD_CHECK(launch_small_linear(emb, u.emb_dim, u.emb_w, u.emb_b, emb_all, u.emb_total, B, u.emb_dim, u.emb_total, ACT_SILU, ACT_NONE, 0, st));
+
+  Fwd f{c, st, B, emb_all, context};
+
+  struct Skip { float* p; int C, H; };
+  std::vector<Skip> hs;
+  int H = S, ch = mch;
+  // level key -> frustum level index by spatial width (attention.py:128,135)
+  auto level_of = [&](int width, const bf16*& ptr, int& depth) {
+    int li = 0, w = S, d = D;
+    while (w != width && li < 3) { w /= 2; d /= 2; ++li; }
+    ptr = levels[li];
+    depth = d;
+    return w == width ? 0 : -1;
+  };
+
+  float* h = A.get<float>(static_cast<size_t>(B) * H * H * mch);
+  if (A.failed) return set_error("workspace exhausted (unet)");
+  MD_CHECK(launch_conv3x3_direct(x_in, u.conv_in_w, u.conv_in_b, h, B, H, H, u.in_channels, mch, st));
+  hs.push_back({h, mch, H});
+
+  for (size_t bi = 1; bi < u.input_blocks.size(); ++bi) {
+    for (const UNetLayer& L : u.input_blocks[bi]) {
+      if (L.kind == 1) {
+        float* o = A.get<float>(static_cast<size_t>(B) * H * H * L.res.cout);
+        if (A.failed) return set_error("workspace exhausted (unet)");
+        MD_CHECK(f.res_block(L.res, h, ch, nullptr, 0, H, H, o));
+        h = o; ch = L.res.cout;
+      } else if (L.kind == 2) {
+        float* o = A.get<float>(static_cast<size_t>(B) * H * H * ch);
+        if (A.failed) return set_error("workspace exhausted (unet)");
+        MD_CHECK(f.spatial_transformer(L.st, h, H, H, o));
+        h = o;
+      } else if (L.kind == 3) {
+        float* o = A.get<float>(static_cast<size_t>(B) * (H / 2) * (H / 2) * ch);
+        if (A.failed) return set_error("workspace exhausted (unet)");
+        MD_CHECK(f.downsample(L.conv, h, H, H, ch, o));
+        h = o; H /= 2;
+      }
+    }
+    hs.push_back({h, ch, H});
+  }
+  {  // middle block + middle_conditions
+    float* o0 = A.get<float>(static_cast<size_t>(B) * H * H * ch);
+    float* o1 = A.get<float>(static_cast<size_t>(B) * H * H * ch);
+    float* o2 = A.get<float>(static_cast<size_t>(B) * H * H * ch);
+    float* o3 = A.get<float>(static_cast<size_t>(B) * H * H * ch);
+    if (A.failed) return set_error("workspace exhausted (unet)");
+    MD_CHECK(f.res_block(u.mid0, h, ch, nullptr, 0, H, H, o0));
+    MD_CHECK(f.spatial_transformer(u.mid1, o0, H, H, o1));
+    MD_CHECK(f.res_block(u.mid2, o1, ch, nullptr, 0, H, H, o2));
+    const bf16* lv; int dd;
+    if (level_of(H, lv, dd) != 0) return set_error("unet: no frustum level of width %d", H);
+    MD_CHECK(f.depth_transformer(u.mid_cond, o2, H, H, lv, dd, o3));
+    h = o3;
+  }
+  for (size_t bi = 0; bi < u.output_blocks.size(); ++bi) {
+    const Skip sk = hs.back();
+    hs.pop_back();
+    bool first = true;
+    for (const UNetLayer& L : u.output_blocks[bi]) {
+      if (L.kind == 1) {
+        float* o = A.get<float>(static_cast<size_t>(B) * H * H * L.res.cout);
+        if (A.failed) return set_error("workspace exhausted (unet)");
+        if (!first) return set_error("unet: unexpected ResBlock position");
+        MD_CHECK(f.res_block(L.res, h, ch, sk.p, sk.C, H, H, o));
+        h = o; ch = L.res.cout;
+      } else if (L.kind == 2) {
+        float* o = A.get<float>(static_cast<size_t>(B) * H * H * ch);
+        if (A.failed) return set_error("workspace exhausted (unet)");
+        MD_CHECK(f.spatial_transformer(L.st, h, H, H, o));
+        h = o;
+      } else if (L.kind == 4) {
+        float* o = A.get<float>(static_cast<size_t>(B) * 4 * H * H * ch);
+        if (A.failed) return set_error("workspace exhausted (unet)");
+        MD_CHECK(f.upsample(L.conv, h, H, H, ch, o));
+        h = o; H *= 2;
+      }
+      first = false;
+    }
+    if (bi >= 3 && bi - 3 < u.out_cond.size()) {  // output_b2c = {3:0, ..., 11:8}
+      const bf16* lv; int dd;
+      if (level_of(H, lv, dd) != 0) return set_error("unet: no frustum level of width %d", H);
+      float* o = A.get<float>(static_cast<size_t>(B) * H * H * ch);
+      if (A.failed) return set_error("workspace exhausted (unet)");
+      MD_CHECK(f.depth_transformer(u.out_cond[bi - 3], h, H, H, lv, dd, o));
+      h = o;
+    }
+  }
+  // out: GN32 + SiLU + conv3x3 320 -> 4
+  bf16* ao = A.get<bf16>(static_cast<size_t>(B) * H * H * ch);
+  if (A.failed) return set_error("workspace exhausted (unet)");
+  MD_CHECK(f.gn(h, ch, false, nullptr, 0, H * H, 32, 1e-5f, u.out_norm, ACT_SILU, ao, nullptr));
+  MD_CHECK(launch_conv3x3_out(ao, u.out_w, u.out_b, eps_out, B, H, H, ch, u.out_channels, st));
+  A.release(m0);
+  return 0;
+}
+
+}  // namespace md
