@@ -113,13 +113,18 @@ MD_API int md_bind_sample(md_ctx* ctx, const float* K, const float* RT, const fl
 MD_API int md_voxelize(const float* vertices, int nv, int32_t* coord, int32_t* out_sh, float* bounds, void* stream);
 
 /* SpatialVolumeNet.construct_spatial_volume (morphable_diffusion.py:182-263) for the bound sample.
- * x_local [n_local][4][S][S] fp32; volume_out [64][V][V][V] fp32 (NCDHW, B = 1). With a communicator set
+ * x_local [n_local][4][S][S] fp32; t_embed [time_embed_dim] (md_embed_time); volume_out [64][V][V][V] fp32
+ * (NCDHW, B = 1). With a communicator set
  * (md_comm_init) the per-view vertex features are all-reduced over ranks inside this call. */
-MD_API int md_spatial_volume(md_ctx* ctx, const float* x_local, float timestep, float* volume_out, void* stream);
+MD_API int md_spatial_volume(md_ctx* ctx, const float* x_local, const float* t_embed, float* volume_out, void* stream);
+
+/* SyncMultiviewDiffusion.embed_time (morphable_diffusion.py:491-494): sinusoid(256) -> Linear -> SiLU -> Linear.
+ * t_embed_out: DEVICE [time_embed_dim]. */
+MD_API int md_embed_time(md_ctx* ctx, float timestep, float* t_embed_out, void* stream);
 
 /* SpatialVolumeNet.construct_view_frustum_volume (morphable_diffusion.py:265-320) for T local views starting at
  * local index lv0.  volume [64][V][V][V]; out_levels[i] NCDHW fp32 [T][C_i][D/2^i][S/2^i][S/2^i]. */
-MD_API int md_frustum_feats(md_ctx* ctx, const float* volume, int lv0, int T, float timestep,
+MD_API int md_frustum_feats(md_ctx* ctx, const float* volume, int lv0, int T, const float* t_embed,
                             float* const out_levels[4], void* stream);
 
 /* DepthWiseAttention.forward (ldm/models/diffusion/attention.py:117-138): x [B][8][S][S], timesteps [B] (HOST
@@ -135,6 +140,31 @@ MD_API int md_denoise_step(md_ctx* ctx, float* x_local, const float* x_input, co
                            float cfg_scale, const float* noise, unsigned long long seed, float* eps_out,
                            void* stream);
 MD_API int md_ddim_timestep(md_ctx* ctx, int index);  /* 1 .. 981 */
+
+
+/* ------------------------------------------------------------------ op level: the other kernels of the step
+ * (exposed so each kernel can be parity-tested in isolation through the C ABI; all pointers are device pointers) */
+
+/* torch.nn.GroupNorm + optional SiLU/ReLU over channels-last x [B][rows][C] (fp32 or bf16) -> bf16 [B][rows][C].
+ * Reference: GroupNorm32 (ldm/modules/diffusionmodules/util.py:199-216), Normalize (ldm/modules/attention.py:85-86),
+ * nn.GroupNorm(8, c) in network.py:166,190,288 and attention.py:56-69.  addvec [B][C] (optional) is added to x
+ * before normalising (FrustumTVBlock: x + t_conv(t) + v_conv(v), network.py:295). */
+MD_API int md_op_group_norm(const void* x, int x_is_bf16, int B, int rows, int C, int groups, float eps,
+                            const float* gamma, const float* beta, const float* addvec, int act, void* out_bf16,
+                            void* stream);
+/* nn.LayerNorm over the last dim of x fp32 [rows][C] -> bf16 (ldm/modules/attention.py:257-259) */
+MD_API int md_op_layer_norm(float* x, const float* gamma, const float* beta, void* out_bf16, long long rows, int C,
+                            float eps, void* stream);
+/* CrossAttention.forward as self-attention (ldm/modules/attention.py:179-203): qkv bf16 [B][S][3*heads*dh] ->
+ * out bf16 [B][S][heads*dh] */
+MD_API int md_op_self_attention(const void* qkv, void* out, int B, int S, int heads, int dh, void* stream);
+/* DepthAttention.forward core (ldm/models/diffusion/attention.py:36-46): q bf16 [B][HW][4*dh],
+ * kv bf16 [B][D][HW][2*4*dh] (k | v) -> out bf16 [B][HW][4*dh] */
+MD_API int md_op_depth_attention(const void* q, const void* kv, void* out, int B, int D, int HW, int dh, void* stream);
+/* CFG combine + DDIM update (morphable_diffusion.py:147-148,675-698) with the schedule of `ctx`.
+ * eps [2T or T][n], x [T][n] in place; noise NULL -> Philox(seed, index, view0 + t). */
+MD_API int md_op_cfg_ddim(md_ctx* ctx, const float* eps, float* x, float* eps_out, const float* noise, int T,
+                          int n_per_view, int index, float cfg_scale, unsigned long long seed, int view0, void* stream);
 
 /* Multi-GPU: one process per GPU; NCCL communicator created from a 128-byte unique id distributed by the host
  * side (torch.distributed).  The only exchange per step is an all-reduce(sum) of the [nv][16] vertex features. */

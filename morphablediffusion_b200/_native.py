@@ -133,13 +133,22 @@ lib.md_workspace_peak.restype = C.c_ulonglong
 lib.md_load_weights.argtypes = [_vp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(_vp), C.POINTER(C.c_longlong), _vp]
 lib.md_bind_sample.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp]
 lib.md_voxelize.argtypes = [_vp, C.c_int, _vp, _vp, _vp, _vp]
-lib.md_spatial_volume.argtypes = [_vp, _vp, C.c_float, _vp, _vp]
-lib.md_frustum_feats.argtypes = [_vp, _vp, C.c_int, C.c_int, C.c_float, C.POINTER(_vp), _vp]
+lib.md_spatial_volume.argtypes = [_vp, _vp, _vp, _vp, _vp]
+lib.md_embed_time.argtypes = [_vp, C.c_float, _vp, _vp]
+lib.md_frustum_feats.argtypes = [_vp, _vp, C.c_int, C.c_int, _vp, C.POINTER(_vp), _vp]
 lib.md_unet_forward.argtypes = [_vp, _vp, C.POINTER(C.c_float), _vp, C.POINTER(_vp), C.c_int, _vp, _vp]
 lib.md_denoise_step.argtypes = [_vp, _vp, _vp, _vp, C.c_int, C.c_float, _vp, C.c_ulonglong, _vp, _vp]
 lib.md_ddim_timestep.argtypes = [_vp, C.c_int]
 lib.md_comm_unique_id.argtypes = [_vp]
 lib.md_comm_init.argtypes = [_vp, C.c_int, C.c_int, _vp]
-for _f in ("md_create", "md_load_weights", "md_bind_sample", "md_voxelize", "md_spatial_volume", "md_frustum_feats",
+for _f in ("md_embed_time", "md_create", "md_load_weights", "md_bind_sample", "md_voxelize", "md_spatial_volume", "md_frustum_feats",
            "md_unet_forward", "md_denoise_step", "md_ddim_timestep", "md_comm_unique_id", "md_comm_init"):
+    getattr(lib, _f).restype = C.c_int
+
+lib.md_op_group_norm.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _vp, _vp, _vp, C.c_int, _vp, _vp]
+lib.md_op_layer_norm.argtypes = [_vp, _vp, _vp, _vp, C.c_longlong, C.c_int, C.c_float, _vp]
+lib.md_op_self_attention.argtypes = [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp]
+lib.md_op_depth_attention.argtypes = [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp]
+lib.md_op_cfg_ddim.argtypes = [_vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_ulonglong, C.c_int, _vp]
+for _f in ("md_op_group_norm", "md_op_layer_norm", "md_op_self_attention", "md_op_depth_attention", "md_op_cfg_ddim"):
     getattr(lib, _f).restype = C.c_int

@@ -236,7 +236,19 @@ int md_voxelize(const float* vertices, int nv, int32_t* coord, int32_t* out_sh, 
   return launch_voxelize(vertices, nv, coord, out_sh, bounds, static_cast<cudaStream_t>(stream));
 }
 
-int md_spatial_volume(md_ctx* ctx, const float* x_local, float timestep, float* volume_out, void* stream) {
+int md_embed_time(md_ctx* ctx, float timestep, float* t_embed_out, void* stream) {
+  MD_CHECK(ensure_ready(ctx, false));
+  Ctx& c = ctx->c;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  c.arena.off = 0;
+  float* d_t = c.arena.get<float>(1);
+  if (c.arena.failed) return set_error("workspace exhausted");
+  fill_kernel<<<1, 32, 0, st>>>(d_t, timestep, 1);
+  MD_CHECK(check_launch("fill"));
+  return embed_time(c, d_t, t_embed_out, st);
+}
+
+int md_spatial_volume(md_ctx* ctx, const float* x_local, const float* t_embed, float* volume_out, void* stream) {
   MD_CHECK(ensure_ready(ctx, true));
   Ctx& c = ctx->c;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -244,14 +256,9 @@ int md_spatial_volume(md_ctx* ctx, const float* x_local, float timestep, float* 
   const int V = mc.spatial_volume_size;
   Arena& A = c.arena;
   A.off = 0;
-  float* d_t = A.get<float>(1);
-  float* t_embed = A.get<float>(mc.time_embed_dim);
   float* vsum = A.get<float>(static_cast<size_t>(c.sb.nv) * 16);
   float* vol = A.get<float>(static_cast<size_t>(V) * V * V * 64);
   if (A.failed) return set_error("workspace exhausted");
-  fill_kernel<<<1, 32, 0, st>>>(d_t, timestep, 1);
-  MD_CHECK(check_launch("fill"));
-  MD_CHECK(embed_time(c, d_t, t_embed, st));
   MD_CHECK(vertex_feature_sum(c, x_local, t_embed, vsum, st));
   if (c.world > 1 && c.nccl_comm) {
     const int r = g_nccl.AllReduce(vsum, vsum, static_cast<size_t>(c.sb.nv) * 16, 7, 0, c.nccl_comm, st);
@@ -261,8 +268,8 @@ int md_spatial_volume(md_ctx* ctx, const float* x_local, float timestep, float* 
   return launch_cl_to_ncdhw(vol, 0, volume_out, 1, 64, static_cast<size_t>(V) * V * V, st);
 }
 
-int md_frustum_feats(md_ctx* ctx, const float* volume, int lv0, int T, float timestep, float* const out_levels[4],
-                     void* stream) {
+int md_frustum_feats(md_ctx* ctx, const float* volume, int lv0, int T, const float* t_embed,
+                     float* const out_levels[4], void* stream) {
   MD_CHECK(ensure_ready(ctx, true));
   Ctx& c = ctx->c;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -270,13 +277,8 @@ int md_frustum_feats(md_ctx* ctx, const float* volume, int lv0, int T, float tim
   const int V = mc.spatial_volume_size, S = mc.latent_size, D = mc.frustum_depth;
   Arena& A = c.arena;
   A.off = 0;
-  float* d_t = A.get<float>(1);
-  float* t_embed = A.get<float>(mc.time_embed_dim);
   float* vol = A.get<float>(static_cast<size_t>(V) * V * V * 64);
   if (A.failed) return set_error("workspace exhausted");
-  fill_kernel<<<1, 32, 0, st>>>(d_t, timestep, 1);
-  MD_CHECK(check_launch("fill"));
-  MD_CHECK(embed_time(c, d_t, t_embed, st));
   ncdhw_to_cl_f32_kernel<<<148 * 8, 256, 0, st>>>(volume, vol, 64, static_cast<size_t>(V) * V * V);
   MD_CHECK(check_launch("ncdhw_to_cl_f32"));
   bf16* levels[4];
@@ -330,6 +332,45 @@ int md_denoise_step(md_ctx* ctx, float* x_local, const float* x_input, const flo
 int md_ddim_timestep(md_ctx* ctx, int index) {
   if (!ctx || index < 0 || index >= static_cast<int>(ctx->c.timesteps.size())) return -1;
   return ctx->c.timesteps[index];
+}
+
+int md_op_group_norm(const void* x, int x_is_bf16, int B, int rows, int C, int groups, float eps, const float* gamma,
+                     const float* beta, const float* addvec, int act, void* out_bf16, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* ws = nullptr;
+  MD_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws), sizeof(float) * 4 * B * C, st));
+  GroupNormArgs g;
+  memset(&g, 0, sizeof(g));
+  g.x0 = x; g.C0 = C; g.x0_bf16 = x_is_bf16; g.B = B; g.rows = rows; g.groups = groups; g.eps = eps;
+  g.gamma = gamma; g.beta = beta; g.addvec = addvec; g.addvec_ld = C; g.stats = ws; g.scale_shift = ws + 2 * B * C;
+  g.out = out_bf16; g.act = act;
+  const int rc = launch_group_norm(g, st);
+  cudaFreeAsync(ws, st);
+  return rc;
+}
+
+int md_op_layer_norm(float* x, const float* gamma, const float* beta, void* out_bf16, long long rows, int C, float eps,
+                     void* stream) {
+  return launch_layer_norm(x, nullptr, 0, gamma, beta, out_bf16, static_cast<size_t>(rows), 1, C, eps,
+                           static_cast<cudaStream_t>(stream));
+}
+
+int md_op_self_attention(const void* qkv, void* out, int B, int S, int heads, int dh, void* stream) {
+  return launch_self_attention(qkv, out, B, S, heads, dh, static_cast<cudaStream_t>(stream));
+}
+
+int md_op_depth_attention(const void* q, const void* kv, void* out, int B, int D, int HW, int dh, void* stream) {
+  return launch_depth_attention(q, kv, out, B, D, HW, 4, dh, static_cast<cudaStream_t>(stream));
+}
+
+int md_op_cfg_ddim(md_ctx* ctx, const float* eps, float* x, float* eps_out, const float* noise, int T, int n_per_view,
+                   int index, float cfg_scale, unsigned long long seed, int view0, void* stream) {
+  if (!ctx) return set_error("null context");
+  Ctx& c = ctx->c;
+  if (index < 0 || index >= static_cast<int>(c.timesteps.size())) return set_error("cfg_ddim: bad index %d", index);
+  return launch_cfg_ddim(eps, x, eps_out, noise, T, n_per_view, cfg_scale != 1.0f, cfg_scale, c.alphas[index],
+                         c.alphas_prev[index], c.sigmas[index], c.sqrt_1m_alphas[index], index != 0, seed,
+                         static_cast<uint32_t>(index), view0, 1, static_cast<cudaStream_t>(stream));
 }
 
 int md_comm_unique_id(void* id128) {

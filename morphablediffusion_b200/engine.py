@@ -96,19 +96,32 @@ class Engine:
         self.n_views, self.view0, self.n_local = n_views, view0, n_local
 
     # ------------------------------------------------------------------ stages
-    def spatial_volume(self, x_local, timestep):
+    def embed_time(self, timestep):
+        out = torch.empty(self.cfg.time_embed_dim, device=self.device)
+        nat.check(nat.lib.md_embed_time(self._h, float(timestep), out.data_ptr(), nat.cur_stream()), "md_embed_time")
+        return out
+
+    def _t_embed(self, t):
+        if torch.is_tensor(t) and t.numel() == self.cfg.time_embed_dim:
+            return t.to(self.device, torch.float32).reshape(-1).contiguous()
+        return self.embed_time(float(t))
+
+    def spatial_volume(self, x_local, t_embed):
+        """t_embed: the [256] embedding (embed_time) or a scalar timestep."""
         x = x_local.to(self.device, torch.float32).contiguous()
+        te = self._t_embed(t_embed)
         out = torch.empty(1, 64, self.V, self.V, self.V, device=self.device)
-        nat.check(nat.lib.md_spatial_volume(self._h, x.data_ptr(), float(timestep), out.data_ptr(), nat.cur_stream()),
+        nat.check(nat.lib.md_spatial_volume(self._h, x.data_ptr(), te.data_ptr(), out.data_ptr(), nat.cur_stream()),
                   "md_spatial_volume")
         return out
 
-    def frustum_feats(self, volume, lv0, T, timestep):
+    def frustum_feats(self, volume, lv0, T, t_embed):
         vol = volume.to(self.device, torch.float32).contiguous()
+        te = self._t_embed(t_embed)
         S, D = self.S, self.D
         outs = [torch.empty(T, self.cfg.volume_dims[i], D >> i, S >> i, S >> i, device=self.device) for i in range(4)]
         arr = (C.c_void_p * 4)(*[o.data_ptr() for o in outs])
-        nat.check(nat.lib.md_frustum_feats(self._h, vol.data_ptr(), lv0, T, float(timestep), arr, nat.cur_stream()),
+        nat.check(nat.lib.md_frustum_feats(self._h, vol.data_ptr(), lv0, T, te.data_ptr(), arr, nat.cur_stream()),
                   "md_frustum_feats")
         return {S >> i: outs[i] for i in range(4)}
 

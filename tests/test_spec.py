@@ -1,0 +1,56 @@
+"""Parameter inventory and shell classes vs the key/shape table dumped from the real reference modules."""
+import json
+import os
+
+import torch
+
+from morphablediffusion_b200 import spec
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+SCHEDULE_BUFFERS = {"betas", "alphas", "alphas_cumprod", "sqrt_alphas_cumprod", "sqrt_one_minus_alphas_cumprod",
+                    "posterior_variance", "posterior_log_variance_clipped"}
+
+
+def ref_spec():
+    return json.load(open(os.path.join(GOLD, "ref_state_dict_spec.json")))
+
+
+def test_model_spec_matches_reference_state_dict():
+    ref = ref_spec()
+    ours = {k: list(v) for k, v in spec.model_spec().items()}
+    assert set(ours) == set(ref)
+    assert all(ours[k] == ref[k] for k in ref)
+
+
+def test_unet_topology():
+    inp, mid, out = spec.UNetConfig().topology()
+    assert len(inp) == 12 and len(out) == 12 and mid == 1280
+    assert [l[0] for l in inp[3]] == ["down"] and [l[0] for l in out[2]] == ["res", "up"]
+    assert [l[0] for l in inp[10]] == ["res"]  # no attention at ds=8
+    assert len(spec.UNetConfig().depth_blocks()) == 10
+
+
+def test_shell_classes_are_state_dict_compatible():
+    from morphablediffusion_b200.ldm_api import SyncMultiviewDiffusion
+    unet_config = {"target": "ldm.models.diffusion.attention.DepthWiseAttention",
+                   "params": dict(volume_dims=[64, 128, 256, 512], image_size=32, in_channels=8, out_channels=4,
+                                  model_channels=320, attention_resolutions=[4, 2, 1], num_res_blocks=2,
+                                  channel_mult=[1, 2, 4, 4], num_heads=8, use_spatial_transformer=True,
+                                  transformer_depth=1, context_dim=768, use_checkpoint=True, legacy=False)}
+    m = SyncMultiviewDiffusion(unet_config, None, projection="perspective", view_num=16, cfg_scale=2.0)
+    sd = m.state_dict()
+    ref = ref_spec()
+    mine = {k: list(v.shape) for k, v in sd.items() if k not in SCHEDULE_BUFFERS}
+    assert mine == ref
+    assert SCHEDULE_BUFFERS <= set(sd)
+    # the reference zero-initialises its output convolutions; so does the shell
+    assert float(sd["model.diffusion_model.out.2.weight"].abs().sum()) == 0.0
+    assert float(sd["model.diffusion_model.input_blocks.1.1.proj_out.weight"].abs().sum()) == 0.0
+    assert float(sd["model.diffusion_model.middle_conditions.proj_out.5.weight"].abs().sum()) == 0.0
+    # error behaviour mirrors the reference (NotImplementedError for unknown sampler / projection)
+    import pytest
+    with pytest.raises(NotImplementedError):
+        SyncMultiviewDiffusion(unet_config, None, sample_type="plms")
+    # CPU execution is refused loudly: there is no fallback
+    with pytest.raises(RuntimeError):
+        m.embed_time(torch.tensor([1]))
