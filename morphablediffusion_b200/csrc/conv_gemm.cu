@@ -3,6 +3,8 @@
 #include "host.h"
 
 #include <mutex>
+#include <stdio.h>
+#include <stdlib.h>
 
 namespace md {
 
@@ -134,6 +136,11 @@ int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
 
   const int total = p.m_tiles * p.n_tiles;
   const int grid = std::min(total, num_sms());
+  static const bool trace = getenv("MD_TRACE") != nullptr;
+  if (trace)
+    fprintf(stderr, "conv_gemm B=%d D=%d H=%d W=%d Cin=%d taps=%d N=%d BN=%d tiles=%dx%d act=%d f32=%d bf16=%d res=%d\n",
+            a.B, a.D, a.H, a.W, a.Cin, a.ntaps, a.N, BN, p.m_tiles, p.n_tiles, a.act, a.out_f32 != nullptr,
+            a.out_bf16 != nullptr, a.res_f32 != nullptr || a.res_bf16 != nullptr);
   switch (BN) {
     case 64:  return launch_impl<64, 8>(tmA, tmB, p, grid, stream);
     case 128: return launch_impl<128, 6>(tmA, tmB, p, grid, stream);

@@ -83,31 +83,40 @@ __global__ void colstats_kernel(const T0* __restrict__ x0, int C0, const T1* __r
 }
 
 // Stage 2: group statistics -> per-(sample, channel) scale/shift:  y = x*scale + shift  ==  GN(x + addvec).
-__global__ void gn_finalize_kernel(const float* __restrict__ stats, const float* __restrict__ gamma,
+// One CTA per sample; the statistics are zeroed again after use so the buffer is ready for the next GroupNorm.
+__global__ void gn_finalize_kernel(float* __restrict__ stats, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, const float* __restrict__ addvec, int addvec_ld,
                                    float* __restrict__ ss, int C, int G, float nrows, float eps) {
+  __shared__ double g1[64], g2[64];
+  __shared__ float gmean[64], grstd[64];
   const int b = blockIdx.x;
   const int cpg = C / G;
+  for (int g = threadIdx.x; g < G; g += blockDim.x) { g1[g] = 0.0; g2[g] = 0.0; }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float* sp = stats + (static_cast<size_t>(b) * C + c) * 2;
+    const double a = sp[0], q = sp[1];
+    sp[0] = 0.f; sp[1] = 0.f;
+    const double tv = addvec ? addvec[static_cast<size_t>(b) * addvec_ld + c] : 0.0;
+    atomicAdd(&g1[c / cpg], a + nrows * tv);
+    atomicAdd(&g2[c / cpg], q + 2.0 * tv * a + nrows * tv * tv);
+  }
+  __syncthreads();
   for (int g = threadIdx.x; g < G; g += blockDim.x) {
-    double s1 = 0.0, s2 = 0.0;
-    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
-      const double a = stats[(static_cast<size_t>(b) * C + c) * 2];
-      const double q = stats[(static_cast<size_t>(b) * C + c) * 2 + 1];
-      const double tv = addvec ? addvec[static_cast<size_t>(b) * addvec_ld + c] : 0.0;
-      s1 += a + nrows * tv;
-      s2 += q + 2.0 * tv * a + nrows * tv * tv;
-    }
     const double n = static_cast<double>(nrows) * cpg;
-    const double mean = s1 / n;
-    double var = s2 / n - mean * mean;
+    const double mean = g1[g] / n;
+    double var = g2[g] / n - mean * mean;
     if (var < 0.0) var = 0.0;
-    const double rstd = 1.0 / sqrt(var + static_cast<double>(eps));
-    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
-      const double tv = addvec ? addvec[static_cast<size_t>(b) * addvec_ld + c] : 0.0;
-      const double sc = gamma[c] * rstd;
-      ss[(static_cast<size_t>(b) * C + c) * 2] = static_cast<float>(sc);
-      ss[(static_cast<size_t>(b) * C + c) * 2 + 1] = static_cast<float>(beta[c] + (tv - mean) * sc);
-    }
+    gmean[g] = static_cast<float>(mean);
+    grstd[g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    const float tv = addvec ? addvec[static_cast<size_t>(b) * addvec_ld + c] : 0.f;
+    const float sc = gamma[c] * grstd[g];
+    ss[(static_cast<size_t>(b) * C + c) * 2] = sc;
+    ss[(static_cast<size_t>(b) * C + c) * 2 + 1] = beta[c] + (tv - gmean[g]) * sc;
   }
 }
 
@@ -149,15 +158,16 @@ static int group_norm_impl(const GroupNormArgs& a, cudaStream_t st) {
   if (CQ > 1024) return set_error("group_norm: C=%d too large", C);
   int R = std::max(1, std::min(8, 256 / CQ));
   const int threads = CQ * R;
-  MD_CUDA(cudaMemsetAsync(a.stats, 0, sizeof(float) * 2 * a.B * C, st));
-  // aim for >= 2 waves of CTAs
-  int rows_per_cta = std::max(R * 4, (a.rows * a.B + 295) / 296);
+  if (!a.stats_prezeroed) MD_CUDA(cudaMemsetAsync(a.stats, 0, sizeof(float) * 2 * a.B * C, st));
+  // aim for several waves of CTAs (small CTAs: CQ*R threads)
+  const int target_ctas = num_sms() * (threads <= 128 ? 16 : 8);
+  int rows_per_cta = std::max(R * 4, static_cast<int>((static_cast<long long>(a.rows) * a.B + target_ctas - 1) / target_ctas));
   rows_per_cta = std::min(rows_per_cta, a.rows);
   dim3 grid((a.rows + rows_per_cta - 1) / rows_per_cta, a.B);
   colstats_kernel<T0, T1><<<grid, threads, threads * 8 * sizeof(float), st>>>(
       static_cast<const T0*>(a.x0), a.C0, static_cast<const T1*>(a.x1), a.C1, a.stats, a.rows, rows_per_cta, R);
   MD_CHECK(check_launch("colstats"));
-  gn_finalize_kernel<<<a.B, 32, 0, st>>>(a.stats, a.gamma, a.beta, a.addvec, a.addvec_ld, a.scale_shift, C, a.groups,
+  gn_finalize_kernel<<<a.B, 256, 0, st>>>(a.stats, a.gamma, a.beta, a.addvec, a.addvec_ld, a.scale_shift, C, a.groups,
                                          static_cast<float>(a.rows), a.eps);
   MD_CHECK(check_launch("gn_finalize"));
   const size_t total4 = static_cast<size_t>(a.B) * a.rows * CQ;
@@ -246,37 +256,47 @@ int launch_layer_norm(float* x, const float* addvec, int addvec_ld, const float*
 }
 
 // ------------------------------------------------------------------------------------------------ small linear
-// out[b][n] = act_out( bias[n] + sum_k act_in(x[b][k]) * W[n][k] );  one warp per output column n, all samples.
+// out[b][n] = act_out( bias[n] + sum_k act_in(x[b][k]) * W[n][k] );  one warp per (sample, output) pair.
 __global__ void small_linear_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ W,
                                     const float* __restrict__ bias, float* __restrict__ out, int ldo, int B, int K,
                                     int N, int act_in, int act_out, int accumulate) {
   const int lane = threadIdx.x & 31;
-  const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (n >= N) return;
+  const long long wid = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  if (wid >= static_cast<long long>(N) * B) return;
+  const int n = static_cast<int>(wid % N);
+  const int b = static_cast<int>(wid / N);
   const float* w = W + static_cast<size_t>(n) * K;
-  for (int b = 0; b < B; ++b) {
-    const float* xb = x + static_cast<size_t>(b) * ldx;
-    float acc = 0.f;
+  const float* xb = x + static_cast<size_t>(b) * ldx;
+  float acc = 0.f;
+  if ((K & 3) == 0) {
+    for (int k = lane * 4; k < K; k += 128) {
+      float4 xv = *reinterpret_cast<const float4*>(xb + k);
+      const float4 wv = __ldg(reinterpret_cast<const float4*>(w + k));
+      if (act_in == ACT_SILU) { xv.x = silu_f(xv.x); xv.y = silu_f(xv.y); xv.z = silu_f(xv.z); xv.w = silu_f(xv.w); }
+      acc += xv.x * wv.x + xv.y * wv.y + xv.z * wv.z + xv.w * wv.w;
+    }
+  } else {
     for (int k = lane; k < K; k += 32) {
       float xv = xb[k];
       if (act_in == ACT_SILU) xv = silu_f(xv);
       acc += xv * __ldg(w + k);
     }
+  }
 #pragma unroll
-    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffff, acc, o);
-    if (lane == 0) {
-      acc += bias ? bias[n] : 0.f;
-      if (act_out == ACT_SILU) acc = silu_f(acc);
-      float* o = out + static_cast<size_t>(b) * ldo + n;
-      *o = accumulate ? (*o + acc) : acc;
-    }
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffff, acc, o);
+  if (lane == 0) {
+    acc += bias ? bias[n] : 0.f;
+    if (act_out == ACT_SILU) acc = silu_f(acc);
+    float* o = out + static_cast<size_t>(b) * ldo + n;
+    *o = accumulate ? (*o + acc) : acc;
   }
 }
 
 int launch_small_linear(const float* x, int ldx, const float* W, const float* bias, float* out, int ldo, int B, int K,
                         int N, int act_in, int act_out, int accumulate, cudaStream_t st) {
   const int threads = 128;
-  const int blocks = (N * 32 + threads - 1) / threads;
+  const long long warps = static_cast<long long>(N) * B;
+  const unsigned blocks = static_cast<unsigned>((warps * 32 + threads - 1) / threads);
   small_linear_kernel<<<blocks, threads, 0, st>>>(x, ldx, W, bias, out, ldo, B, K, N, act_in, act_out, accumulate);
   return check_launch("small_linear");
 }

@@ -48,9 +48,7 @@ struct STW {
   int C = 0, heads = 0;
   NormW norm, ln1, ln2, ln3;
   GemmW proj_in, qkv, o1, ff1, ff2, proj_out;
-  const float* wv2 = nullptr;  // fp32 [C][ctx]   attn2.to_v
-  const float* wo2 = nullptr;  // fp32 [C][C]     attn2.to_out.0
-  const float* bo2 = nullptr;
+  int v2_off = 0;  // offset of this block's attn2 vector inside UNetW::v2 (single context token => attn2 is affine in ctx)
 };
 struct DepthW {
   int dim = 0, inner = 0, ctx = 0, dhead = 0;
@@ -64,7 +62,8 @@ struct UNetLayer {
 struct UNetW {
   int model_channels = 320, in_channels = 8, out_channels = 4, heads = 8, ctx_dim = 768, emb_dim = 1280;
   const float* te0_w = nullptr; const float* te0_b = nullptr; const float* te2_w = nullptr; const float* te2_b = nullptr;
-  float* emb_w = nullptr; float* emb_b = nullptr; int emb_total = 0;  // concatenated emb_layers.1 of all ResBlocks
+  GemmW emb_g; int emb_total = 0;   // concatenated emb_layers.1 of all ResBlocks: [emb_total][emb_dim]
+  GemmW v2_g; int v2_total = 0;     // concatenated (attn2.to_out . attn2.to_v) of all transformer blocks: [v2_total][ctx]
   float* conv_in_w = nullptr; const float* conv_in_b = nullptr;       // fp32 [tap][Cin][Cout]
   std::vector<std::vector<UNetLayer>> input_blocks, output_blocks;
   ResW mid0, mid2; STW mid1;
@@ -119,6 +118,8 @@ struct Ctx {
   std::vector<int> timesteps;
   // step state buffers
   float* d_t = nullptr;  // [max B] timesteps as float
+  float* gn_stats = nullptr;  // persistent all-zero GroupNorm statistics scratch (finalize re-zeroes it)
+  size_t gn_stats_floats = 0;
   // multi-GPU
   void* nccl_comm = nullptr;
   int rank = 0, world = 1;

@@ -366,28 +366,46 @@ int launch_smpl_scatter(const float* vsum, float inv_views, const float* W, cons
 }
 
 // out[r][co] = relu( scale[co] * sum_{k,ci} W[k][ci][co] * in[nbr[r][k]][ci] + shift[co] ),  nbr < 0 = inactive.
+// One thread per (row, 4 output channels): float4 weight loads (coalesced over co), float4 input loads.
 __global__ void sparse_conv_kernel(const float* __restrict__ in, const int32_t* __restrict__ nbr,
                                    const float* __restrict__ W, const float* __restrict__ scale,
                                    const float* __restrict__ shift, float* __restrict__ out, int n_rows, int Cin,
                                    int Cout) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_rows * Cout) return;
-  const int co = i % Cout, r = i / Cout;
-  float acc = 0.f;
+  const int CQ = Cout >> 2;
+  if (i >= n_rows * CQ) return;
+  const int cq = i % CQ, r = i / CQ;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int k = 0; k < 27; ++k) {
-    const int j = nbr[r * 27 + k];
+    const int j = __ldg(nbr + r * 27 + k);
     if (j < 0) continue;
-    const float* ip = in + static_cast<size_t>(j) * Cin;
-    const float* wp = W + static_cast<size_t>(k) * Cin * Cout + co;
-    for (int ci = 0; ci < Cin; ++ci) acc += ip[ci] * __ldg(wp + ci * Cout);
+    const float4* ip = reinterpret_cast<const float4*>(in + static_cast<size_t>(j) * Cin);
+    const float* wp = W + static_cast<size_t>(k) * Cin * Cout + cq * 4;
+#pragma unroll 4
+    for (int c4 = 0; c4 < (Cin >> 2); ++c4) {
+      const float4 a = __ldg(ip + c4);
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(wp + static_cast<size_t>(c4 * 4 + 0) * Cout));
+      const float4 w1 = __ldg(reinterpret_cast<const float4*>(wp + static_cast<size_t>(c4 * 4 + 1) * Cout));
+      const float4 w2 = __ldg(reinterpret_cast<const float4*>(wp + static_cast<size_t>(c4 * 4 + 2) * Cout));
+      const float4 w3 = __ldg(reinterpret_cast<const float4*>(wp + static_cast<size_t>(c4 * 4 + 3) * Cout));
+      acc.x += a.x * w0.x + a.y * w1.x + a.z * w2.x + a.w * w3.x;
+      acc.y += a.x * w0.y + a.y * w1.y + a.z * w2.y + a.w * w3.y;
+      acc.z += a.x * w0.z + a.y * w1.z + a.z * w2.z + a.w * w3.z;
+      acc.w += a.x * w0.w + a.y * w1.w + a.z * w2.w + a.w * w3.w;
+    }
   }
-  out[i] = fmaxf(acc * scale[co] + shift[co], 0.f);
+  const float4 sc = *reinterpret_cast<const float4*>(scale + cq * 4);
+  const float4 sh = *reinterpret_cast<const float4*>(shift + cq * 4);
+  float4 o;
+  o.x = fmaxf(acc.x * sc.x + sh.x, 0.f); o.y = fmaxf(acc.y * sc.y + sh.y, 0.f);
+  o.z = fmaxf(acc.z * sc.z + sh.z, 0.f); o.w = fmaxf(acc.w * sc.w + sh.w, 0.f);
+  *reinterpret_cast<float4*>(out + static_cast<size_t>(r) * Cout + cq * 4) = o;
 }
 
 int launch_sparse_conv(const float* in, const int32_t* nbr, const float* W, const float* scale, const float* shift,
                        float* out, int n_rows, int Cin, int Cout, cudaStream_t st) {
   if (n_rows == 0) return 0;
-  sparse_conv_kernel<<<(n_rows * Cout + 127) / 128, 128, 0, st>>>(in, nbr, W, scale, shift, out, n_rows, Cin, Cout);
+  sparse_conv_kernel<<<(n_rows * (Cout / 4) + 63) / 64, 64, 0, st>>>(in, nbr, W, scale, shift, out, n_rows, Cin, Cout);
   return check_launch("sparse_conv");
 }
 

@@ -17,6 +17,7 @@ struct GroupNormArgs {
   const float* gamma; const float* beta; // [C0+C1]
   const float* addvec; int addvec_ld;    // optional per-sample vector added before normalising
   float* stats;                          // workspace [B][C][2]
+  int stats_prezeroed;                   // 1: buffer is all-zero on entry (the finalize kernel re-zeroes it)
   float* scale_shift;                    // workspace [B][C][2]
   void* out;                             // bf16 [B][rows][C]
   void* raw_out;                         // optional bf16 copy of the un-normalised input

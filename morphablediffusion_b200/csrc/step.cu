@@ -193,6 +193,14 @@ int md_create(md_ctx** out, const md_config* cfg) {
     return set_error("md_create: cudaMalloc(%zu) for the workspace failed: %s", bytes, cudaGetErrorString(e));
   }
   ctx->c.arena.cap = bytes;
+  ctx->c.gn_stats_floats = static_cast<size_t>(2) * (2 * mv) * 4096;
+  e = cudaMalloc(reinterpret_cast<void**>(&ctx->c.gn_stats), ctx->c.gn_stats_floats * sizeof(float));
+  if (e == cudaSuccess) e = cudaMemset(ctx->c.gn_stats, 0, ctx->c.gn_stats_floats * sizeof(float));
+  if (e != cudaSuccess) {
+    cudaFree(ctx->c.arena.base);
+    delete ctx;
+    return set_error("md_create: GroupNorm scratch allocation failed: %s", cudaGetErrorString(e));
+  }
   *out = ctx;
   return 0;
 }
@@ -204,6 +212,7 @@ void md_destroy(md_ctx* ctx) {
   free_weights(ctx->c);
   if (ctx->c.nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->c.nccl_comm);
   cudaFree(ctx->c.arena.base);
+  cudaFree(ctx->c.gn_stats);
   delete ctx;
 }
 

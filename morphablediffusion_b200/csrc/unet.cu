@@ -12,7 +12,7 @@ struct Fwd {
   cudaStream_t st;
   int B;               // samples in this UNet call
   const float* emb_all;  // [B][emb_total] per-ResBlock time-embedding projections
-  const float* context;  // [B][ctx_dim]
+  const float* v2_all;   // [B][v2_total] attn2 output vectors of every transformer block
   int rc = 0;
 
   Arena& A() { return c.arena; }
@@ -56,9 +56,10 @@ struct Fwd {
     memset(&g, 0, sizeof(g));
     g.x0 = x0; g.C0 = C0; g.x0_bf16 = bf0; g.x1 = x1; g.C1 = C1; g.x1_bf16 = bf0;
     g.B = nb; g.rows = rows; g.groups = groups; g.eps = eps; g.gamma = n.g; g.beta = n.b;
-    g.stats = A().get<float>(static_cast<size_t>(nb) * C * 2);
+    if (static_cast<size_t>(nb) * C * 2 > c.gn_stats_floats) return set_error("group norm statistics scratch too small");
+    g.stats = c.gn_stats; g.stats_prezeroed = 1;
     g.scale_shift = A().get<float>(static_cast<size_t>(nb) * C * 2);
-    if (!g.stats || !g.scale_shift) return set_error("workspace exhausted (group norm)");
+    if (!g.scale_shift) return set_error("workspace exhausted (group norm)");
     g.out = out; g.raw_out = raw; g.act = act;
     return launch_group_norm(g, st);
   }
@@ -101,8 +102,6 @@ struct Fwd {
     bf16* att = A().get<bf16>(rows * C);
     bf16* ff = A().get<bf16>(rows * 4 * C);
     bf16* xb = A().get<bf16>(rows * C);
-    float* v2a = A().get<float>(static_cast<size_t>(B) * C);
-    float* v2 = A().get<float>(static_cast<size_t>(B) * C);
     if (A().failed) return set_error("workspace exhausted (spatial transformer)");
     MD_CHECK(gn(x_in, C, false, nullptr, 0, static_cast<int>(S), 32, 1e-6f, s.norm, ACT_NONE, a, nullptr));
     MD_CHECK(gemm(a, S, s.proj_in, nullptr, x, nullptr));
@@ -111,12 +110,10 @@ struct Fwd {
     MD_CHECK(gemm(ln, S, s.qkv, nullptr, nullptr, qkv));
     MD_CHECK(launch_self_attention(qkv, att, B, static_cast<int>(S), s.heads, C / s.heads, st));
     MD_CHECK(gemm(att, S, s.o1, x, x, nullptr));
-    // attn2: one context token => softmax == 1 => attn2(x) = to_out(to_v(ctx)) for every query
-    MD_CHECK(launch_small_linear(context, c.unet.ctx_dim, s.wv2, nullptr, v2a, C, B, c.unet.ctx_dim, C, ACT_NONE,
-                                 ACT_NONE, 0, st));
-    MD_CHECK(launch_small_linear(v2a, C, s.wo2, s.bo2, v2, C, B, C, C, ACT_NONE, ACT_NONE, 0, st));
-    // x += v2[b]; then norm3 -> GEGLU feed-forward
-    MD_CHECK(launch_layer_norm(x, v2, C, s.ln3.g, s.ln3.b, ln, rows, static_cast<int>(S), C, 1e-5f, st));
+    // attn2: one context token => softmax == 1 => attn2(x) = to_out(to_v(ctx)) for every query (precomputed per
+    // forward in v2_all).  x += v2[b]; then norm3 -> GEGLU feed-forward
+    MD_CHECK(launch_layer_norm(x, v2_all + s.v2_off, c.unet.v2_total, s.ln3.g, s.ln3.b, ln, rows, static_cast<int>(S), C,
+                               1e-5f, st));
     MD_CHECK(gemm(ln, S, s.ff1, nullptr, nullptr, ff, ACT_GEGLU));
     MD_CHECK(gemm(ff, S, s.ff2, x, nullptr, xb));
     MD_CHECK(gemm(xb, S, s.proj_out, x_in, out, nullptr));
@@ -200,18 +197,32 @@ int unet_forward(Ctx& c, const float* x_in, const float* timesteps, const float*
   const size_t m0 = A.mark();
   const int mch = u.model_channels;
 
-  // time embedding MLP + all ResBlock emb projections in three launches
+  // time embedding MLP, then every ResBlock's emb projection and every transformer block's attn2 vector as two
+  // tensor-core GEMMs over the batch
   float* temb = A.get<float>(static_cast<size_t>(B) * mch);
   float* e1 = A.get<float>(static_cast<size_t>(B) * u.emb_dim);
   float* emb = A.get<float>(static_cast<size_t>(B) * u.emb_dim);
+  bf16* emb_b = A.get<bf16>(static_cast<size_t>(B) * u.emb_dim);
+  bf16* ctx_b = A.get<bf16>(static_cast<size_t>(B) * u.ctx_dim);
   float* emb_all = A.get<float>(static_cast<size_t>(B) * u.emb_total);
+  float* v2_all = A.get<float>(static_cast<size_t>(B) * u.v2_total);
   if (A.failed) return set_error("workspace exhausted (unet embeddings)");
   MD_CHECK(launch_timestep_embedding(timesteps, temb, B, mch, st));
   MD_CHECK(launch_small_linear(temb, mch, u.te0_w, u.te0_b, e1, u.emb_dim, B, mch, u.emb_dim, ACT_NONE, ACT_SILU, 0, st));
-  MD_CHECK(launch_small_linear(e1, u.emb_dim, u.te2_w, u.te2_b, emb, u.emb_dim, B, u.emb_dim, u.emb_dim, ACT_NONE, ACT_NONE, 0, st));
-  MD_CHECK(launch_small_linear(emb, u.emb_dim, u.emb_w, u.emb_b, emb_all, u.emb_total, B, u.emb_dim, u.emb_total, ACT_SILU, ACT_NONE, 0, st));
+  MD_CHECK(launch_small_linear(e1, u.emb_dim, u.te2_w, u.te2_b, emb, u.emb_dim, B, u.emb_dim, u.emb_dim, ACT_NONE, ACT_SILU, 0, st));
+  MD_CHECK(launch_cast_bf16(emb, emb_b, static_cast<size_t>(B) * u.emb_dim, st));
+  MD_CHECK(launch_cast_bf16(context, ctx_b, static_cast<size_t>(B) * u.ctx_dim, st));
+  {
+    md_conv_gemm_args a;
+    memset(&a, 0, sizeof(a));
+    a.A = emb_b; a.B = 1; a.D = 1; a.H = 1; a.W = B; a.Cin = u.emb_dim; a.Wt = u.emb_g.w; a.N = u.emb_total; a.ntaps = 1;
+    a.bias = u.emb_g.bias; a.out_f32 = emb_all;
+    MD_CHECK(launch_conv_gemm(a, st));
+    a.A = ctx_b; a.Cin = u.ctx_dim; a.Wt = u.v2_g.w; a.N = u.v2_total; a.bias = u.v2_g.bias; a.out_f32 = v2_all;
+    MD_CHECK(launch_conv_gemm(a, st));
+  }
 
-  Fwd f{c, st, B, emb_all, context};
+  Fwd f{c, st, B, emb_all, v2_all};
 
   struct Skip { float* p; int C, H; };
   std::vector<Skip> hs;

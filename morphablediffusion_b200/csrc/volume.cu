@@ -382,7 +382,8 @@ int frustum_levels(Ctx& c, const float* vol, int lv0, int T, const float* t_embe
   // x + t_conv(t) + v_conv(v) -> GN(8) -> SiLU  (network.py:285-311)
   auto norm_act = [&](const FrBlockW& b, const bf16* x, size_t rows, bf16* out) {
     float* tv = A.get<float>(static_cast<size_t>(T) * b.cin);
-    float* stats = A.get<float>(static_cast<size_t>(T) * b.cin * 2);
+    if (static_cast<size_t>(T) * b.cin * 2 > c.gn_stats_floats) return set_error("group norm statistics scratch too small");
+    float* stats = c.gn_stats;
     float* ss = A.get<float>(static_cast<size_t>(T) * b.cin * 2);
     if (A.failed) return set_error("workspace exhausted (frustum norm)");
     MD_CHECK(launch_small_linear(v_emb, vdm, b.v_w, b.v_b, tv, b.cin, T, vdm, b.cin, ACT_NONE, ACT_NONE, 0, st));
@@ -390,7 +391,8 @@ int frustum_levels(Ctx& c, const float* vol, int lv0, int T, const float* t_embe
     GroupNormArgs g;
     memset(&g, 0, sizeof(g));
     g.x0 = x; g.C0 = b.cin; g.x0_bf16 = 1; g.B = T; g.rows = static_cast<int>(rows); g.groups = 8; g.eps = 1e-5f;
-    g.gamma = b.gn.g; g.beta = b.gn.b; g.addvec = tv; g.addvec_ld = b.cin; g.stats = stats; g.scale_shift = ss;
+    g.gamma = b.gn.g; g.beta = b.gn.b; g.addvec = tv; g.addvec_ld = b.cin; g.stats = stats; g.stats_prezeroed = 1;
+    g.scale_shift = ss;
     g.out = out; g.act = ACT_SILU;
     return launch_group_norm(g, st);
   };

@@ -36,6 +36,30 @@ __global__ void permute_rows_f32_kernel(const float* __restrict__ src, float* __
   dst[n] = src[ns];
 }
 
+// C[M][N] (bf16, row stride ldc) = A[M][K] * B[K][N]   (fp32 inputs; load-time only)
+__global__ void matmul_f32_to_bf16_kernel(const float* __restrict__ A, const float* __restrict__ Bm,
+                                          __nv_bfloat16* __restrict__ Cm, int M, int N, int K) {
+  __shared__ float sa[16][17], sb[16][17];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int row = blockIdx.y * 16 + ty, col = blockIdx.x * 16 + tx;
+  float acc = 0.f;
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    sa[ty][tx] = (row < M && k0 + tx < K) ? A[static_cast<size_t>(row) * K + k0 + tx] : 0.f;
+    sb[ty][tx] = (col < N && k0 + ty < K) ? Bm[static_cast<size_t>(k0 + ty) * N + col] : 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc += sa[ty][k] * sb[k][tx];
+    __syncthreads();
+  }
+  if (row < M && col < N) Cm[static_cast<size_t>(row) * N + col] = __float2bfloat16(acc);
+}
+
+__global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    dst[i] = __float2bfloat16(src[i]);
+}
+
 __global__ void bn_fold_kernel(const float* g, const float* b, const float* mean, const float* var, float eps,
                                float* scale, float* shift, int C) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -152,6 +176,8 @@ struct Loader {
     (void)emb_dim;
     return r;
   }
+  int v2_off = 0;
+  std::vector<std::pair<std::string, int>> v2_list;
   STW st_block(const std::string& p, int C, int heads, int ctx) {
     STW s;
     s.C = C; s.heads = heads;
@@ -161,9 +187,9 @@ struct Loader {
     s.ln1 = norm(t + "norm1", C); s.ln2 = norm(t + "norm2", C); s.ln3 = norm(t + "norm3", C);
     s.qkv = gemm_fused({t + "attn1.to_q.weight", t + "attn1.to_k.weight", t + "attn1.to_v.weight"}, C, C);
     s.o1 = gemm(t + "attn1.to_out.0", C, C, 1, true);
-    s.wv2 = copy_f32(t + "attn2.to_v.weight", static_cast<size_t>(C) * ctx);
-    s.wo2 = copy_f32(t + "attn2.to_out.0.weight", static_cast<size_t>(C) * C);
-    s.bo2 = copy_f32(t + "attn2.to_out.0.bias", C);
+    s.v2_off = v2_off;
+    v2_list.push_back({t + "attn2.", C});
+    v2_off += C;
     s.ff1 = gemm(t + "ff.net.0.proj", 8 * C, C, 1, true, /*geglu_inner=*/4 * C);
     s.ff2 = gemm(t + "ff.net.2", C, 4 * C, 1, true);
     s.proj_out = gemm(p + "proj_out", C, C, 1, true);
@@ -295,21 +321,50 @@ int load_all_weights(Ctx& c, const TensorMap& tm, cudaStream_t st) {
   u.out_cond.clear();
   for (int i = 0; i < 9; ++i)
     u.out_cond.push_back(L.depth(P + "output_conditions." + std::to_string(i) + ".", dims[i][0], dims[i][1] / 2, dims[i][1]));
-  // concatenated emb_layers
+  // concatenated emb_layers: one [emb_total][emb_dim] bf16 GEMM operand
   u.emb_total = emb_off;
-  u.emb_w = L.dalloc<float>(static_cast<size_t>(emb_off) * u.emb_dim);
-  u.emb_b = L.dalloc<float>(emb_off);
-  if (u.emb_w && u.emb_b) {
-    int off = 0;
-    for (auto& e : emb_list) {
-      const NamedTensor* w = L.find(e.first + ".weight", static_cast<size_t>(e.second) * u.emb_dim);
-      const NamedTensor* b = L.find(e.first + ".bias", e.second);
-      if (w && b) {
-        cudaMemcpyAsync(u.emb_w + static_cast<size_t>(off) * u.emb_dim, w->ptr, sizeof(float) * e.second * u.emb_dim,
-                        cudaMemcpyDeviceToDevice, st);
-        cudaMemcpyAsync(u.emb_b + off, b->ptr, sizeof(float) * e.second, cudaMemcpyDeviceToDevice, st);
+  {
+    u.emb_g.N = emb_off; u.emb_g.K = u.emb_dim; u.emb_g.taps = 1;
+    u.emb_g.w = L.dalloc<bf16>(static_cast<size_t>(emb_off) * u.emb_dim);
+    float* eb = L.dalloc<float>(emb_off);
+    u.emb_g.bias = eb;
+    if (u.emb_g.w && eb) {
+      int off = 0;
+      for (auto& e : emb_list) {
+        const NamedTensor* w = L.find(e.first + ".weight", static_cast<size_t>(e.second) * u.emb_dim);
+        const NamedTensor* b = L.find(e.first + ".bias", e.second);
+        if (w && b) {
+          f32_to_bf16_kernel<<<256, 256, 0, st>>>(w->ptr, u.emb_g.w + static_cast<size_t>(off) * u.emb_dim,
+                                                  static_cast<size_t>(e.second) * u.emb_dim);
+          cudaMemcpyAsync(eb + off, b->ptr, sizeof(float) * e.second, cudaMemcpyDeviceToDevice, st);
+        }
+        off += e.second;
       }
-      off += e.second;
+    }
+  }
+  // attn2 with ONE context token: softmax == 1, so attn2(x) = to_out(to_v(ctx)) = (W_out W_v) ctx + b_out for every
+  // query.  The products of all transformer blocks are concatenated into one [v2_total][ctx_dim] operand.
+  u.v2_total = L.v2_off;
+  {
+    u.v2_g.N = L.v2_off; u.v2_g.K = u.ctx_dim; u.v2_g.taps = 1;
+    u.v2_g.w = L.dalloc<bf16>(static_cast<size_t>(L.v2_off) * u.ctx_dim);
+    float* vb = L.dalloc<float>(L.v2_off);
+    u.v2_g.bias = vb;
+    if (u.v2_g.w && vb) {
+      int off = 0;
+      for (auto& e : L.v2_list) {
+        const int C = e.second;
+        const NamedTensor* wv = L.find(e.first + "to_v.weight", static_cast<size_t>(C) * u.ctx_dim);
+        const NamedTensor* wo = L.find(e.first + "to_out.0.weight", static_cast<size_t>(C) * C);
+        const NamedTensor* bo = L.find(e.first + "to_out.0.bias", C);
+        if (wv && wo && bo) {
+          dim3 grid((u.ctx_dim + 15) / 16, (C + 15) / 16), blk(16, 16);
+          matmul_f32_to_bf16_kernel<<<grid, blk, 0, st>>>(wo->ptr, wv->ptr, u.v2_g.w + static_cast<size_t>(off) * u.ctx_dim,
+                                                          C, u.ctx_dim, C);
+          cudaMemcpyAsync(vb + off, bo->ptr, sizeof(float) * C, cudaMemcpyDeviceToDevice, st);
+        }
+        off += C;
+      }
     }
   }
 
