@@ -58,6 +58,8 @@ typedef struct md_conv_gemm_args {
   int act;
   float out_scale;          /* 0 -> 1 */
   int BN;                   /* tile N override (64/128/160/256), 0 = auto */
+  float* col_stats;         /* optional [B][stats_ld][2] sum / sum-of-squares accumulation (atomics; pre-zeroed) */
+  int stats_ld;             /* 0 -> N */
 } md_conv_gemm_args;
 
 MD_API int md_op_conv_gemm(const md_conv_gemm_args* args, void* stream);

@@ -30,18 +30,18 @@ static int pow2_floor(int v) {
   return p;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int EPI_WARPS>
 static int launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p, int grid,
                        cudaStream_t stream) {
-  using S = ConvGemmSmem<BN, STAGES>;
+  using S = ConvGemmSmem<BN, STAGES, EPI_WARPS>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BN, STAGES, EPI_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          S::kTotal);
     if (e != cudaSuccess) return set_error("cudaFuncSetAttribute(conv_gemm): %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  conv_gemm_kernel<BN, STAGES><<<grid, 192, S::kTotal, stream>>>(tmA, tmB, p);
+  conv_gemm_kernel<BN, STAGES, EPI_WARPS><<<grid, 64 + 32 * EPI_WARPS, S::kTotal, stream>>>(tmA, tmB, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("conv_gemm launch: %s", cudaGetErrorString(e));
   count_launch();
@@ -90,6 +90,7 @@ int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
   p.res_f32 = a.res_f32; p.res_bf16 = static_cast<const __nv_bfloat16*>(a.res_bf16);
   p.out_f32 = a.out_f32; p.out_bf16 = static_cast<__nv_bfloat16*>(a.out_bf16);
   p.out_scale = a.out_scale == 0.f ? 1.f : a.out_scale;
+  p.col_stats = a.col_stats; p.stats_ld = a.stats_ld ? a.stats_ld : n_out;
   if (p.ldo % 8 != 0) return set_error("conv_gemm: ldo=%d must be a multiple of 8", p.ldo);
   if (a.act == ACT_GEGLU && !a.out_bf16) return set_error("conv_gemm: GEGLU epilogue writes bf16 only");
 
@@ -142,10 +143,10 @@ int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
             a.B, a.D, a.H, a.W, a.Cin, a.ntaps, a.N, BN, p.m_tiles, p.n_tiles, a.act, a.out_f32 != nullptr,
             a.out_bf16 != nullptr, a.res_f32 != nullptr || a.res_bf16 != nullptr);
   switch (BN) {
-    case 64:  return launch_impl<64, 8>(tmA, tmB, p, grid, stream);
-    case 128: return launch_impl<128, 6>(tmA, tmB, p, grid, stream);
-    case 160: return launch_impl<160, 5>(tmA, tmB, p, grid, stream);
-    case 256: return launch_impl<256, 4>(tmA, tmB, p, grid, stream);
+    case 64:  return launch_impl<64, 7, 8>(tmA, tmB, p, grid, stream);
+    case 128: return launch_impl<128, 5, 8>(tmA, tmB, p, grid, stream);
+    case 160: return launch_impl<160, 5, 8>(tmA, tmB, p, grid, stream);
+    case 256: return launch_impl<256, 4, 4>(tmA, tmB, p, grid, stream);
     default:  return set_error("conv_gemm: unsupported BN=%d", BN);
   }
 }

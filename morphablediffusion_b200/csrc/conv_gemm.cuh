@@ -44,27 +44,157 @@ struct ConvGemmParams {
   __nv_bfloat16* out_bf16;
   int act;
   float out_scale;  // multiplies the result before residual (1.0 default)
+  float* col_stats; // optional [B][stats_ld][2]: per-(sample, channel) sum / sum of squares of the fp32 result
+  int stats_ld;
 };
 
 __device__ __forceinline__ float act_silu(float x) { return x / (1.f + __expf(-x)); }
 __device__ __forceinline__ float act_gelu(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int EPI_WARPS>
 struct ConvGemmSmem {
   static constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KB
   static constexpr int kBBytes = BN * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kBarOffset = STAGES * kStageBytes;
-  static constexpr int kTotal = kBarOffset + 256 + 1024;  // barriers + alignment slack
+  static constexpr int kStageOffset = STAGES * kStageBytes;          // EPI_WARPS x 4 KB epilogue staging tiles
+  static constexpr int kBiasOffset = kStageOffset + EPI_WARPS * 4096;  // EPI_WARPS x BN floats
+  static constexpr int kRowOffset = kBiasOffset + EPI_WARPS * BN * 4;  // EPI_WARPS x 32 x (int64 row offset, int sample, pad)
+  static constexpr int kBarOffset = kRowOffset + EPI_WARPS * 32 * 16;
+  static constexpr int kTotal = kBarOffset + 256;
 };
 
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(192, 1)
+// Epilogue of one output tile for one warp (32 accumulator rows), specialised on the residual kind and on the
+// presence of a per-sample vector so that the inner loops are branch-free.
+//   phase 0: issue the chunk's global loads (per-sample vector, residual) in the coalesced phase-2 layout;
+//   phase 1 (row owner): TMEM -> registers, scale + bias (+ GEGLU), swizzled store into a private 32x32 staging tile;
+//   phase 2 (coalesced; one warp instruction = 4 rows x 128 B): + per-sample vector, activation, + residual,
+//            fp32 / bf16 stores, optional per-(sample, channel) sum / sum-of-squares for the next GroupNorm.
+template <int BN, int RES, bool RV>
+__device__ __forceinline__ void epilogue_tile(const ConvGemmParams& p, uint32_t taddr, float* stage, const float* bias_s,
+                                              int lane, int n_tile, const int4* rowinfo, int warp_sample, int c_begin,
+                                              int c_step) {
+  const int prow = lane >> 3;   // phase-2 row within a group of 4
+  const int pchunk = lane & 7;  // phase-2 16-byte chunk within the 128-byte row
+  const bool geglu = (p.act == ACT_GEGLU);
+  constexpr int HALF = BN / 2;
+  const int out_cols = geglu ? HALF : BN;
+  const int n_limit = geglu ? p.N / 2 : p.N;
+  const int n_out0 = n_tile * out_cols;
+#pragma unroll 1
+  for (int c = c_begin; c < out_cols / 32; c += c_step) {
+    const int col = n_out0 + c * 32 + pchunk * 4;
+    const bool col_ok = col < n_limit;
+    const int col_safe = col_ok ? col : 0;
+    // ---- phase 0: all global loads of this chunk in flight together (invalid rows read a safe address)
+    float4 rv4[8];
+    float4 rs4[8];
+    uint2 rb2[8];
+    if (RV || RES != 0) {
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int4 ri = rowinfo[it * 4 + prow];  // (row offset lo, hi, sample, -)
+        const bool ok = ri.z >= 0;
+        const long long ro = ok ? ((static_cast<long long>(ri.y) << 32) | static_cast<unsigned int>(ri.x)) : 0;
+        if (RV) rv4[it] = __ldg(reinterpret_cast<const float4*>(p.rowvec + static_cast<long long>(ok ? ri.z : 0) * p.rowvec_ld + col_safe));
+        if (RES == 1) rs4[it] = *reinterpret_cast<const float4*>(p.res_f32 + ro + col_safe);
+        if (RES == 2) rb2[it] = *reinterpret_cast<const uint2*>(p.res_bf16 + ro + col_safe);
+      }
+    }
+    // ---- phase 1: accumulator chunk -> staging tile
+    {
+      uint32_t v[32];
+      tmem_ld_32x32(taddr + c * 32, v);
+      if (geglu) {
+        uint32_t g[32];
+        tmem_ld_32x32(taddr + HALF + c * 32, g);
+        tc_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 o;
+          float* of = reinterpret_cast<float*>(&o);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float val = __uint_as_float(v[4 * j + e]) + bias_s[c * 32 + 4 * j + e];
+            const float gate = __uint_as_float(g[4 * j + e]) + bias_s[HALF + c * 32 + 4 * j + e];
+            of[e] = val * act_gelu(gate);
+          }
+          *reinterpret_cast<float4*>(stage + lane * 32 + ((j ^ (lane & 7)) << 2)) = o;
+        }
+      } else {
+        tc_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 bb = *reinterpret_cast<const float4*>(bias_s + c * 32 + 4 * j);
+          const float4 o = make_float4(fmaf(__uint_as_float(v[4 * j]), p.out_scale, bb.x),
+                                       fmaf(__uint_as_float(v[4 * j + 1]), p.out_scale, bb.y),
+                                       fmaf(__uint_as_float(v[4 * j + 2]), p.out_scale, bb.z),
+                                       fmaf(__uint_as_float(v[4 * j + 3]), p.out_scale, bb.w));
+          *reinterpret_cast<float4*>(stage + lane * 32 + ((j ^ (lane & 7)) << 2)) = o;
+        }
+      }
+    }
+    __syncwarp();
+    // ---- phase 2: coalesced finish
+    float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int row = it * 4 + prow;
+      const int4 ri = rowinfo[row];
+      const bool ok = (ri.z >= 0) && col_ok;
+      float4 v4 = *reinterpret_cast<const float4*>(stage + row * 32 + ((pchunk ^ (row & 7)) << 2));
+      if (RV) { v4.x += rv4[it].x; v4.y += rv4[it].y; v4.z += rv4[it].z; v4.w += rv4[it].w; }
+      if (p.act == ACT_SILU) {
+        v4.x = act_silu(v4.x); v4.y = act_silu(v4.y); v4.z = act_silu(v4.z); v4.w = act_silu(v4.w);
+      } else if (p.act == ACT_RELU) {
+        v4.x = fmaxf(v4.x, 0.f); v4.y = fmaxf(v4.y, 0.f); v4.z = fmaxf(v4.z, 0.f); v4.w = fmaxf(v4.w, 0.f);
+      } else if (p.act == ACT_GELU) {
+        v4.x = act_gelu(v4.x); v4.y = act_gelu(v4.y); v4.z = act_gelu(v4.z); v4.w = act_gelu(v4.w);
+      }
+      if (RES == 1) { v4.x += rs4[it].x; v4.y += rs4[it].y; v4.z += rs4[it].z; v4.w += rs4[it].w; }
+      if (RES == 2) {
+        v4.x += __uint_as_float(rb2[it].x << 16); v4.y += __uint_as_float(rb2[it].x & 0xffff0000u);
+        v4.z += __uint_as_float(rb2[it].y << 16); v4.w += __uint_as_float(rb2[it].y & 0xffff0000u);
+      }
+      const long long off = ((static_cast<long long>(ri.y) << 32) | static_cast<unsigned int>(ri.x)) + col;
+      if (p.out_f32 && ok) *reinterpret_cast<float4*>(p.out_f32 + off) = v4;
+      if (p.out_bf16 && ok) {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(v4.x, v4.y);
+        __nv_bfloat162 hi = __floats2bfloat162_rn(v4.z, v4.w);
+        uint2 o2;
+        o2.x = *reinterpret_cast<uint32_t*>(&lo);
+        o2.y = *reinterpret_cast<uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(p.out_bf16 + off) = o2;
+      }
+      if (ok) {
+        s1[0] += v4.x; s1[1] += v4.y; s1[2] += v4.z; s1[3] += v4.w;
+        s2[0] += v4.x * v4.x; s2[1] += v4.y * v4.y; s2[2] += v4.z * v4.z; s2[3] += v4.w * v4.w;
+      }
+    }
+    if (p.col_stats) {
+      // lanes l, l^8, l^16, l^24 own the same columns; the host guarantees one sample per warp (warp_sample)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        s1[e] += __shfl_xor_sync(0xffffffff, s1[e], 8);
+        s1[e] += __shfl_xor_sync(0xffffffff, s1[e], 16);
+        s2[e] += __shfl_xor_sync(0xffffffff, s2[e], 8);
+        s2[e] += __shfl_xor_sync(0xffffffff, s2[e], 16);
+      }
+      if (prow == 0 && warp_sample >= 0 && col_ok) {
+        float* cs = p.col_stats + (static_cast<long long>(warp_sample) * p.stats_ld + col) * 2;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { atomicAdd(cs + 2 * e, s1[e]); atomicAdd(cs + 2 * e + 1, s2[e]); }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+template <int BN, int STAGES, int EPI_WARPS>
+__global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const ConvGemmParams p) {
-  using S = ConvGemmSmem<BN, STAGES>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  using S = ConvGemmSmem<BN, STAGES, EPI_WARPS>;
+  extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kBarOffset);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
@@ -84,7 +214,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);
+      mbar_init(&tmem_empty[i], EPI_WARPS);
     }
     fence_mbar_init();
   }
@@ -160,9 +290,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    // ===================== epilogue (warps 2 .. 2+EPI_WARPS) =====================
+    // Warp w reads TMEM lane quarter (w & 3); with 8 epilogue warps the two warps of a quarter split the 32-column
+    // chunks of the tile between them (even / odd).
+    const int ew = warp - 2;
+    const int q = warp & 3;
     const int r = q * 32 + lane;
+    float* stage = reinterpret_cast<float*>(smem + S::kStageOffset) + ew * 1024;
+    float* bias_s = reinterpret_cast<float*>(smem + S::kBiasOffset) + ew * BN;
+    int4* rowinfo = reinterpret_cast<int4*>(smem + S::kRowOffset) + ew * 32;
+    const int c_begin = (EPI_WARPS == 8) ? (ew >> 2) : 0;
+    const int c_step = (EPI_WARPS == 8) ? 2 : 1;
+    const int mode = (p.res_f32 ? 1 : (p.res_bf16 ? 2 : 0)) * 2 + (p.rowvec ? 1 : 0);
     int lt = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
       const int a = lt & 1;
@@ -179,101 +318,30 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int x = xb * p.bw + ix, y = yb * p.bh + iy, z = zb * p.bd + iz, b = m * p.bb + rr;
       const bool valid = (x < p.W) && (y < p.H) && (z < p.D) && (b < p.B);
       const long long orow =
-          ((static_cast<long long>(b) * p.OD + (z * p.osz + p.opz)) * p.OH + (y * p.osy + p.opy)) * p.OW +
-          (x * p.osx + p.opx);
+          (((static_cast<long long>(b) * p.OD + (z * p.osz + p.opz)) * p.OH + (y * p.osy + p.opy)) * p.OW +
+           (x * p.osx + p.opx)) * p.ldo;
+      const int bv = valid ? b : -1;
+      rowinfo[lane] = make_int4(static_cast<int>(orow & 0xffffffffLL), static_cast<int>(orow >> 32), bv, 0);
+      // bias of this tile -> private smem (overlaps with the wait for the accumulator)
+#pragma unroll
+      for (int i = 0; i < (BN + 31) / 32; ++i) {
+        const int e = i * 32 + lane;
+        if (e < BN) bias_s[e] = (p.bias && n_tile * BN + e < p.N) ? __ldg(p.bias + n_tile * BN + e) : 0.f;
+      }
+      // sample of the warp's rows (fused GroupNorm statistics: the host guarantees one sample per warp there)
+      const int warp_sample = __reduce_max_sync(0xffffffff, bv);
+      __syncwarp();
 
       mbar_wait(&tmem_full[a], aph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * BN;
-
-      if (p.act == ACT_GEGLU) {
-        constexpr int HALF = BN / 2;
-        const int n_out0 = n_tile * HALF;
-#pragma unroll 1
-        for (int c = 0; c < HALF / 32; ++c) {
-          uint32_t v[32], g[32];
-          tmem_ld_32x32(taddr + c * 32, v);
-          tmem_ld_32x32(taddr + HALF + c * 32, g);
-          tc_wait_ld();
-          if (valid) {
-            const int nb = n_tile * BN + c * 32;  // packed-row index of the value half
-            __nv_bfloat16* o = p.out_bf16 + orow * p.ldo + n_out0 + c * 32;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              if (n_out0 + c * 32 + j < p.N / 2) {
-                __align__(16) __nv_bfloat16 ob[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                  float val = __uint_as_float(v[j + e]) + (p.bias ? p.bias[nb + j + e] : 0.f);
-                  float gate = __uint_as_float(g[j + e]) + (p.bias ? p.bias[nb + HALF + j + e] : 0.f);
-                  ob[e] = __float2bfloat16(val * act_gelu(gate));
-                }
-                *reinterpret_cast<uint4*>(o + j) = *reinterpret_cast<const uint4*>(ob);
-              }
-            }
-          }
-        }
-      } else {
-        const int n0 = n_tile * BN;
-#pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-          uint32_t v[32];
-          tmem_ld_32x32(taddr + c * 32, v);
-          tc_wait_ld();
-          if (valid) {
-            const int nb = n0 + c * 32;
-            const long long obase = orow * p.ldo + nb;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              if (nb + j < p.N) {
-                float f[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j + e]) * p.out_scale;
-                if (p.bias) {
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) f[e] += __ldg(p.bias + nb + j + e);
-                }
-                if (p.rowvec) {
-                  const float* rv = p.rowvec + static_cast<long long>(b) * p.rowvec_ld + nb + j;
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) f[e] += __ldg(rv + e);
-                }
-                if (p.act == ACT_SILU) {
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) f[e] = act_silu(f[e]);
-                } else if (p.act == ACT_RELU) {
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
-                } else if (p.act == ACT_GELU) {
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) f[e] = act_gelu(f[e]);
-                }
-                if (p.res_f32) {
-                  const float4 r0 = *reinterpret_cast<const float4*>(p.res_f32 + obase + j);
-                  const float4 r1 = *reinterpret_cast<const float4*>(p.res_f32 + obase + j + 4);
-                  f[0] += r0.x; f[1] += r0.y; f[2] += r0.z; f[3] += r0.w;
-                  f[4] += r1.x; f[5] += r1.y; f[6] += r1.z; f[7] += r1.w;
-                }
-                if (p.res_bf16) {
-                  const uint4 rb = *reinterpret_cast<const uint4*>(p.res_bf16 + obase + j);
-                  const __nv_bfloat16* rbh = reinterpret_cast<const __nv_bfloat16*>(&rb);
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) f[e] += __bfloat162float(rbh[e]);
-                }
-                if (p.out_f32) {
-                  *reinterpret_cast<float4*>(p.out_f32 + obase + j) = make_float4(f[0], f[1], f[2], f[3]);
-                  *reinterpret_cast<float4*>(p.out_f32 + obase + j + 4) = make_float4(f[4], f[5], f[6], f[7]);
-                }
-                if (p.out_bf16) {
-                  __align__(16) __nv_bfloat16 ob[8];
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) ob[e] = __float2bfloat16(f[e]);
-                  *reinterpret_cast<uint4*>(p.out_bf16 + obase + j) = *reinterpret_cast<const uint4*>(ob);
-                }
-              }
-            }
-          }
-        }
+      switch (mode) {
+        case 0: epilogue_tile<BN, 0, false>(p, taddr, stage, bias_s, lane, n_tile, rowinfo, warp_sample, c_begin, c_step); break;
+        case 1: epilogue_tile<BN, 0, true>(p, taddr, stage, bias_s, lane, n_tile, rowinfo, warp_sample, c_begin, c_step); break;
+        case 2: epilogue_tile<BN, 1, false>(p, taddr, stage, bias_s, lane, n_tile, rowinfo, warp_sample, c_begin, c_step); break;
+        case 3: epilogue_tile<BN, 1, true>(p, taddr, stage, bias_s, lane, n_tile, rowinfo, warp_sample, c_begin, c_step); break;
+        case 4: epilogue_tile<BN, 2, false>(p, taddr, stage, bias_s, lane, n_tile, rowinfo, warp_sample, c_begin, c_step); break;
+        default: epilogue_tile<BN, 2, true>(p, taddr, stage, bias_s, lane, n_tile, rowinfo, warp_sample, c_begin, c_step); break;
       }
       tc_fence_before();
       __syncwarp();
