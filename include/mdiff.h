@@ -160,9 +160,13 @@ MD_API int md_op_layer_norm(float* x, const float* gamma, const float* beta, voi
 /* CrossAttention.forward as self-attention (ldm/modules/attention.py:179-203): qkv bf16 [B][S][3*heads*dh] ->
  * out bf16 [B][S][heads*dh] */
 MD_API int md_op_self_attention(const void* qkv, void* out, int B, int S, int heads, int dh, void* stream);
-/* DepthAttention.forward core (ldm/models/diffusion/attention.py:36-46): q bf16 [B][HW][4*dh],
- * kv bf16 [B][D][HW][2*4*dh] (k | v) -> out bf16 [B][HW][4*dh] */
-MD_API int md_op_depth_attention(const void* q, const void* kv, void* out, int B, int D, int HW, int dh, void* stream);
+/* DepthAttention.forward core (ldm/models/diffusion/attention.py:36-46), re-associated: K = W_k c and V = W_v c are
+ * never materialised.  qp bf16 [T][HW][4*ctx] = per-head W_k^T q (softmax scale folded in); c1 bf16 [T][D][HW][ctx]
+ * = proj_context conv output BEFORE GroupNorm; ss fp32 [T][ctx][2] = its GroupNorm scale/shift; beta fp32 [ctx];
+ * out cbar bf16 [B][HW][4*ctx] = per-head sum_d softmax_d(qp . c_d) c_d with c = ReLU(c1*scale+shift).
+ * Samples T..B-1 have an all-zero frustum volume (CFG-unconditional half) and receive ReLU(beta). */
+MD_API int md_op_depth_attention(const void* qp, const void* c1, const float* ss, const float* beta, void* cbar, int T,
+                                 int B, int D, int HW, int ctx, void* stream);
 /* CFG combine + DDIM update (morphable_diffusion.py:147-148,675-698) with the schedule of `ctx`.
  * eps [2T or T][n], x [T][n] in place; noise NULL -> Philox(seed, index, view0 + t). */
 MD_API int md_op_cfg_ddim(md_ctx* ctx, const float* eps, float* x, float* eps_out, const float* noise, int T,

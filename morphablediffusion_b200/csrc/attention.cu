@@ -191,90 +191,108 @@ int launch_self_attention(const void* qkv, void* out, int B, int S, int heads, i
 }
 
 // ------------------------------------------------------------------------------------------------ depth attention
-// One warp per (sample, pixel); lane l serves head l/8 with a contiguous chunk of CH = dh/8 channels.
-template <int CH>
-__global__ void depth_attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kv,
-                                       __nv_bfloat16* __restrict__ out, int B, int D, int HW, float scale_log2e) {
-  constexpr int inner = CH * 32;
+// DepthAttention.forward (ldm/models/diffusion/attention.py:26-47) re-associated so that K and V are never built:
+//   sim[h][d] = q_h . (W_k,h c_d) = (W_k,h^T q_h) . c_d =: qp_h . c_d        (qp comes from one GEMM, scale folded in)
+//   out       = W_out concat_h( W_v,h sum_d attn[h][d] c_d ) = W_ov . cbar     (second GEMM on cbar = sum_d attn c_d)
+// with c = ReLU(GroupNorm(proj_context(ctx))) applied on the fly from the pre-norm tensor c1 and its per-(sample,
+// channel) scale/shift.  One warp per (sample, pixel); lane owns CPL = ctx/32 contiguous context channels; a single
+// pass over the D depth samples with an online softmax per head.  Samples b >= T have an all-zero frustum volume
+// (the CFG-unconditional half): c == ReLU(beta) for every depth, attention is uniform and cbar = ReLU(beta).
+//   qp   bf16 [T][HW][4*ctx]      c1 bf16 [T][D][HW][ctx]      ss fp32 [T][ctx][2]      beta fp32 [ctx]
+//   cbar bf16 [B][HW][4*ctx]
+template <int CPL>
+__global__ void depth_attention_kernel(const __nv_bfloat16* __restrict__ qp, const __nv_bfloat16* __restrict__ c1,
+                                       const float* __restrict__ ss, const float* __restrict__ beta,
+                                       __nv_bfloat16* __restrict__ cbar, int T, int B, int D, int HW) {
+  constexpr int ctx = CPL * 32;
   const int lane = threadIdx.x & 31;
   const size_t wid = (blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x) >> 5;
   if (wid >= static_cast<size_t>(B) * HW) return;
   const int b = static_cast<int>(wid / HW);
-  const int p = static_cast<int>(wid % HW);
-  const int c0 = lane * CH;
-
-  float qv[CH];
-  {
-    const __nv_bfloat16* qp = q + wid * inner + c0;
+  const int pix = static_cast<int>(wid % HW);
+  const int j0 = lane * CPL;
+  __nv_bfloat16* op = cbar + wid * (4 * ctx) + j0;
+  if (b >= T) {
 #pragma unroll
-    for (int e = 0; e < CH; e += 4) {
-      const uint2 u = *reinterpret_cast<const uint2*>(qp + e);
-      const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&u.x);
-      const __nv_bfloat162 c = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
-      qv[e] = __low2float(a); qv[e + 1] = __high2float(a); qv[e + 2] = __low2float(c); qv[e + 3] = __high2float(c);
+    for (int e = 0; e < CPL; e += 2) {
+      const __nv_bfloat162 v = __floats2bfloat162_rn(fmaxf(beta[j0 + e], 0.f), fmaxf(beta[j0 + e + 1], 0.f));
+#pragma unroll
+      for (int h = 0; h < 4; ++h) *reinterpret_cast<__nv_bfloat162*>(op + h * ctx + e) = v;
     }
+    return;
   }
-  float acc[CH];
+  float sc[CPL], sh[CPL], q[4][CPL], acc[4][CPL];
 #pragma unroll
-  for (int e = 0; e < CH; ++e) acc[e] = 0.f;
-  float m = -INFINITY, l = 0.f;
-  const __nv_bfloat16* kvp = kv + (static_cast<size_t>(b) * D * HW + p) * (2 * inner) + c0;
-  const size_t dstride = static_cast<size_t>(HW) * 2 * inner;
+  for (int e = 0; e < CPL; ++e) {
+    sc[e] = ss[(static_cast<size_t>(b) * ctx + j0 + e) * 2];
+    sh[e] = ss[(static_cast<size_t>(b) * ctx + j0 + e) * 2 + 1];
+  }
+  const __nv_bfloat16* qb = qp + wid * (4 * ctx) + j0;
+#pragma unroll
+  for (int h = 0; h < 4; ++h)
+#pragma unroll
+    for (int e = 0; e < CPL; e += 2) {
+      const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(qb + h * ctx + e);
+      q[h][e] = __low2float(v); q[h][e + 1] = __high2float(v);
+      acc[h][e] = 0.f; acc[h][e + 1] = 0.f;
+    }
+  float m[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, l[4] = {0.f, 0.f, 0.f, 0.f};
+  const __nv_bfloat16* cp = c1 + (static_cast<size_t>(b) * D * HW + pix) * ctx + j0;
+  const size_t dstride = static_cast<size_t>(HW) * ctx;
   for (int d = 0; d < D; ++d) {
-    const __nv_bfloat16* kp = kvp + d * dstride;
-    float kf[CH], vf[CH];
+    float c[CPL];
 #pragma unroll
-    for (int e = 0; e < CH; e += 4) {
-      const uint2 uk = *reinterpret_cast<const uint2*>(kp + e);
-      const uint2 uv = *reinterpret_cast<const uint2*>(kp + inner + e);
-      const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&uk.x);
-      const __nv_bfloat162 c = *reinterpret_cast<const __nv_bfloat162*>(&uk.y);
-      const __nv_bfloat162 a2 = *reinterpret_cast<const __nv_bfloat162*>(&uv.x);
-      const __nv_bfloat162 c2 = *reinterpret_cast<const __nv_bfloat162*>(&uv.y);
-      kf[e] = __low2float(a); kf[e + 1] = __high2float(a); kf[e + 2] = __low2float(c); kf[e + 3] = __high2float(c);
-      vf[e] = __low2float(a2); vf[e + 1] = __high2float(a2); vf[e + 2] = __low2float(c2); vf[e + 3] = __high2float(c2);
+    for (int e = 0; e < CPL; e += 2) {
+      const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(cp + d * dstride + e);
+      c[e] = fmaxf(__low2float(v) * sc[e] + sh[e], 0.f);
+      c[e + 1] = fmaxf(__high2float(v) * sc[e + 1] + sh[e + 1], 0.f);
     }
-    float s = 0.f;
+    float s[4];
 #pragma unroll
-    for (int e = 0; e < CH; ++e) s += qv[e] * kf[e];
-    s += __shfl_xor_sync(0xffffffff, s, 1);
-    s += __shfl_xor_sync(0xffffffff, s, 2);
-    s += __shfl_xor_sync(0xffffffff, s, 4);
-    const float mn = fmaxf(m, s);
-    const float corr = exp2f((m - mn) * scale_log2e);
-    const float pe = exp2f((s - mn) * scale_log2e);
-    m = mn;
-    l = l * corr + pe;
+    for (int h = 0; h < 4; ++h) {
+      float a = 0.f;
 #pragma unroll
-    for (int e = 0; e < CH; ++e) acc[e] = acc[e] * corr + pe * vf[e];
+      for (int e = 0; e < CPL; ++e) a += q[h][e] * c[e];
+      s[h] = a;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+#pragma unroll
+      for (int h = 0; h < 4; ++h) s[h] += __shfl_xor_sync(0xffffffff, s[h], o);
+    }
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      const float mn = fmaxf(m[h], s[h]);
+      const float corr = __expf(m[h] - mn);
+      const float pe = __expf(s[h] - mn);
+      m[h] = mn;
+      l[h] = l[h] * corr + pe;
+#pragma unroll
+      for (int e = 0; e < CPL; ++e) acc[h][e] = acc[h][e] * corr + pe * c[e];
+    }
   }
-  const float inv = 1.f / l;
-  __nv_bfloat16* op = out + wid * inner + c0;
 #pragma unroll
-  for (int e = 0; e < CH; e += 4) {
-    uint2 u;
-    u.x = pack_bf16(acc[e] * inv, acc[e + 1] * inv);
-    u.y = pack_bf16(acc[e + 2] * inv, acc[e + 3] * inv);
-    *reinterpret_cast<uint2*>(op + e) = u;
+  for (int h = 0; h < 4; ++h) {
+    const float inv = 1.f / l[h];
+#pragma unroll
+    for (int e = 0; e < CPL; e += 2)
+      *reinterpret_cast<__nv_bfloat162*>(op + h * ctx + e) = __floats2bfloat162_rn(acc[h][e] * inv, acc[h][e + 1] * inv);
   }
 }
 
-int launch_depth_attention(const void* q, const void* kv, void* out, int B, int D, int HW, int heads, int dh,
-                           cudaStream_t st) {
-  if (heads != 4) return set_error("depth_attention: heads=%d (DepthTransformer always uses 4)", heads);
-  const int CH = dh / 8;
-  const float scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(dh));
+int launch_depth_attention(const void* qp, const void* c1, const float* ss, const float* beta, void* cbar, int T, int B,
+                           int D, int HW, int ctx, cudaStream_t st) {
   const size_t warps = static_cast<size_t>(B) * HW;
   const unsigned blocks = static_cast<unsigned>((warps * 32 + 127) / 128);
-  const __nv_bfloat16* qq = static_cast<const __nv_bfloat16*>(q);
-  const __nv_bfloat16* kk = static_cast<const __nv_bfloat16*>(kv);
-  __nv_bfloat16* oo = static_cast<__nv_bfloat16*>(out);
-  switch (CH) {
-    case 4: depth_attention_kernel<4><<<blocks, 128, 0, st>>>(qq, kk, oo, B, D, HW, scale_log2e); break;
-    case 8: depth_attention_kernel<8><<<blocks, 128, 0, st>>>(qq, kk, oo, B, D, HW, scale_log2e); break;
-    case 16: depth_attention_kernel<16><<<blocks, 128, 0, st>>>(qq, kk, oo, B, D, HW, scale_log2e); break;
-    case 32: depth_attention_kernel<32><<<blocks, 128, 0, st>>>(qq, kk, oo, B, D, HW, scale_log2e); break;
-    default: return set_error("depth_attention: head dim %d unsupported", dh);
+  const __nv_bfloat16* qq = static_cast<const __nv_bfloat16*>(qp);
+  const __nv_bfloat16* cc = static_cast<const __nv_bfloat16*>(c1);
+  __nv_bfloat16* oo = static_cast<__nv_bfloat16*>(cbar);
+  switch (ctx) {
+    case 64: depth_attention_kernel<2><<<blocks, 128, 0, st>>>(qq, cc, ss, beta, oo, T, B, D, HW); break;
+    case 128: depth_attention_kernel<4><<<blocks, 128, 0, st>>>(qq, cc, ss, beta, oo, T, B, D, HW); break;
+    case 256: depth_attention_kernel<8><<<blocks, 128, 0, st>>>(qq, cc, ss, beta, oo, T, B, D, HW); break;
+    case 512: depth_attention_kernel<16><<<blocks, 128, 0, st>>>(qq, cc, ss, beta, oo, T, B, D, HW); break;
+    default: return set_error("depth_attention: context dim %d unsupported (64/128/256/512)", ctx);
   }
   return check_launch("depth_attention");
 }

@@ -91,6 +91,8 @@ int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
   p.out_f32 = a.out_f32; p.out_bf16 = static_cast<__nv_bfloat16*>(a.out_bf16);
   p.out_scale = a.out_scale == 0.f ? 1.f : a.out_scale;
   p.col_stats = a.col_stats; p.stats_ld = a.stats_ld ? a.stats_ld : n_out;
+  if (a.col_stats && ((p.bw * p.bh * p.bd) % 32) != 0)
+    return set_error("conv_gemm: fused statistics need >= 32 rows per sample per tile (box %dx%dx%d)", p.bw, p.bh, p.bd);
   if (p.ldo % 8 != 0) return set_error("conv_gemm: ldo=%d must be a multiple of 8", p.ldo);
   if (a.act == ACT_GEGLU && !a.out_bf16) return set_error("conv_gemm: GEGLU epilogue writes bf16 only");
 

@@ -83,40 +83,44 @@ __global__ void colstats_kernel(const T0* __restrict__ x0, int C0, const T1* __r
 }
 
 // Stage 2: group statistics -> per-(sample, channel) scale/shift:  y = x*scale + shift  ==  GN(x + addvec).
-// One CTA per sample; the statistics are zeroed again after use so the buffer is ready for the next GroupNorm.
-__global__ void gn_finalize_kernel(float* __restrict__ stats, const float* __restrict__ gamma,
-                                   const float* __restrict__ beta, const float* __restrict__ addvec, int addvec_ld,
-                                   float* __restrict__ ss, int C, int G, float nrows, float eps) {
-  __shared__ double g1[64], g2[64];
-  __shared__ float gmean[64], grstd[64];
+// One CTA per sample, one warp per group.  The statistics come either from the colstats scratch (zeroed again here so
+// the buffer is ready for the next GroupNorm) or from the producing GEMMs' epilogues (two sources for a concat).
+__global__ void gn_finalize_kernel(float* __restrict__ stats0, int C0, float* __restrict__ stats1, int C1, int zero_after,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   const float* __restrict__ addvec, int addvec_ld, float* __restrict__ ss, int G,
+                                   float nrows, float eps) {
   const int b = blockIdx.x;
+  const int C = C0 + C1;
   const int cpg = C / G;
-  for (int g = threadIdx.x; g < G; g += blockDim.x) { g1[g] = 0.0; g2[g] = 0.0; }
-  __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float* sp = stats + (static_cast<size_t>(b) * C + c) * 2;
-    const double a = sp[0], q = sp[1];
-    sp[0] = 0.f; sp[1] = 0.f;
-    const double tv = addvec ? addvec[static_cast<size_t>(b) * addvec_ld + c] : 0.0;
-    atomicAdd(&g1[c / cpg], a + nrows * tv);
-    atomicAdd(&g2[c / cpg], q + 2.0 * tv * a + nrows * tv * tv);
-  }
-  __syncthreads();
-  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int g = warp; g < G; g += nwarps) {
+    double s1 = 0.0, s2 = 0.0;
+    for (int c = g * cpg + lane; c < (g + 1) * cpg; c += 32) {
+      float* sp = (c < C0) ? stats0 + (static_cast<size_t>(b) * C0 + c) * 2
+                           : stats1 + (static_cast<size_t>(b) * C1 + (c - C0)) * 2;
+      const double a = sp[0], q = sp[1];
+      if (zero_after) { sp[0] = 0.f; sp[1] = 0.f; }
+      const double tv = addvec ? addvec[static_cast<size_t>(b) * addvec_ld + c] : 0.0;
+      s1 += a + nrows * tv;
+      s2 += q + 2.0 * tv * a + nrows * tv * tv;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffff, s1, o);
+      s2 += __shfl_xor_sync(0xffffffff, s2, o);
+    }
     const double n = static_cast<double>(nrows) * cpg;
-    const double mean = g1[g] / n;
-    double var = g2[g] / n - mean * mean;
+    const double mean = s1 / n;
+    double var = s2 / n - mean * mean;
     if (var < 0.0) var = 0.0;
-    gmean[g] = static_cast<float>(mean);
-    grstd[g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
-  }
-  __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const int g = c / cpg;
-    const float tv = addvec ? addvec[static_cast<size_t>(b) * addvec_ld + c] : 0.f;
-    const float sc = gamma[c] * grstd[g];
-    ss[(static_cast<size_t>(b) * C + c) * 2] = sc;
-    ss[(static_cast<size_t>(b) * C + c) * 2 + 1] = beta[c] + (tv - gmean[g]) * sc;
+    const float fmean = static_cast<float>(mean);
+    const float frstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    for (int c = g * cpg + lane; c < (g + 1) * cpg; c += 32) {
+      const float tv = addvec ? addvec[static_cast<size_t>(b) * addvec_ld + c] : 0.f;
+      const float sc = gamma[c] * frstd;
+      ss[(static_cast<size_t>(b) * C + c) * 2] = sc;
+      ss[(static_cast<size_t>(b) * C + c) * 2 + 1] = beta[c] + (tv - fmean) * sc;
+    }
   }
 }
 
@@ -158,18 +162,27 @@ static int group_norm_impl(const GroupNormArgs& a, cudaStream_t st) {
   if (CQ > 1024) return set_error("group_norm: C=%d too large", C);
   int R = std::max(1, std::min(8, 256 / CQ));
   const int threads = CQ * R;
-  if (!a.stats_prezeroed) MD_CUDA(cudaMemsetAsync(a.stats, 0, sizeof(float) * 2 * a.B * C, st));
-  // aim for several waves of CTAs (small CTAs: CQ*R threads)
-  const int target_ctas = num_sms() * (threads <= 128 ? 16 : 8);
-  int rows_per_cta = std::max(R * 4, static_cast<int>((static_cast<long long>(a.rows) * a.B + target_ctas - 1) / target_ctas));
-  rows_per_cta = std::min(rows_per_cta, a.rows);
-  dim3 grid((a.rows + rows_per_cta - 1) / rows_per_cta, a.B);
-  colstats_kernel<T0, T1><<<grid, threads, threads * 8 * sizeof(float), st>>>(
-      static_cast<const T0*>(a.x0), a.C0, static_cast<const T1*>(a.x1), a.C1, a.stats, a.rows, rows_per_cta, R);
-  MD_CHECK(check_launch("colstats"));
-  gn_finalize_kernel<<<a.B, 256, 0, st>>>(a.stats, a.gamma, a.beta, a.addvec, a.addvec_ld, a.scale_shift, C, a.groups,
-                                         static_cast<float>(a.rows), a.eps);
+  float* st0 = const_cast<float*>(a.stats0);
+  float* st1 = const_cast<float*>(a.stats1);
+  int c0 = a.C0, c1 = a.C1, zero_after = 0;
+  if (!a.stats0) {  // no statistics from the producers: column pass into the scratch buffer
+    if (!a.stats_prezeroed) MD_CUDA(cudaMemsetAsync(a.stats, 0, sizeof(float) * 2 * a.B * C, st));
+    const int target_ctas = num_sms() * (threads <= 128 ? 16 : 8);
+    int rows_per_cta = std::max(R * 4, static_cast<int>((static_cast<long long>(a.rows) * a.B + target_ctas - 1) / target_ctas));
+    rows_per_cta = std::min(rows_per_cta, a.rows);
+    dim3 grid((a.rows + rows_per_cta - 1) / rows_per_cta, a.B);
+    colstats_kernel<T0, T1><<<grid, threads, threads * 8 * sizeof(float), st>>>(
+        static_cast<const T0*>(a.x0), a.C0, static_cast<const T1*>(a.x1), a.C1, a.stats, a.rows, rows_per_cta, R);
+    MD_CHECK(check_launch("colstats"));
+    st0 = a.stats; st1 = nullptr; c0 = C; c1 = 0; zero_after = 1;
+  } else if (a.C1 > 0 && !a.stats1) {
+    return set_error("group_norm: statistics for the second source are missing");
+  }
+  gn_finalize_kernel<<<a.B, std::min(1024, 32 * a.groups), 0, st>>>(st0, c0, st1, c1, zero_after, a.gamma, a.beta, a.addvec,
+                                                                    a.addvec_ld, a.scale_shift, a.groups,
+                                                                    static_cast<float>(a.rows), a.eps);
   MD_CHECK(check_launch("gn_finalize"));
+  if (!a.out) return 0;  // scale/shift only (consumer applies the affine itself)
   const size_t total4 = static_cast<size_t>(a.B) * a.rows * CQ;
   const int blocks = static_cast<int>(std::min<size_t>((total4 + 255) / 256, static_cast<size_t>(num_sms()) * 16));
   affine_act_kernel<T0, T1><<<blocks, 256, 0, st>>>(static_cast<const T0*>(a.x0), a.C0,

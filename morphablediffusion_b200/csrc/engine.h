@@ -52,7 +52,7 @@ struct STW {
 };
 struct DepthW {
   int dim = 0, inner = 0, ctx = 0, dhead = 0;
-  GemmW proj_in, proj_ctx, to_q, to_kv, to_out, conv1, conv2;
+  GemmW proj_in, proj_ctx, wqk, wov, conv1, conv2;  // wqk / wov: re-associated q.k and out.v products (attention.cu)
   NormW gn_in, gn_ctx, gn_o1, gn_o2;
 };
 struct UNetLayer {
@@ -138,8 +138,10 @@ void free_weights(Ctx& c);
 // unet.cu
 // x_in fp32 NHWC [B][H][W][8]; timesteps fp32 [B]; context fp32 [B][ctx_dim]; levels: bf16 channels-last frustum
 // volumes for the B samples {64@D,S,S ; 128 ; 256 ; 512}; eps_out fp32 NCHW [B][4][H][W].
+// n_ctx: the first n_ctx samples own a frustum volume in `levels`; samples n_ctx..B-1 are conditioned on an all-zero
+// volume (the CFG-unconditional half) and `levels` holds nothing for them.
 int unet_forward(Ctx& c, const float* x_in, const float* timesteps, const float* context, const bf16* const levels[4],
-                 int B, int S, int D, float* eps_out, cudaStream_t st);
+                 int B, int n_ctx, int S, int D, float* eps_out, cudaStream_t st);
 
 // volume.cu
 int bind_sample(Ctx& c, const float* K, const float* RT, const float* v_embed, const float* vertices,

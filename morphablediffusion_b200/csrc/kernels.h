@@ -18,8 +18,9 @@ struct GroupNormArgs {
   const float* addvec; int addvec_ld;    // optional per-sample vector added before normalising
   float* stats;                          // workspace [B][C][2]
   int stats_prezeroed;                   // 1: buffer is all-zero on entry (the finalize kernel re-zeroes it)
+  const float* stats0; const float* stats1;  // optional [B][C0][2] / [B][C1][2] produced by GEMM epilogues (skip the column pass)
   float* scale_shift;                    // workspace [B][C][2]
-  void* out;                             // bf16 [B][rows][C]
+  void* out;                             // bf16 [B][rows][C]; null = only produce scale_shift
   void* raw_out;                         // optional bf16 copy of the un-normalised input
   int act;
 };
@@ -48,8 +49,9 @@ int launch_cfg_ddim(const float* eps, float* x, float* eps_out, const float* noi
 // ---- attention.cu
 // Self-attention over tokens: qkv bf16 [B][S][3*C] (q | k | v, head h at columns h*dh), out bf16 [B][S][C].
 int launch_self_attention(const void* qkv, void* out, int B, int S, int heads, int dh, cudaStream_t st);
-// Depth attention: q bf16 [B][HW][inner], kv bf16 [B][D][HW][2*inner] (k | v), out bf16 [B][HW][inner].
-int launch_depth_attention(const void* q, const void* kv, void* out, int B, int D, int HW, int heads, int dh,
-                           cudaStream_t st);
+// Re-associated depth attention (see attention.cu): qp bf16 [T][HW][4*ctx], c1 bf16 [T][D][HW][ctx] (pre-norm),
+// ss fp32 [T][ctx][2] GroupNorm scale/shift, beta fp32 [ctx]; cbar bf16 [B][HW][4*ctx] (samples >= T: zero volume).
+int launch_depth_attention(const void* qp, const void* c1, const float* ss, const float* beta, void* cbar, int T, int B,
+                           int D, int HW, int ctx, cudaStream_t st);
 
 }  // namespace md

@@ -138,11 +138,11 @@ static int denoise_step_impl(Ctx& c, float* x_local, const float* x_input, const
     const int T = std::min(chunk, sb.n_local - lv0);
     const int B = (cfg ? 2 : 1) * T;
     bf16* levels[4];
-    MD_CHECK(frustum_levels(c, vol, lv0, T, t_embed, B, levels, st));
+    MD_CHECK(frustum_levels(c, vol, lv0, T, t_embed, T, levels, st));
     MD_CHECK(launch_unet_input(x_local + static_cast<size_t>(lv0) * 4 * HW, x_input, 0, x_in, T, HW, cfg, st));
     make_context_kernel<<<(B * mc.context_dim + 255) / 256, 256, 0, st>>>(clip, ctxv, T, B, mc.context_dim);
     MD_CHECK(check_launch("make_context"));
-    MD_CHECK(unet_forward(c, x_in, d_t, ctxv, levels, B, S, D, eps_all, st));
+    MD_CHECK(unet_forward(c, x_in, d_t, ctxv, levels, B, T, S, D, eps_all, st));
     const int add_noise = (index != 0) ? 1 : 0;
     MD_CHECK(launch_cfg_ddim(eps_all, x_local + static_cast<size_t>(lv0) * 4 * HW,
                              eps_out ? eps_out + static_cast<size_t>(lv0) * 4 * HW : nullptr,
@@ -328,7 +328,7 @@ int md_unet_forward(md_ctx* ctx, const float* x, const float* timesteps_host, co
                                                static_cast<size_t>(S) * S);
     MD_CHECK(check_launch("nchw_to_nhwc"));
   }
-  return unet_forward(c, x_in, d_t, context, levels, B, S, D, out, st);
+  return unet_forward(c, x_in, d_t, context, levels, B, B, S, D, out, st);
 }
 
 int md_denoise_step(md_ctx* ctx, float* x_local, const float* x_input, const float* clip_embed, int index,
@@ -368,8 +368,9 @@ int md_op_self_attention(const void* qkv, void* out, int B, int S, int heads, in
   return launch_self_attention(qkv, out, B, S, heads, dh, static_cast<cudaStream_t>(stream));
 }
 
-int md_op_depth_attention(const void* q, const void* kv, void* out, int B, int D, int HW, int dh, void* stream) {
-  return launch_depth_attention(q, kv, out, B, D, HW, 4, dh, static_cast<cudaStream_t>(stream));
+int md_op_depth_attention(const void* qp, const void* c1, const float* ss, const float* beta, void* cbar, int T, int B,
+                          int D, int HW, int ctx, void* stream) {
+  return launch_depth_attention(qp, c1, ss, beta, cbar, T, B, D, HW, ctx, static_cast<cudaStream_t>(stream));
 }
 
 int md_op_cfg_ddim(md_ctx* ctx, const float* eps, float* x, float* eps_out, const float* noise, int T, int n_per_view,

@@ -1,6 +1,8 @@
 // Host orchestration of DepthWiseAttention.forward (ldm/models/diffusion/attention.py:117-138) on the kernels of
 // this library.  Layout: every activation is channels-last; the UNet residual stream `h` is fp32, GEMM operands are
-// bf16 produced by the fused GroupNorm/LayerNorm kernels.
+// bf16 produced by the fused GroupNorm/LayerNorm kernels.  GroupNorm statistics are accumulated by the epilogue of
+// the GEMM that produces the tensor (per-(sample, channel) sum / sum of squares), so a GroupNorm costs one tiny
+// finalize kernel plus one normalise+activate pass.
 #include "engine.h"
 
 namespace md {
@@ -10,12 +12,29 @@ namespace {
 struct Fwd {
   Ctx& c;
   cudaStream_t st;
-  int B;               // samples in this UNet call
+  int B;                 // samples in this UNet call
+  int n_ctx;             // leading samples that own a frustum volume
   const float* emb_all;  // [B][emb_total] per-ResBlock time-embedding projections
   const float* v2_all;   // [B][v2_total] attn2 output vectors of every transformer block
-  int rc = 0;
+  // statistics pool: one [B][C][2] slab per tensor that feeds a GroupNorm, zeroed once per forward
+  float* spool = nullptr;
+  size_t spool_cap = 0, spool_off = 0;
+  std::unordered_map<const void*, float*> stats_of;
 
   Arena& A() { return c.arena; }
+
+  float* new_stats(const void* tensor, int nb, int C) {
+    const size_t n = static_cast<size_t>(nb) * C * 2;
+    if (spool_off + n > spool_cap) return nullptr;
+    float* p = spool + spool_off;
+    spool_off += n;
+    stats_of[tensor] = p;
+    return p;
+  }
+  const float* find_stats(const void* tensor) const {
+    auto it = stats_of.find(tensor);
+    return it == stats_of.end() ? nullptr : it->second;
+  }
 
   static void taps2d(md_conv_gemm_args& a) {
     a.ntaps = 9;
@@ -25,41 +44,59 @@ struct Fwd {
       }
   }
 
-  // conv3x3 (pad 1) or 1x1 on a bf16 NHWC tensor
-  int conv(const bf16* a_in, int H, int W, const GemmW& w, const float* rowvec, int rowvec_ld, const float* res_f32,
-           float* out_f32, bf16* out_bf16, int act = ACT_NONE) {
+  // conv3x3 (pad 1) or 1x1 on a bf16 NHWC tensor of `nb` samples; `stats` = accumulate GroupNorm statistics of the
+  // result (only possible when a warp's 32 output rows stay inside one sample)
+  int conv(const bf16* a_in, int nb, int H, int W, const GemmW& w, const float* rowvec, int rowvec_ld,
+           const float* res_f32, float* out_f32, bf16* out_bf16, bool stats, int act = ACT_NONE) {
     md_conv_gemm_args a;
     memset(&a, 0, sizeof(a));
-    a.A = a_in; a.B = B; a.D = 1; a.H = H; a.W = W; a.Cin = w.K; a.Wt = w.w; a.N = w.N;
+    a.A = a_in; a.B = nb; a.D = 1; a.H = H; a.W = W; a.Cin = w.K; a.Wt = w.w; a.N = w.N;
     if (w.taps == 9) taps2d(a);
     else { a.ntaps = 1; }
     a.bias = w.bias; a.rowvec = rowvec; a.rowvec_ld = rowvec_ld; a.res_f32 = res_f32;
     a.out_f32 = out_f32; a.out_bf16 = out_bf16; a.act = act;
+    if (stats && H * W >= 32) {
+      const void* key = out_f32 ? static_cast<const void*>(out_f32) : static_cast<const void*>(out_bf16);
+      a.col_stats = new_stats(key, nb, w.N);
+      if (!a.col_stats) return set_error("statistics pool exhausted");
+    }
     return launch_conv_gemm(a, st);
   }
-  // plain GEMM over rows = B*H*W tokens
-  int gemm(const bf16* a_in, size_t rows_per_sample, const GemmW& w, const float* res_f32, float* out_f32, bf16* out_bf16,
-           int act = ACT_NONE) {
+  // plain GEMM over rows = nb * rows_per_sample tokens
+  int gemm(const bf16* a_in, int nb, size_t rows_per_sample, const GemmW& w, const float* res_f32, float* out_f32,
+           bf16* out_bf16, bool stats, int act = ACT_NONE) {
     md_conv_gemm_args a;
     memset(&a, 0, sizeof(a));
-    a.A = a_in; a.B = B; a.D = 1; a.H = 1; a.W = static_cast<int>(rows_per_sample); a.Cin = w.K; a.Wt = w.w; a.N = w.N;
+    a.A = a_in; a.B = nb; a.D = 1; a.H = 1; a.W = static_cast<int>(rows_per_sample); a.Cin = w.K; a.Wt = w.w; a.N = w.N;
     a.ntaps = 1;
     a.bias = w.bias; a.res_f32 = res_f32; a.out_f32 = out_f32; a.out_bf16 = out_bf16; a.act = act;
+    if (stats && rows_per_sample >= 32 && rows_per_sample % 32 == 0) {
+      const void* key = out_f32 ? static_cast<const void*>(out_f32) : static_cast<const void*>(out_bf16);
+      a.col_stats = new_stats(key, nb, w.N);
+      if (!a.col_stats) return set_error("statistics pool exhausted");
+    }
     return launch_conv_gemm(a, st);
   }
 
-  int gn(const void* x0, int C0, bool bf0, const void* x1, int C1, int rows, int groups, float eps, const NormW& n,
-         int act, bf16* out, bf16* raw, int Bn = -1) {
+  // GroupNorm (+activation) of (x0 | x1) -> bf16.  out == nullptr: only the per-(sample, channel) scale/shift.
+  int gn(const void* x0, int C0, bool bf0, const void* x1, int C1, int nb, int rows, int groups, float eps,
+         const NormW& n, int act, bf16* out, bf16* raw, float** ss_out = nullptr) {
     const int C = C0 + C1;
-    const int nb = Bn < 0 ? B : Bn;
     GroupNormArgs g;
     memset(&g, 0, sizeof(g));
     g.x0 = x0; g.C0 = C0; g.x0_bf16 = bf0; g.x1 = x1; g.C1 = C1; g.x1_bf16 = bf0;
     g.B = nb; g.rows = rows; g.groups = groups; g.eps = eps; g.gamma = n.g; g.beta = n.b;
-    if (static_cast<size_t>(nb) * C * 2 > c.gn_stats_floats) return set_error("group norm statistics scratch too small");
-    g.stats = c.gn_stats; g.stats_prezeroed = 1;
+    const float* s0 = find_stats(x0);
+    const float* s1 = C1 ? find_stats(x1) : nullptr;
+    if (s0 && (!C1 || s1)) {
+      g.stats0 = s0; g.stats1 = s1;
+    } else {
+      if (static_cast<size_t>(nb) * C * 2 > c.gn_stats_floats) return set_error("group norm statistics scratch too small");
+      g.stats = c.gn_stats; g.stats_prezeroed = 1;
+    }
     g.scale_shift = A().get<float>(static_cast<size_t>(nb) * C * 2);
     if (!g.scale_shift) return set_error("workspace exhausted (group norm)");
+    if (ss_out) *ss_out = g.scale_shift;
     g.out = out; g.raw_out = raw; g.act = act;
     return launch_group_norm(g, st);
   }
@@ -74,17 +111,17 @@ struct Fwd {
     bf16* a2 = A().get<bf16>(rows * r.cout);
     float* skip = r.has_skip ? A().get<float>(rows * r.cout) : nullptr;
     if (A().failed) return set_error("workspace exhausted (res block)");
-    MD_CHECK(gn(x0, C0, false, x1, C1, H * W, 32, 1e-5f, r.n1, ACT_SILU, a1, raw));
-    MD_CHECK(conv(a1, H, W, r.c1, emb_all + r.emb_off, c.unet.emb_total, nullptr, h1, nullptr));
-    MD_CHECK(gn(h1, r.cout, false, nullptr, 0, H * W, 32, 1e-5f, r.n2, ACT_SILU, a2, nullptr));
+    MD_CHECK(gn(x0, C0, false, x1, C1, B, H * W, 32, 1e-5f, r.n1, ACT_SILU, a1, raw));
+    MD_CHECK(conv(a1, B, H, W, r.c1, emb_all + r.emb_off, c.unet.emb_total, nullptr, h1, nullptr, true));
+    MD_CHECK(gn(h1, r.cout, false, nullptr, 0, B, H * W, 32, 1e-5f, r.n2, ACT_SILU, a2, nullptr));
     const float* resid = x0;
     if (r.has_skip) {
-      MD_CHECK(conv(raw, H, W, r.skip, nullptr, 0, nullptr, skip, nullptr));
+      MD_CHECK(conv(raw, B, H, W, r.skip, nullptr, 0, nullptr, skip, nullptr, false));
       resid = skip;
     } else if (C1 != 0) {
       return set_error("res block: identity skip with concatenated input");
     }
-    MD_CHECK(conv(a2, H, W, r.c2, nullptr, 0, resid, out, nullptr));
+    MD_CHECK(conv(a2, B, H, W, r.c2, nullptr, 0, resid, out, nullptr, true));
     A().release(m);
     return 0;
   }
@@ -103,57 +140,58 @@ struct Fwd {
     bf16* ff = A().get<bf16>(rows * 4 * C);
     bf16* xb = A().get<bf16>(rows * C);
     if (A().failed) return set_error("workspace exhausted (spatial transformer)");
-    MD_CHECK(gn(x_in, C, false, nullptr, 0, static_cast<int>(S), 32, 1e-6f, s.norm, ACT_NONE, a, nullptr));
-    MD_CHECK(gemm(a, S, s.proj_in, nullptr, x, nullptr));
+    MD_CHECK(gn(x_in, C, false, nullptr, 0, B, static_cast<int>(S), 32, 1e-6f, s.norm, ACT_NONE, a, nullptr));
+    MD_CHECK(gemm(a, B, S, s.proj_in, nullptr, x, nullptr, false));
     // attn1 (self-attention)
     MD_CHECK(launch_layer_norm(x, nullptr, 0, s.ln1.g, s.ln1.b, ln, rows, static_cast<int>(S), C, 1e-5f, st));
-    MD_CHECK(gemm(ln, S, s.qkv, nullptr, nullptr, qkv));
+    MD_CHECK(gemm(ln, B, S, s.qkv, nullptr, nullptr, qkv, false));
     MD_CHECK(launch_self_attention(qkv, att, B, static_cast<int>(S), s.heads, C / s.heads, st));
-    MD_CHECK(gemm(att, S, s.o1, x, x, nullptr));
+    MD_CHECK(gemm(att, B, S, s.o1, x, x, nullptr, false));
     // attn2: one context token => softmax == 1 => attn2(x) = to_out(to_v(ctx)) for every query (precomputed per
     // forward in v2_all).  x += v2[b]; then norm3 -> GEGLU feed-forward
     MD_CHECK(launch_layer_norm(x, v2_all + s.v2_off, c.unet.v2_total, s.ln3.g, s.ln3.b, ln, rows, static_cast<int>(S), C,
                                1e-5f, st));
-    MD_CHECK(gemm(ln, S, s.ff1, nullptr, nullptr, ff, ACT_GEGLU));
-    MD_CHECK(gemm(ff, S, s.ff2, x, nullptr, xb));
-    MD_CHECK(gemm(xb, S, s.proj_out, x_in, out, nullptr));
+    MD_CHECK(gemm(ln, B, S, s.ff1, nullptr, nullptr, ff, false, ACT_GEGLU));
+    MD_CHECK(gemm(ff, B, S, s.ff2, x, nullptr, xb, false));
+    MD_CHECK(gemm(xb, B, S, s.proj_out, x_in, out, nullptr, true));
     A().release(m);
     return 0;
   }
 
-  // DepthTransformer._forward + DepthAttention.forward (ldm/models/diffusion/attention.py:78-84,26-47)
+  // DepthTransformer._forward + DepthAttention.forward (ldm/models/diffusion/attention.py:78-84,26-47), with the
+  // attention re-associated (attention.cu) and the zero-volume samples (n_ctx..B-1) short-circuited.
   int depth_transformer(const DepthW& d, const float* x_in, int H, int W, const bf16* ctx, int D, float* out) {
     const size_t S = static_cast<size_t>(H) * W;
     const size_t rows = static_cast<size_t>(B) * S;
-    const size_t crows = rows * D;
+    const size_t crows = static_cast<size_t>(n_ctx) * S * D;
     const size_t m = A().mark();
     bf16* xb = A().get<bf16>(rows * d.dim);
     float* y = A().get<float>(rows * d.inner);
     bf16* xq = A().get<bf16>(rows * d.inner);
-    bf16* q = A().get<bf16>(rows * d.inner);
+    bf16* qp = A().get<bf16>(static_cast<size_t>(n_ctx) * S * 4 * d.ctx);
     bf16* c1 = A().get<bf16>(crows * d.ctx);
-    bf16* c2 = A().get<bf16>(crows * d.ctx);
-    bf16* kv = A().get<bf16>(crows * 2 * d.inner);
-    bf16* att = A().get<bf16>(rows * d.inner);
+    bf16* cbar = A().get<bf16>(rows * 4 * d.ctx);
     float* y2 = A().get<float>(rows * d.inner);
     bf16* a1 = A().get<bf16>(rows * d.inner);
     float* y3 = A().get<float>(rows * d.inner);
     bf16* a2 = A().get<bf16>(rows * d.inner);
     if (A().failed) return set_error("workspace exhausted (depth transformer)");
     MD_CHECK(launch_cast_bf16(x_in, xb, rows * d.dim, st));
-    MD_CHECK(gemm(xb, S, d.proj_in, nullptr, y, nullptr));
-    MD_CHECK(gn(y, d.inner, false, nullptr, 0, static_cast<int>(S), 8, 1e-5f, d.gn_in, ACT_SILU, xq, nullptr));
-    MD_CHECK(gemm(xq, S, d.to_q, nullptr, nullptr, q));
-    // context branch
-    MD_CHECK(gemm(ctx, S * D, d.proj_ctx, nullptr, nullptr, c1));
-    MD_CHECK(gn(c1, d.ctx, true, nullptr, 0, static_cast<int>(S * D), 8, 1e-5f, d.gn_ctx, ACT_RELU, c2, nullptr));
-    MD_CHECK(gemm(c2, S * D, d.to_kv, nullptr, nullptr, kv));
-    MD_CHECK(launch_depth_attention(q, kv, att, B, D, static_cast<int>(S), 4, d.dhead, st));
-    MD_CHECK(gemm(att, S, d.to_out, nullptr, y2, nullptr));
-    MD_CHECK(gn(y2, d.inner, false, nullptr, 0, static_cast<int>(S), 8, 1e-5f, d.gn_o1, ACT_RELU, a1, nullptr));
-    MD_CHECK(conv(a1, H, W, d.conv1, nullptr, 0, nullptr, y3, nullptr));
-    MD_CHECK(gn(y3, d.inner, false, nullptr, 0, static_cast<int>(S), 8, 1e-5f, d.gn_o2, ACT_RELU, a2, nullptr));
-    MD_CHECK(conv(a2, H, W, d.conv2, nullptr, 0, x_in, out, nullptr));
+    MD_CHECK(gemm(xb, B, S, d.proj_in, nullptr, y, nullptr, true));
+    MD_CHECK(gn(y, d.inner, false, nullptr, 0, B, static_cast<int>(S), 8, 1e-5f, d.gn_in, ACT_SILU, xq, nullptr));
+    // queries mapped into context space (only the samples that own a volume)
+    MD_CHECK(gemm(xq, n_ctx, S, d.wqk, nullptr, nullptr, qp, false));
+    // context branch: proj_context conv -> GroupNorm statistics; the normalisation + ReLU is applied on read
+    float* ss_ctx = nullptr;
+    MD_CHECK(gemm(ctx, n_ctx, S * D, d.proj_ctx, nullptr, nullptr, c1, true));
+    MD_CHECK(gn(c1, d.ctx, true, nullptr, 0, n_ctx, static_cast<int>(S * D), 8, 1e-5f, d.gn_ctx, ACT_RELU, nullptr, nullptr,
+                &ss_ctx));
+    MD_CHECK(launch_depth_attention(qp, c1, ss_ctx, d.gn_ctx.b, cbar, n_ctx, B, D, static_cast<int>(S), d.ctx, st));
+    MD_CHECK(gemm(cbar, B, S, d.wov, nullptr, y2, nullptr, true));
+    MD_CHECK(gn(y2, d.inner, false, nullptr, 0, B, static_cast<int>(S), 8, 1e-5f, d.gn_o1, ACT_RELU, a1, nullptr));
+    MD_CHECK(conv(a1, B, H, W, d.conv1, nullptr, 0, nullptr, y3, nullptr, true));
+    MD_CHECK(gn(y3, d.inner, false, nullptr, 0, B, static_cast<int>(S), 8, 1e-5f, d.gn_o2, ACT_RELU, a2, nullptr));
+    MD_CHECK(conv(a2, B, H, W, d.conv2, nullptr, 0, x_in, out, nullptr, true));
     A().release(m);
     return 0;
   }
@@ -166,11 +204,9 @@ struct Fwd {
     bf16* patches = A().get<bf16>(orows * 9 * C);
     if (A().failed) return set_error("workspace exhausted (downsample)");
     MD_CHECK(launch_gather_s2(x, 0, patches, B, 1, H, W, C, 1, st));
-    md_conv_gemm_args a;
-    memset(&a, 0, sizeof(a));
-    a.A = patches; a.B = B; a.D = 1; a.H = 1; a.W = OH * OW; a.Cin = 9 * C; a.Wt = w.w; a.N = w.N; a.ntaps = 1;
-    a.bias = w.bias; a.out_f32 = out;
-    MD_CHECK(launch_conv_gemm(a, st));
+    GemmW g = w;
+    g.K = 9 * C; g.taps = 1;
+    MD_CHECK(gemm(patches, B, static_cast<size_t>(OH) * OW, g, nullptr, out, nullptr, true));
     A().release(m);
     return 0;
   }
@@ -181,7 +217,7 @@ struct Fwd {
     bf16* up = A().get<bf16>(orows * C);
     if (A().failed) return set_error("workspace exhausted (upsample)");
     MD_CHECK(launch_upsample2x(x, up, B, H, W, C, st));
-    MD_CHECK(conv(up, 2 * H, 2 * W, w, nullptr, 0, nullptr, out, nullptr));
+    MD_CHECK(conv(up, B, 2 * H, 2 * W, w, nullptr, 0, nullptr, out, nullptr, true));
     A().release(m);
     return 0;
   }
@@ -190,8 +226,9 @@ struct Fwd {
 }  // namespace
 
 int unet_forward(Ctx& c, const float* x_in, const float* timesteps, const float* context, const bf16* const levels[4],
-                 int B, int S, int D, float* eps_out, cudaStream_t st) {
+                 int B, int n_ctx, int S, int D, float* eps_out, cudaStream_t st) {
   if (!c.weights_loaded) return set_error("unet_forward: weights not loaded");
+  if (n_ctx < 1 || n_ctx > B) return set_error("unet_forward: bad n_ctx=%d (B=%d)", n_ctx, B);
   const UNetW& u = c.unet;
   Arena& A = c.arena;
   const size_t m0 = A.mark();
@@ -206,7 +243,11 @@ int unet_forward(Ctx& c, const float* x_in, const float* timesteps, const float*
   bf16* ctx_b = A.get<bf16>(static_cast<size_t>(B) * u.ctx_dim);
   float* emb_all = A.get<float>(static_cast<size_t>(B) * u.emb_total);
   float* v2_all = A.get<float>(static_cast<size_t>(B) * u.v2_total);
+  // statistics pool: ~110 GroupNorm inputs of at most [B][1280][2]
+  const size_t spool_floats = static_cast<size_t>(B) * 2 * 96 * 1024;
+  float* spool = A.get<float>(spool_floats);
   if (A.failed) return set_error("workspace exhausted (unet embeddings)");
+  MD_CUDA(cudaMemsetAsync(spool, 0, spool_floats * sizeof(float), st));
   MD_CHECK(launch_timestep_embedding(timesteps, temb, B, mch, st));
   MD_CHECK(launch_small_linear(temb, mch, u.te0_w, u.te0_b, e1, u.emb_dim, B, mch, u.emb_dim, ACT_NONE, ACT_SILU, 0, st));
   MD_CHECK(launch_small_linear(e1, u.emb_dim, u.te2_w, u.te2_b, emb, u.emb_dim, B, u.emb_dim, u.emb_dim, ACT_NONE, ACT_SILU, 0, st));
@@ -222,7 +263,8 @@ int unet_forward(Ctx& c, const float* x_in, const float* timesteps, const float*
     MD_CHECK(launch_conv_gemm(a, st));
   }
 
-  Fwd f{c, st, B, emb_all, v2_all};
+  Fwd f{c, st, B, n_ctx, emb_all, v2_all};
+  f.spool = spool; f.spool_cap = spool_floats;
 
   struct Skip { float* p; int C, H; };
   std::vector<Skip> hs;
@@ -312,7 +354,7 @@ int unet_forward(Ctx& c, const float* x_in, const float* timesteps, const float*
   // out: GN32 + SiLU + conv3x3 320 -> 4
   bf16* ao = A.get<bf16>(static_cast<size_t>(B) * H * H * ch);
   if (A.failed) return set_error("workspace exhausted (unet)");
-  MD_CHECK(f.gn(h, ch, false, nullptr, 0, H * H, 32, 1e-5f, u.out_norm, ACT_SILU, ao, nullptr));
+  MD_CHECK(f.gn(h, ch, false, nullptr, 0, B, H * H, 32, 1e-5f, u.out_norm, ACT_SILU, ao, nullptr));
   MD_CHECK(launch_conv3x3_out(ao, u.out_w, u.out_b, eps_out, B, H, H, ch, u.out_channels, st));
   A.release(m0);
   return 0;

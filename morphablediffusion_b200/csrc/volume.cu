@@ -371,19 +371,28 @@ int frustum_levels(Ctx& c, const float* vol, int lv0, int T, const float* t_embe
       a.tap[t][0] = kx - 1; a.tap[t][1] = ky - 1; a.tap[t][2] = kz - 1;
     }
   };
-  auto conv3d = [&](const bf16* in, int d, int s, const GemmW& w, bf16* out) {
+  // GroupNorm statistics of every tensor that feeds a FrustumTV(Up)Block are accumulated by the producing GEMM
+  const int stat_ch = vd[0] + 2 * vd[1] + 2 * vd[2] + 2 * vd[3] + vd[2] + vd[1];
+  float* fpool = A.get<float>(static_cast<size_t>(T) * stat_ch * 2);
+  if (A.failed) return set_error("workspace exhausted (frustum statistics)");
+  MD_CUDA(cudaMemsetAsync(fpool, 0, static_cast<size_t>(T) * stat_ch * 2 * sizeof(float), st));
+  size_t fpool_off = 0;
+  auto new_stats = [&](int C) {
+    float* p = fpool + fpool_off;
+    fpool_off += static_cast<size_t>(T) * C * 2;
+    return p;
+  };
+  auto conv3d = [&](const bf16* in, int d, int s, const GemmW& w, bf16* out, float* stats) {
     md_conv_gemm_args a;
     memset(&a, 0, sizeof(a));
     a.A = in; a.B = T; a.D = d; a.H = s; a.W = s; a.Cin = w.K; a.Wt = w.w; a.N = w.N;
     taps3d(a);
-    a.bias = w.bias; a.out_bf16 = out;
+    a.bias = w.bias; a.out_bf16 = out; a.col_stats = stats;
     return launch_conv_gemm(a, st);
   };
   // x + t_conv(t) + v_conv(v) -> GN(8) -> SiLU  (network.py:285-311)
-  auto norm_act = [&](const FrBlockW& b, const bf16* x, size_t rows, bf16* out) {
+  auto norm_act = [&](const FrBlockW& b, const bf16* x, const float* xstats, size_t rows, bf16* out) {
     float* tv = A.get<float>(static_cast<size_t>(T) * b.cin);
-    if (static_cast<size_t>(T) * b.cin * 2 > c.gn_stats_floats) return set_error("group norm statistics scratch too small");
-    float* stats = c.gn_stats;
     float* ss = A.get<float>(static_cast<size_t>(T) * b.cin * 2);
     if (A.failed) return set_error("workspace exhausted (frustum norm)");
     MD_CHECK(launch_small_linear(v_emb, vdm, b.v_w, b.v_b, tv, b.cin, T, vdm, b.cin, ACT_NONE, ACT_NONE, 0, st));
@@ -391,19 +400,19 @@ int frustum_levels(Ctx& c, const float* vol, int lv0, int T, const float* t_embe
     GroupNormArgs g;
     memset(&g, 0, sizeof(g));
     g.x0 = x; g.C0 = b.cin; g.x0_bf16 = 1; g.B = T; g.rows = static_cast<int>(rows); g.groups = 8; g.eps = 1e-5f;
-    g.gamma = b.gn.g; g.beta = b.gn.b; g.addvec = tv; g.addvec_ld = b.cin; g.stats = stats; g.stats_prezeroed = 1;
+    g.gamma = b.gn.g; g.beta = b.gn.b; g.addvec = tv; g.addvec_ld = b.cin; g.stats0 = xstats;
     g.scale_shift = ss;
     g.out = out; g.act = ACT_SILU;
     return launch_group_norm(g, st);
   };
-  auto block = [&](const FrBlockW& b, const bf16* x, int d, int s, bf16* out) {
+  auto block = [&](const FrBlockW& b, const bf16* x, const float* xstats, int d, int s, bf16* out, float* ostats) {
     const size_t rows = static_cast<size_t>(d) * s * s;
     const size_t mm = A.mark();
     bf16* a = A.get<bf16>(static_cast<size_t>(T) * rows * b.cin);
     if (A.failed) return set_error("workspace exhausted (frustum block)");
-    MD_CHECK(norm_act(b, x, rows, a));
+    MD_CHECK(norm_act(b, x, xstats, rows, a));
     if (b.stride == 1) {
-      MD_CHECK(conv3d(a, d, s, b.conv, out));
+      MD_CHECK(conv3d(a, d, s, b.conv, out, ostats));
     } else {
       const size_t orows = static_cast<size_t>(d / 2) * (s / 2) * (s / 2);
       bf16* patches = A.get<bf16>(static_cast<size_t>(T) * orows * 27 * b.cin);
@@ -412,19 +421,20 @@ int frustum_levels(Ctx& c, const float* vol, int lv0, int T, const float* t_embe
       md_conv_gemm_args g;
       memset(&g, 0, sizeof(g));
       g.A = patches; g.B = T; g.D = 1; g.H = 1; g.W = static_cast<int>(orows); g.Cin = 27 * b.cin; g.Wt = b.conv.w;
-      g.N = b.conv.N; g.ntaps = 1; g.bias = b.conv.bias; g.out_bf16 = out;
+      g.N = b.conv.N; g.ntaps = 1; g.bias = b.conv.bias; g.out_bf16 = out; g.col_stats = ostats;
       MD_CHECK(launch_conv_gemm(g, st));
     }
     A.release(mm);
     return 0;
   };
   // ConvTranspose3d(k3,s2,p1,op1) as 8 output-parity classes + skip add
-  auto up = [&](const FrBlockW& b, const bf16* x, int d, int s, const bf16* skip, bf16* out) {
+  auto up = [&](const FrBlockW& b, const bf16* x, const float* xstats, int d, int s, const bf16* skip, bf16* out,
+                float* ostats) {
     const size_t rows = static_cast<size_t>(d) * s * s;
     const size_t mm = A.mark();
     bf16* a = A.get<bf16>(static_cast<size_t>(T) * rows * b.cin);
     if (A.failed) return set_error("workspace exhausted (frustum up)");
-    MD_CHECK(norm_act(b, x, rows, a));
+    MD_CHECK(norm_act(b, x, xstats, rows, a));
     for (int cls = 0; cls < 8; ++cls) {
       const int pz = (cls >> 2) & 1, py = (cls >> 1) & 1, px = cls & 1;
       const GemmW& w = b.upc[cls];
@@ -443,7 +453,7 @@ int frustum_levels(Ctx& c, const float* vol, int lv0, int T, const float* t_embe
       g.OD = 2 * d; g.OH = 2 * s; g.OW = 2 * s;
       g.os[0] = g.os[1] = g.os[2] = 2;
       g.op[0] = px; g.op[1] = py; g.op[2] = pz;
-      g.bias = w.bias; g.res_bf16 = skip; g.out_bf16 = out;
+      g.bias = w.bias; g.res_bf16 = skip; g.out_bf16 = out; g.col_stats = ostats;
       MD_CHECK(launch_conv_gemm(g, st));
     }
     A.release(mm);
@@ -461,16 +471,19 @@ int frustum_levels(Ctx& c, const float* vol, int lv0, int T, const float* t_embe
   if (A.failed) return set_error("workspace exhausted (frustum net)");
   MD_CHECK(launch_frustum_gather(vol, sb.pts + static_cast<size_t>(lv0) * per_view * 3, V, fr_in,
                                  static_cast<size_t>(T) * per_view, st));
-  MD_CHECK(conv3d(fr_in, lD[0], lS[0], F.conv0, x0));
-  MD_CHECK(block(F.blk[0], x0, lD[0], lS[0], t1));          // conv1 (s2)
-  MD_CHECK(block(F.blk[1], t1, lD[1], lS[1], x1));          // conv2
-  MD_CHECK(block(F.blk[2], x1, lD[1], lS[1], t2));          // conv3 (s2)
-  MD_CHECK(block(F.blk[3], t2, lD[2], lS[2], x2));          // conv4
-  MD_CHECK(block(F.blk[4], x2, lD[2], lS[2], t3));          // conv5 (s2)
-  MD_CHECK(block(F.blk[5], t3, lD[3], lS[3], levels[3]));   // conv6 -> x3
-  MD_CHECK(up(F.blk[6], levels[3], lD[3], lS[3], x2, levels[2]));  // up0 + x2
-  MD_CHECK(up(F.blk[7], levels[2], lD[2], lS[2], x1, levels[1]));  // up1 + x1
-  MD_CHECK(up(F.blk[8], levels[1], lD[1], lS[1], x0, levels[0]));  // up2 + x0
+  float* s_x0 = new_stats(vd[0]); float* s_t1 = new_stats(vd[1]); float* s_x1 = new_stats(vd[1]);
+  float* s_t2 = new_stats(vd[2]); float* s_x2 = new_stats(vd[2]); float* s_t3 = new_stats(vd[3]);
+  float* s_l3 = new_stats(vd[3]); float* s_l2 = new_stats(vd[2]); float* s_l1 = new_stats(vd[1]);
+  MD_CHECK(conv3d(fr_in, lD[0], lS[0], F.conv0, x0, s_x0));
+  MD_CHECK(block(F.blk[0], x0, s_x0, lD[0], lS[0], t1, s_t1));          // conv1 (s2)
+  MD_CHECK(block(F.blk[1], t1, s_t1, lD[1], lS[1], x1, s_x1));          // conv2
+  MD_CHECK(block(F.blk[2], x1, s_x1, lD[1], lS[1], t2, s_t2));          // conv3 (s2)
+  MD_CHECK(block(F.blk[3], t2, s_t2, lD[2], lS[2], x2, s_x2));          // conv4
+  MD_CHECK(block(F.blk[4], x2, s_x2, lD[2], lS[2], t3, s_t3));          // conv5 (s2)
+  MD_CHECK(block(F.blk[5], t3, s_t3, lD[3], lS[3], levels[3], s_l3));   // conv6 -> x3
+  MD_CHECK(up(F.blk[6], levels[3], s_l3, lD[3], lS[3], x2, levels[2], s_l2));  // up0 + x2
+  MD_CHECK(up(F.blk[7], levels[2], s_l2, lD[2], lS[2], x1, levels[1], s_l1));  // up1 + x1
+  MD_CHECK(up(F.blk[8], levels[1], s_l1, lD[1], lS[1], x0, levels[0], nullptr));  // up2 + x0
   A.release(m);
   return 0;
 }

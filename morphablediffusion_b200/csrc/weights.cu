@@ -36,22 +36,25 @@ __global__ void permute_rows_f32_kernel(const float* __restrict__ src, float* __
   dst[n] = src[ns];
 }
 
-// C[M][N] (bf16, row stride ldc) = A[M][K] * B[K][N]   (fp32 inputs; load-time only)
-__global__ void matmul_f32_to_bf16_kernel(const float* __restrict__ A, const float* __restrict__ Bm,
-                                          __nv_bfloat16* __restrict__ Cm, int M, int N, int K) {
+// C[m][n] (bf16, row stride ldc) = scale * sum_k A(m,k) * B(k,n), A(m,k) = transA ? A[k*lda+m] : A[m*lda+k],
+// B(k,n) = B[k*ldb+n]   (fp32 inputs; load-time weight products only)
+__global__ void matmul_f32_to_bf16_kernel(const float* __restrict__ A, int lda, int transA, const float* __restrict__ Bm,
+                                          int ldb, __nv_bfloat16* __restrict__ Cm, int ldc, int M, int N, int K,
+                                          float scale) {
   __shared__ float sa[16][17], sb[16][17];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int row = blockIdx.y * 16 + ty, col = blockIdx.x * 16 + tx;
   float acc = 0.f;
   for (int k0 = 0; k0 < K; k0 += 16) {
-    sa[ty][tx] = (row < M && k0 + tx < K) ? A[static_cast<size_t>(row) * K + k0 + tx] : 0.f;
-    sb[ty][tx] = (col < N && k0 + ty < K) ? Bm[static_cast<size_t>(k0 + ty) * N + col] : 0.f;
+    const int ka = k0 + tx;
+    sa[ty][tx] = (row < M && ka < K) ? (transA ? A[static_cast<size_t>(ka) * lda + row] : A[static_cast<size_t>(row) * lda + ka]) : 0.f;
+    sb[ty][tx] = (col < N && k0 + ty < K) ? Bm[static_cast<size_t>(k0 + ty) * ldb + col] : 0.f;
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < 16; ++k) acc += sa[ty][k] * sb[k][tx];
     __syncthreads();
   }
-  if (row < M && col < N) Cm[static_cast<size_t>(row) * N + col] = __float2bfloat16(acc);
+  if (row < M && col < N) Cm[static_cast<size_t>(row) * ldc + col] = __float2bfloat16(acc * scale);
 }
 
 __global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n) {
@@ -202,9 +205,34 @@ struct Loader {
     d.gn_in = norm(p + "proj_in.1", d.inner);
     d.proj_ctx = gemm(p + "proj_context.0", ctx, ctx, 1, false);
     d.gn_ctx = norm(p + "proj_context.1", ctx);
-    d.to_q = gemm(p + "depth_attn.to_q", d.inner, d.inner, 1, false);
-    d.to_kv = gemm_fused({p + "depth_attn.to_k.weight", p + "depth_attn.to_v.weight"}, d.inner, ctx);
-    d.to_out = gemm(p + "depth_attn.to_out", d.inner, d.inner, 1, false);
+    // Re-associated depth attention (attention.cu): per head h
+    //   W_qk[h] = scale * W_k[h]^T W_q[h]  ([ctx][inner]),  W_ov[:, h] = W_out[:, h] W_v[h]  ([inner][ctx])
+    {
+      const NamedTensor* wq = find(p + "depth_attn.to_q.weight", static_cast<size_t>(d.inner) * d.inner);
+      const NamedTensor* wk = find(p + "depth_attn.to_k.weight", static_cast<size_t>(d.inner) * ctx);
+      const NamedTensor* wv = find(p + "depth_attn.to_v.weight", static_cast<size_t>(d.inner) * ctx);
+      const NamedTensor* wo = find(p + "depth_attn.to_out.weight", static_cast<size_t>(d.inner) * d.inner);
+      d.wqk.N = 4 * ctx; d.wqk.K = d.inner; d.wqk.taps = 1;
+      d.wqk.w = dalloc<bf16>(static_cast<size_t>(4) * ctx * d.inner);
+      d.wov.N = d.inner; d.wov.K = 4 * ctx; d.wov.taps = 1;
+      d.wov.w = dalloc<bf16>(static_cast<size_t>(4) * ctx * d.inner);
+      if (wq && wk && wv && wo && d.wqk.w && d.wov.w) {
+        const float scale = 1.f / sqrtf(static_cast<float>(dhead));
+        dim3 blk(16, 16);
+        for (int h = 0; h < 4; ++h) {
+          dim3 g1((d.inner + 15) / 16, (ctx + 15) / 16);
+          matmul_f32_to_bf16_kernel<<<g1, blk, 0, st>>>(wk->ptr + static_cast<size_t>(h) * dhead * ctx, ctx, 1,
+                                                        wq->ptr + static_cast<size_t>(h) * dhead * d.inner, d.inner,
+                                                        d.wqk.w + static_cast<size_t>(h) * ctx * d.inner, d.inner, ctx,
+                                                        d.inner, dhead, scale);
+          dim3 g2((ctx + 15) / 16, (d.inner + 15) / 16);
+          matmul_f32_to_bf16_kernel<<<g2, blk, 0, st>>>(wo->ptr + static_cast<size_t>(h) * dhead, d.inner, 0,
+                                                        wv->ptr + static_cast<size_t>(h) * dhead * ctx, ctx,
+                                                        d.wov.w + static_cast<size_t>(h) * ctx, 4 * ctx, d.inner, ctx,
+                                                        dhead, 1.f);
+        }
+      }
+    }
     d.gn_o1 = norm(p + "proj_out.0", d.inner);
     d.conv1 = gemm(p + "proj_out.2", d.inner, d.inner, 9, false);
     d.gn_o2 = norm(p + "proj_out.3", d.inner);
@@ -359,8 +387,9 @@ int load_all_weights(Ctx& c, const TensorMap& tm, cudaStream_t st) {
         const NamedTensor* bo = L.find(e.first + "to_out.0.bias", C);
         if (wv && wo && bo) {
           dim3 grid((u.ctx_dim + 15) / 16, (C + 15) / 16), blk(16, 16);
-          matmul_f32_to_bf16_kernel<<<grid, blk, 0, st>>>(wo->ptr, wv->ptr, u.v2_g.w + static_cast<size_t>(off) * u.ctx_dim,
-                                                          C, u.ctx_dim, C);
+          matmul_f32_to_bf16_kernel<<<grid, blk, 0, st>>>(wo->ptr, C, 0, wv->ptr, u.ctx_dim,
+                                                          u.v2_g.w + static_cast<size_t>(off) * u.ctx_dim, u.ctx_dim, C,
+                                                          u.ctx_dim, C, 1.f);
           cudaMemcpyAsync(vb + off, bo->ptr, sizeof(float) * C, cudaMemcpyDeviceToDevice, st);
         }
         off += C;

@@ -209,22 +209,56 @@ def test_self_attention(nat, B, S, heads, dh):
     assert rel(out, ref) < 1e-2
 
 
-@pytest.mark.parametrize("B,D,HW,dh", [(2, 48, 1024, 32), (2, 24, 256, 64), (3, 12, 64, 128), (2, 6, 16, 256)])
-def test_depth_attention(nat, B, D, HW, dh):
+@pytest.mark.parametrize("T,B,D,HW,ctx", [(2, 4, 48, 1024, 64), (2, 2, 24, 256, 128), (3, 6, 12, 64, 256), (1, 2, 6, 16, 512)])
+def test_depth_attention(nat, T, B, D, HW, ctx):
+    """Re-associated depth attention against DepthAttention.forward written out with explicit K and V
+    (ldm/models/diffusion/attention.py:26-47): same result, K/V never materialised, zero-volume samples short-cut."""
     torch.manual_seed(8)
+    dh = ctx // 2
     inner = 4 * dh
-    q = bf(torch.randn(B, HW, inner, device="cuda"))
-    kv = bf(torch.randn(B, D, HW, 2 * inner, device="cuda"))
-    out = torch.zeros(B, HW, inner, device="cuda", dtype=torch.bfloat16)
-    nat.check(nat.lib.md_op_depth_attention(q.data_ptr(), kv.data_ptr(), out.data_ptr(), B, D, HW, dh,
-                                            nat.cur_stream()), "depth_attn")
-    qf = q.float().view(B, HW, 4, dh)
-    k = kv[..., :inner].float().view(B, D, HW, 4, dh)
-    v = kv[..., inner:].float().view(B, D, HW, 4, dh)
-    sim = (qf.unsqueeze(1) * k).sum(-1) * dh ** -0.5  # B,D,HW,4
+    Wq, Wk = torch.randn(inner, inner, device="cuda") / inner ** 0.5, torch.randn(inner, ctx, device="cuda") / ctx ** 0.5
+    x = torch.randn(B, HW, inner, device="cuda")
+    c1 = bf(torch.randn(T, D, HW, ctx, device="cuda"))
+    gamma, beta = torch.randn(ctx, device="cuda"), torch.randn(ctx, device="cuda")
+    # GroupNorm(8) scale/shift of c1 per (sample, channel)
+    g = c1.float().view(T, D * HW, 8, ctx // 8)
+    mean = g.mean(dim=(1, 3), keepdim=True)
+    var = g.var(dim=(1, 3), keepdim=True, unbiased=False)
+    rstd = (var + 1e-5).rsqrt().expand(T, 1, 8, ctx // 8).reshape(T, ctx)
+    mean = mean.expand(T, 1, 8, ctx // 8).reshape(T, ctx)
+    scale = gamma * rstd
+    shift = beta - mean * scale
+    ss = torch.stack([scale, shift], -1).contiguous()
+    # qp = per-head W_k^T (W_q x) * dh^-0.5
+    q = (x[:T] @ Wq.t()).view(T, HW, 4, dh)
+    qp = torch.einsum("tphd,hdc->tphc", q, Wk.view(4, dh, ctx)) * dh ** -0.5
+    qp = bf(qp.reshape(T, HW, 4 * ctx)).contiguous()
+    out = torch.zeros(B, HW, 4 * ctx, device="cuda", dtype=torch.bfloat16)
+    nat.check(nat.lib.md_op_depth_attention(qp.data_ptr(), c1.data_ptr(), ss.data_ptr(), beta.data_ptr(), out.data_ptr(),
+                                            T, B, D, HW, ctx, nat.cur_stream()), "depth_attn")
+    c = torch.relu(c1.float() * scale[:, None, None, :] + shift[:, None, None, :])       # T,D,HW,ctx
+    sim = torch.einsum("tphc,tdpc->tdph", qp.float().view(T, HW, 4, ctx), c)               # T,D,HW,4
     attn = sim.softmax(dim=1)
-    ref = (v * attn.unsqueeze(-1)).sum(1).reshape(B, HW, inner)
-    assert rel(out, ref) < 1e-2
+    ref = torch.einsum("tdph,tdpc->tphc", attn, c).reshape(T, HW, 4 * ctx)
+    assert rel(out[:T], ref) < 1e-2
+    if B > T:
+        assert rel(out[T:], torch.relu(beta).repeat(4).expand(B - T, HW, 4 * ctx)) < 5e-3
+
+
+def test_gemm_fused_group_norm_statistics(nat):
+    """The epilogue's per-(sample, channel) sum / sum-of-squares equal a column reduction of the fp32 result."""
+    torch.manual_seed(10)
+    Bn, H, W, Cin, Cout = 3, 16, 16, 128, 320
+    x = bf(torch.randn(Bn, H, W, Cin, device="cuda"))
+    Wt = bf(torch.randn(Cout, 9 * Cin, device="cuda") / (9 * Cin) ** 0.5)
+    bias = torch.randn(Cout, device="cuda")
+    taps = [(kx - 1, ky - 1, 0) for ky in range(3) for kx in range(3)]
+    out = torch.zeros(Bn, H, W, Cout, device="cuda")
+    stats = torch.zeros(Bn, Cout, 2, device="cuda")
+    nat.conv_gemm(x, Wt, B=Bn, D=1, H=H, W=W, Cin=Cin, N=Cout, taps=taps, bias=bias, out_f32=out, col_stats=stats)
+    o = out.view(Bn, H * W, Cout)
+    assert rel(stats[..., 0], o.sum(1)) < 1e-4
+    assert rel(stats[..., 1], (o * o).sum(1)) < 1e-4
 
 
 def test_ddim_noise_is_shard_invariant(nat, engine4):
