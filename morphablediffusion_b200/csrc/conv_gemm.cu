@@ -139,6 +139,7 @@ int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
 
   const int total = p.m_tiles * p.n_tiles;
   const int grid = std::min(total, num_sms());
+  p.contig = (p.n_tiles == 1 && total > 2 * grid) ? 1 : 0;
   static const bool trace = getenv("MD_TRACE") != nullptr;
   if (trace)
     fprintf(stderr, "conv_gemm B=%d D=%d H=%d W=%d Cin=%d taps=%d N=%d BN=%d tiles=%dx%d act=%d f32=%d bf16=%d res=%d\n",

@@ -46,6 +46,7 @@ struct ConvGemmParams {
   float out_scale;  // multiplies the result before residual (1.0 default)
   float* col_stats; // optional [B][stats_ld][2]: per-(sample, channel) sum / sum of squares of the fp32 result
   int stats_ld;
+  int contig;       // contiguous tile run per CTA (see kernel)
 };
 
 __device__ __forceinline__ float act_silu(float x) { return x / (1.f + __expf(-x)); }
@@ -63,16 +64,41 @@ struct ConvGemmSmem {
   static constexpr int kTotal = kBarOffset + 256;
 };
 
+// Adds a warp's running GroupNorm partial sums to global memory: lanes l, l^8, l^16, l^24 own the same columns.
+template <int NCH>
+__device__ __forceinline__ void flush_col_stats(const ConvGemmParams& p, int lane, int sample, int n_out0, int n_limit,
+                                                int c_begin, int c_step, float (&st1)[NCH][4], float (&st2)[NCH][4]) {
+  const int prow = lane >> 3, pchunk = lane & 7;
+#pragma unroll
+  for (int k = 0; k < NCH; ++k) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      st1[k][e] += __shfl_xor_sync(0xffffffff, st1[k][e], 8);
+      st1[k][e] += __shfl_xor_sync(0xffffffff, st1[k][e], 16);
+      st2[k][e] += __shfl_xor_sync(0xffffffff, st2[k][e], 8);
+      st2[k][e] += __shfl_xor_sync(0xffffffff, st2[k][e], 16);
+    }
+    const int col = n_out0 + (c_begin + k * c_step) * 32 + pchunk * 4;
+    if (prow == 0 && sample >= 0 && col < n_limit) {
+      float* cs = p.col_stats + (static_cast<long long>(sample) * p.stats_ld + col) * 2;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { atomicAdd(cs + 2 * e, st1[k][e]); atomicAdd(cs + 2 * e + 1, st2[k][e]); }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { st1[k][e] = 0.f; st2[k][e] = 0.f; }
+  }
+}
+
 // Epilogue of one output tile for one warp (32 accumulator rows), specialised on the residual kind and on the
 // presence of a per-sample vector so that the inner loops are branch-free.
 //   phase 0: issue the chunk's global loads (per-sample vector, residual) in the coalesced phase-2 layout;
 //   phase 1 (row owner): TMEM -> registers, scale + bias (+ GEGLU), swizzled store into a private 32x32 staging tile;
 //   phase 2 (coalesced; one warp instruction = 4 rows x 128 B): + per-sample vector, activation, + residual,
 //            fp32 / bf16 stores, optional per-(sample, channel) sum / sum-of-squares for the next GroupNorm.
-template <int BN, int RES, bool RV>
+template <int BN, int RES, bool RV, int NCH>
 __device__ __forceinline__ void epilogue_tile(const ConvGemmParams& p, uint32_t taddr, float* stage, const float* bias_s,
-                                              int lane, int n_tile, const int4* rowinfo, int warp_sample, int c_begin,
-                                              int c_step) {
+                                              int lane, int n_tile, const int4* rowinfo, int c_begin, int c_step,
+                                              float (&st1)[NCH][4], float (&st2)[NCH][4]) {
   const int prow = lane >> 3;   // phase-2 row within a group of 4
   const int pchunk = lane & 7;  // phase-2 16-byte chunk within the 128-byte row
   const bool geglu = (p.act == ACT_GEGLU);
@@ -80,8 +106,9 @@ __device__ __forceinline__ void epilogue_tile(const ConvGemmParams& p, uint32_t 
   const int out_cols = geglu ? HALF : BN;
   const int n_limit = geglu ? p.N / 2 : p.N;
   const int n_out0 = n_tile * out_cols;
+  int ci = 0;
 #pragma unroll 1
-  for (int c = c_begin; c < out_cols / 32; c += c_step) {
+  for (int c = c_begin; c < out_cols / 32; c += c_step, ++ci) {
     const int col = n_out0 + c * 32 + pchunk * 4;
     const bool col_ok = col < n_limit;
     const int col_safe = col_ok ? col : 0;
@@ -171,18 +198,15 @@ __device__ __forceinline__ void epilogue_tile(const ConvGemmParams& p, uint32_t 
       }
     }
     if (p.col_stats) {
-      // lanes l, l^8, l^16, l^24 own the same columns; the host guarantees one sample per warp (warp_sample)
+      // running sums for this warp's ci-th chunk (flushed by the caller when the sample or the N tile changes)
+      {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        s1[e] += __shfl_xor_sync(0xffffffff, s1[e], 8);
-        s1[e] += __shfl_xor_sync(0xffffffff, s1[e], 16);
-        s2[e] += __shfl_xor_sync(0xffffffff, s2[e], 8);
-        s2[e] += __shfl_xor_sync(0xffffffff, s2[e], 16);
-      }
-      if (prow == 0 && warp_sample >= 0 && col_ok) {
-        float* cs = p.col_stats + (static_cast<long long>(warp_sample) * p.stats_ld + col) * 2;
+        for (int k = 0; k < NCH; ++k) {
+          if (k == ci) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) { atomicAdd(cs + 2 * e, s1[e]); atomicAdd(cs + 2 * e + 1, s2[e]); }
+            for (int e = 0; e < 4; ++e) { st1[k][e] += s1[e]; st2[k][e] += s2[e]; }
+          }
+        }
       }
     }
     __syncwarp();
@@ -229,12 +253,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   const int total_tiles = p.m_tiles * p.n_tiles;
   const int kblocks = p.ntaps * p.kblocks_per_tap;
+  // Tile schedule: interleaved (tile = cta + i*grid) or, for tall single-N-tile problems, one contiguous run per CTA
+  // (consecutive tiles then share a sample, which lets the epilogue keep GroupNorm partial sums in registers).
+  const int per_cta = (total_tiles + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  const int tile_begin = p.contig ? static_cast<int>(blockIdx.x) * per_cta : static_cast<int>(blockIdx.x);
+  const int tile_end = p.contig ? min(total_tiles, tile_begin + per_cta) : total_tiles;
+  const int tile_step = p.contig ? 1 : static_cast<int>(gridDim.x);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
         const int n_tile = tile % p.n_tiles;
         int m = tile / p.n_tiles;
         const int xb = m % p.nxb; m /= p.nxb;
@@ -264,7 +294,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BN);
       int it = 0;
       int lt = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+      for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++lt) {
         const int a = lt & 1;
         const uint32_t aph = (lt >> 1) & 1;
         mbar_wait(&tmem_empty[a], aph ^ 1);
@@ -302,8 +332,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int c_begin = (EPI_WARPS == 8) ? (ew >> 2) : 0;
     const int c_step = (EPI_WARPS == 8) ? 2 : 1;
     const int mode = (p.res_f32 ? 1 : (p.res_bf16 ? 2 : 0)) * 2 + (p.rowvec ? 1 : 0);
+    const int out_cols_t = (p.act == ACT_GEGLU) ? BN / 2 : BN;
+    const int n_limit_t = (p.act == ACT_GEGLU) ? p.N / 2 : p.N;
+    constexpr int NCH = (EPI_WARPS == 8) ? (BN / 32 + 1) / 2 : BN / 32;  // chunks one warp owns per tile
+    float st1[NCH][4], st2[NCH][4];
+#pragma unroll
+    for (int k = 0; k < NCH; ++k)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { st1[k][e] = 0.f; st2[k][e] = 0.f; }
+    int st_sample = -1, st_ntile = -1;
     int lt = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+    for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++lt) {
       const int a = lt & 1;
       const uint32_t aph = (lt >> 1) & 1;
       const int n_tile = tile % p.n_tiles;
@@ -330,23 +369,30 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       // sample of the warp's rows (fused GroupNorm statistics: the host guarantees one sample per warp there)
       const int warp_sample = __reduce_max_sync(0xffffffff, bv);
+      if (p.col_stats && (warp_sample != st_sample || n_tile != st_ntile)) {
+        if (st_sample >= 0)
+          flush_col_stats(p, lane, st_sample, st_ntile * out_cols_t, n_limit_t, c_begin, c_step, st1, st2);
+        st_sample = warp_sample; st_ntile = n_tile;
+      }
       __syncwarp();
 
       mbar_wait(&tmem_full[a], aph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * BN;
       switch (mode) {
-        case 0: epilogue_tile<BN, 0, false>(p, taddr, stage, bias_s, lane, n_tile, rowinfo, warp_sample, c_begin, c_step); break;
-        case 1: epilogue_tile<BN, 0, true>(p, taddr, stage, bias_s, lane, n_tile, rowinfo, warp_sample, c_begin, c_step); break;
-        case 2: epilogue_tile<BN, 1, false>(p, taddr, stage, bias_s, lane, n_tile, rowinfo, warp_sample, c_begin, c_step); break;
-        case 3: epilogue_tile<BN, 1, true>(p, taddr, stage, bias_s, lane, n_tile, rowinfo, warp_sample, c_begin, c_step); break;
-        case 4: epilogue_tile<BN, 2, false>(p, taddr, stage, bias_s, lane, n_tile, rowinfo, warp_sample, c_begin, c_step); break;
-        default: epilogue_tile<BN, 2, true>(p, taddr, stage, bias_s, lane, n_tile, rowinfo, warp_sample, c_begin, c_step); break;
+        case 0: epilogue_tile<BN, 0, false, NCH>(p, taddr, stage, bias_s, lane, n_tile, rowinfo, c_begin, c_step, st1, st2); break;
+        case 1: epilogue_tile<BN, 0, true, NCH>(p, taddr, stage, bias_s, lane, n_tile, rowinfo, c_begin, c_step, st1, st2); break;
+        case 2: epilogue_tile<BN, 1, false, NCH>(p, taddr, stage, bias_s, lane, n_tile, rowinfo, c_begin, c_step, st1, st2); break;
+        case 3: epilogue_tile<BN, 1, true, NCH>(p, taddr, stage, bias_s, lane, n_tile, rowinfo, c_begin, c_step, st1, st2); break;
+        case 4: epilogue_tile<BN, 2, false, NCH>(p, taddr, stage, bias_s, lane, n_tile, rowinfo, c_begin, c_step, st1, st2); break;
+        default: epilogue_tile<BN, 2, true, NCH>(p, taddr, stage, bias_s, lane, n_tile, rowinfo, c_begin, c_step, st1, st2); break;
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[a]);
     }
+    if (p.col_stats && st_sample >= 0)
+      flush_col_stats(p, lane, st_sample, st_ntile * out_cols_t, n_limit_t, c_begin, c_step, st1, st2);
   }
 
   tc_fence_before();
