@@ -95,7 +95,7 @@ __device__ __forceinline__ void flush_col_stats(const ConvGemmParams& p, int lan
 //   phase 1 (row owner): TMEM -> registers, scale + bias (+ GEGLU), swizzled store into a private 32x32 staging tile;
 //   phase 2 (coalesced; one warp instruction = 4 rows x 128 B): + per-sample vector, activation, + residual,
 //            fp32 / bf16 stores, optional per-(sample, channel) sum / sum-of-squares for the next GroupNorm.
-template <int BN, int RES, bool RV, int NCH>
+template <int BN, int RES, bool RV, int NCH, bool STATS>
 __device__ __forceinline__ void epilogue_tile(const ConvGemmParams& p, uint32_t taddr, float* stage, const float* bias_s,
                                               int lane, int n_tile, const int4* rowinfo, int c_begin, int c_step,
                                               float (&st1)[NCH][4], float (&st2)[NCH][4]) {
@@ -192,12 +192,12 @@ __device__ __forceinline__ void epilogue_tile(const ConvGemmParams& p, uint32_t 
         o2.y = *reinterpret_cast<uint32_t*>(&hi);
         *reinterpret_cast<uint2*>(p.out_bf16 + off) = o2;
       }
-      if (ok) {
+      if (STATS && ok) {
         s1[0] += v4.x; s1[1] += v4.y; s1[2] += v4.z; s1[3] += v4.w;
         s2[0] += v4.x * v4.x; s2[1] += v4.y * v4.y; s2[2] += v4.z * v4.z; s2[3] += v4.w * v4.w;
       }
     }
-    if (p.col_stats) {
+    if (STATS) {
       // running sums for this warp's ci-th chunk (flushed by the caller when the sample or the N tile changes)
       {
 #pragma unroll
@@ -211,6 +211,86 @@ __device__ __forceinline__ void epilogue_tile(const ConvGemmParams& p, uint32_t 
     }
     __syncwarp();
   }
+}
+
+// Epilogue warps: loop over this CTA's tiles (same schedule as the producer / MMA warps).
+template <int BN, int STAGES, int EPI_WARPS, bool STATS>
+__device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, uint8_t* smem, uint64_t* tmem_full,
+                                              uint64_t* tmem_empty, uint32_t tmem_base, int warp, int lane,
+                                              int tile_begin, int tile_end, int tile_step) {
+  using S = ConvGemmSmem<BN, STAGES, EPI_WARPS>;
+  // Warp w reads TMEM lane quarter (w & 3); with 8 epilogue warps the two warps of a quarter split the 32-column
+  // chunks of the tile between them (even / odd).
+  const int ew = warp - 2;
+  const int q = warp & 3;
+  const int r = q * 32 + lane;
+  float* stage = reinterpret_cast<float*>(smem + S::kStageOffset) + ew * 1024;
+  float* bias_s = reinterpret_cast<float*>(smem + S::kBiasOffset) + ew * BN;
+  int4* rowinfo = reinterpret_cast<int4*>(smem + S::kRowOffset) + ew * 32;
+  const int c_begin = (EPI_WARPS == 8) ? (ew >> 2) : 0;
+  const int c_step = (EPI_WARPS == 8) ? 2 : 1;
+  const int mode = (p.res_f32 ? 1 : (p.res_bf16 ? 2 : 0)) * 2 + (p.rowvec ? 1 : 0);
+  const int out_cols_t = (p.act == ACT_GEGLU) ? BN / 2 : BN;
+  const int n_limit_t = (p.act == ACT_GEGLU) ? p.N / 2 : p.N;
+  constexpr int NCH = (EPI_WARPS == 8) ? (BN / 32 + 1) / 2 : BN / 32;  // chunks one warp owns per tile
+  float st1[NCH][4], st2[NCH][4];
+#pragma unroll
+  for (int k = 0; k < NCH; ++k)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { st1[k][e] = 0.f; st2[k][e] = 0.f; }
+  int st_sample = -1, st_ntile = -1;
+  int lt = 0;
+  for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++lt) {
+    const int a = lt & 1;
+    const uint32_t aph = (lt >> 1) & 1;
+    const int n_tile = tile % p.n_tiles;
+    int m = tile / p.n_tiles;
+    const int xb = m % p.nxb; m /= p.nxb;
+    const int yb = m % p.nyb; m /= p.nyb;
+    const int zb = m % p.nzb; m /= p.nzb;
+    int rr = r;
+    const int ix = rr % p.bw; rr /= p.bw;
+    const int iy = rr % p.bh; rr /= p.bh;
+    const int iz = rr % p.bd; rr /= p.bd;
+    const int x = xb * p.bw + ix, y = yb * p.bh + iy, z = zb * p.bd + iz, b = m * p.bb + rr;
+    const bool valid = (x < p.W) && (y < p.H) && (z < p.D) && (b < p.B);
+    const long long orow =
+        (((static_cast<long long>(b) * p.OD + (z * p.osz + p.opz)) * p.OH + (y * p.osy + p.opy)) * p.OW +
+         (x * p.osx + p.opx)) * p.ldo;
+    const int bv = valid ? b : -1;
+    rowinfo[lane] = make_int4(static_cast<int>(orow & 0xffffffffLL), static_cast<int>(orow >> 32), bv, 0);
+    // bias of this tile -> private smem (overlaps with the wait for the accumulator)
+#pragma unroll
+    for (int i = 0; i < (BN + 31) / 32; ++i) {
+      const int e = i * 32 + lane;
+      if (e < BN) bias_s[e] = (p.bias && n_tile * BN + e < p.N) ? __ldg(p.bias + n_tile * BN + e) : 0.f;
+    }
+    // sample of the warp's rows (fused GroupNorm statistics: the host guarantees one sample per warp there)
+    const int warp_sample = __reduce_max_sync(0xffffffff, bv);
+    if (STATS && (warp_sample != st_sample || n_tile != st_ntile)) {
+      if (st_sample >= 0)
+        flush_col_stats(p, lane, st_sample, st_ntile * out_cols_t, n_limit_t, c_begin, c_step, st1, st2);
+      st_sample = warp_sample; st_ntile = n_tile;
+    }
+    __syncwarp();
+
+    mbar_wait(&tmem_full[a], aph);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * BN;
+    switch (mode) {
+      case 0: epilogue_tile<BN, 0, false, NCH, STATS>(p, taddr, stage, bias_s, lane, n_tile, rowinfo, c_begin, c_step, st1, st2); break;
+      case 1: epilogue_tile<BN, 0, true, NCH, STATS>(p, taddr, stage, bias_s, lane, n_tile, rowinfo, c_begin, c_step, st1, st2); break;
+      case 2: epilogue_tile<BN, 1, false, NCH, STATS>(p, taddr, stage, bias_s, lane, n_tile, rowinfo, c_begin, c_step, st1, st2); break;
+      case 3: epilogue_tile<BN, 1, true, NCH, STATS>(p, taddr, stage, bias_s, lane, n_tile, rowinfo, c_begin, c_step, st1, st2); break;
+      case 4: epilogue_tile<BN, 2, false, NCH, STATS>(p, taddr, stage, bias_s, lane, n_tile, rowinfo, c_begin, c_step, st1, st2); break;
+      default: epilogue_tile<BN, 2, true, NCH, STATS>(p, taddr, stage, bias_s, lane, n_tile, rowinfo, c_begin, c_step, st1, st2); break;
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&tmem_empty[a]);
+  }
+  if (STATS && st_sample >= 0)
+    flush_col_stats(p, lane, st_sample, st_ntile * out_cols_t, n_limit_t, c_begin, c_step, st1, st2);
 }
 
 template <int BN, int STAGES, int EPI_WARPS>
@@ -321,78 +401,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else {
     // ===================== epilogue (warps 2 .. 2+EPI_WARPS) =====================
-    // Warp w reads TMEM lane quarter (w & 3); with 8 epilogue warps the two warps of a quarter split the 32-column
-    // chunks of the tile between them (even / odd).
-    const int ew = warp - 2;
-    const int q = warp & 3;
-    const int r = q * 32 + lane;
-    float* stage = reinterpret_cast<float*>(smem + S::kStageOffset) + ew * 1024;
-    float* bias_s = reinterpret_cast<float*>(smem + S::kBiasOffset) + ew * BN;
-    int4* rowinfo = reinterpret_cast<int4*>(smem + S::kRowOffset) + ew * 32;
-    const int c_begin = (EPI_WARPS == 8) ? (ew >> 2) : 0;
-    const int c_step = (EPI_WARPS == 8) ? 2 : 1;
-    const int mode = (p.res_f32 ? 1 : (p.res_bf16 ? 2 : 0)) * 2 + (p.rowvec ? 1 : 0);
-    const int out_cols_t = (p.act == ACT_GEGLU) ? BN / 2 : BN;
-    const int n_limit_t = (p.act == ACT_GEGLU) ? p.N / 2 : p.N;
-    constexpr int NCH = (EPI_WARPS == 8) ? (BN / 32 + 1) / 2 : BN / 32;  // chunks one warp owns per tile
-    float st1[NCH][4], st2[NCH][4];
-#pragma unroll
-    for (int k = 0; k < NCH; ++k)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) { st1[k][e] = 0.f; st2[k][e] = 0.f; }
-    int st_sample = -1, st_ntile = -1;
-    int lt = 0;
-    for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++lt) {
-      const int a = lt & 1;
-      const uint32_t aph = (lt >> 1) & 1;
-      const int n_tile = tile % p.n_tiles;
-      int m = tile / p.n_tiles;
-      const int xb = m % p.nxb; m /= p.nxb;
-      const int yb = m % p.nyb; m /= p.nyb;
-      const int zb = m % p.nzb; m /= p.nzb;
-      int rr = r;
-      const int ix = rr % p.bw; rr /= p.bw;
-      const int iy = rr % p.bh; rr /= p.bh;
-      const int iz = rr % p.bd; rr /= p.bd;
-      const int x = xb * p.bw + ix, y = yb * p.bh + iy, z = zb * p.bd + iz, b = m * p.bb + rr;
-      const bool valid = (x < p.W) && (y < p.H) && (z < p.D) && (b < p.B);
-      const long long orow =
-          (((static_cast<long long>(b) * p.OD + (z * p.osz + p.opz)) * p.OH + (y * p.osy + p.opy)) * p.OW +
-           (x * p.osx + p.opx)) * p.ldo;
-      const int bv = valid ? b : -1;
-      rowinfo[lane] = make_int4(static_cast<int>(orow & 0xffffffffLL), static_cast<int>(orow >> 32), bv, 0);
-      // bias of this tile -> private smem (overlaps with the wait for the accumulator)
-#pragma unroll
-      for (int i = 0; i < (BN + 31) / 32; ++i) {
-        const int e = i * 32 + lane;
-        if (e < BN) bias_s[e] = (p.bias && n_tile * BN + e < p.N) ? __ldg(p.bias + n_tile * BN + e) : 0.f;
-      }
-      // sample of the warp's rows (fused GroupNorm statistics: the host guarantees one sample per warp there)
-      const int warp_sample = __reduce_max_sync(0xffffffff, bv);
-      if (p.col_stats && (warp_sample != st_sample || n_tile != st_ntile)) {
-        if (st_sample >= 0)
-          flush_col_stats(p, lane, st_sample, st_ntile * out_cols_t, n_limit_t, c_begin, c_step, st1, st2);
-        st_sample = warp_sample; st_ntile = n_tile;
-      }
-      __syncwarp();
-
-      mbar_wait(&tmem_full[a], aph);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * BN;
-      switch (mode) {
-        case 0: epilogue_tile<BN, 0, false, NCH>(p, taddr, stage, bias_s, lane, n_tile, rowinfo, c_begin, c_step, st1, st2); break;
-        case 1: epilogue_tile<BN, 0, true, NCH>(p, taddr, stage, bias_s, lane, n_tile, rowinfo, c_begin, c_step, st1, st2); break;
-        case 2: epilogue_tile<BN, 1, false, NCH>(p, taddr, stage, bias_s, lane, n_tile, rowinfo, c_begin, c_step, st1, st2); break;
-        case 3: epilogue_tile<BN, 1, true, NCH>(p, taddr, stage, bias_s, lane, n_tile, rowinfo, c_begin, c_step, st1, st2); break;
-        case 4: epilogue_tile<BN, 2, false, NCH>(p, taddr, stage, bias_s, lane, n_tile, rowinfo, c_begin, c_step, st1, st2); break;
-        default: epilogue_tile<BN, 2, true, NCH>(p, taddr, stage, bias_s, lane, n_tile, rowinfo, c_begin, c_step, st1, st2); break;
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[a]);
-    }
-    if (p.col_stats && st_sample >= 0)
-      flush_col_stats(p, lane, st_sample, st_ntile * out_cols_t, n_limit_t, c_begin, c_step, st1, st2);
+    if (p.col_stats)
+      epilogue_loop<BN, STAGES, EPI_WARPS, true>(p, smem, tmem_full, tmem_empty, tmem_base, warp, lane, tile_begin,
+                                                 tile_end, tile_step);
+    else
+      epilogue_loop<BN, STAGES, EPI_WARPS, false>(p, smem, tmem_full, tmem_empty, tmem_base, warp, lane, tile_begin,
+                                                  tile_end, tile_step);
   }
 
   tc_fence_before();
