@@ -584,10 +584,16 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
 __global__ void cfg_ddim_kernel(const float* __restrict__ eps, float* __restrict__ x, float* __restrict__ eps_out,
                                 const float* __restrict__ noise, int T, int n_per_view, int cfg, float cfg_scale,
                                 float a_t, float a_prev, float sigma, float sqrt_1m_at, int add_noise, uint64_t seed,
-                                uint32_t step, int view0, int do_update) {
+                                uint32_t step, int view0, int do_update, const float* __restrict__ dev_params) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int total = T * n_per_view;
   if (i >= total) return;
+  if (dev_params) {  // per-step scalars live in device memory so that one captured CUDA graph serves every DDIM index
+    a_t = dev_params[1]; a_prev = dev_params[2]; sigma = dev_params[3]; sqrt_1m_at = dev_params[4];
+    add_noise = dev_params[5] != 0.f;
+    step = __float_as_uint(dev_params[6]);
+    seed = (static_cast<uint64_t>(__float_as_uint(dev_params[8])) << 32) | __float_as_uint(dev_params[7]);
+  }
   float e = eps[i];
   if (cfg) {
     const float e_uc = eps[total + i];
@@ -620,11 +626,11 @@ __global__ void cfg_ddim_kernel(const float* __restrict__ eps, float* __restrict
 
 int launch_cfg_ddim(const float* eps, float* x, float* eps_out, const float* noise, int T, int n_per_view, int cfg,
                     float cfg_scale, float a_t, float a_prev, float sigma, float sqrt_1m_at, int add_noise,
-                    uint64_t seed, uint32_t step, int view0, int do_update, cudaStream_t st) {
+                    uint64_t seed, uint32_t step, int view0, int do_update, const float* dev_params, cudaStream_t st) {
   const int total = T * n_per_view;
   cfg_ddim_kernel<<<(total + 255) / 256, 256, 0, st>>>(eps, x, eps_out, noise, T, n_per_view, cfg, cfg_scale, a_t,
                                                        a_prev, sigma, sqrt_1m_at, add_noise, seed, step, view0,
-                                                       do_update);
+                                                       do_update, dev_params);
   return check_launch("cfg_ddim");
 }
 

@@ -120,6 +120,16 @@ struct Ctx {
   float* d_t = nullptr;  // [max B] timesteps as float
   float* gn_stats = nullptr;  // persistent all-zero GroupNorm statistics scratch (finalize re-zeroes it)
   size_t gn_stats_floats = 0;
+  // whole-step CUDA graph (captured on the second call with the same pointers; replayed for every DDIM index)
+  cudaStream_t stream = nullptr;       // internal non-blocking stream the step runs on
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+  float* d_step = nullptr;             // [16] per-step scalars read by the captured kernels
+  cudaGraphExec_t graph = nullptr;
+  struct GraphKey { const void* x; const void* xin; const void* clip; const void* noise; const void* eps; float cfg; int bind_gen; int wgen; } gkey{};
+  int graph_warm = 0;                  // calls seen with the current key
+  int graph_launches = 0;              // kernels inside the captured graph (launch accounting on replay)
+  int bind_gen = 0, weights_gen = 0;
+  bool use_graph = true;
   // multi-GPU
   void* nccl_comm = nullptr;
   int rank = 0, world = 1;

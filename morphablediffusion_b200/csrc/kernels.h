@@ -44,7 +44,7 @@ int launch_ncdhw_to_cl_bf16(const float* x, void* out, int B, int C, size_t S, c
 int launch_cl_to_ncdhw(const void* x, int x_is_bf16, float* out, int B, int C, size_t S, cudaStream_t st);
 int launch_cfg_ddim(const float* eps, float* x, float* eps_out, const float* noise, int T, int n_per_view, int cfg,
                     float cfg_scale, float a_t, float a_prev, float sigma, float sqrt_1m_at, int add_noise,
-                    uint64_t seed, uint32_t step, int view0, int do_update, cudaStream_t st);
+                    uint64_t seed, uint32_t step, int view0, int do_update, const float* dev_params, cudaStream_t st);
 
 // ---- attention.cu
 // Self-attention over tokens: qkv bf16 [B][S][3*C] (q | k | v, head h at columns h*dh), out bf16 [B][S][C].

@@ -4,6 +4,7 @@
 
 #include <dlfcn.h>
 #include <math.h>
+#include <stdlib.h>
 
 struct md_ctx { md::Ctx c; };
 
@@ -13,6 +14,18 @@ namespace md {
 __global__ void fill_kernel(float* p, float v, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
+}
+__global__ void fill_from_kernel(float* p, const float* src, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = src[0];
+}
+__global__ void set_step_params_kernel(float* d, float tval, float a_t, float a_prev, float sigma, float s1m, int add_noise,
+                                       uint32_t index, uint64_t seed) {
+  if (threadIdx.x == 0) {
+    d[0] = tval; d[1] = a_t; d[2] = a_prev; d[3] = sigma; d[4] = s1m; d[5] = add_noise ? 1.f : 0.f;
+    d[6] = __uint_as_float(index);
+    d[7] = __uint_as_float(static_cast<uint32_t>(seed)); d[8] = __uint_as_float(static_cast<uint32_t>(seed >> 32));
+  }
 }
 // context rows: first T = clip embedding, remaining (uncond) = 0   (morphable_diffusion.py:135)
 __global__ void make_context_kernel(const float* __restrict__ clip, float* __restrict__ out, int T, int B, int dim) {
@@ -121,8 +134,9 @@ static int denoise_step_impl(Ctx& c, float* x_local, const float* x_input, const
   float* ctxv = A.get<float>(static_cast<size_t>(maxB) * mc.context_dim);
   float* x_in = A.get<float>(static_cast<size_t>(maxB) * HW * 8);
   if (A.failed) return set_error("workspace exhausted (step)");
-  fill_kernel<<<(maxB + 63) / 64, 64, 0, st>>>(d_t, tval, maxB);
+  fill_from_kernel<<<(maxB + 63) / 64, 64, 0, st>>>(d_t, c.d_step, maxB);  // timestep of this index (d_step[0])
   MD_CHECK(check_launch("fill"));
+  (void)tval;
   MD_CHECK(embed_time(c, d_t, t_embed, st));
   MD_CHECK(vertex_feature_sum(c, x_local, t_embed, vsum, st));
   if (c.world > 1) {
@@ -148,7 +162,7 @@ static int denoise_step_impl(Ctx& c, float* x_local, const float* x_input, const
                              eps_out ? eps_out + static_cast<size_t>(lv0) * 4 * HW : nullptr,
                              noise ? noise + static_cast<size_t>(lv0) * 4 * HW : nullptr, T, 4 * HW, cfg, cfg_scale,
                              c.alphas[index], c.alphas_prev[index], c.sigmas[index], c.sqrt_1m_alphas[index],
-                             add_noise, seed, static_cast<uint32_t>(index), sb.view0 + lv0, do_update, st));
+                             add_noise, seed, static_cast<uint32_t>(index), sb.view0 + lv0, do_update, c.d_step, st));
     A.release(m);
   }
   return 0;
@@ -201,6 +215,17 @@ int md_create(md_ctx** out, const md_config* cfg) {
     delete ctx;
     return set_error("md_create: GroupNorm scratch allocation failed: %s", cudaGetErrorString(e));
   }
+  e = cudaStreamCreateWithFlags(&ctx->c.stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->c.ev_in, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->c.ev_out, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&ctx->c.d_step), 16 * sizeof(float));
+  if (e != cudaSuccess) {
+    cudaFree(ctx->c.arena.base);
+    cudaFree(ctx->c.gn_stats);
+    delete ctx;
+    return set_error("md_create: stream / event setup failed: %s", cudaGetErrorString(e));
+  }
+  ctx->c.use_graph = getenv("MD_NO_GRAPH") == nullptr;
   *out = ctx;
   return 0;
 }
@@ -211,6 +236,11 @@ void md_destroy(md_ctx* ctx) {
   free_binding(ctx->c);
   free_weights(ctx->c);
   if (ctx->c.nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->c.nccl_comm);
+  if (ctx->c.graph) cudaGraphExecDestroy(ctx->c.graph);
+  if (ctx->c.stream) cudaStreamDestroy(ctx->c.stream);
+  if (ctx->c.ev_in) cudaEventDestroy(ctx->c.ev_in);
+  if (ctx->c.ev_out) cudaEventDestroy(ctx->c.ev_out);
+  cudaFree(ctx->c.d_step);
   cudaFree(ctx->c.arena.base);
   cudaFree(ctx->c.gn_stats);
   delete ctx;
@@ -229,6 +259,7 @@ int md_load_weights(md_ctx* ctx, int n, const char* const* names, const void* co
     t.numel = static_cast<size_t>(numels[i]);
     tm[names[i]] = t;
   }
+  ctx->c.weights_gen++;
   return load_all_weights(ctx->c, tm, static_cast<cudaStream_t>(stream));
 }
 
@@ -237,6 +268,7 @@ int md_bind_sample(md_ctx* ctx, const float* K, const float* RT, const float* v_
                    int n_local, int projection, void* stream) {
   if (!ctx) return set_error("null context");
   if (projection != 0 && projection != 1) return set_error("NotImplementedError: projection %d", projection);
+  ctx->c.bind_gen++;
   return bind_sample(ctx->c, K, RT, v_embed, vertices, coord, out_sh, bounds, nv, n_views, view0, n_local, projection,
                      static_cast<cudaStream_t>(stream));
 }
@@ -334,8 +366,61 @@ int md_unet_forward(md_ctx* ctx, const float* x, const float* timesteps_host, co
 int md_denoise_step(md_ctx* ctx, float* x_local, const float* x_input, const float* clip_embed, int index,
                     float cfg_scale, const float* noise, unsigned long long seed, float* eps_out, void* stream) {
   MD_CHECK(ensure_ready(ctx, true));
-  return denoise_step_impl(ctx->c, x_local, x_input, clip_embed, index, cfg_scale, noise, seed, eps_out, 1,
-                           static_cast<cudaStream_t>(stream));
+  Ctx& c = ctx->c;
+  if (index < 0 || index >= static_cast<int>(c.timesteps.size())) return set_error("denoise_step: bad DDIM index %d", index);
+  cudaStream_t caller = static_cast<cudaStream_t>(stream);
+  cudaStream_t st = c.stream;
+  // fence the caller's stream into the internal one (the legacy default stream cannot be captured)
+  MD_CUDA(cudaEventRecord(c.ev_in, caller));
+  MD_CUDA(cudaStreamWaitEvent(st, c.ev_in, 0));
+  set_step_params_kernel<<<1, 32, 0, st>>>(c.d_step, static_cast<float>(c.timesteps[index]), c.alphas[index],
+                                           c.alphas_prev[index], c.sigmas[index], c.sqrt_1m_alphas[index], index != 0,
+                                           static_cast<uint32_t>(index), seed);
+  MD_CHECK(check_launch("set_step_params"));
+  const Ctx::GraphKey key{x_local, x_input, clip_embed, noise, eps_out, cfg_scale, c.bind_gen, c.weights_gen};
+  const bool same = memcmp(&key, &c.gkey, sizeof(key)) == 0;
+  int rc = 0;
+  if (!c.use_graph) {
+    rc = denoise_step_impl(c, x_local, x_input, clip_embed, index, cfg_scale, noise, seed, eps_out, 1, st);
+  } else if (same && c.graph) {
+    cudaError_t e = cudaGraphLaunch(c.graph, st);
+    if (e != cudaSuccess) rc = set_error("cudaGraphLaunch: %s", cudaGetErrorString(e));
+    else count_launch(c.graph_launches);
+  } else {
+    if (!same) {
+      if (c.graph) { cudaGraphExecDestroy(c.graph); c.graph = nullptr; }
+      c.gkey = key;
+      c.graph_warm = 0;
+    }
+    if (c.graph_warm == 0) {  // first call with these pointers: plain launches (also sets function attributes)
+      rc = denoise_step_impl(c, x_local, x_input, clip_embed, index, cfg_scale, noise, seed, eps_out, 1, st);
+      c.graph_warm = 1;
+    } else {                  // second call: capture, instantiate, launch
+      const long long before = md_launch_count();
+      cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed);
+      if (e != cudaSuccess) return set_error("cudaStreamBeginCapture: %s", cudaGetErrorString(e));
+      rc = denoise_step_impl(c, x_local, x_input, clip_embed, index, cfg_scale, noise, seed, eps_out, 1, st);
+      cudaGraph_t g = nullptr;
+      e = cudaStreamEndCapture(st, &g);
+      if (rc == 0 && e != cudaSuccess) rc = set_error("cudaStreamEndCapture: %s", cudaGetErrorString(e));
+      if (rc == 0) {
+        e = cudaGraphInstantiate(&c.graph, g, 0);
+        if (e != cudaSuccess) rc = set_error("cudaGraphInstantiate: %s", cudaGetErrorString(e));
+      }
+      if (g) cudaGraphDestroy(g);
+      c.graph_launches = static_cast<int>(md_launch_count() - before);
+      if (rc == 0) {
+        e = cudaGraphLaunch(c.graph, st);
+        if (e != cudaSuccess) rc = set_error("cudaGraphLaunch: %s", cudaGetErrorString(e));
+      } else if (c.graph) {
+        cudaGraphExecDestroy(c.graph);
+        c.graph = nullptr;
+      }
+    }
+  }
+  MD_CUDA(cudaEventRecord(c.ev_out, st));
+  MD_CUDA(cudaStreamWaitEvent(caller, c.ev_out, 0));
+  return rc;
 }
 
 int md_ddim_timestep(md_ctx* ctx, int index) {
@@ -380,7 +465,7 @@ int md_op_cfg_ddim(md_ctx* ctx, const float* eps, float* x, float* eps_out, cons
   if (index < 0 || index >= static_cast<int>(c.timesteps.size())) return set_error("cfg_ddim: bad index %d", index);
   return launch_cfg_ddim(eps, x, eps_out, noise, T, n_per_view, cfg_scale != 1.0f, cfg_scale, c.alphas[index],
                          c.alphas_prev[index], c.sigmas[index], c.sqrt_1m_alphas[index], index != 0, seed,
-                         static_cast<uint32_t>(index), view0, 1, static_cast<cudaStream_t>(stream));
+                         static_cast<uint32_t>(index), view0, 1, nullptr, static_cast<cudaStream_t>(stream));
 }
 
 int md_comm_unique_id(void* id128) {

@@ -369,6 +369,32 @@ def test_step_is_repeatable_and_chunk_invariant(state_dict):
     assert rel(outs[1], outs[0]) < 1e-3
 
 
+def test_cuda_graph_replay_matches_plain_launches(state_dict, monkeypatch):
+    """The step is captured into one CUDA graph on its second call and replayed for every later DDIM index (per-step
+    scalars live in device memory); results must match plain stream launches (MD_NO_GRAPH=1)."""
+    from morphablediffusion_b200 import synth
+    from morphablediffusion_b200.engine import Engine
+    n = 2
+    batch = synth.make_batch(n)
+    x_t, x_input, clip = synth.make_inputs(n)
+    outs = []
+    for no_graph in (False, True):
+        if no_graph:
+            monkeypatch.setenv("MD_NO_GRAPH", "1")
+        eng = Engine(max_views_per_call=n)
+        eng.load_state_dict(state_dict)
+        eng.bind(batch, "perspective")
+        x = x_t[0].cuda().contiguous()
+        xi, cl = x_input[0].cuda().contiguous(), clip[0, 0].cuda().contiguous()
+        for index in (49, 48, 47, 46, 0):
+            eng.denoise_step(x, xi, cl, index, 2.0, seed=77)
+        torch.cuda.synchronize()
+        outs.append(x.cpu())
+        eng.close()
+    assert torch.isfinite(outs[0]).all()
+    assert rel(outs[0], outs[1]) < 5e-3
+
+
 def test_reference_shaped_api(state_dict):
     """The drop-in classes: load a reference-keyed state dict, run the sampler's denoise_apply, compare with the engine."""
     from morphablediffusion_b200 import synth
