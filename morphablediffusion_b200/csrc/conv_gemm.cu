@@ -61,15 +61,18 @@ int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
 
   ConvGemmParams p;
   memset(&p, 0, sizeof(p));
-  p.W = a.W; p.H = a.H; p.D = a.D; p.B = a.B;
+  p.isx = a.in_stride[0] ? a.in_stride[0] : 1; p.isy = a.in_stride[1] ? a.in_stride[1] : 1;
+  p.isz = a.in_stride[2] ? a.in_stride[2] : 1;
+  // tile grid = output positions (= input positions / stride)
+  p.W = (a.W + p.isx - 1) / p.isx; p.H = (a.H + p.isy - 1) / p.isy; p.D = (a.D + p.isz - 1) / p.isz; p.B = a.B;
   int rem = kBlockM;
-  p.bw = std::min(pow2_floor(a.W), rem); rem /= p.bw;
-  p.bh = std::min(pow2_floor(a.H), rem); rem /= p.bh;
-  p.bd = std::min(pow2_floor(a.D), rem); rem /= p.bd;
+  p.bw = std::min(pow2_floor(p.W), rem); rem /= p.bw;
+  p.bh = std::min(pow2_floor(p.H), rem); rem /= p.bh;
+  p.bd = std::min(pow2_floor(p.D), rem); rem /= p.bd;
   p.bb = rem;
-  p.nxb = (a.W + p.bw - 1) / p.bw;
-  p.nyb = (a.H + p.bh - 1) / p.bh;
-  p.nzb = (a.D + p.bd - 1) / p.bd;
+  p.nxb = (p.W + p.bw - 1) / p.bw;
+  p.nyb = (p.H + p.bh - 1) / p.bh;
+  p.nzb = (p.D + p.bd - 1) / p.bd;
   p.nbb = (a.B + p.bb - 1) / p.bb;
   p.m_tiles = p.nxb * p.nyb * p.nzb * p.nbb;
   p.kblocks_per_tap = a.Cin / kBlockK;
@@ -80,7 +83,7 @@ int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
     p.tdz[t] = static_cast<int8_t>(a.tap[t][2]);
   }
   p.N = a.N;
-  p.OW = a.OW ? a.OW : a.W; p.OH = a.OH ? a.OH : a.H; p.OD = a.OD ? a.OD : a.D;
+  p.OW = a.OW ? a.OW : p.W; p.OH = a.OH ? a.OH : p.H; p.OD = a.OD ? a.OD : p.D;
   p.osx = a.os[0] ? a.os[0] : 1; p.osy = a.os[1] ? a.os[1] : 1; p.osz = a.os[2] ? a.os[2] : 1;
   p.opx = a.op[0]; p.opy = a.op[1]; p.opz = a.op[2];
   p.act = a.act;
@@ -96,15 +99,23 @@ int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
   if (p.ldo % 8 != 0) return set_error("conv_gemm: ldo=%d must be a multiple of 8", p.ldo);
   if (a.act == ACT_GEGLU && !a.out_bf16) return set_error("conv_gemm: GEGLU epilogue writes bf16 only");
 
-  // ---- tile N selection
+  // ---- tile N selection: minimise waves x per-tile MMA time (proportional to BN), prefer the wider tile on ties
   int BN = a.BN;
   if (BN == 0) {
-    if (a.act == ACT_GEGLU) BN = 128;
-    else if (a.N % 160 == 0 && a.N % 256 != 0 && (long long)p.m_tiles * (a.N / 160) >= 120) BN = 160;
-    else if (a.N >= 256 && (long long)p.m_tiles * ((a.N + 255) / 256) >= 148) BN = 256;
-    else if (a.N >= 128 && (long long)p.m_tiles * ((a.N + 127) / 128) >= 100) BN = 128;
-    else if (a.N > 64 && a.N % 160 == 0 && a.N % 128 != 0) BN = 160;
-    else BN = (a.N <= 64) ? 64 : ((a.N % 128 == 0 && (long long)p.m_tiles * (a.N / 128) >= 64) ? 128 : 64);
+    if (a.act == ACT_GEGLU) {
+      BN = 128;
+    } else {
+      const int cands[4] = {256, 160, 128, 64};
+      long long best = -1;
+      for (int ci = 0; ci < 4; ++ci) {
+        const int bn = cands[ci];
+        if (bn > 64 && a.N <= bn / 2) continue;                 // mostly-empty tile
+        const long long tiles = static_cast<long long>(p.m_tiles) * ((a.N + bn - 1) / bn);
+        const long long waves = (tiles + num_sms() - 1) / num_sms();
+        const long long cost = waves * (bn + 24);               // +24: per-tile fixed cost (pipeline fill, epilogue tail)
+        if (best < 0 || cost < best) { best = cost; BN = bn; }
+      }
+    }
   }
   if (a.act == ACT_GEGLU && BN != 128) return set_error("conv_gemm: GEGLU requires BN=128");
   p.n_tiles = (a.N + BN - 1) / BN;
@@ -115,9 +126,9 @@ int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
     cuuint64_t dims[5] = {(cuuint64_t)a.Cin, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.D, (cuuint64_t)a.B};
     cuuint64_t strides[4] = {(cuuint64_t)Cpitch * 2, (cuuint64_t)Cpitch * 2 * a.W,
                              (cuuint64_t)Cpitch * 2 * a.W * a.H, (cuuint64_t)Cpitch * 2 * a.W * a.H * a.D};
-    cuuint32_t box[5] = {(cuuint32_t)kBlockK, (cuuint32_t)p.bw, (cuuint32_t)p.bh, (cuuint32_t)p.bd,
-                         (cuuint32_t)p.bb};
-    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    cuuint32_t box[5] = {(cuuint32_t)kBlockK, (cuuint32_t)(p.bw * p.isx), (cuuint32_t)(p.bh * p.isy),
+                         (cuuint32_t)(p.bd * p.isz), (cuuint32_t)p.bb};
+    cuuint32_t es[5] = {1, (cuuint32_t)p.isx, (cuuint32_t)p.isy, (cuuint32_t)p.isz, 1};
     CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(a.A), dims, strides, box,
                      es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -47,10 +47,21 @@ struct ConvGemmParams {
   float* col_stats; // optional [B][stats_ld][2]: per-(sample, channel) sum / sum of squares of the fp32 result
   int stats_ld;
   int contig;       // contiguous tile run per CTA (see kernel)
+  int isx, isy, isz; // input coordinate = output-tile coordinate * is + tap offset (strided convolution via TMA element strides)
 };
 
 __device__ __forceinline__ float act_silu(float x) { return x / (1.f + __expf(-x)); }
-__device__ __forceinline__ float act_gelu(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+// exact-erf GELU (F.gelu default) with erf from Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7): 1 rcp + 1 exp + 6 fma
+__device__ __forceinline__ float act_gelu(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float e = 1.f - poly * t * __expf(-z * z);   // erf(|x|/sqrt2)
+  return 0.5f * x * (1.f + copysignf(e, x));
+}
 
 template <int BN, int STAGES, int EPI_WARPS>
 struct ConvGemmSmem {
@@ -350,7 +361,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int xb = m % p.nxb; m /= p.nxb;
         const int yb = m % p.nyb; m /= p.nyb;
         const int zb = m % p.nzb; m /= p.nzb;
-        const int x0 = xb * p.bw, y0 = yb * p.bh, z0 = zb * p.bd, b0 = m * p.bb;
+        const int x0 = xb * p.bw * p.isx, y0 = yb * p.bh * p.isy, z0 = zb * p.bd * p.isz, b0 = m * p.bb;
         const int n0 = n_tile * BN;
         int kcol = 0;
         for (int tap = 0; tap < p.ntaps; ++tap) {

@@ -335,18 +335,20 @@ int launch_timestep_embedding(const float* t, float* out, int B, int dim, cudaSt
 
 // ------------------------------------------------------------------------------------------------ direct 3x3 conv
 // Small-channel Conv2d 3x3 pad 1 (UNet conv_in 8->320).  x fp32 NHWC, W fp32 [tap][Cin][Cout], out fp32 NHWC.
+// One thread per (pixel, 4 output channels).
 __global__ void conv3x3_direct_kernel(const float* __restrict__ x, const float* __restrict__ W,
                                       const float* __restrict__ bias, float* __restrict__ out, int B, int H, int Wd,
                                       int Cin, int Cout) {
+  const int CQ = Cout >> 2;
   const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
-  const size_t total = static_cast<size_t>(B) * H * Wd * Cout;
+  const size_t total = static_cast<size_t>(B) * H * Wd * CQ;
   if (i >= total) return;
-  const int co = static_cast<int>(i % Cout);
-  size_t p = i / Cout;
+  const int co = static_cast<int>(i % CQ) * 4;
+  size_t p = i / CQ;
   const int xw = static_cast<int>(p % Wd); p /= Wd;
   const int yh = static_cast<int>(p % H);
   const int b = static_cast<int>(p / H);
-  float acc = bias ? bias[co] : 0.f;
+  float4 acc = bias ? *reinterpret_cast<const float4*>(bias + co) : make_float4(0.f, 0.f, 0.f, 0.f);
   for (int ky = 0; ky < 3; ++ky) {
     const int yy = yh + ky - 1;
     if (yy < 0 || yy >= H) continue;
@@ -355,18 +357,36 @@ __global__ void conv3x3_direct_kernel(const float* __restrict__ x, const float* 
       if (xx < 0 || xx >= Wd) continue;
       const float* xp = x + ((static_cast<size_t>(b) * H + yy) * Wd + xx) * Cin;
       const float* wp = W + static_cast<size_t>((ky * 3 + kx) * Cin) * Cout + co;
-      for (int ci = 0; ci < Cin; ++ci) acc += xp[ci] * __ldg(wp + static_cast<size_t>(ci) * Cout);
+      for (int ci = 0; ci < Cin; ++ci) {
+        const float a = xp[ci];
+        const float4 w = __ldg(reinterpret_cast<const float4*>(wp + static_cast<size_t>(ci) * Cout));
+        acc.x += a * w.x; acc.y += a * w.y; acc.z += a * w.z; acc.w += a * w.w;
+      }
     }
   }
-  out[i] = acc;
+  *reinterpret_cast<float4*>(out + ((static_cast<size_t>(b) * H + yh) * Wd + xw) * Cout + co) = acc;
 }
 
 int launch_conv3x3_direct(const float* x, const float* W, const float* bias, float* out, int B, int H, int Wd, int Cin,
                           int Cout, cudaStream_t st) {
-  const size_t total = static_cast<size_t>(B) * H * Wd * Cout;
-  conv3x3_direct_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(x, W, bias, out, B, H, Wd, Cin,
+  if (Cout % 4) return set_error("conv3x3_direct: Cout must be a multiple of 4");
+  const size_t total = static_cast<size_t>(B) * H * Wd * (Cout / 4);
+  conv3x3_direct_kernel<<<static_cast<unsigned>((total + 127) / 128), 128, 0, st>>>(x, W, bias, out, B, H, Wd, Cin,
                                                                                     Cout);
   return check_launch("conv3x3_direct");
+}
+
+// [rows][ld] fp32 (first C columns) -> NCHW [B][C][HW]   (UNet output: the final conv runs as a GEMM padded to 8 columns)
+__global__ void rows_to_nchw_kernel(const float* __restrict__ x, int ld, float* __restrict__ out, int B, int C, int HW) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * C * HW) return;
+  const int p = i % HW, c = (i / HW) % C, b = i / (HW * C);
+  out[i] = x[(static_cast<size_t>(b) * HW + p) * ld + c];
+}
+int launch_rows_to_nchw(const float* x, int ld, float* out, int B, int C, int HW, cudaStream_t st) {
+  const int total = B * C * HW;
+  rows_to_nchw_kernel<<<(total + 255) / 256, 256, 0, st>>>(x, ld, out, B, C, HW);
+  return check_launch("rows_to_nchw");
 }
 
 // Final UNet conv (320 -> 4): bf16 NHWC activations, fp32 weights [tap][Cout<=4][Cin]; one warp per pixel.

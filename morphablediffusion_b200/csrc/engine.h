@@ -68,7 +68,7 @@ struct UNetW {
   std::vector<std::vector<UNetLayer>> input_blocks, output_blocks;
   ResW mid0, mid2; STW mid1;
   DepthW mid_cond; std::vector<DepthW> out_cond;
-  NormW out_norm; float* out_w = nullptr; const float* out_b = nullptr;  // fp32 [tap][Cout][Cin]
+  NormW out_norm; GemmW out_g;  // final conv as a GEMM padded to 8 output columns (rows out_channels..7 are zero)
 };
 
 struct FrBlockW {   // FrustumTVBlock / FrustumTVUpBlock

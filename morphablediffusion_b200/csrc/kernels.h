@@ -34,6 +34,7 @@ int launch_conv3x3_direct(const float* x, const float* W, const float* bias, flo
                           int Cout, cudaStream_t st);
 int launch_conv3x3_out(const void* x_bf16, const float* W, const float* bias, float* out, int B, int H, int Wd, int Cin,
                        int Cout, cudaStream_t st);
+int launch_rows_to_nchw(const float* x, int ld, float* out, int B, int C, int HW, cudaStream_t st);
 int launch_unet_input(const float* x, const float* xc, int xc_per_sample, float* out, int T, int HW, int cfg,
                       cudaStream_t st);
 int launch_cast_bf16(const float* x, void* out, size_t n, cudaStream_t st);

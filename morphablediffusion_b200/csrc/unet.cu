@@ -196,17 +196,24 @@ struct Fwd {
     return 0;
   }
 
-  // Downsample: Conv2d 3x3 stride 2 pad 1 (openaimodel.py:159-161) via patch gather + GEMM
+  // Downsample: Conv2d 3x3 stride 2 pad 1 (openaimodel.py:159-161): implicit GEMM whose TMA boxes step by 2 pixels
   int downsample(const GemmW& w, const float* x, int H, int W, int C, float* out) {
-    const int OH = H / 2, OW = W / 2;
-    const size_t orows = static_cast<size_t>(B) * OH * OW;
+    const size_t rows = static_cast<size_t>(B) * H * W;
     const size_t m = A().mark();
-    bf16* patches = A().get<bf16>(orows * 9 * C);
+    bf16* xb = A().get<bf16>(rows * C);
     if (A().failed) return set_error("workspace exhausted (downsample)");
-    MD_CHECK(launch_gather_s2(x, 0, patches, B, 1, H, W, C, 1, st));
-    GemmW g = w;
-    g.K = 9 * C; g.taps = 1;
-    MD_CHECK(gemm(patches, B, static_cast<size_t>(OH) * OW, g, nullptr, out, nullptr, true));
+    MD_CHECK(launch_cast_bf16(x, xb, rows * C, st));
+    md_conv_gemm_args a;
+    memset(&a, 0, sizeof(a));
+    a.A = xb; a.B = B; a.D = 1; a.H = H; a.W = W; a.Cin = C; a.Wt = w.w; a.N = w.N;
+    taps2d(a);
+    a.in_stride[0] = 2; a.in_stride[1] = 2; a.in_stride[2] = 1;
+    a.bias = w.bias; a.out_f32 = out;
+    if ((H / 2) * (W / 2) >= 32) {
+      a.col_stats = new_stats(out, B, w.N);
+      if (!a.col_stats) return set_error("statistics pool exhausted");
+    }
+    MD_CHECK(launch_conv_gemm(a, st));
     A().release(m);
     return 0;
   }
@@ -355,7 +362,10 @@ int unet_forward(Ctx& c, const float* x_in, const float* timesteps, const float*
   bf16* ao = A.get<bf16>(static_cast<size_t>(B) * H * H * ch);
   if (A.failed) return set_error("workspace exhausted (unet)");
   MD_CHECK(f.gn(h, ch, false, nullptr, 0, B, H * H, 32, 1e-5f, u.out_norm, ACT_SILU, ao, nullptr));
-  MD_CHECK(launch_conv3x3_out(ao, u.out_w, u.out_b, eps_out, B, H, H, ch, u.out_channels, st));
+  float* eps8 = A.get<float>(static_cast<size_t>(B) * H * H * 8);
+  if (A.failed) return set_error("workspace exhausted (unet)");
+  MD_CHECK(f.conv(ao, B, H, H, u.out_g, nullptr, 0, nullptr, eps8, nullptr, false));
+  MD_CHECK(launch_rows_to_nchw(eps8, 8, eps_out, B, u.out_channels, H * H, st));
   A.release(m0);
   return 0;
 }

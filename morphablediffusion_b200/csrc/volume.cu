@@ -414,14 +414,13 @@ int frustum_levels(Ctx& c, const float* vol, int lv0, int T, const float* t_embe
     if (b.stride == 1) {
       MD_CHECK(conv3d(a, d, s, b.conv, out, ostats));
     } else {
-      const size_t orows = static_cast<size_t>(d / 2) * (s / 2) * (s / 2);
-      bf16* patches = A.get<bf16>(static_cast<size_t>(T) * orows * 27 * b.cin);
-      if (A.failed) return set_error("workspace exhausted (frustum patches)");
-      MD_CHECK(launch_gather_s2(a, 1, patches, T, d, s, s, b.cin, 3, st));
+      // Conv3d 3x3x3 stride 2 pad 1: implicit GEMM whose TMA boxes step by 2 voxels (no patch materialisation)
       md_conv_gemm_args g;
       memset(&g, 0, sizeof(g));
-      g.A = patches; g.B = T; g.D = 1; g.H = 1; g.W = static_cast<int>(orows); g.Cin = 27 * b.cin; g.Wt = b.conv.w;
-      g.N = b.conv.N; g.ntaps = 1; g.bias = b.conv.bias; g.out_bf16 = out; g.col_stats = ostats;
+      g.A = a; g.B = T; g.D = d; g.H = s; g.W = s; g.Cin = b.conv.K; g.Wt = b.conv.w; g.N = b.conv.N;
+      taps3d(g);
+      g.in_stride[0] = g.in_stride[1] = g.in_stride[2] = 2;
+      g.bias = b.conv.bias; g.out_bf16 = out; g.col_stats = ostats;
       MD_CHECK(launch_conv_gemm(g, st));
     }
     A.release(mm);

@@ -331,13 +331,21 @@ int load_all_weights(Ctx& c, const TensorMap& tm, cudaStream_t st) {
     }
   }
   u.out_norm = L.norm(P + "out.0", mch);
-  {
+  {  // final conv 320 -> 4: bf16 [8][9*320] (zero rows 4..7) so it runs on the tensor-core implicit GEMM
     const NamedTensor* t = L.find(P + "out.2.weight", static_cast<size_t>(mc.out_channels) * mch * 9);
-    u.out_w = L.dalloc<float>(static_cast<size_t>(mc.out_channels) * mch * 9);
-    if (t && u.out_w)  // fp32 [tap][Cout][Cin]
-      L.pack<float>(t->ptr, u.out_w, mc.out_channels, 9, mch, static_cast<long>(mch) * 9, 1, 9, Loader::iota(), mch,
-                    static_cast<long>(mc.out_channels) * mch, 1);
-    u.out_b = L.copy_f32(P + "out.2.bias", mc.out_channels);
+    const NamedTensor* b = L.find(P + "out.2.bias", mc.out_channels);
+    if (mc.out_channels > 8) return set_error("load_weights: out_channels > 8 unsupported");
+    u.out_g.N = 8; u.out_g.K = mch; u.out_g.taps = 9;
+    u.out_g.w = L.dalloc<bf16>(static_cast<size_t>(8) * mch * 9);
+    float* ob = L.dalloc<float>(8);
+    u.out_g.bias = ob;
+    if (t && b && u.out_g.w && ob) {
+      cudaMemsetAsync(u.out_g.w, 0, sizeof(bf16) * 8 * mch * 9, st);
+      cudaMemsetAsync(ob, 0, sizeof(float) * 8, st);
+      L.pack<bf16>(t->ptr, u.out_g.w, mc.out_channels, 9, mch, static_cast<long>(mch) * 9, 1, 9, Loader::iota(),
+                   static_cast<long>(9) * mch, mch, 1);
+      cudaMemcpyAsync(ob, b->ptr, sizeof(float) * mc.out_channels, cudaMemcpyDeviceToDevice, st);
+    }
   }
   // depth transformers (attention.py:96-115)
   const int cm2 = mc.channel_mult[2], cm1 = mc.channel_mult[1], cm0 = mc.channel_mult[0];

@@ -148,6 +148,33 @@ def test_conv3d_3x3x3(nat, Bn, D, H, W, Cin, Cout):
     assert rel(out, ref) < 1e-5
 
 
+@pytest.mark.parametrize("dims", [(2, 1, 32, 32, 64, 128), (3, 1, 8, 8, 128, 64), (2, 12, 8, 8, 64, 128), (1, 48, 32, 32, 64, 64)])
+def test_strided_conv_via_tma_element_strides(nat, dims):
+    """Conv2d / Conv3d k3 s2 p1 (Downsample, FrustumTVBlock stride 2) as an implicit GEMM whose TMA boxes step by 2."""
+    torch.manual_seed(11)
+    Bn, D, H, W, Cin, Cout = dims
+    three_d = D > 1
+    if three_d:
+        x = bf(torch.randn(Bn, Cin, D, H, W, device="cuda"))
+        w = bf(torch.randn(Cout, Cin, 3, 3, 3, device="cuda") / (27 * Cin) ** 0.5)
+        A = x.permute(0, 2, 3, 4, 1).contiguous()
+        Wt = w.permute(0, 2, 3, 4, 1).reshape(Cout, 27 * Cin).contiguous()
+        taps = [(kx - 1, ky - 1, kz - 1) for kz in range(3) for ky in range(3) for kx in range(3)]
+        out = torch.zeros(Bn, D // 2, H // 2, W // 2, Cout, device="cuda")
+        nat.conv_gemm(A, Wt, B=Bn, D=D, H=H, W=W, Cin=Cin, N=Cout, taps=taps, out_f32=out, in_stride=(2, 2, 2))
+        ref = F.conv3d(x.float(), w.float(), None, stride=2, padding=1).permute(0, 2, 3, 4, 1)
+    else:
+        x = bf(torch.randn(Bn, Cin, H, W, device="cuda"))
+        w = bf(torch.randn(Cout, Cin, 3, 3, device="cuda") / (9 * Cin) ** 0.5)
+        A = x.permute(0, 2, 3, 1).contiguous()
+        Wt = w.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).contiguous()
+        taps = [(kx - 1, ky - 1, 0) for ky in range(3) for kx in range(3)]
+        out = torch.zeros(Bn, H // 2, W // 2, Cout, device="cuda")
+        nat.conv_gemm(A, Wt, B=Bn, D=1, H=H, W=W, Cin=Cin, N=Cout, taps=taps, out_f32=out, in_stride=(2, 2, 1))
+        ref = F.conv2d(x.float(), w.float(), None, stride=2, padding=1).permute(0, 2, 3, 1)
+    assert rel(out, ref) < 1e-5
+
+
 def test_gemm_linearity_at_full_size(nat):
     """Size-independent property at the UNet's largest conv (M=32768, K=2880, N=320): conv(a+b) = conv(a)+conv(b)."""
     torch.manual_seed(4)
