@@ -33,38 +33,68 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-constexpr int kAttBQ = 64;   // queries per CTA (4 warps x 16)
 constexpr int kAttBK = 64;   // keys per tile
 
-// DHP: head dim padded to a multiple of 16.  Row stride DHP+8 keeps ldmatrix rows on distinct banks.
-template <int DHP>
-__global__ void __launch_bounds__(128)
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, bool valid) {
+  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(dst));
+  const int sz = valid ? 16 : 0;  // src-size 0 => 16 bytes of zero fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// DHP: head dim padded to a multiple of 16; NW warps x 16 queries per CTA.  Row stride DHP+8 keeps ldmatrix rows on
+// distinct banks.  K/V tiles are double-buffered with cp.async so the next tile streams in while this one is used.
+template <int DHP, int NW>
+__global__ void __launch_bounds__(NW * 32)
 self_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int S, int heads, int dh,
                       float scale_log2e) {
   constexpr int LD = DHP + 8;
+  constexpr int BQ = NW * 16;
+  constexpr int NT = NW * 32;
   extern __shared__ __align__(16) uint8_t att_smem[];
   __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(att_smem);
-  __nv_bfloat16* sK = sQ + kAttBQ * LD;
-  __nv_bfloat16* sV = sK + kAttBK * LD;
+  __nv_bfloat16* sK = sQ + BQ * LD;            // [2][64][LD]
+  __nv_bfloat16* sV = sK + 2 * kAttBK * LD;    // [2][64][LD]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * kAttBQ;
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * BQ;
   const int C = heads * dh;
   const size_t row_stride = static_cast<size_t>(3) * C;
   const __nv_bfloat16* base = qkv + static_cast<size_t>(b) * S * row_stride + h * dh;
   const int chunks = dh / 8;          // 16-byte chunks of real data per row
   constexpr int chunksP = DHP / 8;    // including zero padding
 
-  auto load_tile = [&](__nv_bfloat16* dst, const __nv_bfloat16* src, int r0) {
-    for (int i = threadIdx.x; i < 64 * chunksP; i += 128) {
-      const int r = i / chunksP, c = i % chunksP;
-      uint4 v = make_uint4(0, 0, 0, 0);
-      if (r0 + r < S && c < chunks)
-        v = *reinterpret_cast<const uint4*>(src + static_cast<size_t>(r0 + r) * row_stride + c * 8);
-      *reinterpret_cast<uint4*>(dst + r * LD + c * 8) = v;
+  // Q tile (synchronous) + zero the padding columns of the K/V buffers once
+  for (int i = threadIdx.x; i < BQ * chunksP; i += NT) {
+    const int r = i / chunksP, c = i % chunksP;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (q0 + r < S && c < chunks) v = *reinterpret_cast<const uint4*>(base + static_cast<size_t>(q0 + r) * row_stride + c * 8);
+    *reinterpret_cast<uint4*>(sQ + r * LD + c * 8) = v;
+  }
+  if (chunks < chunksP) {
+    for (int i = threadIdx.x; i < 4 * kAttBK * (chunksP - chunks); i += NT) {
+      const int r = i / (chunksP - chunks), c = chunks + i % (chunksP - chunks);
+      *reinterpret_cast<uint4*>(sK + r * LD + c * 8) = make_uint4(0, 0, 0, 0);  // sK and sV are contiguous: 4*64 rows
     }
+  }
+  auto prefetch = [&](int tile) {
+    const int k0 = tile * kAttBK;
+    __nv_bfloat16* dk = sK + (tile & 1) * kAttBK * LD;
+    __nv_bfloat16* dv = sV + (tile & 1) * kAttBK * LD;
+    for (int i = threadIdx.x; i < kAttBK * chunks; i += NT) {
+      const int r = i / chunks, c = i % chunks;
+      const bool ok = k0 + r < S;
+      const __nv_bfloat16* src = base + static_cast<size_t>(ok ? k0 + r : 0) * row_stride + c * 8;
+      cp_async16(dk + r * LD + c * 8, src + C, ok);
+      cp_async16(dv + r * LD + c * 8, src + 2 * C, ok);
+    }
+    cp_async_commit();
   };
-  load_tile(sQ, base, q0);
+  const int ntiles = (S + kAttBK - 1) / kAttBK;
+  prefetch(0);
   __syncthreads();
 
   // Q fragments stay in registers for the whole kernel
@@ -81,11 +111,12 @@ self_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __re
   for (int i = 0; i < DHP / 8; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
 
-  for (int k0 = 0; k0 < S; k0 += kAttBK) {
+  for (int t = 0; t < ntiles; ++t) {
+    if (t + 1 < ntiles) { prefetch(t + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
     __syncthreads();
-    load_tile(sK, base + C, k0);
-    load_tile(sV, base + 2 * C, k0);
-    __syncthreads();
+    const __nv_bfloat16* tK = sK + (t & 1) * kAttBK * LD;
+    const __nv_bfloat16* tV = sV + (t & 1) * kAttBK * LD;
+    const int k0 = t * kAttBK;
 
     float s[kAttBK / 8][4];
 #pragma unroll
@@ -96,7 +127,7 @@ self_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __re
         uint32_t bf[2];
         const int r = j * 8 + (lane & 7);
         const int c = kk * 16 + ((lane >> 3) & 1) * 8;
-        ldsm_x2(bf, sK + r * LD + c);
+        ldsm_x2(bf, tK + r * LD + c);
         mma_bf16_16816(s[j], qf[kk], bf);
       }
     }
@@ -129,10 +160,10 @@ self_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __re
     uint32_t pf[kAttBK / 16][4];
 #pragma unroll
     for (int j = 0; j < kAttBK / 8; ++j) {
-      const float p0 = exp2f(s[j][0] * scale_log2e - mb0);
-      const float p1 = exp2f(s[j][1] * scale_log2e - mb0);
-      const float p2 = exp2f(s[j][2] * scale_log2e - mb1);
-      const float p3 = exp2f(s[j][3] * scale_log2e - mb1);
+      const float p0 = exp2f(fmaf(s[j][0], scale_log2e, -mb0));
+      const float p1 = exp2f(fmaf(s[j][1], scale_log2e, -mb0));
+      const float p2 = exp2f(fmaf(s[j][2], scale_log2e, -mb1));
+      const float p3 = exp2f(fmaf(s[j][3], scale_log2e, -mb1));
       l0 += p0 + p1; l1 += p2 + p3;
       pf[j >> 1][(j & 1) * 2 + 0] = pack_bf16(p0, p1);
       pf[j >> 1][(j & 1) * 2 + 1] = pack_bf16(p2, p3);
@@ -143,10 +174,11 @@ self_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __re
       for (int i = 0; i < DHP / 8; ++i) {
         uint32_t bf[2];
         const int r = kk * 16 + (lane & 15);
-        ldsm_x2_trans(bf, sV + r * LD + i * 8);
+        ldsm_x2_trans(bf, tV + r * LD + i * 8);
         mma_bf16_16816(o[i], pf[kk], bf);
       }
     }
+    __syncthreads();  // everyone done with buffer t&1 before it is refilled (tile t+2)
   }
   l0 += __shfl_xor_sync(0xffffffff, l0, 1);
   l0 += __shfl_xor_sync(0xffffffff, l0, 2);
@@ -166,27 +198,30 @@ self_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __re
   }
 }
 
-template <int DHP>
+template <int DHP, int NW>
 static int self_attention_impl(const void* qkv, void* out, int B, int S, int heads, int dh, cudaStream_t st) {
   constexpr int LD = DHP + 8;
-  const int smem = (kAttBQ + 2 * kAttBK) * LD * 2;
+  constexpr int BQ = NW * 16;
+  const int smem = (BQ + 4 * kAttBK) * LD * 2;
   static bool attr = false;
   if (!attr) {
-    MD_CUDA(cudaFuncSetAttribute(self_attention_kernel<DHP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    MD_CUDA(cudaFuncSetAttribute(self_attention_kernel<DHP, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr = true;
   }
-  dim3 grid((S + kAttBQ - 1) / kAttBQ, heads, B);
+  dim3 grid((S + BQ - 1) / BQ, heads, B);
   const float scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(dh));
-  self_attention_kernel<DHP><<<grid, 128, smem, st>>>(static_cast<const __nv_bfloat16*>(qkv),
-                                                      static_cast<__nv_bfloat16*>(out), S, heads, dh, scale_log2e);
+  self_attention_kernel<DHP, NW><<<grid, NW * 32, smem, st>>>(static_cast<const __nv_bfloat16*>(qkv),
+                                                              static_cast<__nv_bfloat16*>(out), S, heads, dh,
+                                                              scale_log2e);
   return check_launch("self_attention");
 }
 
 int launch_self_attention(const void* qkv, void* out, int B, int S, int heads, int dh, cudaStream_t st) {
   if (dh % 8) return set_error("self_attention: head dim %d must be a multiple of 8", dh);
-  if (dh <= 48) return self_attention_impl<48>(qkv, out, B, S, heads, dh, st);
-  if (dh <= 80) return self_attention_impl<80>(qkv, out, B, S, heads, dh, st);
-  if (dh <= 160) return self_attention_impl<160>(qkv, out, B, S, heads, dh, st);
+  const bool big = S >= 128;  // 8 warps x 16 queries per CTA when the sequence is long enough to fill them
+  if (dh <= 48) return big ? self_attention_impl<48, 8>(qkv, out, B, S, heads, dh, st) : self_attention_impl<48, 4>(qkv, out, B, S, heads, dh, st);
+  if (dh <= 80) return big ? self_attention_impl<80, 8>(qkv, out, B, S, heads, dh, st) : self_attention_impl<80, 4>(qkv, out, B, S, heads, dh, st);
+  if (dh <= 160) return big ? self_attention_impl<160, 8>(qkv, out, B, S, heads, dh, st) : self_attention_impl<160, 4>(qkv, out, B, S, heads, dh, st);
   return set_error("self_attention: head dim %d unsupported", dh);
 }
 

@@ -110,6 +110,7 @@ int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
       for (int ci = 0; ci < 4; ++ci) {
         const int bn = cands[ci];
         if (bn > 64 && a.N <= bn / 2) continue;                 // mostly-empty tile
+        if (bn == 256 && p.ntaps * p.kblocks_per_tap < 16) continue;  // 4-warp epilogue variant: needs a long K loop to hide it
         const long long tiles = static_cast<long long>(p.m_tiles) * ((a.N + bn - 1) / bn);
         const long long waves = (tiles + num_sms() - 1) / num_sms();
         const long long cost = waves * (bn + 24);               // +24: per-tile fixed cost (pipeline fill, epilogue tail)

@@ -409,15 +409,50 @@ __global__ void sparse_conv_kernel(const float* __restrict__ in, const int32_t* 
   }
 }
 
+// Wide layers (Cin >= 32): one thread per (row, 4 output channels) — float4 weight loads coalesced over co.
+__global__ void sparse_conv_quad_kernel(const float* __restrict__ in, const int32_t* __restrict__ nbr,
+                                        const float* __restrict__ W, const float* __restrict__ scale,
+                                        const float* __restrict__ shift, float* __restrict__ out, int n_rows, int Cin,
+                                        int Cout) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int CQ = Cout >> 2;
+  if (i >= n_rows * CQ) return;
+  const int cq = i % CQ, r = i / CQ;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int k = 0; k < 27; ++k) {
+    const int j = __ldg(nbr + r * 27 + k);
+    if (j < 0) continue;
+    const float4* ip = reinterpret_cast<const float4*>(in + static_cast<size_t>(j) * Cin);
+    const float* wp = W + static_cast<size_t>(k) * Cin * Cout + cq * 4;
+#pragma unroll 4
+    for (int c4 = 0; c4 < (Cin >> 2); ++c4) {
+      const float4 a = __ldg(ip + c4);
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(wp + static_cast<size_t>(c4 * 4 + 0) * Cout));
+      const float4 w1 = __ldg(reinterpret_cast<const float4*>(wp + static_cast<size_t>(c4 * 4 + 1) * Cout));
+      const float4 w2 = __ldg(reinterpret_cast<const float4*>(wp + static_cast<size_t>(c4 * 4 + 2) * Cout));
+      const float4 w3 = __ldg(reinterpret_cast<const float4*>(wp + static_cast<size_t>(c4 * 4 + 3) * Cout));
+      acc.x += a.x * w0.x + a.y * w1.x + a.z * w2.x + a.w * w3.x;
+      acc.y += a.x * w0.y + a.y * w1.y + a.z * w2.y + a.w * w3.y;
+      acc.z += a.x * w0.z + a.y * w1.z + a.z * w2.z + a.w * w3.z;
+      acc.w += a.x * w0.w + a.y * w1.w + a.z * w2.w + a.w * w3.w;
+    }
+  }
+  const float4 sc = *reinterpret_cast<const float4*>(scale + cq * 4);
+  const float4 sh = *reinterpret_cast<const float4*>(shift + cq * 4);
+  float4 o;
+  o.x = fmaxf(acc.x * sc.x + sh.x, 0.f); o.y = fmaxf(acc.y * sc.y + sh.y, 0.f);
+  o.z = fmaxf(acc.z * sc.z + sh.z, 0.f); o.w = fmaxf(acc.w * sc.w + sh.w, 0.f);
+  *reinterpret_cast<float4*>(out + static_cast<size_t>(r) * Cout + cq * 4) = o;
+}
+
 int launch_sparse_conv(const float* in, const int32_t* nbr, const float* W, const float* scale, const float* shift,
                        float* out, int n_rows, int Cin, int Cout, cudaStream_t st) {
   if (n_rows == 0) return 0;
   const unsigned blocks = (static_cast<unsigned>(n_rows) * 32 + 127) / 128;
   if (Cin == 16 && Cout == 16) sparse_conv_kernel<16, 16><<<blocks, 128, 0, st>>>(in, nbr, W, scale, shift, out, n_rows);
   else if (Cin == 16 && Cout == 32) sparse_conv_kernel<16, 32><<<blocks, 128, 0, st>>>(in, nbr, W, scale, shift, out, n_rows);
-  else if (Cin == 32 && Cout == 32) sparse_conv_kernel<32, 32><<<blocks, 128, 0, st>>>(in, nbr, W, scale, shift, out, n_rows);
-  else if (Cin == 32 && Cout == 64) sparse_conv_kernel<32, 64><<<blocks, 128, 0, st>>>(in, nbr, W, scale, shift, out, n_rows);
-  else if (Cin == 64 && Cout == 64) sparse_conv_kernel<64, 64><<<blocks, 128, 0, st>>>(in, nbr, W, scale, shift, out, n_rows);
+  else if (Cin % 4 == 0 && Cout % 4 == 0)
+    sparse_conv_quad_kernel<<<(n_rows * (Cout / 4) + 63) / 64, 64, 0, st>>>(in, nbr, W, scale, shift, out, n_rows, Cin, Cout);
   else return set_error("sparse_conv: unsupported channels %d -> %d", Cin, Cout);
   return check_launch("sparse_conv");
 }
