@@ -233,9 +233,10 @@ static int group_norm_impl(const GroupNormArgs& a, cudaStream_t st) {
   const int threads = CQ * R;
   if (a.stats0 && (a.C1 == 0 || a.stats1) && a.out) {
     // statistics came from the producers: one fused finalize+apply launch
-    const int target = num_sms() * 4;
+    const int target = num_sms() * 8;
     int rows_per_cta = std::max(1, static_cast<int>((static_cast<long long>(a.rows) * a.B + target - 1) / target));
-    rows_per_cta = std::min(std::max(rows_per_cta, 8), a.rows);
+    const int min_rows = std::max(4, 16384 / C);  // keep the per-CTA statistics prologue small next to the streamed slab
+    rows_per_cta = std::min(std::max(rows_per_cta, min_rows), a.rows);
     dim3 grid((a.rows + rows_per_cta - 1) / rows_per_cta, a.B);
     gn_apply_fused_kernel<T0, T1><<<grid, 256, static_cast<size_t>(C) * 2 * sizeof(float), st>>>(
         static_cast<const T0*>(a.x0), a.C0, static_cast<const T1*>(a.x1), a.C1, a.stats0, a.stats1, a.gamma, a.beta,

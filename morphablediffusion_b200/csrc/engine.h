@@ -124,7 +124,9 @@ struct Ctx {
   cudaStream_t stream = nullptr;       // internal non-blocking stream the step runs on
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
   float* d_step = nullptr;             // [16] per-step scalars read by the captured kernels
-  cudaGraphExec_t graph = nullptr;
+  cudaGraphExec_t graph = nullptr;     // whole step (single rank) or the part before the cross-rank exchange
+  cudaGraphExec_t graph_b = nullptr;   // multi-rank only: the part after the exchange (NCCL runs between the two)
+  float* vsum_ptr = nullptr;           // [Nv][16] vertex-feature sums of the current step (all-reduced over ranks)
   struct GraphKey { const void* x; const void* xin; const void* clip; const void* noise; const void* eps; float cfg; int bind_gen; int wgen; } gkey{};
   int graph_warm = 0;                  // calls seen with the current key
   int graph_launches = 0;              // kernels inside the captured graph (launch accounting on replay)

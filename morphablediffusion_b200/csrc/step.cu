@@ -110,10 +110,22 @@ static int ensure_ready(md_ctx* ctx, bool need_binding) {
   return 0;
 }
 
+// the single cross-rank exchange of the step: sum over ranks of the per-vertex features
+static int allreduce_vsum(Ctx& c, cudaStream_t st) {
+  if (c.world <= 1) return 0;
+  if (!c.nccl_comm) return set_error("denoise_step: world=%d but no communicator (md_comm_init)", c.world);
+  const int r = g_nccl.AllReduce(c.vsum_ptr, c.vsum_ptr, static_cast<size_t>(c.sb.nv) * 16, /*ncclFloat32*/ 7,
+                                 /*ncclSum*/ 0, c.nccl_comm, st);
+  if (r != 0) return set_error("ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+  return 0;
+}
+
 // one denoise step for the local views (all chunks)
 static int denoise_step_impl(Ctx& c, float* x_local, const float* x_input, const float* clip, int index,
                              float cfg_scale, const float* noise, unsigned long long seed, float* eps_out,
-                             int do_update, cudaStream_t st) {
+                             int do_update, cudaStream_t st, int phase = 0) {
+  // phase 0: whole step (the all-reduce is issued inline); phase 1: only the part before the cross-rank exchange;
+  // phase 2: only the part after it.  Phases 1/2 are captured as two CUDA graphs with the NCCL call between them.
   const md_config& mc = c.mcfg;
   const SampleBinding& sb = c.sb;
   if (index < 0 || index >= static_cast<int>(c.timesteps.size())) return set_error("denoise_step: bad DDIM index %d", index);
@@ -134,17 +146,16 @@ static int denoise_step_impl(Ctx& c, float* x_local, const float* x_input, const
   float* ctxv = A.get<float>(static_cast<size_t>(maxB) * mc.context_dim);
   float* x_in = A.get<float>(static_cast<size_t>(maxB) * HW * 8);
   if (A.failed) return set_error("workspace exhausted (step)");
-  fill_from_kernel<<<(maxB + 63) / 64, 64, 0, st>>>(d_t, c.d_step, maxB);  // timestep of this index (d_step[0])
-  MD_CHECK(check_launch("fill"));
   (void)tval;
-  MD_CHECK(embed_time(c, d_t, t_embed, st));
-  MD_CHECK(vertex_feature_sum(c, x_local, t_embed, vsum, st));
-  if (c.world > 1) {
-    if (!c.nccl_comm) return set_error("denoise_step: world=%d but no communicator", c.world);
-    const int r = g_nccl.AllReduce(vsum, vsum, static_cast<size_t>(sb.nv) * 16, /*ncclFloat32*/ 7, /*ncclSum*/ 0,
-                                   c.nccl_comm, st);
-    if (r != 0) return set_error("ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+  c.vsum_ptr = vsum;
+  if (phase != 2) {
+    fill_from_kernel<<<(maxB + 63) / 64, 64, 0, st>>>(d_t, c.d_step, maxB);  // timestep of this index (d_step[0])
+    MD_CHECK(check_launch("fill"));
+    MD_CHECK(embed_time(c, d_t, t_embed, st));
+    MD_CHECK(vertex_feature_sum(c, x_local, t_embed, vsum, st));
   }
+  if (phase == 0) MD_CHECK(allreduce_vsum(c, st));
+  if (phase == 1) return 0;
   MD_CHECK(spatial_volume_from_vsum(c, vsum, vol, st));
 
   const size_t m = A.mark();
@@ -237,6 +248,7 @@ void md_destroy(md_ctx* ctx) {
   free_weights(ctx->c);
   if (ctx->c.nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->c.nccl_comm);
   if (ctx->c.graph) cudaGraphExecDestroy(ctx->c.graph);
+  if (ctx->c.graph_b) cudaGraphExecDestroy(ctx->c.graph_b);
   if (ctx->c.stream) cudaStreamDestroy(ctx->c.stream);
   if (ctx->c.ev_in) cudaEventDestroy(ctx->c.ev_in);
   if (ctx->c.ev_out) cudaEventDestroy(ctx->c.ev_out);
@@ -301,10 +313,8 @@ int md_spatial_volume(md_ctx* ctx, const float* x_local, const float* t_embed, f
   float* vol = A.get<float>(static_cast<size_t>(V) * V * V * 64);
   if (A.failed) return set_error("workspace exhausted");
   MD_CHECK(vertex_feature_sum(c, x_local, t_embed, vsum, st));
-  if (c.world > 1 && c.nccl_comm) {
-    const int r = g_nccl.AllReduce(vsum, vsum, static_cast<size_t>(c.sb.nv) * 16, 7, 0, c.nccl_comm, st);
-    if (r != 0) return set_error("ncclAllReduce failed (%d)", r);
-  }
+  c.vsum_ptr = vsum;
+  if (c.world > 1 && c.nccl_comm) MD_CHECK(allreduce_vsum(c, st));
   MD_CHECK(spatial_volume_from_vsum(c, vsum, vol, st));
   return launch_cl_to_ncdhw(vol, 0, volume_out, 1, 64, static_cast<size_t>(V) * V * V, st);
 }
@@ -384,11 +394,16 @@ int md_denoise_step(md_ctx* ctx, float* x_local, const float* x_input, const flo
     rc = denoise_step_impl(c, x_local, x_input, clip_embed, index, cfg_scale, noise, seed, eps_out, 1, st);
   } else if (same && c.graph) {
     cudaError_t e = cudaGraphLaunch(c.graph, st);
+    if (e == cudaSuccess && c.graph_b) {  // multi-rank: [graph A] -> NCCL all-reduce (not captured) -> [graph B]
+      rc = allreduce_vsum(c, st);
+      if (rc == 0) e = cudaGraphLaunch(c.graph_b, st);
+    }
     if (e != cudaSuccess) rc = set_error("cudaGraphLaunch: %s", cudaGetErrorString(e));
-    else count_launch(c.graph_launches);
+    else if (rc == 0) count_launch(c.graph_launches);
   } else {
     if (!same) {
       if (c.graph) { cudaGraphExecDestroy(c.graph); c.graph = nullptr; }
+      if (c.graph_b) { cudaGraphExecDestroy(c.graph_b); c.graph_b = nullptr; }
       c.gkey = key;
       c.graph_warm = 0;
     }
@@ -397,24 +412,35 @@ int md_denoise_step(md_ctx* ctx, float* x_local, const float* x_input, const flo
       c.graph_warm = 1;
     } else {                  // second call: capture, instantiate, launch
       const long long before = md_launch_count();
-      cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed);
-      if (e != cudaSuccess) return set_error("cudaStreamBeginCapture: %s", cudaGetErrorString(e));
-      rc = denoise_step_impl(c, x_local, x_input, clip_embed, index, cfg_scale, noise, seed, eps_out, 1, st);
-      cudaGraph_t g = nullptr;
-      e = cudaStreamEndCapture(st, &g);
-      if (rc == 0 && e != cudaSuccess) rc = set_error("cudaStreamEndCapture: %s", cudaGetErrorString(e));
-      if (rc == 0) {
-        e = cudaGraphInstantiate(&c.graph, g, 0);
-        if (e != cudaSuccess) rc = set_error("cudaGraphInstantiate: %s", cudaGetErrorString(e));
-      }
-      if (g) cudaGraphDestroy(g);
+      const bool split = c.world > 1;
+      auto capture = [&](int phase, cudaGraphExec_t* out) -> int {
+        cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed);
+        if (e != cudaSuccess) return set_error("cudaStreamBeginCapture: %s", cudaGetErrorString(e));
+        int r = denoise_step_impl(c, x_local, x_input, clip_embed, index, cfg_scale, noise, seed, eps_out, 1, st, phase);
+        cudaGraph_t g = nullptr;
+        e = cudaStreamEndCapture(st, &g);
+        if (r == 0 && e != cudaSuccess) r = set_error("cudaStreamEndCapture: %s", cudaGetErrorString(e));
+        if (r == 0) {
+          e = cudaGraphInstantiate(out, g, 0);
+          if (e != cudaSuccess) r = set_error("cudaGraphInstantiate: %s", cudaGetErrorString(e));
+        }
+        if (g) cudaGraphDestroy(g);
+        return r;
+      };
+      rc = capture(split ? 1 : 0, &c.graph);
+      if (rc == 0 && split) rc = capture(2, &c.graph_b);
       c.graph_launches = static_cast<int>(md_launch_count() - before);
       if (rc == 0) {
-        e = cudaGraphLaunch(c.graph, st);
+        cudaError_t e = cudaGraphLaunch(c.graph, st);
+        if (e == cudaSuccess && split) {
+          rc = allreduce_vsum(c, st);
+          if (rc == 0) e = cudaGraphLaunch(c.graph_b, st);
+        }
         if (e != cudaSuccess) rc = set_error("cudaGraphLaunch: %s", cudaGetErrorString(e));
-      } else if (c.graph) {
-        cudaGraphExecDestroy(c.graph);
-        c.graph = nullptr;
+      }
+      if (rc != 0) {
+        if (c.graph) { cudaGraphExecDestroy(c.graph); c.graph = nullptr; }
+        if (c.graph_b) { cudaGraphExecDestroy(c.graph_b); c.graph_b = nullptr; }
       }
     }
   }
