@@ -60,6 +60,7 @@ typedef struct md_conv_gemm_args {
   int BN;                   /* tile N override (64/128/160/256), 0 = auto */
   float* col_stats;         /* optional [B][stats_ld][2] sum / sum-of-squares accumulation (atomics; pre-zeroed) */
   int stats_ld;             /* 0 -> N */
+  int ksplit;               /* split-K factor: 0 = auto, 1 / -1 = off, >1 = forced */
   int in_stride[3];         /* strided conv: input coord = tile coord * in_stride + tap (x,y,z); 0 -> 1.  B,D,H,W then
                                describe the INPUT tensor and the tile grid covers ceil(dim / in_stride) positions */
 } md_conv_gemm_args;

@@ -24,6 +24,28 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
+// split-K workspace (process-wide, allocated on first use; kernels on one stream are ordered, so sharing is safe)
+static float* g_split_ws = nullptr;
+static size_t g_split_ws_bytes = 0;
+static int* g_split_cnt = nullptr;
+static size_t g_split_cnt_ints = 0;
+
+int ensure_split_workspace() {
+  if (g_split_ws) return 0;
+  const size_t bytes = static_cast<size_t>(96) << 20;
+  const size_t ints = 1 << 16;
+  void* w = nullptr;
+  void* c = nullptr;
+  if (cudaMalloc(&w, bytes) != cudaSuccess || cudaMalloc(&c, ints * sizeof(int)) != cudaSuccess) {
+    cudaGetLastError();
+    return set_error("conv_gemm: split-K workspace allocation failed");
+  }
+  cudaMemset(c, 0, ints * sizeof(int));
+  g_split_ws = static_cast<float*>(w); g_split_ws_bytes = bytes;
+  g_split_cnt = static_cast<int*>(c); g_split_cnt_ints = ints;
+  return 0;
+}
+
 static int pow2_floor(int v) {
   int p = 1;
   while (p * 2 <= v) p *= 2;
@@ -49,6 +71,7 @@ static int launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const Con
 }
 
 int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
+  if (!g_split_ws && a.ksplit >= 0) MD_CHECK(ensure_split_workspace());
   PFN_encodeTiled enc = get_encode();
   if (!enc) return set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
   if (a.Cin % kBlockK != 0) return set_error("conv_gemm: Cin=%d must be a multiple of 64", a.Cin);
@@ -99,21 +122,30 @@ int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
   if (p.ldo % 8 != 0) return set_error("conv_gemm: ldo=%d must be a multiple of 8", p.ldo);
   if (a.act == ACT_GEGLU && !a.out_bf16) return set_error("conv_gemm: GEGLU epilogue writes bf16 only");
 
-  // ---- tile N selection: minimise waves x per-tile MMA time (proportional to BN), prefer the wider tile on ties
+  // ---- tile N and split-K selection: minimise  waves x (per-tile MMA time ~ BN, divided by the K split)  plus a
+  // reduction overhead for split tiles; prefer the wider tile on ties (fewer re-reads of the activation tile)
+  const int kblocks_all = p.ntaps * p.kblocks_per_tap;
+  auto auto_split = [&](long long tiles) {
+    if (a.ksplit != 0 || a.act == ACT_GEGLU || !g_split_ws) return 1;
+    if (tiles * 2 > num_sms() || kblocks_all < 8) return 1;
+    const long long ks = std::min<long long>(std::min<long long>(num_sms() / tiles, kblocks_all / 4), 16);
+    return static_cast<int>(std::max<long long>(ks, 1));
+  };
   int BN = a.BN;
   if (BN == 0) {
     if (a.act == ACT_GEGLU) {
       BN = 128;
     } else {
       const int cands[4] = {256, 160, 128, 64};
-      long long best = -1;
+      double best = -1.0;
       for (int ci = 0; ci < 4; ++ci) {
         const int bn = cands[ci];
-        if (bn > 64 && a.N <= bn / 2) continue;                 // mostly-empty tile
-        if (bn == 256 && p.ntaps * p.kblocks_per_tap < 16) continue;  // 4-warp epilogue variant: needs a long K loop to hide it
+        if (bn > 64 && a.N <= bn / 2) continue;                       // mostly-empty tile
+        if (bn == 256 && kblocks_all < 16) continue;                   // 4-warp epilogue variant needs a long K loop
         const long long tiles = static_cast<long long>(p.m_tiles) * ((a.N + bn - 1) / bn);
-        const long long waves = (tiles + num_sms() - 1) / num_sms();
-        const long long cost = waves * (bn + 24);               // +24: per-tile fixed cost (pipeline fill, epilogue tail)
+        const int ks = auto_split(tiles);
+        const long long waves = (tiles * ks + num_sms() - 1) / num_sms();
+        const double cost = waves * (bn + 24.0) / ks + (ks > 1 ? 0.15 * (bn + 24.0) : 0.0);
         if (best < 0 || cost < best) { best = cost; BN = bn; }
       }
     }
@@ -149,13 +181,31 @@ int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
                                             (unsigned long long)Ktot, a.N);
   }
 
-  const int total = p.m_tiles * p.n_tiles;
+  // ---- split-K for tile-starved problems (few output tiles, long K loop): fills the machine and multiplies the
+  // bytes in flight of what is otherwise a weight-streaming loop on a handful of SMs
+  p.ksplit = 1;
+  if (a.ksplit > 1) {
+    p.ksplit = a.ksplit;
+  } else {
+    p.ksplit = auto_split(static_cast<long long>(p.m_tiles) * p.n_tiles);
+  }
+  if (p.ksplit > 1) {
+    if (a.act == ACT_GEGLU) return set_error("conv_gemm: split-K is not available with the GEGLU epilogue");
+    const size_t need = static_cast<size_t>(p.m_tiles) * p.n_tiles * p.ksplit * 128 * BN * sizeof(float);
+    if (!g_split_ws || need > g_split_ws_bytes || static_cast<size_t>(p.m_tiles) * p.n_tiles * 8 > g_split_cnt_ints) {
+      if (a.ksplit > 1) return set_error("conv_gemm: split-K workspace too small (%zu bytes needed)", need);
+      p.ksplit = 1;
+    }
+    p.split_ws = g_split_ws;
+    p.split_cnt = g_split_cnt;
+  }
+  const int total = p.m_tiles * p.n_tiles * p.ksplit;
   const int grid = std::min(total, num_sms());
-  p.contig = (p.n_tiles == 1 && total > 2 * grid) ? 1 : 0;
+  p.contig = (p.n_tiles == 1 && p.ksplit == 1 && total > 2 * grid) ? 1 : 0;
   static const bool trace = getenv("MD_TRACE") != nullptr;
   if (trace)
-    fprintf(stderr, "conv_gemm B=%d D=%d H=%d W=%d Cin=%d taps=%d N=%d BN=%d tiles=%dx%d act=%d f32=%d bf16=%d res=%d\n",
-            a.B, a.D, a.H, a.W, a.Cin, a.ntaps, a.N, BN, p.m_tiles, p.n_tiles, a.act, a.out_f32 != nullptr,
+    fprintf(stderr, "conv_gemm B=%d D=%d H=%d W=%d Cin=%d taps=%d N=%d BN=%d tiles=%dx%d ks=%d act=%d f32=%d bf16=%d res=%d\n",
+            a.B, a.D, a.H, a.W, a.Cin, a.ntaps, a.N, BN, p.m_tiles, p.n_tiles, p.ksplit, a.act, a.out_f32 != nullptr,
             a.out_bf16 != nullptr, a.res_f32 != nullptr || a.res_bf16 != nullptr);
   switch (BN) {
     case 64:  return launch_impl<64, 7, 8>(tmA, tmB, p, grid, stream);

@@ -47,6 +47,10 @@ struct ConvGemmParams {
   float* col_stats; // optional [B][stats_ld][2]: per-(sample, channel) sum / sum of squares of the fp32 result
   int stats_ld;
   int contig;       // contiguous tile run per CTA (see kernel)
+  int ksplit;       // split-K factor: work item = (tile, split); partial accumulators meet in split_ws, the last
+                    // arriving warp of every (tile, epilogue-warp) pair reduces them and runs the real epilogue
+  float* split_ws;  // [tiles][ksplit][128][BN] fp32
+  int* split_cnt;   // [tiles][EPI_WARPS] arrival counters (zero on entry, reset by the last arrival)
   int isx, isy, isz; // input coordinate = output-tile coordinate * is + tap offset (strided convolution via TMA element strides)
 };
 
@@ -251,7 +255,8 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, uint8_t* 
     for (int e = 0; e < 4; ++e) { st1[k][e] = 0.f; st2[k][e] = 0.f; }
   int st_sample = -1, st_ntile = -1;
   int lt = 0;
-  for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++lt) {
+  for (int item = tile_begin; item < tile_end; item += tile_step, ++lt) {
+    const int tile = item / p.ksplit, sp = item - tile * p.ksplit;
     const int a = lt & 1;
     const uint32_t aph = (lt >> 1) & 1;
     const int n_tile = tile % p.n_tiles;
@@ -288,7 +293,58 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, uint8_t* 
     mbar_wait(&tmem_full[a], aph);
     tc_fence_after();
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * BN;
-    switch (mode) {
+    bool run_epilogue = true;
+    if (p.ksplit > 1) {
+      // split-K: publish this warp's partial accumulators, take a ticket; the last arrival for this (tile, warp)
+      // adds the other splits' partials back into TMEM and then runs the ordinary epilogue on the full sums.
+      const int acc_chunks = BN / 32;
+      float* ws_tile = p.split_ws + static_cast<size_t>(tile) * p.ksplit * (128 * BN);
+      float* mine = ws_tile + static_cast<size_t>(sp) * (128 * BN) + static_cast<size_t>(r) * BN;
+      for (int c = c_begin; c < acc_chunks; c += c_step) {
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + c * 32, v);
+        tc_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          __stcg(reinterpret_cast<float4*>(mine + c * 32) + j,
+                 make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                             __uint_as_float(v[4 * j + 3])));
+      }
+      __threadfence();
+      __syncwarp();
+      int last = 0;
+      if (lane == 0) {
+        int* cnt = p.split_cnt + tile * EPI_WARPS + ew;
+        last = (atomicAdd(cnt, 1) == p.ksplit - 1) ? 1 : 0;
+        if (last) *cnt = 0;  // ready for the next launch
+      }
+      last = __shfl_sync(0xffffffff, last, 0);
+      run_epilogue = last != 0;
+      if (run_epilogue) {
+        __threadfence();
+        for (int c = c_begin; c < acc_chunks; c += c_step) {
+          uint32_t v[32];
+          tmem_ld_32x32(taddr + c * 32, v);
+          tc_wait_ld();
+          for (int s2 = 0; s2 < p.ksplit; ++s2) {
+            if (s2 == sp) continue;
+            const float4* o = reinterpret_cast<const float4*>(ws_tile + static_cast<size_t>(s2) * (128 * BN) +
+                                                              static_cast<size_t>(r) * BN + c * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 t = __ldcg(o + j);
+              v[4 * j] = __float_as_uint(__uint_as_float(v[4 * j]) + t.x);
+              v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + t.y);
+              v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + t.z);
+              v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + t.w);
+            }
+          }
+          tmem_st_32x32(taddr + c * 32, v);
+        }
+        tc_wait_st();
+      }
+    }
+    if (run_epilogue) switch (mode) {
       case 0: epilogue_tile<BN, 0, false, NCH, STATS>(p, taddr, stage, bias_s, lane, n_tile, rowinfo, c_begin, c_step, st1, st2); break;
       case 1: epilogue_tile<BN, 0, true, NCH, STATS>(p, taddr, stage, bias_s, lane, n_tile, rowinfo, c_begin, c_step, st1, st2); break;
       case 2: epilogue_tile<BN, 1, false, NCH, STATS>(p, taddr, stage, bias_s, lane, n_tile, rowinfo, c_begin, c_step, st1, st2); break;
@@ -342,7 +398,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int total_tiles = p.m_tiles * p.n_tiles * p.ksplit;  // work items: (tile, K split)
   const int kblocks = p.ntaps * p.kblocks_per_tap;
   // Tile schedule: interleaved (tile = cta + i*grid) or, for tall single-N-tile problems, one contiguous run per CTA
   // (consecutive tiles then share a sample, which lets the epilogue keep GroupNorm partial sums in registers).
@@ -355,7 +411,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ===================== TMA producer =====================
     if (lane == 0) {
       int it = 0;
-      for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
+      for (int item = tile_begin; item < tile_end; item += tile_step) {
+        const int tile = item / p.ksplit, sp = item - tile * p.ksplit;
+        const int kb0 = (kblocks * sp) / p.ksplit, kb1 = (kblocks * (sp + 1)) / p.ksplit;
         const int n_tile = tile % p.n_tiles;
         int m = tile / p.n_tiles;
         const int xb = m % p.nxb; m /= p.nxb;
@@ -363,19 +421,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int zb = m % p.nzb; m /= p.nzb;
         const int x0 = xb * p.bw * p.isx, y0 = yb * p.bh * p.isy, z0 = zb * p.bd * p.isz, b0 = m * p.bb;
         const int n0 = n_tile * BN;
-        int kcol = 0;
-        for (int tap = 0; tap < p.ntaps; ++tap) {
-          const int cx = x0 + p.tdx[tap], cy = y0 + p.tdy[tap], cz = z0 + p.tdz[tap];
-          for (int kc = 0; kc < p.kblocks_per_tap; ++kc, ++it, kcol += kBlockK) {
-            const int s = it % STAGES;
-            const uint32_t ph = (it / STAGES) & 1;
-            mbar_wait(&empty_bar[s], ph ^ 1);
-            uint8_t* sa = smem + s * S::kStageBytes;
-            uint8_t* sb = sa + S::kABytes;
-            mbar_expect_tx(&full_bar[s], S::kStageBytes);
-            tma_load_5d(sa, &tmA, &full_bar[s], kc * kBlockK, cx, cy, cz, b0);
-            tma_load_2d(sb, &tmB, &full_bar[s], kcol, n0);
-          }
+        int tap = kb0 / p.kblocks_per_tap, kc = kb0 - tap * p.kblocks_per_tap;
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sa = smem + s * S::kStageBytes;
+          uint8_t* sb = sa + S::kABytes;
+          mbar_expect_tx(&full_bar[s], S::kStageBytes);
+          tma_load_5d(sa, &tmA, &full_bar[s], kc * kBlockK, x0 + p.tdx[tap], y0 + p.tdy[tap], z0 + p.tdz[tap], b0);
+          tma_load_2d(sb, &tmB, &full_bar[s], kb * kBlockK, n0);
+          if (++kc == p.kblocks_per_tap) { kc = 0; ++tap; }
         }
       }
     }
@@ -385,13 +441,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BN);
       int it = 0;
       int lt = 0;
-      for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++lt) {
+      for (int item = tile_begin; item < tile_end; item += tile_step, ++lt) {
+        const int sp = item % p.ksplit;
+        const int nkb = (kblocks * (sp + 1)) / p.ksplit - (kblocks * sp) / p.ksplit;
         const int a = lt & 1;
         const uint32_t aph = (lt >> 1) & 1;
         mbar_wait(&tmem_empty[a], aph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + a * BN;
-        for (int kb = 0; kb < kblocks; ++kb, ++it) {
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&full_bar[s], ph);

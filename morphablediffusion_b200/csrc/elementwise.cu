@@ -163,39 +163,49 @@ __global__ void gn_apply_fused_kernel(const T0* __restrict__ x0, int C0, const T
                                       const float* __restrict__ addvec, int addvec_ld, __nv_bfloat16* __restrict__ out,
                                       __nv_bfloat16* __restrict__ raw, int rows, int rows_per_cta, int G, float eps,
                                       int act) {
-  extern __shared__ float ssm[];  // [C][2] scale, shift
+  extern __shared__ float ssm[];  // [C][2]: first the per-channel sums, then scale / shift
+  __shared__ float gmean[64], grstd[64];
   const int C = C0 + C1;
   const int b = blockIdx.y;
   const int cpg = C / G;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const float nrows = static_cast<float>(rows);
+  // (1) all threads: per-channel sums of (x + addvec) into shared memory
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float* sp = (c < C0) ? stats0 + (static_cast<size_t>(b) * C0 + c) * 2
+                               : stats1 + (static_cast<size_t>(b) * C1 + (c - C0)) * 2;
+    const float a = sp[0], q = sp[1];
+    const float tv = addvec ? addvec[static_cast<size_t>(b) * addvec_ld + c] : 0.f;
+    ssm[2 * c] = a + nrows * tv;
+    ssm[2 * c + 1] = q + 2.f * tv * a + nrows * tv * tv;
+  }
+  __syncthreads();
+  // (2) one warp per group: mean / rstd (double accumulation of the per-channel partials)
   for (int g = warp; g < G; g += nwarps) {
     double s1 = 0.0, s2 = 0.0;
-    for (int c = g * cpg + lane; c < (g + 1) * cpg; c += 32) {
-      const float* sp = (c < C0) ? stats0 + (static_cast<size_t>(b) * C0 + c) * 2
-                                 : stats1 + (static_cast<size_t>(b) * C1 + (c - C0)) * 2;
-      const double a = sp[0], q = sp[1];
-      const double tv = addvec ? addvec[static_cast<size_t>(b) * addvec_ld + c] : 0.0;
-      s1 += a + nrows * tv;
-      s2 += q + 2.0 * tv * a + nrows * tv * tv;
-    }
+    for (int c = g * cpg + lane; c < (g + 1) * cpg; c += 32) { s1 += ssm[2 * c]; s2 += ssm[2 * c + 1]; }
 #pragma unroll
     for (int o = 16; o; o >>= 1) {
       s1 += __shfl_xor_sync(0xffffffff, s1, o);
       s2 += __shfl_xor_sync(0xffffffff, s2, o);
     }
-    const double n = static_cast<double>(nrows) * cpg;
-    const double mean = s1 / n;
-    double var = s2 / n - mean * mean;
-    if (var < 0.0) var = 0.0;
-    const float fmean = static_cast<float>(mean);
-    const float frstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
-    for (int c = g * cpg + lane; c < (g + 1) * cpg; c += 32) {
-      const float tv = addvec ? addvec[static_cast<size_t>(b) * addvec_ld + c] : 0.f;
-      const float sc = gamma[c] * frstd;
-      ssm[2 * c] = sc;
-      ssm[2 * c + 1] = beta[c] + (tv - fmean) * sc;
+    if (lane == 0) {
+      const double n = static_cast<double>(nrows) * cpg;
+      const double mean = s1 / n;
+      double var = s2 / n - mean * mean;
+      if (var < 0.0) var = 0.0;
+      gmean[g] = static_cast<float>(mean);
+      grstd[g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
     }
+  }
+  __syncthreads();
+  // (3) all threads: per-channel scale / shift
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    const float tv = addvec ? addvec[static_cast<size_t>(b) * addvec_ld + c] : 0.f;
+    const float sc = gamma[c] * grstd[g];
+    ssm[2 * c] = sc;
+    ssm[2 * c + 1] = beta[c] + (tv - gmean[g]) * sc;
   }
   __syncthreads();
   const int CQ = C >> 2;
@@ -235,7 +245,7 @@ static int group_norm_impl(const GroupNormArgs& a, cudaStream_t st) {
     // statistics came from the producers: one fused finalize+apply launch
     const int target = num_sms() * 8;
     int rows_per_cta = std::max(1, static_cast<int>((static_cast<long long>(a.rows) * a.B + target - 1) / target));
-    const int min_rows = std::max(4, 16384 / C);  // keep the per-CTA statistics prologue small next to the streamed slab
+    const int min_rows = std::max(2, 4096 / C);  // keep the per-CTA statistics prologue small next to the streamed slab
     rows_per_cta = std::min(std::max(rows_per_cta, min_rows), a.rows);
     dim3 grid((a.rows + rows_per_cta - 1) / rows_per_cta, a.B);
     gn_apply_fused_kernel<T0, T1><<<grid, 256, static_cast<size_t>(C) * 2 * sizeof(float), st>>>(

@@ -175,6 +175,28 @@ def test_strided_conv_via_tma_element_strides(nat, dims):
     assert rel(out, ref) < 1e-5
 
 
+@pytest.mark.parametrize("ksplit", [0, 2, 5, 16])
+def test_split_k(nat, ksplit):
+    """Tile-starved conv (4x4 level: M=96 rows, K=9*1280) with the K loop split over CTAs; the last-arriving warp
+    reduces the partials through TMEM and runs the full epilogue (bias + residual + statistics)."""
+    torch.manual_seed(12)
+    Bn, H, W, Cin, Cout = 6, 4, 4, 1280, 320
+    x = bf(torch.randn(Bn, Cin, H, W, device="cuda"))
+    w = bf(torch.randn(Cout, Cin, 3, 3, device="cuda") / (9 * Cin) ** 0.5)
+    bias = torch.randn(Cout, device="cuda")
+    res = torch.randn(Bn, H, W, Cout, device="cuda")
+    A = x.permute(0, 2, 3, 1).contiguous()
+    Wt = w.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).contiguous()
+    taps = [(kx - 1, ky - 1, 0) for ky in range(3) for kx in range(3)]
+    ref = F.conv2d(x.float(), w.float(), bias, padding=1).permute(0, 2, 3, 1) + res
+    for _ in range(3):  # repeated launches: the arrival counters must reset themselves
+        out = torch.zeros(Bn, H, W, Cout, device="cuda")
+        outb = torch.zeros(Bn, H, W, Cout, device="cuda", dtype=torch.bfloat16)
+        nat.conv_gemm(A, Wt, B=Bn, D=1, H=H, W=W, Cin=Cin, N=Cout, taps=taps, bias=bias, res_f32=res, out_f32=out,
+                      out_bf16=outb, ksplit=ksplit)
+        assert rel(out, ref) < 1e-5 and rel(outb, ref) < 5e-3
+
+
 def test_gemm_linearity_at_full_size(nat):
     """Size-independent property at the UNet's largest conv (M=32768, K=2880, N=320): conv(a+b) = conv(a)+conv(b)."""
     torch.manual_seed(4)
