@@ -52,18 +52,18 @@ static int pow2_floor(int v) {
   return p;
 }
 
-template <int BN, int STAGES, int EPI_WARPS>
+template <int BN, int STAGES>
 static int launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p, int grid,
                        cudaStream_t stream) {
-  using S = ConvGemmSmem<BN, STAGES, EPI_WARPS>;
+  using S = ConvGemmSmem<BN, STAGES>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BN, STAGES, EPI_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          S::kTotal);
     if (e != cudaSuccess) return set_error("cudaFuncSetAttribute(conv_gemm): %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  conv_gemm_kernel<BN, STAGES, EPI_WARPS><<<grid, 64 + 32 * EPI_WARPS, S::kTotal, stream>>>(tmA, tmB, p);
+  conv_gemm_kernel<BN, STAGES><<<grid, 64 + 32 * kEpiWarps, S::kTotal, stream>>>(tmA, tmB, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("conv_gemm launch: %s", cudaGetErrorString(e));
   count_launch();
@@ -120,6 +120,9 @@ int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
   if (a.col_stats && ((p.bw * p.bh * p.bd) % 32) != 0)
     return set_error("conv_gemm: fused statistics need >= 32 rows per sample per tile (box %dx%dx%d)", p.bw, p.bh, p.bd);
   if (p.ldo % 8 != 0) return set_error("conv_gemm: ldo=%d must be a multiple of 8", p.ldo);
+  if (static_cast<long long>(a.B) * p.OD * p.OH * p.OW * p.ldo >= (1LL << 31))
+    return set_error("conv_gemm: output of %lld elements exceeds the 32-bit row offsets of the epilogue",
+                     static_cast<long long>(a.B) * p.OD * p.OH * p.OW * p.ldo);
   if (a.act == ACT_GEGLU && !a.out_bf16) return set_error("conv_gemm: GEGLU epilogue writes bf16 only");
 
   // ---- tile N and split-K selection: minimise  waves x (per-tile MMA time ~ BN, divided by the K split)  plus a
@@ -141,7 +144,6 @@ int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
       for (int ci = 0; ci < 4; ++ci) {
         const int bn = cands[ci];
         if (bn > 64 && a.N <= bn / 2) continue;                       // mostly-empty tile
-        if (bn == 256 && kblocks_all < 16) continue;                   // 4-warp epilogue variant needs a long K loop
         const long long tiles = static_cast<long long>(p.m_tiles) * ((a.N + bn - 1) / bn);
         const int ks = auto_split(tiles);
         const long long waves = (tiles * ks + num_sms() - 1) / num_sms();
@@ -192,7 +194,7 @@ int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
   if (p.ksplit > 1) {
     if (a.act == ACT_GEGLU) return set_error("conv_gemm: split-K is not available with the GEGLU epilogue");
     const size_t need = static_cast<size_t>(p.m_tiles) * p.n_tiles * p.ksplit * 128 * BN * sizeof(float);
-    if (!g_split_ws || need > g_split_ws_bytes || static_cast<size_t>(p.m_tiles) * p.n_tiles * 8 > g_split_cnt_ints) {
+    if (!g_split_ws || need > g_split_ws_bytes || static_cast<size_t>(p.m_tiles) * p.n_tiles * kEpiWarps > g_split_cnt_ints) {
       if (a.ksplit > 1) return set_error("conv_gemm: split-K workspace too small (%zu bytes needed)", need);
       p.ksplit = 1;
     }
@@ -208,10 +210,10 @@ int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
             a.B, a.D, a.H, a.W, a.Cin, a.ntaps, a.N, BN, p.m_tiles, p.n_tiles, p.ksplit, a.act, a.out_f32 != nullptr,
             a.out_bf16 != nullptr, a.res_f32 != nullptr || a.res_bf16 != nullptr);
   switch (BN) {
-    case 64:  return launch_impl<64, 7, 8>(tmA, tmB, p, grid, stream);
-    case 128: return launch_impl<128, 5, 8>(tmA, tmB, p, grid, stream);
-    case 160: return launch_impl<160, 5, 8>(tmA, tmB, p, grid, stream);
-    case 256: return launch_impl<256, 4, 4>(tmA, tmB, p, grid, stream);
+    case 64:  return launch_impl<64, 8>(tmA, tmB, p, grid, stream);
+    case 128: return launch_impl<128, 6>(tmA, tmB, p, grid, stream);
+    case 160: return launch_impl<160, 5>(tmA, tmB, p, grid, stream);
+    case 256: return launch_impl<256, 4>(tmA, tmB, p, grid, stream);
     default:  return set_error("conv_gemm: unsupported BN=%d", BN);
   }
 }

@@ -67,33 +67,56 @@ __device__ __forceinline__ float act_gelu(float x) {
   return 0.5f * x * (1.f + copysignf(e, x));
 }
 
-template <int BN, int STAGES, int EPI_WARPS>
+constexpr int kEpiWarps = 16;   // 4 warps per TMEM lane quarter; each owns every 4th 16-column chunk of a tile
+constexpr int kChunk = 16;      // accumulator columns per epilogue chunk (tcgen05.ld 32x32b.x16)
+
+template <int BN, int STAGES>
 struct ConvGemmSmem {
   static constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KB
   static constexpr int kBBytes = BN * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStageOffset = STAGES * kStageBytes;          // EPI_WARPS x 4 KB epilogue staging tiles
-  static constexpr int kBiasOffset = kStageOffset + EPI_WARPS * 4096;  // EPI_WARPS x BN floats
-  static constexpr int kRowOffset = kBiasOffset + EPI_WARPS * BN * 4;  // EPI_WARPS x 32 x (int64 row offset, int sample, pad)
-  static constexpr int kBarOffset = kRowOffset + EPI_WARPS * 32 * 16;
+  static constexpr int kStageOffset = STAGES * kStageBytes;            // kEpiWarps x 2 KB staging tiles (32 rows x 16 fp32)
+  static constexpr int kRowOffset = kStageOffset + kEpiWarps * 2048;   // [2][4 quarters][32] (row offset, sample)
+  static constexpr int kBarOffset = kRowOffset + 2 * 4 * 32 * 8;
   static constexpr int kTotal = kBarOffset + 256;
 };
 
-// Adds a warp's running GroupNorm partial sums to global memory: lanes l, l^8, l^16, l^24 own the same columns.
+// 32 lanes x 16 columns of 32-bit accumulators <-> registers
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+      "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+
+// Adds a warp's running GroupNorm partial sums to global memory.  Phase-2 layout: lane = (row-in-group-of-8 << 2) |
+// 16-byte chunk, so lanes l, l^4, l^8, l^16 own the same 4 columns.
 template <int NCH>
 __device__ __forceinline__ void flush_col_stats(const ConvGemmParams& p, int lane, int sample, int n_out0, int n_limit,
-                                                int c_begin, int c_step, float (&st1)[NCH][4], float (&st2)[NCH][4]) {
-  const int prow = lane >> 3, pchunk = lane & 7;
+                                                int c_begin, float (&st1)[NCH][4], float (&st2)[NCH][4]) {
+  const int prow = lane >> 2, pchunk = lane & 3;
 #pragma unroll
   for (int k = 0; k < NCH; ++k) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      st1[k][e] += __shfl_xor_sync(0xffffffff, st1[k][e], 8);
-      st1[k][e] += __shfl_xor_sync(0xffffffff, st1[k][e], 16);
-      st2[k][e] += __shfl_xor_sync(0xffffffff, st2[k][e], 8);
-      st2[k][e] += __shfl_xor_sync(0xffffffff, st2[k][e], 16);
+#pragma unroll
+      for (int o = 4; o <= 16; o <<= 1) {
+        st1[k][e] += __shfl_xor_sync(0xffffffff, st1[k][e], o);
+        st2[k][e] += __shfl_xor_sync(0xffffffff, st2[k][e], o);
+      }
     }
-    const int col = n_out0 + (c_begin + k * c_step) * 32 + pchunk * 4;
+    const int col = n_out0 + (c_begin + k * 4) * kChunk + pchunk * 4;
     if (prow == 0 && sample >= 0 && col < n_limit) {
       float* cs = p.col_stats + (static_cast<long long>(sample) * p.stats_ld + col) * 2;
 #pragma unroll
@@ -104,18 +127,18 @@ __device__ __forceinline__ void flush_col_stats(const ConvGemmParams& p, int lan
   }
 }
 
-// Epilogue of one output tile for one warp (32 accumulator rows), specialised on the residual kind and on the
-// presence of a per-sample vector so that the inner loops are branch-free.
-//   phase 0: issue the chunk's global loads (per-sample vector, residual) in the coalesced phase-2 layout;
-//   phase 1 (row owner): TMEM -> registers, scale + bias (+ GEGLU), swizzled store into a private 32x32 staging tile;
-//   phase 2 (coalesced; one warp instruction = 4 rows x 128 B): + per-sample vector, activation, + residual,
-//            fp32 / bf16 stores, optional per-(sample, channel) sum / sum-of-squares for the next GroupNorm.
+// Epilogue of one output tile for one warp: its 32 accumulator rows x the 16-column chunks c_begin, c_begin+4, ...
+// Specialised on the residual kind / per-sample vector so that the inner loops are branch-free.
+//   phase 0: issue the chunk's global loads (bias, per-sample vector, residual) in the coalesced phase-2 layout;
+//   phase 1 (row owner): TMEM -> registers, scale (+bias, GEGLU), swizzled store into a private 32x16 staging tile;
+//   phase 2 (coalesced; one warp instruction = 8 rows x 64 B): + bias, + per-sample vector, activation, + residual,
+//            fp32 / bf16 stores, per-(sample, channel) sum / sum-of-squares for the next GroupNorm.
 template <int BN, int RES, bool RV, int NCH, bool STATS>
-__device__ __forceinline__ void epilogue_tile(const ConvGemmParams& p, uint32_t taddr, float* stage, const float* bias_s,
-                                              int lane, int n_tile, const int4* rowinfo, int c_begin, int c_step,
-                                              float (&st1)[NCH][4], float (&st2)[NCH][4]) {
-  const int prow = lane >> 3;   // phase-2 row within a group of 4
-  const int pchunk = lane & 7;  // phase-2 16-byte chunk within the 128-byte row
+__device__ __forceinline__ void epilogue_tile(const ConvGemmParams& p, uint32_t taddr, float* stage, int lane, int n_tile,
+                                              const int2* rowinfo, int c_begin, float (&st1)[NCH][4],
+                                              float (&st2)[NCH][4]) {
+  const int prow = lane >> 2;   // phase-2 row within a group of 8
+  const int pchunk = lane & 3;  // phase-2 16-byte chunk within the 64-byte row
   const bool geglu = (p.act == ACT_GEGLU);
   constexpr int HALF = BN / 2;
   const int out_cols = geglu ? HALF : BN;
@@ -123,55 +146,54 @@ __device__ __forceinline__ void epilogue_tile(const ConvGemmParams& p, uint32_t 
   const int n_out0 = n_tile * out_cols;
   int ci = 0;
 #pragma unroll 1
-  for (int c = c_begin; c < out_cols / 32; c += c_step, ++ci) {
-    const int col = n_out0 + c * 32 + pchunk * 4;
+  for (int c = c_begin; c < out_cols / kChunk; c += 4, ++ci) {
+    const int col = n_out0 + c * kChunk + pchunk * 4;
     const bool col_ok = col < n_limit;
     const int col_safe = col_ok ? col : 0;
     // ---- phase 0: all global loads of this chunk in flight together (invalid rows read a safe address)
-    float4 rv4[8];
-    float4 rs4[8];
-    uint2 rb2[8];
+    float4 rv4[4];
+    float4 rs4[4];
+    uint2 rb2[4];
+    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.bias && !geglu) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col_safe));
     if (RV || RES != 0) {
 #pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int4 ri = rowinfo[it * 4 + prow];  // (row offset lo, hi, sample, -)
-        const bool ok = ri.z >= 0;
-        const long long ro = ok ? ((static_cast<long long>(ri.y) << 32) | static_cast<unsigned int>(ri.x)) : 0;
-        if (RV) rv4[it] = __ldg(reinterpret_cast<const float4*>(p.rowvec + static_cast<long long>(ok ? ri.z : 0) * p.rowvec_ld + col_safe));
+      for (int it = 0; it < 4; ++it) {
+        const int2 ri = rowinfo[it * 8 + prow];  // (row offset in elements or -1, sample)
+        const bool ok = ri.x >= 0;
+        const long long ro = ok ? ri.x : 0;
+        if (RV) rv4[it] = __ldg(reinterpret_cast<const float4*>(p.rowvec + static_cast<long long>(ok ? ri.y : 0) * p.rowvec_ld + col_safe));
         if (RES == 1) rs4[it] = *reinterpret_cast<const float4*>(p.res_f32 + ro + col_safe);
         if (RES == 2) rb2[it] = *reinterpret_cast<const uint2*>(p.res_bf16 + ro + col_safe);
       }
     }
-    // ---- phase 1: accumulator chunk -> staging tile
+    // ---- phase 1: accumulator chunk -> staging tile (16-byte chunk j of row `lane` lands at chunk j ^ ((lane>>1)&3))
     {
-      uint32_t v[32];
-      tmem_ld_32x32(taddr + c * 32, v);
+      uint32_t v[16];
+      tmem_ld_32x16(taddr + c * kChunk, v);
       if (geglu) {
-        uint32_t g[32];
-        tmem_ld_32x32(taddr + HALF + c * 32, g);
+        uint32_t g[16];
+        tmem_ld_32x16(taddr + HALF + c * kChunk, g);
+        const int nb = n_tile * BN + c * kChunk;  // packed-row index of the value half
         tc_wait_ld();
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < 4; ++j) {
+          const float4 bv = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + nb) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4 bg = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + nb + HALF) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
           float4 o;
-          float* of = reinterpret_cast<float*>(&o);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float val = __uint_as_float(v[4 * j + e]) + bias_s[c * 32 + 4 * j + e];
-            const float gate = __uint_as_float(g[4 * j + e]) + bias_s[HALF + c * 32 + 4 * j + e];
-            of[e] = val * act_gelu(gate);
-          }
-          *reinterpret_cast<float4*>(stage + lane * 32 + ((j ^ (lane & 7)) << 2)) = o;
+          o.x = (__uint_as_float(v[4 * j]) + bv.x) * act_gelu(__uint_as_float(g[4 * j]) + bg.x);
+          o.y = (__uint_as_float(v[4 * j + 1]) + bv.y) * act_gelu(__uint_as_float(g[4 * j + 1]) + bg.y);
+          o.z = (__uint_as_float(v[4 * j + 2]) + bv.z) * act_gelu(__uint_as_float(g[4 * j + 2]) + bg.z);
+          o.w = (__uint_as_float(v[4 * j + 3]) + bv.w) * act_gelu(__uint_as_float(g[4 * j + 3]) + bg.w);
+          *reinterpret_cast<float4*>(stage + lane * 16 + ((j ^ ((lane >> 1) & 3)) << 2)) = o;
         }
       } else {
         tc_wait_ld();
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 bb = *reinterpret_cast<const float4*>(bias_s + c * 32 + 4 * j);
-          const float4 o = make_float4(fmaf(__uint_as_float(v[4 * j]), p.out_scale, bb.x),
-                                       fmaf(__uint_as_float(v[4 * j + 1]), p.out_scale, bb.y),
-                                       fmaf(__uint_as_float(v[4 * j + 2]), p.out_scale, bb.z),
-                                       fmaf(__uint_as_float(v[4 * j + 3]), p.out_scale, bb.w));
-          *reinterpret_cast<float4*>(stage + lane * 32 + ((j ^ (lane & 7)) << 2)) = o;
+        for (int j = 0; j < 4; ++j) {
+          const float4 o = make_float4(__uint_as_float(v[4 * j]) * p.out_scale, __uint_as_float(v[4 * j + 1]) * p.out_scale,
+                                       __uint_as_float(v[4 * j + 2]) * p.out_scale, __uint_as_float(v[4 * j + 3]) * p.out_scale);
+          *reinterpret_cast<float4*>(stage + lane * 16 + ((j ^ ((lane >> 1) & 3)) << 2)) = o;
         }
       }
     }
@@ -179,11 +201,12 @@ __device__ __forceinline__ void epilogue_tile(const ConvGemmParams& p, uint32_t 
     // ---- phase 2: coalesced finish
     float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int row = it * 4 + prow;
-      const int4 ri = rowinfo[row];
-      const bool ok = (ri.z >= 0) && col_ok;
-      float4 v4 = *reinterpret_cast<const float4*>(stage + row * 32 + ((pchunk ^ (row & 7)) << 2));
+    for (int it = 0; it < 4; ++it) {
+      const int row = it * 8 + prow;
+      const int2 ri = rowinfo[row];
+      const bool ok = (ri.x >= 0) && col_ok;
+      float4 v4 = *reinterpret_cast<const float4*>(stage + row * 16 + ((pchunk ^ ((row >> 1) & 3)) << 2));
+      v4.x += b4.x; v4.y += b4.y; v4.z += b4.z; v4.w += b4.w;
       if (RV) { v4.x += rv4[it].x; v4.y += rv4[it].y; v4.z += rv4[it].z; v4.w += rv4[it].w; }
       if (p.act == ACT_SILU) {
         v4.x = act_silu(v4.x); v4.y = act_silu(v4.y); v4.z = act_silu(v4.z); v4.w = act_silu(v4.w);
@@ -197,7 +220,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvGemmParams& p, uint32_t 
         v4.x += __uint_as_float(rb2[it].x << 16); v4.y += __uint_as_float(rb2[it].x & 0xffff0000u);
         v4.z += __uint_as_float(rb2[it].y << 16); v4.w += __uint_as_float(rb2[it].y & 0xffff0000u);
       }
-      const long long off = ((static_cast<long long>(ri.y) << 32) | static_cast<unsigned int>(ri.x)) + col;
+      const long long off = static_cast<long long>(ri.x) + col;
       if (p.out_f32 && ok) *reinterpret_cast<float4*>(p.out_f32 + off) = v4;
       if (p.out_bf16 && ok) {
         __nv_bfloat162 lo = __floats2bfloat162_rn(v4.x, v4.y);
@@ -213,14 +236,11 @@ __device__ __forceinline__ void epilogue_tile(const ConvGemmParams& p, uint32_t 
       }
     }
     if (STATS) {
-      // running sums for this warp's ci-th chunk (flushed by the caller when the sample or the N tile changes)
-      {
 #pragma unroll
-        for (int k = 0; k < NCH; ++k) {
-          if (k == ci) {
+      for (int k = 0; k < NCH; ++k) {
+        if (k == ci) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) { st1[k][e] += s1[e]; st2[k][e] += s2[e]; }
-          }
+          for (int e = 0; e < 4; ++e) { st1[k][e] += s1[e]; st2[k][e] += s2[e]; }
         }
       }
     }
@@ -228,26 +248,22 @@ __device__ __forceinline__ void epilogue_tile(const ConvGemmParams& p, uint32_t 
   }
 }
 
-// Epilogue warps: loop over this CTA's tiles (same schedule as the producer / MMA warps).
-template <int BN, int STAGES, int EPI_WARPS, bool STATS>
+// Epilogue warps: loop over this CTA's work items (same schedule as the producer / MMA warps).
+template <int BN, int STAGES, bool STATS>
 __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, uint8_t* smem, uint64_t* tmem_full,
                                               uint64_t* tmem_empty, uint32_t tmem_base, int warp, int lane,
                                               int tile_begin, int tile_end, int tile_step) {
-  using S = ConvGemmSmem<BN, STAGES, EPI_WARPS>;
-  // Warp w reads TMEM lane quarter (w & 3); with 8 epilogue warps the two warps of a quarter split the 32-column
-  // chunks of the tile between them (even / odd).
+  using S = ConvGemmSmem<BN, STAGES>;
   const int ew = warp - 2;
-  const int q = warp & 3;
+  const int q = warp & 3;        // TMEM lane quarter this warp may read
+  const int c_begin = ew >> 2;   // this warp owns chunks c_begin, c_begin + 4, ...
   const int r = q * 32 + lane;
-  float* stage = reinterpret_cast<float*>(smem + S::kStageOffset) + ew * 1024;
-  float* bias_s = reinterpret_cast<float*>(smem + S::kBiasOffset) + ew * BN;
-  int4* rowinfo = reinterpret_cast<int4*>(smem + S::kRowOffset) + ew * 32;
-  const int c_begin = (EPI_WARPS == 8) ? (ew >> 2) : 0;
-  const int c_step = (EPI_WARPS == 8) ? 2 : 1;
+  float* stage = reinterpret_cast<float*>(smem + S::kStageOffset) + ew * 512;
+  int2* rowinfo_base = reinterpret_cast<int2*>(smem + S::kRowOffset);
   const int mode = (p.res_f32 ? 1 : (p.res_bf16 ? 2 : 0)) * 2 + (p.rowvec ? 1 : 0);
   const int out_cols_t = (p.act == ACT_GEGLU) ? BN / 2 : BN;
   const int n_limit_t = (p.act == ACT_GEGLU) ? p.N / 2 : p.N;
-  constexpr int NCH = (EPI_WARPS == 8) ? (BN / 32 + 1) / 2 : BN / 32;  // chunks one warp owns per tile
+  constexpr int NCH = (BN / kChunk + 3) / 4;  // chunks one warp owns per tile
   float st1[NCH][4], st2[NCH][4];
 #pragma unroll
   for (int k = 0; k < NCH; ++k)
@@ -274,39 +290,37 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, uint8_t* 
         (((static_cast<long long>(b) * p.OD + (z * p.osz + p.opz)) * p.OH + (y * p.osy + p.opy)) * p.OW +
          (x * p.osx + p.opx)) * p.ldo;
     const int bv = valid ? b : -1;
-    rowinfo[lane] = make_int4(static_cast<int>(orow & 0xffffffffLL), static_cast<int>(orow >> 32), bv, 0);
-    // bias of this tile -> private smem (overlaps with the wait for the accumulator)
-#pragma unroll
-    for (int i = 0; i < (BN + 31) / 32; ++i) {
-      const int e = i * 32 + lane;
-      if (e < BN) bias_s[e] = (p.bias && n_tile * BN + e < p.N) ? __ldg(p.bias + n_tile * BN + e) : 0.f;
-    }
+    int2* rowinfo = rowinfo_base + ((lt & 1) * 4 + q) * 32;
     // sample of the warp's rows (fused GroupNorm statistics: the host guarantees one sample per warp there)
     const int warp_sample = __reduce_max_sync(0xffffffff, bv);
     if (STATS && (warp_sample != st_sample || n_tile != st_ntile)) {
-      if (st_sample >= 0)
-        flush_col_stats(p, lane, st_sample, st_ntile * out_cols_t, n_limit_t, c_begin, c_step, st1, st2);
+      if (st_sample >= 0) flush_col_stats<NCH>(p, lane, st_sample, st_ntile * out_cols_t, n_limit_t, c_begin, st1, st2);
       st_sample = warp_sample; st_ntile = n_tile;
     }
     __syncwarp();
 
     mbar_wait(&tmem_full[a], aph);
     tc_fence_after();
+    // Row bookkeeping of this quarter, double-buffered by tile parity; the 4 warps of a quarter write identical values.
+    // Written only after the accumulator of this tile is full: by then every warp has released tile lt-2 (the MMA of
+    // this tile needed all 16 arrivals on its accumulator buffer), so nobody still reads this parity's slot.
+    rowinfo[lane] = make_int2(valid ? static_cast<int>(orow) : -1, bv);
+    __syncwarp();
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * BN;
     bool run_epilogue = true;
     if (p.ksplit > 1) {
       // split-K: publish this warp's partial accumulators, take a ticket; the last arrival for this (tile, warp)
       // adds the other splits' partials back into TMEM and then runs the ordinary epilogue on the full sums.
-      const int acc_chunks = BN / 32;
+      constexpr int acc_chunks = BN / kChunk;
       float* ws_tile = p.split_ws + static_cast<size_t>(tile) * p.ksplit * (128 * BN);
       float* mine = ws_tile + static_cast<size_t>(sp) * (128 * BN) + static_cast<size_t>(r) * BN;
-      for (int c = c_begin; c < acc_chunks; c += c_step) {
-        uint32_t v[32];
-        tmem_ld_32x32(taddr + c * 32, v);
+      for (int c = c_begin; c < acc_chunks; c += 4) {
+        uint32_t v[16];
+        tmem_ld_32x16(taddr + c * kChunk, v);
         tc_wait_ld();
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          __stcg(reinterpret_cast<float4*>(mine + c * 32) + j,
+        for (int j = 0; j < 4; ++j)
+          __stcg(reinterpret_cast<float4*>(mine + c * kChunk) + j,
                  make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
                              __uint_as_float(v[4 * j + 3])));
       }
@@ -314,7 +328,7 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, uint8_t* 
       __syncwarp();
       int last = 0;
       if (lane == 0) {
-        int* cnt = p.split_cnt + tile * EPI_WARPS + ew;
+        int* cnt = p.split_cnt + tile * kEpiWarps + ew;
         last = (atomicAdd(cnt, 1) == p.ksplit - 1) ? 1 : 0;
         if (last) *cnt = 0;  // ready for the next launch
       }
@@ -322,16 +336,16 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, uint8_t* 
       run_epilogue = last != 0;
       if (run_epilogue) {
         __threadfence();
-        for (int c = c_begin; c < acc_chunks; c += c_step) {
-          uint32_t v[32];
-          tmem_ld_32x32(taddr + c * 32, v);
+        for (int c = c_begin; c < acc_chunks; c += 4) {
+          uint32_t v[16];
+          tmem_ld_32x16(taddr + c * kChunk, v);
           tc_wait_ld();
           for (int s2 = 0; s2 < p.ksplit; ++s2) {
             if (s2 == sp) continue;
             const float4* o = reinterpret_cast<const float4*>(ws_tile + static_cast<size_t>(s2) * (128 * BN) +
-                                                              static_cast<size_t>(r) * BN + c * 32);
+                                                              static_cast<size_t>(r) * BN + c * kChunk);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < 4; ++j) {
               const float4 t = __ldcg(o + j);
               v[4 * j] = __float_as_uint(__uint_as_float(v[4 * j]) + t.x);
               v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + t.y);
@@ -339,32 +353,32 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, uint8_t* 
               v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + t.w);
             }
           }
-          tmem_st_32x32(taddr + c * 32, v);
+          tmem_st_32x16(taddr + c * kChunk, v);
         }
         tc_wait_st();
       }
     }
     if (run_epilogue) switch (mode) {
-      case 0: epilogue_tile<BN, 0, false, NCH, STATS>(p, taddr, stage, bias_s, lane, n_tile, rowinfo, c_begin, c_step, st1, st2); break;
-      case 1: epilogue_tile<BN, 0, true, NCH, STATS>(p, taddr, stage, bias_s, lane, n_tile, rowinfo, c_begin, c_step, st1, st2); break;
-      case 2: epilogue_tile<BN, 1, false, NCH, STATS>(p, taddr, stage, bias_s, lane, n_tile, rowinfo, c_begin, c_step, st1, st2); break;
-      case 3: epilogue_tile<BN, 1, true, NCH, STATS>(p, taddr, stage, bias_s, lane, n_tile, rowinfo, c_begin, c_step, st1, st2); break;
-      case 4: epilogue_tile<BN, 2, false, NCH, STATS>(p, taddr, stage, bias_s, lane, n_tile, rowinfo, c_begin, c_step, st1, st2); break;
-      default: epilogue_tile<BN, 2, true, NCH, STATS>(p, taddr, stage, bias_s, lane, n_tile, rowinfo, c_begin, c_step, st1, st2); break;
+      case 0: epilogue_tile<BN, 0, false, NCH, STATS>(p, taddr, stage, lane, n_tile, rowinfo, c_begin, st1, st2); break;
+      case 1: epilogue_tile<BN, 0, true, NCH, STATS>(p, taddr, stage, lane, n_tile, rowinfo, c_begin, st1, st2); break;
+      case 2: epilogue_tile<BN, 1, false, NCH, STATS>(p, taddr, stage, lane, n_tile, rowinfo, c_begin, st1, st2); break;
+      case 3: epilogue_tile<BN, 1, true, NCH, STATS>(p, taddr, stage, lane, n_tile, rowinfo, c_begin, st1, st2); break;
+      case 4: epilogue_tile<BN, 2, false, NCH, STATS>(p, taddr, stage, lane, n_tile, rowinfo, c_begin, st1, st2); break;
+      default: epilogue_tile<BN, 2, true, NCH, STATS>(p, taddr, stage, lane, n_tile, rowinfo, c_begin, st1, st2); break;
     }
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(&tmem_empty[a]);
   }
   if (STATS && st_sample >= 0)
-    flush_col_stats(p, lane, st_sample, st_ntile * out_cols_t, n_limit_t, c_begin, c_step, st1, st2);
+    flush_col_stats<NCH>(p, lane, st_sample, st_ntile * out_cols_t, n_limit_t, c_begin, st1, st2);
 }
 
-template <int BN, int STAGES, int EPI_WARPS>
-__global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const ConvGemmParams p) {
-  using S = ConvGemmSmem<BN, STAGES, EPI_WARPS>;
+  using S = ConvGemmSmem<BN, STAGES>;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kBarOffset);
   uint64_t* empty_bar = full_bar + STAGES;
@@ -385,7 +399,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], EPI_WARPS);
+      mbar_init(&tmem_empty[i], kEpiWarps);
     }
     fence_mbar_init();
   }
@@ -469,12 +483,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else {
-    // ===================== epilogue (warps 2 .. 2+EPI_WARPS) =====================
+    // ===================== epilogue (warps 2 .. 17) =====================
     if (p.col_stats)
-      epilogue_loop<BN, STAGES, EPI_WARPS, true>(p, smem, tmem_full, tmem_empty, tmem_base, warp, lane, tile_begin,
+      epilogue_loop<BN, STAGES, true>(p, smem, tmem_full, tmem_empty, tmem_base, warp, lane, tile_begin,
                                                  tile_end, tile_step);
     else
-      epilogue_loop<BN, STAGES, EPI_WARPS, false>(p, smem, tmem_full, tmem_empty, tmem_base, warp, lane, tile_begin,
+      epilogue_loop<BN, STAGES, false>(p, smem, tmem_full, tmem_empty, tmem_base, warp, lane, tile_begin,
                                                   tile_end, tile_step);
   }
 
