@@ -3,6 +3,7 @@
 
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <atomic>
 
 namespace md {
@@ -18,6 +19,12 @@ int set_error(const char* fmt, ...) {
   return -1;
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+bool pdl_enabled() {
+  // programmatic dependent launch is wired through every kernel but measured neutral inside CUDA graphs: opt-in
+  static const bool on = getenv("MD_PDL") != nullptr;
+  return on;
+}
 
 int num_sms() {
   static int n = 0;

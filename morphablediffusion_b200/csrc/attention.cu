@@ -5,6 +5,7 @@
 //   * depth attention of DepthAttention.forward (ldm/models/diffusion/attention.py:26-47): per-pixel softmax over
 //     the D depth samples of a view's frustum volume; one HBM pass over K|V.
 #include "host.h"
+#include "ptx.cuh"
 #include "kernels.h"
 
 namespace md {
@@ -51,6 +52,7 @@ template <int DHP, int NW>
 __global__ void __launch_bounds__(NW * 32)
 self_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int S, int heads, int dh,
                       float scale_log2e) {
+  pdl_grid_sync();
   constexpr int LD = DHP + 8;
   constexpr int BQ = NW * 16;
   constexpr int NT = NW * 32;
@@ -210,7 +212,7 @@ static int self_attention_impl(const void* qkv, void* out, int B, int S, int hea
   }
   dim3 grid((S + BQ - 1) / BQ, heads, B);
   const float scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(dh));
-  self_attention_kernel<DHP, NW><<<grid, NW * 32, smem, st>>>(static_cast<const __nv_bfloat16*>(qkv),
+  launch_pdl(self_attention_kernel<DHP, NW>, dim3(grid), dim3(NW * 32), smem, st, static_cast<const __nv_bfloat16*>(qkv),
                                                               static_cast<__nv_bfloat16*>(out), S, heads, dh,
                                                               scale_log2e);
   return check_launch("self_attention");
@@ -239,6 +241,7 @@ template <int CPL>
 __global__ void depth_attention_kernel(const __nv_bfloat16* __restrict__ qp, const __nv_bfloat16* __restrict__ c1,
                                        const float* __restrict__ ss, const float* __restrict__ beta,
                                        __nv_bfloat16* __restrict__ cbar, int T, int B, int D, int HW) {
+  pdl_grid_sync();
   constexpr int ctx = CPL * 32;
   const int lane = threadIdx.x & 31;
   const size_t wid = (blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x) >> 5;
@@ -274,36 +277,49 @@ __global__ void depth_attention_kernel(const __nv_bfloat16* __restrict__ qp, con
   float m[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, l[4] = {0.f, 0.f, 0.f, 0.f};
   const __nv_bfloat16* cp = c1 + (static_cast<size_t>(b) * D * HW + pix) * ctx + j0;
   const size_t dstride = static_cast<size_t>(HW) * ctx;
-  for (int d = 0; d < D; ++d) {
-    float c[CPL];
+  // D is a multiple of 6 at every level (48 / 24 / 12 / 6): fetch 6 depth samples at a time so that their loads are in
+  // flight together, then fold them into the online softmax one by one
+  constexpr int DB = 6;
+  for (int d0 = 0; d0 < D; d0 += DB) {
+    __nv_bfloat162 raw[DB][CPL / 2];
 #pragma unroll
-    for (int e = 0; e < CPL; e += 2) {
-      const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(cp + d * dstride + e);
-      c[e] = fmaxf(__low2float(v) * sc[e] + sh[e], 0.f);
-      c[e + 1] = fmaxf(__high2float(v) * sc[e + 1] + sh[e + 1], 0.f);
-    }
-    float s[4];
+    for (int dd = 0; dd < DB; ++dd) {
+      const int d = min(d0 + dd, D - 1);
 #pragma unroll
-    for (int h = 0; h < 4; ++h) {
-      float a = 0.f;
-#pragma unroll
-      for (int e = 0; e < CPL; ++e) a += q[h][e] * c[e];
-      s[h] = a;
+      for (int e = 0; e < CPL; e += 2) raw[dd][e / 2] = *reinterpret_cast<const __nv_bfloat162*>(cp + d * dstride + e);
     }
 #pragma unroll
-    for (int o = 16; o; o >>= 1) {
+    for (int dd = 0; dd < DB; ++dd) {
+      if (d0 + dd >= D) break;
+      float c[CPL];
 #pragma unroll
-      for (int h = 0; h < 4; ++h) s[h] += __shfl_xor_sync(0xffffffff, s[h], o);
-    }
+      for (int e = 0; e < CPL; e += 2) {
+        c[e] = fmaxf(__low2float(raw[dd][e / 2]) * sc[e] + sh[e], 0.f);
+        c[e + 1] = fmaxf(__high2float(raw[dd][e / 2]) * sc[e + 1] + sh[e + 1], 0.f);
+      }
+      float s[4];
 #pragma unroll
-    for (int h = 0; h < 4; ++h) {
-      const float mn = fmaxf(m[h], s[h]);
-      const float corr = __expf(m[h] - mn);
-      const float pe = __expf(s[h] - mn);
-      m[h] = mn;
-      l[h] = l[h] * corr + pe;
+      for (int h = 0; h < 4; ++h) {
+        float a = 0.f;
 #pragma unroll
-      for (int e = 0; e < CPL; ++e) acc[h][e] = acc[h][e] * corr + pe * c[e];
+        for (int e = 0; e < CPL; ++e) a += q[h][e] * c[e];
+        s[h] = a;
+      }
+#pragma unroll
+      for (int o = 16; o; o >>= 1) {
+#pragma unroll
+        for (int h = 0; h < 4; ++h) s[h] += __shfl_xor_sync(0xffffffff, s[h], o);
+      }
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        const float mn = fmaxf(m[h], s[h]);
+        const float corr = __expf(m[h] - mn);
+        const float pe = __expf(s[h] - mn);
+        m[h] = mn;
+        l[h] = l[h] * corr + pe;
+#pragma unroll
+        for (int e = 0; e < CPL; ++e) acc[h][e] = acc[h][e] * corr + pe * c[e];
+      }
     }
   }
 #pragma unroll
@@ -323,10 +339,10 @@ int launch_depth_attention(const void* qp, const void* c1, const float* ss, cons
   const __nv_bfloat16* cc = static_cast<const __nv_bfloat16*>(c1);
   __nv_bfloat16* oo = static_cast<__nv_bfloat16*>(cbar);
   switch (ctx) {
-    case 64: depth_attention_kernel<2><<<blocks, 128, 0, st>>>(qq, cc, ss, beta, oo, T, B, D, HW); break;
-    case 128: depth_attention_kernel<4><<<blocks, 128, 0, st>>>(qq, cc, ss, beta, oo, T, B, D, HW); break;
-    case 256: depth_attention_kernel<8><<<blocks, 128, 0, st>>>(qq, cc, ss, beta, oo, T, B, D, HW); break;
-    case 512: depth_attention_kernel<16><<<blocks, 128, 0, st>>>(qq, cc, ss, beta, oo, T, B, D, HW); break;
+    case 64: launch_pdl(depth_attention_kernel<2>, dim3(blocks), dim3(128), 0, st, qq, cc, ss, beta, oo, T, B, D, HW); break;
+    case 128: launch_pdl(depth_attention_kernel<4>, dim3(blocks), dim3(128), 0, st, qq, cc, ss, beta, oo, T, B, D, HW); break;
+    case 256: launch_pdl(depth_attention_kernel<8>, dim3(blocks), dim3(128), 0, st, qq, cc, ss, beta, oo, T, B, D, HW); break;
+    case 512: launch_pdl(depth_attention_kernel<16>, dim3(blocks), dim3(128), 0, st, qq, cc, ss, beta, oo, T, B, D, HW); break;
     default: return set_error("depth_attention: context dim %d unsupported (64/128/256/512)", ctx);
   }
   return check_launch("depth_attention");

@@ -63,7 +63,7 @@ static int launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const Con
     if (e != cudaSuccess) return set_error("cudaFuncSetAttribute(conv_gemm): %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  conv_gemm_kernel<BN, STAGES><<<grid, 64 + 32 * kEpiWarps, S::kTotal, stream>>>(tmA, tmB, p);
+  launch_pdl(conv_gemm_kernel<BN, STAGES>, dim3(grid), dim3(64 + 32 * kEpiWarps), S::kTotal, stream, tmA, tmB, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("conv_gemm launch: %s", cudaGetErrorString(e));
   count_launch();

@@ -411,6 +411,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // barriers, TMEM and descriptors are set up: everything above overlapped the predecessor kernel's tail
+  pdl_grid_sync();
 
   const int total_tiles = p.m_tiles * p.n_tiles * p.ksplit;  // work items: (tile, K split)
   const int kblocks = p.ntaps * p.kblocks_per_tap;

@@ -2,6 +2,7 @@
 // fused activation), LayerNorm, small linear layers (time/view embeddings), small-channel direct convolutions,
 // nearest upsample, stride-2 patch gather, CFG combine + DDIM update.  All activations are channels-last.
 #include "host.h"
+#include "ptx.cuh"
 #include "kernels.h"
 
 namespace md {
@@ -31,6 +32,7 @@ __device__ __forceinline__ void store4(float* p, float4 v) { *reinterpret_cast<f
 template <typename T0, typename T1>
 __global__ void colstats_kernel(const T0* __restrict__ x0, int C0, const T1* __restrict__ x1, int C1,
                                 float* __restrict__ stats, int rows, int rows_per_cta, int R) {
+  pdl_grid_sync();
   extern __shared__ float sm[];
   const int C = C0 + C1;
   const int CQ = C >> 2;
@@ -89,6 +91,7 @@ __global__ void gn_finalize_kernel(float* __restrict__ stats0, int C0, float* __
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                    const float* __restrict__ addvec, int addvec_ld, float* __restrict__ ss, int G,
                                    float nrows, float eps) {
+  pdl_grid_sync();
   const int b = blockIdx.x;
   const int C = C0 + C1;
   const int cpg = C / G;
@@ -129,6 +132,7 @@ template <typename T0, typename T1>
 __global__ void affine_act_kernel(const T0* __restrict__ x0, int C0, const T1* __restrict__ x1, int C1,
                                   const float* __restrict__ ss, __nv_bfloat16* __restrict__ out,
                                   __nv_bfloat16* __restrict__ raw, size_t total4, int rows, int act) {
+  pdl_grid_sync();
   const int C = C0 + C1;
   const int CQ = C >> 2;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total4;
@@ -163,6 +167,7 @@ __global__ void gn_apply_fused_kernel(const T0* __restrict__ x0, int C0, const T
                                       const float* __restrict__ addvec, int addvec_ld, __nv_bfloat16* __restrict__ out,
                                       __nv_bfloat16* __restrict__ raw, int rows, int rows_per_cta, int G, float eps,
                                       int act) {
+  pdl_grid_sync();
   extern __shared__ float ssm[];  // [C][2]: first the per-channel sums, then scale / shift
   __shared__ float gmean[64], grstd[64];
   const int C = C0 + C1;
@@ -208,27 +213,35 @@ __global__ void gn_apply_fused_kernel(const T0* __restrict__ x0, int C0, const T
     ssm[2 * c + 1] = beta[c] + (tv - gmean[g]) * sc;
   }
   __syncthreads();
+  // (4) stream the slab: thread = (4-channel group cq, row lane rsub); scale/shift of the group stay in registers
   const int CQ = C >> 2;
   const int r0 = blockIdx.x * rows_per_cta;
   const int r1 = min(rows, r0 + rows_per_cta);
-  const size_t total4 = static_cast<size_t>(r1 - r0) * CQ;
-  for (size_t i = threadIdx.x; i < total4; i += blockDim.x) {
-    const int cq = static_cast<int>(i % CQ);
-    const size_t row = static_cast<size_t>(b) * rows + r0 + i / CQ;
+  const int R = max(1, static_cast<int>(blockDim.x) / CQ);
+  for (int cq0 = 0; cq0 < CQ; cq0 += blockDim.x) {  // CQ > blockDim.x only for very wide tensors
+    const int cq = cq0 + static_cast<int>(threadIdx.x) % min(CQ, static_cast<int>(blockDim.x));
+    const int rsub = static_cast<int>(threadIdx.x) / min(CQ, static_cast<int>(blockDim.x));
+    if (cq >= CQ || rsub >= R) continue;
     const int c = cq * 4;
-    float4 v;
-    if (c < C0) v = load4(x0 + row * C0 + c);
-    else v = load4(x1 + row * C1 + (c - C0));
-    if (raw) store4(raw + row * C + c, v);
     const float4 s01 = *reinterpret_cast<const float4*>(ssm + 2 * c);
     const float4 s23 = *reinterpret_cast<const float4*>(ssm + 2 * c + 4);
-    float4 y = make_float4(v.x * s01.x + s01.y, v.y * s01.z + s01.w, v.z * s23.x + s23.y, v.w * s23.z + s23.w);
-    if (act == ACT_SILU) {
-      y.x = silu_f(y.x); y.y = silu_f(y.y); y.z = silu_f(y.z); y.w = silu_f(y.w);
-    } else if (act == ACT_RELU) {
-      y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f);
+    const bool first = c < C0;
+    const size_t rowbase = static_cast<size_t>(b) * rows;
+#pragma unroll 4
+    for (int r = r0 + rsub; r < r1; r += R) {
+      const size_t row = rowbase + r;
+      float4 v;
+      if (first) v = load4(x0 + row * C0 + c);
+      else v = load4(x1 + row * C1 + (c - C0));
+      if (raw) store4(raw + row * C + c, v);
+      float4 y = make_float4(v.x * s01.x + s01.y, v.y * s01.z + s01.w, v.z * s23.x + s23.y, v.w * s23.z + s23.w);
+      if (act == ACT_SILU) {
+        y.x = silu_f(y.x); y.y = silu_f(y.y); y.z = silu_f(y.z); y.w = silu_f(y.w);
+      } else if (act == ACT_RELU) {
+        y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f);
+      }
+      store4(out + row * C + c, y);
     }
-    store4(out + row * C + c, y);
   }
 }
 
@@ -248,7 +261,7 @@ static int group_norm_impl(const GroupNormArgs& a, cudaStream_t st) {
     const int min_rows = std::max(2, 4096 / C);  // keep the per-CTA statistics prologue small next to the streamed slab
     rows_per_cta = std::min(std::max(rows_per_cta, min_rows), a.rows);
     dim3 grid((a.rows + rows_per_cta - 1) / rows_per_cta, a.B);
-    gn_apply_fused_kernel<T0, T1><<<grid, 256, static_cast<size_t>(C) * 2 * sizeof(float), st>>>(
+    launch_pdl(gn_apply_fused_kernel<T0, T1>, dim3(grid), dim3(256), static_cast<size_t>(C) * 2 * sizeof(float), st, 
         static_cast<const T0*>(a.x0), a.C0, static_cast<const T1*>(a.x1), a.C1, a.stats0, a.stats1, a.gamma, a.beta,
         a.addvec, a.addvec_ld, static_cast<__nv_bfloat16*>(a.out), static_cast<__nv_bfloat16*>(a.raw_out), a.rows,
         rows_per_cta, a.groups, a.eps, a.act);
@@ -263,21 +276,21 @@ static int group_norm_impl(const GroupNormArgs& a, cudaStream_t st) {
     int rows_per_cta = std::max(R * 4, static_cast<int>((static_cast<long long>(a.rows) * a.B + target_ctas - 1) / target_ctas));
     rows_per_cta = std::min(rows_per_cta, a.rows);
     dim3 grid((a.rows + rows_per_cta - 1) / rows_per_cta, a.B);
-    colstats_kernel<T0, T1><<<grid, threads, threads * 8 * sizeof(float), st>>>(
+    launch_pdl(colstats_kernel<T0, T1>, dim3(grid), dim3(threads), threads * 8 * sizeof(float), st, 
         static_cast<const T0*>(a.x0), a.C0, static_cast<const T1*>(a.x1), a.C1, a.stats, a.rows, rows_per_cta, R);
     MD_CHECK(check_launch("colstats"));
     st0 = a.stats; st1 = nullptr; c0 = C; c1 = 0; zero_after = 1;
   } else if (a.C1 > 0 && !a.stats1) {
     return set_error("group_norm: statistics for the second source are missing");
   }
-  gn_finalize_kernel<<<a.B, std::min(1024, 32 * a.groups), 0, st>>>(st0, c0, st1, c1, zero_after, a.gamma, a.beta, a.addvec,
+  launch_pdl(gn_finalize_kernel, dim3(a.B), dim3(std::min(1024, 32 * a.groups)), 0, st, st0, c0, st1, c1, zero_after, a.gamma, a.beta, a.addvec,
                                                                     a.addvec_ld, a.scale_shift, a.groups,
                                                                     static_cast<float>(a.rows), a.eps);
   MD_CHECK(check_launch("gn_finalize"));
   if (!a.out) return 0;  // scale/shift only (consumer applies the affine itself)
   const size_t total4 = static_cast<size_t>(a.B) * a.rows * CQ;
   const int blocks = static_cast<int>(std::min<size_t>((total4 + 255) / 256, static_cast<size_t>(num_sms()) * 16));
-  affine_act_kernel<T0, T1><<<blocks, 256, 0, st>>>(static_cast<const T0*>(a.x0), a.C0,
+  launch_pdl(affine_act_kernel<T0, T1>, dim3(blocks), dim3(256), 0, st, static_cast<const T0*>(a.x0), a.C0,
                                                     static_cast<const T1*>(a.x1), a.C1, a.scale_shift,
                                                     static_cast<__nv_bfloat16*>(a.out),
                                                     static_cast<__nv_bfloat16*>(a.raw_out), total4, a.rows, a.act);
@@ -298,6 +311,7 @@ template <int MAXV>
 __global__ void layer_norm_kernel(float* __restrict__ x, const float* __restrict__ addvec, int addvec_ld,
                                   const float* __restrict__ gamma, const float* __restrict__ beta,
                                   __nv_bfloat16* __restrict__ out, size_t nrows, int rows_per_sample, int C, float eps) {
+  pdl_grid_sync();
   const int lane = threadIdx.x & 31;
   const size_t row = (blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x) >> 5;
   if (row >= nrows) return;
@@ -355,7 +369,7 @@ int launch_layer_norm(float* x, const float* addvec, int addvec_ld, const float*
   if (C % 4 || C > 1280) return set_error("layer_norm: unsupported C=%d", C);
   const int threads = 256;
   const size_t blocks = (nrows * 32 + threads - 1) / threads;
-  layer_norm_kernel<10><<<static_cast<unsigned>(blocks), threads, 0, st>>>(
+  launch_pdl(layer_norm_kernel<10>, dim3(static_cast<unsigned>(blocks)), dim3(threads), 0, st, 
       x, addvec, addvec_ld, gamma, beta, static_cast<__nv_bfloat16*>(out_bf16), nrows, rows_per_sample, C, eps);
   return check_launch("layer_norm");
 }
@@ -365,6 +379,7 @@ int launch_layer_norm(float* x, const float* addvec, int addvec_ld, const float*
 __global__ void small_linear_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ W,
                                     const float* __restrict__ bias, float* __restrict__ out, int ldo, int B, int K,
                                     int N, int act_in, int act_out, int accumulate) {
+  pdl_grid_sync();
   const int lane = threadIdx.x & 31;
   const long long wid = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
   if (wid >= static_cast<long long>(N) * B) return;
@@ -402,13 +417,14 @@ int launch_small_linear(const float* x, int ldx, const float* W, const float* bi
   const int threads = 128;
   const long long warps = static_cast<long long>(N) * B;
   const unsigned blocks = static_cast<unsigned>((warps * 32 + threads - 1) / threads);
-  small_linear_kernel<<<blocks, threads, 0, st>>>(x, ldx, W, bias, out, ldo, B, K, N, act_in, act_out, accumulate);
+  launch_pdl(small_linear_kernel, dim3(blocks), dim3(threads), 0, st, x, ldx, W, bias, out, ldo, B, K, N, act_in, act_out, accumulate);
   return check_launch("small_linear");
 }
 
 // ------------------------------------------------------------------------------------------------ timestep embedding
 // [cos(t f_i), sin(t f_i)], f_i = exp(-ln(10000) i / half)   (ldm/modules/diffusionmodules/util.py:151-171)
 __global__ void timestep_embedding_kernel(const float* __restrict__ t, float* __restrict__ out, int B, int dim) {
+  pdl_grid_sync();
   const int half = dim / 2;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * half) return;
@@ -421,7 +437,7 @@ __global__ void timestep_embedding_kernel(const float* __restrict__ t, float* __
 
 int launch_timestep_embedding(const float* t, float* out, int B, int dim, cudaStream_t st) {
   const int n = B * (dim / 2);
-  timestep_embedding_kernel<<<(n + 127) / 128, 128, 0, st>>>(t, out, B, dim);
+  launch_pdl(timestep_embedding_kernel, dim3((n + 127) / 128), dim3(128), 0, st, t, out, B, dim);
   return check_launch("timestep_embedding");
 }
 
@@ -431,6 +447,7 @@ int launch_timestep_embedding(const float* t, float* out, int B, int dim, cudaSt
 __global__ void conv3x3_direct_kernel(const float* __restrict__ x, const float* __restrict__ W,
                                       const float* __restrict__ bias, float* __restrict__ out, int B, int H, int Wd,
                                       int Cin, int Cout) {
+  pdl_grid_sync();
   const int CQ = Cout >> 2;
   const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
   const size_t total = static_cast<size_t>(B) * H * Wd * CQ;
@@ -463,13 +480,14 @@ int launch_conv3x3_direct(const float* x, const float* W, const float* bias, flo
                           int Cout, cudaStream_t st) {
   if (Cout % 4) return set_error("conv3x3_direct: Cout must be a multiple of 4");
   const size_t total = static_cast<size_t>(B) * H * Wd * (Cout / 4);
-  conv3x3_direct_kernel<<<static_cast<unsigned>((total + 127) / 128), 128, 0, st>>>(x, W, bias, out, B, H, Wd, Cin,
+  launch_pdl(conv3x3_direct_kernel, dim3(static_cast<unsigned>((total + 127) / 128)), dim3(128), 0, st, x, W, bias, out, B, H, Wd, Cin,
                                                                                     Cout);
   return check_launch("conv3x3_direct");
 }
 
 // [rows][ld] fp32 (first C columns) -> NCHW [B][C][HW]   (UNet output: the final conv runs as a GEMM padded to 8 columns)
 __global__ void rows_to_nchw_kernel(const float* __restrict__ x, int ld, float* __restrict__ out, int B, int C, int HW) {
+  pdl_grid_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * C * HW) return;
   const int p = i % HW, c = (i / HW) % C, b = i / (HW * C);
@@ -477,7 +495,7 @@ __global__ void rows_to_nchw_kernel(const float* __restrict__ x, int ld, float* 
 }
 int launch_rows_to_nchw(const float* x, int ld, float* out, int B, int C, int HW, cudaStream_t st) {
   const int total = B * C * HW;
-  rows_to_nchw_kernel<<<(total + 255) / 256, 256, 0, st>>>(x, ld, out, B, C, HW);
+  launch_pdl(rows_to_nchw_kernel, dim3((total + 255) / 256), dim3(256), 0, st, x, ld, out, B, C, HW);
   return check_launch("rows_to_nchw");
 }
 
@@ -486,6 +504,7 @@ int launch_rows_to_nchw(const float* x, int ld, float* out, int B, int C, int HW
 __global__ void conv3x3_out_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ W,
                                    const float* __restrict__ bias, float* __restrict__ out, int B, int H, int Wd,
                                    int Cin, int Cout) {
+  pdl_grid_sync();
   const int lane = threadIdx.x & 31;
   const size_t pix = (blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x) >> 5;
   if (pix >= static_cast<size_t>(B) * H * Wd) return;
@@ -522,7 +541,7 @@ int launch_conv3x3_out(const void* x_bf16, const float* W, const float* bias, fl
                        int Cout, cudaStream_t st) {
   if (Cout > 4 || Cin % 2) return set_error("conv3x3_out: unsupported Cout=%d Cin=%d", Cout, Cin);
   const size_t warps = static_cast<size_t>(B) * H * Wd;
-  conv3x3_out_kernel<<<static_cast<unsigned>((warps * 32 + 255) / 256), 256, 0, st>>>(
+  launch_pdl(conv3x3_out_kernel, dim3(static_cast<unsigned>((warps * 32 + 255) / 256)), dim3(256), 0, st, 
       static_cast<const __nv_bfloat16*>(x_bf16), W, bias, out, B, H, Wd, Cin, Cout);
   return check_launch("conv3x3_out");
 }
@@ -532,6 +551,7 @@ int launch_conv3x3_out(const void* x_bf16, const float* W, const float* bias, fl
 // first T samples conditional (x_concat / 0.18215), last T unconditional (zeros)  (morphable_diffusion.py:132-146).
 __global__ void unet_input_kernel(const float* __restrict__ x, const float* __restrict__ xc, int xc_per_sample,
                                   float* __restrict__ out, int T, int HW, int cfg) {
+  pdl_grid_sync();
   const int nb = cfg ? 2 * T : T;
   const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
   if (i >= static_cast<size_t>(nb) * HW * 8) return;
@@ -549,12 +569,13 @@ __global__ void unet_input_kernel(const float* __restrict__ x, const float* __re
 int launch_unet_input(const float* x, const float* xc, int xc_per_sample, float* out, int T, int HW, int cfg,
                       cudaStream_t st) {
   const size_t total = static_cast<size_t>(cfg ? 2 * T : T) * HW * 8;
-  unet_input_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(x, xc, xc_per_sample, out, T, HW, cfg);
+  launch_pdl(unet_input_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, st, x, xc, xc_per_sample, out, T, HW, cfg);
   return check_launch("unet_input");
 }
 
 template <typename T>
 __global__ void cast_bf16_kernel(const T* __restrict__ x, __nv_bfloat16* __restrict__ out, size_t n4) {
+  pdl_grid_sync();
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4;
        i += static_cast<size_t>(gridDim.x) * blockDim.x)
     store4(out + i * 4, load4(x + i * 4));
@@ -564,13 +585,14 @@ int launch_cast_bf16(const float* x, void* out, size_t n, cudaStream_t st) {
   if (n % 4) return set_error("cast_bf16: n must be a multiple of 4");
   const size_t n4 = n / 4;
   const int blocks = static_cast<int>(std::min<size_t>((n4 + 255) / 256, static_cast<size_t>(num_sms()) * 16));
-  cast_bf16_kernel<float><<<blocks, 256, 0, st>>>(x, static_cast<__nv_bfloat16*>(out), n4);
+  launch_pdl(cast_bf16_kernel<float>, dim3(blocks), dim3(256), 0, st, x, static_cast<__nv_bfloat16*>(out), n4);
   return check_launch("cast_bf16");
 }
 
 // nearest x2 upsample (Upsample.forward, openaimodel.py:110-120): fp32 NHWC -> bf16 NHWC
 __global__ void upsample2x_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int B, int H, int W,
                                   int C) {
+  pdl_grid_sync();
   const int CQ = C / 4;
   const size_t total = static_cast<size_t>(B) * 2 * H * 2 * W * CQ;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
@@ -588,7 +610,7 @@ __global__ void upsample2x_kernel(const float* __restrict__ x, __nv_bfloat16* __
 int launch_upsample2x(const float* x, void* out, int B, int H, int W, int C, cudaStream_t st) {
   const size_t total = static_cast<size_t>(B) * 4 * H * W * (C / 4);
   const int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, static_cast<size_t>(num_sms()) * 16));
-  upsample2x_kernel<<<blocks, 256, 0, st>>>(x, static_cast<__nv_bfloat16*>(out), B, H, W, C);
+  launch_pdl(upsample2x_kernel, dim3(blocks), dim3(256), 0, st, x, static_cast<__nv_bfloat16*>(out), B, H, W, C);
   return check_launch("upsample2x");
 }
 
@@ -597,6 +619,7 @@ int launch_upsample2x(const float* x, void* out, int B, int H, int W, int C, cud
 template <typename T>
 __global__ void gather_s2_kernel(const T* __restrict__ x, __nv_bfloat16* __restrict__ out, int B, int D, int H, int W,
                                  int C, int OD, int OH, int OW, int kd) {
+  pdl_grid_sync();
   const int CQ = C / 4;
   const int taps = kd * 9;
   const size_t total = static_cast<size_t>(B) * OD * OH * OW * taps * CQ;
@@ -625,11 +648,11 @@ int launch_gather_s2(const void* x, int x_is_bf16, void* out, int B, int D, int 
   const size_t total = static_cast<size_t>(B) * OD * OH * OW * kd * 9 * (C / 4);
   const int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, static_cast<size_t>(num_sms()) * 16));
   if (x_is_bf16)
-    gather_s2_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x),
+    launch_pdl(gather_s2_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, st, static_cast<const __nv_bfloat16*>(x),
                                                             static_cast<__nv_bfloat16*>(out), B, D, H, W, C, OD, OH,
                                                             OW, kd);
   else
-    gather_s2_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(x), static_cast<__nv_bfloat16*>(out), B,
+    launch_pdl(gather_s2_kernel<float>, dim3(blocks), dim3(256), 0, st, static_cast<const float*>(x), static_cast<__nv_bfloat16*>(out), B,
                                                     D, H, W, C, OD, OH, OW, kd);
   return check_launch("gather_s2");
 }
@@ -637,6 +660,7 @@ int launch_gather_s2(const void* x, int x_is_bf16, void* out, int B, int D, int 
 // NCDHW fp32 -> channels-last bf16 (API-boundary transposition of caller-supplied frustum volumes)
 __global__ void ncdhw_to_cl_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int B, int C,
                                         size_t S) {
+  pdl_grid_sync();
   const size_t total = static_cast<size_t>(B) * C * S;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -649,13 +673,14 @@ __global__ void ncdhw_to_cl_bf16_kernel(const float* __restrict__ x, __nv_bfloat
 int launch_ncdhw_to_cl_bf16(const float* x, void* out, int B, int C, size_t S, cudaStream_t st) {
   const size_t total = static_cast<size_t>(B) * C * S;
   const int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, static_cast<size_t>(num_sms()) * 32));
-  ncdhw_to_cl_bf16_kernel<<<blocks, 256, 0, st>>>(x, static_cast<__nv_bfloat16*>(out), B, C, S);
+  launch_pdl(ncdhw_to_cl_bf16_kernel, dim3(blocks), dim3(256), 0, st, x, static_cast<__nv_bfloat16*>(out), B, C, S);
   return check_launch("ncdhw_to_cl_bf16");
 }
 
 // channels-last (bf16 or fp32) -> NCDHW fp32
 template <typename T>
 __global__ void cl_to_ncdhw_kernel(const T* __restrict__ x, float* __restrict__ out, int B, int C, size_t S) {
+  pdl_grid_sync();
   const size_t total = static_cast<size_t>(B) * C * S;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -669,9 +694,9 @@ int launch_cl_to_ncdhw(const void* x, int x_is_bf16, float* out, int B, int C, s
   const size_t total = static_cast<size_t>(B) * C * S;
   const int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, static_cast<size_t>(num_sms()) * 32));
   if (x_is_bf16)
-    cl_to_ncdhw_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), out, B, C, S);
+    launch_pdl(cl_to_ncdhw_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, st, static_cast<const __nv_bfloat16*>(x), out, B, C, S);
   else
-    cl_to_ncdhw_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(x), out, B, C, S);
+    launch_pdl(cl_to_ncdhw_kernel<float>, dim3(blocks), dim3(256), 0, st, static_cast<const float*>(x), out, B, C, S);
   return check_launch("cl_to_ncdhw");
 }
 
@@ -697,6 +722,7 @@ __global__ void cfg_ddim_kernel(const float* __restrict__ eps, float* __restrict
                                 const float* __restrict__ noise, int T, int n_per_view, int cfg, float cfg_scale,
                                 float a_t, float a_prev, float sigma, float sqrt_1m_at, int add_noise, uint64_t seed,
                                 uint32_t step, int view0, int do_update, const float* __restrict__ dev_params) {
+  pdl_grid_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int total = T * n_per_view;
   if (i >= total) return;
@@ -740,7 +766,7 @@ int launch_cfg_ddim(const float* eps, float* x, float* eps_out, const float* noi
                     float cfg_scale, float a_t, float a_prev, float sigma, float sqrt_1m_at, int add_noise,
                     uint64_t seed, uint32_t step, int view0, int do_update, const float* dev_params, cudaStream_t st) {
   const int total = T * n_per_view;
-  cfg_ddim_kernel<<<(total + 255) / 256, 256, 0, st>>>(eps, x, eps_out, noise, T, n_per_view, cfg, cfg_scale, a_t,
+  launch_pdl(cfg_ddim_kernel, dim3((total + 255) / 256), dim3(256), 0, st, eps, x, eps_out, noise, T, n_per_view, cfg, cfg_scale, a_t,
                                                        a_prev, sigma, sqrt_1m_at, add_noise, seed, step, view0,
                                                        do_update, dev_params);
   return check_launch("cfg_ddim");

@@ -8,6 +8,7 @@
 //   frustum_points      per-view ray sample points (utils.py:79-153)
 //   frustum_gather      trilinear gather of the spatial volume along the rays (morphable_diffusion.py:312-315)
 #include "host.h"
+#include "ptx.cuh"
 #include "kernels.h"
 #include "geometry.h"
 
@@ -15,6 +16,7 @@ namespace md {
 
 // ------------------------------------------------------------------------------------------------ voxelize (a1)
 __global__ void minmax_kernel(const float* __restrict__ v, int nv, float* __restrict__ bounds) {
+  pdl_grid_sync();
   __shared__ float smin[3][32], smax[3][32];
   float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
   for (int i = threadIdx.x; i < nv; i += blockDim.x) {
@@ -46,6 +48,7 @@ __global__ void minmax_kernel(const float* __restrict__ v, int nv, float* __rest
 
 __global__ void voxel_coord_kernel(const float* __restrict__ v, int nv, const float* __restrict__ bounds,
                                    int32_t* __restrict__ coord, int32_t* __restrict__ out_sh) {
+  pdl_grid_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const float voxel = 0.005f;
   if (i < nv) {
@@ -64,9 +67,9 @@ __global__ void voxel_coord_kernel(const float* __restrict__ v, int nv, const fl
 }
 
 int launch_voxelize(const float* vertices, int nv, int32_t* coord, int32_t* out_sh, float* bounds, cudaStream_t st) {
-  minmax_kernel<<<1, 1024, 0, st>>>(vertices, nv, bounds);
+  launch_pdl(minmax_kernel, dim3(1), dim3(1024), 0, st, vertices, nv, bounds);
   MD_CHECK(check_launch("minmax"));
-  voxel_coord_kernel<<<(std::max(nv, 3) + 255) / 256, 256, 0, st>>>(vertices, nv, bounds, coord, out_sh);
+  launch_pdl(voxel_coord_kernel, dim3((std::max(nv, 3) + 255) / 256), dim3(256), 0, st, vertices, nv, bounds, coord, out_sh);
   return check_launch("voxel_coord");
 }
 
@@ -159,6 +162,7 @@ __device__ __forceinline__ float silu_g(float x) { return x / (1.f + __expf(-x))
 __global__ void __launch_bounds__(1024, 1)
 target_encoder_kernel(const float* __restrict__ x, const float* __restrict__ t_embed, const float* __restrict__ v_embed,
                       EncWeights W, float* __restrict__ out, int tdim, int vdim) {
+  pdl_grid_sync();
   extern __shared__ __align__(16) uint8_t enc_raw[];
   EncSmem& s = *reinterpret_cast<EncSmem*>(enc_raw);
   const int view = blockIdx.x;
@@ -220,7 +224,7 @@ int launch_target_encoder(const float* x, const float* t_embed, const float* v_e
   EncWeights W;
   static_assert(sizeof(EncWeights) == sizeof(EncWeightsHost), "layout mismatch");
   memcpy(&W, &w, sizeof(W));
-  target_encoder_kernel<<<n_views, 1024, smem, st>>>(x, t_embed, v_embed, W, out, tdim, vdim);
+  launch_pdl(target_encoder_kernel, dim3(n_views), dim3(1024), smem, st, x, t_embed, v_embed, W, out, tdim, vdim);
   return check_launch("target_encoder");
 }
 
@@ -277,6 +281,7 @@ __device__ __forceinline__ float linspace_at(float length, int V, int i) {
 // feats [N][size*size][16] -> vol [N][V][V][V][16] (channels-last; index (d,h,w) <-> world (x=l[w], y=l[h], z=l[d]))
 __global__ void unproject_kernel(const float* __restrict__ feats, const float* __restrict__ proj, int ortho, int size,
                                  int V, float length, float* __restrict__ vol, int n_views) {
+  pdl_grid_sync();
   const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
   const size_t total = static_cast<size_t>(n_views) * V * V * V * 4;
   if (i >= total) return;
@@ -297,7 +302,7 @@ __global__ void unproject_kernel(const float* __restrict__ feats, const float* _
 int launch_unproject(const float* feats, const float* proj, int ortho, int size, int V, float length, float* vol,
                      int n_views, cudaStream_t st) {
   const size_t total = static_cast<size_t>(n_views) * V * V * V * 4;
-  unproject_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(feats, proj, ortho, size, V, length, vol,
+  launch_pdl(unproject_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, st, feats, proj, ortho, size, V, length, vol,
                                                                                n_views);
   return check_launch("unproject");
 }
@@ -309,6 +314,7 @@ int launch_unproject(const float* feats, const float* proj, int ortho, int size,
 __global__ void vertex_features_kernel(const float* __restrict__ feats, const float* __restrict__ proj, int ortho,
                                        int size, int V, float length, const float* __restrict__ vertices, int nv,
                                        int n_views, float* __restrict__ out) {
+  pdl_grid_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nv * 4) return;
   const int cq = i & 3, vi = i >> 2;
@@ -338,7 +344,7 @@ __global__ void vertex_features_kernel(const float* __restrict__ feats, const fl
 
 int launch_vertex_features(const float* feats, const float* proj, int ortho, int size, int V, float length,
                            const float* vertices, int nv, int n_views, float* out, cudaStream_t st) {
-  vertex_features_kernel<<<(nv * 4 + 127) / 128, 128, 0, st>>>(feats, proj, ortho, size, V, length, vertices, nv,
+  launch_pdl(vertex_features_kernel, dim3((nv * 4 + 127) / 128), dim3(128), 0, st, feats, proj, ortho, size, V, length, vertices, nv,
                                                                 n_views, out);
   return check_launch("vertex_features");
 }
@@ -349,6 +355,7 @@ int launch_vertex_features(const float* feats, const float* proj, int ortho, int
 __global__ void smpl_scatter_kernel(const float* __restrict__ vsum, float inv_views, const float* __restrict__ W,
                                     const float* __restrict__ bias, const int32_t* __restrict__ row_vertex, int n_rows,
                                     float* __restrict__ out) {
+  pdl_grid_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_rows * 16) return;
   const int co = i & 15, r = i >> 4;
@@ -361,7 +368,7 @@ __global__ void smpl_scatter_kernel(const float* __restrict__ vsum, float inv_vi
 
 int launch_smpl_scatter(const float* vsum, float inv_views, const float* W, const float* bias,
                         const int32_t* row_vertex, int n_rows, float* out, cudaStream_t st) {
-  smpl_scatter_kernel<<<(n_rows * 16 + 127) / 128, 128, 0, st>>>(vsum, inv_views, W, bias, row_vertex, n_rows, out);
+  launch_pdl(smpl_scatter_kernel, dim3((n_rows * 16 + 127) / 128), dim3(128), 0, st, vsum, inv_views, W, bias, row_vertex, n_rows, out);
   return check_launch("smpl_scatter");
 }
 
@@ -372,6 +379,7 @@ template <int CIN, int COUT>
 __global__ void sparse_conv_kernel(const float* __restrict__ in, const int32_t* __restrict__ nbr,
                                    const float* __restrict__ W, const float* __restrict__ scale,
                                    const float* __restrict__ shift, float* __restrict__ out, int n_rows) {
+  pdl_grid_sync();
   const int lane = threadIdx.x & 31;
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (r >= n_rows) return;
@@ -414,6 +422,7 @@ __global__ void sparse_conv_quad_kernel(const float* __restrict__ in, const int3
                                         const float* __restrict__ W, const float* __restrict__ scale,
                                         const float* __restrict__ shift, float* __restrict__ out, int n_rows, int Cin,
                                         int Cout) {
+  pdl_grid_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int CQ = Cout >> 2;
   if (i >= n_rows * CQ) return;
@@ -449,10 +458,10 @@ int launch_sparse_conv(const float* in, const int32_t* nbr, const float* W, cons
                        float* out, int n_rows, int Cin, int Cout, cudaStream_t st) {
   if (n_rows == 0) return 0;
   const unsigned blocks = (static_cast<unsigned>(n_rows) * 32 + 127) / 128;
-  if (Cin == 16 && Cout == 16) sparse_conv_kernel<16, 16><<<blocks, 128, 0, st>>>(in, nbr, W, scale, shift, out, n_rows);
-  else if (Cin == 16 && Cout == 32) sparse_conv_kernel<16, 32><<<blocks, 128, 0, st>>>(in, nbr, W, scale, shift, out, n_rows);
+  if (Cin == 16 && Cout == 16) launch_pdl(sparse_conv_kernel<16, 16>, dim3(blocks), dim3(128), 0, st, in, nbr, W, scale, shift, out, n_rows);
+  else if (Cin == 16 && Cout == 32) launch_pdl(sparse_conv_kernel<16, 32>, dim3(blocks), dim3(128), 0, st, in, nbr, W, scale, shift, out, n_rows);
   else if (Cin % 4 == 0 && Cout % 4 == 0)
-    sparse_conv_quad_kernel<<<(n_rows * (Cout / 4) + 63) / 64, 64, 0, st>>>(in, nbr, W, scale, shift, out, n_rows, Cin, Cout);
+    launch_pdl(sparse_conv_quad_kernel, dim3((n_rows * (Cout / 4) + 63) / 64), dim3(64), 0, st, in, nbr, W, scale, shift, out, n_rows, Cin, Cout);
   else return set_error("sparse_conv: unsupported channels %d -> %d", Cin, Cout);
   return check_launch("sparse_conv");
 }
@@ -461,6 +470,7 @@ int launch_sparse_conv(const float* in, const int32_t* nbr, const float* W, cons
 // vol[p][c] = sum_j w[p][j] * feat[idx[p][j]][c];  idx < 0 = empty voxel.  feat [n2][64], vol [V^3][64] fp32.
 __global__ void volume_resample_kernel(const float* __restrict__ feat, const int32_t* __restrict__ idx,
                                        const float* __restrict__ wgt, float* __restrict__ vol, int npts) {
+  pdl_grid_sync();
   const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
   if (i >= static_cast<size_t>(npts) * 16) return;
   const int cq = static_cast<int>(i & 15);
@@ -480,7 +490,7 @@ __global__ void volume_resample_kernel(const float* __restrict__ feat, const int
 int launch_volume_resample(const float* feat, const int32_t* idx, const float* wgt, float* vol, int npts,
                            cudaStream_t st) {
   const size_t total = static_cast<size_t>(npts) * 16;
-  volume_resample_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(feat, idx, wgt, vol, npts);
+  launch_pdl(volume_resample_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, st, feat, idx, wgt, vol, npts);
   return check_launch("volume_resample");
 }
 
@@ -489,6 +499,7 @@ int launch_volume_resample(const float* feat, const int32_t* idx, const float* w
 // persp: world = M * (x*dep, y*dep, dep) + t ;  ortho: world = M * (kx, ky, dep) + t with (kx,ky) = Kinv*(gx,gy,1).
 __global__ void frustum_points_kernel(const float* __restrict__ cam, int ortho, int D, int size, float length,
                                       float frustum_len, float* __restrict__ pts, int n_views) {
+  pdl_grid_sync();
   const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
   const size_t per_view = static_cast<size_t>(D) * size * size;
   if (i >= per_view * n_views) return;
@@ -524,7 +535,7 @@ __global__ void frustum_points_kernel(const float* __restrict__ cam, int ortho, 
 int launch_frustum_points(const float* cam, int ortho, int D, int size, float length, float frustum_len, float* pts,
                           int n_views, cudaStream_t st) {
   const size_t total = static_cast<size_t>(D) * size * size * n_views;
-  frustum_points_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(cam, ortho, D, size, length,
+  launch_pdl(frustum_points_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, st, cam, ortho, D, size, length,
                                                                                     frustum_len, pts, n_views);
   return check_launch("frustum_points");
 }
@@ -533,6 +544,7 @@ int launch_frustum_points(const float* cam, int ortho, int D, int size, float le
 // One warp per sample point; lane = channel pair.  vol fp32 [V][V][V][64]; out bf16 [npts][64].
 __global__ void frustum_gather_kernel(const float* __restrict__ vol, const float* __restrict__ pts, int V,
                                       __nv_bfloat16* __restrict__ out, size_t npts) {
+  pdl_grid_sync();
   const int lane = threadIdx.x & 31;
   const size_t p = (blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x) >> 5;
   if (p >= npts) return;
@@ -561,7 +573,7 @@ __global__ void frustum_gather_kernel(const float* __restrict__ vol, const float
 
 int launch_frustum_gather(const float* vol, const float* pts, int V, void* out_bf16, size_t npts, cudaStream_t st) {
   const size_t threads = npts * 32;
-  frustum_gather_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, st>>>(
+  launch_pdl(frustum_gather_kernel, dim3(static_cast<unsigned>((threads + 255) / 256)), dim3(256), 0, st, 
       vol, pts, V, static_cast<__nv_bfloat16*>(out_bf16), npts);
   return check_launch("frustum_gather");
 }

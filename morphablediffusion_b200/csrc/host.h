@@ -30,6 +30,22 @@ int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream);
     if (_e != cudaSuccess) return md::set_error("%s: %s", #expr, cudaGetErrorString(_e)); \
   } while (0)
 
+bool pdl_enabled();
+
+// Launch with programmatic stream serialization: the kernel may start while its predecessor drains; every kernel
+// calls pdl_grid_sync() (griddepcontrol.wait) before touching memory.
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 inline int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("%s launch: %s", what, cudaGetErrorString(e));

@@ -1,6 +1,7 @@
 // Context lifecycle, stage-level C ABI and the fused denoise step (SyncDDIMSampler.denoise_apply,
 // morphable_diffusion.py:701-739).
 #include "engine.h"
+#include "ptx.cuh"
 
 #include <dlfcn.h>
 #include <math.h>
@@ -12,15 +13,18 @@ namespace md {
 
 // ------------------------------------------------------------------ tiny kernels local to the step
 __global__ void fill_kernel(float* p, float v, int n) {
+  pdl_grid_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
 }
 __global__ void fill_from_kernel(float* p, const float* src, int n) {
+  pdl_grid_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = src[0];
 }
 __global__ void set_step_params_kernel(float* d, float tval, float a_t, float a_prev, float sigma, float s1m, int add_noise,
                                        uint32_t index, uint64_t seed) {
+  pdl_grid_sync();
   if (threadIdx.x == 0) {
     d[0] = tval; d[1] = a_t; d[2] = a_prev; d[3] = sigma; d[4] = s1m; d[5] = add_noise ? 1.f : 0.f;
     d[6] = __uint_as_float(index);
@@ -29,11 +33,13 @@ __global__ void set_step_params_kernel(float* d, float tval, float a_t, float a_
 }
 // context rows: first T = clip embedding, remaining (uncond) = 0   (morphable_diffusion.py:135)
 __global__ void make_context_kernel(const float* __restrict__ clip, float* __restrict__ out, int T, int B, int dim) {
+  pdl_grid_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * dim) return;
   out[i] = (i / dim < T) ? clip[i % dim] : 0.f;
 }
 __global__ void ncdhw_to_cl_f32_kernel(const float* __restrict__ x, float* __restrict__ out, int C, size_t S) {
+  pdl_grid_sync();
   const size_t total = static_cast<size_t>(C) * S;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -149,7 +155,7 @@ static int denoise_step_impl(Ctx& c, float* x_local, const float* x_input, const
   (void)tval;
   c.vsum_ptr = vsum;
   if (phase != 2) {
-    fill_from_kernel<<<(maxB + 63) / 64, 64, 0, st>>>(d_t, c.d_step, maxB);  // timestep of this index (d_step[0])
+    launch_pdl(fill_from_kernel, dim3((maxB + 63) / 64), dim3(64), 0, st, d_t, c.d_step, maxB);  // timestep of this index (d_step[0])
     MD_CHECK(check_launch("fill"));
     MD_CHECK(embed_time(c, d_t, t_embed, st));
     MD_CHECK(vertex_feature_sum(c, x_local, t_embed, vsum, st));
@@ -165,7 +171,7 @@ static int denoise_step_impl(Ctx& c, float* x_local, const float* x_input, const
     bf16* levels[4];
     MD_CHECK(frustum_levels(c, vol, lv0, T, t_embed, T, levels, st));
     MD_CHECK(launch_unet_input(x_local + static_cast<size_t>(lv0) * 4 * HW, x_input, 0, x_in, T, HW, cfg, st));
-    make_context_kernel<<<(B * mc.context_dim + 255) / 256, 256, 0, st>>>(clip, ctxv, T, B, mc.context_dim);
+    launch_pdl(make_context_kernel, dim3((B * mc.context_dim + 255) / 256), dim3(256), 0, st, clip, ctxv, T, B, mc.context_dim);
     MD_CHECK(check_launch("make_context"));
     MD_CHECK(unet_forward(c, x_in, d_t, ctxv, levels, B, T, S, D, eps_all, st));
     const int add_noise = (index != 0) ? 1 : 0;
@@ -296,7 +302,7 @@ int md_embed_time(md_ctx* ctx, float timestep, float* t_embed_out, void* stream)
   c.arena.off = 0;
   float* d_t = c.arena.get<float>(1);
   if (c.arena.failed) return set_error("workspace exhausted");
-  fill_kernel<<<1, 32, 0, st>>>(d_t, timestep, 1);
+  launch_pdl(fill_kernel, dim3(1), dim3(32), 0, st, d_t, timestep, 1);
   MD_CHECK(check_launch("fill"));
   return embed_time(c, d_t, t_embed_out, st);
 }
@@ -330,7 +336,7 @@ int md_frustum_feats(md_ctx* ctx, const float* volume, int lv0, int T, const flo
   A.off = 0;
   float* vol = A.get<float>(static_cast<size_t>(V) * V * V * 64);
   if (A.failed) return set_error("workspace exhausted");
-  ncdhw_to_cl_f32_kernel<<<148 * 8, 256, 0, st>>>(volume, vol, 64, static_cast<size_t>(V) * V * V);
+  launch_pdl(ncdhw_to_cl_f32_kernel, dim3(148 * 8), dim3(256), 0, st, volume, vol, 64, static_cast<size_t>(V) * V * V);
   MD_CHECK(check_launch("ncdhw_to_cl_f32"));
   bf16* levels[4];
   MD_CHECK(frustum_levels(c, vol, lv0, T, t_embed, T, levels, st));
@@ -365,7 +371,7 @@ int md_unet_forward(md_ctx* ctx, const float* x, const float* timesteps_host, co
   }
   // NCHW -> NHWC for the 8-channel input (same transposition kernel, fp32 variant per sample)
   for (int b = 0; b < B; ++b) {
-    ncdhw_to_cl_f32_kernel<<<32, 256, 0, st>>>(x + static_cast<size_t>(b) * mc.in_channels * S * S,
+    launch_pdl(ncdhw_to_cl_f32_kernel, dim3(32), dim3(256), 0, st, x + static_cast<size_t>(b) * mc.in_channels * S * S,
                                                x_in + static_cast<size_t>(b) * mc.in_channels * S * S, mc.in_channels,
                                                static_cast<size_t>(S) * S);
     MD_CHECK(check_launch("nchw_to_nhwc"));
@@ -383,7 +389,7 @@ int md_denoise_step(md_ctx* ctx, float* x_local, const float* x_input, const flo
   // fence the caller's stream into the internal one (the legacy default stream cannot be captured)
   MD_CUDA(cudaEventRecord(c.ev_in, caller));
   MD_CUDA(cudaStreamWaitEvent(st, c.ev_in, 0));
-  set_step_params_kernel<<<1, 32, 0, st>>>(c.d_step, static_cast<float>(c.timesteps[index]), c.alphas[index],
+  launch_pdl(set_step_params_kernel, dim3(1), dim3(32), 0, st, c.d_step, static_cast<float>(c.timesteps[index]), c.alphas[index],
                                            c.alphas_prev[index], c.sigmas[index], c.sqrt_1m_alphas[index], index != 0,
                                            static_cast<uint32_t>(index), seed);
   MD_CHECK(check_launch("set_step_params"));
