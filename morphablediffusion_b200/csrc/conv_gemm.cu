@@ -30,6 +30,15 @@ static size_t g_split_ws_bytes = 0;
 static int* g_split_cnt = nullptr;
 static size_t g_split_cnt_ints = 0;
 
+// A second stream may run GEMMs concurrently with the main one (frustum branch of the step): it uses its own
+// split-K workspace, selected host-side around the launches of that branch.
+static float* g_alt_ws = nullptr;
+static int* g_alt_cnt = nullptr;
+static size_t g_alt_bytes = 0, g_alt_ints = 0;
+static bool g_use_alt = false;
+void set_split_workspace_alt(float* ws, size_t bytes, int* cnt, size_t ints) { g_alt_ws = ws; g_alt_bytes = bytes; g_alt_cnt = cnt; g_alt_ints = ints; }
+void use_split_workspace_alt(bool on) { g_use_alt = on && g_alt_ws != nullptr; }
+
 int ensure_split_workspace() {
   if (g_split_ws) return 0;
   const size_t bytes = static_cast<size_t>(96) << 20;
@@ -194,12 +203,16 @@ int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
   if (p.ksplit > 1) {
     if (a.act == ACT_GEGLU) return set_error("conv_gemm: split-K is not available with the GEGLU epilogue");
     const size_t need = static_cast<size_t>(p.m_tiles) * p.n_tiles * p.ksplit * 128 * BN * sizeof(float);
-    if (!g_split_ws || need > g_split_ws_bytes || static_cast<size_t>(p.m_tiles) * p.n_tiles * kEpiWarps > g_split_cnt_ints) {
+    float* ws = g_use_alt ? g_alt_ws : g_split_ws;
+    int* cnt = g_use_alt ? g_alt_cnt : g_split_cnt;
+    const size_t ws_bytes = g_use_alt ? g_alt_bytes : g_split_ws_bytes;
+    const size_t cnt_ints = g_use_alt ? g_alt_ints : g_split_cnt_ints;
+    if (!ws || need > ws_bytes || static_cast<size_t>(p.m_tiles) * p.n_tiles * kEpiWarps > cnt_ints) {
       if (a.ksplit > 1) return set_error("conv_gemm: split-K workspace too small (%zu bytes needed)", need);
       p.ksplit = 1;
     }
-    p.split_ws = g_split_ws;
-    p.split_cnt = g_split_cnt;
+    p.split_ws = ws;
+    p.split_cnt = cnt;
   }
   const int total = p.m_tiles * p.n_tiles * p.ksplit;
   const int grid = std::min(total, num_sms());

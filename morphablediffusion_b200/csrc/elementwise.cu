@@ -157,94 +157,6 @@ __global__ void affine_act_kernel(const T0* __restrict__ x0, int C0, const T1* _
   }
 }
 
-// Finalize + apply in one kernel (statistics already produced by the GEMM epilogues): every CTA owns a slab of rows of
-// one sample, first turns the [C][2] sums of that sample into per-channel scale/shift in shared memory (one warp per
-// group), then streams its rows.
-template <typename T0, typename T1>
-__global__ void gn_apply_fused_kernel(const T0* __restrict__ x0, int C0, const T1* __restrict__ x1, int C1,
-                                      const float* __restrict__ stats0, const float* __restrict__ stats1,
-                                      const float* __restrict__ gamma, const float* __restrict__ beta,
-                                      const float* __restrict__ addvec, int addvec_ld, __nv_bfloat16* __restrict__ out,
-                                      __nv_bfloat16* __restrict__ raw, int rows, int rows_per_cta, int G, float eps,
-                                      int act) {
-  pdl_grid_sync();
-  extern __shared__ float ssm[];  // [C][2]: first the per-channel sums, then scale / shift
-  __shared__ float gmean[64], grstd[64];
-  const int C = C0 + C1;
-  const int b = blockIdx.y;
-  const int cpg = C / G;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  const float nrows = static_cast<float>(rows);
-  // (1) all threads: per-channel sums of (x + addvec) into shared memory
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const float* sp = (c < C0) ? stats0 + (static_cast<size_t>(b) * C0 + c) * 2
-                               : stats1 + (static_cast<size_t>(b) * C1 + (c - C0)) * 2;
-    const float a = sp[0], q = sp[1];
-    const float tv = addvec ? addvec[static_cast<size_t>(b) * addvec_ld + c] : 0.f;
-    ssm[2 * c] = a + nrows * tv;
-    ssm[2 * c + 1] = q + 2.f * tv * a + nrows * tv * tv;
-  }
-  __syncthreads();
-  // (2) one warp per group: mean / rstd (double accumulation of the per-channel partials)
-  for (int g = warp; g < G; g += nwarps) {
-    double s1 = 0.0, s2 = 0.0;
-    for (int c = g * cpg + lane; c < (g + 1) * cpg; c += 32) { s1 += ssm[2 * c]; s2 += ssm[2 * c + 1]; }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) {
-      s1 += __shfl_xor_sync(0xffffffff, s1, o);
-      s2 += __shfl_xor_sync(0xffffffff, s2, o);
-    }
-    if (lane == 0) {
-      const double n = static_cast<double>(nrows) * cpg;
-      const double mean = s1 / n;
-      double var = s2 / n - mean * mean;
-      if (var < 0.0) var = 0.0;
-      gmean[g] = static_cast<float>(mean);
-      grstd[g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
-    }
-  }
-  __syncthreads();
-  // (3) all threads: per-channel scale / shift
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const int g = c / cpg;
-    const float tv = addvec ? addvec[static_cast<size_t>(b) * addvec_ld + c] : 0.f;
-    const float sc = gamma[c] * grstd[g];
-    ssm[2 * c] = sc;
-    ssm[2 * c + 1] = beta[c] + (tv - gmean[g]) * sc;
-  }
-  __syncthreads();
-  // (4) stream the slab: thread = (4-channel group cq, row lane rsub); scale/shift of the group stay in registers
-  const int CQ = C >> 2;
-  const int r0 = blockIdx.x * rows_per_cta;
-  const int r1 = min(rows, r0 + rows_per_cta);
-  const int R = max(1, static_cast<int>(blockDim.x) / CQ);
-  for (int cq0 = 0; cq0 < CQ; cq0 += blockDim.x) {  // CQ > blockDim.x only for very wide tensors
-    const int cq = cq0 + static_cast<int>(threadIdx.x) % min(CQ, static_cast<int>(blockDim.x));
-    const int rsub = static_cast<int>(threadIdx.x) / min(CQ, static_cast<int>(blockDim.x));
-    if (cq >= CQ || rsub >= R) continue;
-    const int c = cq * 4;
-    const float4 s01 = *reinterpret_cast<const float4*>(ssm + 2 * c);
-    const float4 s23 = *reinterpret_cast<const float4*>(ssm + 2 * c + 4);
-    const bool first = c < C0;
-    const size_t rowbase = static_cast<size_t>(b) * rows;
-#pragma unroll 4
-    for (int r = r0 + rsub; r < r1; r += R) {
-      const size_t row = rowbase + r;
-      float4 v;
-      if (first) v = load4(x0 + row * C0 + c);
-      else v = load4(x1 + row * C1 + (c - C0));
-      if (raw) store4(raw + row * C + c, v);
-      float4 y = make_float4(v.x * s01.x + s01.y, v.y * s01.z + s01.w, v.z * s23.x + s23.y, v.w * s23.z + s23.w);
-      if (act == ACT_SILU) {
-        y.x = silu_f(y.x); y.y = silu_f(y.y); y.z = silu_f(y.z); y.w = silu_f(y.w);
-      } else if (act == ACT_RELU) {
-        y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f);
-      }
-      store4(out + row * C + c, y);
-    }
-  }
-}
-
 template <typename T0, typename T1>
 static int group_norm_impl(const GroupNormArgs& a, cudaStream_t st) {
   const int C = a.C0 + a.C1;
@@ -254,19 +166,6 @@ static int group_norm_impl(const GroupNormArgs& a, cudaStream_t st) {
   if (CQ > 1024) return set_error("group_norm: C=%d too large", C);
   int R = std::max(1, std::min(8, 256 / CQ));
   const int threads = CQ * R;
-  if (a.stats0 && (a.C1 == 0 || a.stats1) && a.out) {
-    // statistics came from the producers: one fused finalize+apply launch
-    const int target = num_sms() * 8;
-    int rows_per_cta = std::max(1, static_cast<int>((static_cast<long long>(a.rows) * a.B + target - 1) / target));
-    const int min_rows = std::max(2, 4096 / C);  // keep the per-CTA statistics prologue small next to the streamed slab
-    rows_per_cta = std::min(std::max(rows_per_cta, min_rows), a.rows);
-    dim3 grid((a.rows + rows_per_cta - 1) / rows_per_cta, a.B);
-    launch_pdl(gn_apply_fused_kernel<T0, T1>, dim3(grid), dim3(256), static_cast<size_t>(C) * 2 * sizeof(float), st, 
-        static_cast<const T0*>(a.x0), a.C0, static_cast<const T1*>(a.x1), a.C1, a.stats0, a.stats1, a.gamma, a.beta,
-        a.addvec, a.addvec_ld, static_cast<__nv_bfloat16*>(a.out), static_cast<__nv_bfloat16*>(a.raw_out), a.rows,
-        rows_per_cta, a.groups, a.eps, a.act);
-    return check_launch("gn_apply_fused");
-  }
   float* st0 = const_cast<float*>(a.stats0);
   float* st1 = const_cast<float*>(a.stats1);
   int c0 = a.C0, c1 = a.C1, zero_after = 0;

@@ -112,6 +112,12 @@ struct Ctx {
   bool weights_loaded = false;
   std::vector<void*> weight_allocs;
   Arena arena;
+  // conditioning branch (sparse conv + frustum nets) runs on a second stream, concurrently with the UNet's input half
+  Arena arena2;
+  cudaStream_t stream2 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_levels = nullptr;
+  bool levels_pending = false;         // unet_forward must wait on ev_levels before its first depth transformer
+  float* split_ws2 = nullptr; int* split_cnt2 = nullptr;
   SampleBinding sb;
   // DDIM schedule (host)
   std::vector<float> alphas, alphas_prev, sigmas, sqrt_1m_alphas;

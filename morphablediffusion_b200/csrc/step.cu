@@ -162,18 +162,43 @@ static int denoise_step_impl(Ctx& c, float* x_local, const float* x_input, const
   }
   if (phase == 0) MD_CHECK(allreduce_vsum(c, st));
   if (phase == 1) return 0;
-  MD_CHECK(spatial_volume_from_vsum(c, vsum, vol, st));
 
+  // Conditioning branch (sparse conv -> spatial volume -> frustum nets) and the UNet's input half are independent:
+  // with a single view chunk the former runs on a second stream (own arena, own split-K workspace) and the UNet joins
+  // it right before its first depth transformer.
+  const bool overlap = c.stream2 != nullptr && sb.n_local <= chunk && getenv("MD_NO_OVERLAP") == nullptr;
   const size_t m = A.mark();
   for (int lv0 = 0; lv0 < sb.n_local; lv0 += chunk) {
     const int T = std::min(chunk, sb.n_local - lv0);
     const int B = (cfg ? 2 : 1) * T;
     bf16* levels[4];
-    MD_CHECK(frustum_levels(c, vol, lv0, T, t_embed, T, levels, st));
+    if (overlap) {
+      MD_CUDA(cudaEventRecord(c.ev_fork, st));
+      MD_CUDA(cudaStreamWaitEvent(c.stream2, c.ev_fork, 0));
+      std::swap(c.arena, c.arena2);
+      c.arena.off = 0;
+      c.arena.failed = false;
+      set_split_workspace_alt(c.split_ws2, static_cast<size_t>(48) << 20, c.split_cnt2, 1 << 15);
+      use_split_workspace_alt(true);
+      int rc = spatial_volume_from_vsum(c, vsum, vol, c.stream2);
+      if (rc == 0) rc = frustum_levels(c, vol, lv0, T, t_embed, T, levels, c.stream2);
+      use_split_workspace_alt(false);
+      std::swap(c.arena, c.arena2);
+      if (rc != 0) return rc;
+      MD_CUDA(cudaEventRecord(c.ev_levels, c.stream2));
+      c.levels_pending = true;
+    } else {
+      if (lv0 == 0) MD_CHECK(spatial_volume_from_vsum(c, vsum, vol, st));
+      MD_CHECK(frustum_levels(c, vol, lv0, T, t_embed, T, levels, st));
+    }
     MD_CHECK(launch_unet_input(x_local + static_cast<size_t>(lv0) * 4 * HW, x_input, 0, x_in, T, HW, cfg, st));
     launch_pdl(make_context_kernel, dim3((B * mc.context_dim + 255) / 256), dim3(256), 0, st, clip, ctxv, T, B, mc.context_dim);
     MD_CHECK(check_launch("make_context"));
     MD_CHECK(unet_forward(c, x_in, d_t, ctxv, levels, B, T, S, D, eps_all, st));
+    if (c.levels_pending) {  // defensive: a UNet without depth transformers would never have joined
+      MD_CUDA(cudaStreamWaitEvent(st, c.ev_levels, 0));
+      c.levels_pending = false;
+    }
     const int add_noise = (index != 0) ? 1 : 0;
     MD_CHECK(launch_cfg_ddim(eps_all, x_local + static_cast<size_t>(lv0) * 4 * HW,
                              eps_out ? eps_out + static_cast<size_t>(lv0) * 4 * HW : nullptr,
@@ -242,6 +267,21 @@ int md_create(md_ctx** out, const md_config* cfg) {
     delete ctx;
     return set_error("md_create: stream / event setup failed: %s", cudaGetErrorString(e));
   }
+  {  // second stream for the conditioning branch
+    const size_t bytes2 = (static_cast<size_t>(384) << 20) + static_cast<size_t>(mv * scale * 48.0) * (1ull << 20);
+    cudaError_t e2 = cudaMalloc(reinterpret_cast<void**>(&ctx->c.arena2.base), bytes2);
+    if (e2 == cudaSuccess) {
+      ctx->c.arena2.cap = bytes2;
+      e2 = cudaStreamCreateWithFlags(&ctx->c.stream2, cudaStreamNonBlocking);
+    }
+    if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&ctx->c.ev_fork, cudaEventDisableTiming);
+    if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&ctx->c.ev_levels, cudaEventDisableTiming);
+    const size_t ws2 = static_cast<size_t>(48) << 20, ints2 = 1 << 15;
+    if (e2 == cudaSuccess) e2 = cudaMalloc(reinterpret_cast<void**>(&ctx->c.split_ws2), ws2);
+    if (e2 == cudaSuccess) e2 = cudaMalloc(reinterpret_cast<void**>(&ctx->c.split_cnt2), ints2 * sizeof(int));
+    if (e2 == cudaSuccess) e2 = cudaMemset(ctx->c.split_cnt2, 0, ints2 * sizeof(int));
+    if (e2 != cudaSuccess) { cudaGetLastError(); ctx->c.stream2 = nullptr; }  // overlap simply stays off
+  }
   ctx->c.use_graph = getenv("MD_NO_GRAPH") == nullptr;
   *out = ctx;
   return 0;
@@ -259,6 +299,12 @@ void md_destroy(md_ctx* ctx) {
   if (ctx->c.ev_in) cudaEventDestroy(ctx->c.ev_in);
   if (ctx->c.ev_out) cudaEventDestroy(ctx->c.ev_out);
   cudaFree(ctx->c.d_step);
+  if (ctx->c.stream2) cudaStreamDestroy(ctx->c.stream2);
+  if (ctx->c.ev_fork) cudaEventDestroy(ctx->c.ev_fork);
+  if (ctx->c.ev_levels) cudaEventDestroy(ctx->c.ev_levels);
+  cudaFree(ctx->c.arena2.base);
+  cudaFree(ctx->c.split_ws2);
+  cudaFree(ctx->c.split_cnt2);
   cudaFree(ctx->c.arena.base);
   cudaFree(ctx->c.gn_stats);
   delete ctx;

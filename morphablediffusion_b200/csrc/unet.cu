@@ -322,6 +322,10 @@ int unet_forward(Ctx& c, const float* x_in, const float* timesteps, const float*
     MD_CHECK(f.res_block(u.mid2, o1, ch, nullptr, 0, H, H, o2));
     const bf16* lv; int dd;
     if (level_of(H, lv, dd) != 0) return set_error("unet: no frustum level of width %d", H);
+    if (c.levels_pending) {  // the frustum pyramids are produced on the second stream: join here
+      MD_CUDA(cudaStreamWaitEvent(st, c.ev_levels, 0));
+      c.levels_pending = false;
+    }
     MD_CHECK(f.depth_transformer(u.mid_cond, o2, H, H, lv, dd, o3));
     h = o3;
   }
