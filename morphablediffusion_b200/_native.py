@@ -9,6 +9,8 @@ from pathlib import Path
 
 _ROOT = Path(__file__).resolve().parent
 LIB_PATH = _ROOT / "_lib" / "libmdiff.so"
+if os.environ.get("MD_BUILD_TAG"):  # development variant built by build.py with the same tag (e.g. phase-stamp build)
+    LIB_PATH = _ROOT / "_lib" / os.environ["MD_BUILD_TAG"] / "libmdiff.so"
 
 
 class MdiffError(RuntimeError):

@@ -8,6 +8,10 @@ ROOT = Path(__file__).resolve().parent
 CSRC = ROOT / "csrc"
 OUT = ROOT / "_lib"
 LIB = OUT / "libmdiff.so"
+# development variants: MD_BUILD_FLAGS="-DMD_KPROF" MD_BUILD_TAG=kprof builds _lib/kprof/libmdiff.so beside the product
+if os.environ.get("MD_BUILD_TAG"):
+    OUT = OUT / os.environ["MD_BUILD_TAG"]
+    LIB = OUT / "libmdiff.so"
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
@@ -31,7 +35,7 @@ def needs_build():
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
-    OUT.mkdir(exist_ok=True)
+    OUT.mkdir(parents=True, exist_ok=True)
     objs = []
     procs = []
     for src in sources():
@@ -40,7 +44,7 @@ def build(force=False, verbose=False):
         deps = [src] + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + [ROOT.parent / "include" / "mdiff.h"]
         if not force and obj.exists() and all(obj.stat().st_mtime > d.stat().st_mtime for d in deps):
             continue
-        cmd = ["nvcc", *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
+        cmd = ["nvcc", *NVCC_FLAGS, *os.environ.get("MD_BUILD_FLAGS", "").split(), "-c", str(src), "-o", str(obj)]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

@@ -1,4 +1,6 @@
 // C-ABI surface of libmdiff: error handling, launch accounting and the op-level entry points.
+#include <mutex>
+#include <unordered_set>
 #include "host.h"
 
 #include <stdarg.h>
@@ -24,6 +26,18 @@ bool pdl_enabled() {
   // programmatic dependent launch is wired through every kernel but measured neutral inside CUDA graphs: opt-in
   static const bool on = getenv("MD_PDL") != nullptr;
   return on;
+}
+
+void prefer_max_smem(const void* kernel) {
+  // Every kernel of the step asks for the same (maximum-shared) L1 carve-out: the GEMM needs it anyway, and a uniform
+  // setting means consecutive kernels can share an SM (PDL) and no boundary pays for re-partitioning the SM's SRAM.
+  static const bool off = getenv("MD_NO_CARVEOUT") != nullptr;
+  if (off) return;
+  static std::mutex mu;
+  static std::unordered_set<const void*> seen;
+  std::lock_guard<std::mutex> lk(mu);
+  if (seen.insert(kernel).second)
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
 }
 
 int num_sms() {

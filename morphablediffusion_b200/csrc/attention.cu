@@ -15,6 +15,11 @@ __device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
 }
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], const void* p) {
+  const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(p));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
 __device__ __forceinline__ void ldsm_x2(uint32_t (&r)[2], const void* p) {
   const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(p));
   asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(a));
@@ -34,6 +39,12 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+__device__ __forceinline__ float fast_exp2(float x) {  // ex2.approx.ftz: no denormal fix-up code around the MUFU
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 constexpr int kAttBK = 64;   // keys per tile
 
 __device__ __forceinline__ void cp_async16(void* dst, const void* src, bool valid) {
@@ -48,8 +59,11 @@ template <int N> __device__ __forceinline__ void cp_async_wait() {
 
 // DHP: head dim padded to a multiple of 16; NW warps x 16 queries per CTA.  Row stride DHP+8 keeps ldmatrix rows on
 // distinct banks.  K/V tiles are double-buffered with cp.async so the next tile streams in while this one is used.
+#ifndef MD_ATT_MINBLOCKS
+#define MD_ATT_MINBLOCKS 2
+#endif
 template <int DHP, int NW>
-__global__ void __launch_bounds__(NW * 32)
+__global__ void __launch_bounds__(NW * 32, (DHP <= 48 && NW == 8) ? MD_ATT_MINBLOCKS : 1)
 self_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int S, int heads, int dh,
                       float scale_log2e) {
   pdl_grid_sync();
@@ -82,16 +96,29 @@ self_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __re
       *reinterpret_cast<uint4*>(sK + r * LD + c * 8) = make_uint4(0, 0, 0, 0);  // sK and sV are contiguous: 4*64 rows
     }
   }
+  // K/V tile copy: every thread owns up to kSlots fixed (row, 16-byte chunk) slots of a tile; only the tile origin
+  // changes between tiles, so the index arithmetic is done once
+  constexpr int kSlots = (kAttBK * chunksP + NT - 1) / NT;
+  int slot[kSlots];  // row | chunk << 8, or -1
+#pragma unroll
+  for (int k = 0; k < kSlots; ++k) {
+    const int i = threadIdx.x + k * NT;
+    const int r = i / chunks, c = i - r * chunks;
+    slot[k] = (i < kAttBK * chunks) ? (r | (c << 8)) : -1;
+  }
   auto prefetch = [&](int tile) {
     const int k0 = tile * kAttBK;
     __nv_bfloat16* dk = sK + (tile & 1) * kAttBK * LD;
     __nv_bfloat16* dv = sV + (tile & 1) * kAttBK * LD;
-    for (int i = threadIdx.x; i < kAttBK * chunks; i += NT) {
-      const int r = i / chunks, c = i % chunks;
-      const bool ok = k0 + r < S;
-      const __nv_bfloat16* src = base + static_cast<size_t>(ok ? k0 + r : 0) * row_stride + c * 8;
-      cp_async16(dk + r * LD + c * 8, src + C, ok);
-      cp_async16(dv + r * LD + c * 8, src + 2 * C, ok);
+#pragma unroll
+    for (int k = 0; k < kSlots; ++k) {
+      if (slot[k] >= 0) {
+        const int r = slot[k] & 255, c8 = (slot[k] >> 8) * 8;
+        const bool ok = k0 + r < S;
+        const __nv_bfloat16* src = base + static_cast<size_t>(ok ? k0 + r : 0) * row_stride + c8;
+        cp_async16(dk + r * LD + c8, src + C, ok);
+        cp_async16(dv + r * LD + c8, src + 2 * C, ok);
+      }
     }
     cp_async_commit();
   };
@@ -122,15 +149,19 @@ self_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __re
 
     float s[kAttBK / 8][4];
 #pragma unroll
-    for (int j = 0; j < kAttBK / 8; ++j) {
+    for (int j = 0; j < kAttBK / 8; j += 2) {
       s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+      s[j + 1][0] = s[j + 1][1] = s[j + 1][2] = s[j + 1][3] = 0.f;
 #pragma unroll
       for (int kk = 0; kk < DHP / 16; ++kk) {
-        uint32_t bf[2];
-        const int r = j * 8 + (lane & 7);
+        // one ldmatrix.x4 = B fragments of two 8-key groups: lanes 0-15 address group j, lanes 16-31 group j+1
+        uint32_t bf[4];
+        const int r = (j + (lane >> 4)) * 8 + (lane & 7);
         const int c = kk * 16 + ((lane >> 3) & 1) * 8;
-        ldsm_x2(bf, tK + r * LD + c);
-        mma_bf16_16816(s[j], qf[kk], bf);
+        ldsm_x4(bf, tK + r * LD + c);
+        const uint32_t b0[2] = {bf[0], bf[1]}, b1[2] = {bf[2], bf[3]};
+        mma_bf16_16816(s[j], qf[kk], b0);
+        mma_bf16_16816(s[j + 1], qf[kk], b1);
       }
     }
     // mask keys beyond the sequence
@@ -152,8 +183,8 @@ self_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __re
     mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffff, mx0, 2));
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffff, mx1, 1));
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffff, mx1, 2));
-    const float corr0 = exp2f((m0 - mx0) * scale_log2e);
-    const float corr1 = exp2f((m1 - mx1) * scale_log2e);
+    const float corr0 = fast_exp2((m0 - mx0) * scale_log2e);
+    const float corr1 = fast_exp2((m1 - mx1) * scale_log2e);
     m0 = mx0; m1 = mx1;
     l0 *= corr0; l1 *= corr1;
 #pragma unroll
@@ -162,10 +193,10 @@ self_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __re
     uint32_t pf[kAttBK / 16][4];
 #pragma unroll
     for (int j = 0; j < kAttBK / 8; ++j) {
-      const float p0 = exp2f(fmaf(s[j][0], scale_log2e, -mb0));
-      const float p1 = exp2f(fmaf(s[j][1], scale_log2e, -mb0));
-      const float p2 = exp2f(fmaf(s[j][2], scale_log2e, -mb1));
-      const float p3 = exp2f(fmaf(s[j][3], scale_log2e, -mb1));
+      const float p0 = fast_exp2(fmaf(s[j][0], scale_log2e, -mb0));
+      const float p1 = fast_exp2(fmaf(s[j][1], scale_log2e, -mb0));
+      const float p2 = fast_exp2(fmaf(s[j][2], scale_log2e, -mb1));
+      const float p3 = fast_exp2(fmaf(s[j][3], scale_log2e, -mb1));
       l0 += p0 + p1; l1 += p2 + p3;
       pf[j >> 1][(j & 1) * 2 + 0] = pack_bf16(p0, p1);
       pf[j >> 1][(j & 1) * 2 + 1] = pack_bf16(p2, p3);
@@ -173,11 +204,14 @@ self_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __re
 #pragma unroll
     for (int kk = 0; kk < kAttBK / 16; ++kk) {
 #pragma unroll
-      for (int i = 0; i < DHP / 8; ++i) {
-        uint32_t bf[2];
+      for (int i = 0; i < DHP / 8; i += 2) {
+        // transposed x4: lanes 0-15 address dims i*8.., lanes 16-31 dims (i+1)*8.. of the same 16 keys
+        uint32_t bf[4];
         const int r = kk * 16 + (lane & 15);
-        ldsm_x2_trans(bf, tV + r * LD + i * 8);
-        mma_bf16_16816(o[i], pf[kk], bf);
+        ldsm_x4_trans(bf, tV + r * LD + (i + (lane >> 4)) * 8);
+        const uint32_t b0[2] = {bf[0], bf[1]}, b1[2] = {bf[2], bf[3]};
+        mma_bf16_16816(o[i], pf[kk], b0);
+        mma_bf16_16816(o[i + 1], pf[kk], b1);
       }
     }
     __syncthreads();  // everyone done with buffer t&1 before it is refilled (tile t+2)

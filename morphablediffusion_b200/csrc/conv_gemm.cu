@@ -214,6 +214,11 @@ int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
     p.split_ws = ws;
     p.split_cnt = cnt;
   }
+  p.fd_ksplit = make_fastdiv(p.ksplit);
+  p.fd_ntiles = make_fastdiv(p.n_tiles);
+  p.fd_nxb = make_fastdiv(p.nxb);
+  p.fd_nyb = make_fastdiv(p.nyb);
+  p.fd_nzb = make_fastdiv(p.nzb);
   const int total = p.m_tiles * p.n_tiles * p.ksplit;
   const int grid = std::min(total, num_sms());
   p.contig = (p.n_tiles == 1 && p.ksplit == 1 && total > 2 * grid) ? 1 : 0;
@@ -232,3 +237,15 @@ int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
 }
 
 }  // namespace md
+
+#ifdef MD_KPROF
+// Development builds only: phase time stamps of the last conv_gemm launch ([160 CTAs][16 slots], globaltimer ns).
+extern "C" __attribute__((visibility("default"))) int md_debug_kprof(unsigned long long* host_out, int clear) {
+  if (cudaMemcpyFromSymbol(host_out, md::g_kprof, sizeof(unsigned long long) * 160 * 16) != cudaSuccess) return -1;
+  if (clear) {
+    static unsigned long long zeros[160 * 16];
+    cudaMemcpyToSymbol(md::g_kprof, zeros, sizeof(zeros));
+  }
+  return 0;
+}
+#endif

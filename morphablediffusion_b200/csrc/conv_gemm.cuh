@@ -14,10 +14,45 @@
 
 namespace md {
 
+// Development-only phase stamps (build with -DMD_KPROF): globaltimer per CTA and phase, read back with md_debug_kprof.
+#ifdef MD_KPROF
+__device__ unsigned long long g_kprof[160 * 16];
+__device__ __forceinline__ void kprof(int slot) {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  if (blockIdx.x < 160) g_kprof[blockIdx.x * 16 + slot] = t;
+}
+#define KPROF(slot, cond) do { if (cond) kprof(slot); } while (0)
+#else
+#define KPROF(slot, cond) do { } while (0)
+#endif
+
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
 constexpr int kMaxTaps = 27;
 
+
+// Division by a launch-time constant as multiply + shift (exact for n < 2^31): the per-tile coordinate arithmetic runs
+// in every one of the 18 warps, so runtime integer division there costs more issue slots than the epilogue's payload.
+struct FastDiv {
+  uint32_t mul, shift, d;
+};
+inline FastDiv make_fastdiv(int d) {
+  FastDiv f;
+  f.d = static_cast<uint32_t>(d < 1 ? 1 : d);
+  uint32_t s = 0;
+  while ((1u << s) < f.d) ++s;
+  f.shift = 31 + s;
+  f.mul = static_cast<uint32_t>(((1ull << f.shift) + f.d - 1) / f.d);
+  return f;
+}
+__device__ __forceinline__ int fdiv(int n, const FastDiv& f) {
+  return static_cast<int>((static_cast<unsigned long long>(static_cast<uint32_t>(n)) * f.mul) >> f.shift);
+}
+__device__ __forceinline__ void fdivmod(int n, const FastDiv& f, int& q, int& r) {
+  q = fdiv(n, f);
+  r = n - q * static_cast<int>(f.d);
+}
 
 struct ConvGemmParams {
   // input (A) geometry, channels-last [B][D][H][W][C]
@@ -52,7 +87,24 @@ struct ConvGemmParams {
   float* split_ws;  // [tiles][ksplit][128][BN] fp32
   int* split_cnt;   // [tiles][EPI_WARPS] arrival counters (zero on entry, reset by the last arrival)
   int isx, isy, isz; // input coordinate = output-tile coordinate * is + tap offset (strided convolution via TMA element strides)
+  FastDiv fd_ksplit, fd_ntiles, fd_nxb, fd_nyb, fd_nzb;
 };
+
+// work item -> (n tile, box coordinates, K split)
+struct TileCoord {
+  int tile, sp, n_tile, xb, yb, zb, bblk;
+};
+__device__ __forceinline__ TileCoord decode_item(const ConvGemmParams& p, int item) {
+  TileCoord t;
+  fdivmod(item, p.fd_ksplit, t.tile, t.sp);
+  int m;
+  fdivmod(t.tile, p.fd_ntiles, m, t.n_tile);
+  int m2;
+  fdivmod(m, p.fd_nxb, m2, t.xb);
+  fdivmod(m2, p.fd_nyb, m, t.yb);
+  fdivmod(m, p.fd_nzb, t.bblk, t.zb);
+  return t;
+}
 
 __device__ __forceinline__ float act_silu(float x) { return x / (1.f + __expf(-x)); }
 // exact-erf GELU (F.gelu default) with erf from Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7): 1 rcp + 1 exp + 6 fma
@@ -76,8 +128,7 @@ struct ConvGemmSmem {
   static constexpr int kBBytes = BN * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStageOffset = STAGES * kStageBytes;            // kEpiWarps x 2 KB staging tiles (32 rows x 16 fp32)
-  static constexpr int kRowOffset = kStageOffset + kEpiWarps * 2048;   // [2][4 quarters][32] (row offset, sample)
-  static constexpr int kBarOffset = kRowOffset + 2 * 4 * 32 * 8;
+  static constexpr int kBarOffset = kStageOffset + kEpiWarps * 2048;
   static constexpr int kTotal = kBarOffset + 256;
 };
 
@@ -128,22 +179,31 @@ __device__ __forceinline__ void flush_col_stats(const ConvGemmParams& p, int lan
 }
 
 // Epilogue of one output tile for one warp: its 32 accumulator rows x the 16-column chunks c_begin, c_begin+4, ...
-// Specialised on the residual kind / per-sample vector so that the inner loops are branch-free.
+// Specialised on the residual kind / per-sample vector / presence of an activation so the inner loops are branch-free.
 //   phase 0: issue the chunk's global loads (bias, per-sample vector, residual) in the coalesced phase-2 layout;
 //   phase 1 (row owner): TMEM -> registers, scale (+bias, GEGLU), swizzled store into a private 32x16 staging tile;
 //   phase 2 (coalesced; one warp instruction = 8 rows x 64 B): + bias, + per-sample vector, activation, + residual,
 //            fp32 / bf16 stores, per-(sample, channel) sum / sum-of-squares for the next GroupNorm.
-template <int BN, int RES, bool RV, int NCH, bool STATS>
+// ri[it] = (output row offset in elements or -1, sample) of phase-2 row it*8 + (lane>>2), fetched once per tile.
+template <int BN, int RES, bool RV, int NCH, bool STATS, bool ACTV>
 __device__ __forceinline__ void epilogue_tile(const ConvGemmParams& p, uint32_t taddr, float* stage, int lane, int n_tile,
-                                              const int2* rowinfo, int c_begin, float (&st1)[NCH][4],
+                                              const int2 (&ri)[4], int c_begin, float (&st1)[NCH][4],
                                               float (&st2)[NCH][4]) {
   const int prow = lane >> 2;   // phase-2 row within a group of 8
   const int pchunk = lane & 3;  // phase-2 16-byte chunk within the 64-byte row
-  const bool geglu = (p.act == ACT_GEGLU);
+  const bool geglu = ACTV && (p.act == ACT_GEGLU);
   constexpr int HALF = BN / 2;
   const int out_cols = geglu ? HALF : BN;
   const int n_limit = geglu ? p.N / 2 : p.N;
   const int n_out0 = n_tile * out_cols;
+  const float* const bias = p.bias;
+  float* const out_f32 = p.out_f32;
+  __nv_bfloat16* const out_bf16 = p.out_bf16;
+  const bool scaled = p.out_scale != 1.f;
+  const float* const st_rd = stage + prow * 16;  // phase-2 read base; row it*8+prow -> + it*128, chunk swizzled below
+  const int sw = (prow >> 1) & 3;                // ((it*8 + prow) >> 1) & 3 == (prow >> 1) & 3
+  float* const st_wr = stage + lane * 16;
+  const int swl = (lane >> 1) & 3;
   int ci = 0;
 #pragma unroll 1
   for (int c = c_begin; c < out_cols / kChunk; c += 4, ++ci) {
@@ -155,14 +215,13 @@ __device__ __forceinline__ void epilogue_tile(const ConvGemmParams& p, uint32_t 
     float4 rs4[4];
     uint2 rb2[4];
     float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (p.bias && !geglu) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col_safe));
+    if (bias && !geglu) b4 = __ldg(reinterpret_cast<const float4*>(bias + col_safe));
     if (RV || RES != 0) {
 #pragma unroll
       for (int it = 0; it < 4; ++it) {
-        const int2 ri = rowinfo[it * 8 + prow];  // (row offset in elements or -1, sample)
-        const bool ok = ri.x >= 0;
-        const long long ro = ok ? ri.x : 0;
-        if (RV) rv4[it] = __ldg(reinterpret_cast<const float4*>(p.rowvec + static_cast<long long>(ok ? ri.y : 0) * p.rowvec_ld + col_safe));
+        const bool ok = ri[it].x >= 0;
+        const long long ro = ok ? ri[it].x : 0;
+        if (RV) rv4[it] = __ldg(reinterpret_cast<const float4*>(p.rowvec + static_cast<long long>(ok ? ri[it].y : 0) * p.rowvec_ld + col_safe));
         if (RES == 1) rs4[it] = *reinterpret_cast<const float4*>(p.res_f32 + ro + col_safe);
         if (RES == 2) rb2[it] = *reinterpret_cast<const uint2*>(p.res_bf16 + ro + col_safe);
       }
@@ -178,57 +237,61 @@ __device__ __forceinline__ void epilogue_tile(const ConvGemmParams& p, uint32_t 
         tc_wait_ld();
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float4 bv = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + nb) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-          const float4 bg = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + nb + HALF) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4 bv = bias ? __ldg(reinterpret_cast<const float4*>(bias + nb) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4 bg = bias ? __ldg(reinterpret_cast<const float4*>(bias + nb + HALF) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
           float4 o;
           o.x = (__uint_as_float(v[4 * j]) + bv.x) * act_gelu(__uint_as_float(g[4 * j]) + bg.x);
           o.y = (__uint_as_float(v[4 * j + 1]) + bv.y) * act_gelu(__uint_as_float(g[4 * j + 1]) + bg.y);
           o.z = (__uint_as_float(v[4 * j + 2]) + bv.z) * act_gelu(__uint_as_float(g[4 * j + 2]) + bg.z);
           o.w = (__uint_as_float(v[4 * j + 3]) + bv.w) * act_gelu(__uint_as_float(g[4 * j + 3]) + bg.w);
-          *reinterpret_cast<float4*>(stage + lane * 16 + ((j ^ ((lane >> 1) & 3)) << 2)) = o;
+          *reinterpret_cast<float4*>(st_wr + ((j ^ swl) << 2)) = o;
         }
       } else {
         tc_wait_ld();
+        if (scaled) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 o = make_float4(__uint_as_float(v[4 * j]) * p.out_scale, __uint_as_float(v[4 * j + 1]) * p.out_scale,
-                                       __uint_as_float(v[4 * j + 2]) * p.out_scale, __uint_as_float(v[4 * j + 3]) * p.out_scale);
-          *reinterpret_cast<float4*>(stage + lane * 16 + ((j ^ ((lane >> 1) & 3)) << 2)) = o;
+          for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * p.out_scale);
         }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<uint4*>(st_wr + ((j ^ swl) << 2)) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
       }
     }
     __syncwarp();
-    // ---- phase 2: coalesced finish
+    // ---- phase 2: coalesced finish; all four staged rows are fetched before the arithmetic
+    float4 t4[4];
+#pragma unroll
+    for (int it = 0; it < 4; ++it) t4[it] = *reinterpret_cast<const float4*>(st_rd + it * 128 + ((pchunk ^ sw) << 2));
     float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
-      const int row = it * 8 + prow;
-      const int2 ri = rowinfo[row];
-      const bool ok = (ri.x >= 0) && col_ok;
-      float4 v4 = *reinterpret_cast<const float4*>(stage + row * 16 + ((pchunk ^ ((row >> 1) & 3)) << 2));
+      const bool ok = (ri[it].x >= 0) && col_ok;
+      float4 v4 = t4[it];
       v4.x += b4.x; v4.y += b4.y; v4.z += b4.z; v4.w += b4.w;
       if (RV) { v4.x += rv4[it].x; v4.y += rv4[it].y; v4.z += rv4[it].z; v4.w += rv4[it].w; }
-      if (p.act == ACT_SILU) {
-        v4.x = act_silu(v4.x); v4.y = act_silu(v4.y); v4.z = act_silu(v4.z); v4.w = act_silu(v4.w);
-      } else if (p.act == ACT_RELU) {
-        v4.x = fmaxf(v4.x, 0.f); v4.y = fmaxf(v4.y, 0.f); v4.z = fmaxf(v4.z, 0.f); v4.w = fmaxf(v4.w, 0.f);
-      } else if (p.act == ACT_GELU) {
-        v4.x = act_gelu(v4.x); v4.y = act_gelu(v4.y); v4.z = act_gelu(v4.z); v4.w = act_gelu(v4.w);
+      if (ACTV) {
+        if (p.act == ACT_SILU) {
+          v4.x = act_silu(v4.x); v4.y = act_silu(v4.y); v4.z = act_silu(v4.z); v4.w = act_silu(v4.w);
+        } else if (p.act == ACT_RELU) {
+          v4.x = fmaxf(v4.x, 0.f); v4.y = fmaxf(v4.y, 0.f); v4.z = fmaxf(v4.z, 0.f); v4.w = fmaxf(v4.w, 0.f);
+        } else if (p.act == ACT_GELU) {
+          v4.x = act_gelu(v4.x); v4.y = act_gelu(v4.y); v4.z = act_gelu(v4.z); v4.w = act_gelu(v4.w);
+        }
       }
       if (RES == 1) { v4.x += rs4[it].x; v4.y += rs4[it].y; v4.z += rs4[it].z; v4.w += rs4[it].w; }
       if (RES == 2) {
         v4.x += __uint_as_float(rb2[it].x << 16); v4.y += __uint_as_float(rb2[it].x & 0xffff0000u);
         v4.z += __uint_as_float(rb2[it].y << 16); v4.w += __uint_as_float(rb2[it].y & 0xffff0000u);
       }
-      const long long off = static_cast<long long>(ri.x) + col;
-      if (p.out_f32 && ok) *reinterpret_cast<float4*>(p.out_f32 + off) = v4;
-      if (p.out_bf16 && ok) {
+      const long long off = static_cast<long long>(ri[it].x) + col;
+      if (out_f32 && ok) *reinterpret_cast<float4*>(out_f32 + off) = v4;
+      if (out_bf16 && ok) {
         __nv_bfloat162 lo = __floats2bfloat162_rn(v4.x, v4.y);
         __nv_bfloat162 hi = __floats2bfloat162_rn(v4.z, v4.w);
         uint2 o2;
         o2.x = *reinterpret_cast<uint32_t*>(&lo);
         o2.y = *reinterpret_cast<uint32_t*>(&hi);
-        *reinterpret_cast<uint2*>(p.out_bf16 + off) = o2;
+        *reinterpret_cast<uint2*>(out_bf16 + off) = o2;
       }
       if (STATS && ok) {
         s1[0] += v4.x; s1[1] += v4.y; s1[2] += v4.z; s1[3] += v4.w;
@@ -259,7 +322,6 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, uint8_t* 
   const int c_begin = ew >> 2;   // this warp owns chunks c_begin, c_begin + 4, ...
   const int r = q * 32 + lane;
   float* stage = reinterpret_cast<float*>(smem + S::kStageOffset) + ew * 512;
-  int2* rowinfo_base = reinterpret_cast<int2*>(smem + S::kRowOffset);
   const int mode = (p.res_f32 ? 1 : (p.res_bf16 ? 2 : 0)) * 2 + (p.rowvec ? 1 : 0);
   const int out_cols_t = (p.act == ACT_GEGLU) ? BN / 2 : BN;
   const int n_limit_t = (p.act == ACT_GEGLU) ? p.N / 2 : p.N;
@@ -270,27 +332,24 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, uint8_t* 
 #pragma unroll
     for (int e = 0; e < 4; ++e) { st1[k][e] = 0.f; st2[k][e] = 0.f; }
   int st_sample = -1, st_ntile = -1;
+  // row -> position inside the TMA box (tile independent)
+  int rr = r;
+  const int ix = rr % p.bw; rr /= p.bw;
+  const int iy = rr % p.bh; rr /= p.bh;
+  const int iz = rr % p.bd; rr /= p.bd;
+  const long long plane = static_cast<long long>(p.OW) * p.OH;
   int lt = 0;
   for (int item = tile_begin; item < tile_end; item += tile_step, ++lt) {
-    const int tile = item / p.ksplit, sp = item - tile * p.ksplit;
+    const TileCoord tc = decode_item(p, item);
+    const int tile = tc.tile, sp = tc.sp, n_tile = tc.n_tile;
     const int a = lt & 1;
     const uint32_t aph = (lt >> 1) & 1;
-    const int n_tile = tile % p.n_tiles;
-    int m = tile / p.n_tiles;
-    const int xb = m % p.nxb; m /= p.nxb;
-    const int yb = m % p.nyb; m /= p.nyb;
-    const int zb = m % p.nzb; m /= p.nzb;
-    int rr = r;
-    const int ix = rr % p.bw; rr /= p.bw;
-    const int iy = rr % p.bh; rr /= p.bh;
-    const int iz = rr % p.bd; rr /= p.bd;
-    const int x = xb * p.bw + ix, y = yb * p.bh + iy, z = zb * p.bd + iz, b = m * p.bb + rr;
+    const int x = tc.xb * p.bw + ix, y = tc.yb * p.bh + iy, z = tc.zb * p.bd + iz, b = tc.bblk * p.bb + rr;
     const bool valid = (x < p.W) && (y < p.H) && (z < p.D) && (b < p.B);
     const long long orow =
-        (((static_cast<long long>(b) * p.OD + (z * p.osz + p.opz)) * p.OH + (y * p.osy + p.opy)) * p.OW +
+        ((static_cast<long long>(b) * p.OD + (z * p.osz + p.opz)) * plane + (y * p.osy + p.opy) * p.OW +
          (x * p.osx + p.opx)) * p.ldo;
     const int bv = valid ? b : -1;
-    int2* rowinfo = rowinfo_base + ((lt & 1) * 4 + q) * 32;
     // sample of the warp's rows (fused GroupNorm statistics: the host guarantees one sample per warp there)
     const int warp_sample = __reduce_max_sync(0xffffffff, bv);
     if (STATS && (warp_sample != st_sample || n_tile != st_ntile)) {
@@ -301,11 +360,18 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, uint8_t* 
 
     mbar_wait(&tmem_full[a], aph);
     tc_fence_after();
-    // Row bookkeeping of this quarter, double-buffered by tile parity; the 4 warps of a quarter write identical values.
-    // Written only after the accumulator of this tile is full: by then every warp has released tile lt-2 (the MMA of
-    // this tile needed all 16 arrivals on its accumulator buffer), so nobody still reads this parity's slot.
-    rowinfo[lane] = make_int2(valid ? static_cast<int>(orow) : -1, bv);
-    __syncwarp();
+    KPROF(6, lt == 0 && warp == 2 && lane == 0);
+    // (output row offset or -1, sample) of the four rows this lane finishes in the coalesced phase: they belong to
+    // lanes it*8 + (lane>>2) of this warp
+    int2 ri[4];
+    {
+      const int my_off = valid ? static_cast<int>(orow) : -1;
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        ri[it].x = __shfl_sync(0xffffffff, my_off, it * 8 + (lane >> 2));
+        ri[it].y = __shfl_sync(0xffffffff, bv, it * 8 + (lane >> 2));
+      }
+    }
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * BN;
     bool run_epilogue = true;
     if (p.ksplit > 1) {
@@ -334,6 +400,7 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, uint8_t* 
       }
       last = __shfl_sync(0xffffffff, last, 0);
       run_epilogue = last != 0;
+      KPROF(7, lt == 0 && warp == 2 && lane == 0);
       if (run_epilogue) {
         __threadfence();
         for (int c = c_begin; c < acc_chunks; c += 4) {
@@ -356,19 +423,35 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, uint8_t* 
           tmem_st_32x16(taddr + c * kChunk, v);
         }
         tc_wait_st();
+        KPROF(8, lt == 0 && warp == 2 && lane == 0);
       }
     }
-    if (run_epilogue) switch (mode) {
-      case 0: epilogue_tile<BN, 0, false, NCH, STATS>(p, taddr, stage, lane, n_tile, rowinfo, c_begin, st1, st2); break;
-      case 1: epilogue_tile<BN, 0, true, NCH, STATS>(p, taddr, stage, lane, n_tile, rowinfo, c_begin, st1, st2); break;
-      case 2: epilogue_tile<BN, 1, false, NCH, STATS>(p, taddr, stage, lane, n_tile, rowinfo, c_begin, st1, st2); break;
-      case 3: epilogue_tile<BN, 1, true, NCH, STATS>(p, taddr, stage, lane, n_tile, rowinfo, c_begin, st1, st2); break;
-      case 4: epilogue_tile<BN, 2, false, NCH, STATS>(p, taddr, stage, lane, n_tile, rowinfo, c_begin, st1, st2); break;
-      default: epilogue_tile<BN, 2, true, NCH, STATS>(p, taddr, stage, lane, n_tile, rowinfo, c_begin, st1, st2); break;
+    if (run_epilogue) {
+      if (p.act == ACT_NONE) {
+        switch (mode) {
+          case 0: epilogue_tile<BN, 0, false, NCH, STATS, false>(p, taddr, stage, lane, n_tile, ri, c_begin, st1, st2); break;
+          case 1: epilogue_tile<BN, 0, true, NCH, STATS, false>(p, taddr, stage, lane, n_tile, ri, c_begin, st1, st2); break;
+          case 2: epilogue_tile<BN, 1, false, NCH, STATS, false>(p, taddr, stage, lane, n_tile, ri, c_begin, st1, st2); break;
+          case 3: epilogue_tile<BN, 1, true, NCH, STATS, false>(p, taddr, stage, lane, n_tile, ri, c_begin, st1, st2); break;
+          case 4: epilogue_tile<BN, 2, false, NCH, STATS, false>(p, taddr, stage, lane, n_tile, ri, c_begin, st1, st2); break;
+          default: epilogue_tile<BN, 2, true, NCH, STATS, false>(p, taddr, stage, lane, n_tile, ri, c_begin, st1, st2); break;
+        }
+      } else {
+        switch (mode) {
+          case 0: epilogue_tile<BN, 0, false, NCH, STATS, true>(p, taddr, stage, lane, n_tile, ri, c_begin, st1, st2); break;
+          case 1: epilogue_tile<BN, 0, true, NCH, STATS, true>(p, taddr, stage, lane, n_tile, ri, c_begin, st1, st2); break;
+          case 2: epilogue_tile<BN, 1, false, NCH, STATS, true>(p, taddr, stage, lane, n_tile, ri, c_begin, st1, st2); break;
+          case 3: epilogue_tile<BN, 1, true, NCH, STATS, true>(p, taddr, stage, lane, n_tile, ri, c_begin, st1, st2); break;
+          case 4: epilogue_tile<BN, 2, false, NCH, STATS, true>(p, taddr, stage, lane, n_tile, ri, c_begin, st1, st2); break;
+          default: epilogue_tile<BN, 2, true, NCH, STATS, true>(p, taddr, stage, lane, n_tile, ri, c_begin, st1, st2); break;
+        }
+      }
     }
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(&tmem_empty[a]);
+    KPROF(9, lt == 0 && warp == 2 && lane == 0);
+    KPROF(10, warp == 2 && lane == 0);
   }
   if (STATS && st_sample >= 0)
     flush_col_stats<NCH>(p, lane, st_sample, st_ntile * out_cols_t, n_limit_t, c_begin, st1, st2);
@@ -388,6 +471,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  KPROF(0, threadIdx.x == 0);
   constexpr uint32_t kTmemCols = (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
 
   if (warp == 0 && lane == 0) {
@@ -411,8 +495,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  KPROF(1, threadIdx.x == 0);
   // barriers, TMEM and descriptors are set up: everything above overlapped the predecessor kernel's tail
   pdl_grid_sync();
+  KPROF(2, threadIdx.x == 0);
 
   const int total_tiles = p.m_tiles * p.n_tiles * p.ksplit;  // work items: (tile, K split)
   const int kblocks = p.ntaps * p.kblocks_per_tap;
@@ -428,15 +514,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       int it = 0;
       for (int item = tile_begin; item < tile_end; item += tile_step) {
-        const int tile = item / p.ksplit, sp = item - tile * p.ksplit;
-        const int kb0 = (kblocks * sp) / p.ksplit, kb1 = (kblocks * (sp + 1)) / p.ksplit;
-        const int n_tile = tile % p.n_tiles;
-        int m = tile / p.n_tiles;
-        const int xb = m % p.nxb; m /= p.nxb;
-        const int yb = m % p.nyb; m /= p.nyb;
-        const int zb = m % p.nzb; m /= p.nzb;
-        const int x0 = xb * p.bw * p.isx, y0 = yb * p.bh * p.isy, z0 = zb * p.bd * p.isz, b0 = m * p.bb;
-        const int n0 = n_tile * BN;
+        const TileCoord tc = decode_item(p, item);
+        const int kb0 = fdiv(kblocks * tc.sp, p.fd_ksplit), kb1 = fdiv(kblocks * (tc.sp + 1), p.fd_ksplit);
+        const int x0 = tc.xb * p.bw * p.isx, y0 = tc.yb * p.bh * p.isy, z0 = tc.zb * p.bd * p.isz, b0 = tc.bblk * p.bb;
+        const int n0 = tc.n_tile * BN;
         int tap = kb0 / p.kblocks_per_tap, kc = kb0 - tap * p.kblocks_per_tap;
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % STAGES;
@@ -447,6 +528,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_expect_tx(&full_bar[s], S::kStageBytes);
           tma_load_5d(sa, &tmA, &full_bar[s], kc * kBlockK, x0 + p.tdx[tap], y0 + p.tdy[tap], z0 + p.tdz[tap], b0);
           tma_load_2d(sb, &tmB, &full_bar[s], kb * kBlockK, n0);
+          KPROF(3, it == 0);
           if (++kc == p.kblocks_per_tap) { kc = 0; ++tap; }
         }
       }
@@ -458,8 +540,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int it = 0;
       int lt = 0;
       for (int item = tile_begin; item < tile_end; item += tile_step, ++lt) {
-        const int sp = item % p.ksplit;
-        const int nkb = (kblocks * (sp + 1)) / p.ksplit - (kblocks * sp) / p.ksplit;
+        const int sp = item - fdiv(item, p.fd_ksplit) * p.ksplit;
+        const int nkb = fdiv(kblocks * (sp + 1), p.fd_ksplit) - fdiv(kblocks * sp, p.fd_ksplit);
         const int a = lt & 1;
         const uint32_t aph = (lt >> 1) & 1;
         mbar_wait(&tmem_empty[a], aph ^ 1);
@@ -470,6 +552,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
+          KPROF(4, it == 0);
+          KPROF(5, lt == 0 && kb == nkb - 1);
           const uint32_t sa = smem_u32(smem + s * S::kStageBytes);
           const uint32_t sb = sa + S::kABytes;
           const uint64_t da = make_sw128_kmajor_desc(sa);
@@ -496,9 +580,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
+  KPROF(11, threadIdx.x == 0);
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
+    KPROF(12, lane == 0);
   }
 }
 

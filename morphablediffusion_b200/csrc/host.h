@@ -33,6 +33,7 @@ void use_split_workspace_alt(bool on);
   } while (0)
 
 bool pdl_enabled();
+void prefer_max_smem(const void* kernel);  // once per kernel: pin the L1/shared split so kernel boundaries never reconfigure it
 
 // Launch with programmatic stream serialization: the kernel may start while its predecessor drains; every kernel
 // calls pdl_grid_sync() (griddepcontrol.wait) before touching memory.
@@ -45,6 +46,7 @@ inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
   cfg.attrs = attr; cfg.numAttrs = 1;
+  prefer_max_smem(reinterpret_cast<const void*>(kernel));
   cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
