@@ -163,6 +163,10 @@ MD_API int md_op_layer_norm(float* x, const float* gamma, const float* beta, voi
 /* CrossAttention.forward as self-attention (ldm/modules/attention.py:179-203): qkv bf16 [B][S][3*heads*dh] ->
  * out bf16 [B][S][heads*dh] */
 MD_API int md_op_self_attention(const void* qkv, void* out, int B, int S, int heads, int dh, void* stream);
+/* Same contract with the kernel chosen explicitly (parity / timing of the two implementations against each other):
+ * impl 0 = the library's own choice, 1 = mma.sync flash kernel, 2 = tcgen05/TMEM kernel (S % 128 == 0, dh <= 128). */
+MD_API int md_op_self_attention_impl(const void* qkv, void* out, int B, int S, int heads, int dh, int impl,
+                                     void* stream);
 /* DepthAttention.forward core (ldm/models/diffusion/attention.py:36-46), re-associated: K = W_k c and V = W_v c are
  * never materialised.  qp bf16 [T][HW][4*ctx] = per-head W_k^T q (softmax scale folded in); c1 bf16 [T][D][HW][ctx]
  * = proj_context conv output BEFORE GroupNorm; ss fp32 [T][ctx][2] = its GroupNorm scale/shift; beta fp32 [ctx];

@@ -159,7 +159,9 @@ for _f in ("md_embed_time", "md_create", "md_load_weights", "md_bind_sample", "m
 lib.md_op_group_norm.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _vp, _vp, _vp, C.c_int, _vp, _vp]
 lib.md_op_layer_norm.argtypes = [_vp, _vp, _vp, _vp, C.c_longlong, C.c_int, C.c_float, _vp]
 lib.md_op_self_attention.argtypes = [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp]
+lib.md_op_self_attention_impl.argtypes = [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp]
 lib.md_op_depth_attention.argtypes = [_vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp]
 lib.md_op_cfg_ddim.argtypes = [_vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_ulonglong, C.c_int, _vp]
-for _f in ("md_op_group_norm", "md_op_layer_norm", "md_op_self_attention", "md_op_depth_attention", "md_op_cfg_ddim"):
+for _f in ("md_op_group_norm", "md_op_layer_norm", "md_op_self_attention", "md_op_self_attention_impl", "md_op_depth_attention",
+           "md_op_cfg_ddim"):
     getattr(lib, _f).restype = C.c_int

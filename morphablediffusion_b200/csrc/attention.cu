@@ -8,6 +8,8 @@
 #include "ptx.cuh"
 #include "kernels.h"
 
+#include <stdlib.h>
+
 namespace md {
 
 __device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
@@ -253,6 +255,13 @@ static int self_attention_impl(const void* qkv, void* out, int B, int S, int hea
 }
 
 int launch_self_attention(const void* qkv, void* out, int B, int S, int heads, int dh, cudaStream_t st) {
+  // long sequences run on the tcgen05 kernel (attention_tc.cu); MD_ATT_MMA=1 keeps the mma.sync kernel for A/B timing
+  static const bool force_mma = getenv("MD_ATT_MMA") != nullptr;
+  if (!force_mma && attention_tc_supported(S, dh)) return launch_attention_tc(qkv, out, B, S, heads, dh, st);
+  return launch_self_attention_mma(qkv, out, B, S, heads, dh, st);
+}
+
+int launch_self_attention_mma(const void* qkv, void* out, int B, int S, int heads, int dh, cudaStream_t st) {
   if (dh % 8) return set_error("self_attention: head dim %d must be a multiple of 8", dh);
   const bool big = S >= 128;  // 8 warps x 16 queries per CTA when the sequence is long enough to fill them
   if (dh <= 48) return big ? self_attention_impl<48, 8>(qkv, out, B, S, heads, dh, st) : self_attention_impl<48, 4>(qkv, out, B, S, heads, dh, st);

@@ -24,6 +24,8 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
+void* tensor_map_encode_fn() { return reinterpret_cast<void*>(get_encode()); }
+
 // split-K workspace (process-wide, allocated on first use; kernels on one stream are ordered, so sharing is safe)
 static float* g_split_ws = nullptr;
 static size_t g_split_ws_bytes = 0;
@@ -239,11 +241,11 @@ int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
 }  // namespace md
 
 #ifdef MD_KPROF
-// Development builds only: phase time stamps of the last conv_gemm launch ([160 CTAs][16 slots], globaltimer ns).
+// Development builds only: phase time stamps of the last conv_gemm launch ([160 CTAs][32 slots], globaltimer ns).
 extern "C" __attribute__((visibility("default"))) int md_debug_kprof(unsigned long long* host_out, int clear) {
-  if (cudaMemcpyFromSymbol(host_out, md::g_kprof, sizeof(unsigned long long) * 160 * 16) != cudaSuccess) return -1;
+  if (cudaMemcpyFromSymbol(host_out, md::g_kprof, sizeof(unsigned long long) * 160 * 32) != cudaSuccess) return -1;
   if (clear) {
-    static unsigned long long zeros[160 * 16];
+    static unsigned long long zeros[160 * 32];
     cudaMemcpyToSymbol(md::g_kprof, zeros, sizeof(zeros));
   }
   return 0;

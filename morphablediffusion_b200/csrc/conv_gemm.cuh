@@ -16,11 +16,11 @@ namespace md {
 
 // Development-only phase stamps (build with -DMD_KPROF): globaltimer per CTA and phase, read back with md_debug_kprof.
 #ifdef MD_KPROF
-__device__ unsigned long long g_kprof[160 * 16];
+__device__ unsigned long long g_kprof[160 * 32];
 __device__ __forceinline__ void kprof(int slot) {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  if (blockIdx.x < 160) g_kprof[blockIdx.x * 16 + slot] = t;
+  if (blockIdx.x < 160) g_kprof[blockIdx.x * 32 + slot] = t;
 }
 #define KPROF(slot, cond) do { if (cond) kprof(slot); } while (0)
 #else
@@ -30,6 +30,7 @@ __device__ __forceinline__ void kprof(int slot) {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
 constexpr int kMaxTaps = 27;
+constexpr int kKprofTile = 2;  // tile whose steady-state phases the MD_KPROF build stamps
 
 
 // Division by a launch-time constant as multiply + shift (exact for n < 2^31): the per-tile coordinate arithmetic runs
@@ -106,18 +107,8 @@ __device__ __forceinline__ TileCoord decode_item(const ConvGemmParams& p, int it
   return t;
 }
 
-__device__ __forceinline__ float act_silu(float x) { return x / (1.f + __expf(-x)); }
-// exact-erf GELU (F.gelu default) with erf from Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7): 1 rcp + 1 exp + 6 fma
-__device__ __forceinline__ float act_gelu(float x) {
-  const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.f));
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  const float e = 1.f - poly * t * __expf(-z * z);   // erf(|x|/sqrt2)
-  return 0.5f * x * (1.f + copysignf(e, x));
-}
+__device__ __forceinline__ float act_silu(float x) { return silu_fast(x); }
+__device__ __forceinline__ float act_gelu(float x) { return gelu_fast(x); }
 
 constexpr int kEpiWarps = 16;   // 4 warps per TMEM lane quarter; each owns every 4th 16-column chunk of a tile
 constexpr int kChunk = 16;      // accumulator columns per epilogue chunk (tcgen05.ld 32x32b.x16)
@@ -188,7 +179,7 @@ __device__ __forceinline__ void flush_col_stats(const ConvGemmParams& p, int lan
 template <int BN, int RES, bool RV, int NCH, bool STATS, bool ACTV>
 __device__ __forceinline__ void epilogue_tile(const ConvGemmParams& p, uint32_t taddr, float* stage, int lane, int n_tile,
                                               const int2 (&ri)[4], int c_begin, float (&st1)[NCH][4],
-                                              float (&st2)[NCH][4]) {
+                                              float (&st2)[NCH][4], bool kp = false) {
   const int prow = lane >> 2;   // phase-2 row within a group of 8
   const int pchunk = lane & 3;  // phase-2 16-byte chunk within the 64-byte row
   const bool geglu = ACTV && (p.act == ACT_GEGLU);
@@ -210,6 +201,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvGemmParams& p, uint32_t 
     const int col = n_out0 + c * kChunk + pchunk * 4;
     const bool col_ok = col < n_limit;
     const int col_safe = col_ok ? col : 0;
+    KPROF(21, kp && ci == 0);
     // ---- phase 0: all global loads of this chunk in flight together (invalid rows read a safe address)
     float4 rv4[4];
     float4 rs4[4];
@@ -229,16 +221,22 @@ __device__ __forceinline__ void epilogue_tile(const ConvGemmParams& p, uint32_t 
     // ---- phase 1: accumulator chunk -> staging tile (16-byte chunk j of row `lane` lands at chunk j ^ ((lane>>1)&3))
     {
       uint32_t v[16];
-      tmem_ld_32x16(taddr + c * kChunk, v);
       if (geglu) {
-        uint32_t g[16];
-        tmem_ld_32x16(taddr + HALF + c * kChunk, g);
         const int nb = n_tile * BN + c * kChunk;  // packed-row index of the value half
-        tc_wait_ld();
+        float4 bv4[4], bg4[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float4 bv = bias ? __ldg(reinterpret_cast<const float4*>(bias + nb) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-          const float4 bg = bias ? __ldg(reinterpret_cast<const float4*>(bias + nb + HALF) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+          bv4[j] = bias ? __ldg(reinterpret_cast<const float4*>(bias + nb) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+          bg4[j] = bias ? __ldg(reinterpret_cast<const float4*>(bias + nb + HALF) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        tmem_ld_32x16(taddr + c * kChunk, v);
+        uint32_t g[16];
+        tmem_ld_32x16(taddr + HALF + c * kChunk, g);
+        tc_wait_ld();
+        KPROF(22, kp && ci == 0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 bv = bv4[j], bg = bg4[j];
           float4 o;
           o.x = (__uint_as_float(v[4 * j]) + bv.x) * act_gelu(__uint_as_float(g[4 * j]) + bg.x);
           o.y = (__uint_as_float(v[4 * j + 1]) + bv.y) * act_gelu(__uint_as_float(g[4 * j + 1]) + bg.y);
@@ -247,7 +245,9 @@ __device__ __forceinline__ void epilogue_tile(const ConvGemmParams& p, uint32_t 
           *reinterpret_cast<float4*>(st_wr + ((j ^ swl) << 2)) = o;
         }
       } else {
+        tmem_ld_32x16(taddr + c * kChunk, v);
         tc_wait_ld();
+        KPROF(22, kp && ci == 0);
         if (scaled) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * p.out_scale);
@@ -258,6 +258,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvGemmParams& p, uint32_t 
       }
     }
     __syncwarp();
+    KPROF(23, kp && ci == 0);
     // ---- phase 2: coalesced finish; all four staged rows are fetched before the arithmetic
     float4 t4[4];
 #pragma unroll
@@ -308,7 +309,14 @@ __device__ __forceinline__ void epilogue_tile(const ConvGemmParams& p, uint32_t 
       }
     }
     __syncwarp();
+    KPROF(24, kp && ci == 0);
+    KPROF(25, kp && ci == 1);
   }
+}
+
+// Pulls `bytes` (multiple of 16) at a 16-byte aligned global address into L2 without occupying registers.
+__device__ __forceinline__ void prefetch_l2_bulk(const void* gptr, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
 }
 
 // Epilogue warps: loop over this CTA's work items (same schedule as the producer / MMA warps).
@@ -338,8 +346,28 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, uint8_t* 
   const int iy = rr % p.bh; rr /= p.bh;
   const int iz = rr % p.bd; rr /= p.bd;
   const long long plane = static_cast<long long>(p.OW) * p.OH;
+  // The residual rows of a tile are read chunk by chunk in the coalesced phase, each read a full memory round trip
+  // on the warp's critical path: one tile ahead, the first warp of every lane quarter pulls its 32 residual rows
+  // (this tile's column range) into L2 so those reads become L2 hits.
+  const bool do_prefetch = (c_begin == 0) && (p.ksplit == 1) && (p.res_f32 != nullptr || p.res_bf16 != nullptr);
+  auto prefetch_residual = [&](int item) {
+    if (!do_prefetch || item >= tile_end) return;
+    const TileCoord t = decode_item(p, item);
+    const int x = t.xb * p.bw + ix, y = t.yb * p.bh + iy, z = t.zb * p.bd + iz, b = t.bblk * p.bb + rr;
+    const int n0 = t.n_tile * out_cols_t;
+    const int cols = min(out_cols_t, n_limit_t - n0);
+    if ((x < p.W) && (y < p.H) && (z < p.D) && (b < p.B) && cols > 0) {
+      const long long off =
+          ((static_cast<long long>(b) * p.OD + (z * p.osz + p.opz)) * plane + (y * p.osy + p.opy) * p.OW +
+           (x * p.osx + p.opx)) * p.ldo + n0;
+      if (p.res_f32) prefetch_l2_bulk(p.res_f32 + off, static_cast<uint32_t>(cols) * 4u);
+      else prefetch_l2_bulk(p.res_bf16 + off, static_cast<uint32_t>(cols) * 2u);
+    }
+  };
+  prefetch_residual(tile_begin);
   int lt = 0;
   for (int item = tile_begin; item < tile_end; item += tile_step, ++lt) {
+    prefetch_residual(item + tile_step);
     const TileCoord tc = decode_item(p, item);
     const int tile = tc.tile, sp = tc.sp, n_tile = tc.n_tile;
     const int a = lt & 1;
@@ -358,9 +386,11 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, uint8_t* 
     }
     __syncwarp();
 
+    KPROF(16, lt == kKprofTile && warp == 2 && lane == 0);
     mbar_wait(&tmem_full[a], aph);
     tc_fence_after();
     KPROF(6, lt == 0 && warp == 2 && lane == 0);
+    KPROF(17, lt == kKprofTile && warp == 2 && lane == 0);
     // (output row offset or -1, sample) of the four rows this lane finishes in the coalesced phase: they belong to
     // lanes it*8 + (lane>>2) of this warp
     int2 ri[4];
@@ -426,24 +456,29 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, uint8_t* 
         KPROF(8, lt == 0 && warp == 2 && lane == 0);
       }
     }
+#ifdef MD_KPROF
+    const bool kpf = lt == kKprofTile && warp == 2 && lane == 0;
+#else
+    constexpr bool kpf = false;
+#endif
     if (run_epilogue) {
       if (p.act == ACT_NONE) {
         switch (mode) {
-          case 0: epilogue_tile<BN, 0, false, NCH, STATS, false>(p, taddr, stage, lane, n_tile, ri, c_begin, st1, st2); break;
-          case 1: epilogue_tile<BN, 0, true, NCH, STATS, false>(p, taddr, stage, lane, n_tile, ri, c_begin, st1, st2); break;
-          case 2: epilogue_tile<BN, 1, false, NCH, STATS, false>(p, taddr, stage, lane, n_tile, ri, c_begin, st1, st2); break;
-          case 3: epilogue_tile<BN, 1, true, NCH, STATS, false>(p, taddr, stage, lane, n_tile, ri, c_begin, st1, st2); break;
-          case 4: epilogue_tile<BN, 2, false, NCH, STATS, false>(p, taddr, stage, lane, n_tile, ri, c_begin, st1, st2); break;
-          default: epilogue_tile<BN, 2, true, NCH, STATS, false>(p, taddr, stage, lane, n_tile, ri, c_begin, st1, st2); break;
+          case 0: epilogue_tile<BN, 0, false, NCH, STATS, false>(p, taddr, stage, lane, n_tile, ri, c_begin, st1, st2, kpf); break;
+          case 1: epilogue_tile<BN, 0, true, NCH, STATS, false>(p, taddr, stage, lane, n_tile, ri, c_begin, st1, st2, kpf); break;
+          case 2: epilogue_tile<BN, 1, false, NCH, STATS, false>(p, taddr, stage, lane, n_tile, ri, c_begin, st1, st2, kpf); break;
+          case 3: epilogue_tile<BN, 1, true, NCH, STATS, false>(p, taddr, stage, lane, n_tile, ri, c_begin, st1, st2, kpf); break;
+          case 4: epilogue_tile<BN, 2, false, NCH, STATS, false>(p, taddr, stage, lane, n_tile, ri, c_begin, st1, st2, kpf); break;
+          default: epilogue_tile<BN, 2, true, NCH, STATS, false>(p, taddr, stage, lane, n_tile, ri, c_begin, st1, st2, kpf); break;
         }
       } else {
         switch (mode) {
-          case 0: epilogue_tile<BN, 0, false, NCH, STATS, true>(p, taddr, stage, lane, n_tile, ri, c_begin, st1, st2); break;
-          case 1: epilogue_tile<BN, 0, true, NCH, STATS, true>(p, taddr, stage, lane, n_tile, ri, c_begin, st1, st2); break;
-          case 2: epilogue_tile<BN, 1, false, NCH, STATS, true>(p, taddr, stage, lane, n_tile, ri, c_begin, st1, st2); break;
-          case 3: epilogue_tile<BN, 1, true, NCH, STATS, true>(p, taddr, stage, lane, n_tile, ri, c_begin, st1, st2); break;
-          case 4: epilogue_tile<BN, 2, false, NCH, STATS, true>(p, taddr, stage, lane, n_tile, ri, c_begin, st1, st2); break;
-          default: epilogue_tile<BN, 2, true, NCH, STATS, true>(p, taddr, stage, lane, n_tile, ri, c_begin, st1, st2); break;
+          case 0: epilogue_tile<BN, 0, false, NCH, STATS, true>(p, taddr, stage, lane, n_tile, ri, c_begin, st1, st2, kpf); break;
+          case 1: epilogue_tile<BN, 0, true, NCH, STATS, true>(p, taddr, stage, lane, n_tile, ri, c_begin, st1, st2, kpf); break;
+          case 2: epilogue_tile<BN, 1, false, NCH, STATS, true>(p, taddr, stage, lane, n_tile, ri, c_begin, st1, st2, kpf); break;
+          case 3: epilogue_tile<BN, 1, true, NCH, STATS, true>(p, taddr, stage, lane, n_tile, ri, c_begin, st1, st2, kpf); break;
+          case 4: epilogue_tile<BN, 2, false, NCH, STATS, true>(p, taddr, stage, lane, n_tile, ri, c_begin, st1, st2, kpf); break;
+          default: epilogue_tile<BN, 2, true, NCH, STATS, true>(p, taddr, stage, lane, n_tile, ri, c_begin, st1, st2, kpf); break;
         }
       }
     }
@@ -451,6 +486,7 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, uint8_t* 
     __syncwarp();
     if (lane == 0) mbar_arrive(&tmem_empty[a]);
     KPROF(9, lt == 0 && warp == 2 && lane == 0);
+    KPROF(18, lt == kKprofTile && warp == 2 && lane == 0);
     KPROF(10, warp == 2 && lane == 0);
   }
   if (STATS && st_sample >= 0)
@@ -513,7 +549,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ===================== TMA producer =====================
     if (lane == 0) {
       int it = 0;
-      for (int item = tile_begin; item < tile_end; item += tile_step) {
+      int plt = 0;
+      for (int item = tile_begin; item < tile_end; item += tile_step, ++plt) {
         const TileCoord tc = decode_item(p, item);
         const int kb0 = fdiv(kblocks * tc.sp, p.fd_ksplit), kb1 = fdiv(kblocks * (tc.sp + 1), p.fd_ksplit);
         const int x0 = tc.xb * p.bw * p.isx, y0 = tc.yb * p.bh * p.isy, z0 = tc.zb * p.bd * p.isz, b0 = tc.bblk * p.bb;
@@ -523,6 +560,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
+          KPROF(19, plt == kKprofTile && kb == kb0);
+          KPROF(20, plt == kKprofTile && kb == kb1 - 1);
           uint8_t* sa = smem + s * S::kStageBytes;
           uint8_t* sb = sa + S::kABytes;
           mbar_expect_tx(&full_bar[s], S::kStageBytes);
@@ -546,6 +585,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const uint32_t aph = (lt >> 1) & 1;
         mbar_wait(&tmem_empty[a], aph ^ 1);
         tc_fence_after();
+        KPROF(13, lt == kKprofTile);
         const uint32_t d_tmem = tmem_base + a * BN;
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % STAGES;
@@ -554,6 +594,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           tc_fence_after();
           KPROF(4, it == 0);
           KPROF(5, lt == 0 && kb == nkb - 1);
+          KPROF(14, lt == kKprofTile && kb == 0);
           const uint32_t sa = smem_u32(smem + s * S::kStageBytes);
           const uint32_t sb = sa + S::kABytes;
           const uint64_t da = make_sw128_kmajor_desc(sa);
@@ -566,6 +607,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           tc_commit(&empty_bar[s]);
         }
         tc_commit(&tmem_full[a]);
+        KPROF(15, lt == kKprofTile);
       }
     }
   } else {

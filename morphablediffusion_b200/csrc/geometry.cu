@@ -157,7 +157,7 @@ struct EncWeights {
   const float* fgn_w; const float* fgn_b; const float* fc_w; const float* fc_b;
 };
 
-__device__ __forceinline__ float silu_g(float x) { return x / (1.f + __expf(-x)); }
+__device__ __forceinline__ float silu_g(float x) { return silu_fast(x); }
 
 __global__ void __launch_bounds__(1024, 1)
 target_encoder_kernel(const float* __restrict__ x, const float* __restrict__ t_embed, const float* __restrict__ v_embed,

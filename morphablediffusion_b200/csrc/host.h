@@ -17,6 +17,7 @@ void count_launch(int n = 1);
 int num_sms();
 
 int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream);
+void* tensor_map_encode_fn();  // cuTensorMapEncodeTiled resolved through the runtime (null without a driver)
 void set_split_workspace_alt(float* ws, size_t bytes, int* cnt, size_t ints);
 void use_split_workspace_alt(bool on);
 

@@ -50,6 +50,10 @@ int launch_cfg_ddim(const float* eps, float* x, float* eps_out, const float* noi
 // ---- attention.cu
 // Self-attention over tokens: qkv bf16 [B][S][3*C] (q | k | v, head h at columns h*dh), out bf16 [B][S][C].
 int launch_self_attention(const void* qkv, void* out, int B, int S, int heads, int dh, cudaStream_t st);
+int launch_self_attention_mma(const void* qkv, void* out, int B, int S, int heads, int dh, cudaStream_t st);
+// ---- attention_tc.cu: the same contract on tcgen05 tensor cores (S a multiple of 128, dh <= 128)
+bool attention_tc_supported(int S, int dh);
+int launch_attention_tc(const void* qkv, void* out, int B, int S, int heads, int dh, cudaStream_t st);
 // Re-associated depth attention (see attention.cu): qp bf16 [T][HW][4*ctx], c1 bf16 [T][D][HW][ctx] (pre-norm),
 // ss fp32 [T][ctx][2] GroupNorm scale/shift, beta fp32 [ctx]; cbar bf16 [B][HW][4*ctx] (samples >= T: zero volume).
 int launch_depth_attention(const void* qp, const void* c1, const float* ss, const float* beta, void* cbar, int T, int B,

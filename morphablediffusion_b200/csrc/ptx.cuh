@@ -23,6 +23,35 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// ---------------------------------------------------------------- branch-free transcendental helpers
+// One MUFU each, flush-to-zero, no range fix-up code: the IEEE division / __frcp_rn / __expf forms compile to
+// convergence-barrier-wrapped slow paths that serialise the otherwise independent per-element chains of an epilogue.
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// x * sigmoid(x); exact limits: x -> -inf gives -0, x -> +inf gives x
+__device__ __forceinline__ float silu_fast(float x) {
+  return x * rcp_approx(1.f + ex2_approx(-1.4426950408889634f * x));
+}
+// exact-erf GELU (F.gelu default) with erf from Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7 + 2 MUFU ulps)
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = rcp_approx(fmaf(0.3275911f, z, 1.f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float e = fmaf(-poly * t, ex2_approx(-1.4426950408889634f * z * z), 1.f);   // erf(|x|/sqrt2)
+  return 0.5f * x * (1.f + copysignf(e, x));
+}
+
 // ---------------------------------------------------------------- programmatic dependent launch
 // Every kernel of the library starts with this: wait until the predecessor grid's writes are visible, then allow the
 // successor grid to begin launching (its own prologue overlaps our execution; it waits here in turn).
@@ -81,6 +110,12 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* m, uin
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
                                             int c3, int c4) {
   asm volatile(
@@ -135,6 +170,19 @@ __device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
   return d;
 }
 
+// MN-major (the operand's M/N index is the contiguous one), 128-byte-swizzled tile: one row of 128 B per K index holds
+// 64 consecutive M/N elements; 8-K-row groups are 1024 B apart (stride offset), further 64-element M/N blocks are
+// `mn_block_bytes` apart (leading offset).  Canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units.
+__device__ __forceinline__ uint64_t make_sw128_mnmajor_desc(uint32_t smem_addr, uint32_t mn_block_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>((mn_block_bytes >> 4) & 0x3FFF) << 16;  // leading byte offset
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;                       // stride byte offset
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
 // Instruction descriptor for kind::f16, bf16 x bf16 -> fp32, both operands K-major.
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
   return (1u << 4)       // c_format = F32
@@ -143,6 +191,12 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
          | (0u << 15)    // a K-major
          | (0u << 16)    // b K-major
          | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+
+// Same with a run-time N and an MN-major (transposed) B operand.
+__host__ __device__ constexpr uint32_t make_idesc_bf16_ex(int M, int N, int b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (0u << 15) | (static_cast<uint32_t>(b_mn_major ? 1 : 0) << 16) |
+         (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
 
 // 32 lanes x 32 columns of 32-bit: thread t of the warp receives TMEM lane (base_lane + t), 32 consecutive columns.

@@ -531,6 +531,13 @@ int md_op_self_attention(const void* qkv, void* out, int B, int S, int heads, in
   return launch_self_attention(qkv, out, B, S, heads, dh, static_cast<cudaStream_t>(stream));
 }
 
+int md_op_self_attention_impl(const void* qkv, void* out, int B, int S, int heads, int dh, int impl, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (impl == 1) return launch_self_attention_mma(qkv, out, B, S, heads, dh, st);
+  if (impl == 2) return launch_attention_tc(qkv, out, B, S, heads, dh, st);
+  return launch_self_attention(qkv, out, B, S, heads, dh, st);
+}
+
 int md_op_depth_attention(const void* qp, const void* c1, const float* ss, const float* beta, void* cbar, int T, int B,
                           int D, int HW, int ctx, void* stream) {
   return launch_depth_attention(qp, c1, ss, beta, cbar, T, B, D, HW, ctx, static_cast<cudaStream_t>(stream));
