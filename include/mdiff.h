@@ -35,6 +35,8 @@ MD_API void md_reset_launch_count(void);
  *   Wt  : bf16 packed weights [N][ntaps*Cin] (K-major; tap-major then channel)
  *   out : row-major [rows][ldo]; row = ((b*OD + z*os+op)*OH + y*os+op)*OW + x*os+op
  */
+/* MD_ACT_GEGLU (GEGLU, ldm/modules/attention.py:42-44): Wt / bias rows are packed per tile of 256 rows = 128 value rows
+ * followed by their 128 gate rows (N = 2*inner, a multiple of 256); the output [rows][N/2] is value * gelu(gate), bf16. */
 enum { MD_ACT_NONE = 0, MD_ACT_SILU = 1, MD_ACT_RELU = 2, MD_ACT_GEGLU = 3, MD_ACT_GELU = 4 };
 
 typedef struct md_conv_gemm_args {

@@ -275,118 +275,156 @@ int launch_self_attention_mma(const void* qkv, void* out, int B, int S, int head
 //   sim[h][d] = q_h . (W_k,h c_d) = (W_k,h^T q_h) . c_d =: qp_h . c_d        (qp comes from one GEMM, scale folded in)
 //   out       = W_out concat_h( W_v,h sum_d attn[h][d] c_d ) = W_ov . cbar     (second GEMM on cbar = sum_d attn c_d)
 // with c = ReLU(GroupNorm(proj_context(ctx))) applied on the fly from the pre-norm tensor c1 and its per-(sample,
-// channel) scale/shift.  One warp per (sample, pixel); lane owns CPL = ctx/32 contiguous context channels; a single
-// pass over the D depth samples with an online softmax per head.  Samples b >= T have an all-zero frustum volume
+// channel) scale/shift.  A single pass over the D depth samples with an online softmax per head.  Samples b >= T have an all-zero frustum volume
 // (the CFG-unconditional half): c == ReLU(beta) for every depth, attention is uniform and cbar = ReLU(beta).
 //   qp   bf16 [T][HW][4*ctx]      c1 bf16 [T][D][HW][ctx]      ss fp32 [T][ctx][2]      beta fp32 [ctx]
 //   cbar bf16 [B][HW][4*ctx]
-template <int CPL>
-__global__ void depth_attention_kernel(const __nv_bfloat16* __restrict__ qp, const __nv_bfloat16* __restrict__ c1,
-                                       const float* __restrict__ ss, const float* __restrict__ beta,
-                                       __nv_bfloat16* __restrict__ cbar, int T, int B, int D, int HW) {
+// Thread mapping: TPP = ctx/16 lanes per (sample, pixel), each owning 16 contiguous context channels; a warp covers
+// 32/TPP consecutive pixels (one 16-byte-vectorised, fully coalesced row segment per depth sample).  Per depth sample a
+// lane spends 16 FMAs per head on the score and 16 on the accumulator; the partial scores meet with log2(TPP) shuffle
+// steps per head.  The exponent offset is lazy (moves only when the running maximum grew by more than 2^8), so the
+// accumulator rescale is off the common path.
+template <int TPP>
+__global__ void __launch_bounds__(128)
+depth_attention_kernel(const __nv_bfloat16* __restrict__ qp, const __nv_bfloat16* __restrict__ c1,
+                       const float* __restrict__ ss, const float* __restrict__ beta, __nv_bfloat16* __restrict__ cbar,
+                       int T, int B, int D, int HW) {
   pdl_grid_sync();
-  constexpr int ctx = CPL * 32;
+  constexpr int ctx = TPP * 16;
+  constexpr int PPW = 32 / TPP;  // pixels per warp
   const int lane = threadIdx.x & 31;
+  const int sub = lane % TPP, pw = lane / TPP;
   const size_t wid = (blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x) >> 5;
-  if (wid >= static_cast<size_t>(B) * HW) return;
-  const int b = static_cast<int>(wid / HW);
-  const int pix = static_cast<int>(wid % HW);
-  const int j0 = lane * CPL;
-  __nv_bfloat16* op = cbar + wid * (4 * ctx) + j0;
+  const size_t gp = wid * PPW + pw;  // global pixel index b*HW + pix; HW is a multiple of PPW: one sample per warp
+  if (gp >= static_cast<size_t>(B) * HW) return;
+  const int b = static_cast<int>(gp / HW);
+  const int pix = static_cast<int>(gp % HW);
+  const int j0 = sub * 16;
+  __nv_bfloat16* op = cbar + gp * (4 * ctx) + j0;
   if (b >= T) {
+    uint32_t w[8];
 #pragma unroll
-    for (int e = 0; e < CPL; e += 2) {
-      const __nv_bfloat162 v = __floats2bfloat162_rn(fmaxf(beta[j0 + e], 0.f), fmaxf(beta[j0 + e + 1], 0.f));
+    for (int e = 0; e < 16; e += 2) w[e / 2] = pack_bf16(fmaxf(beta[j0 + e], 0.f), fmaxf(beta[j0 + e + 1], 0.f));
 #pragma unroll
-      for (int h = 0; h < 4; ++h) *reinterpret_cast<__nv_bfloat162*>(op + h * ctx + e) = v;
+    for (int h = 0; h < 4; ++h) {
+      *reinterpret_cast<uint4*>(op + h * ctx) = make_uint4(w[0], w[1], w[2], w[3]);
+      *reinterpret_cast<uint4*>(op + h * ctx + 8) = make_uint4(w[4], w[5], w[6], w[7]);
     }
     return;
   }
-  float sc[CPL], sh[CPL], q[4][CPL], acc[4][CPL];
+  float sc[16], sh[16], q[4][16], acc[4][16];
+  {
+    const float4* sp = reinterpret_cast<const float4*>(ss + (static_cast<size_t>(b) * ctx + j0) * 2);
 #pragma unroll
-  for (int e = 0; e < CPL; ++e) {
-    sc[e] = ss[(static_cast<size_t>(b) * ctx + j0 + e) * 2];
-    sh[e] = ss[(static_cast<size_t>(b) * ctx + j0 + e) * 2 + 1];
-  }
-  const __nv_bfloat16* qb = qp + wid * (4 * ctx) + j0;
-#pragma unroll
-  for (int h = 0; h < 4; ++h)
-#pragma unroll
-    for (int e = 0; e < CPL; e += 2) {
-      const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(qb + h * ctx + e);
-      q[h][e] = __low2float(v); q[h][e + 1] = __high2float(v);
-      acc[h][e] = 0.f; acc[h][e + 1] = 0.f;
+    for (int e = 0; e < 16; e += 2) {
+      const float4 v = sp[e / 2];
+      sc[e] = v.x; sh[e] = v.y; sc[e + 1] = v.z; sh[e + 1] = v.w;
     }
+  }
+  const __nv_bfloat16* qb = qp + gp * (4 * ctx) + j0;
+#pragma unroll
+  for (int h = 0; h < 4; ++h) {
+    const uint4 a = *reinterpret_cast<const uint4*>(qb + h * ctx);
+    const uint4 c = *reinterpret_cast<const uint4*>(qb + h * ctx + 8);
+    const uint32_t w[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {  // scores in the log2 domain: fold log2(e) into the query
+      q[h][2 * e] = __uint_as_float(w[e] << 16) * 1.4426950408889634f;
+      q[h][2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u) * 1.4426950408889634f;
+      acc[h][2 * e] = 0.f; acc[h][2 * e + 1] = 0.f;
+    }
+  }
   float m[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, l[4] = {0.f, 0.f, 0.f, 0.f};
   const __nv_bfloat16* cp = c1 + (static_cast<size_t>(b) * D * HW + pix) * ctx + j0;
   const size_t dstride = static_cast<size_t>(HW) * ctx;
-  // D is a multiple of 6 at every level (48 / 24 / 12 / 6): fetch 6 depth samples at a time so that their loads are in
-  // flight together, then fold them into the online softmax one by one
-  constexpr int DB = 6;
+  // depth samples are fetched three at a time, one batch ahead of the arithmetic (D is a multiple of 6 at every level)
+  constexpr int DB = 3;
+  uint4 nxt[DB][2];
+#pragma unroll
+  for (int dd = 0; dd < DB; ++dd) {
+    const int d = min(dd, D - 1);
+    nxt[dd][0] = *reinterpret_cast<const uint4*>(cp + d * dstride);
+    nxt[dd][1] = *reinterpret_cast<const uint4*>(cp + d * dstride + 8);
+  }
   for (int d0 = 0; d0 < D; d0 += DB) {
-    __nv_bfloat162 raw[DB][CPL / 2];
+    uint4 cur[DB][2];
 #pragma unroll
-    for (int dd = 0; dd < DB; ++dd) {
-      const int d = min(d0 + dd, D - 1);
+    for (int dd = 0; dd < DB; ++dd) { cur[dd][0] = nxt[dd][0]; cur[dd][1] = nxt[dd][1]; }
+    if (d0 + DB < D) {
 #pragma unroll
-      for (int e = 0; e < CPL; e += 2) raw[dd][e / 2] = *reinterpret_cast<const __nv_bfloat162*>(cp + d * dstride + e);
+      for (int dd = 0; dd < DB; ++dd) {
+        const int d = min(d0 + DB + dd, D - 1);
+        nxt[dd][0] = *reinterpret_cast<const uint4*>(cp + d * dstride);
+        nxt[dd][1] = *reinterpret_cast<const uint4*>(cp + d * dstride + 8);
+      }
     }
 #pragma unroll
     for (int dd = 0; dd < DB; ++dd) {
       if (d0 + dd >= D) break;
-      float c[CPL];
+      const uint32_t w[8] = {cur[dd][0].x, cur[dd][0].y, cur[dd][0].z, cur[dd][0].w,
+                             cur[dd][1].x, cur[dd][1].y, cur[dd][1].z, cur[dd][1].w};
+      float c[16];
 #pragma unroll
-      for (int e = 0; e < CPL; e += 2) {
-        c[e] = fmaxf(__low2float(raw[dd][e / 2]) * sc[e] + sh[e], 0.f);
-        c[e + 1] = fmaxf(__high2float(raw[dd][e / 2]) * sc[e + 1] + sh[e + 1], 0.f);
+      for (int e = 0; e < 8; ++e) {
+        c[2 * e] = fmaxf(fmaf(__uint_as_float(w[e] << 16), sc[2 * e], sh[2 * e]), 0.f);
+        c[2 * e + 1] = fmaxf(fmaf(__uint_as_float(w[e] & 0xffff0000u), sc[2 * e + 1], sh[2 * e + 1]), 0.f);
       }
       float s[4];
 #pragma unroll
       for (int h = 0; h < 4; ++h) {
-        float a = 0.f;
+        float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-        for (int e = 0; e < CPL; ++e) a += q[h][e] * c[e];
-        s[h] = a;
+        for (int e = 0; e < 16; e += 2) { a0 = fmaf(q[h][e], c[e], a0); a1 = fmaf(q[h][e + 1], c[e + 1], a1); }
+        s[h] = a0 + a1;
       }
 #pragma unroll
-      for (int o = 16; o; o >>= 1) {
+      for (int o = TPP / 2; o; o >>= 1) {
 #pragma unroll
         for (int h = 0; h < 4; ++h) s[h] += __shfl_xor_sync(0xffffffff, s[h], o);
       }
 #pragma unroll
       for (int h = 0; h < 4; ++h) {
-        const float mn = fmaxf(m[h], s[h]);
-        const float corr = __expf(m[h] - mn);
-        const float pe = __expf(s[h] - mn);
-        m[h] = mn;
-        l[h] = l[h] * corr + pe;
+        if (s[h] > m[h] + 8.f) {  // also the first sample (m = -inf): corr = 0 clears the (already zero) state
+          const float corr = ex2_approx(m[h] - s[h]);
+          m[h] = s[h];
+          l[h] *= corr;
 #pragma unroll
-        for (int e = 0; e < CPL; ++e) acc[h][e] = acc[h][e] * corr + pe * c[e];
+          for (int e = 0; e < 16; ++e) acc[h][e] *= corr;
+        }
+        const float pe = ex2_approx(s[h] - m[h]);
+        l[h] += pe;
+#pragma unroll
+        for (int e = 0; e < 16; ++e) acc[h][e] = fmaf(pe, c[e], acc[h][e]);
       }
     }
   }
 #pragma unroll
   for (int h = 0; h < 4; ++h) {
     const float inv = 1.f / l[h];
+    uint32_t w[8];
 #pragma unroll
-    for (int e = 0; e < CPL; e += 2)
-      *reinterpret_cast<__nv_bfloat162*>(op + h * ctx + e) = __floats2bfloat162_rn(acc[h][e] * inv, acc[h][e + 1] * inv);
+    for (int e = 0; e < 8; ++e) w[e] = pack_bf16(acc[h][2 * e] * inv, acc[h][2 * e + 1] * inv);
+    *reinterpret_cast<uint4*>(op + h * ctx) = make_uint4(w[0], w[1], w[2], w[3]);
+    *reinterpret_cast<uint4*>(op + h * ctx + 8) = make_uint4(w[4], w[5], w[6], w[7]);
   }
 }
 
 int launch_depth_attention(const void* qp, const void* c1, const float* ss, const float* beta, void* cbar, int T, int B,
                            int D, int HW, int ctx, cudaStream_t st) {
-  const size_t warps = static_cast<size_t>(B) * HW;
+  if (ctx != 64 && ctx != 128 && ctx != 256 && ctx != 512)
+    return set_error("depth_attention: context dim %d unsupported (64/128/256/512)", ctx);
+  const int ppw = 32 / (ctx / 16);
+  if (HW % ppw) return set_error("depth_attention: %d pixels per sample is not a multiple of %d", HW, ppw);
+  const size_t warps = (static_cast<size_t>(B) * HW + ppw - 1) / ppw;
   const unsigned blocks = static_cast<unsigned>((warps * 32 + 127) / 128);
   const __nv_bfloat16* qq = static_cast<const __nv_bfloat16*>(qp);
   const __nv_bfloat16* cc = static_cast<const __nv_bfloat16*>(c1);
   __nv_bfloat16* oo = static_cast<__nv_bfloat16*>(cbar);
   switch (ctx) {
-    case 64: launch_pdl(depth_attention_kernel<2>, dim3(blocks), dim3(128), 0, st, qq, cc, ss, beta, oo, T, B, D, HW); break;
-    case 128: launch_pdl(depth_attention_kernel<4>, dim3(blocks), dim3(128), 0, st, qq, cc, ss, beta, oo, T, B, D, HW); break;
-    case 256: launch_pdl(depth_attention_kernel<8>, dim3(blocks), dim3(128), 0, st, qq, cc, ss, beta, oo, T, B, D, HW); break;
-    case 512: launch_pdl(depth_attention_kernel<16>, dim3(blocks), dim3(128), 0, st, qq, cc, ss, beta, oo, T, B, D, HW); break;
-    default: return set_error("depth_attention: context dim %d unsupported (64/128/256/512)", ctx);
+    case 64: launch_pdl(depth_attention_kernel<4>, dim3(blocks), dim3(128), 0, st, qq, cc, ss, beta, oo, T, B, D, HW); break;
+    case 128: launch_pdl(depth_attention_kernel<8>, dim3(blocks), dim3(128), 0, st, qq, cc, ss, beta, oo, T, B, D, HW); break;
+    case 256: launch_pdl(depth_attention_kernel<16>, dim3(blocks), dim3(128), 0, st, qq, cc, ss, beta, oo, T, B, D, HW); break;
+    default: launch_pdl(depth_attention_kernel<32>, dim3(blocks), dim3(128), 0, st, qq, cc, ss, beta, oo, T, B, D, HW); break;
   }
   return check_launch("depth_attention");
 }

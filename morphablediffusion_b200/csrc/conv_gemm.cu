@@ -1,6 +1,5 @@
 // Host launcher for the tcgen05 implicit-GEMM kernel: builds the TMA tensor maps and picks the tile shape.
-#include "conv_gemm.cuh"
-#include "host.h"
+#include "conv_gemm_launch.cuh"
 
 #include <mutex>
 #include <stdio.h>
@@ -24,6 +23,9 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
+#ifdef MD_KPROF
+extern unsigned long long* g_kprof_buf;
+#endif
 void* tensor_map_encode_fn() { return reinterpret_cast<void*>(get_encode()); }
 
 // split-K workspace (process-wide, allocated on first use; kernels on one stream are ordered, so sharing is safe)
@@ -61,24 +63,6 @@ static int pow2_floor(int v) {
   int p = 1;
   while (p * 2 <= v) p *= 2;
   return p;
-}
-
-template <int BN, int STAGES>
-static int launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p, int grid,
-                       cudaStream_t stream) {
-  using S = ConvGemmSmem<BN, STAGES>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         S::kTotal);
-    if (e != cudaSuccess) return set_error("cudaFuncSetAttribute(conv_gemm): %s", cudaGetErrorString(e));
-    attr_set = true;
-  }
-  launch_pdl(conv_gemm_kernel<BN, STAGES>, dim3(grid), dim3(64 + 32 * kEpiWarps), S::kTotal, stream, tmA, tmB, p);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return set_error("conv_gemm launch: %s", cudaGetErrorString(e));
-  count_launch();
-  return 0;
 }
 
 int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
@@ -148,10 +132,16 @@ int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
   int BN = a.BN;
   if (BN == 0) {
     if (a.act == ACT_GEGLU) {
-      BN = 128;
+      BN = kGegluTile;
     } else {
+      // Two cost models over the candidate widths.  Tile-starved problems (some candidate wants split-K) keep the
+      // MMA-time model  waves x (bn + 24) / ksplit  that the split heuristic was tuned with.  Everything else is bound
+      // by the bytes a tile pulls from L2 per K block, (128 + bn) rows (the 12 TB/s L2 caps a 128 x bn tile at
+      // bn / (128 + bn) of ~1.5 PFLOP/s), so there the model is  waves x (bn + 128): it favours the widest tile that
+      // still fills the waves.
       const int cands[4] = {256, 160, 128, 64};
-      double best = -1.0;
+      double best_mma = -1.0, best_l2 = -1.0;
+      int bn_mma = 64, bn_l2 = 0, ks_mma = 1;
       for (int ci = 0; ci < 4; ++ci) {
         const int bn = cands[ci];
         if (bn > 64 && a.N <= bn / 2) continue;                       // mostly-empty tile
@@ -159,11 +149,17 @@ int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
         const int ks = auto_split(tiles);
         const long long waves = (tiles * ks + num_sms() - 1) / num_sms();
         const double cost = waves * (bn + 24.0) / ks + (ks > 1 ? 0.15 * (bn + 24.0) : 0.0);
-        if (best < 0 || cost < best) { best = cost; BN = bn; }
+        if (best_mma < 0 || cost < best_mma) { best_mma = cost; bn_mma = bn; ks_mma = ks; }
+        if (ks == 1) {
+          const double cost_l2 = waves * (bn + 128.0);
+          if (best_l2 < 0 || cost_l2 < best_l2) { best_l2 = cost_l2; bn_l2 = bn; }
+        }
       }
+      BN = (ks_mma == 1 && bn_l2 != 0) ? bn_l2 : bn_mma;
     }
   }
-  if (a.act == ACT_GEGLU && BN != 128) return set_error("conv_gemm: GEGLU requires BN=128");
+  if (a.act == ACT_GEGLU && (BN != kGegluTile || a.N % kGegluTile != 0))
+    return set_error("conv_gemm: GEGLU requires BN=%d and N a multiple of it (N=%d)", kGegluTile, a.N);
   p.n_tiles = (a.N + BN - 1) / BN;
 
   // ---- tensor maps
@@ -216,6 +212,13 @@ int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
     p.split_ws = ws;
     p.split_cnt = cnt;
   }
+#ifdef MD_KPROF
+  if (!g_kprof_buf) {
+    cudaMalloc(&g_kprof_buf, sizeof(unsigned long long) * 160 * 32);
+    cudaMemset(g_kprof_buf, 0, sizeof(unsigned long long) * 160 * 32);
+  }
+  p.kprof = g_kprof_buf;
+#endif
   p.fd_ksplit = make_fastdiv(p.ksplit);
   p.fd_ntiles = make_fastdiv(p.n_tiles);
   p.fd_nxb = make_fastdiv(p.nxb);
@@ -230,10 +233,10 @@ int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
             a.B, a.D, a.H, a.W, a.Cin, a.ntaps, a.N, BN, p.m_tiles, p.n_tiles, p.ksplit, a.act, a.out_f32 != nullptr,
             a.out_bf16 != nullptr, a.res_f32 != nullptr || a.res_bf16 != nullptr);
   switch (BN) {
-    case 64:  return launch_impl<64, 8>(tmA, tmB, p, grid, stream);
-    case 128: return launch_impl<128, 6>(tmA, tmB, p, grid, stream);
-    case 160: return launch_impl<160, 5>(tmA, tmB, p, grid, stream);
-    case 256: return launch_impl<256, 4>(tmA, tmB, p, grid, stream);
+    case 64:  return launch_conv_gemm_bn64(tmA, tmB, p, grid, stream);
+    case 128: return launch_conv_gemm_bn128(tmA, tmB, p, grid, stream);
+    case 160: return launch_conv_gemm_bn160(tmA, tmB, p, grid, stream);
+    case 256: return launch_conv_gemm_bn256(tmA, tmB, p, grid, stream);
     default:  return set_error("conv_gemm: unsupported BN=%d", BN);
   }
 }
@@ -242,12 +245,11 @@ int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
 
 #ifdef MD_KPROF
 // Development builds only: phase time stamps of the last conv_gemm launch ([160 CTAs][32 slots], globaltimer ns).
+namespace md { unsigned long long* g_kprof_buf = nullptr; }
 extern "C" __attribute__((visibility("default"))) int md_debug_kprof(unsigned long long* host_out, int clear) {
-  if (cudaMemcpyFromSymbol(host_out, md::g_kprof, sizeof(unsigned long long) * 160 * 32) != cudaSuccess) return -1;
-  if (clear) {
-    static unsigned long long zeros[160 * 32];
-    cudaMemcpyToSymbol(md::g_kprof, zeros, sizeof(zeros));
-  }
+  if (!md::g_kprof_buf) return -1;
+  if (cudaMemcpy(host_out, md::g_kprof_buf, sizeof(unsigned long long) * 160 * 32, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  if (clear) cudaMemset(md::g_kprof_buf, 0, sizeof(unsigned long long) * 160 * 32);
   return 0;
 }
 #endif

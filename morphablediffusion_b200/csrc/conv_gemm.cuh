@@ -16,13 +16,12 @@ namespace md {
 
 // Development-only phase stamps (build with -DMD_KPROF): globaltimer per CTA and phase, read back with md_debug_kprof.
 #ifdef MD_KPROF
-__device__ unsigned long long g_kprof[160 * 32];
-__device__ __forceinline__ void kprof(int slot) {
+__device__ __forceinline__ void kprof(unsigned long long* buf, int slot) {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  if (blockIdx.x < 160) g_kprof[blockIdx.x * 32 + slot] = t;
+  if (blockIdx.x < 160) buf[blockIdx.x * 32 + slot] = t;
 }
-#define KPROF(slot, cond) do { if (cond) kprof(slot); } while (0)
+#define KPROF(slot, cond) do { if (cond) kprof(p.kprof, slot); } while (0)
 #else
 #define KPROF(slot, cond) do { } while (0)
 #endif
@@ -89,6 +88,9 @@ struct ConvGemmParams {
   int* split_cnt;   // [tiles][EPI_WARPS] arrival counters (zero on entry, reset by the last arrival)
   int isx, isy, isz; // input coordinate = output-tile coordinate * is + tap offset (strided convolution via TMA element strides)
   FastDiv fd_ksplit, fd_ntiles, fd_nxb, fd_nyb, fd_nzb;
+#ifdef MD_KPROF
+  unsigned long long* kprof;  // [160 CTAs][32 slots] phase stamps
+#endif
 };
 
 // work item -> (n tile, box coordinates, K split)
@@ -110,7 +112,12 @@ __device__ __forceinline__ TileCoord decode_item(const ConvGemmParams& p, int it
 __device__ __forceinline__ float act_silu(float x) { return silu_fast(x); }
 __device__ __forceinline__ float act_gelu(float x) { return gelu_fast(x); }
 
-constexpr int kEpiWarps = 16;   // 4 warps per TMEM lane quarter; each owns every 4th 16-column chunk of a tile
+#ifndef MD_EPI_WARPS
+#define MD_EPI_WARPS 16
+#endif
+constexpr int kEpiWarps = MD_EPI_WARPS;   // kEpiWarps/4 warps per TMEM lane quarter; each owns every kCStride-th chunk
+constexpr int kCStride = kEpiWarps / 4;   // 16-column chunks between two chunks of the same warp
+static_assert(kEpiWarps % 4 == 0 && kEpiWarps >= 4 && kEpiWarps <= 16, "epilogue warps come in groups of four");
 constexpr int kChunk = 16;      // accumulator columns per epilogue chunk (tcgen05.ld 32x32b.x16)
 
 template <int BN, int STAGES>
@@ -158,7 +165,7 @@ __device__ __forceinline__ void flush_col_stats(const ConvGemmParams& p, int lan
         st2[k][e] += __shfl_xor_sync(0xffffffff, st2[k][e], o);
       }
     }
-    const int col = n_out0 + (c_begin + k * 4) * kChunk + pchunk * 4;
+    const int col = n_out0 + (c_begin + k * kCStride) * kChunk + pchunk * 4;
     if (prow == 0 && sample >= 0 && col < n_limit) {
       float* cs = p.col_stats + (static_cast<long long>(sample) * p.stats_ld + col) * 2;
 #pragma unroll
@@ -176,13 +183,13 @@ __device__ __forceinline__ void flush_col_stats(const ConvGemmParams& p, int lan
 //   phase 2 (coalesced; one warp instruction = 8 rows x 64 B): + bias, + per-sample vector, activation, + residual,
 //            fp32 / bf16 stores, per-(sample, channel) sum / sum-of-squares for the next GroupNorm.
 // ri[it] = (output row offset in elements or -1, sample) of phase-2 row it*8 + (lane>>2), fetched once per tile.
-template <int BN, int RES, bool RV, int NCH, bool STATS, bool ACTV>
+template <int BN, int RES, bool RV, int NCH, bool STATS, int ACTV>
 __device__ __forceinline__ void epilogue_tile(const ConvGemmParams& p, uint32_t taddr, float* stage, int lane, int n_tile,
                                               const int2 (&ri)[4], int c_begin, float (&st1)[NCH][4],
                                               float (&st2)[NCH][4], bool kp = false) {
   const int prow = lane >> 2;   // phase-2 row within a group of 8
   const int pchunk = lane & 3;  // phase-2 16-byte chunk within the 64-byte row
-  const bool geglu = ACTV && (p.act == ACT_GEGLU);
+  constexpr bool geglu = (ACTV == 2);
   constexpr int HALF = BN / 2;
   const int out_cols = geglu ? HALF : BN;
   const int n_limit = geglu ? p.N / 2 : p.N;
@@ -197,7 +204,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvGemmParams& p, uint32_t 
   const int swl = (lane >> 1) & 3;
   int ci = 0;
 #pragma unroll 1
-  for (int c = c_begin; c < out_cols / kChunk; c += 4, ++ci) {
+  for (int c = c_begin; c < out_cols / kChunk; c += kCStride, ++ci) {
     const int col = n_out0 + c * kChunk + pchunk * 4;
     const bool col_ok = col < n_limit;
     const int col_safe = col_ok ? col : 0;
@@ -270,7 +277,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvGemmParams& p, uint32_t 
       float4 v4 = t4[it];
       v4.x += b4.x; v4.y += b4.y; v4.z += b4.z; v4.w += b4.w;
       if (RV) { v4.x += rv4[it].x; v4.y += rv4[it].y; v4.z += rv4[it].z; v4.w += rv4[it].w; }
-      if (ACTV) {
+      if (ACTV == 1) {
         if (p.act == ACT_SILU) {
           v4.x = act_silu(v4.x); v4.y = act_silu(v4.y); v4.z = act_silu(v4.z); v4.w = act_silu(v4.w);
         } else if (p.act == ACT_RELU) {
@@ -320,7 +327,7 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void* gptr, uint32_t byte
 }
 
 // Epilogue warps: loop over this CTA's work items (same schedule as the producer / MMA warps).
-template <int BN, int STAGES, bool STATS>
+template <int BN, int STAGES, int RES, bool RV, bool STATS, int ACTV>
 __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, uint8_t* smem, uint64_t* tmem_full,
                                               uint64_t* tmem_empty, uint32_t tmem_base, int warp, int lane,
                                               int tile_begin, int tile_end, int tile_step) {
@@ -330,10 +337,9 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, uint8_t* 
   const int c_begin = ew >> 2;   // this warp owns chunks c_begin, c_begin + 4, ...
   const int r = q * 32 + lane;
   float* stage = reinterpret_cast<float*>(smem + S::kStageOffset) + ew * 512;
-  const int mode = (p.res_f32 ? 1 : (p.res_bf16 ? 2 : 0)) * 2 + (p.rowvec ? 1 : 0);
-  const int out_cols_t = (p.act == ACT_GEGLU) ? BN / 2 : BN;
-  const int n_limit_t = (p.act == ACT_GEGLU) ? p.N / 2 : p.N;
-  constexpr int NCH = (BN / kChunk + 3) / 4;  // chunks one warp owns per tile
+  const int out_cols_t = (ACTV == 2) ? BN / 2 : BN;
+  const int n_limit_t = (ACTV == 2) ? p.N / 2 : p.N;
+  constexpr int NCH = (BN / kChunk + kCStride - 1) / kCStride;  // chunks one warp owns per tile
   float st1[NCH][4], st2[NCH][4];
 #pragma unroll
   for (int k = 0; k < NCH; ++k)
@@ -410,7 +416,7 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, uint8_t* 
       constexpr int acc_chunks = BN / kChunk;
       float* ws_tile = p.split_ws + static_cast<size_t>(tile) * p.ksplit * (128 * BN);
       float* mine = ws_tile + static_cast<size_t>(sp) * (128 * BN) + static_cast<size_t>(r) * BN;
-      for (int c = c_begin; c < acc_chunks; c += 4) {
+      for (int c = c_begin; c < acc_chunks; c += kCStride) {
         uint32_t v[16];
         tmem_ld_32x16(taddr + c * kChunk, v);
         tc_wait_ld();
@@ -433,7 +439,7 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, uint8_t* 
       KPROF(7, lt == 0 && warp == 2 && lane == 0);
       if (run_epilogue) {
         __threadfence();
-        for (int c = c_begin; c < acc_chunks; c += 4) {
+        for (int c = c_begin; c < acc_chunks; c += kCStride) {
           uint32_t v[16];
           tmem_ld_32x16(taddr + c * kChunk, v);
           tc_wait_ld();
@@ -461,27 +467,8 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, uint8_t* 
 #else
     constexpr bool kpf = false;
 #endif
-    if (run_epilogue) {
-      if (p.act == ACT_NONE) {
-        switch (mode) {
-          case 0: epilogue_tile<BN, 0, false, NCH, STATS, false>(p, taddr, stage, lane, n_tile, ri, c_begin, st1, st2, kpf); break;
-          case 1: epilogue_tile<BN, 0, true, NCH, STATS, false>(p, taddr, stage, lane, n_tile, ri, c_begin, st1, st2, kpf); break;
-          case 2: epilogue_tile<BN, 1, false, NCH, STATS, false>(p, taddr, stage, lane, n_tile, ri, c_begin, st1, st2, kpf); break;
-          case 3: epilogue_tile<BN, 1, true, NCH, STATS, false>(p, taddr, stage, lane, n_tile, ri, c_begin, st1, st2, kpf); break;
-          case 4: epilogue_tile<BN, 2, false, NCH, STATS, false>(p, taddr, stage, lane, n_tile, ri, c_begin, st1, st2, kpf); break;
-          default: epilogue_tile<BN, 2, true, NCH, STATS, false>(p, taddr, stage, lane, n_tile, ri, c_begin, st1, st2, kpf); break;
-        }
-      } else {
-        switch (mode) {
-          case 0: epilogue_tile<BN, 0, false, NCH, STATS, true>(p, taddr, stage, lane, n_tile, ri, c_begin, st1, st2, kpf); break;
-          case 1: epilogue_tile<BN, 0, true, NCH, STATS, true>(p, taddr, stage, lane, n_tile, ri, c_begin, st1, st2, kpf); break;
-          case 2: epilogue_tile<BN, 1, false, NCH, STATS, true>(p, taddr, stage, lane, n_tile, ri, c_begin, st1, st2, kpf); break;
-          case 3: epilogue_tile<BN, 1, true, NCH, STATS, true>(p, taddr, stage, lane, n_tile, ri, c_begin, st1, st2, kpf); break;
-          case 4: epilogue_tile<BN, 2, false, NCH, STATS, true>(p, taddr, stage, lane, n_tile, ri, c_begin, st1, st2, kpf); break;
-          default: epilogue_tile<BN, 2, true, NCH, STATS, true>(p, taddr, stage, lane, n_tile, ri, c_begin, st1, st2, kpf); break;
-        }
-      }
-    }
+    if (run_epilogue)
+      epilogue_tile<BN, RES, RV, NCH, STATS, ACTV>(p, taddr, stage, lane, n_tile, ri, c_begin, st1, st2, kpf);
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(&tmem_empty[a]);
@@ -493,7 +480,10 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, uint8_t* 
     flush_col_stats<NCH>(p, lane, st_sample, st_ntile * out_cols_t, n_limit_t, c_begin, st1, st2);
 }
 
-template <int BN, int STAGES>
+// RES: 0 none / 1 fp32 / 2 bf16 residual; RV: per-sample additive vector; STATS: fused GroupNorm statistics; ACTV: 0 no
+// activation / 1 SiLU, ReLU or GELU (p.act) / 2 GEGLU.  One kernel per combination keeps every instance a few thousand instructions, so the
+// cold instruction fetches of these short launches stay small.
+template <int BN, int STAGES, int RES, bool RV, bool STATS, int ACTV>
 __global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const ConvGemmParams p) {
@@ -612,12 +602,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else {
     // ===================== epilogue (warps 2 .. 17) =====================
-    if (p.col_stats)
-      epilogue_loop<BN, STAGES, true>(p, smem, tmem_full, tmem_empty, tmem_base, warp, lane, tile_begin,
-                                                 tile_end, tile_step);
-    else
-      epilogue_loop<BN, STAGES, false>(p, smem, tmem_full, tmem_empty, tmem_base, warp, lane, tile_begin,
-                                                  tile_end, tile_step);
+    epilogue_loop<BN, STAGES, RES, RV, STATS, ACTV>(p, smem, tmem_full, tmem_empty, tmem_base, warp, lane, tile_begin,
+                                                   tile_end, tile_step);
   }
 
   tc_fence_before();

@@ -1,0 +1,10 @@
+// conv_gemm kernels with 64-column tiles (8 pipeline stages): all epilogue variants of this width.
+#include "conv_gemm_launch.cuh"
+
+namespace md {
+
+int launch_conv_gemm_bn64(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p, int grid, cudaStream_t st) {
+  return launch_conv_gemm_variant<64, 8>(tmA, tmB, p, grid, st);
+}
+
+}  // namespace md

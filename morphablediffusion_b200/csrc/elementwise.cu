@@ -128,33 +128,118 @@ __global__ void gn_finalize_kernel(float* __restrict__ stats0, int C0, float* __
 }
 
 // Stage 3: y = act(x*scale + shift) -> bf16 (and optionally the raw x as bf16, used by 1x1 skip convolutions).
+// Thread = (channel quad cq, row phase rsub): its four (scale, shift) pairs stay in registers and the row loop has no
+// index arithmetic beyond one add, so the pass runs at HBM speed.  grid = (row chunks, samples).
 template <typename T0, typename T1>
-__global__ void affine_act_kernel(const T0* __restrict__ x0, int C0, const T1* __restrict__ x1, int C1,
-                                  const float* __restrict__ ss, __nv_bfloat16* __restrict__ out,
-                                  __nv_bfloat16* __restrict__ raw, size_t total4, int rows, int act) {
-  pdl_grid_sync();
+__device__ __forceinline__ void affine_rows(const T0* __restrict__ x0, int C0, const T1* __restrict__ x1, int C1,
+                                            const float4 s01, const float4 s23, __nv_bfloat16* __restrict__ out,
+                                            __nv_bfloat16* __restrict__ raw, int b, int rows, int r0, int r1, int c,
+                                            int rsub, int R, int act) {
   const int C = C0 + C1;
-  const int CQ = C >> 2;
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total4;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int cq = static_cast<int>(i % CQ);
-    const size_t row = i / CQ;  // global row = b*rows + r
-    const int b = static_cast<int>(row / rows);
-    const int c = cq * 4;
-    float4 v;
-    if (c < C0) v = load4(x0 + row * C0 + c);
-    else v = load4(x1 + row * C1 + (c - C0));
-    if (raw) store4(raw + row * C + c, v);
-    const float4 s01 = *reinterpret_cast<const float4*>(ss + (static_cast<size_t>(b) * C + c) * 2);
-    const float4 s23 = *reinterpret_cast<const float4*>(ss + (static_cast<size_t>(b) * C + c) * 2 + 4);
+  const size_t base = static_cast<size_t>(b) * rows;
+  const bool first = c < C0;
+  const T0* p0 = x0 + base * C0 + c;
+  const T1* p1 = first ? nullptr : x1 + base * C1 + (c - C0);
+  __nv_bfloat16* po = out + base * C + c;
+  __nv_bfloat16* pr = raw ? raw + base * C + c : nullptr;
+#pragma unroll 4
+  for (int r = r0 + rsub; r < r1; r += R) {
+    const float4 v = first ? load4(p0 + static_cast<size_t>(r) * C0) : load4(p1 + static_cast<size_t>(r) * C1);
+    if (pr) store4(pr + static_cast<size_t>(r) * C, v);
     float4 y = make_float4(v.x * s01.x + s01.y, v.y * s01.z + s01.w, v.z * s23.x + s23.y, v.w * s23.z + s23.w);
     if (act == ACT_SILU) {
       y.x = silu_f(y.x); y.y = silu_f(y.y); y.z = silu_f(y.z); y.w = silu_f(y.w);
     } else if (act == ACT_RELU) {
       y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f);
     }
-    store4(out + row * C + c, y);
+    store4(po + static_cast<size_t>(r) * C, y);
   }
+}
+
+template <typename T0, typename T1>
+__global__ void affine_act_kernel(const T0* __restrict__ x0, int C0, const T1* __restrict__ x1, int C1,
+                                  const float* __restrict__ ss, __nv_bfloat16* __restrict__ out,
+                                  __nv_bfloat16* __restrict__ raw, int rows, int rows_per_cta, int R, int act) {
+  pdl_grid_sync();
+  const int C = C0 + C1;
+  const int CQ = C >> 2;
+  const int b = blockIdx.y;
+  const int cq = threadIdx.x % CQ, rsub = threadIdx.x / CQ;
+  if (rsub >= R) return;
+  const int c = cq * 4;
+  const float4 s01 = *reinterpret_cast<const float4*>(ss + (static_cast<size_t>(b) * C + c) * 2);
+  const float4 s23 = *reinterpret_cast<const float4*>(ss + (static_cast<size_t>(b) * C + c) * 2 + 4);
+  const int r0 = blockIdx.x * rows_per_cta;
+  affine_rows(x0, C0, x1, C1, s01, s23, out, raw, b, rows, r0, min(rows, r0 + rows_per_cta), c, rsub, R, act);
+}
+
+// Stages 2 + 3 in one kernel for statistics that the producing GEMM epilogues accumulated: every CTA reduces the
+// (tiny) per-channel sums of its sample to group mean / rstd in shared memory, derives its threads' scale/shift and
+// streams its rows.  Saves the finalize launch and the scale/shift round trip of ~100 GroupNorms per step.
+template <typename T0, typename T1>
+__global__ void gn_apply_fused_kernel(const T0* __restrict__ x0, int C0, const T1* __restrict__ x1, int C1,
+                                      const float* __restrict__ stats0, const float* __restrict__ stats1,
+                                      const float* __restrict__ gamma, const float* __restrict__ beta,
+                                      const float* __restrict__ addvec, int addvec_ld, int G, float eps,
+                                      __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ raw, int rows,
+                                      int rows_per_cta, int R, int act) {
+  pdl_grid_sync();
+  extern __shared__ float gsm[];  // [G][2] mean, rstd, then [C][2] per-channel (sum, sum of squares) incl. addvec
+  const int C = C0 + C1;
+  const int CQ = C >> 2;
+  const int cpg = C / G;
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+  const float nrows = static_cast<float>(rows);
+  const int cq = threadIdx.x % CQ, rsub = threadIdx.x / CQ;
+  const int c = cq * 4;
+  // this thread's affine parameters are requested first so that their latency overlaps the statistics reduction
+  const float4 g4 = load4(gamma + c), b4 = load4(beta + c);
+  float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (addvec) t4 = load4(addvec + static_cast<size_t>(b) * addvec_ld + c);
+  // one independent load per channel (a single memory round trip for the whole CTA), staged in shared memory
+  float* chs = gsm + 2 * G;
+  for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
+    const float2 sq = (ch < C0) ? *reinterpret_cast<const float2*>(stats0 + (static_cast<size_t>(b) * C0 + ch) * 2)
+                                : *reinterpret_cast<const float2*>(stats1 + (static_cast<size_t>(b) * C1 + (ch - C0)) * 2);
+    const float tv = addvec ? addvec[static_cast<size_t>(b) * addvec_ld + ch] : 0.f;
+    chs[2 * ch] = sq.x + nrows * tv;
+    chs[2 * ch + 1] = sq.y + 2.f * tv * sq.x + nrows * tv * tv;
+  }
+  __syncthreads();
+  // group sums in fp32 (the per-channel sums are fp32 atomics already); only the cancellation-prone
+  // E[x^2] - mean^2 runs in double
+  const double inv_n = 1.0 / (static_cast<double>(nrows) * cpg);
+  for (int g = warp; g < G; g += nwarps) {
+    float s1 = 0.f, s2 = 0.f;
+    for (int ch = g * cpg + lane; ch < (g + 1) * cpg; ch += 32) { s1 += chs[2 * ch]; s2 += chs[2 * ch + 1]; }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffff, s1, o);
+      s2 += __shfl_xor_sync(0xffffffff, s2, o);
+    }
+    if (lane == 0) {
+      const double mean = static_cast<double>(s1) * inv_n;
+      double var = static_cast<double>(s2) * inv_n - mean * mean;
+      if (var < 0.0) var = 0.0;
+      gsm[2 * g] = static_cast<float>(mean);
+      gsm[2 * g + 1] = rsqrtf(static_cast<float>(var) + eps);
+    }
+  }
+  __syncthreads();
+  if (rsub >= R) return;
+  float sc[4], sh[4];
+  const float gg[4] = {g4.x, g4.y, g4.z, g4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w}, tt[4] = {t4.x, t4.y, t4.z, t4.w};
+  int g = c / cpg, rem = c - g * cpg;  // one division; the other three channels step through the group boundary
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    sc[e] = gg[e] * gsm[2 * g + 1];
+    sh[e] = bb[e] + (tt[e] - gsm[2 * g]) * sc[e];
+    if (++rem == cpg) { rem = 0; ++g; }
+  }
+  const int r0 = blockIdx.x * rows_per_cta;
+  affine_rows(x0, C0, x1, C1, make_float4(sc[0], sh[0], sc[1], sh[1]), make_float4(sc[2], sh[2], sc[3], sh[3]), out, raw,
+              b, rows, r0, min(rows, r0 + rows_per_cta), c, rsub, R, act);
 }
 
 template <typename T0, typename T1>
@@ -182,17 +267,31 @@ static int group_norm_impl(const GroupNormArgs& a, cudaStream_t st) {
   } else if (a.C1 > 0 && !a.stats1) {
     return set_error("group_norm: statistics for the second source are missing");
   }
+  // row split of the apply pass: CTAs of up to 512 threads, ~4 per SM in total (every CTA first reduces the group
+  // statistics of its sample, so fewer and fatter CTAs amortise that), at least 4 rows per row phase
+  const int RA = std::max(1, std::min(8, 512 / CQ));
+  const int apply_target = num_sms() * 4;
+  int apply_rows = std::max(RA * 4, static_cast<int>((static_cast<long long>(a.rows) * a.B + apply_target - 1) / apply_target));
+  apply_rows = std::min(apply_rows, a.rows);
+  const dim3 apply_grid((a.rows + apply_rows - 1) / apply_rows, a.B);
+  const int apply_threads = ((CQ * RA + 31) / 32) * 32;
+  const bool vec_ok = !((reinterpret_cast<uintptr_t>(a.gamma) | reinterpret_cast<uintptr_t>(a.beta) |
+                         reinterpret_cast<uintptr_t>(a.addvec)) & 15) && (a.addvec_ld % 4 == 0);
+  if (a.out && a.stats0 && !zero_after && vec_ok) {  // statistics from GEMM epilogues: finalize + apply in one kernel
+    launch_pdl(gn_apply_fused_kernel<T0, T1>, apply_grid, dim3(apply_threads), (a.groups + C) * 2 * sizeof(float), st,
+               static_cast<const T0*>(a.x0), a.C0, static_cast<const T1*>(a.x1), a.C1, static_cast<const float*>(st0),
+               static_cast<const float*>(st1), a.gamma, a.beta, a.addvec, a.addvec_ld, a.groups, a.eps,
+               static_cast<__nv_bfloat16*>(a.out), static_cast<__nv_bfloat16*>(a.raw_out), a.rows, apply_rows, RA, a.act);
+    return check_launch("gn_apply_fused");
+  }
   launch_pdl(gn_finalize_kernel, dim3(a.B), dim3(std::min(1024, 32 * a.groups)), 0, st, st0, c0, st1, c1, zero_after, a.gamma, a.beta, a.addvec,
                                                                     a.addvec_ld, a.scale_shift, a.groups,
                                                                     static_cast<float>(a.rows), a.eps);
   MD_CHECK(check_launch("gn_finalize"));
   if (!a.out) return 0;  // scale/shift only (consumer applies the affine itself)
-  const size_t total4 = static_cast<size_t>(a.B) * a.rows * CQ;
-  const int blocks = static_cast<int>(std::min<size_t>((total4 + 255) / 256, static_cast<size_t>(num_sms()) * 16));
-  launch_pdl(affine_act_kernel<T0, T1>, dim3(blocks), dim3(256), 0, st, static_cast<const T0*>(a.x0), a.C0,
-                                                    static_cast<const T1*>(a.x1), a.C1, a.scale_shift,
-                                                    static_cast<__nv_bfloat16*>(a.out),
-                                                    static_cast<__nv_bfloat16*>(a.raw_out), total4, a.rows, a.act);
+  launch_pdl(affine_act_kernel<T0, T1>, apply_grid, dim3(apply_threads), 0, st, static_cast<const T0*>(a.x0), a.C0,
+             static_cast<const T1*>(a.x1), a.C1, static_cast<const float*>(a.scale_shift),
+             static_cast<__nv_bfloat16*>(a.out), static_cast<__nv_bfloat16*>(a.raw_out), a.rows, apply_rows, RA, a.act);
   return check_launch("affine_act");
 }
 
@@ -205,72 +304,105 @@ int launch_group_norm(const GroupNormArgs& a, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------------------------------ LayerNorm
-// One warp per row.  Optional per-sample vector added first (and written back): x <- x + addvec[b].
-template <int MAXV>
+// One warp per RPW consecutive rows: all RPW rows are requested before the first reduction (one memory round trip per
+// warp instead of one per row) and gamma / beta stay in registers.  Optional per-sample vector added first (and written
+// back): x <- x + addvec[b].  MAXV = ceil(C / 128) float4 per lane.
+template <int MAXV, int RPW>
 __global__ void layer_norm_kernel(float* __restrict__ x, const float* __restrict__ addvec, int addvec_ld,
                                   const float* __restrict__ gamma, const float* __restrict__ beta,
                                   __nv_bfloat16* __restrict__ out, size_t nrows, int rows_per_sample, int C, float eps) {
   pdl_grid_sync();
   const int lane = threadIdx.x & 31;
-  const size_t row = (blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x) >> 5;
-  if (row >= nrows) return;
-  const int nv = C >> 7;  // float4 per lane (C multiple of 128) handled vector-wise; remainder scalar
-  float* xr = x + row * C;
-  const float* av = addvec ? addvec + (row / rows_per_sample) * addvec_ld : nullptr;
-  float4 v[MAXV];
-  float s = 0.f;
+  const size_t row0 = ((blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x) >> 5) * RPW;
+  if (row0 >= nrows) return;
+  float4 v[RPW][MAXV];
 #pragma unroll
-  for (int k = 0; k < MAXV; ++k) {
-    const int c = (k * 32 + lane) * 4;
-    if (c < C) {
-      v[k] = load4(xr + c);
-      if (av) {
-        const float4 a4 = load4(av + c);
-        v[k].x += a4.x; v[k].y += a4.y; v[k].z += a4.z; v[k].w += a4.w;
-        store4(xr + c, v[k]);
+  for (int r = 0; r < RPW; ++r) {
+    const size_t row = row0 + r;
+    if (row < nrows) {
+#pragma unroll
+      for (int k = 0; k < MAXV; ++k) {
+        const int c = (k * 32 + lane) * 4;
+        if (c < C) v[r][k] = load4(x + row * C + c);
       }
-      s += v[k].x + v[k].y + v[k].z + v[k].w;
     }
   }
-  (void)nv;
-#pragma unroll
-  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffff, s, o);
-  const float mean = s / C;
-  float q = 0.f;
+  float4 g[MAXV], bt[MAXV];
 #pragma unroll
   for (int k = 0; k < MAXV; ++k) {
     const int c = (k * 32 + lane) * 4;
-    if (c < C) {
-      const float dx = v[k].x - mean, dy = v[k].y - mean, dz = v[k].z - mean, dw = v[k].w - mean;
-      q += dx * dx + dy * dy + dz * dz + dw * dw;
+    if (c < C) { g[k] = load4(gamma + c); bt[k] = load4(beta + c); }
+  }
+  const float inv_c = 1.f / static_cast<float>(C);
+#pragma unroll
+  for (int r = 0; r < RPW; ++r) {
+    const size_t row = row0 + r;
+    if (row >= nrows) break;
+    float s = 0.f;
+    if (addvec) {
+      const float* av = addvec + (row / rows_per_sample) * addvec_ld;
+#pragma unroll
+      for (int k = 0; k < MAXV; ++k) {
+        const int c = (k * 32 + lane) * 4;
+        if (c < C) {
+          const float4 a4 = load4(av + c);
+          v[r][k].x += a4.x; v[r][k].y += a4.y; v[r][k].z += a4.z; v[r][k].w += a4.w;
+          store4(x + row * C + c, v[r][k]);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k) {
+      const int c = (k * 32 + lane) * 4;
+      if (c < C) s += v[r][k].x + v[r][k].y + v[r][k].z + v[r][k].w;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffff, s, o);
+    const float mean = s * inv_c;
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k) {
+      const int c = (k * 32 + lane) * 4;
+      if (c < C) {
+        const float dx = v[r][k].x - mean, dy = v[r][k].y - mean, dz = v[r][k].z - mean, dw = v[r][k].w - mean;
+        q += dx * dx + dy * dy + dz * dz + dw * dw;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffff, q, o);
+    const float rstd = rsqrtf(q * inv_c + eps);
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k) {
+      const int c = (k * 32 + lane) * 4;
+      if (c < C) {
+        float4 y;
+        y.x = (v[r][k].x - mean) * rstd * g[k].x + bt[k].x;
+        y.y = (v[r][k].y - mean) * rstd * g[k].y + bt[k].y;
+        y.z = (v[r][k].z - mean) * rstd * g[k].z + bt[k].z;
+        y.w = (v[r][k].w - mean) * rstd * g[k].w + bt[k].w;
+        store4(out + row * C + c, y);
+      }
     }
   }
-#pragma unroll
-  for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffff, q, o);
-  const float rstd = rsqrtf(q / C + eps);
-#pragma unroll
-  for (int k = 0; k < MAXV; ++k) {
-    const int c = (k * 32 + lane) * 4;
-    if (c < C) {
-      const float4 g = load4(gamma + c), bt = load4(beta + c);
-      float4 y;
-      y.x = (v[k].x - mean) * rstd * g.x + bt.x;
-      y.y = (v[k].y - mean) * rstd * g.y + bt.y;
-      y.z = (v[k].z - mean) * rstd * g.z + bt.z;
-      y.w = (v[k].w - mean) * rstd * g.w + bt.w;
-      store4(out + row * C + c, y);
-    }
-  }
+}
+
+template <int MAXV, int RPW>
+static int layer_norm_impl(float* x, const float* addvec, int addvec_ld, const float* gamma, const float* beta,
+                           void* out_bf16, size_t nrows, int rows_per_sample, int C, float eps, cudaStream_t st) {
+  const int threads = 256;
+  const size_t warps = (nrows + RPW - 1) / RPW;
+  const size_t blocks = (warps * 32 + threads - 1) / threads;
+  launch_pdl(layer_norm_kernel<MAXV, RPW>, dim3(static_cast<unsigned>(blocks)), dim3(threads), 0, st, x, addvec, addvec_ld,
+             gamma, beta, static_cast<__nv_bfloat16*>(out_bf16), nrows, rows_per_sample, C, eps);
+  return check_launch("layer_norm");
 }
 
 int launch_layer_norm(float* x, const float* addvec, int addvec_ld, const float* gamma, const float* beta,
                       void* out_bf16, size_t nrows, int rows_per_sample, int C, float eps, cudaStream_t st) {
   if (C % 4 || C > 1280) return set_error("layer_norm: unsupported C=%d", C);
-  const int threads = 256;
-  const size_t blocks = (nrows * 32 + threads - 1) / threads;
-  launch_pdl(layer_norm_kernel<10>, dim3(static_cast<unsigned>(blocks)), dim3(threads), 0, st, 
-      x, addvec, addvec_ld, gamma, beta, static_cast<__nv_bfloat16*>(out_bf16), nrows, rows_per_sample, C, eps);
-  return check_launch("layer_norm");
+  if (C <= 384) return layer_norm_impl<3, 4>(x, addvec, addvec_ld, gamma, beta, out_bf16, nrows, rows_per_sample, C, eps, st);
+  if (C <= 640) return layer_norm_impl<5, 2>(x, addvec, addvec_ld, gamma, beta, out_bf16, nrows, rows_per_sample, C, eps, st);
+  return layer_norm_impl<10, 1>(x, addvec, addvec_ld, gamma, beta, out_bf16, nrows, rows_per_sample, C, eps, st);
 }
 
 // ------------------------------------------------------------------------------------------------ small linear

@@ -7,6 +7,9 @@
 namespace md {
 
 enum Act : int { ACT_NONE = 0, ACT_SILU = 1, ACT_RELU = 2, ACT_GEGLU = 3, ACT_GELU = 4 };
+// GEGLU projections are packed per tile of kGegluTile weight rows: kGegluTile/2 value rows, then their kGegluTile/2 gate
+// rows, so one accumulator tile holds both halves (the widest tile: fewest re-reads of the activation rows from L2).
+constexpr int kGegluTile = 256;
 
 // ---- elementwise.cu
 struct GroupNormArgs {

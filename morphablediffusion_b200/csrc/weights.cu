@@ -1,7 +1,7 @@
 // Weight ingestion: the caller hands over the reference state dict (fp32 device tensors addressed by the
 // reference's nn.Module paths) and this file re-lays it out for the kernels:
 //   conv / linear weights -> bf16 [N][tap][Cin] (K-major operands of conv_gemm), q|k|v and k|v fused along N,
-//   GEGLU projection interleaved per 128-row tile, ConvTranspose3d split into 8 output-parity classes,
+//   GEGLU projection interleaved per 256-row tile (128 value | 128 gate), ConvTranspose3d split into 8 output-parity classes,
 //   BatchNorm1d (eval) folded into scale/shift, all ResBlock emb_layers concatenated into one matrix.
 #include "engine.h"
 
@@ -20,8 +20,9 @@ __global__ void pack_kernel(const float* __restrict__ src, OutT* __restrict__ ds
     const int n = static_cast<int>(idx / (static_cast<size_t>(I) * T));
     int ns = n;
     if (geglu_inner > 0) {
-      const int tile = n / 128, r = n % 128;
-      ns = (r < 64) ? (tile * 64 + r) : (geglu_inner + tile * 64 + (r - 64));
+      constexpr int H = kGegluTile / 2;
+      const int tile = n / kGegluTile, r = n % kGegluTile;
+      ns = (r < H) ? (tile * H + r) : (geglu_inner + tile * H + (r - H));
     }
     const float v = src[ns * sn + taps.t[t] * st + i * si];
     dst[n * dn + t * dt + i * di] = static_cast<OutT>(v);
@@ -31,8 +32,9 @@ __global__ void pack_kernel(const float* __restrict__ src, OutT* __restrict__ ds
 __global__ void permute_rows_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, int N, int geglu_inner) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
-  const int tile = n / 128, r = n % 128;
-  const int ns = (r < 64) ? (tile * 64 + r) : (geglu_inner + tile * 64 + (r - 64));
+  constexpr int H = kGegluTile / 2;
+  const int tile = n / kGegluTile, r = n % kGegluTile;
+  const int ns = (r < H) ? (tile * H + r) : (geglu_inner + tile * H + (r - H));
   dst[n] = src[ns];
 }
 

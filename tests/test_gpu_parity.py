@@ -102,13 +102,13 @@ def test_gemm_epilogues(nat):
                   out_f32=out, out_bf16=outb, act="silu")
     ref = F.silu(A.float() @ Wt.float().t() + bias + rv.repeat_interleave(rows, 0)) + res
     assert rel(out, ref) < 1e-5 and rel(outb, ref) < 5e-3
-    # GEGLU: value * gelu(gate) with the 128-row tile interleave the library's weight packer produces
+    # GEGLU: value * gelu(gate) with the 256-row tile interleave (128 value | 128 gate) of the library's weight packer
     inner = 1280
     Wf = torch.randn(2 * inner, 320, device="cuda") / 320 ** 0.5
     bfull = torch.randn(2 * inner, device="cuda")
     idx = []
-    for j in range(inner // 64):
-        idx += list(range(j * 64, (j + 1) * 64)) + list(range(inner + j * 64, inner + (j + 1) * 64))
+    for j in range(inner // 128):
+        idx += list(range(j * 128, (j + 1) * 128)) + list(range(inner + j * 128, inner + (j + 1) * 128))
     idx = torch.tensor(idx, device="cuda")
     A2 = bf(torch.randn(512, 320, device="cuda"))
     o = torch.zeros(512, inner, device="cuda", dtype=torch.bfloat16)

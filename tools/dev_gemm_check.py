@@ -57,8 +57,8 @@ def case_geglu(M=512, K=320, inner=1280):
     A = bf(torch.randn(M, K, device=dev))
     Wfull = torch.randn(2 * inner, K, device=dev) / K ** 0.5
     bfull = torch.randn(2 * inner, device=dev)
-    # pack: tile j of 128 rows = [64 value rows | 64 gate rows]
-    half = 64
+    # pack: tile j of 256 rows = [128 value rows | 128 gate rows]
+    half = 128
     idx = []
     for j in range(inner // half):
         idx += list(range(j * half, (j + 1) * half)) + list(range(inner + j * half, inner + (j + 1) * half))

@@ -29,6 +29,7 @@ timeout 900 ncu --profile-from-start off --set full --clock-control none --impor
   -o $O/full -f python tools/profile_step.py 16 > $O/full.log 2>&1
 ncu -i $O/full.ncu-rep --page raw --csv > $O/full_raw.csv 2>> $O/full.log
 ncu -i $O/full.ncu-rep --page details --csv > $O/full_details.csv 2>> $O/full.log
+ncu -i $O/full.ncu-rep --page source --csv 2>> $O/full.log | gzip -9 > $O/full_source.csv.gz
 sz=$(stat -c %s $O/full.ncu-rep 2>/dev/null || echo 0)
 if [ "$sz" -gt 25000000 ]; then rm -f $O/full.ncu-rep; echo "full.ncu-rep dropped ($sz bytes)" >> $O/full.log; fi
 fi

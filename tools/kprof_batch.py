@@ -83,7 +83,7 @@ if __name__ == "__main__":
     sel = sys.argv[1:]
     cases = [
         ("frustum_ctx_1x1", dict(B=16, H=1, W=49152, K=64, N=64, BN=64, stats=True)),
-        ("geglu_l0", dict(B=32, H=1, W=1024, K=320, N=2560, BN=128, act="geglu")),
+        ("geglu_l0", dict(B=32, H=1, W=1024, K=320, N=2560, BN=256, act="geglu")),
         ("proj_l0_res", dict(B=32, H=1, W=1024, K=320, N=320, BN=160, mode="res")),
         ("qkv_l0", dict(B=32, H=1, W=1024, K=320, N=960, BN=160)),
         ("conv_l0_res", dict(B=32, H=32, W=32, K=320, N=320, taps_n=9, BN=160, mode="res", stats=True)),
