@@ -159,6 +159,12 @@ MD_API int md_ddim_timestep(md_ctx* ctx, int index);  /* 1 .. 981 */
 MD_API int md_op_group_norm(const void* x, int x_is_bf16, int B, int rows, int C, int groups, float eps,
                             const float* gamma, const float* beta, const float* addvec, int act, void* out_bf16,
                             void* stream);
+/* Same GroupNorm with the per-(sample, channel) statistics supplied by the caller: stats fp32 [B][C][2] = (sum, sum of
+ * squares) over the rows, exactly what md_op_conv_gemm's col_stats epilogue accumulates.  This is the path the step
+ * uses after every tensor-core GEMM (finalize + apply in one kernel). */
+MD_API int md_op_group_norm_stats(const void* x, int x_is_bf16, int B, int rows, int C, int groups, float eps,
+                                  const float* gamma, const float* beta, const float* addvec, int act,
+                                  const float* stats, void* out_bf16, void* stream);
 /* nn.LayerNorm over the last dim of x fp32 [rows][C] -> bf16 (ldm/modules/attention.py:257-259) */
 MD_API int md_op_layer_norm(float* x, const float* gamma, const float* beta, void* out_bf16, long long rows, int C,
                             float eps, void* stream);

@@ -157,6 +157,8 @@ for _f in ("md_embed_time", "md_create", "md_load_weights", "md_bind_sample", "m
     getattr(lib, _f).restype = C.c_int
 
 lib.md_op_group_norm.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _vp, _vp, _vp, C.c_int, _vp, _vp]
+lib.md_op_group_norm_stats.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp]
+lib.md_op_group_norm_stats.restype = C.c_int
 lib.md_op_layer_norm.argtypes = [_vp, _vp, _vp, _vp, C.c_longlong, C.c_int, C.c_float, _vp]
 lib.md_op_self_attention.argtypes = [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp]
 lib.md_op_self_attention_impl.argtypes = [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp]

@@ -521,6 +521,23 @@ int md_op_group_norm(const void* x, int x_is_bf16, int B, int rows, int C, int g
   return rc;
 }
 
+int md_op_group_norm_stats(const void* x, int x_is_bf16, int B, int rows, int C, int groups, float eps, const float* gamma,
+                           const float* beta, const float* addvec, int act, const float* stats, void* out_bf16,
+                           void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!stats || !out_bf16) return set_error("md_op_group_norm_stats: stats and out are required");
+  float* ws = nullptr;
+  MD_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws), sizeof(float) * 2 * B * C, st));
+  GroupNormArgs g;
+  memset(&g, 0, sizeof(g));
+  g.x0 = x; g.C0 = C; g.x0_bf16 = x_is_bf16; g.B = B; g.rows = rows; g.groups = groups; g.eps = eps;
+  g.gamma = gamma; g.beta = beta; g.addvec = addvec; g.addvec_ld = C; g.stats0 = stats; g.scale_shift = ws;
+  g.out = out_bf16; g.act = act;
+  const int rc = launch_group_norm(g, st);
+  cudaFreeAsync(ws, st);
+  return rc;
+}
+
 int md_op_layer_norm(float* x, const float* gamma, const float* beta, void* out_bf16, long long rows, int C, float eps,
                      void* stream) {
   return launch_layer_norm(x, nullptr, 0, gamma, beta, out_bf16, static_cast<size_t>(rows), 1, C, eps,

@@ -233,6 +233,42 @@ def test_group_norm(nat, B, rows, C, G, act, bf16_in):
     assert rel(out, ref) < 5e-3
 
 
+@pytest.mark.parametrize("B,rows,C,G,act,bf16_in", [(3, 1024, 320, 32, 1, False), (2, 256, 2560, 32, 1, False),
+                                                    (2, 64, 1280, 32, 0, False), (2, 6144, 128, 8, 1, True),
+                                                    (2, 49152, 64, 8, 2, True), (1, 37, 64, 32, 1, False)])
+def test_group_norm_from_epilogue_statistics(nat, B, rows, C, G, act, bf16_in):
+    """The step's GroupNorm path: per-(sample, channel) sum / sum of squares as the GEMM epilogues accumulate them,
+    group finalize + normalise + activation in one kernel."""
+    torch.manual_seed(15)
+    x = torch.randn(B, rows, C, device="cuda") * 2 + 0.5
+    if bf16_in:
+        x = bf(x)
+    gamma, beta = torch.randn(C, device="cuda"), torch.randn(C, device="cuda")
+    addvec = torch.randn(B, C, device="cuda") if bf16_in else None
+    xf = x.float()
+    stats = torch.stack([xf.sum(1), (xf * xf).sum(1)], dim=-1).contiguous()  # [B][C][2]
+    out = torch.zeros(B, rows, C, device="cuda", dtype=torch.bfloat16)
+    nat.check(nat.lib.md_op_group_norm_stats(x.data_ptr(), int(bf16_in), B, rows, C, G, 1e-5, gamma.data_ptr(),
+                                             beta.data_ptr(), nat.ptr(addvec), act, stats.data_ptr(), out.data_ptr(),
+                                             nat.cur_stream()), "gn_stats")
+    xin = xf + (addvec[:, None, :] if addvec is not None else 0)
+    ref = F.group_norm(xin.permute(0, 2, 1), G, gamma, beta, 1e-5).permute(0, 2, 1)
+    ref = F.silu(ref) if act == 1 else (F.relu(ref) if act == 2 else ref)
+    assert rel(out, ref) < 5e-3
+
+
+@pytest.mark.parametrize("C,rows", [(320, 777), (640, 515), (1280, 130)])
+def test_layer_norm_row_tails(nat, C, rows):
+    """Row counts that are not a multiple of the rows a warp owns (4 / 2 / 1)."""
+    torch.manual_seed(16)
+    x = torch.randn(rows, C, device="cuda") * 3 + 1
+    g, b = torch.randn(C, device="cuda"), torch.randn(C, device="cuda")
+    out = torch.zeros(rows, C, device="cuda", dtype=torch.bfloat16)
+    nat.check(nat.lib.md_op_layer_norm(x.data_ptr(), g.data_ptr(), b.data_ptr(), out.data_ptr(), rows, C, 1e-5,
+                                       nat.cur_stream()), "ln")
+    assert rel(out, F.layer_norm(x, (C,), g, b, 1e-5)) < 5e-3
+
+
 @pytest.mark.parametrize("C", [320, 640, 1280])
 def test_layer_norm(nat, C):
     torch.manual_seed(6)
@@ -242,6 +278,34 @@ def test_layer_norm(nat, C):
     nat.check(nat.lib.md_op_layer_norm(x.data_ptr(), g.data_ptr(), b.data_ptr(), out.data_ptr(), 777, C, 1e-5,
                                        nat.cur_stream()), "ln")
     assert rel(out, F.layer_norm(x, (C,), g, b, 1e-5)) < 5e-3
+
+
+@pytest.mark.parametrize("B,S,heads,dh,qscale", [(2, 1024, 8, 40, 1.0), (2, 1024, 8, 40, 8.0), (3, 256, 8, 80, 1.0),
+                                                 (3, 256, 8, 80, 6.0), (1, 128, 4, 64, 1.0), (2, 384, 2, 128, 1.0),
+                                                 (1, 4096, 8, 40, 1.0)])
+@pytest.mark.parametrize("impl", [1, 2])
+def test_self_attention_both_kernels(nat, B, S, heads, dh, qscale, impl):
+    """mma.sync flash kernel (impl 1) and tcgen05/TMEM kernel (impl 2) against an fp32 softmax; qscale > 1 gives
+    logits whose running maximum keeps growing, which exercises the lazy in-TMEM output rescale of impl 2."""
+    torch.manual_seed(17)
+    C = heads * dh
+    qkv = torch.randn(B, S, 3 * C, device="cuda")
+    qkv[..., :C] *= qscale
+    qkv = bf(qkv)
+    out = torch.full((B, S, C), float("nan"), device="cuda", dtype=torch.bfloat16)
+    nat.check(nat.lib.md_op_self_attention_impl(qkv.data_ptr(), out.data_ptr(), B, S, heads, dh, impl,
+                                                nat.cur_stream()), "attn")
+    q, k, v = [t.float().view(B, S, heads, dh).permute(0, 2, 1, 3) for t in qkv.chunk(3, dim=-1)]
+    ref = torch.softmax(q @ k.transpose(-1, -2) * dh ** -0.5, -1) @ v
+    ref = ref.permute(0, 2, 1, 3).reshape(B, S, C)
+    assert rel(out, ref) < 1e-2
+
+
+def test_self_attention_tc_rejects_unsupported_shapes(nat):
+    qkv = torch.zeros(1, 64, 3 * 160, device="cuda", dtype=torch.bfloat16)
+    out = torch.zeros(1, 64, 160, device="cuda", dtype=torch.bfloat16)
+    assert nat.lib.md_op_self_attention_impl(qkv.data_ptr(), out.data_ptr(), 1, 64, 1, 160, 2, nat.cur_stream()) != 0
+    assert b"attention_tc" in nat.lib.md_last_error()
 
 
 @pytest.mark.parametrize("B,S,heads,dh", [(2, 1024, 8, 40), (3, 256, 8, 80), (2, 64, 8, 160), (5, 16, 8, 160),
