@@ -54,6 +54,7 @@ class ConvGemmArgs(C.Structure):
         ("stats_ld", C.c_int),
         ("ksplit", C.c_int),
         ("in_stride", C.c_int * 3),
+        ("cta_pair", C.c_int),
     ]
 
 
@@ -88,7 +89,7 @@ ACT = {"none": 0, "silu": 1, "relu": 2, "geglu": 3, "gelu": 4}
 
 def conv_gemm(A, Wt, *, B, D, H, W, Cin, N, taps, bias=None, rowvec=None, res_f32=None, res_bf16=None,
               out_f32=None, out_bf16=None, act="none", Cpitch=0, out_dims=None, os_=None, op=None, ldo=0,
-              out_scale=1.0, BN=0, col_stats=None, in_stride=None, ksplit=0):
+              out_scale=1.0, BN=0, col_stats=None, in_stride=None, ksplit=0, cta_pair=0):
     a = ConvGemmArgs()
     a.A = ptr(A); a.B, a.D, a.H, a.W = B, D, H, W
     a.Cin, a.Cpitch = Cin, Cpitch
@@ -112,6 +113,7 @@ def conv_gemm(A, Wt, *, B, D, H, W, Cin, N, taps, bias=None, rowvec=None, res_f3
     a.ldo = ldo; a.act = ACT[act]; a.out_scale = out_scale; a.BN = BN
     a.col_stats = ptr(col_stats)
     a.ksplit = ksplit
+    a.cta_pair = cta_pair
     if in_stride:
         for j in range(3):
             a.in_stride[j] = in_stride[j]

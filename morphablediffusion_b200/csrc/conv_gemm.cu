@@ -177,19 +177,6 @@ int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
     if (r != CUDA_SUCCESS) return set_error("cuTensorMapEncodeTiled(A) failed: %d (W=%d H=%d D=%d B=%d C=%d)", (int)r,
                                             a.W, a.H, a.D, a.B, a.Cin);
   }
-  {
-    const cuuint64_t Ktot = (cuuint64_t)a.ntaps * a.Cin;
-    cuuint64_t dims[2] = {Ktot, (cuuint64_t)a.N};
-    cuuint64_t strides[1] = {Ktot * 2};
-    cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)BN};
-    cuuint32_t es[2] = {1, 1};
-    CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(a.Wt), dims, strides, box,
-                     es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return set_error("cuTensorMapEncodeTiled(B) failed: %d (K=%llu N=%d)", (int)r,
-                                            (unsigned long long)Ktot, a.N);
-  }
-
   // ---- split-K for tile-starved problems (few output tiles, long K loop): fills the machine and multiplies the
   // bytes in flight of what is otherwise a weight-streaming loop on a handful of SMs
   p.ksplit = 1;
@@ -212,6 +199,39 @@ int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
     p.split_ws = ws;
     p.split_cnt = cnt;
   }
+  // ---- CTA pairs (cta_group::2) for tile-rich problems on the two widest tiles: half the L2 bytes per FLOP
+  // Measured on the 16-view step: +3..5 % on the long-K 3x3 convolutions in isolation, neutral to slightly negative on
+  // short-K GEMMs (their time is in the epilogue) and neutral on the whole step (72.97 vs 73.16 steps/s), i.e. the
+  // single-CTA tiles are not L2-bound but shared-memory-bandwidth bound (TMA writes + operand reads of 128 + BN rows
+  // per K block against 128 B/clk), which pairs only relieve by a quarter.  So pairs are opt-in: args.cta_pair = 1, or
+  // MD_CG2=1 (from 40 K blocks up) / MD_CG2=2 (whenever eligible).
+  static const int cg2_env = getenv("MD_CG2") ? atoi(getenv("MD_CG2")) : 0;
+  const int cg2_mode = a.cta_pair != 0 ? (a.cta_pair > 0 ? 2 : 0) : cg2_env;
+  const int cg2_min_kblocks = cg2_mode >= 2 ? 1 : 40;
+  p.m_pairs = (p.m_tiles + 1) / 2;
+  int cg2_pairs = 0;
+  if (cg2_mode > 0 && p.ksplit == 1 && (BN == 160 || BN == 256) && p.m_tiles >= 2 && kblocks_all >= cg2_min_kblocks) {
+    int resident = 0;
+    const int rc = (BN == 160) ? launch_conv_gemm_cg2_bn160(tmA, tmA, p, 0, stream, &resident)
+                               : launch_conv_gemm_cg2_bn256(tmA, tmA, p, 0, stream, &resident);
+    if (rc == 0 && resident > 0 && p.m_pairs * p.n_tiles >= resident) {
+      p.cg2 = 1;
+      cg2_pairs = std::min(p.m_pairs * p.n_tiles, resident);
+    }
+  }
+  {
+    const cuuint64_t Ktot = (cuuint64_t)a.ntaps * a.Cin;
+    cuuint64_t dims[2] = {Ktot, (cuuint64_t)a.N};
+    cuuint64_t strides[1] = {Ktot * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)(p.cg2 ? BN / 2 : BN)};  // a pair CTA stages half the rows
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(a.Wt), dims, strides, box,
+                     es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error("cuTensorMapEncodeTiled(B) failed: %d (K=%llu N=%d)", (int)r,
+                                            (unsigned long long)Ktot, a.N);
+  }
+
 #ifdef MD_KPROF
   if (!g_kprof_buf) {
     cudaMalloc(&g_kprof_buf, sizeof(unsigned long long) * 160 * 32);
@@ -224,14 +244,17 @@ int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
   p.fd_nxb = make_fastdiv(p.nxb);
   p.fd_nyb = make_fastdiv(p.nyb);
   p.fd_nzb = make_fastdiv(p.nzb);
-  const int total = p.m_tiles * p.n_tiles * p.ksplit;
-  const int grid = std::min(total, num_sms());
-  p.contig = (p.n_tiles == 1 && p.ksplit == 1 && total > 2 * grid) ? 1 : 0;
+  const int total = p.cg2 ? p.m_pairs * p.n_tiles : p.m_tiles * p.n_tiles * p.ksplit;
+  const int grid = p.cg2 ? 2 * cg2_pairs : std::min(total, num_sms());
+  p.contig = (p.n_tiles == 1 && p.ksplit == 1 && total > 2 * (p.cg2 ? cg2_pairs : grid)) ? 1 : 0;
   static const bool trace = getenv("MD_TRACE") != nullptr;
   if (trace)
-    fprintf(stderr, "conv_gemm B=%d D=%d H=%d W=%d Cin=%d taps=%d N=%d BN=%d tiles=%dx%d ks=%d act=%d f32=%d bf16=%d res=%d\n",
-            a.B, a.D, a.H, a.W, a.Cin, a.ntaps, a.N, BN, p.m_tiles, p.n_tiles, p.ksplit, a.act, a.out_f32 != nullptr,
+    fprintf(stderr, "conv_gemm B=%d D=%d H=%d W=%d Cin=%d taps=%d N=%d BN=%d tiles=%dx%d ks=%d cg2=%d act=%d f32=%d bf16=%d res=%d\n",
+            a.B, a.D, a.H, a.W, a.Cin, a.ntaps, a.N, BN, p.m_tiles, p.n_tiles, p.ksplit, p.cg2, a.act, a.out_f32 != nullptr,
             a.out_bf16 != nullptr, a.res_f32 != nullptr || a.res_bf16 != nullptr);
+  if (p.cg2)
+    return (BN == 160) ? launch_conv_gemm_cg2_bn160(tmA, tmB, p, grid, stream, nullptr)
+                       : launch_conv_gemm_cg2_bn256(tmA, tmB, p, grid, stream, nullptr);
   switch (BN) {
     case 64:  return launch_conv_gemm_bn64(tmA, tmB, p, grid, stream);
     case 128: return launch_conv_gemm_bn128(tmA, tmB, p, grid, stream);

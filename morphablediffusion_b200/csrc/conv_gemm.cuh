@@ -88,6 +88,8 @@ struct ConvGemmParams {
   int* split_cnt;   // [tiles][EPI_WARPS] arrival counters (zero on entry, reset by the last arrival)
   int isx, isy, isz; // input coordinate = output-tile coordinate * is + tap offset (strided convolution via TMA element strides)
   FastDiv fd_ksplit, fd_ntiles, fd_nxb, fd_nyb, fd_nzb;
+  int cg2;      // 1: CTA-pair kernel; a work item is an (M-tile pair, N tile) and this CTA owns M tile 2*pair + rank
+  int m_pairs;  // ceil(m_tiles / 2)
 #ifdef MD_KPROF
   unsigned long long* kprof;  // [160 CTAs][32 slots] phase stamps
 #endif
@@ -102,6 +104,8 @@ __device__ __forceinline__ TileCoord decode_item(const ConvGemmParams& p, int it
   fdivmod(item, p.fd_ksplit, t.tile, t.sp);
   int m;
   fdivmod(t.tile, p.fd_ntiles, m, t.n_tile);
+  if (p.cg2) m = 2 * m + static_cast<int>(cluster_ctarank());  // an odd tile count leaves the last pair's second
+                                                              // tile out of range: zero-filled loads, masked stores
   int m2;
   fdivmod(m, p.fd_nxb, m2, t.xb);
   fdivmod(m2, p.fd_nyb, m, t.yb);
@@ -327,16 +331,15 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void* gptr, uint32_t byte
 }
 
 // Epilogue warps: loop over this CTA's work items (same schedule as the producer / MMA warps).
-template <int BN, int STAGES, int RES, bool RV, bool STATS, int ACTV>
+template <int BN, int STAGES, int RES, bool RV, bool STATS, int ACTV, int STAGE_OFFSET>
 __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, uint8_t* smem, uint64_t* tmem_full,
                                               uint64_t* tmem_empty, uint32_t tmem_base, int warp, int lane,
                                               int tile_begin, int tile_end, int tile_step) {
-  using S = ConvGemmSmem<BN, STAGES>;
   const int ew = warp - 2;
   const int q = warp & 3;        // TMEM lane quarter this warp may read
   const int c_begin = ew >> 2;   // this warp owns chunks c_begin, c_begin + 4, ...
   const int r = q * 32 + lane;
-  float* stage = reinterpret_cast<float*>(smem + S::kStageOffset) + ew * 512;
+  float* stage = reinterpret_cast<float*>(smem + STAGE_OFFSET) + ew * 512;
   const int out_cols_t = (ACTV == 2) ? BN / 2 : BN;
   const int n_limit_t = (ACTV == 2) ? p.N / 2 : p.N;
   constexpr int NCH = (BN / kChunk + kCStride - 1) / kCStride;  // chunks one warp owns per tile
@@ -471,7 +474,10 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, uint8_t* 
       epilogue_tile<BN, RES, RV, NCH, STATS, ACTV>(p, taddr, stage, lane, n_tile, ri, c_begin, st1, st2, kpf);
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(&tmem_empty[a]);
+    if (lane == 0) {
+      if (p.cg2) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[a]), 0));  // the pair leader issues the MMAs
+      else mbar_arrive(&tmem_empty[a]);
+    }
     KPROF(9, lt == 0 && warp == 2 && lane == 0);
     KPROF(18, lt == kKprofTile && warp == 2 && lane == 0);
     KPROF(10, warp == 2 && lane == 0);
@@ -602,8 +608,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else {
     // ===================== epilogue (warps 2 .. 17) =====================
-    epilogue_loop<BN, STAGES, RES, RV, STATS, ACTV>(p, smem, tmem_full, tmem_empty, tmem_base, warp, lane, tile_begin,
-                                                   tile_end, tile_step);
+    epilogue_loop<BN, STAGES, RES, RV, STATS, ACTV, S::kStageOffset>(p, smem, tmem_full, tmem_empty, tmem_base, warp, lane,
+                                                                    tile_begin, tile_end, tile_step);
   }
 
   tc_fence_before();
@@ -613,6 +619,140 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
     KPROF(12, lane == 0);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ CTA-pair variant
+// Two CTAs of a cluster compute one 256 x BN tile with cta_group::2 MMAs: each CTA stages its own 128 A rows and HALF
+// of the B rows (BN/2 weight rows), so a pair pulls (256 + BN) operand rows from L2 for 256 x BN outputs: twice the
+// FLOP per L2 byte of the single-CTA kernel, which is what that kernel is bound by.  The leader (cluster rank 0) issues
+// the MMAs; its full barrier counts the TMA bytes of both CTAs; commits are multicast to both CTAs' barriers; both CTAs
+// run the ordinary epilogue on their own 128 accumulator rows and release the accumulator on the leader's barrier.
+template <int BN, int STAGES>
+struct ConvGemmSmem2 {
+  static constexpr int kABytes = kBlockM * kBlockK * 2;        // 16 KB: this CTA's 128 rows
+  static constexpr int kBBytes = (BN / 2) * kBlockK * 2;       // this CTA's half of the B tile
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStageOffset = STAGES * kStageBytes;
+  static constexpr int kBarOffset = kStageOffset + kEpiWarps * 2048;
+  static constexpr int kTotal = kBarOffset + 256;
+};
+
+template <int BN, int STAGES, int RES, bool RV, bool STATS, int ACTV>
+__global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1)
+conv_gemm_cg2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     const ConvGemmParams p) {
+  using S = ConvGemmSmem2<BN, STAGES>;
+  static_assert(S::kBBytes % 1024 == 0, "B half tile must keep the 1024-byte swizzle alignment");
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kBarOffset);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  constexpr uint32_t kTmemCols = (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);   // leader: one arrive.expect_tx per phase, bytes of both CTAs
+      mbar_init(&empty_bar[i], 1);  // one multicast commit per phase
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 2 * kEpiWarps);  // epilogue warps of both CTAs (used on the leader only)
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_cg2(tmem_slot, kTmemCols);
+    tmem_relinquish_cg2();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // both CTAs' barriers exist before any remote arrive / multicast commit / pair TMA
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_grid_sync();
+
+  const int npairs = static_cast<int>(gridDim.x) >> 1;
+  const int pair = static_cast<int>(blockIdx.x) >> 1;
+  const int total_tiles = p.m_pairs * p.n_tiles;  // work items: (M-tile pair, N tile); no split-K in this kernel
+  const int kblocks = p.ntaps * p.kblocks_per_tap;
+  const int per_pair = (total_tiles + npairs - 1) / npairs;
+  const int tile_begin = p.contig ? pair * per_pair : pair;
+  const int tile_end = p.contig ? min(total_tiles, tile_begin + per_pair) : total_tiles;
+  const int tile_step = p.contig ? 1 : npairs;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int it = 0;
+      for (int item = tile_begin; item < tile_end; item += tile_step) {
+        const TileCoord tc = decode_item(p, item);
+        const int x0 = tc.xb * p.bw * p.isx, y0 = tc.yb * p.bh * p.isy, z0 = tc.zb * p.bd * p.isz, b0 = tc.bblk * p.bb;
+        const int n0 = tc.n_tile * BN + static_cast<int>(rank) * (BN / 2);
+        int tap = 0, kc = 0;
+        for (int kb = 0; kb < kblocks; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sa = smem + s * S::kStageBytes;
+          uint8_t* sb = sa + S::kABytes;
+          if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * S::kStageBytes);
+          const uint32_t lead_bar = mapa_shared(smem_u32(&full_bar[s]), 0);
+          tma_load_5d_cg2(sa, &tmA, lead_bar, kc * kBlockK, x0 + p.tdx[tap], y0 + p.tdy[tap], z0 + p.tdz[tap], b0);
+          tma_load_2d_cg2(sb, &tmB, lead_bar, kb * kBlockK, n0);
+          if (++kc == p.kblocks_per_tap) { kc = 0; ++tap; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (pair leader only) =====================
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(2 * kBlockM, BN);
+      int it = 0;
+      int lt = 0;
+      for (int item = tile_begin; item < tile_end; item += tile_step, ++lt) {
+        const int a = lt & 1;
+        const uint32_t aph = (lt >> 1) & 1;
+        mbar_wait(&tmem_empty[a], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + a * BN;
+        for (int kb = 0; kb < kblocks; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * S::kStageBytes);
+          const uint32_t sb = sa + S::kABytes;
+          const uint64_t da = make_sw128_kmajor_desc(sa);
+          const uint64_t db = make_sw128_kmajor_desc(sb);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k)
+            tc_mma_f16_cg2(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          tc_commit_cg2(&empty_bar[s], 3);
+        }
+        tc_commit_cg2(&tmem_full[a], 3);
+      }
+    }
+  } else {
+    // ===================== epilogue (both CTAs, their own 128 rows) =====================
+    epilogue_loop<BN, STAGES, RES, RV, STATS, ACTV, S::kStageOffset>(p, smem, tmem_full, tmem_empty, tmem_base, warp, lane,
+                                                                    tile_begin, tile_end, tile_step);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the leader's MMAs read the peer's shared memory and both CTAs' barriers are still in use
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_cg2(tmem_base, kTmemCols);
   }
 }
 

@@ -213,6 +213,39 @@ def test_gemm_linearity_at_full_size(nat):
     assert rel(outs[2], outs[0] + outs[1]) < 1e-5
 
 
+def test_conv_gemm_cta_pair_kernel(nat):
+    """cta_group::2 kernels (two CTAs of a cluster on one 256-row tile, each staging half of the weight rows):
+    a linear layer with an odd number of 128-row tiles (the last pair's second tile is out of range), per-sample
+    vector + SiLU + residual, and a 3x3 convolution with fused statistics; the result must agree with the single-CTA path."""
+    torch.manual_seed(21)
+    Bn, rows, K, N = 151, 128, 320, 320
+    M = Bn * rows
+    A = bf(torch.randn(M, K, device="cuda"))
+    Wt = bf(torch.randn(N, K, device="cuda") / K ** 0.5)
+    bias, rv, res = torch.randn(N, device="cuda"), torch.randn(Bn, N, device="cuda"), torch.randn(M, N, device="cuda")
+    outs = []
+    for pair in (1, -1):
+        o = torch.zeros(M, N, device="cuda")
+        nat.conv_gemm(A, Wt, B=Bn, D=1, H=1, W=rows, Cin=K, N=N, taps=[(0, 0, 0)], bias=bias, rowvec=rv, res_f32=res,
+                      out_f32=o, act="silu", cta_pair=pair)
+        outs.append(o)
+    ref = F.silu(A.float() @ Wt.float().t() + bias + rv.repeat_interleave(rows, 0)) + res
+    assert rel(outs[0], ref) < 1e-5 and rel(outs[0], outs[1]) < 1e-6
+    # conv3x3 64 -> 320 on 32 samples of 32x32 with GroupNorm statistics
+    x = bf(torch.randn(32, 64, 32, 32, device="cuda"))
+    w = bf(torch.randn(320, 64, 3, 3, device="cuda") / (9 * 64) ** 0.5)
+    Ax = x.permute(0, 2, 3, 1).contiguous()
+    Wp = w.permute(0, 2, 3, 1).reshape(320, 9 * 64).contiguous()
+    taps = [(dx, dy, 0) for dy in (-1, 0, 1) for dx in (-1, 0, 1)]
+    o = torch.zeros(32 * 1024, 320, device="cuda")
+    st = torch.zeros(32, 320, 2, device="cuda")
+    nat.conv_gemm(Ax, Wp, B=32, D=1, H=32, W=32, Cin=64, N=320, taps=taps, out_f32=o, col_stats=st, cta_pair=1)
+    refc = F.conv2d(x.float(), w.float(), None, padding=1).permute(0, 2, 3, 1).reshape(-1, 320)
+    assert rel(o, refc) < 1e-5
+    sref = torch.stack([refc.view(32, 1024, 320).sum(1), (refc.view(32, 1024, 320) ** 2).sum(1)], -1)
+    assert rel(st, sref) < 1e-4
+
+
 # ----------------------------------------------------------------------------- norm / attention kernels
 @pytest.mark.parametrize("B,rows,C,G,act,bf16_in", [(3, 1024, 320, 32, 1, False), (2, 256, 1920, 32, 1, False),
                                                     (2, 16, 1280, 32, 0, False), (2, 6144, 128, 8, 1, True),
