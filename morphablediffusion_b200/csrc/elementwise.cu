@@ -242,6 +242,85 @@ __global__ void gn_apply_fused_kernel(const T0* __restrict__ x0, int C0, const T
               b, rows, r0, min(rows, r0 + rows_per_cta), c, rsub, R, act);
 }
 
+// Small tensors (the 4x4 UNet level: 16 rows per sample) have no statistics from a GEMM epilogue (a 128-row tile spans
+// several samples there) and were three latency-bound launches (column pass, finalize, apply).  One CTA per (sample,
+// group) keeps the group's rows x channels-per-group values in registers: mean, then the centred sum of squares, then
+// normalise + activation, all in one launch.
+constexpr int kGnSmallThreads = 128;
+constexpr int kGnSmallPerThread = 4;  // float4 per thread: up to 128 * 4 * 4 = 2048 values per (sample, group)
+template <typename T0, typename T1>
+__global__ void __launch_bounds__(kGnSmallThreads)
+gn_small_kernel(const T0* __restrict__ x0, int C0, const T1* __restrict__ x1, int C1, const float* __restrict__ gamma,
+                const float* __restrict__ beta, int G, float eps, __nv_bfloat16* __restrict__ out,
+                __nv_bfloat16* __restrict__ raw, int rows, int act) {
+  pdl_grid_sync();
+  __shared__ float red[kGnSmallThreads / 32];
+  __shared__ float bcast;
+  const int C = C0 + C1;
+  const int cpg = C / G, q4 = cpg >> 2;  // float4 per row of the group
+  const int g = blockIdx.x, b = blockIdx.y;
+  const int n4 = rows * q4;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float4 v[kGnSmallPerThread];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < kGnSmallPerThread; ++k) {
+    const int e = threadIdx.x + k * kGnSmallThreads;
+    v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (e < n4) {
+      const int r = e / q4, c = g * cpg + (e - r * q4) * 4;
+      const size_t row = static_cast<size_t>(b) * rows + r;
+      v[k] = (c < C0) ? load4(x0 + row * C0 + c) : load4(x1 + row * C1 + (c - C0));
+      s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+    }
+  }
+  auto block_sum = [&](float val) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) val += __shfl_xor_sync(0xffffffff, val, o);
+    if (lane == 0) red[warp] = val;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+      for (int w = 0; w < kGnSmallThreads / 32; ++w) t += red[w];
+      bcast = t;
+    }
+    __syncthreads();
+    const float r = bcast;
+    __syncthreads();
+    return r;
+  };
+  const float inv_n = 1.f / static_cast<float>(rows * cpg);
+  const float mean = block_sum(s) * inv_n;
+  float q = 0.f;
+#pragma unroll
+  for (int k = 0; k < kGnSmallPerThread; ++k) {
+    const int e = threadIdx.x + k * kGnSmallThreads;
+    if (e < n4) {
+      const float dx = v[k].x - mean, dy = v[k].y - mean, dz = v[k].z - mean, dw = v[k].w - mean;
+      q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+    }
+  }
+  const float rstd = rsqrtf(block_sum(q) * inv_n + eps);
+#pragma unroll
+  for (int k = 0; k < kGnSmallPerThread; ++k) {
+    const int e = threadIdx.x + k * kGnSmallThreads;
+    if (e < n4) {
+      const int r = e / q4, c = g * cpg + (e - r * q4) * 4;
+      const size_t row = static_cast<size_t>(b) * rows + r;
+      if (raw) store4(raw + row * C + c, v[k]);
+      const float4 g4 = load4(gamma + c), b4 = load4(beta + c);
+      float4 y = make_float4((v[k].x - mean) * rstd * g4.x + b4.x, (v[k].y - mean) * rstd * g4.y + b4.y,
+                             (v[k].z - mean) * rstd * g4.z + b4.z, (v[k].w - mean) * rstd * g4.w + b4.w);
+      if (act == ACT_SILU) {
+        y.x = silu_f(y.x); y.y = silu_f(y.y); y.z = silu_f(y.z); y.w = silu_f(y.w);
+      } else if (act == ACT_RELU) {
+        y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f);
+      }
+      store4(out + row * C + c, y);
+    }
+  }
+}
+
 template <typename T0, typename T1>
 static int group_norm_impl(const GroupNormArgs& a, cudaStream_t st) {
   const int C = a.C0 + a.C1;
@@ -249,6 +328,17 @@ static int group_norm_impl(const GroupNormArgs& a, cudaStream_t st) {
   if (C % a.groups) return set_error("group_norm: C=%d not divisible by groups=%d", C, a.groups);
   const int CQ = C / 4;
   if (CQ > 1024) return set_error("group_norm: C=%d too large", C);
+  {  // single-launch path for small (sample, group) slabs without producer statistics
+    const int cpg = C / a.groups;
+    const bool aligned = !((reinterpret_cast<uintptr_t>(a.gamma) | reinterpret_cast<uintptr_t>(a.beta)) & 15);
+    if (!a.stats0 && a.out && !a.addvec && cpg % 4 == 0 && aligned &&
+        static_cast<long long>(a.rows) * cpg <= kGnSmallThreads * kGnSmallPerThread * 4) {
+      launch_pdl(gn_small_kernel<T0, T1>, dim3(a.groups, a.B), dim3(kGnSmallThreads), 0, st, static_cast<const T0*>(a.x0), a.C0,
+                 static_cast<const T1*>(a.x1), a.C1, a.gamma, a.beta, a.groups, a.eps, static_cast<__nv_bfloat16*>(a.out),
+                 static_cast<__nv_bfloat16*>(a.raw_out), a.rows, a.act);
+      return check_launch("gn_small");
+    }
+  }
   int R = std::max(1, std::min(8, 256 / CQ));
   const int threads = CQ * R;
   float* st0 = const_cast<float*>(a.stats0);
