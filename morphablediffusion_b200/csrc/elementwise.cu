@@ -357,14 +357,16 @@ static int group_norm_impl(const GroupNormArgs& a, cudaStream_t st) {
   } else if (a.C1 > 0 && !a.stats1) {
     return set_error("group_norm: statistics for the second source are missing");
   }
-  // row split of the apply pass: CTAs of up to 512 threads, ~4 per SM in total (every CTA first reduces the group
-  // statistics of its sample, so fewer and fatter CTAs amortise that), at least 4 rows per row phase
-  const int RA = std::max(1, std::min(8, 512 / CQ));
-  const int apply_target = num_sms() * 4;
-  int apply_rows = std::max(RA * 4, static_cast<int>((static_cast<long long>(a.rows) * a.B + apply_target - 1) / apply_target));
+  // row split of the apply pass: CTAs of ~512 threads (channel quads x up to 32 row phases), exactly one wave of them
+  // (2 per SM at the kernel's ~54 registers; every CTA first reduces the group statistics of its sample, so fewer and
+  // fatter CTAs amortise that, and a second partial wave would double the time of these 10-30 us kernels)
+  const int RA = std::max(1, std::min(32, 512 / CQ));
+  const int apply_threads = ((CQ * RA + 31) / 32) * 32;
+  const int apply_target = num_sms() * (apply_threads > 256 ? 2 : 4);
+  const int gx_max = std::max(1, apply_target / a.B);
+  int apply_rows = std::max(RA, (a.rows + gx_max - 1) / gx_max);
   apply_rows = std::min(apply_rows, a.rows);
   const dim3 apply_grid((a.rows + apply_rows - 1) / apply_rows, a.B);
-  const int apply_threads = ((CQ * RA + 31) / 32) * 32;
   const bool vec_ok = !((reinterpret_cast<uintptr_t>(a.gamma) | reinterpret_cast<uintptr_t>(a.beta) |
                          reinterpret_cast<uintptr_t>(a.addvec)) & 15) && (a.addvec_ld % 4 == 0);
   if (a.out && a.stats0 && !zero_after && vec_ok) {  // statistics from GEMM epilogues: finalize + apply in one kernel
