@@ -239,6 +239,8 @@ int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
   }
   p.kprof = g_kprof_buf;
 #endif
+  static const int gemm_dbg = getenv("MD_GEMM_DBG") ? atoi(getenv("MD_GEMM_DBG")) : 0;
+  p.dbg = gemm_dbg;
   p.fd_ksplit = make_fastdiv(p.ksplit);
   p.fd_ntiles = make_fastdiv(p.n_tiles);
   p.fd_nxb = make_fastdiv(p.nxb);

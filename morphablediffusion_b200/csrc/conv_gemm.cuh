@@ -88,6 +88,8 @@ struct ConvGemmParams {
   int* split_cnt;   // [tiles][EPI_WARPS] arrival counters (zero on entry, reset by the last arrival)
   int isx, isy, isz; // input coordinate = output-tile coordinate * is + tap offset (strided convolution via TMA element strides)
   FastDiv fd_ksplit, fd_ntiles, fd_nxb, fd_nyb, fd_nzb;
+  int dbg;      // development only (MD_GEMM_DBG): 1 = skip the epilogue work, 2 = skip the MMAs, 4 = skip the TMA loads;
+                // results are garbage, the timings isolate which pipeline stage bounds a shape
   int cg2;      // 1: CTA-pair kernel; a work item is an (M-tile pair, N tile) and this CTA owns M tile 2*pair + rank
   int m_pairs;  // ceil(m_tiles / 2)
 #ifdef MD_KPROF
@@ -470,7 +472,7 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, uint8_t* 
 #else
     constexpr bool kpf = false;
 #endif
-    if (run_epilogue)
+    if (run_epilogue && !(p.dbg & 1))
       epilogue_tile<BN, RES, RV, NCH, STATS, ACTV>(p, taddr, stage, lane, n_tile, ri, c_begin, st1, st2, kpf);
     tc_fence_before();
     __syncwarp();
@@ -560,9 +562,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           KPROF(20, plt == kKprofTile && kb == kb1 - 1);
           uint8_t* sa = smem + s * S::kStageBytes;
           uint8_t* sb = sa + S::kABytes;
-          mbar_expect_tx(&full_bar[s], S::kStageBytes);
-          tma_load_5d(sa, &tmA, &full_bar[s], kc * kBlockK, x0 + p.tdx[tap], y0 + p.tdy[tap], z0 + p.tdz[tap], b0);
-          tma_load_2d(sb, &tmB, &full_bar[s], kb * kBlockK, n0);
+          if (p.dbg & 4) {
+            mbar_arrive(&full_bar[s]);
+          } else {
+            mbar_expect_tx(&full_bar[s], S::kStageBytes);
+            tma_load_5d(sa, &tmA, &full_bar[s], kc * kBlockK, x0 + p.tdx[tap], y0 + p.tdy[tap], z0 + p.tdz[tap], b0);
+            tma_load_2d(sb, &tmB, &full_bar[s], kb * kBlockK, n0);
+          }
           KPROF(3, it == 0);
           if (++kc == p.kblocks_per_tap) { kc = 0; ++tap; }
         }
@@ -595,10 +601,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint32_t sb = sa + S::kABytes;
           const uint64_t da = make_sw128_kmajor_desc(sa);
           const uint64_t db = make_sw128_kmajor_desc(sb);
+          if (!(p.dbg & 2)) {
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            // advance 16 bf16 = 32 B inside the 128-B swizzle atom: +2 in the (addr >> 4) field
-            tc_mma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < kBlockK / 16; ++k) {
+              // advance 16 bf16 = 32 B inside the 128-B swizzle atom: +2 in the (addr >> 4) field
+              tc_mma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
           }
           tc_commit(&empty_bar[s]);
         }
