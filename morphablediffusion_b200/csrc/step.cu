@@ -154,19 +154,22 @@ static int denoise_step_impl(Ctx& c, float* x_local, const float* x_input, const
   if (A.failed) return set_error("workspace exhausted (step)");
   (void)tval;
   c.vsum_ptr = vsum;
+  // Conditioning branch (target-view encoder -> vertex features -> sparse conv -> spatial volume -> frustum nets) and
+  // the UNet's input half are independent: with a single view chunk the former runs on a second stream (own arena, own
+  // split-K workspace) and the UNet joins it right before its first depth transformer.  On one rank the whole branch
+  // moves over (the encoder is one CTA per view: 0.25 ms during which the UNet would otherwise wait); with several
+  // ranks the part before the cross-rank exchange stays on the main stream (it is captured as its own graph).
+  const bool overlap = c.stream2 != nullptr && sb.n_local <= chunk && getenv("MD_NO_OVERLAP") == nullptr;
+  const bool vf_on_side = overlap && phase == 0 && c.world <= 1;
   if (phase != 2) {
     launch_pdl(fill_from_kernel, dim3((maxB + 63) / 64), dim3(64), 0, st, d_t, c.d_step, maxB);  // timestep of this index (d_step[0])
     MD_CHECK(check_launch("fill"));
     MD_CHECK(embed_time(c, d_t, t_embed, st));
-    MD_CHECK(vertex_feature_sum(c, x_local, t_embed, vsum, st));
+    if (!vf_on_side) MD_CHECK(vertex_feature_sum(c, x_local, t_embed, vsum, st));
   }
   if (phase == 0) MD_CHECK(allreduce_vsum(c, st));
   if (phase == 1) return 0;
 
-  // Conditioning branch (sparse conv -> spatial volume -> frustum nets) and the UNet's input half are independent:
-  // with a single view chunk the former runs on a second stream (own arena, own split-K workspace) and the UNet joins
-  // it right before its first depth transformer.
-  const bool overlap = c.stream2 != nullptr && sb.n_local <= chunk && getenv("MD_NO_OVERLAP") == nullptr;
   const size_t m = A.mark();
   for (int lv0 = 0; lv0 < sb.n_local; lv0 += chunk) {
     const int T = std::min(chunk, sb.n_local - lv0);
@@ -180,7 +183,8 @@ static int denoise_step_impl(Ctx& c, float* x_local, const float* x_input, const
       c.arena.failed = false;
       set_split_workspace_alt(c.split_ws2, static_cast<size_t>(48) << 20, c.split_cnt2, 1 << 15);
       use_split_workspace_alt(true);
-      int rc = spatial_volume_from_vsum(c, vsum, vol, c.stream2);
+      int rc = vf_on_side ? vertex_feature_sum(c, x_local, t_embed, vsum, c.stream2) : 0;
+      if (rc == 0) rc = spatial_volume_from_vsum(c, vsum, vol, c.stream2);
       if (rc == 0) rc = frustum_levels(c, vol, lv0, T, t_embed, T, levels, c.stream2);
       use_split_workspace_alt(false);
       std::swap(c.arena, c.arena2);
@@ -526,16 +530,23 @@ int md_op_group_norm_stats(const void* x, int x_is_bf16, int B, int rows, int C,
                            void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (!stats || !out_bf16) return set_error("md_op_group_norm_stats: stats and out are required");
-  float* ws = nullptr;
-  MD_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws), sizeof(float) * 2 * B * C, st));
+  // scale/shift scratch for the (rare) unfused fallback: process-wide, grow-only, so that the call itself launches
+  // nothing but the GroupNorm kernels (bench.py times it)
+  static float* ws = nullptr;
+  static size_t ws_floats = 0;
+  const size_t need = static_cast<size_t>(2) * B * C;
+  if (need > ws_floats) {
+    if (ws) cudaFree(ws);
+    ws = nullptr; ws_floats = 0;
+    MD_CUDA(cudaMalloc(reinterpret_cast<void**>(&ws), need * sizeof(float)));
+    ws_floats = need;
+  }
   GroupNormArgs g;
   memset(&g, 0, sizeof(g));
   g.x0 = x; g.C0 = C; g.x0_bf16 = x_is_bf16; g.B = B; g.rows = rows; g.groups = groups; g.eps = eps;
   g.gamma = gamma; g.beta = beta; g.addvec = addvec; g.addvec_ld = C; g.stats0 = stats; g.scale_shift = ws;
   g.out = out_bf16; g.act = act;
-  const int rc = launch_group_norm(g, st);
-  cudaFreeAsync(ws, st);
-  return rc;
+  return launch_group_norm(g, st);
 }
 
 int md_op_layer_norm(float* x, const float* gamma, const float* beta, void* out_bf16, long long rows, int C, float eps,
