@@ -232,7 +232,7 @@ int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
                                             (unsigned long long)Ktot, a.N);
   }
 
-  // ---- experimental TMA-store epilogue (MD_EPI_TMA=1): one output, no fused statistics, no bf16 residual, no GEGLU,
+  // ---- experimental TMA-store epilogue (MD_EPI_TMA=1): one output, no fused statistics, no bf16 residual,
   // no split-K, plain output geometry; the output leaves as 16-column x 32-row boxes of the per-warp staging tile
   CUtensorMap tmO = tmA;
   {
@@ -241,7 +241,7 @@ int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
     const bool plain = p.osx == 1 && p.osy == 1 && p.osz == 1 && p.opx == 0 && p.opy == 0 && p.opz == 0 && p.OW == p.W &&
                        p.OH == p.H && p.OD == p.D;
     void* optr = a.out_f32 ? static_cast<void*>(a.out_f32) : a.out_bf16;
-    if (epi_tma_on && one_out && plain && !a.col_stats && !a.res_bf16 && a.act != ACT_GEGLU && p.ksplit == 1 &&
+    if (epi_tma_on && one_out && plain && !a.col_stats && !a.res_bf16 && p.ksplit == 1 &&
         !(reinterpret_cast<uintptr_t>(optr) & 15)) {
       // a lane quarter's 32 rows inside the tile box (x fastest): sub-box dims and the origin of every quarter
       int qd[4], bd4[4] = {p.bw, p.bh, p.bd, p.bb}, rem = 32;

@@ -339,17 +339,42 @@ template <int BN, int RES, bool RV, int ACTV>
 __device__ __forceinline__ void epilogue_tile_tma(const ConvGemmParams& p, const CUtensorMap* tmO, uint32_t taddr,
                                                   float* stage, int lane, int n_tile, long long orow, int bv,
                                                   int c_begin, int x0, int y0, int z0, int b0) {
-  static_assert(ACTV != 2, "the GEGLU epilogue keeps the coalesced path");
-  const int n_out0 = n_tile * BN;
+  constexpr bool geglu = (ACTV == 2);
+  constexpr int HALF = BN / 2;
+  constexpr int out_cols = geglu ? HALF : BN;
+  const int n_limit = geglu ? p.N / 2 : p.N;
+  const int n_out0 = n_tile * out_cols;
   const bool f32out = p.out_f32 != nullptr;
   const bool valid = bv >= 0;
   const long long ro = valid ? orow : 0;
   const float* rvp = RV ? p.rowvec + static_cast<long long>(valid ? bv : 0) * p.rowvec_ld : nullptr;
   const bool scaled = p.out_scale != 1.f;
 #pragma unroll 1
-  for (int c = c_begin; c < BN / kChunk; c += kCStride) {
+  for (int c = c_begin; c < out_cols / kChunk; c += kCStride) {
     const int col = n_out0 + c * kChunk;
-    if (col >= p.N) break;
+    if (col >= n_limit) break;
+    float o[16];
+    if constexpr (geglu) {
+      // value | gate halves of the accumulator tile; packed bias rows follow the same interleave
+      const int nb = n_tile * BN + c * kChunk;
+      float4 bv4[4], bg4[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        bv4[j] = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + nb) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        bg4[j] = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + nb + HALF) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      uint32_t v[16], g[16];
+      tmem_ld_32x16(taddr + c * kChunk, v);
+      tmem_ld_32x16(taddr + HALF + c * kChunk, g);
+      tc_wait_ld();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        o[4 * j + 0] = (__uint_as_float(v[4 * j + 0]) + bv4[j].x) * act_gelu(__uint_as_float(g[4 * j + 0]) + bg4[j].x);
+        o[4 * j + 1] = (__uint_as_float(v[4 * j + 1]) + bv4[j].y) * act_gelu(__uint_as_float(g[4 * j + 1]) + bg4[j].y);
+        o[4 * j + 2] = (__uint_as_float(v[4 * j + 2]) + bv4[j].z) * act_gelu(__uint_as_float(g[4 * j + 2]) + bg4[j].z);
+        o[4 * j + 3] = (__uint_as_float(v[4 * j + 3]) + bv4[j].w) * act_gelu(__uint_as_float(g[4 * j + 3]) + bg4[j].w);
+      }
+    } else {
     const bool full = col + kChunk <= p.N;  // a ragged last chunk reads bias / residual element-safe below
     float4 b4[4], r4[4], v4[4];
 #pragma unroll
@@ -362,7 +387,6 @@ __device__ __forceinline__ void epilogue_tile_tma(const ConvGemmParams& p, const
     uint32_t v[16];
     tmem_ld_32x16(taddr + c * kChunk, v);
     tc_wait_ld();
-    float o[16];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       float e[4] = {__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
@@ -382,6 +406,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const ConvGemmParams& p, const
         o[4 * j + t] = y;
       }
     }
+    }  // !geglu
     // the previous chunk's store must have finished reading the staging tile
     if (lane == 0) tma_store_wait_read();
     __syncwarp();
@@ -560,7 +585,7 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, const CUt
     constexpr bool kpf = false;
 #endif
     if (run_epilogue && !(p.dbg & 1)) {
-      if constexpr (!STATS && ACTV != 2 && RES != 2) {
+      if constexpr (!STATS && RES != 2) {
         if (p.epi_tma) {
           const int16_t* qo = p.qorg[q];
           epilogue_tile_tma<BN, RES, RV, ACTV>(p, tmO, taddr, stage, lane, n_tile, orow, bv, c_begin,
