@@ -237,11 +237,14 @@ int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
   CUtensorMap tmO = tmA;
   {
     static const bool epi_tma_on = getenv("MD_EPI_TMA") != nullptr && atoi(getenv("MD_EPI_TMA")) != 0;
+    // measured (r01y): -10..19 % on the bf16-out GEMMs without residual (qkv, GEGLU), +5..11 % on fp32-residual ones
+    // (their per-lane residual reads touch 32 sectors per request), so residual launches need MD_EPI_TMA=2
+    static const bool epi_tma_res = getenv("MD_EPI_TMA") != nullptr && atoi(getenv("MD_EPI_TMA")) >= 2;
     const bool one_out = (a.out_f32 != nullptr) != (a.out_bf16 != nullptr);
     const bool plain = p.osx == 1 && p.osy == 1 && p.osz == 1 && p.opx == 0 && p.opy == 0 && p.opz == 0 && p.OW == p.W &&
                        p.OH == p.H && p.OD == p.D;
     void* optr = a.out_f32 ? static_cast<void*>(a.out_f32) : a.out_bf16;
-    if (epi_tma_on && one_out && plain && !a.col_stats && !a.res_bf16 && p.ksplit == 1 &&
+    if (epi_tma_on && one_out && plain && !a.col_stats && !a.res_bf16 && (!a.res_f32 || epi_tma_res) && p.ksplit == 1 &&
         !(reinterpret_cast<uintptr_t>(optr) & 15)) {
       // a lane quarter's 32 rows inside the tile box (x fastest): sub-box dims and the origin of every quarter
       int qd[4], bd4[4] = {p.bw, p.bh, p.bd, p.bb}, rem = 32;
