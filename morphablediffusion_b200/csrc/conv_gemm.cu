@@ -212,8 +212,8 @@ int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
   int cg2_pairs = 0;
   if (cg2_mode > 0 && p.ksplit == 1 && (BN == 160 || BN == 256) && p.m_tiles >= 2 && kblocks_all >= cg2_min_kblocks) {
     int resident = 0;
-    const int rc = (BN == 160) ? launch_conv_gemm_cg2_bn160(tmA, tmA, p, 0, stream, &resident)
-                               : launch_conv_gemm_cg2_bn256(tmA, tmA, p, 0, stream, &resident);
+    const int rc = (BN == 160) ? launch_conv_gemm_cg2_bn160(tmA, tmA, tmA, p, 0, stream, &resident)
+                               : launch_conv_gemm_cg2_bn256(tmA, tmA, tmA, p, 0, stream, &resident);
     if (rc == 0 && resident > 0 && p.m_pairs * p.n_tiles >= resident) {
       p.cg2 = 1;
       cg2_pairs = std::min(p.m_pairs * p.n_tiles, resident);
@@ -232,6 +232,40 @@ int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
                                             (unsigned long long)Ktot, a.N);
   }
 
+  // ---- experimental TMA-store epilogue (MD_EPI_TMA=1): one output, no fused statistics, no bf16 residual,
+  // no split-K, plain output geometry; the output leaves as 16-column x 32-row boxes of the per-warp staging tile
+  CUtensorMap tmO = tmA;
+  {
+    static const bool epi_tma_on = getenv("MD_EPI_TMA") != nullptr && atoi(getenv("MD_EPI_TMA")) != 0;
+    // measured (r01y): -10..19 % on the bf16-out GEMMs without residual (qkv, GEGLU), +5..11 % on fp32-residual ones
+    // (their per-lane residual reads touch 32 sectors per request), so residual launches need MD_EPI_TMA=2
+    static const bool epi_tma_res = getenv("MD_EPI_TMA") != nullptr && atoi(getenv("MD_EPI_TMA")) >= 2;
+    const bool one_out = (a.out_f32 != nullptr) != (a.out_bf16 != nullptr);
+    const bool plain = p.osx == 1 && p.osy == 1 && p.osz == 1 && p.opx == 0 && p.opy == 0 && p.opz == 0 && p.OW == p.W &&
+                       p.OH == p.H && p.OD == p.D;
+    void* optr = a.out_f32 ? static_cast<void*>(a.out_f32) : a.out_bf16;
+    if (epi_tma_on && one_out && plain && !a.col_stats && !a.res_bf16 && (!a.res_f32 || epi_tma_res) && p.ksplit == 1 &&
+        !(reinterpret_cast<uintptr_t>(optr) & 15)) {
+      // a lane quarter's 32 rows inside the tile box (x fastest): sub-box dims and the origin of every quarter
+      int qd[4], bd4[4] = {p.bw, p.bh, p.bd, p.bb}, rem = 32;
+      for (int i = 0; i < 4; ++i) { qd[i] = std::min(bd4[i], rem); rem /= qd[i]; }
+      for (int qi = 0; qi < 4; ++qi) {
+        int r = qi * 32;
+        for (int i = 0; i < 4; ++i) { p.qorg[qi][i] = static_cast<int16_t>(r % bd4[i]); r /= bd4[i]; }
+      }
+      const size_t es = a.out_f32 ? 4 : 2;
+      cuuint64_t dims[5] = {(cuuint64_t)n_out, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.D, (cuuint64_t)a.B};
+      cuuint64_t strides[4] = {(cuuint64_t)p.ldo * es, (cuuint64_t)p.ldo * es * p.W, (cuuint64_t)p.ldo * es * p.W * p.H,
+                               (cuuint64_t)p.ldo * es * p.W * p.H * p.D};
+      cuuint32_t box[5] = {(cuuint32_t)kChunk, (cuuint32_t)qd[0], (cuuint32_t)qd[1], (cuuint32_t)qd[2], (cuuint32_t)qd[3]};
+      cuuint32_t es5[5] = {1, 1, 1, 1, 1};
+      CUresult r = enc(&tmO, a.out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, optr, dims,
+                       strides, box, es5, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       a.out_f32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r == CUDA_SUCCESS) p.epi_tma = 1;
+    }
+  }
 #ifdef MD_KPROF
   if (!g_kprof_buf) {
     cudaMalloc(&g_kprof_buf, sizeof(unsigned long long) * 160 * 32);
@@ -255,13 +289,13 @@ int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
             a.B, a.D, a.H, a.W, a.Cin, a.ntaps, a.N, BN, p.m_tiles, p.n_tiles, p.ksplit, p.cg2, a.act, a.out_f32 != nullptr,
             a.out_bf16 != nullptr, a.res_f32 != nullptr || a.res_bf16 != nullptr);
   if (p.cg2)
-    return (BN == 160) ? launch_conv_gemm_cg2_bn160(tmA, tmB, p, grid, stream, nullptr)
-                       : launch_conv_gemm_cg2_bn256(tmA, tmB, p, grid, stream, nullptr);
+    return (BN == 160) ? launch_conv_gemm_cg2_bn160(tmA, tmB, tmO, p, grid, stream, nullptr)
+                       : launch_conv_gemm_cg2_bn256(tmA, tmB, tmO, p, grid, stream, nullptr);
   switch (BN) {
-    case 64:  return launch_conv_gemm_bn64(tmA, tmB, p, grid, stream);
-    case 128: return launch_conv_gemm_bn128(tmA, tmB, p, grid, stream);
-    case 160: return launch_conv_gemm_bn160(tmA, tmB, p, grid, stream);
-    case 256: return launch_conv_gemm_bn256(tmA, tmB, p, grid, stream);
+    case 64:  return launch_conv_gemm_bn64(tmA, tmB, tmO, p, grid, stream);
+    case 128: return launch_conv_gemm_bn128(tmA, tmB, tmO, p, grid, stream);
+    case 160: return launch_conv_gemm_bn160(tmA, tmB, tmO, p, grid, stream);
+    case 256: return launch_conv_gemm_bn256(tmA, tmB, tmO, p, grid, stream);
     default:  return set_error("conv_gemm: unsupported BN=%d", BN);
   }
 }

@@ -88,6 +88,9 @@ struct ConvGemmParams {
   int* split_cnt;   // [tiles][EPI_WARPS] arrival counters (zero on entry, reset by the last arrival)
   int isx, isy, isz; // input coordinate = output-tile coordinate * is + tap offset (strided convolution via TMA element strides)
   FastDiv fd_ksplit, fd_ntiles, fd_nxb, fd_nyb, fd_nzb;
+  int epi_tma;  // 1: the output leaves through TMA stores of the per-warp staging tile (no fused statistics, one output,
+                // plain output geometry); qorg = position of an epilogue warp's 32 rows inside the tile box, per lane quarter
+  int16_t qorg[4][4];
   int dbg;      // development only (MD_GEMM_DBG): 1 = skip the epilogue work, 2 = skip the MMAs, 4 = skip the TMA loads;
                 // results are garbage, the timings isolate which pipeline stage bounds a shape
   int cg2;      // 1: CTA-pair kernel; a work item is an (M-tile pair, N tile) and this CTA owns M tile 2*pair + rank
@@ -327,6 +330,115 @@ __device__ __forceinline__ void epilogue_tile(const ConvGemmParams& p, uint32_t 
   }
 }
 
+// TMA-store epilogue of one output tile for one warp (experimental, p.epi_tma): everything is finished in the
+// row-owner layout the accumulator comes in (lane = output row): bias, per-sample vector and fp32 residual are read as
+// four 16-byte loads per lane, the result is written into the warp's swizzled staging tile (exactly the layout of a
+// SWIZZLE_64B / SWIZZLE_32B TMA box of 16 columns x 32 rows) and one lane hands it to the TMA.  No per-element global
+// addressing, no second pass over shared memory: ~1/3 of the instructions of the coalesced epilogue.
+template <int BN, int RES, bool RV, int ACTV>
+__device__ __forceinline__ void epilogue_tile_tma(const ConvGemmParams& p, const CUtensorMap* tmO, uint32_t taddr,
+                                                  float* stage, int lane, int n_tile, long long orow, int bv,
+                                                  int c_begin, int x0, int y0, int z0, int b0) {
+  constexpr bool geglu = (ACTV == 2);
+  constexpr int HALF = BN / 2;
+  constexpr int out_cols = geglu ? HALF : BN;
+  const int n_limit = geglu ? p.N / 2 : p.N;
+  const int n_out0 = n_tile * out_cols;
+  const bool f32out = p.out_f32 != nullptr;
+  const bool valid = bv >= 0;
+  const long long ro = valid ? orow : 0;
+  const float* rvp = RV ? p.rowvec + static_cast<long long>(valid ? bv : 0) * p.rowvec_ld : nullptr;
+  const bool scaled = p.out_scale != 1.f;
+#pragma unroll 1
+  for (int c = c_begin; c < out_cols / kChunk; c += kCStride) {
+    const int col = n_out0 + c * kChunk;
+    if (col >= n_limit) break;
+    float o[16];
+    if constexpr (geglu) {
+      // value | gate halves of the accumulator tile; packed bias rows follow the same interleave
+      const int nb = n_tile * BN + c * kChunk;
+      float4 bv4[4], bg4[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        bv4[j] = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + nb) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        bg4[j] = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + nb + HALF) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      uint32_t v[16], g[16];
+      tmem_ld_32x16(taddr + c * kChunk, v);
+      tmem_ld_32x16(taddr + HALF + c * kChunk, g);
+      tc_wait_ld();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        o[4 * j + 0] = (__uint_as_float(v[4 * j + 0]) + bv4[j].x) * act_gelu(__uint_as_float(g[4 * j + 0]) + bg4[j].x);
+        o[4 * j + 1] = (__uint_as_float(v[4 * j + 1]) + bv4[j].y) * act_gelu(__uint_as_float(g[4 * j + 1]) + bg4[j].y);
+        o[4 * j + 2] = (__uint_as_float(v[4 * j + 2]) + bv4[j].z) * act_gelu(__uint_as_float(g[4 * j + 2]) + bg4[j].z);
+        o[4 * j + 3] = (__uint_as_float(v[4 * j + 3]) + bv4[j].w) * act_gelu(__uint_as_float(g[4 * j + 3]) + bg4[j].w);
+      }
+    } else {
+    const bool full = col + kChunk <= p.N;  // a ragged last chunk reads bias / residual element-safe below
+    float4 b4[4], r4[4], v4[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int cj = (full || col + 4 * j + 4 <= p.N) ? col + 4 * j : 0;
+      b4[j] = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + cj)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (RV) v4[j] = __ldg(reinterpret_cast<const float4*>(rvp + cj));
+      if (RES == 1) r4[j] = *reinterpret_cast<const float4*>(p.res_f32 + ro + cj);
+    }
+    uint32_t v[16];
+    tmem_ld_32x16(taddr + c * kChunk, v);
+    tc_wait_ld();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float e[4] = {__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                    __uint_as_float(v[4 * j + 3])};
+      const float bb[4] = {b4[j].x, b4[j].y, b4[j].z, b4[j].w};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        float y = scaled ? e[t] * p.out_scale : e[t];
+        y += bb[t];
+        if (RV) y += (t == 0 ? v4[j].x : t == 1 ? v4[j].y : t == 2 ? v4[j].z : v4[j].w);
+        if (ACTV == 1) {
+          if (p.act == ACT_SILU) y = act_silu(y);
+          else if (p.act == ACT_RELU) y = fmaxf(y, 0.f);
+          else if (p.act == ACT_GELU) y = act_gelu(y);
+        }
+        if (RES == 1) y += (t == 0 ? r4[j].x : t == 1 ? r4[j].y : t == 2 ? r4[j].z : r4[j].w);
+        o[4 * j + t] = y;
+      }
+    }
+    }  // !geglu
+    // the previous chunk's store must have finished reading the staging tile
+    if (lane == 0) tma_store_wait_read();
+    __syncwarp();
+    if (f32out) {
+      float* st_wr = stage + lane * 16;
+      const int swl = (lane >> 1) & 3;  // SWIZZLE_64B: 16-byte chunk index ^= address bits 7..8
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<float4*>(st_wr + ((j ^ swl) << 2)) = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+    } else {
+      uint8_t* st_wr = reinterpret_cast<uint8_t*>(stage) + lane * 32;
+      const int sw1 = (lane >> 2) & 1;  // SWIZZLE_32B: 16-byte chunk index ^= address bit 7
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        uint32_t w[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          __nv_bfloat162 h = __floats2bfloat162_rn(o[8 * j + 2 * t], o[8 * j + 2 * t + 1]);
+          w[t] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        *reinterpret_cast<uint4*>(st_wr + ((j ^ sw1) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    }
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_5d(tmO, stage, col, x0, y0, z0, b0);
+      tma_store_commit();
+    }
+  }
+}
+
 // Pulls `bytes` (multiple of 16) at a 16-byte aligned global address into L2 without occupying registers.
 __device__ __forceinline__ void prefetch_l2_bulk(const void* gptr, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
@@ -334,9 +446,9 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void* gptr, uint32_t byte
 
 // Epilogue warps: loop over this CTA's work items (same schedule as the producer / MMA warps).
 template <int BN, int STAGES, int RES, bool RV, bool STATS, int ACTV, int STAGE_OFFSET>
-__device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, uint8_t* smem, uint64_t* tmem_full,
-                                              uint64_t* tmem_empty, uint32_t tmem_base, int warp, int lane,
-                                              int tile_begin, int tile_end, int tile_step) {
+__device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, const CUtensorMap* tmO, uint8_t* smem,
+                                              uint64_t* tmem_full, uint64_t* tmem_empty, uint32_t tmem_base, int warp,
+                                              int lane, int tile_begin, int tile_end, int tile_step) {
   const int ew = warp - 2;
   const int q = warp & 3;        // TMEM lane quarter this warp may read
   const int c_begin = ew >> 2;   // this warp owns chunks c_begin, c_begin + 4, ...
@@ -472,8 +584,20 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, uint8_t* 
 #else
     constexpr bool kpf = false;
 #endif
-    if (run_epilogue && !(p.dbg & 1))
-      epilogue_tile<BN, RES, RV, NCH, STATS, ACTV>(p, taddr, stage, lane, n_tile, ri, c_begin, st1, st2, kpf);
+    if (run_epilogue && !(p.dbg & 1)) {
+      if constexpr (!STATS && RES != 2) {
+        if (p.epi_tma) {
+          const int16_t* qo = p.qorg[q];
+          epilogue_tile_tma<BN, RES, RV, ACTV>(p, tmO, taddr, stage, lane, n_tile, orow, bv, c_begin,
+                                               tc.xb * p.bw + qo[0], tc.yb * p.bh + qo[1], tc.zb * p.bd + qo[2],
+                                               tc.bblk * p.bb + qo[3]);
+        } else {
+          epilogue_tile<BN, RES, RV, NCH, STATS, ACTV>(p, taddr, stage, lane, n_tile, ri, c_begin, st1, st2, kpf);
+        }
+      } else {
+        epilogue_tile<BN, RES, RV, NCH, STATS, ACTV>(p, taddr, stage, lane, n_tile, ri, c_begin, st1, st2, kpf);
+      }
+    }
     tc_fence_before();
     __syncwarp();
     if (lane == 0) {
@@ -486,6 +610,7 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, uint8_t* 
   }
   if (STATS && st_sample >= 0)
     flush_col_stats<NCH>(p, lane, st_sample, st_ntile * out_cols_t, n_limit_t, c_begin, st1, st2);
+  if (p.epi_tma && lane == 0) tma_store_wait_all();  // the CTA's shared memory must outlive its bulk stores
 }
 
 // RES: 0 none / 1 fp32 / 2 bf16 residual; RV: per-sample additive vector; STATS: fused GroupNorm statistics; ACTV: 0 no
@@ -494,7 +619,7 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, uint8_t* 
 template <int BN, int STAGES, int RES, bool RV, bool STATS, int ACTV>
 __global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const ConvGemmParams p) {
+                 const __grid_constant__ CUtensorMap tmO, const ConvGemmParams p) {
   using S = ConvGemmSmem<BN, STAGES>;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kBarOffset);
@@ -511,6 +636,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
+    if (p.epi_tma) prefetch_tmap(&tmO);
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -616,7 +742,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else {
     // ===================== epilogue (warps 2 .. 17) =====================
-    epilogue_loop<BN, STAGES, RES, RV, STATS, ACTV, S::kStageOffset>(p, smem, tmem_full, tmem_empty, tmem_base, warp, lane,
+    epilogue_loop<BN, STAGES, RES, RV, STATS, ACTV, S::kStageOffset>(p, &tmO, smem, tmem_full, tmem_empty, tmem_base, warp, lane,
                                                                     tile_begin, tile_end, tile_step);
   }
 
@@ -649,7 +775,7 @@ struct ConvGemmSmem2 {
 template <int BN, int STAGES, int RES, bool RV, bool STATS, int ACTV>
 __global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1)
 conv_gemm_cg2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                     const ConvGemmParams p) {
+                     const __grid_constant__ CUtensorMap tmO, const ConvGemmParams p) {
   using S = ConvGemmSmem2<BN, STAGES>;
   static_assert(S::kBBytes % 1024 == 0, "B half tile must keep the 1024-byte swizzle alignment");
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -667,6 +793,7 @@ conv_gemm_cg2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
+    if (p.epi_tma) prefetch_tmap(&tmO);
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);   // leader: one arrive.expect_tx per phase, bytes of both CTAs
       mbar_init(&empty_bar[i], 1);  // one multicast commit per phase
@@ -751,7 +878,7 @@ conv_gemm_cg2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     }
   } else {
     // ===================== epilogue (both CTAs, their own 128 rows) =====================
-    epilogue_loop<BN, STAGES, RES, RV, STATS, ACTV, S::kStageOffset>(p, smem, tmem_full, tmem_empty, tmem_base, warp, lane,
+    epilogue_loop<BN, STAGES, RES, RV, STATS, ACTV, S::kStageOffset>(p, &tmO, smem, tmem_full, tmem_empty, tmem_base, warp, lane,
                                                                     tile_begin, tile_end, tile_step);
   }
 

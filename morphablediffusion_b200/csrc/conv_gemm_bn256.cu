@@ -3,8 +3,8 @@
 
 namespace md {
 
-int launch_conv_gemm_bn256(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p, int grid, cudaStream_t st) {
-  return launch_conv_gemm_variant<256, 4>(tmA, tmB, p, grid, st);
+int launch_conv_gemm_bn256(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const ConvGemmParams& p, int grid, cudaStream_t st) {
+  return launch_conv_gemm_variant<256, 4>(tmA, tmB, tmO, p, grid, st);
 }
 
 }  // namespace md

@@ -3,8 +3,8 @@
 
 namespace md {
 
-int launch_conv_gemm_bn64(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p, int grid, cudaStream_t st) {
-  return launch_conv_gemm_variant<64, 8>(tmA, tmB, p, grid, st);
+int launch_conv_gemm_bn64(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const ConvGemmParams& p, int grid, cudaStream_t st) {
+  return launch_conv_gemm_variant<64, 8>(tmA, tmB, tmO, p, grid, st);
 }
 
 }  // namespace md

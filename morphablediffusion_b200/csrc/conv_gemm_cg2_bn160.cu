@@ -3,9 +3,9 @@
 
 namespace md {
 
-int launch_conv_gemm_cg2_bn160(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p, int grid,
+int launch_conv_gemm_cg2_bn160(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const ConvGemmParams& p, int grid,
                                 cudaStream_t st, int* max_pairs) {
-  return launch_conv_gemm_cg2_variant<160, 7>(tmA, tmB, p, grid, st, max_pairs);
+  return launch_conv_gemm_cg2_variant<160, 7>(tmA, tmB, tmO, p, grid, st, max_pairs);
 }
 
 }  // namespace md

@@ -7,16 +7,16 @@
 
 namespace md {
 
-int launch_conv_gemm_bn64(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p, int grid, cudaStream_t st);
-int launch_conv_gemm_bn128(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p, int grid, cudaStream_t st);
-int launch_conv_gemm_bn160(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p, int grid, cudaStream_t st);
-int launch_conv_gemm_bn256(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p, int grid, cudaStream_t st);
+int launch_conv_gemm_bn64(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const ConvGemmParams& p, int grid, cudaStream_t st);
+int launch_conv_gemm_bn128(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const ConvGemmParams& p, int grid, cudaStream_t st);
+int launch_conv_gemm_bn160(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const ConvGemmParams& p, int grid, cudaStream_t st);
+int launch_conv_gemm_bn256(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const ConvGemmParams& p, int grid, cudaStream_t st);
 // CTA-pair (cta_group::2) kernels exist for the two widest tiles; max_pairs != nullptr only queries residency
-int launch_conv_gemm_cg2_bn160(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p, int grid, cudaStream_t st, int* max_pairs);
-int launch_conv_gemm_cg2_bn256(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p, int grid, cudaStream_t st, int* max_pairs);
+int launch_conv_gemm_cg2_bn160(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const ConvGemmParams& p, int grid, cudaStream_t st, int* max_pairs);
+int launch_conv_gemm_cg2_bn256(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const ConvGemmParams& p, int grid, cudaStream_t st, int* max_pairs);
 
 template <int BN, int STAGES, int RES, bool RV, bool STATS, int ACTV>
-int launch_conv_gemm_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p, int grid,
+int launch_conv_gemm_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const ConvGemmParams& p, int grid,
                          cudaStream_t stream) {
   using S = ConvGemmSmem<BN, STAGES>;
   auto kernel = conv_gemm_kernel<BN, STAGES, RES, RV, STATS, ACTV>;
@@ -26,7 +26,7 @@ int launch_conv_gemm_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
     if (e != cudaSuccess) return set_error("cudaFuncSetAttribute(conv_gemm): %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  launch_pdl(kernel, dim3(grid), dim3(64 + 32 * kEpiWarps), S::kTotal, stream, tmA, tmB, p);
+  launch_pdl(kernel, dim3(grid), dim3(64 + 32 * kEpiWarps), S::kTotal, stream, tmA, tmB, tmO, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("conv_gemm launch: %s", cudaGetErrorString(e));
   count_launch();
@@ -36,7 +36,7 @@ int launch_conv_gemm_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
 // CTA-pair kernel: clusters of two CTAs; `grid` is the number of CTAs (even).  *max_pairs (optional) receives the number
 // of pairs that can be resident at once (asked once per kernel instance).
 template <int BN, int STAGES, int RES, bool RV, bool STATS, int ACTV>
-int launch_conv_gemm_cg2_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p, int grid,
+int launch_conv_gemm_cg2_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const ConvGemmParams& p, int grid,
                              cudaStream_t stream, int* max_pairs) {
   using S = ConvGemmSmem2<BN, STAGES>;
   auto kernel = conv_gemm_cg2_kernel<BN, STAGES, RES, RV, STATS, ACTV>;
@@ -64,7 +64,7 @@ int launch_conv_gemm_cg2_one(const CUtensorMap& tmA, const CUtensorMap& tmB, con
   if (max_pairs) { *max_pairs = resident_pairs; return 0; }
   cfg.gridDim = dim3(grid);
   prefer_max_smem(reinterpret_cast<const void*>(kernel));
-  cudaLaunchKernelEx(&cfg, kernel, tmA, tmB, p);
+  cudaLaunchKernelEx(&cfg, kernel, tmA, tmB, tmO, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("conv_gemm_cg2 launch: %s", cudaGetErrorString(e));
   count_launch();
@@ -72,71 +72,71 @@ int launch_conv_gemm_cg2_one(const CUtensorMap& tmA, const CUtensorMap& tmB, con
 }
 
 template <int BN, int STAGES, int RES, bool RV, bool STATS>
-int launch_conv_gemm_cg2_act(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p, int grid,
+int launch_conv_gemm_cg2_act(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const ConvGemmParams& p, int grid,
                              cudaStream_t st, int* max_pairs) {
-  if (p.act == ACT_NONE) return launch_conv_gemm_cg2_one<BN, STAGES, RES, RV, STATS, 0>(tmA, tmB, p, grid, st, max_pairs);
+  if (p.act == ACT_NONE) return launch_conv_gemm_cg2_one<BN, STAGES, RES, RV, STATS, 0>(tmA, tmB, tmO, p, grid, st, max_pairs);
   if (p.act == ACT_GEGLU) {
     if constexpr (BN == kGegluTile && RES == 0 && !RV && !STATS)
-      return launch_conv_gemm_cg2_one<BN, STAGES, RES, RV, STATS, 2>(tmA, tmB, p, grid, st, max_pairs);
+      return launch_conv_gemm_cg2_one<BN, STAGES, RES, RV, STATS, 2>(tmA, tmB, tmO, p, grid, st, max_pairs);
     else
       return set_error("conv_gemm: the GEGLU epilogue exists for the widest tile without residual / vector / statistics only");
   }
-  return launch_conv_gemm_cg2_one<BN, STAGES, RES, RV, STATS, 1>(tmA, tmB, p, grid, st, max_pairs);
+  return launch_conv_gemm_cg2_one<BN, STAGES, RES, RV, STATS, 1>(tmA, tmB, tmO, p, grid, st, max_pairs);
 }
 
 // max_pairs != nullptr: only report how many CTA pairs of this instance fit on the device at once
 template <int BN, int STAGES>
-int launch_conv_gemm_cg2_variant(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p, int grid,
+int launch_conv_gemm_cg2_variant(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const ConvGemmParams& p, int grid,
                                  cudaStream_t st, int* max_pairs) {
   const int res = p.res_f32 ? 1 : (p.res_bf16 ? 2 : 0);
   const int key = res * 4 + (p.rowvec ? 2 : 0) + (p.col_stats ? 1 : 0);
   switch (key) {
-    case 0: return launch_conv_gemm_cg2_act<BN, STAGES, 0, false, false>(tmA, tmB, p, grid, st, max_pairs);
-    case 1: return launch_conv_gemm_cg2_act<BN, STAGES, 0, false, true>(tmA, tmB, p, grid, st, max_pairs);
-    case 2: return launch_conv_gemm_cg2_act<BN, STAGES, 0, true, false>(tmA, tmB, p, grid, st, max_pairs);
-    case 3: return launch_conv_gemm_cg2_act<BN, STAGES, 0, true, true>(tmA, tmB, p, grid, st, max_pairs);
-    case 4: return launch_conv_gemm_cg2_act<BN, STAGES, 1, false, false>(tmA, tmB, p, grid, st, max_pairs);
-    case 5: return launch_conv_gemm_cg2_act<BN, STAGES, 1, false, true>(tmA, tmB, p, grid, st, max_pairs);
-    case 6: return launch_conv_gemm_cg2_act<BN, STAGES, 1, true, false>(tmA, tmB, p, grid, st, max_pairs);
-    case 7: return launch_conv_gemm_cg2_act<BN, STAGES, 1, true, true>(tmA, tmB, p, grid, st, max_pairs);
-    case 8: return launch_conv_gemm_cg2_act<BN, STAGES, 2, false, false>(tmA, tmB, p, grid, st, max_pairs);
-    case 9: return launch_conv_gemm_cg2_act<BN, STAGES, 2, false, true>(tmA, tmB, p, grid, st, max_pairs);
-    case 10: return launch_conv_gemm_cg2_act<BN, STAGES, 2, true, false>(tmA, tmB, p, grid, st, max_pairs);
-    default: return launch_conv_gemm_cg2_act<BN, STAGES, 2, true, true>(tmA, tmB, p, grid, st, max_pairs);
+    case 0: return launch_conv_gemm_cg2_act<BN, STAGES, 0, false, false>(tmA, tmB, tmO, p, grid, st, max_pairs);
+    case 1: return launch_conv_gemm_cg2_act<BN, STAGES, 0, false, true>(tmA, tmB, tmO, p, grid, st, max_pairs);
+    case 2: return launch_conv_gemm_cg2_act<BN, STAGES, 0, true, false>(tmA, tmB, tmO, p, grid, st, max_pairs);
+    case 3: return launch_conv_gemm_cg2_act<BN, STAGES, 0, true, true>(tmA, tmB, tmO, p, grid, st, max_pairs);
+    case 4: return launch_conv_gemm_cg2_act<BN, STAGES, 1, false, false>(tmA, tmB, tmO, p, grid, st, max_pairs);
+    case 5: return launch_conv_gemm_cg2_act<BN, STAGES, 1, false, true>(tmA, tmB, tmO, p, grid, st, max_pairs);
+    case 6: return launch_conv_gemm_cg2_act<BN, STAGES, 1, true, false>(tmA, tmB, tmO, p, grid, st, max_pairs);
+    case 7: return launch_conv_gemm_cg2_act<BN, STAGES, 1, true, true>(tmA, tmB, tmO, p, grid, st, max_pairs);
+    case 8: return launch_conv_gemm_cg2_act<BN, STAGES, 2, false, false>(tmA, tmB, tmO, p, grid, st, max_pairs);
+    case 9: return launch_conv_gemm_cg2_act<BN, STAGES, 2, false, true>(tmA, tmB, tmO, p, grid, st, max_pairs);
+    case 10: return launch_conv_gemm_cg2_act<BN, STAGES, 2, true, false>(tmA, tmB, tmO, p, grid, st, max_pairs);
+    default: return launch_conv_gemm_cg2_act<BN, STAGES, 2, true, true>(tmA, tmB, tmO, p, grid, st, max_pairs);
   }
 }
 
 template <int BN, int STAGES, int RES, bool RV, bool STATS>
-int launch_conv_gemm_act(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p, int grid,
+int launch_conv_gemm_act(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const ConvGemmParams& p, int grid,
                          cudaStream_t st) {
-  if (p.act == ACT_NONE) return launch_conv_gemm_one<BN, STAGES, RES, RV, STATS, 0>(tmA, tmB, p, grid, st);
+  if (p.act == ACT_NONE) return launch_conv_gemm_one<BN, STAGES, RES, RV, STATS, 0>(tmA, tmB, tmO, p, grid, st);
   if (p.act == ACT_GEGLU) {
     if constexpr (BN == kGegluTile && RES == 0 && !RV && !STATS)
-      return launch_conv_gemm_one<BN, STAGES, RES, RV, STATS, 2>(tmA, tmB, p, grid, st);
+      return launch_conv_gemm_one<BN, STAGES, RES, RV, STATS, 2>(tmA, tmB, tmO, p, grid, st);
     else
       return set_error("conv_gemm: the GEGLU epilogue exists for the widest tile without residual / vector / statistics only");
   }
-  return launch_conv_gemm_one<BN, STAGES, RES, RV, STATS, 1>(tmA, tmB, p, grid, st);
+  return launch_conv_gemm_one<BN, STAGES, RES, RV, STATS, 1>(tmA, tmB, tmO, p, grid, st);
 }
 
 template <int BN, int STAGES>
-int launch_conv_gemm_variant(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p, int grid,
+int launch_conv_gemm_variant(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const ConvGemmParams& p, int grid,
                              cudaStream_t st) {
   const int res = p.res_f32 ? 1 : (p.res_bf16 ? 2 : 0);
   const int key = res * 4 + (p.rowvec ? 2 : 0) + (p.col_stats ? 1 : 0);
   switch (key) {
-    case 0: return launch_conv_gemm_act<BN, STAGES, 0, false, false>(tmA, tmB, p, grid, st);
-    case 1: return launch_conv_gemm_act<BN, STAGES, 0, false, true>(tmA, tmB, p, grid, st);
-    case 2: return launch_conv_gemm_act<BN, STAGES, 0, true, false>(tmA, tmB, p, grid, st);
-    case 3: return launch_conv_gemm_act<BN, STAGES, 0, true, true>(tmA, tmB, p, grid, st);
-    case 4: return launch_conv_gemm_act<BN, STAGES, 1, false, false>(tmA, tmB, p, grid, st);
-    case 5: return launch_conv_gemm_act<BN, STAGES, 1, false, true>(tmA, tmB, p, grid, st);
-    case 6: return launch_conv_gemm_act<BN, STAGES, 1, true, false>(tmA, tmB, p, grid, st);
-    case 7: return launch_conv_gemm_act<BN, STAGES, 1, true, true>(tmA, tmB, p, grid, st);
-    case 8: return launch_conv_gemm_act<BN, STAGES, 2, false, false>(tmA, tmB, p, grid, st);
-    case 9: return launch_conv_gemm_act<BN, STAGES, 2, false, true>(tmA, tmB, p, grid, st);
-    case 10: return launch_conv_gemm_act<BN, STAGES, 2, true, false>(tmA, tmB, p, grid, st);
-    default: return launch_conv_gemm_act<BN, STAGES, 2, true, true>(tmA, tmB, p, grid, st);
+    case 0: return launch_conv_gemm_act<BN, STAGES, 0, false, false>(tmA, tmB, tmO, p, grid, st);
+    case 1: return launch_conv_gemm_act<BN, STAGES, 0, false, true>(tmA, tmB, tmO, p, grid, st);
+    case 2: return launch_conv_gemm_act<BN, STAGES, 0, true, false>(tmA, tmB, tmO, p, grid, st);
+    case 3: return launch_conv_gemm_act<BN, STAGES, 0, true, true>(tmA, tmB, tmO, p, grid, st);
+    case 4: return launch_conv_gemm_act<BN, STAGES, 1, false, false>(tmA, tmB, tmO, p, grid, st);
+    case 5: return launch_conv_gemm_act<BN, STAGES, 1, false, true>(tmA, tmB, tmO, p, grid, st);
+    case 6: return launch_conv_gemm_act<BN, STAGES, 1, true, false>(tmA, tmB, tmO, p, grid, st);
+    case 7: return launch_conv_gemm_act<BN, STAGES, 1, true, true>(tmA, tmB, tmO, p, grid, st);
+    case 8: return launch_conv_gemm_act<BN, STAGES, 2, false, false>(tmA, tmB, tmO, p, grid, st);
+    case 9: return launch_conv_gemm_act<BN, STAGES, 2, false, true>(tmA, tmB, tmO, p, grid, st);
+    case 10: return launch_conv_gemm_act<BN, STAGES, 2, true, false>(tmA, tmB, tmO, p, grid, st);
+    default: return launch_conv_gemm_act<BN, STAGES, 2, true, true>(tmA, tmB, tmO, p, grid, st);
   }
 }
 
