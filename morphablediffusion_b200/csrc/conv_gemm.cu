@@ -232,19 +232,21 @@ int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
                                             (unsigned long long)Ktot, a.N);
   }
 
-  // ---- experimental TMA-store epilogue (MD_EPI_TMA=1): one output, no fused statistics, no bf16 residual,
-  // no split-K, plain output geometry; the output leaves as 16-column x 32-row boxes of the per-warp staging tile
+  // ---- TMA-store epilogue: one output, no fused statistics, no residual, no split-K, plain output geometry; the
+  // output leaves as 16-column x 32-row boxes of the per-warp staging tile.  Measured (gpurun r01y/r01z): -10..19 % on
+  // the bf16-out GEMMs without residual (qkv, GEGLU); fp32-residual launches get 5-11 % slower this way (their per-lane
+  // residual reads touch 32 sectors per request) and keep the coalesced epilogue unless MD_EPI_TMA=2.  MD_EPI_TMA=0
+  // switches the path off.
   CUtensorMap tmO = tmA;
   {
-    static const bool epi_tma_on = getenv("MD_EPI_TMA") != nullptr && atoi(getenv("MD_EPI_TMA")) != 0;
-    // measured (r01y): -10..19 % on the bf16-out GEMMs without residual (qkv, GEGLU), +5..11 % on fp32-residual ones
-    // (their per-lane residual reads touch 32 sectors per request), so residual launches need MD_EPI_TMA=2
-    static const bool epi_tma_res = getenv("MD_EPI_TMA") != nullptr && atoi(getenv("MD_EPI_TMA")) >= 2;
+    static const int epi_tma_mode = getenv("MD_EPI_TMA") ? atoi(getenv("MD_EPI_TMA")) : 1;
+    const bool epi_tma_on = epi_tma_mode != 0, epi_tma_res = epi_tma_mode >= 2;
     const bool one_out = (a.out_f32 != nullptr) != (a.out_bf16 != nullptr);
     const bool plain = p.osx == 1 && p.osy == 1 && p.osz == 1 && p.opx == 0 && p.opy == 0 && p.opz == 0 && p.OW == p.W &&
                        p.OH == p.H && p.OD == p.D;
     void* optr = a.out_f32 ? static_cast<void*>(a.out_f32) : a.out_bf16;
-    if (epi_tma_on && one_out && plain && !a.col_stats && !a.res_bf16 && (!a.res_f32 || epi_tma_res) && p.ksplit == 1 &&
+    if (epi_tma_on && !p.cg2 && one_out && plain && !a.col_stats && !a.res_bf16 && (!a.res_f32 || epi_tma_res) &&
+        p.ksplit == 1 &&
         !(reinterpret_cast<uintptr_t>(optr) & 15)) {
       // a lane quarter's 32 rows inside the tile box (x fastest): sub-box dims and the origin of every quarter
       int qd[4], bd4[4] = {p.bw, p.bh, p.bd, p.bb}, rem = 32;
