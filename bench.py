@@ -59,7 +59,18 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
-    def stop(self):
+    def wait_live(self, timeout=3.0):
+        """Blocks until nvidia-smi has delivered its first row (it takes a few hundred ms to start), so that the
+        timed region that follows is actually sampled."""
+        t0 = time.time()
+        while self.proc and not self.rows and time.time() - t0 < timeout:
+            time.sleep(0.02)
+
+    def mark(self):
+        """Index of the next row: rows[mark_begin:mark_end] are the samples taken between two marks."""
+        return len(self.rows)
+
+    def stop(self, begin=0, end=None):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -67,6 +78,9 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:  # noqa: BLE001
             self.proc.kill()
+        window = self.rows[begin:(end + 1) if end is not None else None]
+        if window:  # samples taken inside the timed region (plus the one in flight at its end)
+            self.rows = window
         sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
         mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         reasons = set()
@@ -234,14 +248,17 @@ def run_ours(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        sampler.wait_live()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    m0 = sampler.mark()
     e0.record()
     for i in range(steps):
         eng.denoise_step(x_dev, xin_dev, clip_dev, idx(i), 2.0, seed=6033)
     e1.record()
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    m1 = sampler.mark()
+    clocks = sampler.stop(m0, m1) if rank == 0 else None
     launches = nat.lib.md_launch_count()
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
