@@ -137,7 +137,8 @@ def kernel_rooflines(dev, tensor_peak, hbm_peak):
     fl = 4.0 * B * heads * S * S * dh
     out.append({"kernel": "attention_tc_kernel", "shape": "32 x 8 heads x 1024 tokens x 40", "bound": "tensor",
                 "achieved": fl / t / 1e12, "peak": tensor_peak, "unit": "TFLOP/s", "frac": fl / t / 1e12 / tensor_peak,
-                "us": t * 1e6, "note": "exp-bound: 268 M ex2 per launch on 16 MUFU lanes/SM/clk = 60 us floor"})
+                "us": t * 1e6, "note": "exp-bound: 268 M ex2 per launch on 16 MUFU lanes/SM/clk = 60 us floor",
+                "traffic": 68.7e6, "traffic_source": "profiles/r01_attention_tc_full_v9.md (dram read + write, ncu --set full)"})
     # GroupNorm + SiLU apply (HBM-bound): fp32 [32][1024][320] -> bf16
     x = torch.randn(32, 1024, 320, device=dev)
     stats = torch.stack([x.sum(1), (x * x).sum(1)], dim=-1).contiguous()
@@ -149,7 +150,8 @@ def kernel_rooflines(dev, tensor_peak, hbm_peak):
     by = x.numel() * 6.0
     out.append({"kernel": "gn_apply_fused_kernel", "shape": "fp32 [32][1024][320] -> bf16, GroupNorm32 + SiLU",
                 "bound": "hbm", "achieved": by / t / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": by / t / 1e9 / hbm_peak,
-                "us": t * 1e6})
+                "us": t * 1e6, "traffic": 42.3e6,
+                "traffic_source": "profiles/r01_gn_apply_fused_full_v8.md (dram read + write; the bf16 output stays in L2)"})
     return out
 
 
