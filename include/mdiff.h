@@ -150,6 +150,11 @@ MD_API int md_denoise_step(md_ctx* ctx, float* x_local, const float* x_input, co
                            float cfg_scale, const float* noise, unsigned long long seed, float* eps_out,
                            void* stream);
 MD_API int md_ddim_timestep(md_ctx* ctx, int index);  /* 1 .. 981 */
+/* SyncDDIMSampler(model, ddim_num_steps, "uniform", ddim_eta) (morphable_diffusion.py:649-672): rebuilds the DDIM
+ * schedule (timesteps range(0,1000,1000/steps)+1, alphas, alphas_prev, sigmas) of the context.  Cheap; may be called
+ * between steps (the per-step scalars are passed to the captured step through a device buffer). */
+MD_API int md_set_ddim(md_ctx* ctx, int ddim_steps, float ddim_eta);
+MD_API int md_ddim_steps(md_ctx* ctx);
 
 
 /* ------------------------------------------------------------------ op level: the other kernels of the step

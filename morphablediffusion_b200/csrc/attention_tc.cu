@@ -106,42 +106,49 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    // warp-uniform control flow (operands stay in uniform registers), one elected lane issues
+    if (elect_one()) {
       mbar_expect_tx(q_full, NWG * NDB * kBox);
       for (int w = 0; w < NWG; ++w)
         for (int db = 0; db < NDB; ++db)
           tma_load_3d(smem + L::kQ + (w * NDB + db) * kBox, &tmQKV, q_full, db * 64, h, row0 + q0 + w * 128);
-      for (int j = 0; j < nt; ++j) {
-        const int s = j % STAGES;
-        const uint32_t ph = (j / STAGES) & 1;
-        mbar_wait(&kv_empty[s], ph ^ 1);
-        uint8_t* base = smem + L::kKV + s * L::kStageBytes;
+    }
+    int s = 0;
+    uint32_t ph = 0;
+    for (int j = 0; j < nt; ++j) {
+      mbar_wait(&kv_empty[s], ph ^ 1);
+      uint8_t* base = smem + L::kKV + s * L::kStageBytes;
+      if (elect_one()) {
         mbar_expect_tx(&kv_full[s], L::kStageBytes);
+#pragma unroll
         for (int db = 0; db < NDB; ++db)
           tma_load_3d(base + db * kBox, &tmQKV, &kv_full[s], db * 64, heads + h, row0 + j * 128);
+#pragma unroll
         for (int db = 0; db < NDB; ++db)
           tma_load_3d(base + (NDB + db) * kBox, &tmQKV, &kv_full[s], db * 64, 2 * heads + h, row0 + j * 128);
       }
+      if (++s == STAGES) { s = 0; ph ^= 1; }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc_qk = make_idesc_bf16_ex(128, 128, 0);
-      const uint32_t idesc_pv = make_idesc_bf16_ex(128, npv, 1);
-      mbar_wait(q_full, 0);
-      tc_fence_after();
-      for (int j = 0; j <= nt; ++j) {
-        if (j < nt) {
-          const int s = j % STAGES;
-          mbar_wait(&kv_full[s], (j / STAGES) & 1);
-          tc_fence_after();
-          const uint32_t kbase = smem_u32(smem + L::kKV + s * L::kStageBytes);
-          for (int w = 0; w < NWG; ++w) {
-            if (j > 0) {
-              mbar_wait(&s_free[w], (j - 1) & 1);
-              tc_fence_after();
-            }
-            const uint32_t qbase = smem_u32(smem + L::kQ + w * NDB * kBox);
+    // warp-uniform loop; every MMA and commit comes from the same elected lane
+    const uint32_t idesc_qk = make_idesc_bf16_ex(128, 128, 0);
+    const uint32_t idesc_pv = make_idesc_bf16_ex(128, npv, 1);
+    mbar_wait(q_full, 0);
+    tc_fence_after();
+    for (int j = 0; j <= nt; ++j) {
+      if (j < nt) {
+        const int s = j % STAGES;
+        mbar_wait(&kv_full[s], (j / STAGES) & 1);
+        tc_fence_after();
+        const uint32_t kbase = smem_u32(smem + L::kKV + s * L::kStageBytes);
+        for (int w = 0; w < NWG; ++w) {
+          if (j > 0) {
+            mbar_wait(&s_free[w], (j - 1) & 1);
+            tc_fence_after();
+          }
+          const uint32_t qbase = smem_u32(smem + L::kQ + w * NDB * kBox);
+          if (elect_one()) {
             for (int ks = 0; ks < ksteps; ++ks) {
               const uint32_t off = (ks >> 2) * kBox;
               const uint64_t da = make_sw128_kmajor_desc(qbase + off) + 2 * (ks & 3);
@@ -151,14 +158,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __
             tc_commit(&s_full[w]);
           }
         }
-        if (j > 0) {
-          const int jp = j - 1;
-          const int sp = jp % STAGES;
-          const uint32_t vbase = smem_u32(smem + L::kKV + sp * L::kStageBytes + NDB * kBox);
-          for (int w = 0; w < NWG; ++w) {
-            mbar_wait(&p_ready[w], jp & 1);
-            tc_fence_after();
-            const uint32_t pbase = smem_u32(smem + L::kP + w * 2 * kBox);
+      }
+      if (j > 0) {
+        const int jp = j - 1;
+        const int sp = jp % STAGES;
+        const uint32_t vbase = smem_u32(smem + L::kKV + sp * L::kStageBytes + NDB * kBox);
+        for (int w = 0; w < NWG; ++w) {
+          mbar_wait(&p_ready[w], jp & 1);
+          tc_fence_after();
+          const uint32_t pbase = smem_u32(smem + L::kP + w * 2 * kBox);
+          if (elect_one()) {
+#pragma unroll
             for (int ks = 0; ks < 8; ++ks) {  // 128 keys = 8 K steps of 16
               const uint64_t da = make_sw128_kmajor_desc(pbase + (ks >> 2) * kBox) + 2 * (ks & 3);
               // V tile: [key][64 dims] rows of 128 B; a K step = 16 keys = 2048 B; dim blocks of 64 are kBox apart
@@ -167,10 +177,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __
             }
             tc_commit(&pv_done[w]);
           }
-          tc_commit(&kv_empty[sp]);
         }
+        if (elect_one()) tc_commit(&kv_empty[sp]);
       }
     }
+    __syncwarp();
   } else {
     // ===================== softmax warpgroups =====================
     const int w = (warp - 2) >> 2;

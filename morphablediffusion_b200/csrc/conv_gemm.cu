@@ -28,35 +28,38 @@ extern unsigned long long* g_kprof_buf;
 #endif
 void* tensor_map_encode_fn() { return reinterpret_cast<void*>(get_encode()); }
 
-// split-K workspace (process-wide, allocated on first use; kernels on one stream are ordered, so sharing is safe)
-static float* g_split_ws = nullptr;
-static size_t g_split_ws_bytes = 0;
-static int* g_split_cnt = nullptr;
-static size_t g_split_cnt_ints = 0;
-
-// A second stream may run GEMMs concurrently with the main one (frustum branch of the step): it uses its own
-// split-K workspace, selected host-side around the launches of that branch.
-static float* g_alt_ws = nullptr;
-static int* g_alt_cnt = nullptr;
-static size_t g_alt_bytes = 0, g_alt_ints = 0;
-static bool g_use_alt = false;
-void set_split_workspace_alt(float* ws, size_t bytes, int* cnt, size_t ints) { g_alt_ws = ws; g_alt_bytes = bytes; g_alt_cnt = cnt; g_alt_ints = ints; }
-void use_split_workspace_alt(bool on) { g_use_alt = on && g_alt_ws != nullptr; }
-
-int ensure_split_workspace() {
-  if (g_split_ws) return 0;
-  const size_t bytes = static_cast<size_t>(96) << 20;
-  const size_t ints = 1 << 16;
-  void* w = nullptr;
+// ---- split-K workspaces: per context, selected per host thread (host.h); a process-wide default only serves the
+// op-level entry point
+static thread_local const SplitWorkspace* t_split = nullptr;
+const SplitWorkspace* select_split_workspace(const SplitWorkspace* w) {
+  const SplitWorkspace* prev = t_split;
+  t_split = w;
+  return prev;
+}
+int alloc_split_workspace(SplitWorkspace& w, size_t bytes, size_t ints) {
+  void* p = nullptr;
   void* c = nullptr;
-  if (cudaMalloc(&w, bytes) != cudaSuccess || cudaMalloc(&c, ints * sizeof(int)) != cudaSuccess) {
+  if (cudaMalloc(&p, bytes) != cudaSuccess || cudaMalloc(&c, ints * sizeof(int)) != cudaSuccess ||
+      cudaMemset(c, 0, ints * sizeof(int)) != cudaSuccess) {
     cudaGetLastError();
+    if (p) cudaFree(p);
+    if (c) cudaFree(c);
     return set_error("conv_gemm: split-K workspace allocation failed");
   }
-  cudaMemset(c, 0, ints * sizeof(int));
-  g_split_ws = static_cast<float*>(w); g_split_ws_bytes = bytes;
-  g_split_cnt = static_cast<int*>(c); g_split_cnt_ints = ints;
+  w.ws = static_cast<float*>(p); w.bytes = bytes;
+  w.cnt = static_cast<int*>(c); w.ints = ints;
   return 0;
+}
+void free_split_workspace(SplitWorkspace& w) {
+  if (w.ws) cudaFree(w.ws);
+  if (w.cnt) cudaFree(w.cnt);
+  w = SplitWorkspace();
+}
+static const SplitWorkspace* default_split_workspace() {
+  static SplitWorkspace def;
+  static std::once_flag once;
+  std::call_once(once, [] { alloc_split_workspace(def, static_cast<size_t>(96) << 20, 1 << 16); });
+  return def.ws ? &def : nullptr;
 }
 
 static int pow2_floor(int v) {
@@ -66,7 +69,7 @@ static int pow2_floor(int v) {
 }
 
 int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
-  if (!g_split_ws && a.ksplit >= 0) MD_CHECK(ensure_split_workspace());
+  const SplitWorkspace* sw = a.ksplit < 0 ? nullptr : (t_split ? t_split : default_split_workspace());
   PFN_encodeTiled enc = get_encode();
   if (!enc) return set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
   if (a.Cin % kBlockK != 0) return set_error("conv_gemm: Cin=%d must be a multiple of 64", a.Cin);
@@ -124,7 +127,7 @@ int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
   // reduction overhead for split tiles; prefer the wider tile on ties (fewer re-reads of the activation tile)
   const int kblocks_all = p.ntaps * p.kblocks_per_tap;
   auto auto_split = [&](long long tiles) {
-    if (a.ksplit != 0 || a.act == ACT_GEGLU || !g_split_ws) return 1;
+    if (a.ksplit != 0 || a.act == ACT_GEGLU || !sw) return 1;
     if (tiles * 2 > num_sms() || kblocks_all < 8) return 1;
     const long long ks = std::min<long long>(std::min<long long>(num_sms() / tiles, kblocks_all / 4), 16);
     return static_cast<int>(std::max<long long>(ks, 1));
@@ -188,10 +191,10 @@ int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
   if (p.ksplit > 1) {
     if (a.act == ACT_GEGLU) return set_error("conv_gemm: split-K is not available with the GEGLU epilogue");
     const size_t need = static_cast<size_t>(p.m_tiles) * p.n_tiles * p.ksplit * 128 * BN * sizeof(float);
-    float* ws = g_use_alt ? g_alt_ws : g_split_ws;
-    int* cnt = g_use_alt ? g_alt_cnt : g_split_cnt;
-    const size_t ws_bytes = g_use_alt ? g_alt_bytes : g_split_ws_bytes;
-    const size_t cnt_ints = g_use_alt ? g_alt_ints : g_split_cnt_ints;
+    float* ws = sw ? sw->ws : nullptr;
+    int* cnt = sw ? sw->cnt : nullptr;
+    const size_t ws_bytes = sw ? sw->bytes : 0;
+    const size_t cnt_ints = sw ? sw->ints : 0;
     if (!ws || need > ws_bytes || static_cast<size_t>(p.m_tiles) * p.n_tiles * kEpiWarps > cnt_ints) {
       if (a.ksplit > 1) return set_error("conv_gemm: split-K workspace too small (%zu bytes needed)", need);
       p.ksplit = 1;
@@ -199,15 +202,14 @@ int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
     p.split_ws = ws;
     p.split_cnt = cnt;
   }
-  // ---- CTA pairs (cta_group::2) for tile-rich problems on the two widest tiles: half the L2 bytes per FLOP
-  // Measured on the 16-view step: +3..5 % on the long-K 3x3 convolutions in isolation, neutral to slightly negative on
-  // short-K GEMMs (their time is in the epilogue) and neutral on the whole step (72.97 vs 73.16 steps/s), i.e. the
-  // single-CTA tiles are not L2-bound but shared-memory-bandwidth bound (TMA writes + operand reads of 128 + BN rows
-  // per K block against 128 B/clk), which pairs only relieve by a quarter.  So pairs are opt-in: args.cta_pair = 1, or
-  // MD_CG2=1 (from 40 K blocks up) / MD_CG2=2 (whenever eligible).
-  static const int cg2_env = getenv("MD_CG2") ? atoi(getenv("MD_CG2")) : 0;
+  // ---- CTA pairs (cta_group::2) for tile-rich problems on the two widest tiles: half the weight bytes per FLOP.
+  // With the warp-uniform issue loops the long-K convolutions are bound by operand traffic, and pairs win from ~24 K
+  // blocks up (r02a, isolated, warm: 640->640 @32x32 207 -> 181 us, 1920->640 @16x16 148 -> 129 us = 1.40 PFLOP/s,
+  // 320->320 @32x32 72 -> 63 us); below that the launches are epilogue-bound and pairs lose (no TMA-store epilogue).
+  // MD_CG2=0 switches pairs off, MD_CG2=2 uses them whenever eligible; args.cta_pair overrides per call.
+  static const int cg2_env = getenv("MD_CG2") ? atoi(getenv("MD_CG2")) : 1;
   const int cg2_mode = a.cta_pair != 0 ? (a.cta_pair > 0 ? 2 : 0) : cg2_env;
-  const int cg2_min_kblocks = cg2_mode >= 2 ? 1 : 40;
+  const int cg2_min_kblocks = cg2_mode >= 2 ? 1 : 24;
   p.m_pairs = (p.m_tiles + 1) / 2;
   int cg2_pairs = 0;
   if (cg2_mode > 0 && p.ksplit == 1 && (BN == 160 || BN == 256) && p.m_tiles >= 2 && kblocks_all >= cg2_min_kblocks) {

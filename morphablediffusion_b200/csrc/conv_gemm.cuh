@@ -671,23 +671,25 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
-      int it = 0;
-      int plt = 0;
-      for (int item = tile_begin; item < tile_end; item += tile_step, ++plt) {
-        const TileCoord tc = decode_item(p, item);
-        const int kb0 = fdiv(kblocks * tc.sp, p.fd_ksplit), kb1 = fdiv(kblocks * (tc.sp + 1), p.fd_ksplit);
-        const int x0 = tc.xb * p.bw * p.isx, y0 = tc.yb * p.bh * p.isy, z0 = tc.zb * p.bd * p.isz, b0 = tc.bblk * p.bb;
-        const int n0 = tc.n_tile * BN;
-        int tap = kb0 / p.kblocks_per_tap, kc = kb0 - tap * p.kblocks_per_tap;
-        for (int kb = kb0; kb < kb1; ++kb, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
-          mbar_wait(&empty_bar[s], ph ^ 1);
-          KPROF(19, plt == kKprofTile && kb == kb0);
-          KPROF(20, plt == kKprofTile && kb == kb1 - 1);
-          uint8_t* sa = smem + s * S::kStageBytes;
-          uint8_t* sb = sa + S::kABytes;
+    // The whole warp walks the schedule (warp-uniform control flow keeps addresses and coordinates in uniform
+    // registers: no per-instruction R2UR election loops around UTMALDG); one elected lane issues.
+    int s = 0;
+    uint32_t ph = 0;
+    int it = 0;
+    int plt = 0;
+    for (int item = tile_begin; item < tile_end; item += tile_step, ++plt) {
+      const TileCoord tc = decode_item(p, item);
+      const int kb0 = fdiv(kblocks * tc.sp, p.fd_ksplit), kb1 = fdiv(kblocks * (tc.sp + 1), p.fd_ksplit);
+      const int x0 = tc.xb * p.bw * p.isx, y0 = tc.yb * p.bh * p.isy, z0 = tc.zb * p.bd * p.isz, b0 = tc.bblk * p.bb;
+      const int n0 = tc.n_tile * BN;
+      int tap = kb0 / p.kblocks_per_tap, kc = kb0 - tap * p.kblocks_per_tap;
+      for (int kb = kb0; kb < kb1; ++kb, ++it) {
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        KPROF(19, lane == 0 && plt == kKprofTile && kb == kb0);
+        KPROF(20, lane == 0 && plt == kKprofTile && kb == kb1 - 1);
+        uint8_t* sa = smem + s * S::kStageBytes;
+        uint8_t* sb = sa + S::kABytes;
+        if (elect_one()) {
           if (p.dbg & 4) {
             mbar_arrive(&full_bar[s]);
           } else {
@@ -695,38 +697,41 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tma_load_5d(sa, &tmA, &full_bar[s], kc * kBlockK, x0 + p.tdx[tap], y0 + p.tdy[tap], z0 + p.tdz[tap], b0);
             tma_load_2d(sb, &tmB, &full_bar[s], kb * kBlockK, n0);
           }
-          KPROF(3, it == 0);
-          if (++kc == p.kblocks_per_tap) { kc = 0; ++tap; }
         }
+        KPROF(3, lane == 0 && it == 0);
+        if (++kc == p.kblocks_per_tap) { kc = 0; ++tap; }
+        if (++s == STAGES) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BN);
-      int it = 0;
-      int lt = 0;
-      for (int item = tile_begin; item < tile_end; item += tile_step, ++lt) {
-        const int sp = item - fdiv(item, p.fd_ksplit) * p.ksplit;
-        const int nkb = fdiv(kblocks * (sp + 1), p.fd_ksplit) - fdiv(kblocks * sp, p.fd_ksplit);
-        const int a = lt & 1;
-        const uint32_t aph = (lt >> 1) & 1;
-        mbar_wait(&tmem_empty[a], aph ^ 1);
+    // Warp-uniform loop as well; the MMAs and their commits come from the same elected lane (tcgen05.commit tracks the
+    // issuing thread's MMAs; elect.sync with a full mask always names the same lane).
+    constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BN);
+    int s = 0;
+    uint32_t ph = 0;
+    int it = 0;
+    int lt = 0;
+    for (int item = tile_begin; item < tile_end; item += tile_step, ++lt) {
+      const int sp = item - fdiv(item, p.fd_ksplit) * p.ksplit;
+      const int nkb = fdiv(kblocks * (sp + 1), p.fd_ksplit) - fdiv(kblocks * sp, p.fd_ksplit);
+      const int a = lt & 1;
+      const uint32_t aph = (lt >> 1) & 1;
+      mbar_wait(&tmem_empty[a], aph ^ 1);
+      tc_fence_after();
+      KPROF(13, lane == 0 && lt == kKprofTile);
+      const uint32_t d_tmem = tmem_base + a * BN;
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        mbar_wait(&full_bar[s], ph);
         tc_fence_after();
-        KPROF(13, lt == kKprofTile);
-        const uint32_t d_tmem = tmem_base + a * BN;
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
-          mbar_wait(&full_bar[s], ph);
-          tc_fence_after();
-          KPROF(4, it == 0);
-          KPROF(5, lt == 0 && kb == nkb - 1);
-          KPROF(14, lt == kKprofTile && kb == 0);
-          const uint32_t sa = smem_u32(smem + s * S::kStageBytes);
-          const uint32_t sb = sa + S::kABytes;
-          const uint64_t da = make_sw128_kmajor_desc(sa);
-          const uint64_t db = make_sw128_kmajor_desc(sb);
+        KPROF(4, lane == 0 && it == 0);
+        KPROF(5, lane == 0 && lt == 0 && kb == nkb - 1);
+        KPROF(14, lane == 0 && lt == kKprofTile && kb == 0);
+        const uint32_t sa = smem_u32(smem + s * S::kStageBytes);
+        const uint32_t sb = sa + S::kABytes;
+        const uint64_t da = make_sw128_kmajor_desc(sa);
+        const uint64_t db = make_sw128_kmajor_desc(sb);
+        if (elect_one()) {
           if (!(p.dbg & 2)) {
 #pragma unroll
             for (int k = 0; k < kBlockK / 16; ++k) {
@@ -736,10 +741,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           tc_commit(&empty_bar[s]);
         }
-        tc_commit(&tmem_full[a]);
-        KPROF(15, lt == kKprofTile);
+        if (++s == STAGES) { s = 0; ph ^= 1; }
       }
+      if (elect_one()) tc_commit(&tmem_full[a]);
+      KPROF(15, lane == 0 && lt == kKprofTile);
     }
+    __syncwarp();
   } else {
     // ===================== epilogue (warps 2 .. 17) =====================
     epilogue_loop<BN, STAGES, RES, RV, STATS, ACTV, S::kStageOffset>(p, &tmO, smem, tmem_full, tmem_empty, tmem_base, warp, lane,
@@ -826,32 +833,34 @@ conv_gemm_cg2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
-    if (lane == 0) {
-      int it = 0;
-      for (int item = tile_begin; item < tile_end; item += tile_step) {
-        const TileCoord tc = decode_item(p, item);
-        const int x0 = tc.xb * p.bw * p.isx, y0 = tc.yb * p.bh * p.isy, z0 = tc.zb * p.bd * p.isz, b0 = tc.bblk * p.bb;
-        const int n0 = tc.n_tile * BN + static_cast<int>(rank) * (BN / 2);
-        int tap = 0, kc = 0;
-        for (int kb = 0; kb < kblocks; ++kb, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
-          mbar_wait(&empty_bar[s], ph ^ 1);
-          uint8_t* sa = smem + s * S::kStageBytes;
-          uint8_t* sb = sa + S::kABytes;
+    // warp-uniform loop, one elected lane issues (see conv_gemm_kernel)
+    int s = 0;
+    uint32_t ph = 0;
+    for (int item = tile_begin; item < tile_end; item += tile_step) {
+      const TileCoord tc = decode_item(p, item);
+      const int x0 = tc.xb * p.bw * p.isx, y0 = tc.yb * p.bh * p.isy, z0 = tc.zb * p.bd * p.isz, b0 = tc.bblk * p.bb;
+      const int n0 = tc.n_tile * BN + static_cast<int>(rank) * (BN / 2);
+      int tap = 0, kc = 0;
+      for (int kb = 0; kb < kblocks; ++kb) {
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* sa = smem + s * S::kStageBytes;
+        uint8_t* sb = sa + S::kABytes;
+        const uint32_t lead_bar = mapa_shared(smem_u32(&full_bar[s]), 0);
+        if (elect_one()) {
           if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * S::kStageBytes);
-          const uint32_t lead_bar = mapa_shared(smem_u32(&full_bar[s]), 0);
           tma_load_5d_cg2(sa, &tmA, lead_bar, kc * kBlockK, x0 + p.tdx[tap], y0 + p.tdy[tap], z0 + p.tdz[tap], b0);
           tma_load_2d_cg2(sb, &tmB, lead_bar, kb * kBlockK, n0);
-          if (++kc == p.kblocks_per_tap) { kc = 0; ++tap; }
         }
+        if (++kc == p.kblocks_per_tap) { kc = 0; ++tap; }
+        if (++s == STAGES) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (pair leader only) =====================
-    if (lane == 0 && rank == 0) {
+    if (rank == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(2 * kBlockM, BN);
-      int it = 0;
+      int s = 0;
+      uint32_t ph = 0;
       int lt = 0;
       for (int item = tile_begin; item < tile_end; item += tile_step, ++lt) {
         const int a = lt & 1;
@@ -859,22 +868,24 @@ conv_gemm_cg2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         mbar_wait(&tmem_empty[a], aph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + a * BN;
-        for (int kb = 0; kb < kblocks; ++kb, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
+        for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + s * S::kStageBytes);
           const uint32_t sb = sa + S::kABytes;
           const uint64_t da = make_sw128_kmajor_desc(sa);
           const uint64_t db = make_sw128_kmajor_desc(sb);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k)
-            tc_mma_f16_cg2(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-          tc_commit_cg2(&empty_bar[s], 3);
+            for (int k = 0; k < kBlockK / 16; ++k)
+              tc_mma_f16_cg2(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            tc_commit_cg2(&empty_bar[s], 3);
+          }
+          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
-        tc_commit_cg2(&tmem_full[a], 3);
+        if (elect_one()) tc_commit_cg2(&tmem_full[a], 3);
       }
+      __syncwarp();
     }
   } else {
     // ===================== epilogue (both CTAs, their own 128 rows) =====================

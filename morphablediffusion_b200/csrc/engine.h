@@ -117,7 +117,7 @@ struct Ctx {
   cudaStream_t stream2 = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_levels = nullptr;
   bool levels_pending = false;         // unet_forward must wait on ev_levels before its first depth transformer
-  float* split_ws2 = nullptr; int* split_cnt2 = nullptr;
+  SplitWorkspace split_main, split_side;   // split-K workspaces of the two streams (host.h)
   SampleBinding sb;
   // DDIM schedule (host)
   std::vector<float> alphas, alphas_prev, sigmas, sqrt_1m_alphas;

@@ -18,8 +18,21 @@ int num_sms();
 
 int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream);
 void* tensor_map_encode_fn();  // cuTensorMapEncodeTiled resolved through the runtime (null without a driver)
-void set_split_workspace_alt(float* ws, size_t bytes, int* cnt, size_t ints);
-void use_split_workspace_alt(bool on);
+// Split-K workspace of the launches issued by the calling host thread.  Every context owns its own (one per stream it
+// launches GEMMs on) and selects it around its launches with a SplitScope; nothing here is shared between contexts.
+// Without a selection (op-level md_op_conv_gemm) a lazily allocated process-wide workspace is used: such calls must be
+// stream-ordered with respect to each other.
+struct SplitWorkspace { float* ws = nullptr; size_t bytes = 0; int* cnt = nullptr; size_t ints = 0; };
+int alloc_split_workspace(SplitWorkspace& w, size_t bytes, size_t ints);
+void free_split_workspace(SplitWorkspace& w);
+const SplitWorkspace* select_split_workspace(const SplitWorkspace* w);  // thread-local; returns the previous selection
+struct SplitScope {
+  const SplitWorkspace* prev;
+  explicit SplitScope(const SplitWorkspace* w) : prev(select_split_workspace(w)) {}
+  ~SplitScope() { select_split_workspace(prev); }
+  SplitScope(const SplitScope&) = delete;
+  SplitScope& operator=(const SplitScope&) = delete;
+};
 
 #define MD_CHECK(expr)                 \
   do {                                 \

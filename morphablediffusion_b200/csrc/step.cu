@@ -181,12 +181,13 @@ static int denoise_step_impl(Ctx& c, float* x_local, const float* x_input, const
       std::swap(c.arena, c.arena2);
       c.arena.off = 0;
       c.arena.failed = false;
-      set_split_workspace_alt(c.split_ws2, static_cast<size_t>(48) << 20, c.split_cnt2, 1 << 15);
-      use_split_workspace_alt(true);
-      int rc = vf_on_side ? vertex_feature_sum(c, x_local, t_embed, vsum, c.stream2) : 0;
-      if (rc == 0) rc = spatial_volume_from_vsum(c, vsum, vol, c.stream2);
-      if (rc == 0) rc = frustum_levels(c, vol, lv0, T, t_embed, T, levels, c.stream2);
-      use_split_workspace_alt(false);
+      int rc;
+      {
+        SplitScope side(&c.split_side);
+        rc = vf_on_side ? vertex_feature_sum(c, x_local, t_embed, vsum, c.stream2) : 0;
+        if (rc == 0) rc = spatial_volume_from_vsum(c, vsum, vol, c.stream2);
+        if (rc == 0) rc = frustum_levels(c, vol, lv0, T, t_embed, T, levels, c.stream2);
+      }
       std::swap(c.arena, c.arena2);
       if (rc != 0) return rc;
       MD_CUDA(cudaEventRecord(c.ev_levels, c.stream2));
@@ -280,11 +281,13 @@ int md_create(md_ctx** out, const md_config* cfg) {
     }
     if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&ctx->c.ev_fork, cudaEventDisableTiming);
     if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&ctx->c.ev_levels, cudaEventDisableTiming);
-    const size_t ws2 = static_cast<size_t>(48) << 20, ints2 = 1 << 15;
-    if (e2 == cudaSuccess) e2 = cudaMalloc(reinterpret_cast<void**>(&ctx->c.split_ws2), ws2);
-    if (e2 == cudaSuccess) e2 = cudaMalloc(reinterpret_cast<void**>(&ctx->c.split_cnt2), ints2 * sizeof(int));
-    if (e2 == cudaSuccess) e2 = cudaMemset(ctx->c.split_cnt2, 0, ints2 * sizeof(int));
+    if (e2 == cudaSuccess && alloc_split_workspace(ctx->c.split_side, static_cast<size_t>(48) << 20, 1 << 15) != 0)
+      e2 = cudaErrorMemoryAllocation;
     if (e2 != cudaSuccess) { cudaGetLastError(); ctx->c.stream2 = nullptr; }  // overlap simply stays off
+  }
+  if (alloc_split_workspace(ctx->c.split_main, static_cast<size_t>(96) << 20, 1 << 16) != 0) {
+    md_destroy(ctx);
+    return -1;
   }
   ctx->c.use_graph = getenv("MD_NO_GRAPH") == nullptr;
   *out = ctx;
@@ -307,8 +310,8 @@ void md_destroy(md_ctx* ctx) {
   if (ctx->c.ev_fork) cudaEventDestroy(ctx->c.ev_fork);
   if (ctx->c.ev_levels) cudaEventDestroy(ctx->c.ev_levels);
   cudaFree(ctx->c.arena2.base);
-  cudaFree(ctx->c.split_ws2);
-  cudaFree(ctx->c.split_cnt2);
+  free_split_workspace(ctx->c.split_main);
+  free_split_workspace(ctx->c.split_side);
   cudaFree(ctx->c.arena.base);
   cudaFree(ctx->c.gn_stats);
   delete ctx;
@@ -360,6 +363,7 @@ int md_embed_time(md_ctx* ctx, float timestep, float* t_embed_out, void* stream)
 int md_spatial_volume(md_ctx* ctx, const float* x_local, const float* t_embed, float* volume_out, void* stream) {
   MD_CHECK(ensure_ready(ctx, true));
   Ctx& c = ctx->c;
+  SplitScope split_scope(&c.split_main);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const md_config& mc = c.mcfg;
   const int V = mc.spatial_volume_size;
@@ -379,6 +383,7 @@ int md_frustum_feats(md_ctx* ctx, const float* volume, int lv0, int T, const flo
                      float* const out_levels[4], void* stream) {
   MD_CHECK(ensure_ready(ctx, true));
   Ctx& c = ctx->c;
+  SplitScope split_scope(&c.split_main);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const md_config& mc = c.mcfg;
   const int V = mc.spatial_volume_size, S = mc.latent_size, D = mc.frustum_depth;
@@ -401,6 +406,7 @@ int md_unet_forward(md_ctx* ctx, const float* x, const float* timesteps_host, co
                     const float* const source[4], int B, float* out, void* stream) {
   MD_CHECK(ensure_ready(ctx, false));
   Ctx& c = ctx->c;
+  SplitScope split_scope(&c.split_main);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const md_config& mc = c.mcfg;
   const int S = mc.latent_size, D = mc.frustum_depth;
@@ -433,6 +439,7 @@ int md_denoise_step(md_ctx* ctx, float* x_local, const float* x_input, const flo
                     float cfg_scale, const float* noise, unsigned long long seed, float* eps_out, void* stream) {
   MD_CHECK(ensure_ready(ctx, true));
   Ctx& c = ctx->c;
+  SplitScope split_scope(&c.split_main);
   if (index < 0 || index >= static_cast<int>(c.timesteps.size())) return set_error("denoise_step: bad DDIM index %d", index);
   cudaStream_t caller = static_cast<cudaStream_t>(stream);
   cudaStream_t st = c.stream;
@@ -504,6 +511,18 @@ int md_denoise_step(md_ctx* ctx, float* x_local, const float* x_input, const flo
   MD_CUDA(cudaStreamWaitEvent(caller, c.ev_out, 0));
   return rc;
 }
+
+int md_set_ddim(md_ctx* ctx, int ddim_steps, float ddim_eta) {
+  if (!ctx) return set_error("null context");
+  if (ddim_steps < 1 || ddim_steps > 1000) return set_error("md_set_ddim: ddim_steps=%d out of range 1..1000", ddim_steps);
+  if (ddim_eta < 0.f) return set_error("md_set_ddim: negative eta");
+  ctx->c.mcfg.ddim_steps = ddim_steps;
+  ctx->c.mcfg.ddim_eta = ddim_eta;
+  make_schedule(ctx->c);  // per-step scalars reach the captured graph through d_step: no re-capture needed
+  return 0;
+}
+
+int md_ddim_steps(md_ctx* ctx) { return ctx ? static_cast<int>(ctx->c.timesteps.size()) : -1; }
 
 int md_ddim_timestep(md_ctx* ctx, int index) {
   if (!ctx || index < 0 || index >= static_cast<int>(ctx->c.timesteps.size())) return -1;

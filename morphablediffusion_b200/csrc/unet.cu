@@ -55,10 +55,12 @@ struct Fwd {
     else { a.ntaps = 1; }
     a.bias = w.bias; a.rowvec = rowvec; a.rowvec_ld = rowvec_ld; a.res_f32 = res_f32;
     a.out_f32 = out_f32; a.out_bf16 = out_bf16; a.act = act;
+    const void* key = out_f32 ? static_cast<const void*>(out_f32) : static_cast<const void*>(out_bf16);
     if (stats && H * W >= 32) {
-      const void* key = out_f32 ? static_cast<const void*>(out_f32) : static_cast<const void*>(out_bf16);
       a.col_stats = new_stats(key, nb, w.N);
       if (!a.col_stats) return set_error("statistics pool exhausted");
+    } else {
+      stats_of.erase(key);  // the arena recycles addresses: statistics of an earlier tensor must not outlive it
     }
     return launch_conv_gemm(a, st);
   }
@@ -70,10 +72,12 @@ struct Fwd {
     a.A = a_in; a.B = nb; a.D = 1; a.H = 1; a.W = static_cast<int>(rows_per_sample); a.Cin = w.K; a.Wt = w.w; a.N = w.N;
     a.ntaps = 1;
     a.bias = w.bias; a.res_f32 = res_f32; a.out_f32 = out_f32; a.out_bf16 = out_bf16; a.act = act;
+    const void* key = out_f32 ? static_cast<const void*>(out_f32) : static_cast<const void*>(out_bf16);
     if (stats && rows_per_sample >= 32 && rows_per_sample % 32 == 0) {
-      const void* key = out_f32 ? static_cast<const void*>(out_f32) : static_cast<const void*>(out_bf16);
       a.col_stats = new_stats(key, nb, w.N);
       if (!a.col_stats) return set_error("statistics pool exhausted");
+    } else {
+      stats_of.erase(key);
     }
     return launch_conv_gemm(a, st);
   }
@@ -212,6 +216,8 @@ struct Fwd {
     if ((H / 2) * (W / 2) >= 32) {
       a.col_stats = new_stats(out, B, w.N);
       if (!a.col_stats) return set_error("statistics pool exhausted");
+    } else {
+      stats_of.erase(out);
     }
     MD_CHECK(launch_conv_gemm(a, st));
     A().release(m);

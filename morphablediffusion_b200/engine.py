@@ -44,6 +44,7 @@ class Engine:
             nat.check(nat.lib.md_create(C.byref(self._h), C.byref(cfg)), "md_create")
         self.S, self.V, self.D = latent_size, cfg.spatial_volume_size, cfg.frustum_depth
         self.n_views = self.view0 = self.n_local = 0
+        self.ddim = (int(ddim_steps), float(ddim_eta))
 
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
@@ -146,6 +147,12 @@ class Engine:
                                           int(index), float(cfg_scale), nat.ptr(noise), int(seed), nat.ptr(eps),
                                           nat.cur_stream()), "md_denoise_step")
         return eps
+
+    def set_ddim(self, ddim_steps, ddim_eta=1.0):
+        """Schedule of SyncDDIMSampler(model, ddim_steps, ddim_eta=...) (morphable_diffusion.py:649-672)."""
+        if (int(ddim_steps), float(ddim_eta)) != self.ddim:
+            nat.check(nat.lib.md_set_ddim(self._h, int(ddim_steps), float(ddim_eta)), "md_set_ddim")
+            self.ddim = (int(ddim_steps), float(ddim_eta))
 
     def ddim_timestep(self, index):
         return nat.lib.md_ddim_timestep(self._h, index)

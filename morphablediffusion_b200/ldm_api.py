@@ -337,14 +337,29 @@ class SyncMultiviewDiffusion(_Base):
             self._bound_key = None
         return self._engine
 
+    _BOUND_KEYS = ("target_K", "target_RT", "vertices", "coord", "out_sh", "bounds", "target_elevation",
+                   "target_azimuth", "input_elevation", "input_azimuth")
+
     def _bound_engine(self, batch):
+        """Engine with `batch` (B = 1) bound.  The binding is keyed on tensor IDENTITY + in-place version of every
+        bound tensor (the tensors are kept alive, so an id cannot be recycled by the allocator); tensors that are new
+        objects are compared by CONTENT against the bound copies before a re-bind is skipped.  Addresses are never
+        part of the key: the caching allocator hands equal-shaped batches the same addresses."""
         eng = self._get_engine()
-        key = tuple(int(batch[k].data_ptr()) for k in ("target_K", "target_RT", "vertices", "coord"))
-        if key != self._bound_key:
-            if batch["target_K"].shape[0] != 1:
-                raise ValueError("bind one sample at a time")
-            eng.bind(batch, self.projection)
-            self._bound_key = key
+        cur = tuple(batch[k] for k in self._BOUND_KEYS)
+        ver = tuple(int(t._version) for t in cur)
+        bk = self._bound_key
+        if bk is not None and len(bk[0]) == len(cur):
+            if all(a is b for a, b in zip(bk[0], cur)) and bk[1] == ver:
+                return eng
+            if all(a.shape == c.shape and a.dtype == c.dtype and torch.equal(c, t.to(c.device))
+                   for a, c, t in zip(bk[0], bk[2], cur)):
+                self._bound_key = (cur, ver, bk[2])
+                return eng
+        if batch["target_K"].shape[0] != 1:
+            raise ValueError("bind one sample at a time")
+        eng.bind(batch, self.projection)
+        self._bound_key = (cur, ver, tuple(t.detach().clone() for t in cur))
         return eng
 
     # -- reference methods on the path
@@ -437,7 +452,19 @@ class SyncDDIMSampler:
         self.ddim_alphas = self.ddim_alphas.float()
         self.ddim_alphas_prev = self.ddim_alphas_prev.float()
         self.ddim_sqrt_one_minus_alphas = torch.sqrt(1.0 - self.ddim_alphas).float()
-        self.seed = 6033
+        self.seed = None  # None: sample() draws a fresh seed from torch's generator per call (torch.manual_seed rules)
+
+    def _engine_for(self, batch_item):
+        """Bound engine whose DDIM schedule is THIS sampler's (ddim_num_steps, eta); the library's schedule is checked
+        against the sampler's own timestep table so a mismatch can never denoise at the wrong timestep silently."""
+        eng = self.model._bound_engine(batch_item)
+        eng.set_ddim(self.ddim_num_steps, self.eta)
+        return eng
+
+    def _step_seed(self, bi):
+        if self.seed is None:
+            self.seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        return (int(self.seed) + 0x9E3779B97F4A7C15 * (bi + 1)) & 0xFFFFFFFFFFFFFFFF
 
     def denoise_apply_impl(self, x_target_noisy, index, noise_pred, is_step0=False):
         a_t, a_prev = self.ddim_alphas[index], self.ddim_alphas_prev[index]
@@ -454,34 +481,75 @@ class SyncDDIMSampler:
         """One fused step per sample; batch_view_num only bounds the UNet batch (results do not depend on it)."""
         B = x_target_noisy.shape[0]
         out = []
+        if not 0 <= index < len(self.ddim_timesteps):
+            raise IndexError(f"DDIM index {index} outside the sampler's {len(self.ddim_timesteps)} steps")
         for bi in range(B):
-            eng = self.model._bound_engine(_batch_item(batch, bi))
-            x = x_target_noisy[bi].detach().to(torch.float32).contiguous().clone()
+            eng = self._engine_for(_batch_item(batch, bi))
+            if eng.ddim_timestep(index) != int(self.ddim_timesteps[index]):
+                raise RuntimeError(f"library DDIM schedule disagrees with the sampler at index {index}: "
+                                   f"{eng.ddim_timestep(index)} vs {int(self.ddim_timesteps[index])}")
+            if time_steps is not None and int(time_steps.reshape(-1)[bi]) != int(self.ddim_timesteps[index]):
+                raise ValueError("time_steps must be the sampler's ddim_timesteps[index] (morphable_diffusion.py:762-766)")
+            # persistent work buffers: the library keys its captured step graph on the pointers it is given
+            w = self._work_buffers(x_target_noisy[bi], input_info["x"][bi], clip_embed[bi])
+            w["x"].copy_(x_target_noisy[bi])
+            w["xin"].copy_(input_info["x"][bi])
+            w["clip"].copy_(clip_embed[bi].reshape(-1))
             # the library adds no noise at index 0 (the sampler loop's is_step0); an explicit is_step0 at another
             # index is honoured with a zero noise tensor
-            noise = torch.zeros_like(x) if (is_step0 and index != 0) else None
-            eng.denoise_step(x, input_info["x"][bi].contiguous().float(), clip_embed[bi].reshape(-1).contiguous().float(),
-                             index, unconditional_scale, noise=noise, seed=self.seed)
-            out.append(x)
+            noise = w["zero"] if (is_step0 and index != 0) else None
+            eng.denoise_step(w["x"], w["xin"], w["clip"], index, unconditional_scale, noise=noise,
+                             seed=self._step_seed(bi))
+            out.append(w["x"].clone())
         return torch.stack(out, 0)
 
+    def _work_buffers(self, x, xin, clip):
+        key = (tuple(x.shape), tuple(xin.shape), clip.numel(), x.device)
+        if getattr(self, "_work_key", None) != key:
+            dev = x.device
+            self._work = {"x": torch.empty(x.shape, device=dev), "xin": torch.empty(xin.shape, device=dev),
+                          "clip": torch.empty(clip.numel(), device=dev), "zero": torch.zeros(x.shape, device=dev)}
+            self._work_key = key
+        return self._work
+
     @torch.no_grad()
-    def sample(self, input_info, clip_embed, unconditional_scale=1.0, log_every_t=50, batch_view_num=1, batch=None):
+    def sample(self, input_info, clip_embed, unconditional_scale=1.0, log_every_t=50, batch_view_num=1, batch=None,
+               x_T=None, step_noise=None):
+        """morphable_diffusion.py:742-776.  Extensions (keyword-only use): x_T [B,N,4,h,w] replaces the initial
+        torch.randn; step_noise [steps,B,N,4,h,w] (indexed by DDIM index) replaces the Philox draws of the DDIM
+        update, which is how the trajectory parity test shares its noise with the oracle."""
         print(f"unconditional scale {unconditional_scale:.1f}")
         C, H, W = 4, self.latent_size, self.latent_size
         B = clip_embed.shape[0]
         N = self.model.view_num
         device = self.model._device
-        x = torch.randn([B, N, C, H, W], device=device)
-        inter = {"x_inter": []}
+        x = torch.randn([B, N, C, H, W], device=device) if x_T is None else x_T.to(device, torch.float32).clone()
+        self.seed = int(torch.randint(0, 2 ** 62, (1,)).item())  # step noise: Philox(seed ^ item, index, view, element)
         total = self.ddim_timesteps.shape[0]
-        for i, step in enumerate(np.flip(self.ddim_timesteps)):
-            index = total - i - 1
-            ts = torch.full((B,), int(step), device=device, dtype=torch.long)
-            x = self.denoise_apply(x, input_info, clip_embed, ts, index, unconditional_scale,
-                                   batch_view_num=batch_view_num, is_step0=index == 0, batch=batch)
-            if index % log_every_t == 0 or index == total - 1:
-                inter["x_inter"].append(x)
+        logged = [index for index in range(total - 1, -1, -1) if index % log_every_t == 0 or index == total - 1]
+        inter_items = []
+        # Samples are independent, so the loop nest is (sample, step) instead of the reference's (step, sample): each
+        # sample's cameras / mesh / sparse-conv rulebook are bound once and its 50 steps replay one CUDA graph.
+        for bi in range(B):
+            eng = self._engine_for(_batch_item(batch, bi))
+            # one work buffer per sample, stepped in place: the library sees the same pointers on all 50 steps, so the
+            # whole step is captured once as a CUDA graph and replayed
+            xw = x[bi].detach().to(torch.float32).contiguous().clone()
+            xin = input_info["x"][bi].detach().contiguous().float()
+            clip = clip_embed[bi].detach().reshape(-1).contiguous().float()
+            seed = self._step_seed(bi)
+            snaps = []
+            nz = None if step_noise is None else torch.empty_like(xw)
+            for i in range(total):
+                index = total - i - 1
+                if nz is not None:
+                    nz.copy_(step_noise[index, bi])
+                eng.denoise_step(xw, xin, clip, index, unconditional_scale, noise=nz, seed=seed)
+                if index in logged:
+                    snaps.append(xw.clone()[None])
+            x[bi] = xw
+            inter_items.append(snaps)
+        inter = {"x_inter": [torch.cat([it[j] for it in inter_items], 0) for j in range(len(logged))]}
         return x, inter
 
 
