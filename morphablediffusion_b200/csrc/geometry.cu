@@ -213,19 +213,229 @@ target_encoder_kernel(const float* __restrict__ x, const float* __restrict__ t_e
   for (int q = 0; q < 4; ++q) o[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
 }
 
-int launch_target_encoder(const float* x, const float* t_embed, const float* v_embed, const EncWeightsHost& w,
-                          float* out, int n_views, int tdim, int vdim, cudaStream_t st) {
-  static bool attr = false;
-  const int smem = sizeof(EncSmem);
-  if (!attr) {
-    MD_CUDA(cudaFuncSetAttribute(target_encoder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr = true;
+// ---- cluster version: a cluster of 8 CTAs runs the encoder of one view, each CTA owning S/8 latent rows (one thread
+// per pixel).  Halo rows of every conv input are copied out of the neighbour CTAs' shared memory (DSMEM) and the
+// GroupNorm statistics are reduced over the cluster, so a view's 0.25 ms single-SM latency chain becomes ~8x shorter
+// and any latent size with S % 8 == 0 and S*S/8 <= 512 fits (S = 64: BASELINE config 1).
+constexpr int kEncCluster = 8;
+struct EncClusterLayout {   // offsets in floats into dynamic shared memory
+  int tmp, w, red, part, gstat, tv, total;
+  __host__ __device__ EncClusterLayout(int S) {
+    const int RP = S / kEncCluster;
+    tmp = 0;                                  // [2][16][(RP + 2) * S]: ping-pong conv input incl. one halo row either side
+    w = tmp + 2 * 16 * (RP + 2) * S;          // [9 * 16 * 16]
+    red = w + 9 * 16 * 16;                    // [32 warps][16]
+    part = red + 32 * 16;                     // [2][16] this CTA's GroupNorm partial sums (ping-pong)
+    gstat = part + 32;                        // [16]
+    tv = gstat + 16;                          // [16]
+    total = tv + 16;
   }
+};
+
+__device__ __forceinline__ float ld_dsmem_f32(const float* local_ptr, uint32_t rank) {
+  float v;
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(mapa_shared(smem_u32(local_ptr), rank)) : "memory");
+  return v;
+}
+
+// GroupNorm(8 groups of 2 channels) statistics of this view: CTA partials -> cluster reduction through DSMEM
+__device__ void encc_group_stats(float* sm, const EncClusterLayout& L, const float (&v)[16], int pp, float n_elems) {
+  float part[16];
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    part[g] = v[2 * g] + v[2 * g + 1];
+    part[8 + g] = v[2 * g] * v[2 * g] + v[2 * g + 1] * v[2 * g + 1];
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+#pragma unroll
+  for (int e = 0; e < 16; ++e) {
+    float a = part[e];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffff, a, o);
+    if (lane == 0) sm[L.red + warp * 16 + e] = a;
+  }
+  __syncthreads();
+  if (threadIdx.x < 16) {
+    float a = 0.f;
+    for (int w = 0; w < nwarp; ++w) a += sm[L.red + w * 16 + threadIdx.x];
+    sm[L.part + pp * 16 + threadIdx.x] = a;
+  }
+  cluster_sync_all();
+  if (threadIdx.x < 8) {
+    double s1 = 0.0, s2 = 0.0;
+    for (uint32_t r = 0; r < kEncCluster; ++r) {
+      s1 += ld_dsmem_f32(sm + L.part + pp * 16 + threadIdx.x, r);
+      s2 += ld_dsmem_f32(sm + L.part + pp * 16 + 8 + threadIdx.x, r);
+    }
+    const double mean = s1 / n_elems;
+    double var = s2 / n_elems - mean * mean;
+    if (var < 0) var = 0;
+    sm[L.gstat + threadIdx.x] = static_cast<float>(mean);
+    sm[L.gstat + 8 + threadIdx.x] = static_cast<float>(1.0 / sqrt(var + 1e-5));
+  }
+  __syncthreads();
+}
+
+// halo rows of buffer `b`: row 0 <- last interior row of the CTA above, row RP+1 <- first interior row of the CTA below
+__device__ void encc_halo(float* sm, const EncClusterLayout& L, int b, int S, int RP, uint32_t rank, int nch) {
+  const int plane = (RP + 2) * S;
+  float* buf = sm + L.tmp + b * 16 * plane;
+  cluster_sync_all();  // every CTA's interior rows of buffer b are written
+  for (int i = threadIdx.x; i < 2 * nch * S; i += blockDim.x) {
+    const int x = i % S, c = (i / S) % nch, side = i / (S * nch);
+    float v = 0.f;
+    if (side == 0) {
+      if (rank > 0) v = ld_dsmem_f32(buf + c * plane + RP * S + x, rank - 1);
+      buf[c * plane + x] = v;
+    } else {
+      if (rank + 1 < kEncCluster) v = ld_dsmem_f32(buf + c * plane + S + x, rank + 1);
+      buf[c * plane + (RP + 1) * S + x] = v;
+    }
+  }
+  __syncthreads();
+}
+
+template <int CIN>
+__device__ void encc_conv3x3(float* sm, const EncClusterLayout& L, int b, int S, int RP, const float* __restrict__ gw,
+                             const float* __restrict__ gb, float (&acc)[16]) {
+  for (int i = threadIdx.x; i < 9 * CIN * 16; i += blockDim.x) {
+    const int co = i % 16, ci = (i / 16) % CIN, tap = i / (16 * CIN);
+    sm[L.w + i] = gw[(co * CIN + ci) * 9 + tap];
+  }
+  __syncthreads();
+  const int plane = (RP + 2) * S;
+  const float* buf = sm + L.tmp + b * 16 * plane;
+  const int px = threadIdx.x % S, py = threadIdx.x / S;
+#pragma unroll
+  for (int co = 0; co < 16; ++co) acc[co] = gb[co];
+  for (int ky = 0; ky < 3; ++ky) {
+    const int yy = py + ky;  // halo-inclusive row index; rows outside the image hold zeros
+    for (int kx = 0; kx < 3; ++kx) {
+      const int xx = px + kx - 1;
+      if (xx < 0 || xx >= S) continue;
+      const float* wp = sm + L.w + (ky * 3 + kx) * CIN * 16;
+#pragma unroll
+      for (int ci = 0; ci < CIN; ++ci) {
+        const float a = buf[ci * plane + yy * S + xx];
+        const float4* w4 = reinterpret_cast<const float4*>(wp + ci * 16);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 w = w4[q];
+          acc[4 * q + 0] += a * w.x; acc[4 * q + 1] += a * w.y; acc[4 * q + 2] += a * w.z; acc[4 * q + 3] += a * w.w;
+        }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(512, 1)
+target_encoder_cluster_kernel(const float* __restrict__ x, const float* __restrict__ t_embed,
+                              const float* __restrict__ v_embed, EncWeights W, float* __restrict__ out, int tdim, int vdim,
+                              int S) {
+  pdl_grid_sync();
+  extern __shared__ __align__(16) float encc_sm[];
+  float* sm = encc_sm;
+  const EncClusterLayout L(S);
+  const int RP = S / kEncCluster;
+  const uint32_t rank = cluster_ctarank();
+  const int view = blockIdx.x / kEncCluster;
+  const int p = threadIdx.x;
+  const int px = p % S, py = p / S;
+  const int gy = static_cast<int>(rank) * RP + py;
+  const int plane = (RP + 2) * S;
+  const float n_elems = 2.f * S * S;
+  const size_t HW = static_cast<size_t>(S) * S;
+  float f[16], acc[16];
+  int b = 0, pp = 0;
+
+  // init conv 4 -> 16: the input comes from global memory, halo rows included
+  for (int i = p; i < 4 * plane; i += blockDim.x) {
+    const int xx = i % S, r = (i / S) % (RP + 2), c = i / plane;
+    const int yy = static_cast<int>(rank) * RP + r - 1;
+    sm[L.tmp + c * plane + r * S + xx] =
+        (yy >= 0 && yy < S) ? x[(static_cast<size_t>(view) * 4 + c) * HW + static_cast<size_t>(yy) * S + xx] : 0.f;
+  }
+  __syncthreads();
+  encc_conv3x3<4>(sm, L, 0, S, RP, W.init_w, W.init_b, f);
+
+  auto activate_into = [&](const float (&y)[16], const float* gw, const float* gbv) {
+    b ^= 1;
+    float* buf = sm + L.tmp + b * 16 * plane;
+#pragma unroll
+    for (int c = 0; c < 16; ++c)
+      buf[c * plane + (py + 1) * S + px] =
+          silu_g((y[c] - sm[L.gstat + (c >> 1)]) * sm[L.gstat + 8 + (c >> 1)] * gw[c] + gbv[c]);
+    encc_halo(sm, L, b, S, RP, rank, 16);
+  };
+
+  for (int rb = 0; rb < 3; ++rb) {
+    const EncWeights::Res& R = W.res[rb];
+    if (p < 16) {  // per-channel time/view bias (1x1 convs on a 1x1 map)
+      float a = R.te_b[p] + R.ve_b[p];
+      for (int k = 0; k < tdim; ++k) a += R.te_w[p * tdim + k] * t_embed[k];
+      for (int k = 0; k < vdim; ++k) a += R.ve_w[p * vdim + k] * v_embed[view * vdim + k];
+      sm[L.tv + p] = a;
+    }
+    __syncthreads();
+    float y[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) y[c] = f[c] + sm[L.tv + c];
+    encc_group_stats(sm, L, y, pp, n_elems); pp ^= 1;
+    activate_into(y, R.gn0_w, R.gn0_b);
+    encc_conv3x3<16>(sm, L, b, S, RP, R.c0_w, R.c0_b, acc);
+    encc_group_stats(sm, L, acc, pp, n_elems); pp ^= 1;
+    activate_into(acc, R.gn1_w, R.gn1_b);
+    encc_conv3x3<16>(sm, L, b, S, RP, R.c1_w, R.c1_b, acc);
+#pragma unroll
+    for (int c = 0; c < 16; ++c) f[c] += acc[c];
+  }
+  encc_group_stats(sm, L, f, pp, n_elems); pp ^= 1;
+  activate_into(f, W.fgn_w, W.fgn_b);
+  encc_conv3x3<16>(sm, L, b, S, RP, W.fc_w, W.fc_b, acc);
+  // channels-last output [view][pixel][16]
+  float4* o = reinterpret_cast<float4*>(out + (static_cast<size_t>(view) * HW + static_cast<size_t>(gy) * S + px) * 16);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) o[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+  cluster_sync_all();  // no CTA may exit while a neighbour can still read its shared memory
+}
+
+int launch_target_encoder(const float* x, const float* t_embed, const float* v_embed, const EncWeightsHost& w,
+                          float* out, int n_views, int tdim, int vdim, int S, cudaStream_t st) {
   EncWeights W;
   static_assert(sizeof(EncWeights) == sizeof(EncWeightsHost), "layout mismatch");
   memcpy(&W, &w, sizeof(W));
-  launch_pdl(target_encoder_kernel, dim3(n_views), dim3(1024), smem, st, x, t_embed, v_embed, W, out, tdim, vdim);
-  return check_launch("target_encoder");
+  static const bool single = getenv("MD_ENC_SINGLE") != nullptr;  // the one-CTA-per-view kernel (S = 32 only), for A/B
+  if (single && S == 32) {
+    static bool attr = false;
+    const int smem = sizeof(EncSmem);
+    if (!attr) {
+      MD_CUDA(cudaFuncSetAttribute(target_encoder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      attr = true;
+    }
+    launch_pdl(target_encoder_kernel, dim3(n_views), dim3(1024), smem, st, x, t_embed, v_embed, W, out, tdim, vdim);
+    return check_launch("target_encoder");
+  }
+  if (S % kEncCluster != 0 || S * S / kEncCluster > 512 || S * S / kEncCluster < 32)
+    return set_error("target_encoder: latent size %d unsupported (needs S %% 8 == 0 and 32 <= S*S/8 <= 512)", S);
+  const EncClusterLayout L(S);
+  const int smem = L.total * static_cast<int>(sizeof(float));
+  static int smem_set = 0;
+  if (smem > smem_set) {
+    MD_CUDA(cudaFuncSetAttribute(target_encoder_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    smem_set = smem;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kEncCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.gridDim = dim3(n_views * kEncCluster); cfg.blockDim = dim3(S * S / kEncCluster);
+  cfg.dynamicSmemBytes = smem; cfg.stream = st; cfg.attrs = attr; cfg.numAttrs = 2;
+  cudaLaunchKernelEx(&cfg, target_encoder_cluster_kernel, x, t_embed, v_embed, W, out, tdim, vdim, S);
+  return check_launch("target_encoder_cluster");
 }
 
 // ------------------------------------------------------------------------------------------------ projection helpers

@@ -19,7 +19,7 @@ struct EncWeightsHost {
 
 int launch_voxelize(const float* vertices, int nv, int32_t* coord, int32_t* out_sh, float* bounds, cudaStream_t st);
 int launch_target_encoder(const float* x, const float* t_embed, const float* v_embed, const EncWeightsHost& w,
-                          float* out, int n_views, int tdim, int vdim, cudaStream_t st);
+                          float* out, int n_views, int tdim, int vdim, int S, cudaStream_t st);
 int launch_unproject(const float* feats, const float* proj, int ortho, int size, int V, float length, float* vol,
                      int n_views, cudaStream_t st);
 int launch_vertex_features(const float* feats, const float* proj, int ortho, int size, int V, float length,

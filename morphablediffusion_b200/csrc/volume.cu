@@ -295,13 +295,12 @@ int embed_time(Ctx& c, const float* t_dev, float* t_embed, cudaStream_t st) {
 int vertex_feature_sum(Ctx& c, const float* x_local, const float* t_embed, float* vsum, cudaStream_t st) {
   const SampleBinding& sb = c.sb;
   const md_config& mc = c.mcfg;
-  if (mc.latent_size != 32) return set_error("target encoder kernel is specialised for 32x32 latents");
   Arena& A = c.arena;
   const size_t m = A.mark();
-  float* feats = A.get<float>(static_cast<size_t>(sb.n_local) * 1024 * 16);
+  float* feats = A.get<float>(static_cast<size_t>(sb.n_local) * mc.latent_size * mc.latent_size * 16);
   if (A.failed) return set_error("workspace exhausted (encoder)");
   MD_CHECK(launch_target_encoder(x_local, t_embed, sb.v_embed + static_cast<size_t>(sb.view0) * mc.view_dim, c.vol.enc,
-                                 feats, sb.n_local, mc.time_embed_dim, mc.view_dim, st));
+                                 feats, sb.n_local, mc.time_embed_dim, mc.view_dim, mc.latent_size, st));
   MD_CHECK(launch_vertex_features(feats, sb.proj + static_cast<size_t>(sb.view0) * 12, sb.ortho, mc.latent_size,
                                   mc.spatial_volume_size, mc.spatial_volume_length, sb.vertices, sb.nv, sb.n_local,
                                   vsum, st));

@@ -261,6 +261,20 @@ class SpatialVolumeNet(_ParamTree):
         return per_level, None
 
 
+def _build_frozen(factory):
+    """disable_training_module (morphable_diffusion.py:53-65) around a factory that may not be constructible here
+    (reference package or its dependencies / checkpoints absent): returns (module or None, reason)."""
+    try:
+        m = factory()
+    except Exception as e:  # noqa: BLE001 - ImportError, FileNotFoundError (CLIP checkpoint), ...
+        return None, f"{type(e).__name__}: {e}"
+    m = m.eval()
+    m.train = lambda mode=True: m
+    for p in m.parameters():
+        p.requires_grad = False
+    return m, None
+
+
 def _batch_item(batch, bi):
     return {k: (v[bi:bi + 1] if torch.is_tensor(v) else v) for k, v in batch.items()}
 
@@ -281,10 +295,9 @@ class SyncMultiviewDiffusion(_Base):
         self.projection = projection
         self.time_embed_dim = 256
         self.time_embed = nn.Sequential(nn.Linear(256, 256), nn.SiLU(True), nn.Linear(256, 256))
-        self.first_stage_scale_factor = 0.18215
-        self.first_stage_model = None      # frozen SD VAE: attach to use prepare()/decode_first_stage()
-        self.clip_image_encoder = None     # frozen CLIP ViT-L/14 image embedder
+        self._init_first_stage()
         self._init_schedule()
+        self._init_clip_image_encoder()
         self.spatial_volume = SpatialVolumeNet(self.time_embed_dim, self.viewpoint_dim, self.view_num,
                                                projection=projection, use_spatial_volume=use_spatial_volume)
         import weakref
@@ -315,6 +328,27 @@ class SyncMultiviewDiffusion(_Base):
 
     def _init_multiview(self):
         pass  # reads assets/thuman_meta.pkl in the reference; cameras always arrive through the batch dict
+
+    # -- frozen side models (morphable_diffusion.py:399-431): built through the reference's own classes when the
+    # reference package is importable behind the compat shim (they run once per sample, outside the step loop);
+    # otherwise left None for the user to attach.  Their parameters then sit under the reference's state-dict keys
+    # (first_stage_model.*, clip_image_encoder.*), so reference checkpoints load unchanged.
+    def _init_first_stage(self):
+        first_stage_config = {
+            "target": "ldm.models.autoencoder.AutoencoderKL",
+            "params": {"embed_dim": 4, "monitor": "val/rec_loss",
+                       "ddconfig": {"double_z": True, "z_channels": 4, "resolution": self.image_size, "in_channels": 3,
+                                    "out_ch": 3, "ch": 128, "ch_mult": [1, 2, 4, 4], "num_res_blocks": 2,
+                                    "attn_resolutions": [], "dropout": 0.0},
+                       "lossconfig": {"target": "torch.nn.Identity"}}}
+        self.first_stage_scale_factor = 0.18215
+        self.first_stage_model, self._first_stage_error = _build_frozen(lambda: instantiate_from_config(first_stage_config))
+
+    def _init_clip_image_encoder(self):
+        def build():
+            mod = importlib.import_module("ldm.modules.encoders.modules")
+            return mod.FrozenCLIPImageEmbedder(model=self.clip_image_encoder_path)
+        self.clip_image_encoder, self._clip_error = _build_frozen(build)
 
     @property
     def _device(self):
@@ -382,7 +416,8 @@ class SyncMultiviewDiffusion(_Base):
     # -- frozen side models (outside the step loop; not rebuilt — attach the reference's own modules)
     def encode_first_stage(self, x, sample=True):
         if self.first_stage_model is None:
-            raise RuntimeError("attach the frozen AutoencoderKL as model.first_stage_model (outside the hot path)")
+            raise RuntimeError("no first_stage_model: the reference AutoencoderKL could not be built "
+                               f"({self._first_stage_error}); attach it as model.first_stage_model")
         with torch.no_grad():
             posterior = self.first_stage_model.encode(x)
             z = posterior.sample() if sample else posterior.mode()
@@ -390,13 +425,15 @@ class SyncMultiviewDiffusion(_Base):
 
     def decode_first_stage(self, z):
         if self.first_stage_model is None:
-            raise RuntimeError("attach the frozen AutoencoderKL as model.first_stage_model (outside the hot path)")
+            raise RuntimeError("no first_stage_model: the reference AutoencoderKL could not be built "
+                               f"({self._first_stage_error}); attach it as model.first_stage_model")
         with torch.no_grad():
             return self.first_stage_model.decode(z / self.first_stage_scale_factor)
 
     def prepare(self, batch):
         if self.clip_image_encoder is None:
-            raise RuntimeError("attach the frozen CLIP image embedder as model.clip_image_encoder (outside the hot path)")
+            raise RuntimeError("no clip_image_encoder: the reference FrozenCLIPImageEmbedder could not be built "
+                               f"({self._clip_error}); attach it as model.clip_image_encoder")
         image_input = batch["input_image"].permute(0, 3, 1, 2)
         x_input = self.encode_first_stage(image_input)
         input_info = {"image": image_input, "elevation": batch["input_elevation"][:, 0], "x": x_input}

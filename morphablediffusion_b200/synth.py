@@ -143,10 +143,12 @@ def voxelize_cpu(vertices):
     return coord, out_sh, torch.stack([min_xyz, max_xyz], 0)
 
 
-def make_batch(n_views=16, projection="perspective", mesh="flame", seed=6033, unique_voxels=False):
-    """The `batch` dict wire format of generate_face.py:227-241 (B = 1), CPU tensors."""
+def make_batch(n_views=16, projection="perspective", mesh="flame", seed=6033, unique_voxels=False, image_size=256):
+    """The `batch` dict wire format of generate_face.py:227-241 (B = 1), CPU tensors.  image_size scales the
+    perspective intrinsics (512 px: f = 3090.475, c = 256 — BASELINE config 1)."""
     if projection == "perspective":
-        K, RT = virtual_cameras(n_views)
+        r = image_size / 256.0
+        K, RT = virtual_cameras(n_views, focal=1545.23757707405 * r, c=128.0 * r)
     else:
         K, RT = ortho_cameras(n_views)
     v = head_mesh(seed=seed) if mesh == "flame" else body_points(seed=seed)
@@ -175,3 +177,10 @@ def make_inputs(n_views=16, latent=32, seed=6033):
     x_input = torch.randn(1, 4, latent, latent, generator=g)
     clip = torch.randn(1, 1, 768, generator=g)
     return x_t, x_input, clip
+
+
+def step_noise(seed, index, shape):
+    """Shared DDIM step noise of the trajectory parity test: the draw of DDIM index `index` (the reference run of
+    oracle/make_golden.py and the GPU test both regenerate it from the seed)."""
+    g = torch.Generator().manual_seed(seed * 1000 + index)
+    return torch.randn(shape, generator=g)

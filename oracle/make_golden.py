@@ -60,13 +60,14 @@ def ref_eps(model, x_t, x_input, clip, t, cfg_scale, batch, bvn):
     return torch.cat(e_t, 1), vol, frustum0
 
 
-def run_config(name, n_views, projection, mesh, index=49, cfg_scale=2.0, seed=6033, bvn=4):
+def run_config(name, n_views, projection, mesh, index=49, cfg_scale=2.0, seed=6033, bvn=4, latent=32):
     torch.manual_seed(0)
     t0 = time.time()
-    model, ns = ref_import.build_reference_model(projection=projection, view_num=n_views, cfg_scale=cfg_scale)
+    model, ns = ref_import.build_reference_model(projection=projection, view_num=n_views, cfg_scale=cfg_scale,
+                                                 latent=latent)
     sd = load_synth(model, seed)
-    batch = synth.make_batch(n_views, projection, mesh, seed)
-    x_t, x_input, clip = synth.make_inputs(n_views, 32, seed)
+    batch = synth.make_batch(n_views, projection, mesh, seed, image_size=latent * 8)
+    x_t, x_input, clip = synth.make_inputs(n_views, latent, seed)
     step = int(model.sampler.ddim_timesteps[index])
     t = torch.full((1,), step, dtype=torch.long)
     g = torch.Generator().manual_seed(seed + 7)
@@ -85,7 +86,7 @@ def run_config(name, n_views, projection, mesh, index=49, cfg_scale=2.0, seed=60
     t_ref = time.time() - t0
     # ---- oracle on the same inputs
     t0 = time.time()
-    cfg = O.VolumeCfg(projection=projection, num_views=n_views)
+    cfg = O.VolumeCfg(projection=projection, num_views=n_views, input_image_size=latent * 8)
     sched = O.make_schedule()
     with torch.no_grad():
         o_eps, parts = O.denoise_eps(sd, cfg, x_t, x_input, clip, t, cfg_scale, batch, bvn, return_parts=True)
@@ -95,12 +96,49 @@ def run_config(name, n_views, projection, mesh, index=49, cfg_scale=2.0, seed=60
           f"vol {maxerr(parts['spatial_volume'], vol)}  x_prev {maxerr(o_prev, x_prev)}", flush=True)
     np.savez_compressed(
         GOLD / f"{name}.npz",
-        n_views=n_views, projection=projection, mesh=mesh, index=index, cfg_scale=cfg_scale, seed=seed,
+        n_views=n_views, projection=projection, mesh=mesh, index=index, cfg_scale=cfg_scale, seed=seed, latent=latent,
         eps=eps.numpy(), x_prev=x_prev.numpy(), noise_seed=seed + 7,
         vol_sub=vol[:, :, ::4, ::4, ::4].numpy(), vol_absmean=float(vol.abs().mean()),
         **{f"frustum0_{k}": v[:, ::8, ::2, ::2, ::2].numpy() for k, v in fr0.items()},
         timestep=step)
     return model, sd
+
+
+step_noise = synth.step_noise
+
+
+def run_trajectory(name, n_views=2, steps=50, cfg_scale=2.0, seed=6033, keep=(40, 30, 20, 10, 0)):
+    """The reference's SyncDDIMSampler.sample loop (morphable_diffusion.py:742-776) for all `steps` DDIM steps with
+    the reference's own per-step methods; the only substitution is that the sigma_t * randn of denoise_apply_impl
+    (:696) uses `step_noise` so the trajectory can be reproduced elsewhere."""
+    torch.manual_seed(0)
+    model, ns = ref_import.build_reference_model(view_num=n_views, cfg_scale=cfg_scale, sample_steps=steps)
+    load_synth(model, seed)
+    batch = synth.make_batch(n_views, "perspective", "flame", seed)
+    x, x_input, clip = synth.make_inputs(n_views, 32, seed)
+    s = model.sampler
+    total = s.ddim_timesteps.shape[0]
+    snaps = {}
+    eps_first = None
+    t0 = time.time()
+    with torch.no_grad():
+        for i, step in enumerate(np.flip(s.ddim_timesteps)):
+            index = total - i - 1
+            t = torch.full((1,), int(step), dtype=torch.long)
+            eps, _, _ = ref_eps(model, x, x_input, clip, t, cfg_scale, batch, n_views)
+            if eps_first is None:
+                eps_first = eps.clone()
+            x = s.denoise_apply_impl(x, index, eps, is_step0=True)      # the reference's update without its RNG draw
+            if index != 0:
+                x = x + s.ddim_sigmas[index] * step_noise(seed, index, x.shape)
+            if index in keep:
+                snaps[index] = x.clone()
+            if i % 10 == 0:
+                print(f"[{name}] step {i}/{total} |x| {float(x.abs().mean()):.4f} ({time.time() - t0:.0f}s)", flush=True)
+    np.savez_compressed(GOLD / f"{name}.npz", n_views=n_views, steps=total, cfg_scale=cfg_scale, seed=seed,
+                        x0=x.numpy(), eps_first=eps_first.numpy(),
+                        **{f"x_at_{k}": v.numpy() for k, v in snaps.items()})
+    print(f"[{name}] done in {time.time() - t0:.0f}s  |x0| mean {float(x.abs().mean()):.4f} max {float(x.abs().max()):.3f}")
 
 
 def unet_only(seed=6033):
@@ -132,9 +170,26 @@ def spec_dump():
 if __name__ == "__main__":
     GOLD.mkdir(parents=True, exist_ok=True)
     torch.set_num_threads(8)
-    spec_dump()
-    unet_only()
-    run_config("step_n4_persp", 4, "perspective", "flame", index=49)
-    run_config("step_n4_ortho", 4, "orthographic", "body", index=20)
-    if "--skip-n16" not in sys.argv:
+    only = [a for a in sys.argv[1:] if not a.startswith("--")]
+    want = lambda n: not only or n in only
+    if want("spec"):
+        spec_dump()
+    if want("unet_b2"):
+        unet_only()
+    if want("step_n4_persp"):
+        run_config("step_n4_persp", 4, "perspective", "flame", index=49)
+    if want("step_n4_ortho"):
+        run_config("step_n4_ortho", 4, "orthographic", "body", index=20)
+    if want("step_n16_persp") and "--skip-n16" not in sys.argv:
         run_config("step_n16_persp", 16, "perspective", "flame", index=49)
+    # round 2: the remaining BASELINE.json configurations
+    if want("step_n16_ortho_body"):   # config 4: SMPL-X-sized body (10 475 points), 16 orthographic views
+        run_config("step_n16_ortho_body", 16, "orthographic", "body", index=30, bvn=8)
+    if want("step_n8_persp"):         # config 5: view-count sweep (smpl_feature_extractor.num_views = N)
+        run_config("step_n8_persp", 8, "perspective", "flame", index=10, bvn=8)
+    if want("step_n32_persp"):
+        run_config("step_n32_persp", 32, "perspective", "flame", index=40, bvn=8)
+    if want("step_n4_lat64"):         # config 1: 4 views @ 64x64 latent (input_image_size = 512)
+        run_config("step_n4_lat64", 4, "perspective", "flame", index=49, latent=64)
+    if want("traj_n2_50"):            # a2: the 50-step sampler loop
+        run_trajectory("traj_n2_50", 2, 50)

@@ -107,7 +107,7 @@ UNET_PARAMS = dict(volume_dims=[64, 128, 256, 512], image_size=32, in_channels=8
                    context_dim=768, use_checkpoint=False, legacy=False)
 
 
-def build_reference_model(projection="perspective", view_num=16, cfg_scale=2.0, sample_steps=50):
+def build_reference_model(projection="perspective", view_num=16, cfg_scale=2.0, sample_steps=50, latent=32):
     """A SyncMultiviewDiffusion with everything on the per-step path constructed by the reference's own code and
     the frozen side models (VAE, CLIP — outside the step loop, no checkpoint here) skipped."""
     import torch.nn as nn
@@ -117,15 +117,18 @@ def build_reference_model(projection="perspective", view_num=16, cfg_scale=2.0, 
     nn.Module.__init__(m)
     m.view_num = view_num
     m.viewpoint_dim = 4
-    m.image_size = 256
+    m.image_size = latent * 8
     m.cfg_scale = cfg_scale
     m._init_time_step_embedding()
     m._init_schedule()
-    m.spatial_volume = md.SpatialVolumeNet(m.time_embed_dim, m.viewpoint_dim, m.view_num, projection=projection,
-                                           use_spatial_volume=False)
+    # input_image_size is a constructor argument of the reference's SpatialVolumeNet (morphable_diffusion.py:152-157);
+    # SyncMultiviewDiffusion.__init__ never passes it (:351), which is why the stock model is tied to 32x32 latents
+    m.spatial_volume = md.SpatialVolumeNet(m.time_embed_dim, m.viewpoint_dim, m.view_num, input_image_size=latent * 8,
+                                           projection=projection, use_spatial_volume=False)
     m.spatial_volume.smpl_feature_extractor.num_views = view_num
-    unet_config = {"target": "ldm.models.diffusion.attention.DepthWiseAttention", "params": dict(UNET_PARAMS)}
+    unet_config = {"target": "ldm.models.diffusion.attention.DepthWiseAttention",
+                   "params": dict(UNET_PARAMS, image_size=latent)}
     m.model = md.UNetWrapper(unet_config)
-    m.sampler = md.SyncDDIMSampler(m, sample_steps, "uniform", 1.0, latent_size=32)
+    m.sampler = md.SyncDDIMSampler(m, sample_steps, "uniform", 1.0, latent_size=latent)
     m.eval()
     return m, ns

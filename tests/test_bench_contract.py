@@ -17,16 +17,22 @@ def run_bench(*args, timeout=600):
 
 
 def test_reference_arm_prints_the_contract_line():
-    p = run_bench("--impl", "reference", "--steps", "1", "--warmup", "0")
+    # 4 views keep the CPU suite short; the default (16 views, BASELINE config 2) differs only in the view count
+    p = run_bench("--impl", "reference", "--steps", "1", "--warmup", "0", "--views", "4")
     assert p.returncode == 0, p.stderr[-2000:]
     lines = [l for l in p.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "steps/s" and d["higher_is_better"] is True
-    assert d["metric"] == "16-view 256^2 DDIM denoise-steps/sec" and d["value"] > 0
+    assert d["metric"] == "4-view 256^2 DDIM denoise-steps/sec" and d["value"] > 0
+    sys.path.insert(0, ROOT)
+    import bench
+    assert bench.metric_name(16, 32) == "16-view 256^2 DDIM denoise-steps/sec"   # BASELINE.json's metric by default
+    assert bench.main.__module__ == "bench"
     assert d["config"]["workload"].startswith("FLAME face")
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] == os.cpu_count() and cb["value"] == d["value"] and "views" in cb["sample"]
+    assert cb["kind"] == "port" and cb["cores"] == os.cpu_count() and cb["value"] == d["value"]
+    assert "4 of 4 views" in cb["sample"]   # full steps of the workload, never a view sub-sample scaled up
     assert d["e2e"] == {"value": d["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert abs(d["ms_per_step"] - 1000.0 / d["value"]) < 1e-6 * d["ms_per_step"]
 
