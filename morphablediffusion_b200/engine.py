@@ -45,6 +45,7 @@ class Engine:
         self.S, self.V, self.D = latent_size, cfg.spatial_volume_size, cfg.frustum_depth
         self.n_views = self.view0 = self.n_local = 0
         self.ddim = (int(ddim_steps), float(ddim_eta))
+        self.bind_count = 0   # md_bind_sample calls so far (tests check that edited batches re-bind)
 
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
@@ -95,6 +96,7 @@ class Engine:
                                          verts.shape[0], n_views, view0, n_local, PROJECTIONS[projection],
                                          nat.cur_stream()), "md_bind_sample")
         self.n_views, self.view0, self.n_local = n_views, view0, n_local
+        self.bind_count += 1
 
     # ------------------------------------------------------------------ stages
     def embed_time(self, timestep):

@@ -67,7 +67,8 @@ def test_denoise_step_baseline_configs(state_dict, name, chunk):
 def test_view_sweep_n64_properties(state_dict):
     """N = 64 (top of BASELINE config 5) has no CPU golden (a reference step takes minutes); properties instead:
     (1) every view's epsilon is finite and of unit scale; (2) views are processed independently given the shared
-    spatial volume, so the 64-view step in chunks of 16 equals the same step in chunks of 32 to bf16 run-to-run level;
+    spatial volume, so the 64-view step in chunks of 16 equals the same step in chunks of 32 to the run-to-run level of two
+    identical chunk-16 runs;
     (3) DDIM noise is keyed by the global view index, so the chunking does not change x_prev either."""
     from morphablediffusion_b200 import synth
     from morphablediffusion_b200.engine import Engine
@@ -75,7 +76,7 @@ def test_view_sweep_n64_properties(state_dict):
     batch = synth.make_batch(n)
     x_t, x_input, clip = synth.make_inputs(n)
     outs = []
-    for chunk in (16, 32):
+    for chunk in (16, 16, 32):
         eng = Engine(max_views_per_call=chunk)
         eng.load_state_dict(state_dict)
         eng.bind(batch, "perspective")
@@ -85,10 +86,17 @@ def test_view_sweep_n64_properties(state_dict):
         torch.cuda.synchronize()
         outs.append((eps.cpu(), x.cpu()))
         eng.close()
-    e16, x16 = outs[0]
-    e32, x32 = outs[1]
+    (e16, x16), (e16b, x16b), (e32, x32) = outs
     assert torch.isfinite(e16).all() and 0.3 < float(e16.std()) < 3.0
-    assert rel(e16, e32) < 2e-3 and rel(x16, x32) < 2e-3
+    # run-to-run level of the SAME configuration (fp32 atomics in the GroupNorm statistics and split-K arrival order
+    # reorder sums; bf16 roundings downstream then flip): measured 7e-3 at N = 64, the same size as the error against
+    # the fp32 reference.  A different chunking must stay at that level, and within the single-step parity bound.
+    noise = rel(e16b, e16)
+    assert noise < BF16_REL
+    assert rel(e32, e16) < max(2.0 * noise, 2e-3) and rel(x32, x16) < max(2.0 * rel(x16b, x16), 2e-3), \
+        (rel(e32, e16), noise)
+    per_view = [rel(e32[v], e16[v]) for v in range(n)]
+    assert max(per_view) < 3.0 * max(noise, 1e-3), max(per_view)   # no single view stands out (no chunk-edge bug)
 
 
 def _shell(n_views, state_dict, sample_steps=50):
@@ -156,11 +164,21 @@ def test_sampler_with_other_step_counts(state_dict):
         assert rel(out, ref) < BF16_REL, (steps, rel(out, ref))
     with pytest.raises(IndexError):
         sampler.denoise_apply(x_t.cuda(), {"x": x_input.cuda()}, clip.cuda(), None, 25, 2.0, batch=batch)
-    # the binding key is content + identity, never addresses: an in-place camera edit must re-bind
-    a = sampler.denoise_apply(x_t.cuda(), {"x": x_input.cuda()}, clip.cuda(), None, 7, 2.0, is_step0=True, batch=batch)
-    batch["target_RT"][0, 1, 0, 3] += 0.3
-    b = sampler.denoise_apply(x_t.cuda(), {"x": x_input.cuda()}, clip.cuda(), None, 7, 2.0, is_step0=True, batch=batch)
-    assert rel(b[0, 1], a[0, 1]) > 1e-3
+    # the binding key is content + identity, never addresses: an unchanged batch must not re-bind, an in-place camera
+    # edit must (with random weights the epsilon itself barely depends on one camera, so the re-bind is observed
+    # directly and through the frustum features of the edited view)
+    eng = model._engine
+    sampler.denoise_apply(x_t.cuda(), {"x": x_input.cuda()}, clip.cuda(), None, 7, 2.0, is_step0=True, batch=batch)
+    binds = eng.bind_count
+    sampler.denoise_apply(x_t.cuda(), {"x": x_input.cuda()}, clip.cuda(), None, 7, 2.0, is_step0=True, batch=batch)
+    assert eng.bind_count == binds
+    vol = eng.spatial_volume(x_t[0].cuda(), 500.0)
+    f_a = eng.frustum_feats(vol, 0, n, 500.0)[32]
+    batch["target_RT"][0, 1, :, 3] += torch.tensor([0.4, -0.3, 0.5], device="cuda")
+    sampler.denoise_apply(x_t.cuda(), {"x": x_input.cuda()}, clip.cuda(), None, 7, 2.0, is_step0=True, batch=batch)
+    assert eng.bind_count == binds + 1
+    f_b = eng.frustum_feats(vol, 0, n, 500.0)[32]
+    assert rel(f_b[0], f_a[0]) < 1e-3 and rel(f_b[1], f_a[1]) > 1e-2, (rel(f_b[0], f_a[0]), rel(f_b[1], f_a[1]))
 
 
 def test_sample_seeds_differ_between_calls_and_items(state_dict):
