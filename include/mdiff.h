@@ -66,8 +66,10 @@ typedef struct md_conv_gemm_args {
   int in_stride[3];         /* strided conv: input coord = tile coord * in_stride + tap (x,y,z); 0 -> 1.  B,D,H,W then
                                describe the INPUT tensor and the tile grid covers ceil(dim / in_stride) positions */
   int cta_pair;             /* CTA-pair (cta_group::2, 256-row tiles over two SMs) kernel: 0 = library default
-                               (off unless MD_CG2 is set), 1 = use it whenever the problem is eligible (tile width 160 or
-                               256, no split-K, at least one full wave of pairs), -1 = never */
+                               (from 24 K blocks up; MD_CG2 overrides), 1 = use it whenever the problem is eligible (tile
+                               width 160 or 256, no split-K, at least one full wave of pairs), -1 = never */
+  int tail_split;           /* last partial wave of tiles split along K: 0 = library default (on; MD_HYBRID=0 switches it
+                               off), 1 = on, -1 = off */
 } md_conv_gemm_args;
 
 MD_API int md_op_conv_gemm(const md_conv_gemm_args* args, void* stream);

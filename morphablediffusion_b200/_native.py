@@ -55,6 +55,7 @@ class ConvGemmArgs(C.Structure):
         ("ksplit", C.c_int),
         ("in_stride", C.c_int * 3),
         ("cta_pair", C.c_int),
+        ("tail_split", C.c_int),
     ]
 
 

@@ -234,6 +234,35 @@ int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
                                             (unsigned long long)Ktot, a.N);
   }
 
+  // ---- whole waves unsplit, the last partial wave split along K.  A persistent grid of G CTAs (pairs) walks T tiles
+  // in ceil(T / G) rounds; when the last round holds only rem = T mod G tiles, those are split ks = G / rem ways so
+  // that the round costs ~1/ks of a tile (plus the partial-sum exchange) instead of a whole one, e.g. 320 tiles of
+  // 256 columns on 148 SMs: 2.16 -> 3 rounds become 2 + 1/6.  Uses the split-K machinery of the tile-starved launches
+  // (workspace slots and arrival counters are indexed from the first split tile).  MD_HYBRID=0 switches it off.
+  const int tiles_all = p.cg2 ? p.m_pairs * p.n_tiles : p.m_tiles * p.n_tiles;
+  const int slots = p.cg2 ? cg2_pairs : std::min(tiles_all, num_sms());
+  const bool contig = p.n_tiles == 1 && p.ksplit == 1 && tiles_all > 2 * slots;
+  p.items_main = p.ksplit > 1 ? 0 : tiles_all;
+  {
+    static const int hybrid_env = getenv("MD_HYBRID") ? atoi(getenv("MD_HYBRID")) : 1;
+    const int hybrid = a.tail_split != 0 ? (a.tail_split > 0 ? 1 : 0) : hybrid_env;
+    if (hybrid && p.ksplit == 1 && a.ksplit == 0 && !contig && sw && tiles_all > slots && kblocks_all >= 8) {
+      const int rem = tiles_all % slots;
+      const int ks = rem ? std::min(std::min(slots / rem, kblocks_all / 4), 6) : 1;
+      if (ks >= 2) {
+        const size_t ws_slots = static_cast<size_t>(rem) * (p.cg2 ? 2 : 1);
+        const size_t need = ws_slots * ks * 128 * BN * sizeof(float);
+        if (need <= sw->bytes && ws_slots * kEpiWarps <= sw->ints) {
+          p.ksplit = ks;
+          p.items_main = tiles_all - rem;
+          p.split_ws = sw->ws;
+          p.split_cnt = sw->cnt;
+        }
+      }
+    }
+  }
+  p.total_items = p.items_main + (tiles_all - p.items_main) * p.ksplit;
+
   // ---- TMA-store epilogue: one output, no fused statistics, no residual, no split-K, plain output geometry; the
   // output leaves as 16-column x 32-row boxes of the per-warp staging tile.  Measured (gpurun r01y/r01z): -10..19 % on
   // the bf16-out GEMMs without residual (qkv, GEGLU); fp32-residual launches get 5-11 % slower this way (their per-lane
@@ -248,7 +277,7 @@ int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
                        p.OH == p.H && p.OD == p.D;
     void* optr = a.out_f32 ? static_cast<void*>(a.out_f32) : a.out_bf16;
     if (epi_tma_on && !p.cg2 && one_out && plain && !a.col_stats && !a.res_bf16 && (!a.res_f32 || epi_tma_res) &&
-        p.ksplit == 1 &&
+        (p.ksplit == 1 || p.items_main > 0) &&
         !(reinterpret_cast<uintptr_t>(optr) & 15)) {
       // a lane quarter's 32 rows inside the tile box (x fastest): sub-box dims and the origin of every quarter
       int qd[4], bd4[4] = {p.bw, p.bh, p.bd, p.bb}, rem = 32;
@@ -284,13 +313,13 @@ int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
   p.fd_nxb = make_fastdiv(p.nxb);
   p.fd_nyb = make_fastdiv(p.nyb);
   p.fd_nzb = make_fastdiv(p.nzb);
-  const int total = p.cg2 ? p.m_pairs * p.n_tiles : p.m_tiles * p.n_tiles * p.ksplit;
-  const int grid = p.cg2 ? 2 * cg2_pairs : std::min(total, num_sms());
-  p.contig = (p.n_tiles == 1 && p.ksplit == 1 && total > 2 * (p.cg2 ? cg2_pairs : grid)) ? 1 : 0;
+  const int total = p.total_items;
+  const int grid = p.cg2 ? 2 * std::min(total, cg2_pairs) : std::min(total, num_sms());
+  p.contig = contig ? 1 : 0;
   static const bool trace = getenv("MD_TRACE") != nullptr;
   if (trace)
-    fprintf(stderr, "conv_gemm B=%d D=%d H=%d W=%d Cin=%d taps=%d N=%d BN=%d tiles=%dx%d ks=%d cg2=%d act=%d f32=%d bf16=%d res=%d\n",
-            a.B, a.D, a.H, a.W, a.Cin, a.ntaps, a.N, BN, p.m_tiles, p.n_tiles, p.ksplit, p.cg2, a.act, a.out_f32 != nullptr,
+    fprintf(stderr, "conv_gemm B=%d D=%d H=%d W=%d Cin=%d taps=%d N=%d BN=%d tiles=%dx%d ks=%d main=%d cg2=%d act=%d f32=%d bf16=%d res=%d\n",
+            a.B, a.D, a.H, a.W, a.Cin, a.ntaps, a.N, BN, p.m_tiles, p.n_tiles, p.ksplit, p.items_main, p.cg2, a.act, a.out_f32 != nullptr,
             a.out_bf16 != nullptr, a.res_f32 != nullptr || a.res_bf16 != nullptr);
   if (p.cg2)
     return (BN == 160) ? launch_conv_gemm_cg2_bn160(tmA, tmB, tmO, p, grid, stream, nullptr)

@@ -82,10 +82,14 @@ struct ConvGemmParams {
   float* col_stats; // optional [B][stats_ld][2]: per-(sample, channel) sum / sum of squares of the fp32 result
   int stats_ld;
   int contig;       // contiguous tile run per CTA (see kernel)
-  int ksplit;       // split-K factor: work item = (tile, split); partial accumulators meet in split_ws, the last
-                    // arriving warp of every (tile, epilogue-warp) pair reduces them and runs the real epilogue
-  float* split_ws;  // [tiles][ksplit][128][BN] fp32
-  int* split_cnt;   // [tiles][EPI_WARPS] arrival counters (zero on entry, reset by the last arrival)
+  int ksplit;       // split-K factor of the SPLIT tiles: work item = (tile, split); partial accumulators meet in split_ws,
+                    // the last arriving warp of every (tile, epilogue-warp) pair reduces them and runs the real epilogue
+  int items_main;   // leading tiles (CTA-pair kernel: pair tiles) that run unsplit; the tiles behind them are split
+                    // ksplit ways.  0 = every tile split (tile-starved problems); all tiles (ksplit 1) = no split;
+                    // in between = whole waves unsplit and the last partial wave split along K to fill the machine
+  int total_items;  // items_main + (tiles - items_main) * ksplit
+  float* split_ws;  // [split tiles (x2 in the pair kernel)][ksplit][128][BN] fp32
+  int* split_cnt;   // [split tiles (x2)][EPI_WARPS] arrival counters (zero on entry, reset by the last arrival)
   int isx, isy, isz; // input coordinate = output-tile coordinate * is + tap offset (strided convolution via TMA element strides)
   FastDiv fd_ksplit, fd_ntiles, fd_nxb, fd_nyb, fd_nzb;
   int epi_tma;  // 1: the output leaves through TMA stores of the per-warp staging tile (no fused statistics, one output,
@@ -102,11 +106,26 @@ struct ConvGemmParams {
 
 // work item -> (n tile, box coordinates, K split)
 struct TileCoord {
-  int tile, sp, n_tile, xb, yb, zb, bblk;
+  int tile, sp, ns, n_tile, xb, yb, zb, bblk;   // ns: number of K splits of this tile (1 or p.ksplit)
 };
+// work item -> (tile, split index, split count)
+__device__ __forceinline__ void decode_split(const ConvGemmParams& p, int item, int& tile, int& sp, int& ns) {
+  if (item < p.items_main) {
+    tile = item; sp = 0; ns = 1;
+  } else {
+    int q;
+    fdivmod(item - p.items_main, p.fd_ksplit, q, sp);
+    tile = p.items_main + q; ns = p.ksplit;
+  }
+}
+// K-block range [kb0, kb1) of split sp out of ns
+__device__ __forceinline__ void split_krange(const ConvGemmParams& p, int kblocks, int sp, int ns, int& kb0, int& kb1) {
+  if (ns == 1) { kb0 = 0; kb1 = kblocks; }
+  else { kb0 = fdiv(kblocks * sp, p.fd_ksplit); kb1 = fdiv(kblocks * (sp + 1), p.fd_ksplit); }
+}
 __device__ __forceinline__ TileCoord decode_item(const ConvGemmParams& p, int item) {
   TileCoord t;
-  fdivmod(item, p.fd_ksplit, t.tile, t.sp);
+  decode_split(p, item, t.tile, t.sp, t.ns);
   int m;
   fdivmod(t.tile, p.fd_ntiles, m, t.n_tile);
   if (p.cg2) m = 2 * m + static_cast<int>(cluster_ctarank());  // an odd tile count leaves the last pair's second
@@ -472,10 +491,11 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, const CUt
   // The residual rows of a tile are read chunk by chunk in the coalesced phase, each read a full memory round trip
   // on the warp's critical path: one tile ahead, the first warp of every lane quarter pulls its 32 residual rows
   // (this tile's column range) into L2 so those reads become L2 hits.
-  const bool do_prefetch = (c_begin == 0) && (p.ksplit == 1) && (p.res_f32 != nullptr || p.res_bf16 != nullptr);
+  const bool do_prefetch = (c_begin == 0) && (p.res_f32 != nullptr || p.res_bf16 != nullptr);
   auto prefetch_residual = [&](int item) {
     if (!do_prefetch || item >= tile_end) return;
     const TileCoord t = decode_item(p, item);
+    if (t.ns != 1) return;   // split tiles: only the last arrival reads the residual
     const int x = t.xb * p.bw + ix, y = t.yb * p.bh + iy, z = t.zb * p.bd + iz, b = t.bblk * p.bb + rr;
     const int n0 = t.n_tile * out_cols_t;
     const int cols = min(out_cols_t, n_limit_t - n0);
@@ -527,11 +547,13 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, const CUt
     }
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * BN;
     bool run_epilogue = true;
-    if (p.ksplit > 1) {
+    if (tc.ns > 1) {
       // split-K: publish this warp's partial accumulators, take a ticket; the last arrival for this (tile, warp)
       // adds the other splits' partials back into TMEM and then runs the ordinary epilogue on the full sums.
       constexpr int acc_chunks = BN / kChunk;
-      float* ws_tile = p.split_ws + static_cast<size_t>(tile) * p.ksplit * (128 * BN);
+      // slot of this CTA's tile among the split tiles (both CTAs of a pair work on the same pair tile)
+      const int ws_idx = p.cg2 ? 2 * (tile - p.items_main) + static_cast<int>(cluster_ctarank()) : tile - p.items_main;
+      float* ws_tile = p.split_ws + static_cast<size_t>(ws_idx) * p.ksplit * (128 * BN);
       float* mine = ws_tile + static_cast<size_t>(sp) * (128 * BN) + static_cast<size_t>(r) * BN;
       for (int c = c_begin; c < acc_chunks; c += kCStride) {
         uint32_t v[16];
@@ -547,7 +569,7 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, const CUt
       __syncwarp();
       int last = 0;
       if (lane == 0) {
-        int* cnt = p.split_cnt + tile * kEpiWarps + ew;
+        int* cnt = p.split_cnt + ws_idx * kEpiWarps + ew;
         last = (atomicAdd(cnt, 1) == p.ksplit - 1) ? 1 : 0;
         if (last) *cnt = 0;  // ready for the next launch
       }
@@ -660,7 +682,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   pdl_grid_sync();
   KPROF(2, threadIdx.x == 0);
 
-  const int total_tiles = p.m_tiles * p.n_tiles * p.ksplit;  // work items: (tile, K split)
+  const int total_tiles = p.total_items;  // work items: (tile, K split)
   const int kblocks = p.ntaps * p.kblocks_per_tap;
   // Tile schedule: interleaved (tile = cta + i*grid) or, for tall single-N-tile problems, one contiguous run per CTA
   // (consecutive tiles then share a sample, which lets the epilogue keep GroupNorm partial sums in registers).
@@ -679,7 +701,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int plt = 0;
     for (int item = tile_begin; item < tile_end; item += tile_step, ++plt) {
       const TileCoord tc = decode_item(p, item);
-      const int kb0 = fdiv(kblocks * tc.sp, p.fd_ksplit), kb1 = fdiv(kblocks * (tc.sp + 1), p.fd_ksplit);
+      int kb0, kb1;
+      split_krange(p, kblocks, tc.sp, tc.ns, kb0, kb1);
       const int x0 = tc.xb * p.bw * p.isx, y0 = tc.yb * p.bh * p.isy, z0 = tc.zb * p.bd * p.isz, b0 = tc.bblk * p.bb;
       const int n0 = tc.n_tile * BN;
       int tap = kb0 / p.kblocks_per_tap, kc = kb0 - tap * p.kblocks_per_tap;
@@ -713,8 +736,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int it = 0;
     int lt = 0;
     for (int item = tile_begin; item < tile_end; item += tile_step, ++lt) {
-      const int sp = item - fdiv(item, p.fd_ksplit) * p.ksplit;
-      const int nkb = fdiv(kblocks * (sp + 1), p.fd_ksplit) - fdiv(kblocks * sp, p.fd_ksplit);
+      int tile_, sp, ns, kb0, kb1;
+      decode_split(p, item, tile_, sp, ns);
+      split_krange(p, kblocks, sp, ns, kb0, kb1);
+      const int nkb = kb1 - kb0;
       const int a = lt & 1;
       const uint32_t aph = (lt >> 1) & 1;
       mbar_wait(&tmem_empty[a], aph ^ 1);
@@ -824,7 +849,7 @@ conv_gemm_cg2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 
   const int npairs = static_cast<int>(gridDim.x) >> 1;
   const int pair = static_cast<int>(blockIdx.x) >> 1;
-  const int total_tiles = p.m_pairs * p.n_tiles;  // work items: (M-tile pair, N tile); no split-K in this kernel
+  const int total_tiles = p.total_items;  // work items: (M-tile pair, N tile, K split)
   const int kblocks = p.ntaps * p.kblocks_per_tap;
   const int per_pair = (total_tiles + npairs - 1) / npairs;
   const int tile_begin = p.contig ? pair * per_pair : pair;
@@ -840,8 +865,10 @@ conv_gemm_cg2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const TileCoord tc = decode_item(p, item);
       const int x0 = tc.xb * p.bw * p.isx, y0 = tc.yb * p.bh * p.isy, z0 = tc.zb * p.bd * p.isz, b0 = tc.bblk * p.bb;
       const int n0 = tc.n_tile * BN + static_cast<int>(rank) * (BN / 2);
-      int tap = 0, kc = 0;
-      for (int kb = 0; kb < kblocks; ++kb) {
+      int kb0, kb1;
+      split_krange(p, kblocks, tc.sp, tc.ns, kb0, kb1);
+      int tap = kb0 / p.kblocks_per_tap, kc = kb0 - tap * p.kblocks_per_tap;
+      for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&empty_bar[s], ph ^ 1);
         uint8_t* sa = smem + s * S::kStageBytes;
         uint8_t* sb = sa + S::kABytes;
@@ -868,7 +895,11 @@ conv_gemm_cg2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         mbar_wait(&tmem_empty[a], aph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + a * BN;
-        for (int kb = 0; kb < kblocks; ++kb) {
+        int tile_, sp, ns, kb0, kb1;
+        decode_split(p, item, tile_, sp, ns);
+        split_krange(p, kblocks, sp, ns, kb0, kb1);
+        const int nkb = kb1 - kb0;
+        for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + s * S::kStageBytes);

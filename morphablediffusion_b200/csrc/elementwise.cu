@@ -1,6 +1,6 @@
 // HBM-bound helper kernels of the denoise step: GroupNorm (column statistics -> per-(sample,channel) affine ->
-// fused activation), LayerNorm, small linear layers (time/view embeddings), small-channel direct convolutions,
-// nearest upsample, stride-2 patch gather, CFG combine + DDIM update.  All activations are channels-last.
+// fused activation), LayerNorm, small linear layers (time/view embeddings), nearest upsample, layout helpers,
+// CFG combine + DDIM update.  All activations are channels-last.
 #include "host.h"
 #include "ptx.cuh"
 #include "kernels.h"
@@ -130,11 +130,28 @@ __global__ void gn_finalize_kernel(float* __restrict__ stats0, int C0, float* __
 // Stage 3: y = act(x*scale + shift) -> bf16 (and optionally the raw x as bf16, used by 1x1 skip convolutions).
 // Thread = (channel quad cq, row phase rsub): its four (scale, shift) pairs stay in registers and the row loop has no
 // index arithmetic beyond one add, so the pass runs at HBM speed.  grid = (row chunks, samples).
+// The first kAffPre rows of a thread can be requested by the caller BEFORE the scale/shift are known (pre[] holds them,
+// `npre` of them valid): the fused kernel issues them ahead of its statistics phase so that the group reduction and
+// its two block barriers overlap the first memory round trip instead of preceding it.
+constexpr int kAffPre = 4;
+template <typename T0, typename T1>
+__device__ __forceinline__ float4 affine_load(const T0* p0, int C0, const T1* p1, int C1, bool first, int r) {
+  return first ? load4(p0 + static_cast<size_t>(r) * C0) : load4(p1 + static_cast<size_t>(r) * C1);
+}
+__device__ __forceinline__ float4 affine_apply(const float4 v, const float4 s01, const float4 s23, int act) {
+  float4 y = make_float4(v.x * s01.x + s01.y, v.y * s01.z + s01.w, v.z * s23.x + s23.y, v.w * s23.z + s23.w);
+  if (act == ACT_SILU) {
+    y.x = silu_f(y.x); y.y = silu_f(y.y); y.z = silu_f(y.z); y.w = silu_f(y.w);
+  } else if (act == ACT_RELU) {
+    y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f);
+  }
+  return y;
+}
 template <typename T0, typename T1>
 __device__ __forceinline__ void affine_rows(const T0* __restrict__ x0, int C0, const T1* __restrict__ x1, int C1,
                                             const float4 s01, const float4 s23, __nv_bfloat16* __restrict__ out,
                                             __nv_bfloat16* __restrict__ raw, int b, int rows, int r0, int r1, int c,
-                                            int rsub, int R, int act) {
+                                            int rsub, int R, int act, const float4* pre = nullptr) {
   const int C = C0 + C1;
   const size_t base = static_cast<size_t>(b) * rows;
   const bool first = c < C0;
@@ -142,17 +159,31 @@ __device__ __forceinline__ void affine_rows(const T0* __restrict__ x0, int C0, c
   const T1* p1 = first ? nullptr : x1 + base * C1 + (c - C0);
   __nv_bfloat16* po = out + base * C + c;
   __nv_bfloat16* pr = raw ? raw + base * C + c : nullptr;
-#pragma unroll 4
-  for (int r = r0 + rsub; r < r1; r += R) {
-    const float4 v = first ? load4(p0 + static_cast<size_t>(r) * C0) : load4(p1 + static_cast<size_t>(r) * C1);
-    if (pr) store4(pr + static_cast<size_t>(r) * C, v);
-    float4 y = make_float4(v.x * s01.x + s01.y, v.y * s01.z + s01.w, v.z * s23.x + s23.y, v.w * s23.z + s23.w);
-    if (act == ACT_SILU) {
-      y.x = silu_f(y.x); y.y = silu_f(y.y); y.z = silu_f(y.z); y.w = silu_f(y.w);
-    } else if (act == ACT_RELU) {
-      y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f);
+  int r = r0 + rsub;
+  if (pre) {
+#pragma unroll
+    for (int k = 0; k < kAffPre; ++k, r += R) {
+      if (r < r1) {
+        if (pr) store4(pr + static_cast<size_t>(r) * C, pre[k]);
+        store4(po + static_cast<size_t>(r) * C, affine_apply(pre[k], s01, s23, act));
+      }
     }
-    store4(po + static_cast<size_t>(r) * C, y);
+  }
+  // batches of four rows: all four loads are in flight before the first store
+  for (; r + 3 * R < r1; r += 4 * R) {
+    float4 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = affine_load(p0, C0, p1, C1, first, r + k * R);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (pr) store4(pr + static_cast<size_t>(r + k * R) * C, v[k]);
+      store4(po + static_cast<size_t>(r + k * R) * C, affine_apply(v[k], s01, s23, act));
+    }
+  }
+  for (; r < r1; r += R) {
+    const float4 v = affine_load(p0, C0, p1, C1, first, r);
+    if (pr) store4(pr + static_cast<size_t>(r) * C, v);
+    store4(po + static_cast<size_t>(r) * C, affine_apply(v, s01, s23, act));
   }
 }
 
@@ -193,7 +224,22 @@ __global__ void gn_apply_fused_kernel(const T0* __restrict__ x0, int C0, const T
   const float nrows = static_cast<float>(rows);
   const int cq = threadIdx.x % CQ, rsub = threadIdx.x / CQ;
   const int c = cq * 4;
-  // this thread's affine parameters are requested first so that their latency overlaps the statistics reduction
+  // this thread's first rows and its affine parameters are requested first: their latency overlaps the statistics
+  // reduction below (two block barriers and a double-precision variance) instead of following it
+  const int r0 = blockIdx.x * rows_per_cta;
+  const int r1 = min(rows, r0 + rows_per_cta);
+  float4 pre[kAffPre];
+  if (rsub < R) {
+    const bool first = c < C0;
+    const size_t base = static_cast<size_t>(b) * rows;
+    const T0* p0 = x0 + base * C0 + c;
+    const T1* p1 = first ? nullptr : x1 + base * C1 + (c - C0);
+#pragma unroll
+    for (int k = 0; k < kAffPre; ++k) {
+      const int r = r0 + rsub + k * R;
+      pre[k] = (r < r1) ? affine_load(p0, C0, p1, C1, first, r) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
   const float4 g4 = load4(gamma + c), b4 = load4(beta + c);
   float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
   if (addvec) t4 = load4(addvec + static_cast<size_t>(b) * addvec_ld + c);
@@ -237,9 +283,8 @@ __global__ void gn_apply_fused_kernel(const T0* __restrict__ x0, int C0, const T
     sh[e] = bb[e] + (tt[e] - gsm[2 * g]) * sc[e];
     if (++rem == cpg) { rem = 0; ++g; }
   }
-  const int r0 = blockIdx.x * rows_per_cta;
   affine_rows(x0, C0, x1, C1, make_float4(sc[0], sh[0], sc[1], sh[1]), make_float4(sc[2], sh[2], sc[3], sh[3]), out, raw,
-              b, rows, r0, min(rows, r0 + rows_per_cta), c, rsub, R, act);
+              b, rows, r0, r1, c, rsub, R, act, pre);
 }
 
 // Small tensors (the 4x4 UNet level: 16 rows per sample) have no statistics from a GEMM epilogue (a 128-row tile spans
@@ -564,50 +609,6 @@ int launch_timestep_embedding(const float* t, float* out, int B, int dim, cudaSt
   return check_launch("timestep_embedding");
 }
 
-// ------------------------------------------------------------------------------------------------ direct 3x3 conv
-// Small-channel Conv2d 3x3 pad 1 (UNet conv_in 8->320).  x fp32 NHWC, W fp32 [tap][Cin][Cout], out fp32 NHWC.
-// One thread per (pixel, 4 output channels).
-__global__ void conv3x3_direct_kernel(const float* __restrict__ x, const float* __restrict__ W,
-                                      const float* __restrict__ bias, float* __restrict__ out, int B, int H, int Wd,
-                                      int Cin, int Cout) {
-  pdl_grid_sync();
-  const int CQ = Cout >> 2;
-  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
-  const size_t total = static_cast<size_t>(B) * H * Wd * CQ;
-  if (i >= total) return;
-  const int co = static_cast<int>(i % CQ) * 4;
-  size_t p = i / CQ;
-  const int xw = static_cast<int>(p % Wd); p /= Wd;
-  const int yh = static_cast<int>(p % H);
-  const int b = static_cast<int>(p / H);
-  float4 acc = bias ? *reinterpret_cast<const float4*>(bias + co) : make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int ky = 0; ky < 3; ++ky) {
-    const int yy = yh + ky - 1;
-    if (yy < 0 || yy >= H) continue;
-    for (int kx = 0; kx < 3; ++kx) {
-      const int xx = xw + kx - 1;
-      if (xx < 0 || xx >= Wd) continue;
-      const float* xp = x + ((static_cast<size_t>(b) * H + yy) * Wd + xx) * Cin;
-      const float* wp = W + static_cast<size_t>((ky * 3 + kx) * Cin) * Cout + co;
-      for (int ci = 0; ci < Cin; ++ci) {
-        const float a = xp[ci];
-        const float4 w = __ldg(reinterpret_cast<const float4*>(wp + static_cast<size_t>(ci) * Cout));
-        acc.x += a * w.x; acc.y += a * w.y; acc.z += a * w.z; acc.w += a * w.w;
-      }
-    }
-  }
-  *reinterpret_cast<float4*>(out + ((static_cast<size_t>(b) * H + yh) * Wd + xw) * Cout + co) = acc;
-}
-
-int launch_conv3x3_direct(const float* x, const float* W, const float* bias, float* out, int B, int H, int Wd, int Cin,
-                          int Cout, cudaStream_t st) {
-  if (Cout % 4) return set_error("conv3x3_direct: Cout must be a multiple of 4");
-  const size_t total = static_cast<size_t>(B) * H * Wd * (Cout / 4);
-  launch_pdl(conv3x3_direct_kernel, dim3(static_cast<unsigned>((total + 127) / 128)), dim3(128), 0, st, x, W, bias, out, B, H, Wd, Cin,
-                                                                                    Cout);
-  return check_launch("conv3x3_direct");
-}
-
 // [rows][ld] fp32 (first C columns) -> NCHW [B][C][HW]   (UNet output: the final conv runs as a GEMM padded to 8 columns)
 __global__ void rows_to_nchw_kernel(const float* __restrict__ x, int ld, float* __restrict__ out, int B, int C, int HW) {
   pdl_grid_sync();
@@ -620,53 +621,6 @@ int launch_rows_to_nchw(const float* x, int ld, float* out, int B, int C, int HW
   const int total = B * C * HW;
   launch_pdl(rows_to_nchw_kernel, dim3((total + 255) / 256), dim3(256), 0, st, x, ld, out, B, C, HW);
   return check_launch("rows_to_nchw");
-}
-
-// Final UNet conv (320 -> 4): bf16 NHWC activations, fp32 weights [tap][Cout<=4][Cin]; one warp per pixel.
-// Output is NCHW fp32 (the layout of the epsilon tensor at the API boundary).
-__global__ void conv3x3_out_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ W,
-                                   const float* __restrict__ bias, float* __restrict__ out, int B, int H, int Wd,
-                                   int Cin, int Cout) {
-  pdl_grid_sync();
-  const int lane = threadIdx.x & 31;
-  const size_t pix = (blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x) >> 5;
-  if (pix >= static_cast<size_t>(B) * H * Wd) return;
-  const int xw = static_cast<int>(pix % Wd);
-  const int yh = static_cast<int>((pix / Wd) % H);
-  const int b = static_cast<int>(pix / (static_cast<size_t>(Wd) * H));
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int ky = 0; ky < 3; ++ky) {
-    const int yy = yh + ky - 1;
-    if (yy < 0 || yy >= H) continue;
-    for (int kx = 0; kx < 3; ++kx) {
-      const int xx = xw + kx - 1;
-      if (xx < 0 || xx >= Wd) continue;
-      const __nv_bfloat16* xp = x + ((static_cast<size_t>(b) * H + yy) * Wd + xx) * Cin;
-      const float* wp = W + static_cast<size_t>(ky * 3 + kx) * Cout * Cin;
-      for (int c = lane * 2; c < Cin; c += 64) {
-        const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(xp + c);
-        const float v0 = __low2float(v), v1 = __high2float(v);
-        for (int co = 0; co < Cout; ++co) {
-          acc[co] += v0 * __ldg(wp + co * Cin + c) + v1 * __ldg(wp + co * Cin + c + 1);
-        }
-      }
-    }
-  }
-  for (int co = 0; co < Cout; ++co) {
-    float a = acc[co];
-#pragma unroll
-    for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffff, a, o);
-    if (lane == 0) out[((static_cast<size_t>(b) * Cout + co) * H + yh) * Wd + xw] = a + (bias ? bias[co] : 0.f);
-  }
-}
-
-int launch_conv3x3_out(const void* x_bf16, const float* W, const float* bias, float* out, int B, int H, int Wd, int Cin,
-                       int Cout, cudaStream_t st) {
-  if (Cout > 4 || Cin % 2) return set_error("conv3x3_out: unsupported Cout=%d Cin=%d", Cout, Cin);
-  const size_t warps = static_cast<size_t>(B) * H * Wd;
-  launch_pdl(conv3x3_out_kernel, dim3(static_cast<unsigned>((warps * 32 + 255) / 256)), dim3(256), 0, st, 
-      static_cast<const __nv_bfloat16*>(x_bf16), W, bias, out, B, H, Wd, Cin, Cout);
-  return check_launch("conv3x3_out");
 }
 
 // ------------------------------------------------------------------------------------------------ layout helpers
@@ -694,6 +648,30 @@ int launch_unet_input(const float* x, const float* xc, int xc_per_sample, float*
   const size_t total = static_cast<size_t>(cfg ? 2 * T : T) * HW * 8;
   launch_pdl(unet_input_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, st, x, xc, xc_per_sample, out, T, HW, cfg);
   return check_launch("unet_input");
+}
+
+// fp32 [rows][C] -> bf16 [rows][Cpad] with zero padding (C, Cpad multiples of 4, Cpad >= C): the UNet's 8-channel input
+// padded to one 64-channel K block, so conv_in runs on the tensor-core implicit GEMM like every other convolution.
+__global__ void pad_cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, size_t rows, int C,
+                                     int Cpad) {
+  pdl_grid_sync();
+  const int q = Cpad >> 2;
+  const size_t total = rows * q;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t r = i / q;
+    const int c = static_cast<int>(i - r * q) * 4;
+    const float4 v = c < C ? load4(x + r * C + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    store4(out + r * Cpad + c, v);
+  }
+}
+
+int launch_pad_cast_bf16(const float* x, void* out, size_t rows, int C, int Cpad, cudaStream_t st) {
+  if ((C % 4) || (Cpad % 4) || Cpad < C) return set_error("pad_cast_bf16: bad channel counts %d -> %d", C, Cpad);
+  const size_t total = rows * (Cpad / 4);
+  const int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, static_cast<size_t>(num_sms()) * 16));
+  launch_pdl(pad_cast_bf16_kernel, dim3(blocks), dim3(256), 0, st, x, static_cast<__nv_bfloat16*>(out), rows, C, Cpad);
+  return check_launch("pad_cast_bf16");
 }
 
 template <typename T>
@@ -735,49 +713,6 @@ int launch_upsample2x(const float* x, void* out, int B, int H, int W, int C, cud
   const int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, static_cast<size_t>(num_sms()) * 16));
   launch_pdl(upsample2x_kernel, dim3(blocks), dim3(256), 0, st, x, static_cast<__nv_bfloat16*>(out), B, H, W, C);
   return check_launch("upsample2x");
-}
-
-// Stride-2, pad-1, k=3 patch gather ("im2col") for the few strided convolutions:
-// in [B][D][H][W][C] -> out [B][OD][OH][OW][taps][C] with zero fill; 2-D uses D=OD=1 and 9 taps.
-template <typename T>
-__global__ void gather_s2_kernel(const T* __restrict__ x, __nv_bfloat16* __restrict__ out, int B, int D, int H, int W,
-                                 int C, int OD, int OH, int OW, int kd) {
-  pdl_grid_sync();
-  const int CQ = C / 4;
-  const int taps = kd * 9;
-  const size_t total = static_cast<size_t>(B) * OD * OH * OW * taps * CQ;
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int cq = static_cast<int>(i % CQ);
-    size_t p = i / CQ;
-    const int tap = static_cast<int>(p % taps); p /= taps;
-    const int ox = static_cast<int>(p % OW); p /= OW;
-    const int oy = static_cast<int>(p % OH); p /= OH;
-    const int oz = static_cast<int>(p % OD);
-    const int b = static_cast<int>(p / OD);
-    const int kx = tap % 3, ky = (tap / 3) % 3, kz = tap / 9;
-    const int ix = 2 * ox - 1 + kx, iy = 2 * oy - 1 + ky;
-    const int iz = (kd == 3) ? (2 * oz - 1 + kz) : oz;
-    float4 v = make_float4(0, 0, 0, 0);
-    if (ix >= 0 && ix < W && iy >= 0 && iy < H && iz >= 0 && iz < D)
-      v = load4(x + (((static_cast<size_t>(b) * D + iz) * H + iy) * W + ix) * C + cq * 4);
-    store4(out + i * 4, v);
-  }
-}
-
-int launch_gather_s2(const void* x, int x_is_bf16, void* out, int B, int D, int H, int W, int C, int kd,
-                     cudaStream_t st) {
-  const int OD = (kd == 3) ? (D + 1) / 2 : D, OH = (H + 1) / 2, OW = (W + 1) / 2;
-  const size_t total = static_cast<size_t>(B) * OD * OH * OW * kd * 9 * (C / 4);
-  const int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, static_cast<size_t>(num_sms()) * 16));
-  if (x_is_bf16)
-    launch_pdl(gather_s2_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, st, static_cast<const __nv_bfloat16*>(x),
-                                                            static_cast<__nv_bfloat16*>(out), B, D, H, W, C, OD, OH,
-                                                            OW, kd);
-  else
-    launch_pdl(gather_s2_kernel<float>, dim3(blocks), dim3(256), 0, st, static_cast<const float*>(x), static_cast<__nv_bfloat16*>(out), B,
-                                                    D, H, W, C, OD, OH, OW, kd);
-  return check_launch("gather_s2");
 }
 
 // NCDHW fp32 -> channels-last bf16 (API-boundary transposition of caller-supplied frustum volumes)

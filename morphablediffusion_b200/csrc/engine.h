@@ -64,7 +64,7 @@ struct UNetW {
   const float* te0_w = nullptr; const float* te0_b = nullptr; const float* te2_w = nullptr; const float* te2_b = nullptr;
   GemmW emb_g; int emb_total = 0;   // concatenated emb_layers.1 of all ResBlocks: [emb_total][emb_dim]
   GemmW v2_g; int v2_total = 0;     // concatenated (attn2.to_out . attn2.to_v) of all transformer blocks: [v2_total][ctx]
-  float* conv_in_w = nullptr; const float* conv_in_b = nullptr;       // fp32 [tap][Cin][Cout]
+  GemmW conv_in_g;                  // conv_in with Cin zero-padded to one 64-channel K block: bf16 [mch][9][64]
   std::vector<std::vector<UNetLayer>> input_blocks, output_blocks;
   ResW mid0, mid2; STW mid1;
   DepthW mid_cond; std::vector<DepthW> out_cond;

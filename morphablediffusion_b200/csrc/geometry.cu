@@ -1,7 +1,6 @@
 // Geometry group of the denoise step (HBM / latency bound):
 //   voxelize            mesh vertices -> voxel indices (generate_face.py:214-225), bit-exact integer rule
 //   target_encoder      NoisyTargetViewEncoder (network.py:163-207), one CTA per view, everything in shared memory
-//   unproject           per-view latent features -> 32^3 volume (utils.py:20-76 + grid_sample 2-D)
 //   vertex_features     fused unproject + trilinear gather at the mesh vertices, summed over views
 //   sparse_conv         rulebook gather-conv with folded BatchNorm + ReLU (network.py:74-161)
 //   volume_resample     sparse-conv output -> 32^3 world grid (morphable_diffusion.py:234-255)
@@ -485,36 +484,6 @@ __device__ __forceinline__ void bilinear16_acc(const float* __restrict__ fmap, i
 __device__ __forceinline__ float linspace_at(float length, int V, int i) {
   const float step = (2.f * length) / static_cast<float>(V - 1);
   return (i < V / 2) ? (-length + step * i) : (length - step * (V - 1 - i));
-}
-
-// ------------------------------------------------------------------------------------------------ unproject (K2)
-// feats [N][size*size][16] -> vol [N][V][V][V][16] (channels-last; index (d,h,w) <-> world (x=l[w], y=l[h], z=l[d]))
-__global__ void unproject_kernel(const float* __restrict__ feats, const float* __restrict__ proj, int ortho, int size,
-                                 int V, float length, float* __restrict__ vol, int n_views) {
-  pdl_grid_sync();
-  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
-  const size_t total = static_cast<size_t>(n_views) * V * V * V * 4;
-  if (i >= total) return;
-  const int cq = static_cast<int>(i & 3);
-  size_t r = i >> 2;
-  const int w = static_cast<int>(r % V); r /= V;
-  const int h = static_cast<int>(r % V); r /= V;
-  const int d = static_cast<int>(r % V);
-  const int n = static_cast<int>(r / V);
-  float px, py;
-  project_point(proj + n * 12, ortho, linspace_at(length, V, w), linspace_at(length, V, h), linspace_at(length, V, d),
-                size, px, py);
-  float4 acc = make_float4(0, 0, 0, 0);
-  bilinear16_acc(feats + static_cast<size_t>(n) * size * size * 16, size, px, py, cq, 1.f, acc);
-  *reinterpret_cast<float4*>(vol + (i >> 2) * 16 + cq * 4) = acc;
-}
-
-int launch_unproject(const float* feats, const float* proj, int ortho, int size, int V, float length, float* vol,
-                     int n_views, cudaStream_t st) {
-  const size_t total = static_cast<size_t>(n_views) * V * V * V * 4;
-  launch_pdl(unproject_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, st, feats, proj, ortho, size, V, length, vol,
-                                                                               n_views);
-  return check_launch("unproject");
 }
 
 // ------------------------------------------------------------------------------------------------ vertex features (K2+K3)

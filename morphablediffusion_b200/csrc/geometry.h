@@ -20,8 +20,6 @@ struct EncWeightsHost {
 int launch_voxelize(const float* vertices, int nv, int32_t* coord, int32_t* out_sh, float* bounds, cudaStream_t st);
 int launch_target_encoder(const float* x, const float* t_embed, const float* v_embed, const EncWeightsHost& w,
                           float* out, int n_views, int tdim, int vdim, int S, cudaStream_t st);
-int launch_unproject(const float* feats, const float* proj, int ortho, int size, int V, float length, float* vol,
-                     int n_views, cudaStream_t st);
 int launch_vertex_features(const float* feats, const float* proj, int ortho, int size, int V, float length,
                            const float* vertices, int nv, int n_views, float* out, cudaStream_t st);
 int launch_smpl_scatter(const float* vsum, float inv_views, const float* W, const float* bias,

@@ -33,17 +33,12 @@ int launch_layer_norm(float* x, const float* addvec, int addvec_ld, const float*
 int launch_small_linear(const float* x, int ldx, const float* W, const float* bias, float* out, int ldo, int B, int K,
                         int N, int act_in, int act_out, int accumulate, cudaStream_t st);
 int launch_timestep_embedding(const float* t, float* out, int B, int dim, cudaStream_t st);
-int launch_conv3x3_direct(const float* x, const float* W, const float* bias, float* out, int B, int H, int Wd, int Cin,
-                          int Cout, cudaStream_t st);
-int launch_conv3x3_out(const void* x_bf16, const float* W, const float* bias, float* out, int B, int H, int Wd, int Cin,
-                       int Cout, cudaStream_t st);
 int launch_rows_to_nchw(const float* x, int ld, float* out, int B, int C, int HW, cudaStream_t st);
 int launch_unet_input(const float* x, const float* xc, int xc_per_sample, float* out, int T, int HW, int cfg,
                       cudaStream_t st);
 int launch_cast_bf16(const float* x, void* out, size_t n, cudaStream_t st);
+int launch_pad_cast_bf16(const float* x, void* out, size_t rows, int C, int Cpad, cudaStream_t st);
 int launch_upsample2x(const float* x, void* out, int B, int H, int W, int C, cudaStream_t st);
-int launch_gather_s2(const void* x, int x_is_bf16, void* out, int B, int D, int H, int W, int C, int kd,
-                     cudaStream_t st);
 int launch_ncdhw_to_cl_bf16(const float* x, void* out, int B, int C, size_t S, cudaStream_t st);
 int launch_cl_to_ncdhw(const void* x, int x_is_bf16, float* out, int B, int C, size_t S, cudaStream_t st);
 int launch_cfg_ddim(const float* eps, float* x, float* eps_out, const float* noise, int T, int n_per_view, int cfg,

@@ -106,18 +106,20 @@ struct Fwd {
   }
 
   // ResBlock._forward (openaimodel.py:256-276).  Input is (x0 | x1) channel-concatenated (x1 may be null).
-  int res_block(const ResW& r, const float* x0, int C0, const float* x1, int C1, int H, int W, float* out) {
+  // out_b: optional bf16 copy of the result for a consumer that needs a GEMM operand (downsample, depth transformer)
+  int res_block(const ResW& r, const float* x0, int C0, const float* x1, int C1, int H, int W, float* out,
+                bf16* out_b = nullptr) {
     const size_t rows = static_cast<size_t>(B) * H * W;
     const size_t m = A().mark();
     bf16* a1 = A().get<bf16>(rows * r.cin);
     bf16* raw = r.has_skip ? A().get<bf16>(rows * r.cin) : nullptr;
-    float* h1 = A().get<float>(rows * r.cout);
+    bf16* h1 = A().get<bf16>(rows * r.cout);   // consumed by GroupNorm only: bf16 (statistics come from the fp32 accumulators)
     bf16* a2 = A().get<bf16>(rows * r.cout);
     float* skip = r.has_skip ? A().get<float>(rows * r.cout) : nullptr;
     if (A().failed) return set_error("workspace exhausted (res block)");
     MD_CHECK(gn(x0, C0, false, x1, C1, B, H * W, 32, 1e-5f, r.n1, ACT_SILU, a1, raw));
-    MD_CHECK(conv(a1, B, H, W, r.c1, emb_all + r.emb_off, c.unet.emb_total, nullptr, h1, nullptr, true));
-    MD_CHECK(gn(h1, r.cout, false, nullptr, 0, B, H * W, 32, 1e-5f, r.n2, ACT_SILU, a2, nullptr));
+    MD_CHECK(conv(a1, B, H, W, r.c1, emb_all + r.emb_off, c.unet.emb_total, nullptr, nullptr, h1, true));
+    MD_CHECK(gn(h1, r.cout, true, nullptr, 0, B, H * W, 32, 1e-5f, r.n2, ACT_SILU, a2, nullptr));
     const float* resid = x0;
     if (r.has_skip) {
       MD_CHECK(conv(raw, B, H, W, r.skip, nullptr, 0, nullptr, skip, nullptr, false));
@@ -125,13 +127,13 @@ struct Fwd {
     } else if (C1 != 0) {
       return set_error("res block: identity skip with concatenated input");
     }
-    MD_CHECK(conv(a2, B, H, W, r.c2, nullptr, 0, resid, out, nullptr, true));
+    MD_CHECK(conv(a2, B, H, W, r.c2, nullptr, 0, resid, out, out_b, true));
     A().release(m);
     return 0;
   }
 
   // SpatialTransformer.forward (ldm/modules/attention.py:325-336), depth 1, single-token context.
-  int spatial_transformer(const STW& s, const float* x_in, int H, int W, float* out) {
+  int spatial_transformer(const STW& s, const float* x_in, int H, int W, float* out, bf16* out_b = nullptr) {
     const int C = s.C;
     const size_t S = static_cast<size_t>(H) * W;
     const size_t rows = static_cast<size_t>(B) * S;
@@ -157,32 +159,33 @@ struct Fwd {
                                1e-5f, st));
     MD_CHECK(gemm(ln, B, S, s.ff1, nullptr, nullptr, ff, false, ACT_GEGLU));
     MD_CHECK(gemm(ff, B, S, s.ff2, x, nullptr, xb, false));
-    MD_CHECK(gemm(xb, B, S, s.proj_out, x_in, out, nullptr, true));
+    MD_CHECK(gemm(xb, B, S, s.proj_out, x_in, out, out_b, true));
     A().release(m);
     return 0;
   }
 
   // DepthTransformer._forward + DepthAttention.forward (ldm/models/diffusion/attention.py:78-84,26-47), with the
   // attention re-associated (attention.cu) and the zero-volume samples (n_ctx..B-1) short-circuited.
-  int depth_transformer(const DepthW& d, const float* x_in, int H, int W, const bf16* ctx, int D, float* out) {
+  int depth_transformer(const DepthW& d, const float* x_in, const bf16* x_in_b, int H, int W, const bf16* ctx, int D,
+                        float* out) {
     const size_t S = static_cast<size_t>(H) * W;
     const size_t rows = static_cast<size_t>(B) * S;
     const size_t crows = static_cast<size_t>(n_ctx) * S * D;
     const size_t m = A().mark();
-    bf16* xb = A().get<bf16>(rows * d.dim);
-    float* y = A().get<float>(rows * d.inner);
+    bf16* xb = x_in_b ? nullptr : A().get<bf16>(rows * d.dim);
+    bf16* y = A().get<bf16>(rows * d.inner);    // y, y2, y3 feed GroupNorms only: bf16
     bf16* xq = A().get<bf16>(rows * d.inner);
     bf16* qp = A().get<bf16>(static_cast<size_t>(n_ctx) * S * 4 * d.ctx);
     bf16* c1 = A().get<bf16>(crows * d.ctx);
     bf16* cbar = A().get<bf16>(rows * 4 * d.ctx);
-    float* y2 = A().get<float>(rows * d.inner);
+    bf16* y2 = A().get<bf16>(rows * d.inner);
     bf16* a1 = A().get<bf16>(rows * d.inner);
-    float* y3 = A().get<float>(rows * d.inner);
+    bf16* y3 = A().get<bf16>(rows * d.inner);
     bf16* a2 = A().get<bf16>(rows * d.inner);
     if (A().failed) return set_error("workspace exhausted (depth transformer)");
-    MD_CHECK(launch_cast_bf16(x_in, xb, rows * d.dim, st));
-    MD_CHECK(gemm(xb, B, S, d.proj_in, nullptr, y, nullptr, true));
-    MD_CHECK(gn(y, d.inner, false, nullptr, 0, B, static_cast<int>(S), 8, 1e-5f, d.gn_in, ACT_SILU, xq, nullptr));
+    if (!x_in_b) MD_CHECK(launch_cast_bf16(x_in, xb, rows * d.dim, st));
+    MD_CHECK(gemm(x_in_b ? x_in_b : xb, B, S, d.proj_in, nullptr, nullptr, y, true));
+    MD_CHECK(gn(y, d.inner, true, nullptr, 0, B, static_cast<int>(S), 8, 1e-5f, d.gn_in, ACT_SILU, xq, nullptr));
     // queries mapped into context space (only the samples that own a volume)
     MD_CHECK(gemm(xq, n_ctx, S, d.wqk, nullptr, nullptr, qp, false));
     // context branch: proj_context conv -> GroupNorm statistics; the normalisation + ReLU is applied on read
@@ -191,25 +194,25 @@ struct Fwd {
     MD_CHECK(gn(c1, d.ctx, true, nullptr, 0, n_ctx, static_cast<int>(S * D), 8, 1e-5f, d.gn_ctx, ACT_RELU, nullptr, nullptr,
                 &ss_ctx));
     MD_CHECK(launch_depth_attention(qp, c1, ss_ctx, d.gn_ctx.b, cbar, n_ctx, B, D, static_cast<int>(S), d.ctx, st));
-    MD_CHECK(gemm(cbar, B, S, d.wov, nullptr, y2, nullptr, true));
-    MD_CHECK(gn(y2, d.inner, false, nullptr, 0, B, static_cast<int>(S), 8, 1e-5f, d.gn_o1, ACT_RELU, a1, nullptr));
-    MD_CHECK(conv(a1, B, H, W, d.conv1, nullptr, 0, nullptr, y3, nullptr, true));
-    MD_CHECK(gn(y3, d.inner, false, nullptr, 0, B, static_cast<int>(S), 8, 1e-5f, d.gn_o2, ACT_RELU, a2, nullptr));
+    MD_CHECK(gemm(cbar, B, S, d.wov, nullptr, nullptr, y2, true));
+    MD_CHECK(gn(y2, d.inner, true, nullptr, 0, B, static_cast<int>(S), 8, 1e-5f, d.gn_o1, ACT_RELU, a1, nullptr));
+    MD_CHECK(conv(a1, B, H, W, d.conv1, nullptr, 0, nullptr, nullptr, y3, true));
+    MD_CHECK(gn(y3, d.inner, true, nullptr, 0, B, static_cast<int>(S), 8, 1e-5f, d.gn_o2, ACT_RELU, a2, nullptr));
     MD_CHECK(conv(a2, B, H, W, d.conv2, nullptr, 0, x_in, out, nullptr, true));
     A().release(m);
     return 0;
   }
 
   // Downsample: Conv2d 3x3 stride 2 pad 1 (openaimodel.py:159-161): implicit GEMM whose TMA boxes step by 2 pixels
-  int downsample(const GemmW& w, const float* x, int H, int W, int C, float* out) {
+  int downsample(const GemmW& w, const float* x, const bf16* x_b, int H, int W, int C, float* out) {
     const size_t rows = static_cast<size_t>(B) * H * W;
     const size_t m = A().mark();
-    bf16* xb = A().get<bf16>(rows * C);
+    bf16* xb = x_b ? nullptr : A().get<bf16>(rows * C);
     if (A().failed) return set_error("workspace exhausted (downsample)");
-    MD_CHECK(launch_cast_bf16(x, xb, rows * C, st));
+    if (!x_b) MD_CHECK(launch_cast_bf16(x, xb, rows * C, st));
     md_conv_gemm_args a;
     memset(&a, 0, sizeof(a));
-    a.A = xb; a.B = B; a.D = 1; a.H = H; a.W = W; a.Cin = C; a.Wt = w.w; a.N = w.N;
+    a.A = x_b ? x_b : xb; a.B = B; a.D = 1; a.H = H; a.W = W; a.Cin = C; a.Wt = w.w; a.N = w.N;
     taps2d(a);
     a.in_stride[0] = 2; a.in_stride[1] = 2; a.in_stride[2] = 1;
     a.bias = w.bias; a.out_f32 = out;
@@ -224,13 +227,13 @@ struct Fwd {
     return 0;
   }
   // Upsample: nearest x2 + Conv2d 3x3 (openaimodel.py:110-120)
-  int upsample(const GemmW& w, const float* x, int H, int W, int C, float* out) {
+  int upsample(const GemmW& w, const float* x, int H, int W, int C, float* out, bf16* out_b = nullptr) {
     const size_t orows = static_cast<size_t>(B) * 4 * H * W;
     const size_t m = A().mark();
     bf16* up = A().get<bf16>(orows * C);
     if (A().failed) return set_error("workspace exhausted (upsample)");
     MD_CHECK(launch_upsample2x(x, up, B, H, W, C, st));
-    MD_CHECK(conv(up, B, 2 * H, 2 * W, w, nullptr, 0, nullptr, out, nullptr, true));
+    MD_CHECK(conv(up, B, 2 * H, 2 * W, w, nullptr, 0, nullptr, out, out_b, true));
     A().release(m);
     return 0;
   }
@@ -293,26 +296,44 @@ int unet_forward(Ctx& c, const float* x_in, const float* timesteps, const float*
 
   float* h = A.get<float>(static_cast<size_t>(B) * H * H * mch);
   if (A.failed) return set_error("workspace exhausted (unet)");
-  MD_CHECK(launch_conv3x3_direct(x_in, u.conv_in_w, u.conv_in_b, h, B, H, H, u.in_channels, mch, st));
+  {  // conv_in on the tensor-core path: the 8 input channels are padded to one 64-channel K block (zero weights
+     // there), which also gives the first GroupNorm its statistics from the GEMM epilogue
+    const size_t m1 = A.mark();
+    bf16* xin_b = A.get<bf16>(static_cast<size_t>(B) * H * H * 64);
+    if (A.failed) return set_error("workspace exhausted (unet)");
+    MD_CHECK(launch_pad_cast_bf16(x_in, xin_b, static_cast<size_t>(B) * H * H, u.in_channels, 64, st));
+    MD_CHECK(f.conv(xin_b, B, H, H, u.conv_in_g, nullptr, 0, nullptr, h, nullptr, true));
+    A.release(m1);
+  }
   hs.push_back({h, mch, H});
 
+  // hb: bf16 copy of h, written by the producing GEMM's epilogue when the next consumer takes h as a GEMM operand
+  // (stride-2 downsample convolution, depth transformer proj_in); saves a separate cast pass
+  bf16* hb = nullptr;
   for (size_t bi = 1; bi < u.input_blocks.size(); ++bi) {
-    for (const UNetLayer& L : u.input_blocks[bi]) {
+    const std::vector<UNetLayer>& layers = u.input_blocks[bi];
+    const bool next_down = bi + 1 < u.input_blocks.size() && !u.input_blocks[bi + 1].empty() &&
+                           u.input_blocks[bi + 1][0].kind == 3;
+    for (size_t li = 0; li < layers.size(); ++li) {
+      const UNetLayer& L = layers[li];
+      const bool want_b = next_down && li + 1 == layers.size();
       if (L.kind == 1) {
         float* o = A.get<float>(static_cast<size_t>(B) * H * H * L.res.cout);
+        bf16* ob = want_b ? A.get<bf16>(static_cast<size_t>(B) * H * H * L.res.cout) : nullptr;
         if (A.failed) return set_error("workspace exhausted (unet)");
-        MD_CHECK(f.res_block(L.res, h, ch, nullptr, 0, H, H, o));
-        h = o; ch = L.res.cout;
+        MD_CHECK(f.res_block(L.res, h, ch, nullptr, 0, H, H, o, ob));
+        h = o; hb = ob; ch = L.res.cout;
       } else if (L.kind == 2) {
         float* o = A.get<float>(static_cast<size_t>(B) * H * H * ch);
+        bf16* ob = want_b ? A.get<bf16>(static_cast<size_t>(B) * H * H * ch) : nullptr;
         if (A.failed) return set_error("workspace exhausted (unet)");
-        MD_CHECK(f.spatial_transformer(L.st, h, H, H, o));
-        h = o;
+        MD_CHECK(f.spatial_transformer(L.st, h, H, H, o, ob));
+        h = o; hb = ob;
       } else if (L.kind == 3) {
         float* o = A.get<float>(static_cast<size_t>(B) * (H / 2) * (H / 2) * ch);
         if (A.failed) return set_error("workspace exhausted (unet)");
-        MD_CHECK(f.downsample(L.conv, h, H, H, ch, o));
-        h = o; H /= 2;
+        MD_CHECK(f.downsample(L.conv, h, hb, H, H, ch, o));
+        h = o; hb = nullptr; H /= 2;
       }
     }
     hs.push_back({h, ch, H});
@@ -321,51 +342,58 @@ int unet_forward(Ctx& c, const float* x_in, const float* timesteps, const float*
     float* o0 = A.get<float>(static_cast<size_t>(B) * H * H * ch);
     float* o1 = A.get<float>(static_cast<size_t>(B) * H * H * ch);
     float* o2 = A.get<float>(static_cast<size_t>(B) * H * H * ch);
+    bf16* o2b = A.get<bf16>(static_cast<size_t>(B) * H * H * ch);
     float* o3 = A.get<float>(static_cast<size_t>(B) * H * H * ch);
     if (A.failed) return set_error("workspace exhausted (unet)");
     MD_CHECK(f.res_block(u.mid0, h, ch, nullptr, 0, H, H, o0));
     MD_CHECK(f.spatial_transformer(u.mid1, o0, H, H, o1));
-    MD_CHECK(f.res_block(u.mid2, o1, ch, nullptr, 0, H, H, o2));
+    MD_CHECK(f.res_block(u.mid2, o1, ch, nullptr, 0, H, H, o2, o2b));
     const bf16* lv; int dd;
     if (level_of(H, lv, dd) != 0) return set_error("unet: no frustum level of width %d", H);
     if (c.levels_pending) {  // the frustum pyramids are produced on the second stream: join here
       MD_CUDA(cudaStreamWaitEvent(st, c.ev_levels, 0));
       c.levels_pending = false;
     }
-    MD_CHECK(f.depth_transformer(u.mid_cond, o2, H, H, lv, dd, o3));
+    MD_CHECK(f.depth_transformer(u.mid_cond, o2, o2b, H, H, lv, dd, o3));
     h = o3;
   }
   for (size_t bi = 0; bi < u.output_blocks.size(); ++bi) {
     const Skip sk = hs.back();
     hs.pop_back();
-    bool first = true;
-    for (const UNetLayer& L : u.output_blocks[bi]) {
+    const std::vector<UNetLayer>& layers = u.output_blocks[bi];
+    const bool cond = bi >= 3 && bi - 3 < u.out_cond.size();  // output_b2c = {3:0, ..., 11:8}
+    hb = nullptr;
+    for (size_t li = 0; li < layers.size(); ++li) {
+      const UNetLayer& L = layers[li];
+      const bool want_b = cond && li + 1 == layers.size();
       if (L.kind == 1) {
         float* o = A.get<float>(static_cast<size_t>(B) * H * H * L.res.cout);
+        bf16* ob = want_b ? A.get<bf16>(static_cast<size_t>(B) * H * H * L.res.cout) : nullptr;
         if (A.failed) return set_error("workspace exhausted (unet)");
-        if (!first) return set_error("unet: unexpected ResBlock position");
-        MD_CHECK(f.res_block(L.res, h, ch, sk.p, sk.C, H, H, o));
-        h = o; ch = L.res.cout;
+        if (li != 0) return set_error("unet: unexpected ResBlock position");
+        MD_CHECK(f.res_block(L.res, h, ch, sk.p, sk.C, H, H, o, ob));
+        h = o; hb = ob; ch = L.res.cout;
       } else if (L.kind == 2) {
         float* o = A.get<float>(static_cast<size_t>(B) * H * H * ch);
+        bf16* ob = want_b ? A.get<bf16>(static_cast<size_t>(B) * H * H * ch) : nullptr;
         if (A.failed) return set_error("workspace exhausted (unet)");
-        MD_CHECK(f.spatial_transformer(L.st, h, H, H, o));
-        h = o;
+        MD_CHECK(f.spatial_transformer(L.st, h, H, H, o, ob));
+        h = o; hb = ob;
       } else if (L.kind == 4) {
         float* o = A.get<float>(static_cast<size_t>(B) * 4 * H * H * ch);
+        bf16* ob = want_b ? A.get<bf16>(static_cast<size_t>(B) * 4 * H * H * ch) : nullptr;
         if (A.failed) return set_error("workspace exhausted (unet)");
-        MD_CHECK(f.upsample(L.conv, h, H, H, ch, o));
-        h = o; H *= 2;
+        MD_CHECK(f.upsample(L.conv, h, H, H, ch, o, ob));
+        h = o; hb = ob; H *= 2;
       }
-      first = false;
     }
-    if (bi >= 3 && bi - 3 < u.out_cond.size()) {  // output_b2c = {3:0, ..., 11:8}
+    if (cond) {
       const bf16* lv; int dd;
       if (level_of(H, lv, dd) != 0) return set_error("unet: no frustum level of width %d", H);
       float* o = A.get<float>(static_cast<size_t>(B) * H * H * ch);
       if (A.failed) return set_error("workspace exhausted (unet)");
-      MD_CHECK(f.depth_transformer(u.out_cond[bi - 3], h, H, H, lv, dd, o));
-      h = o;
+      MD_CHECK(f.depth_transformer(u.out_cond[bi - 3], h, hb, H, H, lv, dd, o));
+      h = o; hb = nullptr;
     }
   }
   // out: GN32 + SiLU + conv3x3 320 -> 4

@@ -262,13 +262,17 @@ int load_all_weights(Ctx& c, const TensorMap& tm, cudaStream_t st) {
   int emb_off = 0;
   std::vector<std::pair<std::string, int>> emb_list;
 
-  {  // conv_in: fp32 [tap][Cin][Cout]
+  {  // conv_in (8 -> 320): bf16 [mch][9][64], input channels zero-padded to one K block of the implicit GEMM
+    if (mc.in_channels > 64 || mc.in_channels % 4) return set_error("load_weights: in_channels=%d unsupported", mc.in_channels);
     const NamedTensor* t = L.find(P + "input_blocks.0.0.weight", static_cast<size_t>(mch) * mc.in_channels * 9);
-    u.conv_in_w = L.dalloc<float>(static_cast<size_t>(mch) * mc.in_channels * 9);
-    if (t && u.conv_in_w)
-      L.pack<float>(t->ptr, u.conv_in_w, mch, 9, mc.in_channels, static_cast<long>(mc.in_channels) * 9, 1, 9,
-                    Loader::iota(), 1, static_cast<long>(mc.in_channels) * mch, mch);
-    u.conv_in_b = L.copy_f32(P + "input_blocks.0.0.bias", mch);
+    u.conv_in_g.N = mch; u.conv_in_g.K = 64; u.conv_in_g.taps = 9;
+    u.conv_in_g.w = L.dalloc<bf16>(static_cast<size_t>(mch) * 9 * 64);
+    if (t && u.conv_in_g.w) {
+      cudaMemsetAsync(u.conv_in_g.w, 0, sizeof(bf16) * mch * 9 * 64, st);
+      L.pack<bf16>(t->ptr, u.conv_in_g.w, mch, 9, mc.in_channels, static_cast<long>(mc.in_channels) * 9, 1, 9,
+                   Loader::iota(), static_cast<long>(9) * 64, 64, 1);
+    }
+    u.conv_in_g.bias = L.copy_f32(P + "input_blocks.0.0.bias", mch);
   }
   std::vector<int> chans{mch};
   int ch = mch, ds = 1;

@@ -178,7 +178,8 @@ def test_sampler_with_other_step_counts(state_dict):
     sampler.denoise_apply(x_t.cuda(), {"x": x_input.cuda()}, clip.cuda(), None, 7, 2.0, is_step0=True, batch=batch)
     assert eng.bind_count == binds + 1
     f_b = eng.frustum_feats(vol, 0, n, 500.0)[32]
-    assert rel(f_b[0], f_a[0]) < 1e-3 and rel(f_b[1], f_a[1]) > 1e-2, (rel(f_b[0], f_a[0]), rel(f_b[1], f_a[1]))
+    same, moved = rel(f_b[0], f_a[0]), rel(f_b[1], f_a[1])   # untouched view: bf16 run-to-run level (measured 4e-3)
+    assert same < 1e-2 and moved > 3 * max(same, 3e-3), (same, moved)
 
 
 def test_sample_seeds_differ_between_calls_and_items(state_dict):
