@@ -90,7 +90,7 @@ ACT = {"none": 0, "silu": 1, "relu": 2, "geglu": 3, "gelu": 4}
 
 def conv_gemm(A, Wt, *, B, D, H, W, Cin, N, taps, bias=None, rowvec=None, res_f32=None, res_bf16=None,
               out_f32=None, out_bf16=None, act="none", Cpitch=0, out_dims=None, os_=None, op=None, ldo=0,
-              out_scale=1.0, BN=0, col_stats=None, in_stride=None, ksplit=0, cta_pair=0):
+              out_scale=1.0, BN=0, col_stats=None, in_stride=None, ksplit=0, cta_pair=0, tail_split=0):
     a = ConvGemmArgs()
     a.A = ptr(A); a.B, a.D, a.H, a.W = B, D, H, W
     a.Cin, a.Cpitch = Cin, Cpitch
@@ -115,6 +115,7 @@ def conv_gemm(A, Wt, *, B, D, H, W, Cin, N, taps, bias=None, rowvec=None, res_f3
     a.col_stats = ptr(col_stats)
     a.ksplit = ksplit
     a.cta_pair = cta_pair
+    a.tail_split = tail_split
     if in_stride:
         for j in range(3):
             a.in_stride[j] = in_stride[j]

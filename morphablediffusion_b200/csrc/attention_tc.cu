@@ -17,6 +17,7 @@
 #include "kernels.h"
 
 #include <cuda.h>
+#include <stdlib.h>
 
 namespace md {
 
@@ -58,8 +59,11 @@ __device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t (&v)[
 }
 
 // qkv viewed as [B*S rows][3*heads slots][dh]; grid = (S / (128*NWG), heads, B)
+// One-warpgroup instances leave room for two CTAs per SM (112 KB of shared memory, 256 TMEM columns, 168 registers x
+// 192 threads each): the second CTA's prologue, first TMA round trip and output epilogue overlap the first one's
+// softmax instead of serialising with it.
 template <int NDB, int NWG, int STAGES>
-__global__ void __launch_bounds__(64 + 128 * NWG, 1)
+__global__ void __launch_bounds__(64 + 128 * NWG, (NWG == 1 && NDB == 1 && STAGES == 2) ? 2 : 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restrict__ out, int S, int heads, int dh,
                     float scale_log2e) {
   using L = AttSmem<NDB, NWG, STAGES>;
@@ -325,6 +329,8 @@ int launch_attention_tc(const void* qkv, void* out, int B, int S, int heads, int
   if (!attention_tc_supported(S, dh)) return set_error("attention_tc: unsupported shape S=%d dh=%d", S, dh);
   if (reinterpret_cast<uintptr_t>(qkv) & 15) return set_error("attention_tc: qkv must be 16-byte aligned");
   if (dh <= 64) {
+    static const int variant = getenv("MD_ATT_VARIANT") ? atoi(getenv("MD_ATT_VARIANT")) : 0;
+    if (variant == 1) return attention_tc_impl<1, 1, 2>(qkv, out, B, S, heads, dh, st);
     if (S % 256 == 0) return attention_tc_impl<1, 2, 3>(qkv, out, B, S, heads, dh, st);
     return attention_tc_impl<1, 1, 3>(qkv, out, B, S, heads, dh, st);
   }

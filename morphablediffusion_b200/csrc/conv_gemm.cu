@@ -39,8 +39,9 @@ const SplitWorkspace* select_split_workspace(const SplitWorkspace* w) {
 int alloc_split_workspace(SplitWorkspace& w, size_t bytes, size_t ints) {
   void* p = nullptr;
   void* c = nullptr;
+  // both all-zero between launches: the last arrival of every split tile restores the zeros it consumed
   if (cudaMalloc(&p, bytes) != cudaSuccess || cudaMalloc(&c, ints * sizeof(int)) != cudaSuccess ||
-      cudaMemset(c, 0, ints * sizeof(int)) != cudaSuccess) {
+      cudaMemset(p, 0, bytes) != cudaSuccess || cudaMemset(c, 0, ints * sizeof(int)) != cudaSuccess) {
     cudaGetLastError();
     if (p) cudaFree(p);
     if (c) cudaFree(c);
@@ -58,7 +59,7 @@ void free_split_workspace(SplitWorkspace& w) {
 static const SplitWorkspace* default_split_workspace() {
   static SplitWorkspace def;
   static std::once_flag once;
-  std::call_once(once, [] { alloc_split_workspace(def, static_cast<size_t>(96) << 20, 1 << 16); });
+  std::call_once(once, [] { alloc_split_workspace(def, static_cast<size_t>(32) << 20, 1 << 14); });
   return def.ws ? &def : nullptr;
 }
 
@@ -190,7 +191,7 @@ int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
   }
   if (p.ksplit > 1) {
     if (a.act == ACT_GEGLU) return set_error("conv_gemm: split-K is not available with the GEGLU epilogue");
-    const size_t need = static_cast<size_t>(p.m_tiles) * p.n_tiles * p.ksplit * 128 * BN * sizeof(float);
+    const size_t need = static_cast<size_t>(p.m_tiles) * p.n_tiles * 128 * BN * sizeof(float);  // one accumulation tile per split tile
     float* ws = sw ? sw->ws : nullptr;
     int* cnt = sw ? sw->cnt : nullptr;
     const size_t ws_bytes = sw ? sw->bytes : 0;
@@ -234,34 +235,36 @@ int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
                                             (unsigned long long)Ktot, a.N);
   }
 
-  // ---- whole waves unsplit, the last partial wave split along K.  A persistent grid of G CTAs (pairs) walks T tiles
-  // in ceil(T / G) rounds; when the last round holds only rem = T mod G tiles, those are split ks = G / rem ways so
-  // that the round costs ~1/ks of a tile (plus the partial-sum exchange) instead of a whole one, e.g. 320 tiles of
-  // 256 columns on 148 SMs: 2.16 -> 3 rounds become 2 + 1/6.  Uses the split-K machinery of the tile-starved launches
-  // (workspace slots and arrival counters are indexed from the first split tile).  MD_HYBRID=0 switches it off.
+  // ---- whole waves unsplit, the partial wave split along K.  A persistent grid of G CTAs (pairs) walks T tiles in
+  // ceil(T / G) rounds; when one round holds only rem = T mod G tiles, those are split ks = G / rem ways so that the
+  // round costs ~1/ks of a tile instead of a whole one, e.g. 320 tiles of 256 columns on 148 SMs: 2.16 -> 3 rounds
+  // become 2 + 1/6.  The split items run FIRST: the partial-sum exchange (measured 5-10 us of pure latency: publish,
+  // ticket, read back) then overlaps the next tile's main loop through the second TMEM accumulator instead of
+  // ending the kernel.  Uses the split-K machinery of the tile-starved launches.  MD_HYBRID=0 switches it off.
   const int tiles_all = p.cg2 ? p.m_pairs * p.n_tiles : p.m_tiles * p.n_tiles;
   const int slots = p.cg2 ? cg2_pairs : std::min(tiles_all, num_sms());
   const bool contig = p.n_tiles == 1 && p.ksplit == 1 && tiles_all > 2 * slots;
-  p.items_main = p.ksplit > 1 ? 0 : tiles_all;
+  p.split_tiles = p.ksplit > 1 ? tiles_all : 0;
   {
     static const int hybrid_env = getenv("MD_HYBRID") ? atoi(getenv("MD_HYBRID")) : 1;
     const int hybrid = a.tail_split != 0 ? (a.tail_split > 0 ? 1 : 0) : hybrid_env;
-    if (hybrid && p.ksplit == 1 && a.ksplit == 0 && !contig && sw && tiles_all > slots && kblocks_all >= 8) {
+    if (hybrid && p.ksplit == 1 && a.ksplit == 0 && !contig && sw && tiles_all > slots && kblocks_all >= 96) {
       const int rem = tiles_all % slots;
       const int ks = rem ? std::min(std::min(slots / rem, kblocks_all / 4), 6) : 1;
       if (ks >= 2) {
         const size_t ws_slots = static_cast<size_t>(rem) * (p.cg2 ? 2 : 1);
-        const size_t need = ws_slots * ks * 128 * BN * sizeof(float);
+        const size_t need = ws_slots * 128 * BN * sizeof(float);
         if (need <= sw->bytes && ws_slots * kEpiWarps <= sw->ints) {
           p.ksplit = ks;
-          p.items_main = tiles_all - rem;
+          p.split_tiles = rem;
           p.split_ws = sw->ws;
           p.split_cnt = sw->cnt;
         }
       }
     }
   }
-  p.total_items = p.items_main + (tiles_all - p.items_main) * p.ksplit;
+  p.split_items = p.split_tiles * p.ksplit;
+  p.total_items = p.split_items + (tiles_all - p.split_tiles);
 
   // ---- TMA-store epilogue: one output, no fused statistics, no residual, no split-K, plain output geometry; the
   // output leaves as 16-column x 32-row boxes of the per-warp staging tile.  Measured (gpurun r01y/r01z): -10..19 % on
@@ -277,7 +280,7 @@ int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
                        p.OH == p.H && p.OD == p.D;
     void* optr = a.out_f32 ? static_cast<void*>(a.out_f32) : a.out_bf16;
     if (epi_tma_on && !p.cg2 && one_out && plain && !a.col_stats && !a.res_bf16 && (!a.res_f32 || epi_tma_res) &&
-        (p.ksplit == 1 || p.items_main > 0) &&
+        (p.ksplit == 1 || p.split_tiles < tiles_all) &&
         !(reinterpret_cast<uintptr_t>(optr) & 15)) {
       // a lane quarter's 32 rows inside the tile box (x fastest): sub-box dims and the origin of every quarter
       int qd[4], bd4[4] = {p.bw, p.bh, p.bd, p.bb}, rem = 32;
@@ -318,8 +321,8 @@ int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
   p.contig = contig ? 1 : 0;
   static const bool trace = getenv("MD_TRACE") != nullptr;
   if (trace)
-    fprintf(stderr, "conv_gemm B=%d D=%d H=%d W=%d Cin=%d taps=%d N=%d BN=%d tiles=%dx%d ks=%d main=%d cg2=%d act=%d f32=%d bf16=%d res=%d\n",
-            a.B, a.D, a.H, a.W, a.Cin, a.ntaps, a.N, BN, p.m_tiles, p.n_tiles, p.ksplit, p.items_main, p.cg2, a.act, a.out_f32 != nullptr,
+    fprintf(stderr, "conv_gemm B=%d D=%d H=%d W=%d Cin=%d taps=%d N=%d BN=%d tiles=%dx%d ks=%d split_tiles=%d cg2=%d act=%d f32=%d bf16=%d res=%d\n",
+            a.B, a.D, a.H, a.W, a.Cin, a.ntaps, a.N, BN, p.m_tiles, p.n_tiles, p.ksplit, p.split_tiles, p.cg2, a.act, a.out_f32 != nullptr,
             a.out_bf16 != nullptr, a.res_f32 != nullptr || a.res_bf16 != nullptr);
   if (p.cg2)
     return (BN == 160) ? launch_conv_gemm_cg2_bn160(tmA, tmB, tmO, p, grid, stream, nullptr)

@@ -84,10 +84,12 @@ struct ConvGemmParams {
   int contig;       // contiguous tile run per CTA (see kernel)
   int ksplit;       // split-K factor of the SPLIT tiles: work item = (tile, split); partial accumulators meet in split_ws,
                     // the last arriving warp of every (tile, epilogue-warp) pair reduces them and runs the real epilogue
-  int items_main;   // leading tiles (CTA-pair kernel: pair tiles) that run unsplit; the tiles behind them are split
-                    // ksplit ways.  0 = every tile split (tile-starved problems); all tiles (ksplit 1) = no split;
-                    // in between = whole waves unsplit and the last partial wave split along K to fill the machine
-  int total_items;  // items_main + (tiles - items_main) * ksplit
+  int split_tiles;  // the first split_tiles tiles (CTA-pair kernel: pair tiles) are split ksplit ways and their items come
+                    // FIRST in the schedule, the remaining tiles run unsplit behind them.  All tiles = tile-starved
+                    // problems; 0 = no split; in between = the partial wave of a persistent grid is split along K to
+                    // fill the machine, and running it first hides the partial-sum exchange behind the whole waves
+  int split_items;  // split_tiles * ksplit
+  int total_items;  // split_items + (tiles - split_tiles)
   float* split_ws;  // [split tiles (x2 in the pair kernel)][ksplit][128][BN] fp32
   int* split_cnt;   // [split tiles (x2)][EPI_WARPS] arrival counters (zero on entry, reset by the last arrival)
   int isx, isy, isz; // input coordinate = output-tile coordinate * is + tap offset (strided convolution via TMA element strides)
@@ -110,12 +112,11 @@ struct TileCoord {
 };
 // work item -> (tile, split index, split count)
 __device__ __forceinline__ void decode_split(const ConvGemmParams& p, int item, int& tile, int& sp, int& ns) {
-  if (item < p.items_main) {
-    tile = item; sp = 0; ns = 1;
+  if (item < p.split_items) {
+    fdivmod(item, p.fd_ksplit, tile, sp);
+    ns = p.ksplit;
   } else {
-    int q;
-    fdivmod(item - p.items_main, p.fd_ksplit, q, sp);
-    tile = p.items_main + q; ns = p.ksplit;
+    tile = p.split_tiles + (item - p.split_items); sp = 0; ns = 1;
   }
 }
 // K-block range [kb0, kb1) of split sp out of ns
@@ -552,18 +553,21 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, const CUt
       // adds the other splits' partials back into TMEM and then runs the ordinary epilogue on the full sums.
       constexpr int acc_chunks = BN / kChunk;
       // slot of this CTA's tile among the split tiles (both CTAs of a pair work on the same pair tile)
-      const int ws_idx = p.cg2 ? 2 * (tile - p.items_main) + static_cast<int>(cluster_ctarank()) : tile - p.items_main;
-      float* ws_tile = p.split_ws + static_cast<size_t>(ws_idx) * p.ksplit * (128 * BN);
-      float* mine = ws_tile + static_cast<size_t>(sp) * (128 * BN) + static_cast<size_t>(r) * BN;
+      const int ws_idx = p.cg2 ? 2 * tile + static_cast<int>(cluster_ctarank()) : tile;
+      // Exchange through ONE fp32 accumulation tile per split tile: every split adds its partial with vector
+      // red.global.add (fire and forget, no round trip; four floats per lane and 512 contiguous bytes per warp
+      // instruction: layout [16-column chunk][4-column group][128 rows][4]), the last arrival reads the sums once,
+      // restores the zeros and puts them into TMEM.  Cost per CTA is independent of the split count; the tile is all-zero
+      // between launches (allocated zeroed, every element that is added to is read and re-zeroed by the last arrival).
+      float* ws_row = p.split_ws + static_cast<size_t>(ws_idx) * (128 * BN) + r * 4;
       for (int c = c_begin; c < acc_chunks; c += kCStride) {
         uint32_t v[16];
         tmem_ld_32x16(taddr + c * kChunk, v);
         tc_wait_ld();
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          __stcg(reinterpret_cast<float4*>(mine + c * kChunk) + j,
-                 make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
-                             __uint_as_float(v[4 * j + 3])));
+          red_add_v4_f32(ws_row + (c * 4 + j) * 512, __uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                         __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
       }
       __threadfence();
       __syncwarp();
@@ -577,25 +581,36 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, const CUt
       run_epilogue = last != 0;
       KPROF(7, lt == 0 && warp == 2 && lane == 0);
       if (run_epilogue) {
-        __threadfence();
-        for (int c = c_begin; c < acc_chunks; c += kCStride) {
+        // every split has published before taking its ticket and the loads below depend on the ticket; they bypass L1
+        // (ld.cg), so no second fence is needed.
+        // Two chunks (32 registers) are requested per memory round trip.
+        for (int c0 = c_begin; c0 < acc_chunks; c0 += 2 * kCStride) {
+          const int c1 = c0 + kCStride;
+          const bool two = c1 < acc_chunks;
+          float4 t0[4], t1[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) t0[j] = __ldcg(reinterpret_cast<const float4*>(ws_row + (c0 * 4 + j) * 512));
+          if (two) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) t1[j] = __ldcg(reinterpret_cast<const float4*>(ws_row + (c1 * 4 + j) * 512));
+          }
           uint32_t v[16];
-          tmem_ld_32x16(taddr + c * kChunk, v);
-          tc_wait_ld();
-          for (int s2 = 0; s2 < p.ksplit; ++s2) {
-            if (s2 == sp) continue;
-            const float4* o = reinterpret_cast<const float4*>(ws_tile + static_cast<size_t>(s2) * (128 * BN) +
-                                                              static_cast<size_t>(r) * BN + c * kChunk);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            v[4 * j] = __float_as_uint(t0[j].x); v[4 * j + 1] = __float_as_uint(t0[j].y);
+            v[4 * j + 2] = __float_as_uint(t0[j].z); v[4 * j + 3] = __float_as_uint(t0[j].w);
+            __stcg(reinterpret_cast<float4*>(ws_row + (c0 * 4 + j) * 512), make_float4(0.f, 0.f, 0.f, 0.f));
+          }
+          tmem_st_32x16(taddr + c0 * kChunk, v);
+          if (two) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const float4 t = __ldcg(o + j);
-              v[4 * j] = __float_as_uint(__uint_as_float(v[4 * j]) + t.x);
-              v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + t.y);
-              v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + t.z);
-              v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + t.w);
+              v[4 * j] = __float_as_uint(t1[j].x); v[4 * j + 1] = __float_as_uint(t1[j].y);
+              v[4 * j + 2] = __float_as_uint(t1[j].z); v[4 * j + 3] = __float_as_uint(t1[j].w);
+              __stcg(reinterpret_cast<float4*>(ws_row + (c1 * 4 + j) * 512), make_float4(0.f, 0.f, 0.f, 0.f));
             }
+            tmem_st_32x16(taddr + c1 * kChunk, v);
           }
-          tmem_st_32x16(taddr + c * kChunk, v);
         }
         tc_wait_st();
         KPROF(8, lt == 0 && warp == 2 && lane == 0);

@@ -52,6 +52,16 @@ __device__ __forceinline__ float gelu_fast(float x) {
   return 0.5f * x * (1.f + copysignf(e, x));
 }
 
+// fire-and-forget fp32 add into global memory (performed at the L2; no return value, no round trip)
+__device__ __forceinline__ void red_add_f32(float* addr, float v) {
+  asm volatile("red.relaxed.gpu.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
+}
+// four floats per lane in one reduction (16-byte aligned): a quarter of the L2 atomic operations of the scalar form
+__device__ __forceinline__ void red_add_v4_f32(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
+}
+
 // ---------------------------------------------------------------- programmatic dependent launch
 // Every kernel of the library starts with this: wait until the predecessor grid's writes are visible, then allow the
 // successor grid to begin launching (its own prologue overlaps our execution; it waits here in turn).

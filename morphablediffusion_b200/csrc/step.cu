@@ -281,11 +281,11 @@ int md_create(md_ctx** out, const md_config* cfg) {
     }
     if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&ctx->c.ev_fork, cudaEventDisableTiming);
     if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&ctx->c.ev_levels, cudaEventDisableTiming);
-    if (e2 == cudaSuccess && alloc_split_workspace(ctx->c.split_side, static_cast<size_t>(48) << 20, 1 << 15) != 0)
+    if (e2 == cudaSuccess && alloc_split_workspace(ctx->c.split_side, static_cast<size_t>(24) << 20, 1 << 14) != 0)
       e2 = cudaErrorMemoryAllocation;
     if (e2 != cudaSuccess) { cudaGetLastError(); ctx->c.stream2 = nullptr; }  // overlap simply stays off
   }
-  if (alloc_split_workspace(ctx->c.split_main, static_cast<size_t>(96) << 20, 1 << 16) != 0) {
+  if (alloc_split_workspace(ctx->c.split_main, static_cast<size_t>(32) << 20, 1 << 14) != 0) {
     md_destroy(ctx);
     return -1;
   }

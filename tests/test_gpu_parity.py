@@ -246,6 +246,82 @@ def test_conv_gemm_cta_pair_kernel(nat):
     assert rel(st, sref) < 1e-4
 
 
+@pytest.mark.parametrize("case", ["pair256", "pair160_stats", "single_res", "geglu_tma", "bf16_tma"])
+def test_conv_gemm_tail_split(nat, case):
+    """Hybrid schedule: whole waves of tiles run unsplit, the last partial wave is split along K (last arrival reduces
+    through TMEM, then the ordinary epilogue).  Every case has more tiles than SMs (pairs) and a remainder; the result
+    must agree with torch and, to fp32 summation-order level, with the same launch without the tail split.  Repeated
+    launches check that the arrival counters reset themselves."""
+    torch.manual_seed(31)
+    taps9 = [(dx, dy, 0) for dy in (-1, 0, 1) for dx in (-1, 0, 1)]
+    kw, ref_fn = {}, None
+    if case == "pair256":        # 16x16 level: 64 M tiles x 5 N tiles of 256 = 160 pair tiles on 74 pairs
+        Bn, H, W, Cin, N = 32, 16, 16, 320, 1280
+        kw = dict(cta_pair=1)
+    elif case == "pair160_stats":  # 32x32 level: 256 M tiles x 2 N tiles of 160, fused statistics + per-sample vector
+        Bn, H, W, Cin, N = 32, 32, 32, 192, 320
+        kw = dict(cta_pair=1, BN=160)
+    elif case == "single_res":   # single-CTA kernel, fp32 residual: 170 M tiles x 2 N tiles = 340 tiles on 148 SMs
+        Bn, H, W, Cin, N = 85, 16, 16, 128, 320
+        kw = dict(cta_pair=-1, BN=160)
+    else:                        # plain linears through the TMA-store epilogue
+        Bn, H, W, Cin, N = 34, 1, 128, 640, 2560 if case == "geglu_tma" else 1280   # 340 / 170 tiles of 256 columns
+        kw = dict(cta_pair=-1, BN=256)
+    conv = H > 1
+    taps = taps9 if conv else [(0, 0, 0)]
+    K = Cin * len(taps)
+    M = Bn * H * W
+    A = bf(torch.randn(Bn, H, W, Cin, device="cuda"))
+    Wt = bf(torch.randn(N, K, device="cuda") / K ** 0.5)
+    bias = torch.randn(N, device="cuda")
+    if conv:
+        w4 = Wt.view(N, 3, 3, Cin).permute(0, 3, 1, 2).float()
+        y = F.conv2d(A.permute(0, 3, 1, 2).float(), w4, bias, padding=1).permute(0, 2, 3, 1).reshape(M, N)
+    else:
+        y = A.view(M, K).float() @ Wt.float().t() + bias
+    outs = []
+    rv = torch.randn(Bn, N, device="cuda")
+    res = torch.randn(M, N, device="cuda") if case == "single_res" else None
+    for tail in (1, 1, -1):
+        st = None
+        if case == "pair160_stats":
+            st = torch.zeros(Bn, N, 2, device="cuda")
+            o = torch.zeros(M, N, device="cuda")
+            nat.conv_gemm(A, Wt, B=Bn, D=1, H=H, W=W, Cin=Cin, N=N, taps=taps, bias=bias, rowvec=rv, out_f32=o,
+                          col_stats=st, tail_split=tail, **kw)
+            ref = y + rv.repeat_interleave(H * W, 0)
+            sref = torch.stack([ref.view(Bn, H * W, N).sum(1), (ref.view(Bn, H * W, N) ** 2).sum(1)], -1)
+            assert rel(st, sref) < 1e-4
+        elif case == "single_res":
+            o = torch.zeros(M, N, device="cuda")
+            nat.conv_gemm(A, Wt, B=Bn, D=1, H=H, W=W, Cin=Cin, N=N, taps=taps, bias=bias, res_f32=res, out_f32=o,
+                          act="silu", tail_split=tail, **kw)
+            ref = F.silu(y) + res
+        elif case == "geglu_tma":
+            inner = N // 2
+            idx = []
+            for j in range(inner // 128):
+                idx += list(range(j * 128, (j + 1) * 128)) + list(range(inner + j * 128, inner + (j + 1) * 128))
+            idx = torch.tensor(idx, device="cuda")
+            o = torch.zeros(M, inner, device="cuda", dtype=torch.bfloat16)
+            nat.conv_gemm(A, Wt[idx].contiguous(), B=Bn, D=1, H=H, W=W, Cin=Cin, N=N, taps=taps,
+                          bias=bias[idx].contiguous(), out_bf16=o, act="geglu", tail_split=tail, **kw)
+            ref = y[:, :inner] * F.gelu(y[:, inner:])
+        elif case == "bf16_tma":
+            o = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16)
+            nat.conv_gemm(A, Wt, B=Bn, D=1, H=H, W=W, Cin=Cin, N=N, taps=taps, bias=bias, out_bf16=o, tail_split=tail,
+                          **kw)
+            ref = y
+        else:
+            o = torch.zeros(M, N, device="cuda")
+            nat.conv_gemm(A, Wt, B=Bn, D=1, H=H, W=W, Cin=Cin, N=N, taps=taps, bias=bias, out_f32=o, tail_split=tail,
+                          **kw)
+            ref = y
+        assert rel(o, ref) < (5e-3 if o.dtype == torch.bfloat16 else 1e-5), (case, tail, rel(o, ref))
+        outs.append(o.float())
+    assert rel(outs[1], outs[0]) < 1e-6 and rel(outs[2], outs[0]) < (4e-3 if o.dtype == torch.bfloat16 else 1e-6)
+
+
 # ----------------------------------------------------------------------------- norm / attention kernels
 @pytest.mark.parametrize("B,rows,C,G,act,bf16_in", [(3, 1024, 320, 32, 1, False), (2, 256, 1920, 32, 1, False),
                                                     (2, 16, 1280, 32, 0, False), (2, 6144, 128, 8, 1, True),
