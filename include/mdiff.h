@@ -68,6 +68,8 @@ typedef struct md_conv_gemm_args {
   int cta_pair;             /* CTA-pair (cta_group::2, 256-row tiles over two SMs) kernel: 0 = library default
                                (from 24 K blocks up; MD_CG2 overrides), 1 = use it whenever the problem is eligible (tile
                                width 160 or 256, no split-K, at least one full wave of pairs), -1 = never */
+  int Wpitch;               /* row pitch of Wt in elements (a weight matrix that is a column slice of a wider one,
+                               e.g. the keys inside a fused q|k activation); 0 -> ntaps*Cin; multiple of 8 */
   int tail_split;           /* last partial wave of tiles split along K: 0 = library default (on; MD_HYBRID=0 switches it
                                off), 1 = on, -1 = off */
 } md_conv_gemm_args;
@@ -151,6 +153,13 @@ MD_API int md_unet_forward(md_ctx* ctx, const float* x, const float* timesteps_h
 MD_API int md_denoise_step(md_ctx* ctx, float* x_local, const float* x_input, const float* clip_embed, int index,
                            float cfg_scale, const float* noise, unsigned long long seed, float* eps_out,
                            void* stream);
+/* SyncMultiviewDiffusion.decode_first_stage (morphable_diffusion.py:468-471) for n latents: image = Decoder(
+ * post_quant_conv(x / 0.18215)) (ldm/models/autoencoder.py:330-333, ldm/modules/diffusionmodules/model.py:462-569).
+ * x [n][4][S][S] (the sampler's output for n views, device, fp32), image [n][3][8S][8S] (device, fp32, NCHW).
+ * latent_size S: 0 -> the context's.  Needs the first_stage_model.decoder.* / post_quant_conv.* tensors among the weights
+ * given to md_load_weights (md_has_vae tells); views are independent, so with several ranks each decodes its own. */
+MD_API int md_vae_decode(md_ctx* ctx, const float* x, float* image, int n, int latent_size, void* stream);
+MD_API int md_has_vae(md_ctx* ctx);
 MD_API int md_ddim_timestep(md_ctx* ctx, int index);  /* 1 .. 981 */
 /* SyncDDIMSampler(model, ddim_num_steps, "uniform", ddim_eta) (morphable_diffusion.py:649-672): rebuilds the DDIM
  * schedule (timesteps range(0,1000,1000/steps)+1, alphas, alphas_prev, sigmas) of the context.  Cheap; may be called
@@ -176,6 +185,8 @@ MD_API int md_op_group_norm_stats(const void* x, int x_is_bf16, int B, int rows,
                                   const float* gamma, const float* beta, const float* addvec, int act,
                                   const float* stats, void* out_bf16, void* stream);
 /* nn.LayerNorm over the last dim of x fp32 [rows][C] -> bf16 (ldm/modules/attention.py:257-259) */
+/* row softmax fp32 [rows][n] -> bf16 (AttnBlock of the first-stage decoder, model.py:190-192); n a multiple of 4 */
+MD_API int md_op_softmax_rows(const float* x, void* out_bf16, long long rows, int n, void* stream);
 MD_API int md_op_layer_norm(float* x, const float* gamma, const float* beta, void* out_bf16, long long rows, int C,
                             float eps, void* stream);
 /* CrossAttention.forward as self-attention (ldm/modules/attention.py:179-203): qkv bf16 [B][S][3*heads*dh] ->

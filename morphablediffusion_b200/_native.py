@@ -55,6 +55,7 @@ class ConvGemmArgs(C.Structure):
         ("ksplit", C.c_int),
         ("in_stride", C.c_int * 3),
         ("cta_pair", C.c_int),
+        ("Wpitch", C.c_int),
         ("tail_split", C.c_int),
     ]
 
@@ -90,7 +91,7 @@ ACT = {"none": 0, "silu": 1, "relu": 2, "geglu": 3, "gelu": 4}
 
 def conv_gemm(A, Wt, *, B, D, H, W, Cin, N, taps, bias=None, rowvec=None, res_f32=None, res_bf16=None,
               out_f32=None, out_bf16=None, act="none", Cpitch=0, out_dims=None, os_=None, op=None, ldo=0,
-              out_scale=1.0, BN=0, col_stats=None, in_stride=None, ksplit=0, cta_pair=0, tail_split=0):
+              out_scale=1.0, BN=0, col_stats=None, in_stride=None, ksplit=0, cta_pair=0, tail_split=0, Wpitch=0):
     a = ConvGemmArgs()
     a.A = ptr(A); a.B, a.D, a.H, a.W = B, D, H, W
     a.Cin, a.Cpitch = Cin, Cpitch
@@ -116,6 +117,7 @@ def conv_gemm(A, Wt, *, B, D, H, W, Cin, N, taps, bias=None, rowvec=None, res_f3
     a.ksplit = ksplit
     a.cta_pair = cta_pair
     a.tail_split = tail_split
+    a.Wpitch = Wpitch
     if in_stride:
         for j in range(3):
             a.in_stride[j] = in_stride[j]
@@ -156,15 +158,20 @@ lib.md_denoise_step.argtypes = [_vp, _vp, _vp, _vp, C.c_int, C.c_float, _vp, C.c
 lib.md_ddim_timestep.argtypes = [_vp, C.c_int]
 lib.md_set_ddim.argtypes = [_vp, C.c_int, C.c_float]
 lib.md_ddim_steps.argtypes = [_vp]
+lib.md_vae_decode.argtypes = [_vp, _vp, _vp, C.c_int, C.c_int, _vp]
+lib.md_has_vae.argtypes = [_vp]
 lib.md_comm_unique_id.argtypes = [_vp]
 lib.md_comm_init.argtypes = [_vp, C.c_int, C.c_int, _vp]
 for _f in ("md_embed_time", "md_create", "md_load_weights", "md_bind_sample", "md_voxelize", "md_spatial_volume", "md_frustum_feats",
-           "md_unet_forward", "md_denoise_step", "md_ddim_timestep", "md_set_ddim", "md_ddim_steps", "md_comm_unique_id", "md_comm_init"):
+           "md_unet_forward", "md_denoise_step", "md_ddim_timestep", "md_set_ddim", "md_ddim_steps", "md_comm_unique_id", "md_comm_init",
+           "md_vae_decode", "md_has_vae"):
     getattr(lib, _f).restype = C.c_int
 
 lib.md_op_group_norm.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _vp, _vp, _vp, C.c_int, _vp, _vp]
 lib.md_op_group_norm_stats.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp]
 lib.md_op_group_norm_stats.restype = C.c_int
+lib.md_op_softmax_rows.argtypes = [_vp, _vp, C.c_longlong, C.c_int, _vp]
+lib.md_op_softmax_rows.restype = C.c_int
 lib.md_op_layer_norm.argtypes = [_vp, _vp, _vp, _vp, C.c_longlong, C.c_int, C.c_float, _vp]
 lib.md_op_self_attention.argtypes = [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp]
 lib.md_op_self_attention_impl.argtypes = [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp]

@@ -80,6 +80,8 @@ int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
     return set_error("conv_gemm: operands must be 16-byte aligned");
   const int Cpitch = a.Cpitch ? a.Cpitch : a.Cin;
   if (Cpitch % 8 != 0) return set_error("conv_gemm: channel pitch %d must be a multiple of 8", Cpitch);
+  if (a.Wpitch % 8 != 0 || (a.Wpitch && a.Wpitch < a.ntaps * a.Cin))
+    return set_error("conv_gemm: weight pitch %d must be a multiple of 8 and cover K=%d", a.Wpitch, a.ntaps * a.Cin);
 
   ConvGemmParams p;
   memset(&p, 0, sizeof(p));
@@ -225,7 +227,7 @@ int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
   {
     const cuuint64_t Ktot = (cuuint64_t)a.ntaps * a.Cin;
     cuuint64_t dims[2] = {Ktot, (cuuint64_t)a.N};
-    cuuint64_t strides[1] = {Ktot * 2};
+    cuuint64_t strides[1] = {(a.Wpitch ? (cuuint64_t)a.Wpitch : Ktot) * 2};
     cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)(p.cg2 ? BN / 2 : BN)};  // a pair CTA stages half the rows
     cuuint32_t es[2] = {1, 1};
     CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(a.Wt), dims, strides, box,

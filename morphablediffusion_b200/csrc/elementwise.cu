@@ -674,6 +674,88 @@ int launch_pad_cast_bf16(const float* x, void* out, size_t rows, int C, int Cpad
   return check_launch("pad_cast_bf16");
 }
 
+// AutoencoderKL.decode input (ldm/models/autoencoder.py:330-332): z = post_quant_conv(x * in_scale), a 1x1 convolution
+// over 4 channels, written as the bf16 channels-last operand of the decoder's conv_in with the channels zero-padded to
+// one 64-wide K block.  One thread per (sample, pixel, 4-channel group).
+__global__ void vae_input_kernel(const float* __restrict__ x, const float* __restrict__ pq, float in_scale,
+                                 __nv_bfloat16* __restrict__ out, int B, int HW) {
+  pdl_grid_sync();
+  const size_t total = static_cast<size_t>(B) * HW * 16;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(i & 15);
+    const size_t bp = i >> 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (g == 0) {
+      const size_t b = bp / HW, pix = bp - b * HW;
+      float in[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) in[c] = x[(b * 4 + c) * HW + pix] * in_scale;
+      float o[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float a = pq[16 + k];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) a = fmaf(pq[k * 4 + c], in[c], a);
+        o[k] = a;
+      }
+      v = make_float4(o[0], o[1], o[2], o[3]);
+    }
+    store4(out + bp * 64 + g * 4, v);
+  }
+}
+
+int launch_vae_input(const float* x, const float* pq, float in_scale, void* out_bf16, int B, int HW, cudaStream_t st) {
+  const size_t total = static_cast<size_t>(B) * HW * 16;
+  const int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, static_cast<size_t>(num_sms()) * 16));
+  launch_pdl(vae_input_kernel, dim3(blocks), dim3(256), 0, st, x, pq, in_scale, static_cast<__nv_bfloat16*>(out_bf16), B, HW);
+  return check_launch("vae_input");
+}
+
+// Row softmax fp32 -> bf16, one warp per row (n a multiple of 4): max, sum of exponentials, normalise; the row is read
+// three times, the second and third time out of L1/L2.
+__global__ void softmax_rows_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, size_t rows, int n) {
+  pdl_grid_sync();
+  const int lane = threadIdx.x & 31;
+  const size_t warp = (blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x) >> 5;
+  const size_t nwarps = (static_cast<size_t>(gridDim.x) * blockDim.x) >> 5;
+  for (size_t r = warp; r < rows; r += nwarps) {
+    const float* xr = x + r * n;
+    float m = -3.0e38f;
+    for (int c = lane * 4; c < n; c += 128) {
+      const float4 v = load4(xr + c);
+      m = fmaxf(m, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffff, m, o));
+    const float mb = m * 1.4426950408889634f;
+    float s = 0.f;
+    for (int c = lane * 4; c < n; c += 128) {
+      const float4 v = load4(xr + c);
+      s += ex2_approx(fmaf(v.x, 1.4426950408889634f, -mb)) + ex2_approx(fmaf(v.y, 1.4426950408889634f, -mb)) +
+           ex2_approx(fmaf(v.z, 1.4426950408889634f, -mb)) + ex2_approx(fmaf(v.w, 1.4426950408889634f, -mb));
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffff, s, o);
+    const float inv = 1.f / s;
+    __nv_bfloat16* orow = out + r * n;
+    for (int c = lane * 4; c < n; c += 128) {
+      const float4 v = load4(xr + c);
+      store4(orow + c, make_float4(ex2_approx(fmaf(v.x, 1.4426950408889634f, -mb)) * inv,
+                                   ex2_approx(fmaf(v.y, 1.4426950408889634f, -mb)) * inv,
+                                   ex2_approx(fmaf(v.z, 1.4426950408889634f, -mb)) * inv,
+                                   ex2_approx(fmaf(v.w, 1.4426950408889634f, -mb)) * inv));
+    }
+  }
+}
+
+int launch_softmax_rows(const float* x, void* out_bf16, size_t rows, int n, cudaStream_t st) {
+  if (n % 4) return set_error("softmax_rows: n=%d must be a multiple of 4", n);
+  const int blocks = static_cast<int>(std::min<size_t>((rows + 7) / 8, static_cast<size_t>(num_sms()) * 8));
+  launch_pdl(softmax_rows_kernel, dim3(blocks), dim3(256), 0, st, x, static_cast<__nv_bfloat16*>(out_bf16), rows, n);
+  return check_launch("softmax_rows");
+}
+
 template <typename T>
 __global__ void cast_bf16_kernel(const T* __restrict__ x, __nv_bfloat16* __restrict__ out, size_t n4) {
   pdl_grid_sync();

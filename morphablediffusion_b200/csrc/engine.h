@@ -71,6 +71,28 @@ struct UNetW {
   NormW out_norm; GemmW out_g;  // final conv as a GEMM padded to 8 output columns (rows out_channels..7 are zero)
 };
 
+// First-stage decoder (AutoencoderKL.decode = post_quant_conv + Decoder, ldm/models/autoencoder.py:330-333,
+// ldm/modules/diffusionmodules/model.py:462-569), attn_resolutions = [] as built by morphable_diffusion.py:399-414.
+struct VaeAttnW {
+  int C = 0;
+  NormW norm;
+  GemmW qk;                        // q | k fused along N: [2C][C]
+  bf16* wv = nullptr;              // v weight [C][C] (used as the A operand of V^T = Wv . h^T)
+  const float* bv = nullptr;       // v bias, added after the P.V product (softmax rows sum to 1)
+  GemmW proj;
+};
+struct VaeW {
+  bool loaded = false;
+  float* pq = nullptr;             // post_quant_conv: [4][4] weight then [4] bias (fp32)
+  int z_channels = 4, out_ch = 3;
+  GemmW conv_in, conv_out;         // Cin padded to 64 / N padded to 8
+  ResW mid1, mid2;
+  VaeAttnW attn;
+  std::vector<std::vector<ResW>> up;   // up[i_level][i_block], reference indexing (level 3 runs first)
+  GemmW upsample[4];               // up[i_level].upsample.conv for i_level >= 1
+  NormW norm_out;
+};
+
 struct FrBlockW {   // FrustumTVBlock / FrustumTVUpBlock
   int cin = 0, cout = 0, stride = 1; bool up = false;
   const float* t_w = nullptr; const float* t_b = nullptr; const float* v_w = nullptr; const float* v_b = nullptr;
@@ -109,6 +131,7 @@ struct Ctx {
   md_config mcfg;
   UNetW unet;
   VolumeW vol;
+  VaeW vae;
   bool weights_loaded = false;
   std::vector<void*> weight_allocs;
   Arena arena;
@@ -160,6 +183,10 @@ void free_weights(Ctx& c);
 // volume (the CFG-unconditional half) and `levels` holds nothing for them.
 int unet_forward(Ctx& c, const float* x_in, const float* timesteps, const float* context, const bf16* const levels[4],
                  int B, int n_ctx, int S, int D, float* eps_out, cudaStream_t st);
+
+// unet.cu: decode_first_stage for T latents.  x fp32 NCHW [T][4][S][S] (scaled latents: divided by 0.18215 inside),
+// image fp32 NCHW [T][3][8S][8S].
+int vae_decode(Ctx& c, const float* x, float* image, int T, int S, cudaStream_t st);
 
 // volume.cu
 int bind_sample(Ctx& c, const float* K, const float* RT, const float* v_embed, const float* vertices,

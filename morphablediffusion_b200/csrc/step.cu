@@ -512,6 +512,24 @@ int md_denoise_step(md_ctx* ctx, float* x_local, const float* x_input, const flo
   return rc;
 }
 
+int md_has_vae(md_ctx* ctx) { return ctx && ctx->c.vae.loaded ? 1 : 0; }
+
+int md_vae_decode(md_ctx* ctx, const float* x, float* image, int n, int latent_size, void* stream) {
+  MD_CHECK(ensure_ready(ctx, false));
+  Ctx& c = ctx->c;
+  SplitScope split_scope(&c.split_main);
+  if (latent_size <= 0) latent_size = c.mcfg.latent_size;
+  // views are independent: chunks bound the workspace (and the 32-bit row offsets of the GEMM epilogue)
+  const int chunk = std::max(1, c.mcfg.max_views_per_call > 0 ? std::min(c.mcfg.max_views_per_call, 16) : 16);
+  const size_t in_per = static_cast<size_t>(4) * latent_size * latent_size;
+  const size_t out_per = static_cast<size_t>(3) * 64 * latent_size * latent_size;
+  for (int i0 = 0; i0 < n; i0 += chunk) {
+    const int T = std::min(chunk, n - i0);
+    MD_CHECK(vae_decode(c, x + i0 * in_per, image + i0 * out_per, T, latent_size, static_cast<cudaStream_t>(stream)));
+  }
+  return 0;
+}
+
 int md_set_ddim(md_ctx* ctx, int ddim_steps, float ddim_eta) {
   if (!ctx) return set_error("null context");
   if (ddim_steps < 1 || ddim_steps > 1000) return set_error("md_set_ddim: ddim_steps=%d out of range 1..1000", ddim_steps);
@@ -566,6 +584,10 @@ int md_op_group_norm_stats(const void* x, int x_is_bf16, int B, int rows, int C,
   g.gamma = gamma; g.beta = beta; g.addvec = addvec; g.addvec_ld = C; g.stats0 = stats; g.scale_shift = ws;
   g.out = out_bf16; g.act = act;
   return launch_group_norm(g, st);
+}
+
+int md_op_softmax_rows(const float* x, void* out_bf16, long long rows, int n, void* stream) {
+  return launch_softmax_rows(x, out_bf16, static_cast<size_t>(rows), n, static_cast<cudaStream_t>(stream));
 }
 
 int md_op_layer_norm(float* x, const float* gamma, const float* beta, void* out_bf16, long long rows, int C, float eps,

@@ -5,6 +5,8 @@
 // finalize kernel plus one normalise+activate pass.
 #include "engine.h"
 
+#include <math.h>
+
 namespace md {
 
 namespace {
@@ -16,6 +18,7 @@ struct Fwd {
   int n_ctx;             // leading samples that own a frustum volume
   const float* emb_all;  // [B][emb_total] per-ResBlock time-embedding projections
   const float* v2_all;   // [B][v2_total] attn2 output vectors of every transformer block
+  float res_eps = 1e-5f; // GroupNorm eps of the ResBlocks (UNet GroupNorm32: 1e-5; first-stage Normalize: 1e-6)
   // statistics pool: one [B][C][2] slab per tensor that feeds a GroupNorm, zeroed once per forward
   float* spool = nullptr;
   size_t spool_cap = 0, spool_off = 0;
@@ -117,9 +120,11 @@ struct Fwd {
     bf16* a2 = A().get<bf16>(rows * r.cout);
     float* skip = r.has_skip ? A().get<float>(rows * r.cout) : nullptr;
     if (A().failed) return set_error("workspace exhausted (res block)");
-    MD_CHECK(gn(x0, C0, false, x1, C1, B, H * W, 32, 1e-5f, r.n1, ACT_SILU, a1, raw));
-    MD_CHECK(conv(a1, B, H, W, r.c1, emb_all + r.emb_off, c.unet.emb_total, nullptr, nullptr, h1, true));
-    MD_CHECK(gn(h1, r.cout, true, nullptr, 0, B, H * W, 32, 1e-5f, r.n2, ACT_SILU, a2, nullptr));
+    MD_CHECK(gn(x0, C0, false, x1, C1, B, H * W, 32, res_eps, r.n1, ACT_SILU, a1, raw));
+    // per-sample time-embedding vector (UNet ResBlock); the first-stage ResnetBlock has none (temb is None)
+    const float* rv = emb_all ? emb_all + r.emb_off : nullptr;
+    MD_CHECK(conv(a1, B, H, W, r.c1, rv, rv ? c.unet.emb_total : 0, nullptr, nullptr, h1, true));
+    MD_CHECK(gn(h1, r.cout, true, nullptr, 0, B, H * W, 32, res_eps, r.n2, ACT_SILU, a2, nullptr));
     const float* resid = x0;
     if (r.has_skip) {
       MD_CHECK(conv(raw, B, H, W, r.skip, nullptr, 0, nullptr, skip, nullptr, false));
@@ -405,6 +410,112 @@ int unet_forward(Ctx& c, const float* x_in, const float* timesteps, const float*
   MD_CHECK(f.conv(ao, B, H, H, u.out_g, nullptr, 0, nullptr, eps8, nullptr, false));
   MD_CHECK(launch_rows_to_nchw(eps8, 8, eps_out, B, u.out_channels, H * H, st));
   A.release(m0);
+  return 0;
+}
+
+// decode_first_stage (morphable_diffusion.py:468-471) = AutoencoderKL.decode (ldm/models/autoencoder.py:330-333) =
+// post_quant_conv + Decoder.forward (ldm/modules/diffusionmodules/model.py:535-569) on the UNet's kernels: ResnetBlock =
+// GroupNorm(eps 1e-6)+SiLU -> conv3x3 -> GroupNorm+SiLU -> conv3x3 (+ 1x1 nin_shortcut), statistics from the GEMM
+// epilogues; Upsample = nearest x2 + conv3x3; the single AttnBlock (one head of 512 channels over h*w positions) as
+// three tensor-core GEMMs per sample around a row softmax: S = q k^T (the keys are the "weight" operand, addressed
+// inside the fused q|k activation through its row pitch), V^T = Wv h^T (so that V arrives K-major for the last
+// product), O = softmax(S) V + b_v.
+int vae_decode(Ctx& c, const float* x, float* image, int T, int S, cudaStream_t st) {
+  if (!c.vae.loaded) return set_error("vae_decode: no first-stage decoder weights were loaded (first_stage_model.*)");
+  if (T < 1 || S < 8 || S % 8) return set_error("vae_decode: bad shape T=%d S=%d", T, S);
+  const VaeW& v = c.vae;
+  Arena& A = c.arena;
+  A.off = 0;
+  A.failed = false;
+  Fwd f{c, st, T, T, nullptr, nullptr};
+  f.res_eps = 1e-6f;
+  const size_t spool_floats = static_cast<size_t>(T) * 2 * 48 * 512;   // ~35 GroupNorm inputs of at most [T][512][2]
+  f.spool = A.get<float>(spool_floats);
+  f.spool_cap = spool_floats;
+  if (A.failed) return set_error("workspace exhausted (vae statistics)");
+  MD_CUDA(cudaMemsetAsync(f.spool, 0, spool_floats * sizeof(float), st));
+
+  int H = S;
+  int ch = v.conv_in.N;
+  const size_t HW = static_cast<size_t>(H) * H;
+  // the decoder has no skip connections: every layer consumes h and produces the next h, so two buffers of the largest
+  // activation (the 256-channel tensor at full resolution behind the last Upsample) alternate
+  const size_t max_act = static_cast<size_t>(T) * HW * 64 * 256;
+  float* bufs[2] = {A.get<float>(max_act), A.get<float>(max_act)};
+  if (A.failed) return set_error("workspace exhausted (vae activations: %zu MB)", (2 * max_act * sizeof(float)) >> 20);
+  int cur = 0;
+  float* h = bufs[0];
+  {
+    const size_t m = A.mark();
+    bf16* zin = A.get<bf16>(static_cast<size_t>(T) * HW * 64);
+    if (A.failed) return set_error("workspace exhausted (vae)");
+    MD_CHECK(launch_vae_input(x, v.pq, 1.f / 0.18215f, zin, T, static_cast<int>(HW), st));
+    MD_CHECK(f.conv(zin, T, H, H, v.conv_in, nullptr, 0, nullptr, h, nullptr, true));
+    A.release(m);
+  }
+  auto next_buf = [&]() { cur ^= 1; return bufs[cur]; };
+  auto block = [&](const ResW& r) -> int {
+    float* o = next_buf();
+    MD_CHECK(f.res_block(r, h, ch, nullptr, 0, H, H, o));
+    h = o; ch = r.cout;
+    return 0;
+  };
+  MD_CHECK(block(v.mid1));
+  {  // AttnBlock (model.py:177-203)
+    const VaeAttnW& a = v.attn;
+    const int C = a.C;
+    const int Sx = H * H;
+    if (Sx % 64) return set_error("vae_decode: attention over %d positions (must be a multiple of 64)", Sx);
+    float* o = next_buf();
+    const size_t m = A.mark();
+    bf16* hn = A.get<bf16>(static_cast<size_t>(T) * Sx * C);
+    bf16* qk = A.get<bf16>(static_cast<size_t>(T) * Sx * 2 * C);
+    bf16* vT = A.get<bf16>(static_cast<size_t>(C) * Sx);
+    float* sc = A.get<float>(static_cast<size_t>(Sx) * Sx);
+    bf16* pr = A.get<bf16>(static_cast<size_t>(Sx) * Sx);
+    bf16* att = A.get<bf16>(static_cast<size_t>(T) * Sx * C);
+    if (A.failed) return set_error("workspace exhausted (vae attention)");
+    MD_CHECK(f.gn(h, C, false, nullptr, 0, T, Sx, 32, 1e-6f, a.norm, ACT_NONE, hn, nullptr));
+    MD_CHECK(f.gemm(hn, T, Sx, a.qk, nullptr, nullptr, qk, false));
+    for (int b = 0; b < T; ++b) {
+      md_conv_gemm_args g;
+      const bf16* hb = hn + static_cast<size_t>(b) * Sx * C;
+      const bf16* qb = qk + static_cast<size_t>(b) * Sx * 2 * C;
+      // V^T [C][Sx] = Wv [C][C] . h_b^T: the normalised activations of sample b are the K-major "weight" operand
+      memset(&g, 0, sizeof(g));
+      g.A = a.wv; g.B = 1; g.D = 1; g.H = 1; g.W = C; g.Cin = C; g.Wt = hb; g.N = Sx; g.ntaps = 1; g.out_bf16 = vT;
+      MD_CHECK(launch_conv_gemm(g, st));
+      // scores [Sx][Sx] = q_b k_b^T * C^-0.5 (q at columns 0..C-1, k at C..2C-1 of the fused activation)
+      memset(&g, 0, sizeof(g));
+      g.A = qb; g.B = 1; g.D = 1; g.H = 1; g.W = Sx; g.Cin = C; g.Cpitch = 2 * C; g.Wt = qb + C; g.Wpitch = 2 * C;
+      g.N = Sx; g.ntaps = 1; g.out_f32 = sc; g.out_scale = 1.f / sqrtf(static_cast<float>(C));
+      MD_CHECK(launch_conv_gemm(g, st));
+      MD_CHECK(launch_softmax_rows(sc, pr, static_cast<size_t>(Sx), Sx, st));
+      // O [Sx][C] = P V + b_v
+      memset(&g, 0, sizeof(g));
+      g.A = pr; g.B = 1; g.D = 1; g.H = 1; g.W = Sx; g.Cin = Sx; g.Wt = vT; g.N = C; g.ntaps = 1; g.bias = a.bv;
+      g.out_bf16 = att + static_cast<size_t>(b) * Sx * C;
+      MD_CHECK(launch_conv_gemm(g, st));
+    }
+    MD_CHECK(f.gemm(att, T, Sx, a.proj, h, o, nullptr, true));
+    A.release(m);
+    h = o;
+  }
+  MD_CHECK(block(v.mid2));
+  for (int lev = static_cast<int>(v.up.size()) - 1; lev >= 0; --lev) {
+    for (const ResW& r : v.up[lev]) MD_CHECK(block(r));
+    if (lev != 0) {
+      float* o = next_buf();
+      MD_CHECK(f.upsample(v.upsample[lev], h, H, H, ch, o));
+      h = o; H *= 2;
+    }
+  }
+  bf16* ao = A.get<bf16>(static_cast<size_t>(T) * H * H * ch);
+  float* rgb8 = A.get<float>(static_cast<size_t>(T) * H * H * 8);
+  if (A.failed) return set_error("workspace exhausted (vae)");
+  MD_CHECK(f.gn(h, ch, false, nullptr, 0, T, H * H, 32, 1e-6f, v.norm_out, ACT_SILU, ao, nullptr));
+  MD_CHECK(f.conv(ao, T, H, H, v.conv_out, nullptr, 0, nullptr, rgb8, nullptr, false));
+  MD_CHECK(launch_rows_to_nchw(rgb8, 8, image, T, v.out_ch, H * H, st));
   return 0;
 }
 

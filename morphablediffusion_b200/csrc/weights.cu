@@ -503,6 +503,96 @@ int load_all_weights(Ctx& c, const TensorMap& tm, cudaStream_t st) {
       }
     }
   }
+  // ------------------------------------------------ first-stage decoder (optional: present when the caller's state
+  // dict carries first_stage_model.*, generate_face.py:75-76 loads it with the rest of the checkpoint)
+  c.vae = VaeW();
+  const std::string FS = "first_stage_model.";
+  if (L.has(FS + "decoder.conv_in.weight")) {
+    VaeW& a = c.vae;
+    const std::string Dp = FS + "decoder.";
+    const int ch = 128, nlev = 4, nres = 2;                 // morphable_diffusion.py:399-414
+    const int ch_mult[4] = {1, 2, 4, 4};
+    int block_in = ch * ch_mult[nlev - 1];
+    {  // post_quant_conv: fp32 [4][4] | [4]
+      const NamedTensor* w = L.find(FS + "post_quant_conv.weight", 16);
+      const NamedTensor* b = L.find(FS + "post_quant_conv.bias", 4);
+      a.pq = L.dalloc<float>(20);
+      if (w && b && a.pq) {
+        cudaMemcpyAsync(a.pq, w->ptr, 16 * sizeof(float), cudaMemcpyDeviceToDevice, st);
+        cudaMemcpyAsync(a.pq + 16, b->ptr, 4 * sizeof(float), cudaMemcpyDeviceToDevice, st);
+      }
+    }
+    {  // conv_in 4 -> 512 with the input channels zero-padded to one K block
+      const NamedTensor* t = L.find(Dp + "conv_in.weight", static_cast<size_t>(block_in) * 4 * 9);
+      a.conv_in.N = block_in; a.conv_in.K = 64; a.conv_in.taps = 9;
+      a.conv_in.w = L.dalloc<bf16>(static_cast<size_t>(block_in) * 9 * 64);
+      if (t && a.conv_in.w) {
+        cudaMemsetAsync(a.conv_in.w, 0, sizeof(bf16) * block_in * 9 * 64, st);
+        L.pack<bf16>(t->ptr, a.conv_in.w, block_in, 9, 4, 4 * 9, 1, 9, Loader::iota(), static_cast<long>(9) * 64, 64, 1);
+      }
+      a.conv_in.bias = L.copy_f32(Dp + "conv_in.bias", block_in);
+    }
+    auto vres = [&](const std::string& q, int cin, int cout) {
+      ResW r;
+      r.cin = cin; r.cout = cout; r.emb_off = -1;
+      r.n1 = L.norm(q + "norm1", cin);
+      r.c1 = L.gemm(q + "conv1", cout, cin, 9, true);
+      r.n2 = L.norm(q + "norm2", cout);
+      r.c2 = L.gemm(q + "conv2", cout, cout, 9, true);
+      r.has_skip = cin != cout;
+      if (r.has_skip) r.skip = L.gemm(q + "nin_shortcut", cout, cin, 1, true);
+      return r;
+    };
+    a.mid1 = vres(Dp + "mid.block_1.", block_in, block_in);
+    a.mid2 = vres(Dp + "mid.block_2.", block_in, block_in);
+    {  // AttnBlock: q | k fused; v kept as a [C][C] matrix (it becomes the A operand of V^T = Wv . h^T)
+      VaeAttnW& t = a.attn;
+      t.C = block_in;
+      const std::string q = Dp + "mid.attn_1.";
+      t.norm = L.norm(q + "norm", block_in);
+      t.qk = L.gemm_fused({q + "q.weight", q + "k.weight"}, block_in, block_in);
+      {
+        float* qkb = L.dalloc<float>(2 * block_in);
+        const NamedTensor* bq = L.find(q + "q.bias", block_in);
+        const NamedTensor* bk = L.find(q + "k.bias", block_in);
+        if (qkb && bq && bk) {
+          cudaMemcpyAsync(qkb, bq->ptr, sizeof(float) * block_in, cudaMemcpyDeviceToDevice, st);
+          cudaMemcpyAsync(qkb + block_in, bk->ptr, sizeof(float) * block_in, cudaMemcpyDeviceToDevice, st);
+        }
+        t.qk.bias = qkb;
+      }
+      t.wv = L.dalloc<bf16>(static_cast<size_t>(block_in) * block_in);
+      if (t.wv) L.pack_conv_into(t.wv, q + "v.weight", block_in, block_in, 1);
+      t.bv = L.copy_f32(q + "v.bias", block_in);
+      t.proj = L.gemm(q + "proj_out", block_in, block_in, 1, true);
+    }
+    a.up.assign(nlev, std::vector<ResW>());
+    for (int lev = nlev - 1; lev >= 0; --lev) {
+      const int block_out = ch * ch_mult[lev];
+      for (int ib = 0; ib < nres + 1; ++ib) {
+        a.up[lev].push_back(vres(Dp + "up." + std::to_string(lev) + ".block." + std::to_string(ib) + ".", block_in, block_out));
+        block_in = block_out;
+      }
+      if (lev != 0) a.upsample[lev] = L.gemm(Dp + "up." + std::to_string(lev) + ".upsample.conv", block_in, block_in, 9, true);
+    }
+    a.norm_out = L.norm(Dp + "norm_out", block_in);
+    {  // conv_out 128 -> 3, padded to 8 output columns
+      const NamedTensor* t = L.find(Dp + "conv_out.weight", static_cast<size_t>(3) * block_in * 9);
+      const NamedTensor* b = L.find(Dp + "conv_out.bias", 3);
+      a.conv_out.N = 8; a.conv_out.K = block_in; a.conv_out.taps = 9;
+      a.conv_out.w = L.dalloc<bf16>(static_cast<size_t>(8) * block_in * 9);
+      float* ob = L.dalloc<float>(8);
+      a.conv_out.bias = ob;
+      if (t && b && a.conv_out.w && ob) {
+        cudaMemsetAsync(a.conv_out.w, 0, sizeof(bf16) * 8 * block_in * 9, st);
+        cudaMemsetAsync(ob, 0, sizeof(float) * 8, st);
+        L.pack<bf16>(t->ptr, a.conv_out.w, 3, 9, block_in, static_cast<long>(block_in) * 9, 1, 9, Loader::iota(),
+                     static_cast<long>(9) * block_in, block_in, 1);
+        cudaMemcpyAsync(ob, b->ptr, sizeof(float) * 3, cudaMemcpyDeviceToDevice, st);
+      }
+    }
+    a.loaded = L.rc == 0;
+  }
   if (L.rc != 0) { free_weights(c); return L.rc; }
   MD_CUDA(cudaStreamSynchronize(st));
   c.weights_loaded = true;
@@ -513,6 +603,7 @@ void free_weights(Ctx& c) {
   for (void* p : c.weight_allocs) cudaFree(p);
   c.weight_allocs.clear();
   c.weights_loaded = false;
+  c.vae.loaded = false;
 }
 
 }  // namespace md

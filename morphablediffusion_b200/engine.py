@@ -150,6 +150,18 @@ class Engine:
                                           nat.cur_stream()), "md_denoise_step")
         return eps
 
+    def has_vae(self):
+        """True when the loaded state dict carried first_stage_model.decoder.* / post_quant_conv.*."""
+        return bool(nat.lib.md_has_vae(self._h))
+
+    def vae_decode(self, x):
+        """decode_first_stage (morphable_diffusion.py:468-471): x [n,4,S,S] scaled latents -> images [n,3,8S,8S]."""
+        x = x.to(self.device, torch.float32).contiguous()
+        n, _, S, _ = x.shape
+        out = torch.empty(n, 3, 8 * S, 8 * S, device=self.device)
+        nat.check(nat.lib.md_vae_decode(self._h, x.data_ptr(), out.data_ptr(), n, S, nat.cur_stream()), "md_vae_decode")
+        return out
+
     def set_ddim(self, ddim_steps, ddim_eta=1.0):
         """Schedule of SyncDDIMSampler(model, ddim_steps, ddim_eta=...) (morphable_diffusion.py:649-672)."""
         if (int(ddim_steps), float(ddim_eta)) != self.ddim:

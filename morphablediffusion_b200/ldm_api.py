@@ -275,6 +275,23 @@ def _build_frozen(factory):
     return m, None
 
 
+class _ParamTree(nn.Module):
+    """Parameters registered under dotted state-dict keys (nested containers), nothing else: holds the first-stage
+    decoder tensors under the reference's names when the reference's AutoencoderKL class cannot be built (its import
+    needs `taming`), so reference checkpoints still load and the CUDA decoder finds its weights."""
+
+    def __init__(self, spec=None):
+        super().__init__()
+        for key, shape in (spec or {}).items():
+            node = self
+            parts = key.split(".")
+            for name in parts[:-1]:
+                if not hasattr(node, name):
+                    node.add_module(name, _ParamTree())
+                node = getattr(node, name)
+            node.register_parameter(parts[-1], nn.Parameter(torch.zeros(tuple(shape)), requires_grad=False))
+
+
 def _batch_item(batch, bi):
     return {k: (v[bi:bi + 1] if torch.is_tensor(v) else v) for k, v in batch.items()}
 
@@ -343,6 +360,11 @@ class SyncMultiviewDiffusion(_Base):
                        "lossconfig": {"target": "torch.nn.Identity"}}}
         self.first_stage_scale_factor = 0.18215
         self.first_stage_model, self._first_stage_error = _build_frozen(lambda: instantiate_from_config(first_stage_config))
+        if self.first_stage_model is None:
+            # decode_first_stage runs in the CUDA library either way; without the reference class only the parameter
+            # slots (post_quant_conv + decoder, reference key names) are needed.  encode_first_stage stays unavailable.
+            dec = {k[len("first_stage_model."):]: v for k, v in _spec.vae_decoder_spec().items()}
+            self.first_stage_model = _ParamTree(dec).eval()
 
     def _init_clip_image_encoder(self):
         def build():
@@ -365,7 +387,8 @@ class SyncMultiviewDiffusion(_Base):
                                   image_size=self.image_size, smpl_num_views=0, device=dev)
         if self._engine_version != ver:
             sd = {k: v for k, v in self.state_dict().items()
-                  if k.startswith(("time_embed.", "spatial_volume.", "model.diffusion_model."))}
+                  if k.startswith(("time_embed.", "spatial_volume.", "model.diffusion_model.",
+                                   "first_stage_model.decoder.", "first_stage_model.post_quant_conv."))}
             self._engine.load_state_dict(sd)
             self._engine_version = ver
             self._bound_key = None
@@ -415,20 +438,21 @@ class SyncMultiviewDiffusion(_Base):
 
     # -- frozen side models (outside the step loop; not rebuilt — attach the reference's own modules)
     def encode_first_stage(self, x, sample=True):
-        if self.first_stage_model is None:
-            raise RuntimeError("no first_stage_model: the reference AutoencoderKL could not be built "
+        if not hasattr(self.first_stage_model, "encode"):
+            raise RuntimeError("no first-stage encoder: the reference AutoencoderKL could not be built "
                                f"({self._first_stage_error}); attach it as model.first_stage_model")
         with torch.no_grad():
             posterior = self.first_stage_model.encode(x)
             z = posterior.sample() if sample else posterior.mode()
             return z.detach() * self.first_stage_scale_factor
 
+    @torch.no_grad()
     def decode_first_stage(self, z):
-        if self.first_stage_model is None:
-            raise RuntimeError("no first_stage_model: the reference AutoencoderKL could not be built "
-                               f"({self._first_stage_error}); attach it as model.first_stage_model")
-        with torch.no_grad():
-            return self.first_stage_model.decode(z / self.first_stage_scale_factor)
+        """morphable_diffusion.py:468-471 on the CUDA library (md_vae_decode): z [B,4,h,w] -> image [B,3,8h,8w]."""
+        eng = self._get_engine()
+        if not eng.has_vae():
+            raise RuntimeError("the loaded state dict carries no first_stage_model.decoder.* tensors")
+        return eng.vae_decode(z)
 
     def prepare(self, batch):
         if self.clip_image_encoder is None:

@@ -228,6 +228,41 @@ def spatial_volume_spec(prefix="spatial_volume.", time_dim=256, view_dim=4, dims
     return s
 
 
+def vae_decoder_spec(prefix="first_stage_model.", ch=128, ch_mult=(1, 2, 4, 4), num_res_blocks=2, z_channels=4,
+                     out_ch=3, embed_dim=4):
+    """AutoencoderKL.post_quant_conv + Decoder (ldm/models/autoencoder.py:303, ldm/modules/diffusionmodules/model.py:
+    462-533) for the first-stage configuration of morphable_diffusion.py:399-414 (attn_resolutions = [])."""
+    s = OrderedDict()
+    _conv(s, prefix + "post_quant_conv", z_channels, embed_dim, 1)
+    d = prefix + "decoder."
+    block_in = ch * ch_mult[-1]
+    _conv(s, d + "conv_in", block_in, z_channels, 3)
+
+    def resnet(p, cin, cout):
+        _norm(s, p + "norm1", cin)
+        _conv(s, p + "conv1", cout, cin, 3)
+        _norm(s, p + "norm2", cout)
+        _conv(s, p + "conv2", cout, cout, 3)
+        if cin != cout:
+            _conv(s, p + "nin_shortcut", cout, cin, 1)
+
+    resnet(d + "mid.block_1.", block_in, block_in)
+    _norm(s, d + "mid.attn_1.norm", block_in)
+    for n in ("q", "k", "v", "proj_out"):
+        _conv(s, d + "mid.attn_1." + n, block_in, block_in, 1)
+    resnet(d + "mid.block_2.", block_in, block_in)
+    for i_level in reversed(range(len(ch_mult))):
+        block_out = ch * ch_mult[i_level]
+        for i_block in range(num_res_blocks + 1):
+            resnet(d + f"up.{i_level}.block.{i_block}.", block_in, block_out)
+            block_in = block_out
+        if i_level != 0:
+            _conv(s, d + f"up.{i_level}.upsample.conv", block_in, block_in, 3)
+    _norm(s, d + "norm_out", block_in)
+    _conv(s, d + "conv_out", out_ch, block_in, 3)
+    return s
+
+
 def model_spec(cfg=None):
     """Every tensor of SyncMultiviewDiffusion that the per-step path reads (VAE / CLIP are outside the loop)."""
     s = OrderedDict()

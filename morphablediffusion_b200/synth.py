@@ -43,6 +43,11 @@ def init_tensor(key, shape, seed=6033):
     return torch.randn(shape, generator=g) * std
 
 
+def make_vae_state_dict(seed=6033, prefix="first_stage_model."):
+    """Seeded post_quant_conv + Decoder weights under the reference's state-dict keys."""
+    return {k: init_tensor(k, shp, seed) for k, shp in _spec.vae_decoder_spec(prefix).items()}
+
+
 def make_state_dict(cfg=None, seed=6033, keys=None):
     sd = {}
     for k, shp in _spec.model_spec(cfg).items():

@@ -558,6 +558,51 @@ def denoise_apply(sd, cfg, sched, x_t, x_input, clip_embed, time_steps, index, c
     return ddim_update(sched, x_t, index, eps, noise)
 
 
+# ----------------------------------------------------------------------------- VAE decode
+
+
+def vae_resnet_block(x, sd, p):
+    """ResnetBlock.forward with temb = None, ldm/modules/diffusionmodules/model.py:121-141 (GroupNorm eps 1e-6, :39)."""
+    h = conv(F.silu(group_norm(x, sd, p + "norm1", 32, 1e-6)), sd, p + "conv1", padding=1)
+    h = conv(F.silu(group_norm(h, sd, p + "norm2", 32, 1e-6)), sd, p + "conv2", padding=1)
+    if (p + "nin_shortcut.weight") in sd:
+        x = conv(x, sd, p + "nin_shortcut")
+    return x + h
+
+
+def vae_attn_block(x, sd, p):
+    """AttnBlock.forward, model.py:177-203: single-head attention over the h*w positions, scale c^-0.5."""
+    h_ = group_norm(x, sd, p + "norm", 32, 1e-6)
+    q, k, v = conv(h_, sd, p + "q"), conv(h_, sd, p + "k"), conv(h_, sd, p + "v")
+    b, c, hh, ww = q.shape
+    q = q.reshape(b, c, hh * ww).permute(0, 2, 1)
+    k = k.reshape(b, c, hh * ww)
+    w_ = torch.softmax(torch.bmm(q, k) * (int(c) ** (-0.5)), dim=2)
+    v = v.reshape(b, c, hh * ww)
+    h_ = torch.bmm(v, w_.permute(0, 2, 1)).reshape(b, c, hh, ww)
+    return x + conv(h_, sd, p + "proj_out")
+
+
+def vae_decode(sd, z, prefix="first_stage_model.", ch_mult=(1, 2, 4, 4), num_res_blocks=2):
+    """AutoencoderKL.decode (ldm/models/autoencoder.py:330-333: post_quant_conv, then Decoder) and Decoder.forward
+    (model.py:535-569) for attn_resolutions = [] (the configuration morphable_diffusion.py:399-414 builds).
+    z: [B, 4, h, w] already divided by the scale factor (decode_first_stage, morphable_diffusion.py:468-471)."""
+    d = prefix + "decoder."
+    h = conv(z, sd, prefix + "post_quant_conv")
+    h = conv(h, sd, d + "conv_in", padding=1)
+    h = vae_resnet_block(h, sd, d + "mid.block_1.")
+    h = vae_attn_block(h, sd, d + "mid.attn_1.")
+    h = vae_resnet_block(h, sd, d + "mid.block_2.")
+    for i_level in reversed(range(len(ch_mult))):
+        for i_block in range(num_res_blocks + 1):
+            h = vae_resnet_block(h, sd, d + f"up.{i_level}.block.{i_block}.")
+        if i_level != 0:
+            h = F.interpolate(h, scale_factor=2.0, mode="nearest")
+            h = conv(h, sd, d + f"up.{i_level}.upsample.conv", padding=1)
+    h = F.silu(group_norm(h, sd, d + "norm_out", 32, 1e-6))
+    return conv(h, sd, d + "conv_out", padding=1)
+
+
 def voxelize(vertices):
     """CPU voxelisation rule, generate_face.py:214-225 == ldm/data/facescape.py:165-175.
     vertices [Nv,3] f32 -> coord [Nv,3] i32 (d,h,w), out_sh [3] i32, bounds [2,3] f32."""

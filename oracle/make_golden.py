@@ -158,6 +158,31 @@ def unet_only(seed=6033):
     np.savez_compressed(GOLD / "unet_b2.npz", out=ref.numpy(), seed=seed, input_seed=seed + 11)
 
 
+def vae_decode_golden(name, n_views, latent, seed=6033):
+    """decode_first_stage (morphable_diffusion.py:468-471) through the reference's own Decoder class
+    (ldm/modules/diffusionmodules/model.py:462-569) and a Conv2d post_quant_conv (autoencoder.py:303,330-333; the
+    AutoencoderKL class itself needs `taming`, which is not installed, so its two-line decode() is spelled out)."""
+    import importlib
+    ref_import.reference()
+    m = importlib.import_module("ldm.modules.diffusionmodules.model")
+    dd = dict(double_z=True, z_channels=4, resolution=256, in_channels=3, out_ch=3, ch=128, ch_mult=[1, 2, 4, 4],
+              num_res_blocks=2, attn_resolutions=[], dropout=0.0)   # morphable_diffusion.py:399-414
+    dec = m.Decoder(**dd).eval()
+    sd = synth.make_vae_state_dict(seed)
+    dec.load_state_dict({k[len("first_stage_model.decoder."):]: v for k, v in sd.items() if ".decoder." in k})
+    pq = torch.nn.Conv2d(4, 4, 1)
+    pq.load_state_dict({"weight": sd["first_stage_model.post_quant_conv.weight"],
+                        "bias": sd["first_stage_model.post_quant_conv.bias"]})
+    x = torch.randn(n_views, 4, latent, latent, generator=torch.Generator().manual_seed(seed + 77))
+    t0 = time.time()
+    with torch.no_grad():
+        ref = dec(pq(x / 0.18215))
+        ours = O.vae_decode(sd, x / 0.18215)
+    print(f"[{name}] oracle err/max", maxerr(ours, ref), f"{time.time() - t0:.0f}s", flush=True)
+    np.savez_compressed(GOLD / f"{name}.npz", image=ref.numpy().astype(np.float16) if latent >= 32 else ref.numpy(),
+                        n_views=n_views, latent=latent, seed=seed, input_seed=seed + 77)
+
+
 def spec_dump():
     model, ns = ref_import.build_reference_model()
     skip = ("betas", "alphas", "alphas_cumprod", "sqrt_alphas_cumprod", "sqrt_one_minus_alphas_cumprod",
@@ -165,6 +190,16 @@ def spec_dump():
     d = {k: list(v.shape) for k, v in model.state_dict().items() if k not in skip}
     (GOLD / "ref_state_dict_spec.json").write_text(json.dumps(d, indent=0))
     print("[spec] keys", len(d))
+    # first-stage decoder (reference Decoder class; post_quant_conv is autoencoder.py:303 Conv2d(embed_dim, z_channels, 1))
+    import importlib
+    m = importlib.import_module("ldm.modules.diffusionmodules.model")
+    dec = m.Decoder(double_z=True, z_channels=4, resolution=256, in_channels=3, out_ch=3, ch=128, ch_mult=[1, 2, 4, 4],
+                    num_res_blocks=2, attn_resolutions=[], dropout=0.0)
+    dv = {"first_stage_model.decoder." + k: list(v.shape) for k, v in dec.state_dict().items()}
+    dv["first_stage_model.post_quant_conv.weight"] = [4, 4, 1, 1]
+    dv["first_stage_model.post_quant_conv.bias"] = [4]
+    (GOLD / "ref_vae_decoder_spec.json").write_text(json.dumps(dv, indent=0))
+    print("[spec] first-stage decoder keys", len(dv))
 
 
 if __name__ == "__main__":
@@ -191,5 +226,9 @@ if __name__ == "__main__":
         run_config("step_n32_persp", 32, "perspective", "flame", index=40, bvn=8)
     if want("step_n4_lat64"):         # config 1: 4 views @ 64x64 latent (input_image_size = 512)
         run_config("step_n4_lat64", 4, "perspective", "flame", index=49, latent=64)
+    if want("vae_n2_lat8"):           # §8f rank 1: VAE decode, small latent (CPU oracle test) and the real size (GPU test)
+        vae_decode_golden("vae_n2_lat8", 2, 8)
+    if want("vae_n2_lat32"):
+        vae_decode_golden("vae_n2_lat32", 2, 32)
     if want("traj_n2_50"):            # a2: the 50-step sampler loop
         run_trajectory("traj_n2_50", 2, 50)

@@ -22,3 +22,9 @@ def built_lib():
 def state_dict():
     from morphablediffusion_b200 import synth
     return synth.make_state_dict()
+
+
+@pytest.fixture(scope="session")
+def vae_state_dict():
+    from morphablediffusion_b200 import synth
+    return synth.make_vae_state_dict()

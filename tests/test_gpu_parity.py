@@ -631,7 +631,8 @@ def test_reference_shaped_api(state_dict):
     missing, unexpected = model.load_state_dict(state_dict, strict=False)
     assert not unexpected and all(k.split(".")[0] in ("betas", "alphas", "alphas_cumprod", "sqrt_alphas_cumprod",
                                                       "sqrt_one_minus_alphas_cumprod", "posterior_variance",
-                                                      "posterior_log_variance_clipped") for k in missing)
+                                                      "posterior_log_variance_clipped", "first_stage_model",
+                                                      "clip_image_encoder") for k in missing)
     model = model.cuda().eval()
     batch = {k: v.cuda() for k, v in synth.make_batch(n).items()}
     x_t, x_input, clip = synth.make_inputs(n)

@@ -50,6 +50,19 @@ def test_denoise_step_matches_reference(state_dict, name):
     assert rel(parts["spatial_volume"][:, :, ::4, ::4, ::4], torch.from_numpy(gold["vol_sub"])) < TOL
 
 
+def test_vae_decode_matches_reference_decoder():
+    """decode_first_stage restatement vs the reference's own Decoder class (tests/golden/vae_n2_lat8.npz, 8x8 latents so
+    the CPU run takes a second); the same function at 32x32 latents is the checker of the GPU test."""
+    gold = np.load(os.path.join(GOLD, "vae_n2_lat8.npz"))
+    n, latent, seed = int(gold["n_views"]), int(gold["latent"]), int(gold["seed"])
+    sd = synth.make_vae_state_dict(seed)
+    x = torch.randn(n, 4, latent, latent, generator=torch.Generator().manual_seed(int(gold["input_seed"])))
+    with torch.no_grad():
+        img = O.vae_decode(sd, x / 0.18215)
+    assert img.shape == (n, 3, 8 * latent, 8 * latent)
+    assert rel(img, torch.from_numpy(gold["image"])) < TOL
+
+
 def test_schedule_constants():
     s = O.make_schedule()
     assert s["timesteps"][0] == 1 and s["timesteps"][-1] == 981 and len(s["timesteps"]) == 50
