@@ -126,6 +126,13 @@ MD_API int md_bind_sample(md_ctx* ctx, const float* K, const float* RT, const fl
  * bounds [2][3] f32.  Bit-exact with torch.round((v[:, [2,1,0]] - min) / 0.005).int(). */
 MD_API int md_voxelize(const float* vertices, int nv, int32_t* coord, int32_t* out_sh, float* bounds, void* stream);
 
+/* Batch construction either side of the path (generate_face.py:203-249), so that the batch dict can be produced on the
+ * device: md_affine_points = the rigid alignment of the fitted mesh (scale, so3 rotation + translation, scale, axis swap
+ * composed into one map v' = A v + b; A row-major [9] and b [3] are HOST arrays), md_voxelize = coord / out_sh / bounds
+ * (rule a1), md_images_to_u8 = clamp(x,-1,1) -> (x+1)/2*255 -> uint8, NCHW fp32 [n][3][H][W] -> NHWC uint8 [n][H][W][3]. */
+MD_API int md_affine_points(const float* v, int n, const float* A9_host, const float* b3_host, float* out, void* stream);
+MD_API int md_images_to_u8(const float* img, unsigned char* out, int n, int H, int W, void* stream);
+
 /* SpatialVolumeNet.construct_spatial_volume (morphable_diffusion.py:182-263) for the bound sample.
  * x_local [n_local][4][S][S] fp32; t_embed [time_embed_dim] (md_embed_time); volume_out [64][V][V][V] fp32
  * (NCDHW, B = 1). With a communicator set

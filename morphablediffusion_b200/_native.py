@@ -93,9 +93,10 @@ def conv_gemm(A, Wt, *, B, D, H, W, Cin, N, taps, bias=None, rowvec=None, res_f3
               out_f32=None, out_bf16=None, act="none", Cpitch=0, out_dims=None, os_=None, op=None, ldo=0,
               out_scale=1.0, BN=0, col_stats=None, in_stride=None, ksplit=0, cta_pair=0, tail_split=0, Wpitch=0):
     a = ConvGemmArgs()
-    a.A = ptr(A); a.B, a.D, a.H, a.W = B, D, H, W
+    a.A = (A.data_ptr() if Cpitch else ptr(A)); a.B, a.D, a.H, a.W = B, D, H, W
     a.Cin, a.Cpitch = Cin, Cpitch
-    a.Wt = ptr(Wt); a.N = N
+    # Wpitch: Wt is a column slice of a wider row-major matrix (rows Wpitch elements apart); only its base address is used
+    a.Wt = (Wt.data_ptr() if Wpitch else ptr(Wt)); a.N = N
     a.ntaps = len(taps)
     for i, t in enumerate(taps):
         for j in range(3):
@@ -150,6 +151,10 @@ lib.md_workspace_peak.restype = C.c_ulonglong
 lib.md_load_weights.argtypes = [_vp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(_vp), C.POINTER(C.c_longlong), _vp]
 lib.md_bind_sample.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp]
 lib.md_voxelize.argtypes = [_vp, C.c_int, _vp, _vp, _vp, _vp]
+lib.md_affine_points.argtypes = [_vp, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), _vp, _vp]
+lib.md_affine_points.restype = C.c_int
+lib.md_images_to_u8.argtypes = [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp]
+lib.md_images_to_u8.restype = C.c_int
 lib.md_spatial_volume.argtypes = [_vp, _vp, _vp, _vp, _vp]
 lib.md_embed_time.argtypes = [_vp, C.c_float, _vp, _vp]
 lib.md_frustum_feats.argtypes = [_vp, _vp, C.c_int, C.c_int, _vp, C.POINTER(_vp), _vp]

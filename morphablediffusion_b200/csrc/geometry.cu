@@ -72,6 +72,50 @@ int launch_voxelize(const float* vertices, int nv, int32_t* coord, int32_t* out_
   return check_launch("voxel_coord");
 }
 
+// ------------------------------------------------------------------------------------------------ batch construction
+// Rigid alignment of the fitted mesh (generate_face.py:203-213: scale, so3 rotation + translation, scale, axis swap), one
+// affine map v' = A v + b per vertex (A row-major, composed on the host in double precision).
+struct Affine3 { float a[9]; float b[3]; };
+__global__ void affine_points_kernel(const float* __restrict__ v, int n, Affine3 m, float* __restrict__ out) {
+  pdl_grid_sync();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float x = v[3 * i], y = v[3 * i + 1], z = v[3 * i + 2];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) out[3 * i + k] = fmaf(m.a[3 * k], x, fmaf(m.a[3 * k + 1], y, fmaf(m.a[3 * k + 2], z, m.b[k])));
+}
+
+int launch_affine_points(const float* v, int n, const float* A9, const float* b3, float* out, cudaStream_t st) {
+  Affine3 m;
+  for (int i = 0; i < 9; ++i) m.a[i] = A9[i];
+  for (int i = 0; i < 3; ++i) m.b[i] = b3[i];
+  launch_pdl(affine_points_kernel, dim3((std::max(n, 1) + 255) / 256), dim3(256), 0, st, v, n, m, out);
+  return check_launch("affine_points");
+}
+
+// Decoded images -> 8-bit pixels (generate_face.py:246-249): clamp to [-1, 1], (x + 1) / 2 * 255, truncate;
+// NCHW fp32 [n][3][HW] -> NHWC uint8 [n][HW][3].
+__global__ void images_to_u8_kernel(const float* __restrict__ img, uint8_t* __restrict__ out, int n, int HW) {
+  pdl_grid_sync();
+  const size_t total = static_cast<size_t>(n) * HW;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t b = i / HW, p = i - b * HW;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float x = fminf(fmaxf(img[(b * 3 + c) * HW + p], -1.f), 1.f);
+      out[i * 3 + c] = static_cast<uint8_t>(__fmul_rn(__fmul_rn(__fadd_rn(x, 1.f), 0.5f), 255.f));
+    }
+  }
+}
+
+int launch_images_to_u8(const float* img, uint8_t* out, int n, int HW, cudaStream_t st) {
+  const size_t total = static_cast<size_t>(n) * HW;
+  const int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, static_cast<size_t>(148) * 16));
+  launch_pdl(images_to_u8_kernel, dim3(std::max(blocks, 1)), dim3(256), 0, st, img, out, n, HW);
+  return check_launch("images_to_u8");
+}
+
 // ------------------------------------------------------------------------------------------------ target encoder (K1)
 // One CTA (1024 threads = one thread per latent pixel) runs the whole 8-conv encoder of one view out of shared memory.
 struct EncSmem {
@@ -720,40 +764,62 @@ int launch_frustum_points(const float* cam, int ortho, int D, int size, float le
 }
 
 // ------------------------------------------------------------------------------------------------ frustum gather (K8)
-// One warp per sample point; lane = channel pair.  vol fp32 [V][V][V][64]; out bf16 [npts][64].
-__global__ void frustum_gather_kernel(const float* __restrict__ vol, const float* __restrict__ pts, int V,
-                                      __nv_bfloat16* __restrict__ out, size_t npts) {
+// Trilinear sample of the shared spatial volume at every frustum point (grid_sample, align_corners=True, zeros padding;
+// morphable_diffusion.py:301-307).  vol fp32 [V][V][V][64] (8.4 MB: L2 resident); out bf16 [npts][64].
+// Eight lanes per point, eight channels per lane: a warp works on four consecutive points, every lane has its sixteen
+// 16-byte corner loads in flight together and stores 16 bytes (512 contiguous bytes per warp store).  Consecutive points
+// are neighbouring pixels of one depth slice, so the corner reads are L1 hits; the kernel is bound by the 2 KB of corner
+// data each point pulls through the L1 (3.2 GB per 16-view step), not by the 101 MB it writes.
+__global__ void __launch_bounds__(256) frustum_gather_kernel(const float* __restrict__ vol, const float* __restrict__ pts,
+                                                             int V, __nv_bfloat16* __restrict__ out, size_t npts) {
   pdl_grid_sync();
-  const int lane = threadIdx.x & 31;
-  const size_t p = (blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x) >> 5;
-  if (p >= npts) return;
-  const float gx = pts[p * 3], gy = pts[p * 3 + 1], gz = pts[p * 3 + 2];
-  const float ix = ((gx + 1.f) / 2.f) * (V - 1), iy = ((gy + 1.f) / 2.f) * (V - 1), iz = ((gz + 1.f) / 2.f) * (V - 1);
-  const float fx = floorf(ix), fy = floorf(iy), fz = floorf(iz);
-  const float ax = ix - fx, ay = iy - fy, az = iz - fz;
-  // clamp before the int conversion so far-away points cannot overflow
-  const int x0 = static_cast<int>(fminf(fmaxf(fx, -2.f), static_cast<float>(V)));
-  const int y0 = static_cast<int>(fminf(fmaxf(fy, -2.f), static_cast<float>(V)));
-  const int z0 = static_cast<int>(fminf(fmaxf(fz, -2.f), static_cast<float>(V)));
-  float a0 = 0.f, a1 = 0.f;
+  const int oct = threadIdx.x & 7;           // channels [8*oct, 8*oct + 8)
+  const size_t stride = (static_cast<size_t>(gridDim.x) * blockDim.x) >> 3;
+  for (size_t p = (blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x) >> 3; p < npts; p += stride) {
+    const float gx = pts[p * 3], gy = pts[p * 3 + 1], gz = pts[p * 3 + 2];
+    const float ix = ((gx + 1.f) / 2.f) * (V - 1), iy = ((gy + 1.f) / 2.f) * (V - 1), iz = ((gz + 1.f) / 2.f) * (V - 1);
+    const float fx = floorf(ix), fy = floorf(iy), fz = floorf(iz);
+    const float ax = ix - fx, ay = iy - fy, az = iz - fz;
+    // clamp before the int conversion so far-away points cannot overflow
+    const int x0 = static_cast<int>(fminf(fmaxf(fx, -2.f), static_cast<float>(V)));
+    const int y0 = static_cast<int>(fminf(fmaxf(fy, -2.f), static_cast<float>(V)));
+    const int z0 = static_cast<int>(fminf(fmaxf(fz, -2.f), static_cast<float>(V)));
+    float4 lo[8], hi[8];
+    float w[8];
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    const int dx = c & 1, dy = (c >> 1) & 1, dz = c >> 2;
-    const int xx = x0 + dx, yy = y0 + dy, zz = z0 + dz;
-    if (xx < 0 || xx >= V || yy < 0 || yy >= V || zz < 0 || zz >= V) continue;
-    const float w = (dx ? ax : 1.f - ax) * (dy ? ay : 1.f - ay) * (dz ? az : 1.f - az);
-    const float2 v = *reinterpret_cast<const float2*>(vol + ((static_cast<size_t>(zz) * V + yy) * V + xx) * 64 + lane * 2);
-    a0 += w * v.x;
-    a1 += w * v.y;
+    for (int c = 0; c < 8; ++c) {
+      const int dx = c & 1, dy = (c >> 1) & 1, dz = c >> 2;
+      const int xx = x0 + dx, yy = y0 + dy, zz = z0 + dz;
+      const bool ok = xx >= 0 && xx < V && yy >= 0 && yy < V && zz >= 0 && zz < V;
+      w[c] = ok ? (dx ? ax : 1.f - ax) * (dy ? ay : 1.f - ay) * (dz ? az : 1.f - az) : 0.f;
+      const float* src = vol + ((static_cast<size_t>(ok ? zz : 0) * V + (ok ? yy : 0)) * V + (ok ? xx : 0)) * 64 + oct * 8;
+      lo[c] = __ldg(reinterpret_cast<const float4*>(src));
+      hi[c] = __ldg(reinterpret_cast<const float4*>(src) + 1);
+    }
+    // same accumulation order as the one-warp-per-point kernel it replaces: corners 0..7, a += w * v
+    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      if (w[c] != 0.f) {
+        a[0] += w[c] * lo[c].x; a[1] += w[c] * lo[c].y; a[2] += w[c] * lo[c].z; a[3] += w[c] * lo[c].w;
+        a[4] += w[c] * hi[c].x; a[5] += w[c] * hi[c].y; a[6] += w[c] * hi[c].z; a[7] += w[c] * hi[c].w;
+      }
+    }
+    uint4 o;
+    __nv_bfloat162 t;
+    t = __floats2bfloat162_rn(a[0], a[1]); o.x = *reinterpret_cast<uint32_t*>(&t);
+    t = __floats2bfloat162_rn(a[2], a[3]); o.y = *reinterpret_cast<uint32_t*>(&t);
+    t = __floats2bfloat162_rn(a[4], a[5]); o.z = *reinterpret_cast<uint32_t*>(&t);
+    t = __floats2bfloat162_rn(a[6], a[7]); o.w = *reinterpret_cast<uint32_t*>(&t);
+    *reinterpret_cast<uint4*>(out + p * 64 + oct * 8) = o;
   }
-  __nv_bfloat162 o = __floats2bfloat162_rn(a0, a1);
-  *reinterpret_cast<__nv_bfloat162*>(out + p * 64 + lane * 2) = o;
 }
 
 int launch_frustum_gather(const float* vol, const float* pts, int V, void* out_bf16, size_t npts, cudaStream_t st) {
-  const size_t threads = npts * 32;
-  launch_pdl(frustum_gather_kernel, dim3(static_cast<unsigned>((threads + 255) / 256)), dim3(256), 0, st, 
-      vol, pts, V, static_cast<__nv_bfloat16*>(out_bf16), npts);
+  const size_t threads = npts * 8;
+  const unsigned blocks = static_cast<unsigned>(std::min<size_t>((threads + 255) / 256, static_cast<size_t>(num_sms()) * 32));
+  launch_pdl(frustum_gather_kernel, dim3(std::max(blocks, 1u)), dim3(256), 0, st, vol, pts, V,
+             static_cast<__nv_bfloat16*>(out_bf16), npts);
   return check_launch("frustum_gather");
 }
 

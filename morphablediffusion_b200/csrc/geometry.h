@@ -30,6 +30,9 @@ int launch_volume_resample(const float* feat, const int32_t* idx, const float* w
                            cudaStream_t st);
 int launch_frustum_points(const float* cam, int ortho, int D, int size, float length, float frustum_len, float* pts,
                           int n_views, cudaStream_t st);
+// batch construction (generate_face.py:203-249)
+int launch_affine_points(const float* v, int n, const float* A9_host, const float* b3_host, float* out, cudaStream_t st);
+int launch_images_to_u8(const float* img, uint8_t* out, int n, int HW, cudaStream_t st);
 int launch_frustum_gather(const float* vol, const float* pts, int V, void* out_bf16, size_t npts, cudaStream_t st);
 
 }  // namespace md

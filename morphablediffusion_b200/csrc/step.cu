@@ -348,6 +348,16 @@ int md_voxelize(const float* vertices, int nv, int32_t* coord, int32_t* out_sh, 
   return launch_voxelize(vertices, nv, coord, out_sh, bounds, static_cast<cudaStream_t>(stream));
 }
 
+int md_affine_points(const float* v, int n, const float* A9_host, const float* b3_host, float* out, void* stream) {
+  if (!v || !out || !A9_host || !b3_host || n < 0) return set_error("md_affine_points: bad arguments");
+  return launch_affine_points(v, n, A9_host, b3_host, out, static_cast<cudaStream_t>(stream));
+}
+
+int md_images_to_u8(const float* img, unsigned char* out, int n, int H, int W, void* stream) {
+  if (!img || !out || n < 0 || H < 1 || W < 1) return set_error("md_images_to_u8: bad arguments");
+  return launch_images_to_u8(img, out, n, H * W, static_cast<cudaStream_t>(stream));
+}
+
 int md_embed_time(md_ctx* ctx, float timestep, float* t_embed_out, void* stream) {
   MD_CHECK(ensure_ready(ctx, false));
   Ctx& c = ctx->c;

@@ -470,8 +470,11 @@ class SyncMultiviewDiffusion(_Base):
         _, clip_embed, input_info = self.prepare(batch)
         x_sample, inter = sampler.sample(input_info, clip_embed, unconditional_scale=cfg_scale,
                                          log_every_t=inter_interval, batch_view_num=batch_view_num, batch=batch)
-        N = x_sample.shape[1]
-        x_sample = torch.stack([self.decode_first_stage(x_sample[:, ni]) for ni in range(N)], 1)
+        # morphable_diffusion.py:572 decodes view by view; the views are independent, so all B*N latents go through one
+        # md_vae_decode call (the library chunks them)
+        B, N = x_sample.shape[:2]
+        img = self.decode_first_stage(x_sample.reshape(B * N, *x_sample.shape[2:]))
+        x_sample = img.view(B, N, *img.shape[1:])
         if return_inter_results:
             raise NotImplementedError("intermediate decoding is outside the hot path")
         return x_sample

@@ -617,3 +617,25 @@ def voxelize(vertices):
     out_sh = torch.ceil((max_dhw - min_dhw) / voxel).int()
     out_sh = (out_sh | 3) + 1
     return coord, out_sh, bounds
+
+
+def align_mica_vertices(verts):
+    """generate_face.py:203-213, operation by operation (fp32 torch): *1.087, so3 rotation + translation, *2.5, axis swap.
+    The rotation is pytorch3d's so3_exponential_map (Rodrigues' formula; pytorch3d is not installed here)."""
+    v = verts.float() * 1.087
+    pose = torch.tensor([1.6811e+00, -2.6845e-02, -2.8883e-02, 8.5418e-04, -3.4041e-03, 1.0564e-02])
+    w = pose[:3].double()
+    theta = torch.sqrt(torch.clamp((w * w).sum(), min=1e-8))
+    K = torch.tensor([[0.0, -w[2], w[1]], [w[2], 0.0, -w[0]], [-w[1], w[0], 0.0]], dtype=torch.float64)
+    R = (torch.eye(3, dtype=torch.float64) + torch.sin(theta) / theta * K + (1 - torch.cos(theta)) / theta ** 2 * (K @ K)).float()
+    v = (R @ v.T).T + pose[3:].reshape(-1, 3)
+    v = v * 2.5
+    return (torch.tensor([[1., 0., 0.], [0., 0., 1.], [0., -1., 0]]) @ v.T).T
+
+
+def images_to_u8(x):
+    """generate_face.py:246-249: (clamp(x, -1, 1) + 1) * 0.5 * 255 -> uint8 (numpy astype truncates), [..,3,H,W] -> [..,H,W,3]."""
+    y = (torch.clamp(x.float(), max=1.0, min=-1.0) + 1) * 0.5
+    y = y.permute(*range(x.dim() - 3), -2, -1, -3).cpu().numpy() * 255
+    return torch.from_numpy(y.astype("uint8"))
+

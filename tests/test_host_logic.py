@@ -115,3 +115,19 @@ def test_view_sharding_allreduce_equals_unsharded_sum():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert err < 1e-5
+
+
+def test_alignment_map_composes_the_reference_operations():
+    """generate_face.py:203-213 as one affine map (batch.alignment_map) against the operation-by-operation oracle."""
+    import numpy as np
+    import torch
+    from morphablediffusion_b200 import batch, synth
+    from oracle import ldm_oracle as O
+    R = batch.so3_exponential_map(batch.MICA_POSE[:3])
+    assert np.allclose(R @ R.T, np.eye(3), atol=1e-12) and abs(np.linalg.det(R) - 1.0) < 1e-12
+    A, b = batch.alignment_map()
+    v = synth.head_mesh()[:500] * 0.4
+    ref = O.align_mica_vertices(v)
+    got = v.double() @ torch.from_numpy(A).double().T + torch.from_numpy(b).double()
+    assert float((got - ref.double()).abs().max()) < 2e-6
+
