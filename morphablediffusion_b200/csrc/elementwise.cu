@@ -443,11 +443,12 @@ int launch_group_norm(const GroupNormArgs& a, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------------ LayerNorm
 // One warp per RPW consecutive rows: all RPW rows are requested before the first reduction (one memory round trip per
 // warp instead of one per row) and gamma / beta stay in registers.  Optional per-sample vector added first (and written
-// back): x <- x + addvec[b].  MAXV = ceil(C / 128) float4 per lane.
+// back when write_back != 0): x <- x + addvec[b].  MAXV = ceil(C / 128) float4 per lane.
 template <int MAXV, int RPW>
 __global__ void layer_norm_kernel(float* __restrict__ x, const float* __restrict__ addvec, int addvec_ld,
                                   const float* __restrict__ gamma, const float* __restrict__ beta,
-                                  __nv_bfloat16* __restrict__ out, size_t nrows, int rows_per_sample, int C, float eps) {
+                                  __nv_bfloat16* __restrict__ out, size_t nrows, int rows_per_sample, int C, float eps,
+                                  int write_back) {
   pdl_grid_sync();
   const int lane = threadIdx.x & 31;
   const size_t row0 = ((blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x) >> 5) * RPW;
@@ -484,7 +485,7 @@ __global__ void layer_norm_kernel(float* __restrict__ x, const float* __restrict
         if (c < C) {
           const float4 a4 = load4(av + c);
           v[r][k].x += a4.x; v[r][k].y += a4.y; v[r][k].z += a4.z; v[r][k].w += a4.w;
-          store4(x + row * C + c, v[r][k]);
+          if (write_back) store4(x + row * C + c, v[r][k]);
         }
       }
     }
@@ -525,21 +526,23 @@ __global__ void layer_norm_kernel(float* __restrict__ x, const float* __restrict
 
 template <int MAXV, int RPW>
 static int layer_norm_impl(float* x, const float* addvec, int addvec_ld, const float* gamma, const float* beta,
-                           void* out_bf16, size_t nrows, int rows_per_sample, int C, float eps, cudaStream_t st) {
+                           void* out_bf16, size_t nrows, int rows_per_sample, int C, float eps, int write_back,
+                           cudaStream_t st) {
   const int threads = 256;
   const size_t warps = (nrows + RPW - 1) / RPW;
   const size_t blocks = (warps * 32 + threads - 1) / threads;
   launch_pdl(layer_norm_kernel<MAXV, RPW>, dim3(static_cast<unsigned>(blocks)), dim3(threads), 0, st, x, addvec, addvec_ld,
-             gamma, beta, static_cast<__nv_bfloat16*>(out_bf16), nrows, rows_per_sample, C, eps);
+             gamma, beta, static_cast<__nv_bfloat16*>(out_bf16), nrows, rows_per_sample, C, eps, write_back);
   return check_launch("layer_norm");
 }
 
 int launch_layer_norm(float* x, const float* addvec, int addvec_ld, const float* gamma, const float* beta,
-                      void* out_bf16, size_t nrows, int rows_per_sample, int C, float eps, cudaStream_t st) {
+                      void* out_bf16, size_t nrows, int rows_per_sample, int C, float eps, cudaStream_t st,
+                      int write_back) {
   if (C % 4 || C > 1280) return set_error("layer_norm: unsupported C=%d", C);
-  if (C <= 384) return layer_norm_impl<3, 4>(x, addvec, addvec_ld, gamma, beta, out_bf16, nrows, rows_per_sample, C, eps, st);
-  if (C <= 640) return layer_norm_impl<5, 2>(x, addvec, addvec_ld, gamma, beta, out_bf16, nrows, rows_per_sample, C, eps, st);
-  return layer_norm_impl<10, 1>(x, addvec, addvec_ld, gamma, beta, out_bf16, nrows, rows_per_sample, C, eps, st);
+  if (C <= 384) return layer_norm_impl<3, 4>(x, addvec, addvec_ld, gamma, beta, out_bf16, nrows, rows_per_sample, C, eps, write_back, st);
+  if (C <= 640) return layer_norm_impl<5, 2>(x, addvec, addvec_ld, gamma, beta, out_bf16, nrows, rows_per_sample, C, eps, write_back, st);
+  return layer_norm_impl<10, 1>(x, addvec, addvec_ld, gamma, beta, out_bf16, nrows, rows_per_sample, C, eps, write_back, st);
 }
 
 // ------------------------------------------------------------------------------------------------ small linear

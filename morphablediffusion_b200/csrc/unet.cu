@@ -69,12 +69,13 @@ struct Fwd {
   }
   // plain GEMM over rows = nb * rows_per_sample tokens
   int gemm(const bf16* a_in, int nb, size_t rows_per_sample, const GemmW& w, const float* res_f32, float* out_f32,
-           bf16* out_bf16, bool stats, int act = ACT_NONE) {
+           bf16* out_bf16, bool stats, int act = ACT_NONE, const float* rowvec = nullptr, int rowvec_ld = 0) {
     md_conv_gemm_args a;
     memset(&a, 0, sizeof(a));
     a.A = a_in; a.B = nb; a.D = 1; a.H = 1; a.W = static_cast<int>(rows_per_sample); a.Cin = w.K; a.Wt = w.w; a.N = w.N;
     a.ntaps = 1;
     a.bias = w.bias; a.res_f32 = res_f32; a.out_f32 = out_f32; a.out_bf16 = out_bf16; a.act = act;
+    a.rowvec = rowvec; a.rowvec_ld = rowvec_ld;
     const void* key = out_f32 ? static_cast<const void*>(out_f32) : static_cast<const void*>(out_bf16);
     if (stats && rows_per_sample >= 32 && rows_per_sample % 32 == 0) {
       a.col_stats = new_stats(key, nb, w.N);
@@ -159,11 +160,12 @@ struct Fwd {
     MD_CHECK(launch_self_attention(qkv, att, B, static_cast<int>(S), s.heads, C / s.heads, st));
     MD_CHECK(gemm(att, B, S, s.o1, x, x, nullptr, false));
     // attn2: one context token => softmax == 1 => attn2(x) = to_out(to_v(ctx)) for every query (precomputed per
-    // forward in v2_all).  x += v2[b]; then norm3 -> GEGLU feed-forward
+    // forward in v2_all): x2 = x + v2[b].  norm3 sees x2 without writing it back; the feed-forward's output GEMM adds
+    // the vector again as its per-sample epilogue vector: xb = ff2(geglu(ff1(norm3(x2)))) + v2[b] + x
     MD_CHECK(launch_layer_norm(x, v2_all + s.v2_off, c.unet.v2_total, s.ln3.g, s.ln3.b, ln, rows, static_cast<int>(S), C,
-                               1e-5f, st));
+                               1e-5f, st, /*write_back=*/0));
     MD_CHECK(gemm(ln, B, S, s.ff1, nullptr, nullptr, ff, false, ACT_GEGLU));
-    MD_CHECK(gemm(ff, B, S, s.ff2, x, nullptr, xb, false));
+    MD_CHECK(gemm(ff, B, S, s.ff2, x, nullptr, xb, false, ACT_NONE, v2_all + s.v2_off, c.unet.v2_total));
     MD_CHECK(gemm(xb, B, S, s.proj_out, x_in, out, out_b, true));
     A().release(m);
     return 0;
