@@ -163,7 +163,41 @@ def kernel_rooflines(dev, tensor_peak, hbm_peak):
     out.append({"kernel": "gn_apply_fused_kernel", "shape": "fp32 [32][1024][320] -> bf16, GroupNorm32 + SiLU",
                 "bound": "hbm", "achieved": by / t / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": by / t / 1e9 / hbm_peak,
                 "us": t * 1e6, "traffic": 42.3e6,
-                "traffic_source": "profiles/r01_gn_apply_fused_full_v8.md (dram read + write; the bf16 output stays in L2)"})
+                "traffic_source": "profiles/r01_gn_apply_fused_full_v8.md (dram read + write; the bf16 output stays in L2); "
+                                  "in-step launches: profiles/r02_hbm_kernels_full.md"})
+    return out
+
+
+def vae_decode_block(args, dev, tensor_peak):
+    """SURVEY §8f rank 1 beside the headline metric: decode_first_stage of the N views (md_vae_decode) on this GPU,
+    device-timed; 622 GFLOP per view at 256x256."""
+    from morphablediffusion_b200 import synth
+    from morphablediffusion_b200.engine import Engine
+    sd = dict(synth.make_state_dict())
+    sd.update(synth.make_vae_state_dict())
+    eng = Engine(latent_size=args.latent, image_size=args.latent * 8, max_views_per_call=16)
+    eng.load_state_dict(sd)
+    del sd
+    x = torch.randn(args.views, 4, args.latent, args.latent, device=dev)
+    for _ in range(2):
+        img = eng.vae_decode(x)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 5
+    e0.record()
+    for _ in range(reps):
+        img = eng.vae_decode(x)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    ok = bool(torch.isfinite(img).all())
+    eng.close()
+    torch.cuda.empty_cache()
+    out = {"what": f"decode_first_stage of {args.views} views @{args.latent * 8}x{args.latent * 8} (md_vae_decode)",
+           "ms": ms, "views_per_s": args.views / ms * 1e3, "finite": ok}
+    if args.latent == 32:
+        tf = args.views * 622e9 / (ms * 1e-3) / 1e12
+        out.update({"tflops": tf, "frac_of_burst": tf / tensor_peak, "denoise_step_equivalents": None})
     return out
 
 
@@ -403,6 +437,14 @@ def run_ours(args):
                 line["roofline"]["kernels"] = kernel_rooflines(dev, burst, hbm)
             except Exception as e:  # noqa: BLE001
                 line["roofline"]["kernels_error"] = str(e)
+        if world == 1 and not args.no_vae:
+            eng.close()
+            torch.cuda.empty_cache()
+            try:
+                line["vae_decode"] = vae_decode_block(args, dev, burst)
+                line["vae_decode"]["denoise_step_equivalents"] = line["vae_decode"]["ms"] / (ms_total / steps)
+            except Exception as e:  # noqa: BLE001
+                line["vae_decode"] = {"error": f"{type(e).__name__}: {e}"[:300]}
         if world == 1 and not args.no_eager:
             eng.close()
             torch.cuda.empty_cache()
@@ -431,6 +473,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-eager", action="store_true", help="skip the PyTorch-eager-on-GPU library baseline")
     ap.add_argument("--no-kernels", action="store_true", help="skip the per-kernel roofline timings")
+    ap.add_argument("--no-vae", action="store_true", help="skip the first-stage decode timing block")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -18,6 +18,10 @@ CASES = {
     "conv_l3": dict(B=32, H=4, W=4, K=1280, N=1280, taps_n=9, BN=64, mode="res"),
     "ff2_l2": dict(B=32, H=1, W=64, K=5120, N=1280, BN=128, mode="bf16"),
     "ff2_l0": dict(B=32, H=1, W=1024, K=1280, N=320, BN=160, mode="bf16res"),
+    # the three roofline.kernels shapes of bench.py (library's own tile choice, fused statistics)
+    "roof_conv640_l0": dict(B=32, H=32, W=32, K=640, N=640, taps_n=9, BN=0, mode="f32", stats=True),
+    "roof_conv320_l0": dict(B=32, H=32, W=32, K=320, N=320, taps_n=9, BN=0, mode="f32", stats=True),
+    "roof_conv1280_l1": dict(B=32, H=16, W=16, K=1280, N=1280, taps_n=9, BN=0, mode="f32", stats=True),
 }
 
 
