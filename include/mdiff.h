@@ -167,6 +167,13 @@ MD_API int md_denoise_step(md_ctx* ctx, float* x_local, const float* x_input, co
  * given to md_load_weights (md_has_vae tells); views are independent, so with several ranks each decodes its own. */
 MD_API int md_vae_decode(md_ctx* ctx, const float* x, float* image, int n, int latent_size, void* stream);
 MD_API int md_has_vae(md_ctx* ctx);
+/* The VAE half of SyncMultiviewDiffusion.prepare (morphable_diffusion.py:473-486, encode_first_stage :460-466):
+ * moments = quant_conv(Encoder(image)) (ldm/models/autoencoder.py:324-328, ldm/modules/diffusionmodules/model.py:368-459).
+ * image [n][3][8S][8S] in [-1, 1] (device, fp32, NCHW), moments [n][8][S][S] = mean | logvar; the caller draws the
+ * posterior sample (mean + exp(0.5 logvar) * noise) and applies the 0.18215 scale, as DiagonalGaussianDistribution does.
+ * Needs first_stage_model.encoder.* / quant_conv.* among the loaded weights (md_has_vae_encoder tells). */
+MD_API int md_vae_encode(md_ctx* ctx, const float* image, float* moments, int n, int latent_size, void* stream);
+MD_API int md_has_vae_encoder(md_ctx* ctx);
 MD_API int md_ddim_timestep(md_ctx* ctx, int index);  /* 1 .. 981 */
 /* SyncDDIMSampler(model, ddim_num_steps, "uniform", ddim_eta) (morphable_diffusion.py:649-672): rebuilds the DDIM
  * schedule (timesteps range(0,1000,1000/steps)+1, alphas, alphas_prev, sigmas) of the context.  Cheap; may be called

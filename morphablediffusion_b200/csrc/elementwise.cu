@@ -715,6 +715,34 @@ int launch_vae_input(const float* x, const float* pq, float in_scale, void* out_
   return check_launch("vae_input");
 }
 
+// Image -> operand of the first-stage encoder's conv_in: NCHW fp32 [B][C <= 4][HW] -> bf16 [B][HW][64], zero-padded to one
+// K block.  One thread per (sample, pixel, 4-channel group).
+__global__ void nchw_to_cl64_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int B, int C, size_t HW) {
+  pdl_grid_sync();
+  const size_t total = static_cast<size_t>(B) * HW * 16;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(i & 15);
+    const size_t bp = i >> 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (g == 0) {
+      const size_t b = bp / HW, pix = bp - b * HW;
+      float in[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int c = 0; c < C; ++c) in[c] = x[(b * C + c) * HW + pix];
+      v = make_float4(in[0], in[1], in[2], in[3]);
+    }
+    store4(out + bp * 64 + g * 4, v);
+  }
+}
+
+int launch_nchw_to_cl64(const float* x, void* out_bf16, int B, int C, size_t HW, cudaStream_t st) {
+  if (C < 1 || C > 4) return set_error("nchw_to_cl64: C=%d unsupported", C);
+  const size_t total = static_cast<size_t>(B) * HW * 16;
+  const int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, static_cast<size_t>(num_sms()) * 16));
+  launch_pdl(nchw_to_cl64_kernel, dim3(blocks), dim3(256), 0, st, x, static_cast<__nv_bfloat16*>(out_bf16), B, C, HW);
+  return check_launch("nchw_to_cl64");
+}
+
 // Row softmax fp32 -> bf16, one warp per row (n a multiple of 4): max, sum of exponentials, normalise; the row is read
 // three times, the second and third time out of L1/L2.
 __global__ void softmax_rows_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, size_t rows, int n) {

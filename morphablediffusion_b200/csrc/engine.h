@@ -93,6 +93,18 @@ struct VaeW {
   NormW norm_out;
 };
 
+// First-stage encoder up to the posterior moments (AutoencoderKL.encode, autoencoder.py:324-328; Encoder, model.py:368-459)
+struct VaeEncW {
+  bool loaded = false;
+  GemmW conv_in;                   // 3 -> 128, Cin padded to 64
+  std::vector<std::vector<ResW>> down;   // down[i_level][i_block]
+  GemmW downsample[4];             // down[i_level].downsample.conv for i_level < 3 (k3 s2, pad right/bottom)
+  ResW mid1, mid2;
+  VaeAttnW attn;
+  NormW norm_out;
+  GemmW conv_out;                  // quant_conv (1x1) folded into conv_out: 512 -> 8 moments
+};
+
 struct FrBlockW {   // FrustumTVBlock / FrustumTVUpBlock
   int cin = 0, cout = 0, stride = 1; bool up = false;
   const float* t_w = nullptr; const float* t_b = nullptr; const float* v_w = nullptr; const float* v_b = nullptr;
@@ -132,6 +144,7 @@ struct Ctx {
   UNetW unet;
   VolumeW vol;
   VaeW vae;
+  VaeEncW vae_enc;
   bool weights_loaded = false;
   std::vector<void*> weight_allocs;
   Arena arena;
@@ -187,6 +200,8 @@ int unet_forward(Ctx& c, const float* x_in, const float* timesteps, const float*
 // unet.cu: decode_first_stage for T latents.  x fp32 NCHW [T][4][S][S] (scaled latents: divided by 0.18215 inside),
 // image fp32 NCHW [T][3][8S][8S].
 int vae_decode(Ctx& c, const float* x, float* image, int T, int S, cudaStream_t st);
+// AutoencoderKL.encode up to the moments: image fp32 NCHW [T][3][8S][8S] in [-1,1] -> moments fp32 NCHW [T][8][S][S]
+int vae_encode(Ctx& c, const float* image, float* moments, int T, int S, cudaStream_t st);
 
 // volume.cu
 int bind_sample(Ctx& c, const float* K, const float* RT, const float* v_embed, const float* vertices,

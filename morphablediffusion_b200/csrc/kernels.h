@@ -43,6 +43,8 @@ int launch_pad_cast_bf16(const float* x, void* out, size_t rows, int C, int Cpad
 // VAE input: post_quant_conv (1x1, pq = [4][4] weight | [4] bias) of x * in_scale, NCHW fp32 [B][4][HW] -> bf16 [B][HW][64]
 // zero-padded to one K block;  row softmax fp32 [rows][n] -> bf16 (AttnBlock, model.py:190-192)
 int launch_vae_input(const float* x, const float* pq, float in_scale, void* out_bf16, int B, int HW, cudaStream_t st);
+// NCHW fp32 [B][C][HW] (C <= 4) -> bf16 channels-last [B][HW][64], zero-padded (first-stage encoder input)
+int launch_nchw_to_cl64(const float* x, void* out_bf16, int B, int C, size_t HW, cudaStream_t st);
 int launch_softmax_rows(const float* x, void* out_bf16, size_t rows, int n, cudaStream_t st);
 int launch_upsample2x(const float* x, void* out, int B, int H, int W, int C, cudaStream_t st);
 int launch_ncdhw_to_cl_bf16(const float* x, void* out, int B, int C, size_t S, cudaStream_t st);

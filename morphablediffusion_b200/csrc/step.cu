@@ -540,6 +540,23 @@ int md_vae_decode(md_ctx* ctx, const float* x, float* image, int n, int latent_s
   return 0;
 }
 
+int md_has_vae_encoder(md_ctx* ctx) { return ctx && ctx->c.vae_enc.loaded ? 1 : 0; }
+
+int md_vae_encode(md_ctx* ctx, const float* image, float* moments, int n, int latent_size, void* stream) {
+  MD_CHECK(ensure_ready(ctx, false));
+  Ctx& c = ctx->c;
+  SplitScope split_scope(&c.split_main);
+  if (latent_size <= 0) latent_size = c.mcfg.latent_size;
+  const int chunk = std::max(1, c.mcfg.max_views_per_call > 0 ? std::min(c.mcfg.max_views_per_call, 16) : 16);
+  const size_t in_per = static_cast<size_t>(3) * 64 * latent_size * latent_size;
+  const size_t out_per = static_cast<size_t>(8) * latent_size * latent_size;
+  for (int i0 = 0; i0 < n; i0 += chunk) {
+    const int T = std::min(chunk, n - i0);
+    MD_CHECK(vae_encode(c, image + i0 * in_per, moments + i0 * out_per, T, latent_size, static_cast<cudaStream_t>(stream)));
+  }
+  return 0;
+}
+
 int md_set_ddim(md_ctx* ctx, int ddim_steps, float ddim_eta) {
   if (!ctx) return set_error("null context");
   if (ddim_steps < 1 || ddim_steps > 1000) return set_error("md_set_ddim: ddim_steps=%d out of range 1..1000", ddim_steps);

@@ -211,7 +211,9 @@ struct Fwd {
   }
 
   // Downsample: Conv2d 3x3 stride 2 pad 1 (openaimodel.py:159-161): implicit GEMM whose TMA boxes step by 2 pixels
-  int downsample(const GemmW& w, const float* x, const bf16* x_b, int H, int W, int C, float* out) {
+  // tap0 = -1: Conv2d k3 s2 p1 (UNet Downsample); tap0 = 0: the first-stage Downsample (model.py:70-78: zero pad on the
+  // right / bottom only, conv k3 s2 p0), i.e. taps 0..2 with the out-of-range column / row zero-filled by TMA
+  int downsample(const GemmW& w, const float* x, const bf16* x_b, int H, int W, int C, float* out, int tap0 = -1) {
     const size_t rows = static_cast<size_t>(B) * H * W;
     const size_t m = A().mark();
     bf16* xb = x_b ? nullptr : A().get<bf16>(rows * C);
@@ -221,6 +223,7 @@ struct Fwd {
     memset(&a, 0, sizeof(a));
     a.A = x_b ? x_b : xb; a.B = B; a.D = 1; a.H = H; a.W = W; a.Cin = C; a.Wt = w.w; a.N = w.N;
     taps2d(a);
+    for (int t = 0; t < 9; ++t) { a.tap[t][0] += tap0 + 1; a.tap[t][1] += tap0 + 1; }
     a.in_stride[0] = 2; a.in_stride[1] = 2; a.in_stride[2] = 1;
     a.bias = w.bias; a.out_f32 = out;
     if ((H / 2) * (W / 2) >= 32) {
@@ -415,6 +418,45 @@ int unet_forward(Ctx& c, const float* x_in, const float* timesteps, const float*
   return 0;
 }
 
+// AttnBlock of the first-stage models (model.py:177-203): h fp32 [T][Sx][C] with GEMM-epilogue statistics -> o.
+static int vae_attn_block(Fwd& f, Arena& A, const VaeAttnW& a, const float* h, float* o, int T, int Sx, cudaStream_t st) {
+  const int C = a.C;
+  if (Sx % 64) return set_error("first-stage attention over %d positions (must be a multiple of 64)", Sx);
+  const size_t m = A.mark();
+  bf16* hn = A.get<bf16>(static_cast<size_t>(T) * Sx * C);
+  bf16* qk = A.get<bf16>(static_cast<size_t>(T) * Sx * 2 * C);
+  bf16* vT = A.get<bf16>(static_cast<size_t>(C) * Sx);
+  float* sc = A.get<float>(static_cast<size_t>(Sx) * Sx);
+  bf16* pr = A.get<bf16>(static_cast<size_t>(Sx) * Sx);
+  bf16* att = A.get<bf16>(static_cast<size_t>(T) * Sx * C);
+  if (A.failed) return set_error("workspace exhausted (first-stage attention)");
+  MD_CHECK(f.gn(h, C, false, nullptr, 0, T, Sx, 32, 1e-6f, a.norm, ACT_NONE, hn, nullptr));
+  MD_CHECK(f.gemm(hn, T, Sx, a.qk, nullptr, nullptr, qk, false));
+  for (int b = 0; b < T; ++b) {
+    md_conv_gemm_args g;
+    const bf16* hb = hn + static_cast<size_t>(b) * Sx * C;
+    const bf16* qb = qk + static_cast<size_t>(b) * Sx * 2 * C;
+    // V^T [C][Sx] = Wv [C][C] . h_b^T: the normalised activations of sample b are the K-major "weight" operand
+    memset(&g, 0, sizeof(g));
+    g.A = a.wv; g.B = 1; g.D = 1; g.H = 1; g.W = C; g.Cin = C; g.Wt = hb; g.N = Sx; g.ntaps = 1; g.out_bf16 = vT;
+    MD_CHECK(launch_conv_gemm(g, st));
+    // scores [Sx][Sx] = q_b k_b^T * C^-0.5 (q at columns 0..C-1, k at C..2C-1 of the fused activation)
+    memset(&g, 0, sizeof(g));
+    g.A = qb; g.B = 1; g.D = 1; g.H = 1; g.W = Sx; g.Cin = C; g.Cpitch = 2 * C; g.Wt = qb + C; g.Wpitch = 2 * C;
+    g.N = Sx; g.ntaps = 1; g.out_f32 = sc; g.out_scale = 1.f / sqrtf(static_cast<float>(C));
+    MD_CHECK(launch_conv_gemm(g, st));
+    MD_CHECK(launch_softmax_rows(sc, pr, static_cast<size_t>(Sx), Sx, st));
+    // O [Sx][C] = P V + b_v
+    memset(&g, 0, sizeof(g));
+    g.A = pr; g.B = 1; g.D = 1; g.H = 1; g.W = Sx; g.Cin = Sx; g.Wt = vT; g.N = C; g.ntaps = 1; g.bias = a.bv;
+    g.out_bf16 = att + static_cast<size_t>(b) * Sx * C;
+    MD_CHECK(launch_conv_gemm(g, st));
+  }
+  MD_CHECK(f.gemm(att, T, Sx, a.proj, h, o, nullptr, true));
+  A.release(m);
+  return 0;
+}
+
 // decode_first_stage (morphable_diffusion.py:468-471) = AutoencoderKL.decode (ldm/models/autoencoder.py:330-333) =
 // post_quant_conv + Decoder.forward (ldm/modules/diffusionmodules/model.py:535-569) on the UNet's kernels: ResnetBlock =
 // GroupNorm(eps 1e-6)+SiLU -> conv3x3 -> GroupNorm+SiLU -> conv3x3 (+ 1x1 nin_shortcut), statistics from the GEMM
@@ -464,43 +506,8 @@ int vae_decode(Ctx& c, const float* x, float* image, int T, int S, cudaStream_t 
   };
   MD_CHECK(block(v.mid1));
   {  // AttnBlock (model.py:177-203)
-    const VaeAttnW& a = v.attn;
-    const int C = a.C;
-    const int Sx = H * H;
-    if (Sx % 64) return set_error("vae_decode: attention over %d positions (must be a multiple of 64)", Sx);
     float* o = next_buf();
-    const size_t m = A.mark();
-    bf16* hn = A.get<bf16>(static_cast<size_t>(T) * Sx * C);
-    bf16* qk = A.get<bf16>(static_cast<size_t>(T) * Sx * 2 * C);
-    bf16* vT = A.get<bf16>(static_cast<size_t>(C) * Sx);
-    float* sc = A.get<float>(static_cast<size_t>(Sx) * Sx);
-    bf16* pr = A.get<bf16>(static_cast<size_t>(Sx) * Sx);
-    bf16* att = A.get<bf16>(static_cast<size_t>(T) * Sx * C);
-    if (A.failed) return set_error("workspace exhausted (vae attention)");
-    MD_CHECK(f.gn(h, C, false, nullptr, 0, T, Sx, 32, 1e-6f, a.norm, ACT_NONE, hn, nullptr));
-    MD_CHECK(f.gemm(hn, T, Sx, a.qk, nullptr, nullptr, qk, false));
-    for (int b = 0; b < T; ++b) {
-      md_conv_gemm_args g;
-      const bf16* hb = hn + static_cast<size_t>(b) * Sx * C;
-      const bf16* qb = qk + static_cast<size_t>(b) * Sx * 2 * C;
-      // V^T [C][Sx] = Wv [C][C] . h_b^T: the normalised activations of sample b are the K-major "weight" operand
-      memset(&g, 0, sizeof(g));
-      g.A = a.wv; g.B = 1; g.D = 1; g.H = 1; g.W = C; g.Cin = C; g.Wt = hb; g.N = Sx; g.ntaps = 1; g.out_bf16 = vT;
-      MD_CHECK(launch_conv_gemm(g, st));
-      // scores [Sx][Sx] = q_b k_b^T * C^-0.5 (q at columns 0..C-1, k at C..2C-1 of the fused activation)
-      memset(&g, 0, sizeof(g));
-      g.A = qb; g.B = 1; g.D = 1; g.H = 1; g.W = Sx; g.Cin = C; g.Cpitch = 2 * C; g.Wt = qb + C; g.Wpitch = 2 * C;
-      g.N = Sx; g.ntaps = 1; g.out_f32 = sc; g.out_scale = 1.f / sqrtf(static_cast<float>(C));
-      MD_CHECK(launch_conv_gemm(g, st));
-      MD_CHECK(launch_softmax_rows(sc, pr, static_cast<size_t>(Sx), Sx, st));
-      // O [Sx][C] = P V + b_v
-      memset(&g, 0, sizeof(g));
-      g.A = pr; g.B = 1; g.D = 1; g.H = 1; g.W = Sx; g.Cin = Sx; g.Wt = vT; g.N = C; g.ntaps = 1; g.bias = a.bv;
-      g.out_bf16 = att + static_cast<size_t>(b) * Sx * C;
-      MD_CHECK(launch_conv_gemm(g, st));
-    }
-    MD_CHECK(f.gemm(att, T, Sx, a.proj, h, o, nullptr, true));
-    A.release(m);
+    MD_CHECK(vae_attn_block(f, A, v.attn, h, o, T, H * H, st));
     h = o;
   }
   MD_CHECK(block(v.mid2));
@@ -518,6 +525,70 @@ int vae_decode(Ctx& c, const float* x, float* image, int T, int S, cudaStream_t 
   MD_CHECK(f.gn(h, ch, false, nullptr, 0, T, H * H, 32, 1e-6f, v.norm_out, ACT_SILU, ao, nullptr));
   MD_CHECK(f.conv(ao, T, H, H, v.conv_out, nullptr, 0, nullptr, rgb8, nullptr, false));
   MD_CHECK(launch_rows_to_nchw(rgb8, 8, image, T, v.out_ch, H * H, st));
+  return 0;
+}
+
+// AutoencoderKL.encode up to the posterior moments (ldm/models/autoencoder.py:324-328): Encoder.forward
+// (ldm/modules/diffusionmodules/model.py:432-459) + quant_conv (folded into conv_out at load time).  Same kernels as the
+// decoder; Downsample (:70-78) is the stride-2 implicit GEMM with taps 0..2 (right / bottom zero padding = TMA zero fill).
+int vae_encode(Ctx& c, const float* image, float* moments, int T, int S, cudaStream_t st) {
+  if (!c.vae_enc.loaded) return set_error("vae_encode: no first-stage encoder weights were loaded (first_stage_model.encoder.*)");
+  if (T < 1 || S < 8 || S % 8) return set_error("vae_encode: bad shape T=%d S=%d", T, S);
+  const VaeEncW& v = c.vae_enc;
+  Arena& A = c.arena;
+  A.off = 0;
+  A.failed = false;
+  Fwd f{c, st, T, T, nullptr, nullptr};
+  f.res_eps = 1e-6f;
+  const size_t spool_floats = static_cast<size_t>(T) * 2 * 48 * 512;
+  f.spool = A.get<float>(spool_floats);
+  f.spool_cap = spool_floats;
+  if (A.failed) return set_error("workspace exhausted (vae statistics)");
+  MD_CUDA(cudaMemsetAsync(f.spool, 0, spool_floats * sizeof(float), st));
+
+  int H = 8 * S;
+  int ch = v.conv_in.N;
+  const size_t max_act = static_cast<size_t>(T) * H * H * ch;   // the 128-channel tensors at full resolution
+  float* bufs[2] = {A.get<float>(max_act), A.get<float>(max_act)};
+  if (A.failed) return set_error("workspace exhausted (vae encoder activations: %zu MB)", (2 * max_act * sizeof(float)) >> 20);
+  int cur = 0;
+  float* h = bufs[0];
+  auto next_buf = [&]() { cur ^= 1; return bufs[cur]; };
+  {
+    const size_t m = A.mark();
+    bf16* xin = A.get<bf16>(static_cast<size_t>(T) * H * H * 64);
+    if (A.failed) return set_error("workspace exhausted (vae encoder input)");
+    MD_CHECK(launch_nchw_to_cl64(image, xin, T, 3, static_cast<size_t>(H) * H, st));
+    MD_CHECK(f.conv(xin, T, H, H, v.conv_in, nullptr, 0, nullptr, h, nullptr, true));
+    A.release(m);
+  }
+  auto block = [&](const ResW& r) -> int {
+    float* o = next_buf();
+    MD_CHECK(f.res_block(r, h, ch, nullptr, 0, H, H, o));
+    h = o; ch = r.cout;
+    return 0;
+  };
+  for (size_t lev = 0; lev < v.down.size(); ++lev) {
+    for (const ResW& r : v.down[lev]) MD_CHECK(block(r));
+    if (lev + 1 != v.down.size()) {
+      float* o = next_buf();
+      MD_CHECK(f.downsample(v.downsample[lev], h, nullptr, H, H, ch, o, /*tap0=*/0));
+      h = o; H /= 2;
+    }
+  }
+  MD_CHECK(block(v.mid1));
+  {
+    float* o = next_buf();
+    MD_CHECK(vae_attn_block(f, A, v.attn, h, o, T, H * H, st));
+    h = o;
+  }
+  MD_CHECK(block(v.mid2));
+  bf16* ao = A.get<bf16>(static_cast<size_t>(T) * H * H * ch);
+  float* mom8 = A.get<float>(static_cast<size_t>(T) * H * H * 8);
+  if (A.failed) return set_error("workspace exhausted (vae encoder)");
+  MD_CHECK(f.gn(h, ch, false, nullptr, 0, T, H * H, 32, 1e-6f, v.norm_out, ACT_SILU, ao, nullptr));
+  MD_CHECK(f.conv(ao, T, H, H, v.conv_out, nullptr, 0, nullptr, mom8, nullptr, false));
+  MD_CHECK(launch_rows_to_nchw(mom8, 8, moments, T, 8, H * H, st));
   return 0;
 }
 

@@ -74,6 +74,16 @@ __global__ void bn_fold_kernel(const float* g, const float* b, const float* mean
   shift[c] = b[c] - mean[c] * s;
 }
 
+// out[o] = b2[o] + sum_j W[o][j] * b1[j]   (bias of two composed linear maps, n <= 32)
+__global__ void fold_bias_kernel(const float* __restrict__ W, const float* __restrict__ b1, const float* __restrict__ b2,
+                                 float* __restrict__ out, int n) {
+  const int o = threadIdx.x;
+  if (o >= n) return;
+  float a = b2[o];
+  for (int j = 0; j < n; ++j) a += W[o * n + j] * b1[j];
+  out[o] = a;
+}
+
 struct Loader {
   Ctx& c;
   const TensorMap& tm;
@@ -163,6 +173,52 @@ struct Loader {
     g.w = dalloc<bf16>(static_cast<size_t>(g.N) * I);
     if (!g.w) return g;
     for (size_t k = 0; k < names.size(); ++k) pack_conv_into(g.w + k * static_cast<size_t>(O_each) * I, names[k], O_each, I, 1);
+    return g;
+  }
+
+  // first-stage ResnetBlock (model.py:82-141, temb_channels = 0) and AttnBlock (:150-203)
+  ResW vae_res(const std::string& q, int cin, int cout) {
+    ResW r;
+    r.cin = cin; r.cout = cout; r.emb_off = -1;
+    r.n1 = norm(q + "norm1", cin);
+    r.c1 = gemm(q + "conv1", cout, cin, 9, true);
+    r.n2 = norm(q + "norm2", cout);
+    r.c2 = gemm(q + "conv2", cout, cout, 9, true);
+    r.has_skip = cin != cout;
+    if (r.has_skip) r.skip = gemm(q + "nin_shortcut", cout, cin, 1, true);
+    return r;
+  }
+  VaeAttnW vae_attn(const std::string& q, int C) {
+    // q | k fused; v kept as a [C][C] matrix (it becomes the A operand of V^T = Wv . h^T)
+    VaeAttnW t;
+    t.C = C;
+    t.norm = norm(q + "norm", C);
+    t.qk = gemm_fused({q + "q.weight", q + "k.weight"}, C, C);
+    float* qkb = dalloc<float>(2 * C);
+    const NamedTensor* bq = find(q + "q.bias", C);
+    const NamedTensor* bk = find(q + "k.bias", C);
+    if (qkb && bq && bk) {
+      cudaMemcpyAsync(qkb, bq->ptr, sizeof(float) * C, cudaMemcpyDeviceToDevice, st);
+      cudaMemcpyAsync(qkb + C, bk->ptr, sizeof(float) * C, cudaMemcpyDeviceToDevice, st);
+    }
+    t.qk.bias = qkb;
+    t.wv = dalloc<bf16>(static_cast<size_t>(C) * C);
+    if (t.wv) pack_conv_into(t.wv, q + "v.weight", C, C, 1);
+    t.bv = copy_f32(q + "v.bias", C);
+    t.proj = gemm(q + "proj_out", C, C, 1, true);
+    return t;
+  }
+  // conv with Cin <= 64 zero-padded to one K block: bf16 [O][9][64]
+  GemmW conv_padded_in(const std::string& p, int O, int I) {
+    GemmW g;
+    g.N = O; g.K = 64; g.taps = 9;
+    const NamedTensor* t = find(p + ".weight", static_cast<size_t>(O) * I * 9);
+    g.w = dalloc<bf16>(static_cast<size_t>(O) * 9 * 64);
+    if (t && g.w) {
+      cudaMemsetAsync(g.w, 0, sizeof(bf16) * O * 9 * 64, st);
+      pack<bf16>(t->ptr, g.w, O, 9, I, static_cast<long>(I) * 9, 1, 9, iota(), static_cast<long>(9) * 64, 64, 1);
+    }
+    g.bias = copy_f32(p + ".bias", O);
     return g;
   }
 
@@ -522,55 +578,15 @@ int load_all_weights(Ctx& c, const TensorMap& tm, cudaStream_t st) {
         cudaMemcpyAsync(a.pq + 16, b->ptr, 4 * sizeof(float), cudaMemcpyDeviceToDevice, st);
       }
     }
-    {  // conv_in 4 -> 512 with the input channels zero-padded to one K block
-      const NamedTensor* t = L.find(Dp + "conv_in.weight", static_cast<size_t>(block_in) * 4 * 9);
-      a.conv_in.N = block_in; a.conv_in.K = 64; a.conv_in.taps = 9;
-      a.conv_in.w = L.dalloc<bf16>(static_cast<size_t>(block_in) * 9 * 64);
-      if (t && a.conv_in.w) {
-        cudaMemsetAsync(a.conv_in.w, 0, sizeof(bf16) * block_in * 9 * 64, st);
-        L.pack<bf16>(t->ptr, a.conv_in.w, block_in, 9, 4, 4 * 9, 1, 9, Loader::iota(), static_cast<long>(9) * 64, 64, 1);
-      }
-      a.conv_in.bias = L.copy_f32(Dp + "conv_in.bias", block_in);
-    }
-    auto vres = [&](const std::string& q, int cin, int cout) {
-      ResW r;
-      r.cin = cin; r.cout = cout; r.emb_off = -1;
-      r.n1 = L.norm(q + "norm1", cin);
-      r.c1 = L.gemm(q + "conv1", cout, cin, 9, true);
-      r.n2 = L.norm(q + "norm2", cout);
-      r.c2 = L.gemm(q + "conv2", cout, cout, 9, true);
-      r.has_skip = cin != cout;
-      if (r.has_skip) r.skip = L.gemm(q + "nin_shortcut", cout, cin, 1, true);
-      return r;
-    };
-    a.mid1 = vres(Dp + "mid.block_1.", block_in, block_in);
-    a.mid2 = vres(Dp + "mid.block_2.", block_in, block_in);
-    {  // AttnBlock: q | k fused; v kept as a [C][C] matrix (it becomes the A operand of V^T = Wv . h^T)
-      VaeAttnW& t = a.attn;
-      t.C = block_in;
-      const std::string q = Dp + "mid.attn_1.";
-      t.norm = L.norm(q + "norm", block_in);
-      t.qk = L.gemm_fused({q + "q.weight", q + "k.weight"}, block_in, block_in);
-      {
-        float* qkb = L.dalloc<float>(2 * block_in);
-        const NamedTensor* bq = L.find(q + "q.bias", block_in);
-        const NamedTensor* bk = L.find(q + "k.bias", block_in);
-        if (qkb && bq && bk) {
-          cudaMemcpyAsync(qkb, bq->ptr, sizeof(float) * block_in, cudaMemcpyDeviceToDevice, st);
-          cudaMemcpyAsync(qkb + block_in, bk->ptr, sizeof(float) * block_in, cudaMemcpyDeviceToDevice, st);
-        }
-        t.qk.bias = qkb;
-      }
-      t.wv = L.dalloc<bf16>(static_cast<size_t>(block_in) * block_in);
-      if (t.wv) L.pack_conv_into(t.wv, q + "v.weight", block_in, block_in, 1);
-      t.bv = L.copy_f32(q + "v.bias", block_in);
-      t.proj = L.gemm(q + "proj_out", block_in, block_in, 1, true);
-    }
+    a.conv_in = L.conv_padded_in(Dp + "conv_in", block_in, 4);   // 4 -> 512
+    a.mid1 = L.vae_res(Dp + "mid.block_1.", block_in, block_in);
+    a.mid2 = L.vae_res(Dp + "mid.block_2.", block_in, block_in);
+    a.attn = L.vae_attn(Dp + "mid.attn_1.", block_in);
     a.up.assign(nlev, std::vector<ResW>());
     for (int lev = nlev - 1; lev >= 0; --lev) {
       const int block_out = ch * ch_mult[lev];
       for (int ib = 0; ib < nres + 1; ++ib) {
-        a.up[lev].push_back(vres(Dp + "up." + std::to_string(lev) + ".block." + std::to_string(ib) + ".", block_in, block_out));
+        a.up[lev].push_back(L.vae_res(Dp + "up." + std::to_string(lev) + ".block." + std::to_string(ib) + ".", block_in, block_out));
         block_in = block_out;
       }
       if (lev != 0) a.upsample[lev] = L.gemm(Dp + "up." + std::to_string(lev) + ".upsample.conv", block_in, block_in, 9, true);
@@ -593,6 +609,51 @@ int load_all_weights(Ctx& c, const TensorMap& tm, cudaStream_t st) {
     }
     a.loaded = L.rc == 0;
   }
+  // ------------------------------------------------ first-stage encoder (optional, SURVEY §8f rank 2: the VAE half of prepare())
+  c.vae_enc = VaeEncW();
+  if (L.has(FS + "encoder.conv_in.weight")) {
+    VaeEncW& e = c.vae_enc;
+    const std::string Ep = FS + "encoder.";
+    const int ch = 128, nlev = 4, nres = 2;
+    const int ch_mult[4] = {1, 2, 4, 4}, in_mult[5] = {1, 1, 2, 4, 4};
+    e.conv_in = L.conv_padded_in(Ep + "conv_in", ch, 3);
+    int block_in = ch;
+    e.down.assign(nlev, std::vector<ResW>());
+    for (int lev = 0; lev < nlev; ++lev) {
+      block_in = ch * in_mult[lev];
+      const int block_out = ch * ch_mult[lev];
+      for (int ib = 0; ib < nres; ++ib) {
+        e.down[lev].push_back(L.vae_res(Ep + "down." + std::to_string(lev) + ".block." + std::to_string(ib) + ".", block_in, block_out));
+        block_in = block_out;
+      }
+      if (lev != nlev - 1) e.downsample[lev] = L.gemm(Ep + "down." + std::to_string(lev) + ".downsample.conv", block_in, block_in, 9, true);
+    }
+    e.mid1 = L.vae_res(Ep + "mid.block_1.", block_in, block_in);
+    e.attn = L.vae_attn(Ep + "mid.attn_1.", block_in);
+    e.mid2 = L.vae_res(Ep + "mid.block_2.", block_in, block_in);
+    e.norm_out = L.norm(Ep + "norm_out", block_in);
+    {  // quant_conv (1x1, 8 -> 8) folded into conv_out (3x3, 512 -> 8): W' = Wq . Wc, b' = Wq bc + bq
+      const NamedTensor* wc = L.find(Ep + "conv_out.weight", static_cast<size_t>(8) * block_in * 9);
+      const NamedTensor* bc = L.find(Ep + "conv_out.bias", 8);
+      const NamedTensor* wq = L.find(FS + "quant_conv.weight", 64);
+      const NamedTensor* bq = L.find(FS + "quant_conv.bias", 8);
+      const size_t kk = static_cast<size_t>(9) * block_in;
+      float* wc_packed = L.dalloc<float>(8 * kk);   // [j][tap][ci]
+      e.conv_out.N = 8; e.conv_out.K = block_in; e.conv_out.taps = 9;
+      e.conv_out.w = L.dalloc<bf16>(8 * kk);
+      float* ob = L.dalloc<float>(8);
+      e.conv_out.bias = ob;
+      if (wc && bc && wq && bq && wc_packed && e.conv_out.w && ob) {
+        L.pack<float>(wc->ptr, wc_packed, 8, 9, block_in, static_cast<long>(block_in) * 9, 1, 9, Loader::iota(),
+                      static_cast<long>(kk), block_in, 1);
+        dim3 grid(static_cast<unsigned>((kk + 15) / 16), 1), blk(16, 16);
+        matmul_f32_to_bf16_kernel<<<grid, blk, 0, st>>>(wq->ptr, 8, 0, wc_packed, static_cast<int>(kk), e.conv_out.w,
+                                                        static_cast<int>(kk), 8, static_cast<int>(kk), 8, 1.f);
+        fold_bias_kernel<<<1, 32, 0, st>>>(wq->ptr, bc->ptr, bq->ptr, ob, 8);
+      }
+    }
+    e.loaded = L.rc == 0;
+  }
   if (L.rc != 0) { free_weights(c); return L.rc; }
   MD_CUDA(cudaStreamSynchronize(st));
   c.weights_loaded = true;
@@ -604,6 +665,7 @@ void free_weights(Ctx& c) {
   c.weight_allocs.clear();
   c.weights_loaded = false;
   c.vae.loaded = false;
+  c.vae_enc.loaded = false;
 }
 
 }  // namespace md

@@ -162,6 +162,17 @@ class Engine:
         nat.check(nat.lib.md_vae_decode(self._h, x.data_ptr(), out.data_ptr(), n, S, nat.cur_stream()), "md_vae_decode")
         return out
 
+    def has_vae_encoder(self):
+        return bool(nat.lib.md_has_vae_encoder(self._h))
+
+    def vae_encode_moments(self, image):
+        """AutoencoderKL.encode up to the moments: image [n,3,8S,8S] in [-1,1] -> [n,8,S,S] (mean | logvar)."""
+        x = image.to(self.device, torch.float32).contiguous()
+        n, _, H, _ = x.shape
+        out = torch.empty(n, 8, H // 8, H // 8, device=self.device)
+        nat.check(nat.lib.md_vae_encode(self._h, x.data_ptr(), out.data_ptr(), n, H // 8, nat.cur_stream()), "md_vae_encode")
+        return out
+
     def set_ddim(self, ddim_steps, ddim_eta=1.0):
         """Schedule of SyncDDIMSampler(model, ddim_steps, ddim_eta=...) (morphable_diffusion.py:649-672)."""
         if (int(ddim_steps), float(ddim_eta)) != self.ddim:

@@ -361,10 +361,11 @@ class SyncMultiviewDiffusion(_Base):
         self.first_stage_scale_factor = 0.18215
         self.first_stage_model, self._first_stage_error = _build_frozen(lambda: instantiate_from_config(first_stage_config))
         if self.first_stage_model is None:
-            # decode_first_stage runs in the CUDA library either way; without the reference class only the parameter
-            # slots (post_quant_conv + decoder, reference key names) are needed.  encode_first_stage stays unavailable.
-            dec = {k[len("first_stage_model."):]: v for k, v in _spec.vae_decoder_spec().items()}
-            self.first_stage_model = _ParamTree(dec).eval()
+            # encode_first_stage / decode_first_stage run in the CUDA library either way; without the reference class
+            # only the parameter slots (encoder + quant_conv, post_quant_conv + decoder; reference key names) are needed
+            fs = {k[len("first_stage_model."):]: v
+                  for k, v in list(_spec.vae_encoder_spec().items()) + list(_spec.vae_decoder_spec().items())}
+            self.first_stage_model = _ParamTree(fs).eval()
 
     def _init_clip_image_encoder(self):
         def build():
@@ -388,7 +389,8 @@ class SyncMultiviewDiffusion(_Base):
         if self._engine_version != ver:
             sd = {k: v for k, v in self.state_dict().items()
                   if k.startswith(("time_embed.", "spatial_volume.", "model.diffusion_model.",
-                                   "first_stage_model.decoder.", "first_stage_model.post_quant_conv."))}
+                                   "first_stage_model.decoder.", "first_stage_model.post_quant_conv.",
+                                   "first_stage_model.encoder.", "first_stage_model.quant_conv."))}
             self._engine.load_state_dict(sd)
             self._engine_version = ver
             self._bound_key = None
@@ -437,14 +439,18 @@ class SyncMultiviewDiffusion(_Base):
         return clip_, feats, x_in
 
     # -- frozen side models (outside the step loop; not rebuilt — attach the reference's own modules)
+    @torch.no_grad()
     def encode_first_stage(self, x, sample=True):
-        if not hasattr(self.first_stage_model, "encode"):
-            raise RuntimeError("no first-stage encoder: the reference AutoencoderKL could not be built "
-                               f"({self._first_stage_error}); attach it as model.first_stage_model")
-        with torch.no_grad():
-            posterior = self.first_stage_model.encode(x)
-            z = posterior.sample() if sample else posterior.mode()
-            return z.detach() * self.first_stage_scale_factor
+        """morphable_diffusion.py:460-466 on the CUDA library (md_vae_encode gives the posterior moments; the sample is
+        drawn here exactly as DiagonalGaussianDistribution.sample does: CPU torch.randn moved to the device)."""
+        eng = self._get_engine()
+        if not eng.has_vae_encoder():
+            raise RuntimeError("the loaded state dict carries no first_stage_model.encoder.* tensors")
+        mean, logvar = torch.chunk(eng.vae_encode_moments(x), 2, dim=1)
+        if not sample:
+            return mean * self.first_stage_scale_factor
+        std = torch.exp(0.5 * torch.clamp(logvar, -30.0, 20.0))
+        return (mean + std * torch.randn(mean.shape).to(mean.device)) * self.first_stage_scale_factor
 
     @torch.no_grad()
     def decode_first_stage(self, z):

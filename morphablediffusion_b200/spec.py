@@ -263,6 +263,43 @@ def vae_decoder_spec(prefix="first_stage_model.", ch=128, ch_mult=(1, 2, 4, 4), 
     return s
 
 
+def vae_encoder_spec(prefix="first_stage_model.", ch=128, ch_mult=(1, 2, 4, 4), num_res_blocks=2, z_channels=4,
+                     in_channels=3, embed_dim=4):
+    """AutoencoderKL.quant_conv + Encoder (ldm/models/autoencoder.py:302, ldm/modules/diffusionmodules/model.py:368-430),
+    double_z = True, attn_resolutions = []."""
+    s = OrderedDict()
+    _conv(s, prefix + "quant_conv", 2 * embed_dim, 2 * z_channels, 1)
+    e = prefix + "encoder."
+    _conv(s, e + "conv_in", ch, in_channels, 3)
+
+    def resnet(p, cin, cout):
+        _norm(s, p + "norm1", cin)
+        _conv(s, p + "conv1", cout, cin, 3)
+        _norm(s, p + "norm2", cout)
+        _conv(s, p + "conv2", cout, cout, 3)
+        if cin != cout:
+            _conv(s, p + "nin_shortcut", cout, cin, 1)
+
+    in_ch_mult = (1,) + tuple(ch_mult)
+    block_in = ch
+    for i_level in range(len(ch_mult)):
+        block_in = ch * in_ch_mult[i_level]
+        block_out = ch * ch_mult[i_level]
+        for i_block in range(num_res_blocks):
+            resnet(e + f"down.{i_level}.block.{i_block}.", block_in, block_out)
+            block_in = block_out
+        if i_level != len(ch_mult) - 1:
+            _conv(s, e + f"down.{i_level}.downsample.conv", block_in, block_in, 3)
+    resnet(e + "mid.block_1.", block_in, block_in)
+    _norm(s, e + "mid.attn_1.norm", block_in)
+    for n in ("q", "k", "v", "proj_out"):
+        _conv(s, e + "mid.attn_1." + n, block_in, block_in, 1)
+    resnet(e + "mid.block_2.", block_in, block_in)
+    _norm(s, e + "norm_out", block_in)
+    _conv(s, e + "conv_out", 2 * z_channels, block_in, 3)
+    return s
+
+
 def model_spec(cfg=None):
     """Every tensor of SyncMultiviewDiffusion that the per-step path reads (VAE / CLIP are outside the loop)."""
     s = OrderedDict()

@@ -48,6 +48,11 @@ def make_vae_state_dict(seed=6033, prefix="first_stage_model."):
     return {k: init_tensor(k, shp, seed) for k, shp in _spec.vae_decoder_spec(prefix).items()}
 
 
+def make_vae_encoder_state_dict(seed=6033, prefix="first_stage_model."):
+    """Seeded quant_conv + Encoder weights under the reference's state-dict keys."""
+    return {k: init_tensor(k, shp, seed) for k, shp in _spec.vae_encoder_spec(prefix).items()}
+
+
 def make_state_dict(cfg=None, seed=6033, keys=None):
     sd = {}
     for k, shp in _spec.model_spec(cfg).items():

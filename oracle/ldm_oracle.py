@@ -619,6 +619,34 @@ def voxelize(vertices):
     return coord, out_sh, bounds
 
 
+def vae_encode_moments(sd, x, prefix="first_stage_model.", ch_mult=(1, 2, 4, 4), num_res_blocks=2):
+    """AutoencoderKL.encode up to the posterior parameters (ldm/models/autoencoder.py:324-328: Encoder, quant_conv) with
+    Encoder.forward of ldm/modules/diffusionmodules/model.py:432-459 and Downsample (:70-78: pad (0,1,0,1), conv k3 s2 p0)
+    for attn_resolutions = [].  x: [B, 3, H, W] in [-1, 1] -> moments [B, 8, H/8, W/8] (mean | logvar)."""
+    e = prefix + "encoder."
+    h = conv(x, sd, e + "conv_in", padding=1)
+    for i_level in range(len(ch_mult)):
+        for i_block in range(num_res_blocks):
+            h = vae_resnet_block(h, sd, e + f"down.{i_level}.block.{i_block}.")
+        if i_level != len(ch_mult) - 1:
+            h = conv(F.pad(h, (0, 1, 0, 1), mode="constant", value=0), sd, e + f"down.{i_level}.downsample.conv", stride=2)
+    h = vae_resnet_block(h, sd, e + "mid.block_1.")
+    h = vae_attn_block(h, sd, e + "mid.attn_1.")
+    h = vae_resnet_block(h, sd, e + "mid.block_2.")
+    h = conv(F.silu(group_norm(h, sd, e + "norm_out", 32, 1e-6)), sd, e + "conv_out", padding=1)
+    return conv(h, sd, prefix + "quant_conv")
+
+
+def vae_posterior_sample(moments, noise=None, scale=0.18215):
+    """DiagonalGaussianDistribution (ldm/modules/distributions/distributions.py:24-44) + encode_first_stage
+    (morphable_diffusion.py:460-466): mean + exp(0.5 * clamp(logvar, -30, 20)) * noise, times the scale factor;
+    noise None = posterior.mode()."""
+    mean, logvar = torch.chunk(moments, 2, dim=1)
+    if noise is None:
+        return mean * scale
+    return (mean + torch.exp(0.5 * torch.clamp(logvar, -30.0, 20.0)) * noise) * scale
+
+
 def align_mica_vertices(verts):
     """generate_face.py:203-213, operation by operation (fp32 torch): *1.087, so3 rotation + translation, *2.5, axis swap.
     The rotation is pytorch3d's so3_exponential_map (Rodrigues' formula; pytorch3d is not installed here)."""

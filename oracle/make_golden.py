@@ -183,6 +183,28 @@ def vae_decode_golden(name, n_views, latent, seed=6033):
                         n_views=n_views, latent=latent, seed=seed, input_seed=seed + 77)
 
 
+def vae_encode_golden(name, n, size, seed=6033):
+    """AutoencoderKL.encode up to the moments (autoencoder.py:324-328) through the reference's own Encoder class
+    (model.py:368-459) and a Conv2d quant_conv (autoencoder.py:302), on seeded weights and a seeded image in [-1, 1]."""
+    import importlib
+    ref_import.reference()
+    m = importlib.import_module("ldm.modules.diffusionmodules.model")
+    dd = dict(double_z=True, z_channels=4, resolution=256, in_channels=3, out_ch=3, ch=128, ch_mult=[1, 2, 4, 4],
+              num_res_blocks=2, attn_resolutions=[], dropout=0.0)
+    enc = m.Encoder(**dd).eval()
+    sd = synth.make_vae_encoder_state_dict(seed)
+    enc.load_state_dict({k[len("first_stage_model.encoder."):]: v for k, v in sd.items() if ".encoder." in k})
+    qc = torch.nn.Conv2d(8, 8, 1)
+    qc.load_state_dict({"weight": sd["first_stage_model.quant_conv.weight"], "bias": sd["first_stage_model.quant_conv.bias"]})
+    x = torch.rand(n, 3, size, size, generator=torch.Generator().manual_seed(seed + 78)) * 2 - 1
+    t0 = time.time()
+    with torch.no_grad():
+        ref = qc(enc(x))
+        ours = O.vae_encode_moments(sd, x)
+    print(f"[{name}] oracle err/max", maxerr(ours, ref), f"{time.time() - t0:.0f}s", flush=True)
+    np.savez_compressed(GOLD / f"{name}.npz", moments=ref.numpy(), n=n, size=size, seed=seed, input_seed=seed + 78)
+
+
 def spec_dump():
     model, ns = ref_import.build_reference_model()
     skip = ("betas", "alphas", "alphas_cumprod", "sqrt_alphas_cumprod", "sqrt_one_minus_alphas_cumprod",
@@ -200,6 +222,13 @@ def spec_dump():
     dv["first_stage_model.post_quant_conv.bias"] = [4]
     (GOLD / "ref_vae_decoder_spec.json").write_text(json.dumps(dv, indent=0))
     print("[spec] first-stage decoder keys", len(dv))
+    enc = m.Encoder(double_z=True, z_channels=4, resolution=256, in_channels=3, out_ch=3, ch=128, ch_mult=[1, 2, 4, 4],
+                    num_res_blocks=2, attn_resolutions=[], dropout=0.0)
+    ev = {"first_stage_model.encoder." + k: list(v.shape) for k, v in enc.state_dict().items()}
+    ev["first_stage_model.quant_conv.weight"] = [8, 8, 1, 1]
+    ev["first_stage_model.quant_conv.bias"] = [8]
+    (GOLD / "ref_vae_encoder_spec.json").write_text(json.dumps(ev, indent=0))
+    print("[spec] first-stage encoder keys", len(ev))
 
 
 if __name__ == "__main__":
@@ -230,5 +259,9 @@ if __name__ == "__main__":
         vae_decode_golden("vae_n2_lat8", 2, 8)
     if want("vae_n2_lat32"):
         vae_decode_golden("vae_n2_lat32", 2, 32)
+    if want("vae_enc_n2_64"):         # §8f rank 2 (VAE half): encoder moments, small image (CPU test) and 256x256 (GPU test)
+        vae_encode_golden("vae_enc_n2_64", 2, 64)
+    if want("vae_enc_n2_256"):
+        vae_encode_golden("vae_enc_n2_256", 2, 256)
     if want("traj_n2_50"):            # a2: the 50-step sampler loop
         run_trajectory("traj_n2_50", 2, 50)

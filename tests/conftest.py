@@ -28,3 +28,9 @@ def state_dict():
 def vae_state_dict():
     from morphablediffusion_b200 import synth
     return synth.make_vae_state_dict()
+
+
+@pytest.fixture(scope="session")
+def vae_encoder_state_dict():
+    from morphablediffusion_b200 import synth
+    return synth.make_vae_encoder_state_dict()

@@ -62,6 +62,55 @@ def test_vae_decode_full_size_properties(vae_engine):
     assert rel(img[5:6], one) < 1e-2
 
 
+@pytest.mark.parametrize("name", ["vae_enc_n2_64", "vae_enc_n2_256"])
+def test_vae_encode_vs_reference_golden(state_dict, vae_encoder_state_dict, name):
+    """md_vae_encode (moments = quant_conv(Encoder(image)), SURVEY §8f rank 2, VAE half) vs the reference Encoder class."""
+    from morphablediffusion_b200.engine import Engine
+    gold = np.load(os.path.join(GOLD, name + ".npz"))
+    n, size = int(gold["n"]), int(gold["size"])
+    x = torch.rand(n, 3, size, size, generator=torch.Generator().manual_seed(int(gold["input_seed"]))) * 2 - 1
+    sd = dict(state_dict)
+    sd.update(vae_encoder_state_dict)
+    eng = Engine(max_views_per_call=16)
+    try:
+        eng.load_state_dict(sd)
+        assert eng.has_vae_encoder() and not eng.has_vae()
+        mom = eng.vae_encode_moments(x.cuda())
+        torch.cuda.synchronize()
+    finally:
+        eng.close()
+    ref = torch.from_numpy(gold["moments"])
+    assert mom.shape == ref.shape
+    assert rel(mom, ref) < BF16_REL and maxrel(mom, ref) < BF16_MAX, (rel(mom, ref), maxrel(mom, ref))
+
+
+def test_shell_encode_first_stage(state_dict, vae_encoder_state_dict):
+    """encode_first_stage through the drop-in class: mode() equals the library's mean * 0.18215 and the golden; sample()
+    follows torch's generator like DiagonalGaussianDistribution.sample."""
+    from morphablediffusion_b200.ldm_api import SyncMultiviewDiffusion
+    from oracle import ldm_oracle as O
+    gold = np.load(os.path.join(GOLD, "vae_enc_n2_256.npz"))
+    sd = dict(state_dict)
+    sd.update(vae_encoder_state_dict)
+    unet_config = {"target": "ldm.models.diffusion.attention.DepthWiseAttention",
+                   "params": dict(volume_dims=[64, 128, 256, 512], image_size=32, in_channels=8, out_channels=4,
+                                  model_channels=320, attention_resolutions=[4, 2, 1], num_res_blocks=2,
+                                  channel_mult=[1, 2, 4, 4], num_heads=8, use_spatial_transformer=True,
+                                  transformer_depth=1, context_dim=768, use_checkpoint=True, legacy=False)}
+    model = SyncMultiviewDiffusion(unet_config, None, projection="perspective", view_num=2, cfg_scale=2.0)
+    model.load_state_dict(sd, strict=False)
+    model = model.cuda().eval()
+    x = torch.rand(2, 3, 256, 256, generator=torch.Generator().manual_seed(int(gold["input_seed"]))) * 2 - 1
+    ref_mom = torch.from_numpy(gold["moments"])
+    z_mode = model.encode_first_stage(x.cuda(), sample=False)
+    assert rel(z_mode, O.vae_posterior_sample(ref_mom)) < BF16_REL
+    torch.manual_seed(11)
+    z = model.encode_first_stage(x.cuda(), sample=True)
+    torch.manual_seed(11)
+    noise = torch.randn(2, 4, 32, 32)
+    assert rel(z, O.vae_posterior_sample(ref_mom, noise)) < BF16_REL
+
+
 def test_vae_missing_weights_fail_loudly(state_dict):
     from morphablediffusion_b200 import _native as nat
     from morphablediffusion_b200.engine import Engine

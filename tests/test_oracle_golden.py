@@ -63,6 +63,20 @@ def test_vae_decode_matches_reference_decoder():
     assert rel(img, torch.from_numpy(gold["image"])) < TOL
 
 
+def test_vae_encode_matches_reference_encoder():
+    """AutoencoderKL.encode restatement (moments) vs the reference's own Encoder class on a 64x64 image."""
+    gold = np.load(os.path.join(GOLD, "vae_enc_n2_64.npz"))
+    n, size, seed = int(gold["n"]), int(gold["size"]), int(gold["seed"])
+    sd = synth.make_vae_encoder_state_dict(seed)
+    x = torch.rand(n, 3, size, size, generator=torch.Generator().manual_seed(int(gold["input_seed"]))) * 2 - 1
+    with torch.no_grad():
+        mom = O.vae_encode_moments(sd, x)
+    assert mom.shape == (n, 8, size // 8, size // 8)
+    assert rel(mom, torch.from_numpy(gold["moments"])) < TOL
+    z = O.vae_posterior_sample(mom)                      # mode() * 0.18215
+    assert torch.allclose(z, mom[:, :4] * 0.18215)
+
+
 def test_schedule_constants():
     s = O.make_schedule()
     assert s["timesteps"][0] == 1 and s["timesteps"][-1] == 981 and len(s["timesteps"]) == 50

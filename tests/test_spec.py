@@ -45,6 +45,8 @@ def test_shell_classes_are_state_dict_compatible():
     # first-stage decoder slots (held under the reference's key names; the reference class itself needs `taming`)
     vae = {k: list(v.shape) for k, v in sd.items() if k.startswith(("first_stage_model.decoder.", "first_stage_model.post_quant_conv."))}
     assert vae == json.load(open(os.path.join(GOLD, "ref_vae_decoder_spec.json")))
+    enc = {k: list(v.shape) for k, v in sd.items() if k.startswith(("first_stage_model.encoder.", "first_stage_model.quant_conv."))}
+    assert enc == json.load(open(os.path.join(GOLD, "ref_vae_encoder_spec.json")))
     assert SCHEDULE_BUFFERS <= set(sd)
     # the reference zero-initialises its output convolutions; so does the shell
     assert float(sd["model.diffusion_model.out.2.weight"].abs().sum()) == 0.0
