@@ -275,21 +275,17 @@ def _build_frozen(factory):
     return m, None
 
 
-class _ParamTree(nn.Module):
-    """Parameters registered under dotted state-dict keys (nested containers), nothing else: holds the first-stage
-    decoder tensors under the reference's names when the reference's AutoencoderKL class cannot be built (its import
-    needs `taming`), so reference checkpoints still load and the CUDA decoder finds its weights."""
+class _FirstStageParams(_ParamTree):
+    """Parameter slots of the first-stage model under the reference's key names, nothing else: used when the reference's
+    AutoencoderKL class cannot be built (its import needs `taming`), so that reference checkpoints still load and the
+    CUDA encoder / decoder find their weights."""
 
-    def __init__(self, spec=None):
+    def __init__(self, spec):
         super().__init__()
-        for key, shape in (spec or {}).items():
-            node = self
-            parts = key.split(".")
-            for name in parts[:-1]:
-                if not hasattr(node, name):
-                    node.add_module(name, _ParamTree())
-                node = getattr(node, name)
-            node.register_parameter(parts[-1], nn.Parameter(torch.zeros(tuple(shape)), requires_grad=False))
+        self._register_spec(spec, init=False)
+        for p in self.parameters():
+            p.requires_grad = False
+            p.data.zero_()
 
 
 def _batch_item(batch, bi):
@@ -365,7 +361,7 @@ class SyncMultiviewDiffusion(_Base):
             # only the parameter slots (encoder + quant_conv, post_quant_conv + decoder; reference key names) are needed
             fs = {k[len("first_stage_model."):]: v
                   for k, v in list(_spec.vae_encoder_spec().items()) + list(_spec.vae_decoder_spec().items())}
-            self.first_stage_model = _ParamTree(fs).eval()
+            self.first_stage_model = _FirstStageParams(fs).eval()
 
     def _init_clip_image_encoder(self):
         def build():
@@ -482,18 +478,57 @@ class SyncMultiviewDiffusion(_Base):
         img = self.decode_first_stage(x_sample.reshape(B * N, *x_sample.shape[2:]))
         x_sample = img.view(B, N, *img.shape[1:])
         if return_inter_results:
-            raise NotImplementedError("intermediate decoding is outside the hot path")
+            # morphable_diffusion.py:573-585: decode the recorded intermediate latents of every inter_view_interval-th view
+            xi = torch.stack(inter["x_inter"], 2)                                   # B,N,T,C,H,W
+            xi = xi[:, ::inter_view_interval]
+            Bn, Nn, Tn = xi.shape[:3]
+            dec = self.decode_first_stage(xi.reshape(Bn * Nn * Tn, *xi.shape[3:]))
+            return x_sample, dec.view(Bn, Nn, Tn, *dec.shape[1:])
         return x_sample
 
-    # -- Lightning hooks: signatures kept, training path not built
+    # -- logging / Lightning evaluation hooks (morphable_diffusion.py:588-624): no autograd involved, they run on the library
+    def log_image(self, x_sample, batch, step, output_dir):
+        """One row per sample: the input image followed by the N generated views, saved as <step>.jpg (:588-598)."""
+        from pathlib import Path
+
+        from .batch import images_to_uint8
+        u8 = images_to_uint8(x_sample).cpu().numpy()                               # B,N,H,W,3
+        inp = ((torch.clip(batch["input_image"], min=-1, max=1).cpu().numpy() * 0.5 + 0.5) * 255).astype(np.uint8)
+        rows = [np.concatenate([inp[bi]] + [u8[bi, ni] for ni in range(u8.shape[1])], 1) for bi in range(u8.shape[0])]
+        grid = np.concatenate(rows, 0)
+        path = Path(output_dir) / f"{step}.jpg"
+        try:
+            from PIL import Image
+            Image.fromarray(grid).save(str(path))
+        except ImportError:  # no image writer in this environment: keep the pixels
+            np.save(str(path.with_suffix(".npy")), grid)
+        return grid
+
+    @torch.no_grad()
+    def validation_step(self, batch, batch_idx):
+        from pathlib import Path
+        if batch_idx == 0 and getattr(self, "global_rank", 0) == 0:
+            self.eval()
+            step = getattr(self, "global_step", 0)
+            batch_ = {k: ({k_: v_[:self.output_num] for k_, v_ in v.items()} if isinstance(v, dict) else v[:self.output_num])
+                      for k, v in batch.items()}
+            x_sample = self.sample(self.sampler, batch_, self.cfg_scale, self.batch_view_num)
+            output_dir = Path(self.image_dir) / "images" / "val"
+            output_dir.mkdir(exist_ok=True, parents=True)
+            self.log_image(x_sample, batch_, step, output_dir=output_dir)
+
+    @torch.no_grad()
+    def test_step(self, batch, batch_idx):
+        from pathlib import Path
+        self.eval()
+        x_sample = self.sample(self.sampler, batch, self.cfg_scale, self.batch_view_num)
+        output_dir = Path(self.outdir)
+        output_dir.mkdir(exist_ok=True, parents=True)
+        self.log_image(x_sample, batch, batch_idx, output_dir=output_dir)
+
+    # -- training: signatures kept, not built (SURVEY.md §8f rank 3: autograd for the CUDA kernels)
     def training_step(self, batch):
         raise NotImplementedError("training path (autograd for the CUDA kernels) is not built yet")
-
-    def validation_step(self, batch, batch_idx):
-        raise NotImplementedError("training path is not built yet")
-
-    def test_step(self, batch, batch_idx):
-        raise NotImplementedError("training path is not built yet")
 
     def configure_optimizers(self):
         raise NotImplementedError("training path is not built yet")

@@ -111,6 +111,53 @@ def test_shell_encode_first_stage(state_dict, vae_encoder_state_dict):
     assert rel(z, O.vae_posterior_sample(ref_mom, noise)) < BF16_REL
 
 
+def test_model_sample_end_to_end(state_dict, vae_state_dict, vae_encoder_state_dict, tmp_path):
+    """SyncMultiviewDiffusion.sample (morphable_diffusion.py:567-587) through the drop-in classes: prepare (library VAE
+    encode; CLIP is the one attached module — a stand-in here), the DDIM loop, decode of all views; return_inter_results
+    and the validation / test hooks (:600-624), which only sample and write an image strip."""
+    from morphablediffusion_b200 import batch as B, synth
+    from morphablediffusion_b200.ldm_api import SyncDDIMSampler, SyncMultiviewDiffusion
+
+    class StubClip(torch.nn.Module):
+        def encode(self, image):
+            g = torch.Generator().manual_seed(3)
+            return torch.randn(image.shape[0], 1, 768, generator=g).to(image.device)
+
+    sd = dict(state_dict)
+    sd.update(vae_state_dict)
+    sd.update(vae_encoder_state_dict)
+    unet_config = {"target": "ldm.models.diffusion.attention.DepthWiseAttention",
+                   "params": dict(volume_dims=[64, 128, 256, 512], image_size=32, in_channels=8, out_channels=4,
+                                  model_channels=320, attention_resolutions=[4, 2, 1], num_res_blocks=2,
+                                  channel_mult=[1, 2, 4, 4], num_heads=8, use_spatial_transformer=True,
+                                  transformer_depth=1, context_dim=768, use_checkpoint=True, legacy=False)}
+    n = 4
+    model = SyncMultiviewDiffusion(unet_config, None, projection="perspective", view_num=n, cfg_scale=2.0, sample_steps=4,
+                                   batch_view_num=4, output_num=1)
+    model.load_state_dict(sd, strict=False)
+    model.clip_image_encoder = StubClip()
+    model = model.cuda().eval()
+    img = torch.rand(256, 256, 3, generator=torch.Generator().manual_seed(8)) * 2 - 1
+    data = B.build_batch(img, synth.head_mesh() * 0.37, n_views=n)
+    sampler = SyncDDIMSampler(model, 4, latent_size=32)
+    torch.manual_seed(5)
+    x = model.sample(sampler, data, 2.0, 4)
+    assert x.shape == (1, n, 3, 256, 256) and torch.isfinite(x).all()
+    torch.manual_seed(5)
+    x2, inter = model.sample(sampler, data, 2.0, 4, return_inter_results=True, inter_interval=2, inter_view_interval=2)
+    assert rel(x2, x) < 2e-2                                   # same torch seed -> same posterior sample, x_T, step seeds
+    assert inter.shape[:2] == (1, 2) and inter.shape[3:] == (3, 256, 256) and torch.isfinite(inter).all()
+    strip = B.image_strip(x)
+    assert strip.shape == (256, n * 256, 3)
+    model.image_dir, model.outdir = str(tmp_path / "log"), str(tmp_path / "test")
+    model.validation_step(data, 0)
+    model.test_step(data, 3)
+    assert any((tmp_path / "log" / "images" / "val").iterdir()) and any((tmp_path / "test").iterdir())
+    import pytest as _pt
+    with _pt.raises(NotImplementedError):
+        model.training_step(data)
+
+
 def test_vae_missing_weights_fail_loudly(state_dict):
     from morphablediffusion_b200 import _native as nat
     from morphablediffusion_b200.engine import Engine

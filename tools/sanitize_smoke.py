@@ -81,4 +81,49 @@ ln(67, 640)
 ln(33, 1280)
 depth(1, 2, 12, 64, 64)
 depth(1, 2, 6, 16, 512)
+
+
+def split_gemm(tail):
+    """uniform split-K (tile-starved) and the partial-wave split, through the red.add exchange"""
+    A = bf(torch.randn(6, 4, 4, 1280, device=dev))
+    taps = [(dx, dy, 0) for dy in (-1, 0, 1) for dx in (-1, 0, 1)]
+    Wt = bf(torch.randn(320, 9 * 1280, device=dev) / (9 * 1280) ** 0.5)
+    o = torch.zeros(96, 320, device=dev)
+    nat.conv_gemm(A, Wt, B=6, D=1, H=4, W=4, Cin=1280, N=320, taps=taps, out_f32=o, ksplit=5)
+    A2 = bf(torch.randn(85, 16, 16, 128, device=dev))
+    W2 = bf(torch.randn(320, 9 * 128, device=dev) / (9 * 128) ** 0.5)
+    o2 = torch.zeros(85 * 256, 320, device=dev)
+    nat.conv_gemm(A2, W2, B=85, D=1, H=16, W=16, Cin=128, N=320, taps=taps, out_f32=o2, BN=160, cta_pair=-1, tail_split=tail)
+    torch.cuda.synchronize()
+    print("split gemm", tail, float(o.abs().mean()), float(o2.abs().mean()))
+
+
+def vae_small():
+    from morphablediffusion_b200 import synth
+    from morphablediffusion_b200.engine import Engine
+    sd = dict(synth.make_state_dict())
+    sd.update(synth.make_vae_state_dict())
+    sd.update(synth.make_vae_encoder_state_dict())
+    eng = Engine(max_views_per_call=2)
+    eng.load_state_dict(sd)
+    img = eng.vae_decode(torch.randn(1, 4, 8, 8, device=dev))
+    mom = eng.vae_encode_moments(torch.rand(1, 3, 64, 64, device=dev) * 2 - 1)
+    torch.cuda.synchronize()
+    print("vae", float(img.abs().mean()), float(mom.abs().mean()))
+    eng.close()
+
+
+def batch_ops():
+    from morphablediffusion_b200 import batch
+    v = batch.align_vertices(torch.randn(777, 3, device=dev))
+    u8 = batch.images_to_uint8(torch.randn(1, 2, 3, 24, 40, device=dev))
+    torch.cuda.synchronize()
+    print("batch ops", float(v.abs().mean()), int(u8.sum()))
+
+
+split_gemm(1)
+split_gemm(-1)
+batch_ops()
+if "--vae" in sys.argv:
+    vae_small()
 print("sanitize smoke done")
