@@ -37,7 +37,7 @@ MD_API void md_reset_launch_count(void);
  */
 /* MD_ACT_GEGLU (GEGLU, ldm/modules/attention.py:42-44): Wt / bias rows are packed per tile of 256 rows = 128 value rows
  * followed by their 128 gate rows (N = 2*inner, a multiple of 256); the output [rows][N/2] is value * gelu(gate), bf16. */
-enum { MD_ACT_NONE = 0, MD_ACT_SILU = 1, MD_ACT_RELU = 2, MD_ACT_GEGLU = 3, MD_ACT_GELU = 4 };
+enum { MD_ACT_NONE = 0, MD_ACT_SILU = 1, MD_ACT_RELU = 2, MD_ACT_GEGLU = 3, MD_ACT_GELU = 4, MD_ACT_QUICKGELU = 5 };
 
 typedef struct md_conv_gemm_args {
   const void* A;      /* bf16 */
@@ -174,6 +174,12 @@ MD_API int md_has_vae(md_ctx* ctx);
  * Needs first_stage_model.encoder.* / quant_conv.* among the loaded weights (md_has_vae_encoder tells). */
 MD_API int md_vae_encode(md_ctx* ctx, const float* image, float* moments, int n, int latent_size, void* stream);
 MD_API int md_has_vae_encoder(md_ctx* ctx);
+/* The CLIP half of SyncMultiviewDiffusion.prepare (morphable_diffusion.py:487-488): FrozenCLIPImageEmbedder.encode
+ * (ldm/modules/encoders/modules.py:363-382) = bicubic resize to 224 (align_corners), CLIP normalisation, ViT-L/14 image
+ * tower, projection.  image [n][3][H][W] in [-1, 1] (device, fp32, NCHW) -> embed [n][768] (the caller adds the token axis).
+ * Needs clip_image_encoder.model.visual.* among the loaded weights (md_has_clip tells). */
+MD_API int md_clip_embed(md_ctx* ctx, const float* image, float* embed, int n, int H, int W, void* stream);
+MD_API int md_has_clip(md_ctx* ctx);
 MD_API int md_ddim_timestep(md_ctx* ctx, int index);  /* 1 .. 981 */
 /* SyncDDIMSampler(model, ddim_num_steps, "uniform", ddim_eta) (morphable_diffusion.py:649-672): rebuilds the DDIM
  * schedule (timesteps range(0,1000,1000/steps)+1, alphas, alphas_prev, sigmas) of the context.  Cheap; may be called

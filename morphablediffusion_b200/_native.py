@@ -86,7 +86,7 @@ def cur_stream():
     return torch.cuda.current_stream().cuda_stream
 
 
-ACT = {"none": 0, "silu": 1, "relu": 2, "geglu": 3, "gelu": 4}
+ACT = {"none": 0, "silu": 1, "relu": 2, "geglu": 3, "gelu": 4, "quickgelu": 5}
 
 
 def conv_gemm(A, Wt, *, B, D, H, W, Cin, N, taps, bias=None, rowvec=None, res_f32=None, res_bf16=None,
@@ -167,11 +167,13 @@ lib.md_vae_decode.argtypes = [_vp, _vp, _vp, C.c_int, C.c_int, _vp]
 lib.md_has_vae.argtypes = [_vp]
 lib.md_vae_encode.argtypes = [_vp, _vp, _vp, C.c_int, C.c_int, _vp]
 lib.md_has_vae_encoder.argtypes = [_vp]
+lib.md_clip_embed.argtypes = [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]
+lib.md_has_clip.argtypes = [_vp]
 lib.md_comm_unique_id.argtypes = [_vp]
 lib.md_comm_init.argtypes = [_vp, C.c_int, C.c_int, _vp]
 for _f in ("md_embed_time", "md_create", "md_load_weights", "md_bind_sample", "md_voxelize", "md_spatial_volume", "md_frustum_feats",
            "md_unet_forward", "md_denoise_step", "md_ddim_timestep", "md_set_ddim", "md_ddim_steps", "md_comm_unique_id", "md_comm_init",
-           "md_vae_decode", "md_has_vae", "md_vae_encode", "md_has_vae_encoder"):
+           "md_vae_decode", "md_has_vae", "md_vae_encode", "md_has_vae_encoder", "md_clip_embed", "md_has_clip"):
     getattr(lib, _f).restype = C.c_int
 
 lib.md_op_group_norm.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _vp, _vp, _vp, C.c_int, _vp, _vp]

@@ -140,6 +140,7 @@ __device__ __forceinline__ TileCoord decode_item(const ConvGemmParams& p, int it
 
 __device__ __forceinline__ float act_silu(float x) { return silu_fast(x); }
 __device__ __forceinline__ float act_gelu(float x) { return gelu_fast(x); }
+__device__ __forceinline__ float act_quickgelu(float x) { return x * rcp_approx(1.f + ex2_approx(-1.702f * 1.4426950408889634f * x)); }
 
 #ifndef MD_EPI_WARPS
 #define MD_EPI_WARPS 16
@@ -313,6 +314,8 @@ __device__ __forceinline__ void epilogue_tile(const ConvGemmParams& p, uint32_t 
           v4.x = fmaxf(v4.x, 0.f); v4.y = fmaxf(v4.y, 0.f); v4.z = fmaxf(v4.z, 0.f); v4.w = fmaxf(v4.w, 0.f);
         } else if (p.act == ACT_GELU) {
           v4.x = act_gelu(v4.x); v4.y = act_gelu(v4.y); v4.z = act_gelu(v4.z); v4.w = act_gelu(v4.w);
+        } else if (p.act == ACT_QUICKGELU) {
+          v4.x = act_quickgelu(v4.x); v4.y = act_quickgelu(v4.y); v4.z = act_quickgelu(v4.z); v4.w = act_quickgelu(v4.w);
         }
       }
       if (RES == 1) { v4.x += rs4[it].x; v4.y += rs4[it].y; v4.z += rs4[it].z; v4.w += rs4[it].w; }
@@ -421,6 +424,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const ConvGemmParams& p, const
           if (p.act == ACT_SILU) y = act_silu(y);
           else if (p.act == ACT_RELU) y = fmaxf(y, 0.f);
           else if (p.act == ACT_GELU) y = act_gelu(y);
+          else if (p.act == ACT_QUICKGELU) y = act_quickgelu(y);
         }
         if (RES == 1) y += (t == 0 ? r4[j].x : t == 1 ? r4[j].y : t == 2 ? r4[j].z : r4[j].w);
         o[4 * j + t] = y;

@@ -743,6 +743,109 @@ int launch_nchw_to_cl64(const float* x, void* out_bf16, int B, int C, size_t HW,
   return check_launch("nchw_to_cl64");
 }
 
+// ------------------------------------------------------------------------------------------------ CLIP image tower input
+// FrozenCLIPImageEmbedder.preprocess (ldm/modules/encoders/modules.py:363-371) fused with the patch extraction of conv1
+// (patch 14, stride 14): bicubic resize to 224 x 224 (torch upsample_bicubic2d, align_corners = True, A = -0.75, border
+// indices clamped), (x + 1) / 2, CLIP mean / std, written as the bf16 GEMM operand [B * 256 patches][640] with
+// k = c * 196 + ky * 14 + kx (the flattening of conv1.weight [1024][3][14][14]) and zeros for k >= 588.
+__device__ __forceinline__ float cubic1(float x) { return ((1.25f * x - 2.25f) * x) * x + 1.f; }                 // |x| <= 1, A = -0.75
+__device__ __forceinline__ float cubic2(float x) { return ((-0.75f * x + 3.75f) * x - 6.f) * x + 3.f; }         // 1 < |x| < 2
+__global__ void clip_patches_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int B, int H, int W) {
+  pdl_grid_sync();
+  const size_t total = static_cast<size_t>(B) * 256 * 640;
+  const float sy = static_cast<float>(H - 1) / 223.f, sx = static_cast<float>(W - 1) / 223.f;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int k = static_cast<int>(i % 640);
+    const size_t bp = i / 640;
+    float v = 0.f;
+    if (k < 588) {
+      const int patch = static_cast<int>(bp & 255);
+      const size_t b = bp >> 8;
+      const int c = k / 196, r = k - c * 196, ky = r / 14, kx = r - ky * 14;
+      const int oy = (patch >> 4) * 14 + ky, ox = (patch & 15) * 14 + kx;
+      const float fy = sy * oy, fx = sx * ox;
+      const int iy = static_cast<int>(floorf(fy)), ix = static_cast<int>(floorf(fx));
+      const float ty = fy - iy, tx = fx - ix;
+      const float wx[4] = {cubic2(tx + 1.f), cubic1(tx), cubic1(1.f - tx), cubic2(2.f - tx)};
+      const float wy[4] = {cubic2(ty + 1.f), cubic1(ty), cubic1(1.f - ty), cubic2(2.f - ty)};
+      const float* plane = img + (b * 3 + c) * static_cast<size_t>(H) * W;
+      float acc = 0.f;
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const int yy = min(max(iy - 1 + a, 0), H - 1);
+        float row = 0.f;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) row += plane[static_cast<size_t>(yy) * W + min(max(ix - 1 + e, 0), W - 1)] * wx[e];
+        acc += row * wy[a];
+      }
+      const float mean = c == 0 ? 0.48145466f : (c == 1 ? 0.4578275f : 0.40821073f);
+      const float sd = c == 0 ? 0.26862954f : (c == 1 ? 0.26130258f : 0.27577711f);
+      v = ((acc + 1.f) / 2.f - mean) / sd;
+    }
+    out[i] = __float2bfloat16(v);
+  }
+}
+
+int launch_clip_patches(const float* image, void* out_bf16, int B, int H, int W, cudaStream_t st) {
+  const size_t total = static_cast<size_t>(B) * 256 * 640;
+  const int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, static_cast<size_t>(num_sms()) * 16));
+  launch_pdl(clip_patches_kernel, dim3(blocks), dim3(256), 0, st, image, static_cast<__nv_bfloat16*>(out_bf16), B, H, W);
+  return check_launch("clip_patches");
+}
+
+// [class token | patch embeddings] + positional embedding, then ln_pre (clip/model.py VisionTransformer.forward): one warp
+// per token, C = 1024 (8 float4 per lane).  patches fp32 [B][ntok-1][C] -> x fp32 [B][ntok][C] (the residual stream).
+__global__ void clip_tokens_kernel(const float* __restrict__ patches, const float* __restrict__ class_emb,
+                                   const float* __restrict__ pos_emb, const float* __restrict__ g,
+                                   const float* __restrict__ bta, float* __restrict__ x, int B, int ntok, int C) {
+  pdl_grid_sync();
+  const int lane = threadIdx.x & 31;
+  const size_t row = (blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x) >> 5;
+  if (row >= static_cast<size_t>(B) * ntok) return;
+  const size_t b = row / ntok;
+  const int t = static_cast<int>(row - b * ntok);
+  const float* src = t == 0 ? class_emb : patches + (b * (ntok - 1) + (t - 1)) * C;
+  const float* pos = pos_emb + static_cast<size_t>(t) * C;
+  float4 v[8];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int c = (k * 32 + lane) * 4;
+    const float4 a = load4(src + c), p4 = load4(pos + c);
+    v[k] = make_float4(a.x + p4.x, a.y + p4.y, a.z + p4.z, a.w + p4.w);
+    s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffff, s, o);
+  const float mean = s / C;
+  float q = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float dx = v[k].x - mean, dy = v[k].y - mean, dz = v[k].z - mean, dw = v[k].w - mean;
+    q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffff, q, o);
+  const float rstd = rsqrtf(q / C + 1e-5f);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int c = (k * 32 + lane) * 4;
+    const float4 g4 = load4(g + c), b4 = load4(bta + c);
+    store4(x + row * C + c, make_float4((v[k].x - mean) * rstd * g4.x + b4.x, (v[k].y - mean) * rstd * g4.y + b4.y,
+                                        (v[k].z - mean) * rstd * g4.z + b4.z, (v[k].w - mean) * rstd * g4.w + b4.w));
+  }
+}
+
+int launch_clip_tokens(const float* patches, const float* class_emb, const float* pos_emb, const float* g, const float* b,
+                       float* x, int B, int ntok, int C, cudaStream_t st) {
+  if (C != 1024) return set_error("clip_tokens: width %d unsupported (ViT-L/14: 1024)", C);
+  const size_t rows = static_cast<size_t>(B) * ntok;
+  launch_pdl(clip_tokens_kernel, dim3(static_cast<unsigned>((rows * 32 + 255) / 256)), dim3(256), 0, st, patches, class_emb,
+             pos_emb, g, b, x, B, ntok, C);
+  return check_launch("clip_tokens");
+}
+
 // Row softmax fp32 -> bf16, one warp per row (n a multiple of 4): max, sum of exponentials, normalise; the row is read
 // three times, the second and third time out of L1/L2.
 __global__ void softmax_rows_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, size_t rows, int n) {

@@ -105,6 +105,18 @@ struct VaeEncW {
   GemmW conv_out;                  // quant_conv (1x1) folded into conv_out: 512 -> 8 moments
 };
 
+// CLIP ViT-L/14 image tower (FrozenCLIPImageEmbedder, ldm/modules/encoders/modules.py:343-382; OpenAI clip VisionTransformer)
+struct ClipLayerW { NormW ln1, ln2; GemmW qkv, out, fc, proj; };
+struct ClipW {
+  bool loaded = false;
+  int width = 1024, heads = 16, ntok = 257, out_dim = 768;
+  GemmW conv1;                     // patch embedding as a GEMM: [width][640] (K = 3*14*14 = 588 zero-padded)
+  const float* class_emb = nullptr; const float* pos_emb = nullptr;
+  NormW ln_pre, ln_post;
+  std::vector<ClipLayerW> layers;
+  GemmW proj;                      // proj^T: [out_dim][width]
+};
+
 struct FrBlockW {   // FrustumTVBlock / FrustumTVUpBlock
   int cin = 0, cout = 0, stride = 1; bool up = false;
   const float* t_w = nullptr; const float* t_b = nullptr; const float* v_w = nullptr; const float* v_b = nullptr;
@@ -145,6 +157,7 @@ struct Ctx {
   VolumeW vol;
   VaeW vae;
   VaeEncW vae_enc;
+  ClipW clip;
   bool weights_loaded = false;
   std::vector<void*> weight_allocs;
   Arena arena;
@@ -202,6 +215,9 @@ int unet_forward(Ctx& c, const float* x_in, const float* timesteps, const float*
 int vae_decode(Ctx& c, const float* x, float* image, int T, int S, cudaStream_t st);
 // AutoencoderKL.encode up to the moments: image fp32 NCHW [T][3][8S][8S] in [-1,1] -> moments fp32 NCHW [T][8][S][S]
 int vae_encode(Ctx& c, const float* image, float* moments, int T, int S, cudaStream_t st);
+
+// FrozenCLIPImageEmbedder.encode: image fp32 NCHW [n][3][H][W] in [-1,1] -> embedding fp32 [n][768]
+int clip_embed(Ctx& c, const float* image, float* out, int n, int H, int W, cudaStream_t st);
 
 // volume.cu
 int bind_sample(Ctx& c, const float* K, const float* RT, const float* v_embed, const float* vertices,

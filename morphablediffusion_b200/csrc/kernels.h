@@ -6,7 +6,7 @@
 
 namespace md {
 
-enum Act : int { ACT_NONE = 0, ACT_SILU = 1, ACT_RELU = 2, ACT_GEGLU = 3, ACT_GELU = 4 };
+enum Act : int { ACT_NONE = 0, ACT_SILU = 1, ACT_RELU = 2, ACT_GEGLU = 3, ACT_GELU = 4, ACT_QUICKGELU = 5 };  // QuickGELU: x * sigmoid(1.702 x) (CLIP)
 // GEGLU projections are packed per tile of kGegluTile weight rows: kGegluTile/2 value rows, then their kGegluTile/2 gate
 // rows, so one accumulator tile holds both halves (the widest tile: fewest re-reads of the activation rows from L2).
 constexpr int kGegluTile = 256;
@@ -45,6 +45,10 @@ int launch_pad_cast_bf16(const float* x, void* out, size_t rows, int C, int Cpad
 int launch_vae_input(const float* x, const float* pq, float in_scale, void* out_bf16, int B, int HW, cudaStream_t st);
 // NCHW fp32 [B][C][HW] (C <= 4) -> bf16 channels-last [B][HW][64], zero-padded (first-stage encoder input)
 int launch_nchw_to_cl64(const float* x, void* out_bf16, int B, int C, size_t HW, cudaStream_t st);
+// CLIP image tower: preprocess + patchify, token assembly + ln_pre
+int launch_clip_patches(const float* image, void* out_bf16, int B, int H, int W, cudaStream_t st);
+int launch_clip_tokens(const float* patches, const float* class_emb, const float* pos_emb, const float* g, const float* b,
+                       float* x, int B, int ntok, int C, cudaStream_t st);
 int launch_softmax_rows(const float* x, void* out_bf16, size_t rows, int n, cudaStream_t st);
 int launch_upsample2x(const float* x, void* out, int B, int H, int W, int C, cudaStream_t st);
 int launch_ncdhw_to_cl_bf16(const float* x, void* out, int B, int C, size_t S, cudaStream_t st);

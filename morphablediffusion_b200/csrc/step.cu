@@ -557,6 +557,21 @@ int md_vae_encode(md_ctx* ctx, const float* image, float* moments, int n, int la
   return 0;
 }
 
+int md_has_clip(md_ctx* ctx) { return ctx && ctx->c.clip.loaded ? 1 : 0; }
+
+int md_clip_embed(md_ctx* ctx, const float* image, float* embed, int n, int H, int W, void* stream) {
+  MD_CHECK(ensure_ready(ctx, false));
+  Ctx& c = ctx->c;
+  SplitScope split_scope(&c.split_main);
+  const int chunk = 16;
+  for (int i0 = 0; i0 < n; i0 += chunk) {
+    const int T = std::min(chunk, n - i0);
+    MD_CHECK(clip_embed(c, image + static_cast<size_t>(i0) * 3 * H * W, embed + static_cast<size_t>(i0) * c.clip.out_dim, T, H, W,
+                        static_cast<cudaStream_t>(stream)));
+  }
+  return 0;
+}
+
 int md_set_ddim(md_ctx* ctx, int ddim_steps, float ddim_eta) {
   if (!ctx) return set_error("null context");
   if (ddim_steps < 1 || ddim_steps > 1000) return set_error("md_set_ddim: ddim_steps=%d out of range 1..1000", ddim_steps);

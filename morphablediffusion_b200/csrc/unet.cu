@@ -592,4 +592,47 @@ int vae_encode(Ctx& c, const float* image, float* moments, int T, int S, cudaStr
   return 0;
 }
 
+// FrozenCLIPImageEmbedder.encode (ldm/modules/encoders/modules.py:363-382) = preprocess + clip encode_image (OpenAI clip
+// VisionTransformer.forward): bicubic resize / normalise / patchify (one kernel) -> patch-embedding GEMM -> class token +
+// positions + ln_pre -> 24 x {LayerNorm -> qkv GEMM -> attention (257 tokens, 16 heads of 64: mma.sync kernel) -> out_proj
+// GEMM adding into the fp32 residual stream -> LayerNorm -> c_fc GEMM with QuickGELU epilogue -> c_proj GEMM adding into
+// the stream} -> ln_post of the class tokens -> projection GEMM.
+int clip_embed(Ctx& c, const float* image, float* out, int n, int H, int W, cudaStream_t st) {
+  if (!c.clip.loaded) return set_error("clip_embed: no CLIP image-tower weights were loaded (clip_image_encoder.model.visual.*)");
+  if (n < 1 || H < 2 || W < 2) return set_error("clip_embed: bad shape n=%d H=%d W=%d", n, H, W);
+  const ClipW& q = c.clip;
+  const int C = q.width, S = q.ntok, heads = q.heads;
+  Arena& A = c.arena;
+  A.off = 0;
+  A.failed = false;
+  Fwd f{c, st, n, n, nullptr, nullptr};
+  const size_t rows = static_cast<size_t>(n) * S;
+  bf16* patches = A.get<bf16>(static_cast<size_t>(n) * (S - 1) * 640);
+  float* pe = A.get<float>(static_cast<size_t>(n) * (S - 1) * C);
+  float* x = A.get<float>(rows * C);
+  bf16* ln = A.get<bf16>(rows * C);
+  bf16* qkv = A.get<bf16>(rows * 3 * C);
+  bf16* att = A.get<bf16>(rows * C);
+  bf16* hid = A.get<bf16>(rows * 4 * C);
+  float* cls = A.get<float>(static_cast<size_t>(n) * C);
+  bf16* cls_b = A.get<bf16>(static_cast<size_t>(n) * C);
+  if (A.failed) return set_error("workspace exhausted (clip)");
+  MD_CHECK(launch_clip_patches(image, patches, n, H, W, st));
+  MD_CHECK(f.gemm(patches, n, S - 1, q.conv1, nullptr, pe, nullptr, false));
+  MD_CHECK(launch_clip_tokens(pe, q.class_emb, q.pos_emb, q.ln_pre.g, q.ln_pre.b, x, n, S, C, st));
+  for (const ClipLayerW& l : q.layers) {
+    MD_CHECK(launch_layer_norm(x, nullptr, 0, l.ln1.g, l.ln1.b, ln, rows, S, C, 1e-5f, st));
+    MD_CHECK(f.gemm(ln, n, S, l.qkv, nullptr, nullptr, qkv, false));
+    MD_CHECK(launch_self_attention(qkv, att, n, S, heads, C / heads, st));
+    MD_CHECK(f.gemm(att, n, S, l.out, x, x, nullptr, false));
+    MD_CHECK(launch_layer_norm(x, nullptr, 0, l.ln2.g, l.ln2.b, ln, rows, S, C, 1e-5f, st));
+    MD_CHECK(f.gemm(ln, n, S, l.fc, nullptr, nullptr, hid, false, ACT_QUICKGELU));
+    MD_CHECK(f.gemm(hid, n, S, l.proj, x, x, nullptr, false));
+  }
+  MD_CUDA(cudaMemcpy2DAsync(cls, sizeof(float) * C, x, sizeof(float) * S * C, sizeof(float) * C, n, cudaMemcpyDeviceToDevice, st));
+  MD_CHECK(launch_layer_norm(cls, nullptr, 0, q.ln_post.g, q.ln_post.b, cls_b, n, 1, C, 1e-5f, st));
+  MD_CHECK(f.gemm(cls_b, 1, n, q.proj, nullptr, out, nullptr, false));
+  return 0;
+}
+
 }  // namespace md

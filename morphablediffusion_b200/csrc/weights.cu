@@ -654,6 +654,49 @@ int load_all_weights(Ctx& c, const TensorMap& tm, cudaStream_t st) {
     }
     e.loaded = L.rc == 0;
   }
+  // ------------------------------------------------ CLIP image tower (optional, SURVEY §8f rank 2: the CLIP half of prepare())
+  c.clip = ClipW();
+  const std::string CV = "clip_image_encoder.model.visual.";
+  if (L.has(CV + "conv1.weight")) {
+    ClipW& q = c.clip;
+    const int Wd = q.width;
+    {  // conv1 [width][3][14][14] -> bf16 [width][640]: the torch flattening (c, ky, kx) is already the K order; pad 588 -> 640
+      const NamedTensor* t = L.find(CV + "conv1.weight", static_cast<size_t>(Wd) * 588);
+      q.conv1.N = Wd; q.conv1.K = 640; q.conv1.taps = 1;
+      q.conv1.w = L.dalloc<bf16>(static_cast<size_t>(Wd) * 640);
+      if (t && q.conv1.w) {
+        cudaMemsetAsync(q.conv1.w, 0, sizeof(bf16) * Wd * 640, st);
+        L.pack<bf16>(t->ptr, q.conv1.w, Wd, 1, 588, 588, 0, 1, Loader::iota(), 640, 0, 1);
+      }
+    }
+    q.class_emb = L.copy_f32(CV + "class_embedding", Wd);
+    q.pos_emb = L.copy_f32(CV + "positional_embedding", static_cast<size_t>(q.ntok) * Wd);
+    q.ln_pre = L.norm(CV + "ln_pre", Wd);
+    q.ln_post = L.norm(CV + "ln_post", Wd);
+    int n_layers = 0;
+    while (L.has(CV + "transformer.resblocks." + std::to_string(n_layers) + ".ln_1.weight")) ++n_layers;
+    q.layers.resize(n_layers);
+    for (int i = 0; i < n_layers; ++i) {
+      const std::string b = CV + "transformer.resblocks." + std::to_string(i) + ".";
+      ClipLayerW& l = q.layers[i];
+      l.ln1 = L.norm(b + "ln_1", Wd);
+      l.ln2 = L.norm(b + "ln_2", Wd);
+      l.qkv.N = 3 * Wd; l.qkv.K = Wd; l.qkv.taps = 1;
+      l.qkv.w = L.dalloc<bf16>(static_cast<size_t>(3) * Wd * Wd);
+      if (l.qkv.w) L.pack_conv_into(l.qkv.w, b + "attn.in_proj_weight", 3 * Wd, Wd, 1);
+      l.qkv.bias = L.copy_f32(b + "attn.in_proj_bias", 3 * Wd);
+      l.out = L.gemm(b + "attn.out_proj", Wd, Wd, 1, true);
+      l.fc = L.gemm(b + "mlp.c_fc", 4 * Wd, Wd, 1, true);
+      l.proj = L.gemm(b + "mlp.c_proj", Wd, 4 * Wd, 1, true);
+    }
+    {  // proj [width][out_dim] -> GEMM weight [out_dim][width] (transposed)
+      const NamedTensor* t = L.find(CV + "proj", static_cast<size_t>(Wd) * q.out_dim);
+      q.proj.N = q.out_dim; q.proj.K = Wd; q.proj.taps = 1;
+      q.proj.w = L.dalloc<bf16>(static_cast<size_t>(q.out_dim) * Wd);
+      if (t && q.proj.w) L.pack<bf16>(t->ptr, q.proj.w, q.out_dim, 1, Wd, 1, 0, q.out_dim, Loader::iota(), Wd, 0, 1);
+    }
+    q.loaded = L.rc == 0 && n_layers > 0;
+  }
   if (L.rc != 0) { free_weights(c); return L.rc; }
   MD_CUDA(cudaStreamSynchronize(st));
   c.weights_loaded = true;
@@ -666,6 +709,7 @@ void free_weights(Ctx& c) {
   c.weights_loaded = false;
   c.vae.loaded = false;
   c.vae_enc.loaded = false;
+  c.clip.loaded = false;
 }
 
 }  // namespace md

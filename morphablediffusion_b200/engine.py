@@ -173,6 +173,17 @@ class Engine:
         nat.check(nat.lib.md_vae_encode(self._h, x.data_ptr(), out.data_ptr(), n, H // 8, nat.cur_stream()), "md_vae_encode")
         return out
 
+    def has_clip(self):
+        return bool(nat.lib.md_has_clip(self._h))
+
+    def clip_embed(self, image):
+        """FrozenCLIPImageEmbedder.encode: image [n,3,H,W] in [-1,1] -> [n,1,768]."""
+        x = image.to(self.device, torch.float32).contiguous()
+        n, _, H, W = x.shape
+        out = torch.empty(n, 768, device=self.device)
+        nat.check(nat.lib.md_clip_embed(self._h, x.data_ptr(), out.data_ptr(), n, H, W, nat.cur_stream()), "md_clip_embed")
+        return out.unsqueeze(1)
+
     def set_ddim(self, ddim_steps, ddim_eta=1.0):
         """Schedule of SyncDDIMSampler(model, ddim_steps, ddim_eta=...) (morphable_diffusion.py:649-672)."""
         if (int(ddim_steps), float(ddim_eta)) != self.ddim:

@@ -275,10 +275,10 @@ def _build_frozen(factory):
     return m, None
 
 
-class _FirstStageParams(_ParamTree):
-    """Parameter slots of the first-stage model under the reference's key names, nothing else: used when the reference's
-    AutoencoderKL class cannot be built (its import needs `taming`), so that reference checkpoints still load and the
-    CUDA encoder / decoder find their weights."""
+class _FrozenParams(_ParamTree):
+    """Parameter slots of a frozen side model (first-stage VAE, CLIP image tower) under the reference's key names, nothing
+    else: used when the reference's own class cannot be built (AutoencoderKL needs `taming`, FrozenCLIPImageEmbedder the
+    `clip` package), so that reference checkpoints still load and the CUDA implementations find their weights."""
 
     def __init__(self, spec):
         super().__init__()
@@ -361,13 +361,18 @@ class SyncMultiviewDiffusion(_Base):
             # only the parameter slots (encoder + quant_conv, post_quant_conv + decoder; reference key names) are needed
             fs = {k[len("first_stage_model."):]: v
                   for k, v in list(_spec.vae_encoder_spec().items()) + list(_spec.vae_decoder_spec().items())}
-            self.first_stage_model = _FirstStageParams(fs).eval()
+            self.first_stage_model = _FrozenParams(fs).eval()
 
     def _init_clip_image_encoder(self):
         def build():
             mod = importlib.import_module("ldm.modules.encoders.modules")
             return mod.FrozenCLIPImageEmbedder(model=self.clip_image_encoder_path)
         self.clip_image_encoder, self._clip_error = _build_frozen(build)
+        if self.clip_image_encoder is None:
+            # the image tower runs in the CUDA library (md_clip_embed); without the reference class / the `clip` package
+            # only its parameter slots (clip key names under model.visual.*) are needed
+            cv = {k[len("clip_image_encoder."):]: v for k, v in _spec.clip_visual_spec().items()}
+            self.clip_image_encoder = _FrozenParams(cv).eval()
 
     @property
     def _device(self):
@@ -386,7 +391,8 @@ class SyncMultiviewDiffusion(_Base):
             sd = {k: v for k, v in self.state_dict().items()
                   if k.startswith(("time_embed.", "spatial_volume.", "model.diffusion_model.",
                                    "first_stage_model.decoder.", "first_stage_model.post_quant_conv.",
-                                   "first_stage_model.encoder.", "first_stage_model.quant_conv."))}
+                                   "first_stage_model.encoder.", "first_stage_model.quant_conv.",
+                                   "clip_image_encoder.model.visual."))}
             self._engine.load_state_dict(sd)
             self._engine_version = ver
             self._bound_key = None
@@ -456,16 +462,22 @@ class SyncMultiviewDiffusion(_Base):
             raise RuntimeError("the loaded state dict carries no first_stage_model.decoder.* tensors")
         return eng.vae_decode(z)
 
+    @torch.no_grad()
     def prepare(self, batch):
-        if self.clip_image_encoder is None:
-            raise RuntimeError("no clip_image_encoder: the reference FrozenCLIPImageEmbedder could not be built "
-                               f"({self._clip_error}); attach it as model.clip_image_encoder")
+        """morphable_diffusion.py:473-489 with both frozen side models on the CUDA library: VAE encode of the input image
+        (md_vae_encode) and its CLIP embedding (md_clip_embed).  The reference's 16 target encodes are discarded at
+        inference (x is unused by sample) and are skipped here."""
         image_input = batch["input_image"].permute(0, 3, 1, 2)
         x_input = self.encode_first_stage(image_input)
         input_info = {"image": image_input, "elevation": batch["input_elevation"][:, 0], "x": x_input}
-        with torch.no_grad():
+        eng = self._get_engine()
+        if eng.has_clip():
+            clip_embed = eng.clip_embed(image_input)
+        elif hasattr(self.clip_image_encoder, "encode"):      # a user-attached embedder
             clip_embed = self.clip_image_encoder.encode(image_input)
-        return None, clip_embed, input_info  # the reference's 16 target encodes are discarded at inference
+        else:
+            raise RuntimeError("the loaded state dict carries no clip_image_encoder.model.visual.* tensors")
+        return None, clip_embed, input_info
 
     def sample(self, sampler, batch, cfg_scale, batch_view_num, return_inter_results=False, inter_interval=50,
                inter_view_interval=2):

@@ -300,6 +300,29 @@ def vae_encoder_spec(prefix="first_stage_model.", ch=128, ch_mult=(1, 2, 4, 4), 
     return s
 
 
+def clip_visual_spec(prefix="clip_image_encoder.model.visual.", width=1024, layers=24, patch=14, image=224, out_dim=768):
+    """The image tower of OpenAI CLIP ViT-L/14 as `clip.load` builds it (clip/model.py VisionTransformer, pinned only as
+    the `clip` requirement of the reference): the tensors FrozenCLIPImageEmbedder.forward reads
+    (ldm/modules/encoders/modules.py:363-382 -> model.encode_image -> model.visual)."""
+    s = OrderedDict()
+    s[prefix + "class_embedding"] = (width,)
+    s[prefix + "positional_embedding"] = ((image // patch) ** 2 + 1, width)
+    s[prefix + "proj"] = (width, out_dim)
+    s[prefix + "conv1.weight"] = (width, 3, patch, patch)
+    _norm(s, prefix + "ln_pre", width)
+    for i in range(layers):
+        b = prefix + f"transformer.resblocks.{i}."
+        s[b + "attn.in_proj_weight"] = (3 * width, width)
+        s[b + "attn.in_proj_bias"] = (3 * width,)
+        _linear(s, b + "attn.out_proj", width, width)
+        _norm(s, b + "ln_1", width)
+        _linear(s, b + "mlp.c_fc", 4 * width, width)
+        _linear(s, b + "mlp.c_proj", width, 4 * width)
+        _norm(s, b + "ln_2", width)
+    _norm(s, prefix + "ln_post", width)
+    return s
+
+
 def model_spec(cfg=None):
     """Every tensor of SyncMultiviewDiffusion that the per-step path reads (VAE / CLIP are outside the loop)."""
     s = OrderedDict()

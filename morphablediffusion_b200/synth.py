@@ -53,6 +53,25 @@ def make_vae_encoder_state_dict(seed=6033, prefix="first_stage_model."):
     return {k: init_tensor(k, shp, seed) for k, shp in _spec.vae_encoder_spec(prefix).items()}
 
 
+def make_clip_state_dict(seed=6033, prefix="clip_image_encoder.model.visual."):
+    """Seeded CLIP ViT-L/14 image-tower weights under the `clip` package's key names."""
+    sd = {}
+    for k, shp in _spec.clip_visual_spec(prefix).items():
+        g = torch.Generator().manual_seed(_seed_for(k, seed))
+        leaf = k.rsplit(".", 1)[-1]
+        if leaf in ("class_embedding", "positional_embedding"):
+            sd[k] = torch.randn(shp, generator=g) * 0.3
+        elif leaf == "proj":
+            sd[k] = torch.randn(shp, generator=g) * shp[0] ** -0.5
+        elif leaf == "in_proj_bias":
+            sd[k] = 0.05 * torch.randn(shp, generator=g)
+        elif leaf == "in_proj_weight":
+            sd[k] = torch.randn(shp, generator=g) * shp[1] ** -0.5
+        else:
+            sd[k] = init_tensor(k, shp, seed)
+    return sd
+
+
 def make_state_dict(cfg=None, seed=6033, keys=None):
     sd = {}
     for k, shp in _spec.model_spec(cfg).items():

@@ -647,6 +647,60 @@ def vae_posterior_sample(moments, noise=None, scale=0.18215):
     return (mean + torch.exp(0.5 * torch.clamp(logvar, -30.0, 20.0)) * noise) * scale
 
 
+# ----------------------------------------------------------------------------- CLIP image embedder
+CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)
+CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
+
+
+def clip_preprocess(x):
+    """FrozenCLIPImageEmbedder.preprocess (ldm/modules/encoders/modules.py:363-371): kornia.geometry.resize(bicubic,
+    align_corners=True, antialias=False) is torch's F.interpolate with those arguments; then [-1,1] -> [0,1] and the CLIP
+    mean / std normalisation (kornia.enhance.normalize)."""
+    x = F.interpolate(x.float(), size=(224, 224), mode="bicubic", align_corners=True)
+    x = (x + 1.0) / 2.0
+    mean = torch.tensor(CLIP_MEAN, device=x.device).view(1, 3, 1, 1)
+    std = torch.tensor(CLIP_STD, device=x.device).view(1, 3, 1, 1)
+    return (x - mean) / std
+
+
+def clip_encode_image(sd, x, prefix="clip_image_encoder.model.visual.", heads=16):
+    """model.encode_image -> VisionTransformer.forward of the OpenAI `clip` package (clip/model.py; the package is a
+    requirement of the reference and not vendored: its published algorithm is restated here and pinned against the
+    independent HuggingFace implementation of the same checkpoint format in oracle/make_golden.py):
+    conv1 (patch 14, no bias) -> [class token | patches] + positional embedding -> ln_pre -> 24 x {x += attn(ln_1(x));
+    x += c_proj(QuickGELU(c_fc(ln_2(x))))} -> ln_post(class token) @ proj.   x: preprocessed [B,3,224,224] -> [B,768]."""
+    p = prefix
+    w = _w(sd, p + "conv1.weight")
+    h = F.conv2d(x, w, None, stride=w.shape[-1])                       # B,1024,16,16
+    B, C = h.shape[:2]
+    h = h.reshape(B, C, -1).permute(0, 2, 1)                           # B,256,1024
+    cls = _w(sd, p + "class_embedding").view(1, 1, C).expand(B, 1, C)
+    h = torch.cat([cls, h], dim=1) + _w(sd, p + "positional_embedding")
+    h = F.layer_norm(h, (C,), _w(sd, p + "ln_pre.weight"), _w(sd, p + "ln_pre.bias"), 1e-5)
+    n_layers = 1 + max(int(k[len(p) + len("transformer.resblocks."):].split(".")[0]) for k in sd
+                       if k.startswith(p + "transformer.resblocks."))
+    dh = C // heads
+    for i in range(n_layers):
+        b = p + f"transformer.resblocks.{i}."
+        y = F.layer_norm(h, (C,), _w(sd, b + "ln_1.weight"), _w(sd, b + "ln_1.bias"), 1e-5)
+        qkv = F.linear(y, _w(sd, b + "attn.in_proj_weight"), _w(sd, b + "attn.in_proj_bias"))
+        q, k, v = (t.view(B, -1, heads, dh).transpose(1, 2) for t in qkv.chunk(3, dim=-1))
+        a = torch.softmax(q @ k.transpose(-1, -2) * dh ** -0.5, dim=-1) @ v
+        a = a.transpose(1, 2).reshape(B, -1, C)
+        h = h + linear(a, sd, b + "attn.out_proj")
+        y = F.layer_norm(h, (C,), _w(sd, b + "ln_2.weight"), _w(sd, b + "ln_2.bias"), 1e-5)
+        y = linear(y, sd, b + "mlp.c_fc")
+        y = y * torch.sigmoid(1.702 * y)                               # QuickGELU
+        h = h + linear(y, sd, b + "mlp.c_proj")
+    cls_out = F.layer_norm(h[:, 0], (C,), _w(sd, p + "ln_post.weight"), _w(sd, p + "ln_post.bias"), 1e-5)
+    return cls_out @ _w(sd, p + "proj")
+
+
+def clip_image_embed(sd, image, prefix="clip_image_encoder.model.visual."):
+    """FrozenCLIPImageEmbedder.encode (modules.py:373-382): image [B,3,H,W] in [-1,1] -> [B,1,768]."""
+    return clip_encode_image(sd, clip_preprocess(image), prefix).unsqueeze(1)
+
+
 def align_mica_vertices(verts):
     """generate_face.py:203-213, operation by operation (fp32 torch): *1.087, so3 rotation + translation, *2.5, axis swap.
     The rotation is pytorch3d's so3_exponential_map (Rodrigues' formula; pytorch3d is not installed here)."""

@@ -205,6 +205,47 @@ def vae_encode_golden(name, n, size, seed=6033):
     np.savez_compressed(GOLD / f"{name}.npz", moments=ref.numpy(), n=n, size=size, seed=seed, input_seed=seed + 78)
 
 
+def clip_golden(name, n, size, seed=6033):
+    """CLIP image embedding of a seeded image on seeded ViT-L/14 weights.  The `clip` package is not installed, so the
+    independent implementation used to pin the restatement is HuggingFace transformers' CLIPVisionModelWithProjection
+    (same architecture, its own code): the seeded weights are renamed into its state dict and both must agree."""
+    from transformers import CLIPVisionConfig, CLIPVisionModelWithProjection
+    sd = synth.make_clip_state_dict(seed)
+    p = "clip_image_encoder.model.visual."
+    cfg = CLIPVisionConfig(hidden_size=1024, intermediate_size=4096, num_hidden_layers=24, num_attention_heads=16,
+                           image_size=224, patch_size=14, projection_dim=768, hidden_act="quick_gelu", layer_norm_eps=1e-5)
+    hf = CLIPVisionModelWithProjection(cfg).eval()
+    m = {"vision_model.embeddings.class_embedding": sd[p + "class_embedding"],
+         "vision_model.embeddings.patch_embedding.weight": sd[p + "conv1.weight"],
+         "vision_model.embeddings.position_embedding.weight": sd[p + "positional_embedding"],
+         "vision_model.pre_layrnorm.weight": sd[p + "ln_pre.weight"], "vision_model.pre_layrnorm.bias": sd[p + "ln_pre.bias"],
+         "vision_model.post_layernorm.weight": sd[p + "ln_post.weight"], "vision_model.post_layernorm.bias": sd[p + "ln_post.bias"],
+         "visual_projection.weight": sd[p + "proj"].t().contiguous()}
+    for i in range(24):
+        b, h = p + f"transformer.resblocks.{i}.", f"vision_model.encoder.layers.{i}."
+        wq, wk, wv = sd[b + "attn.in_proj_weight"].chunk(3, 0)
+        bq, bk, bv = sd[b + "attn.in_proj_bias"].chunk(3, 0)
+        m.update({h + "self_attn.q_proj.weight": wq, h + "self_attn.k_proj.weight": wk, h + "self_attn.v_proj.weight": wv,
+                  h + "self_attn.q_proj.bias": bq, h + "self_attn.k_proj.bias": bk, h + "self_attn.v_proj.bias": bv,
+                  h + "self_attn.out_proj.weight": sd[b + "attn.out_proj.weight"], h + "self_attn.out_proj.bias": sd[b + "attn.out_proj.bias"],
+                  h + "layer_norm1.weight": sd[b + "ln_1.weight"], h + "layer_norm1.bias": sd[b + "ln_1.bias"],
+                  h + "layer_norm2.weight": sd[b + "ln_2.weight"], h + "layer_norm2.bias": sd[b + "ln_2.bias"],
+                  h + "mlp.fc1.weight": sd[b + "mlp.c_fc.weight"], h + "mlp.fc1.bias": sd[b + "mlp.c_fc.bias"],
+                  h + "mlp.fc2.weight": sd[b + "mlp.c_proj.weight"], h + "mlp.fc2.bias": sd[b + "mlp.c_proj.bias"]})
+    missing, unexpected = hf.load_state_dict(m, strict=False)
+    missing = [k for k in missing if "position_ids" not in k]
+    assert not missing and not unexpected, (missing[:5], unexpected[:5])
+    x = torch.rand(n, 3, size, size, generator=torch.Generator().manual_seed(seed + 79)) * 2 - 1
+    t0 = time.time()
+    with torch.no_grad():
+        pre = O.clip_preprocess(x)
+        ref = hf(pixel_values=pre).image_embeds.unsqueeze(1)
+        ours = O.clip_image_embed(sd, x)
+    print(f"[{name}] oracle vs transformers err/max", maxerr(ours, ref), f"{time.time() - t0:.0f}s", flush=True)
+    np.savez_compressed(GOLD / f"{name}.npz", embed=ref.numpy(), pre_sub=pre[:, :, ::16, ::16].numpy(), n=n, size=size,
+                        seed=seed, input_seed=seed + 79)
+
+
 def spec_dump():
     model, ns = ref_import.build_reference_model()
     skip = ("betas", "alphas", "alphas_cumprod", "sqrt_alphas_cumprod", "sqrt_one_minus_alphas_cumprod",
@@ -263,5 +304,7 @@ if __name__ == "__main__":
         vae_encode_golden("vae_enc_n2_64", 2, 64)
     if want("vae_enc_n2_256"):
         vae_encode_golden("vae_enc_n2_256", 2, 256)
+    if want("clip_n2_256"):           # §8f rank 2 (CLIP half): image embedding of two 256x256 images
+        clip_golden("clip_n2_256", 2, 256)
     if want("traj_n2_50"):            # a2: the 50-step sampler loop
         run_trajectory("traj_n2_50", 2, 50)

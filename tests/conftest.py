@@ -34,3 +34,9 @@ def vae_state_dict():
 def vae_encoder_state_dict():
     from morphablediffusion_b200 import synth
     return synth.make_vae_encoder_state_dict()
+
+
+@pytest.fixture(scope="session")
+def clip_state_dict():
+    from morphablediffusion_b200 import synth
+    return synth.make_clip_state_dict()

@@ -111,21 +111,53 @@ def test_shell_encode_first_stage(state_dict, vae_encoder_state_dict):
     assert rel(z, O.vae_posterior_sample(ref_mom, noise)) < BF16_REL
 
 
-def test_model_sample_end_to_end(state_dict, vae_state_dict, vae_encoder_state_dict, tmp_path):
-    """SyncMultiviewDiffusion.sample (morphable_diffusion.py:567-587) through the drop-in classes: prepare (library VAE
-    encode; CLIP is the one attached module — a stand-in here), the DDIM loop, decode of all views; return_inter_results
-    and the validation / test hooks (:600-624), which only sample and write an image strip."""
+def test_clip_embed_vs_golden(state_dict, clip_state_dict):
+    """md_clip_embed (CLIP half) vs the golden embedding (HuggingFace CLIPVisionModelWithProjection on the
+    seeded ViT-L/14 weights, fp32): bicubic resize + normalisation + 24-layer image tower + projection."""
+    from morphablediffusion_b200.engine import Engine
+    gold = np.load(os.path.join(GOLD, "clip_n2_256.npz"))
+    n, size = int(gold["n"]), int(gold["size"])
+    x = torch.rand(n, 3, size, size, generator=torch.Generator().manual_seed(int(gold["input_seed"]))) * 2 - 1
+    sd = dict(state_dict)
+    sd.update(clip_state_dict)
+    eng = Engine(max_views_per_call=16)
+    try:
+        eng.load_state_dict(sd)
+        assert eng.has_clip()
+        emb = eng.clip_embed(x.cuda())
+        torch.cuda.synchronize()
+    finally:
+        eng.close()
+    ref = torch.from_numpy(gold["embed"])
+    assert emb.shape == ref.shape
+    assert rel(emb, ref) < BF16_REL, rel(emb, ref)
+
+
+def test_quickgelu_epilogue():
+    from morphablediffusion_b200 import _native as nat
+    torch.manual_seed(2)
+    A = torch.randn(300, 256, device="cuda").to(torch.bfloat16)
+    Wt = (torch.randn(512, 256, device="cuda") / 16).to(torch.bfloat16)
+    bias = torch.randn(512, device="cuda")
+    o = torch.zeros(300, 512, device="cuda")
+    ob = torch.zeros(300, 512, device="cuda", dtype=torch.bfloat16)
+    nat.conv_gemm(A, Wt, B=1, D=1, H=1, W=300, Cin=256, N=512, taps=[(0, 0, 0)], bias=bias, out_f32=o, act="quickgelu")
+    nat.conv_gemm(A, Wt, B=1, D=1, H=1, W=300, Cin=256, N=512, taps=[(0, 0, 0)], bias=bias, out_bf16=ob, act="quickgelu")
+    y = A.float() @ Wt.float().t() + bias
+    ref = y * torch.sigmoid(1.702 * y)
+    assert rel(o, ref) < 1e-5 and rel(ob, ref) < 5e-3
+
+
+def test_model_sample_end_to_end(state_dict, vae_state_dict, vae_encoder_state_dict, clip_state_dict, tmp_path):
+    """SyncMultiviewDiffusion.sample (morphable_diffusion.py:567-587) through the drop-in classes, every stage on the
+    library: prepare (VAE encode + CLIP embed), the DDIM loop, decode of all views; return_inter_results and the
+    validation / test hooks (:600-624), which only sample and write an image strip."""
     from morphablediffusion_b200 import batch as B, synth
     from morphablediffusion_b200.ldm_api import SyncDDIMSampler, SyncMultiviewDiffusion
-
-    class StubClip(torch.nn.Module):
-        def encode(self, image):
-            g = torch.Generator().manual_seed(3)
-            return torch.randn(image.shape[0], 1, 768, generator=g).to(image.device)
-
     sd = dict(state_dict)
     sd.update(vae_state_dict)
     sd.update(vae_encoder_state_dict)
+    sd.update(clip_state_dict)
     unet_config = {"target": "ldm.models.diffusion.attention.DepthWiseAttention",
                    "params": dict(volume_dims=[64, 128, 256, 512], image_size=32, in_channels=8, out_channels=4,
                                   model_channels=320, attention_resolutions=[4, 2, 1], num_res_blocks=2,
@@ -134,9 +166,12 @@ def test_model_sample_end_to_end(state_dict, vae_state_dict, vae_encoder_state_d
     n = 4
     model = SyncMultiviewDiffusion(unet_config, None, projection="perspective", view_num=n, cfg_scale=2.0, sample_steps=4,
                                    batch_view_num=4, output_num=1)
-    model.load_state_dict(sd, strict=False)
-    model.clip_image_encoder = StubClip()
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected and all(k.split(".")[0] in ("betas", "alphas", "alphas_cumprod", "sqrt_alphas_cumprod",
+                                                      "sqrt_one_minus_alphas_cumprod", "posterior_variance",
+                                                      "posterior_log_variance_clipped") for k in missing)
     model = model.cuda().eval()
+    assert model._get_engine().has_clip() and model._get_engine().has_vae() and model._get_engine().has_vae_encoder()
     img = torch.rand(256, 256, 3, generator=torch.Generator().manual_seed(8)) * 2 - 1
     data = B.build_batch(img, synth.head_mesh() * 0.37, n_views=n)
     sampler = SyncDDIMSampler(model, 4, latent_size=32)

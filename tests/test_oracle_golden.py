@@ -77,6 +77,21 @@ def test_vae_encode_matches_reference_encoder():
     assert torch.allclose(z, mom[:, :4] * 0.18215)
 
 
+def test_clip_image_embedder_matches_independent_implementation(clip_state_dict):
+    """FrozenCLIPImageEmbedder.encode restatement vs tests/golden/clip_n2_256.npz, which oracle/make_golden.py produced with
+    HuggingFace transformers' CLIPVisionModelWithProjection on the same seeded weights (the `clip` package itself is
+    absent); also the preprocess (bicubic align_corners resize + CLIP normalisation) on a sub-sampled grid."""
+    gold = np.load(os.path.join(GOLD, "clip_n2_256.npz"))
+    n, size = int(gold["n"]), int(gold["size"])
+    x = torch.rand(n, 3, size, size, generator=torch.Generator().manual_seed(int(gold["input_seed"]))) * 2 - 1
+    with torch.no_grad():
+        pre = O.clip_preprocess(x)
+        emb = O.clip_image_embed(clip_state_dict, x)
+    assert emb.shape == (n, 1, 768)
+    assert rel(pre[:, :, ::16, ::16], torch.from_numpy(gold["pre_sub"])) < 1e-6
+    assert rel(emb, torch.from_numpy(gold["embed"])) < TOL
+
+
 def test_schedule_constants():
     s = O.make_schedule()
     assert s["timesteps"][0] == 1 and s["timesteps"][-1] == 981 and len(s["timesteps"]) == 50

@@ -40,11 +40,14 @@ def test_shell_classes_are_state_dict_compatible():
     m = SyncMultiviewDiffusion(unet_config, None, projection="perspective", view_num=16, cfg_scale=2.0)
     sd = m.state_dict()
     ref = ref_spec()
-    mine = {k: list(v.shape) for k, v in sd.items() if k not in SCHEDULE_BUFFERS and not k.startswith("first_stage_model.")}
+    mine = {k: list(v.shape) for k, v in sd.items()
+            if k not in SCHEDULE_BUFFERS and not k.startswith(("first_stage_model.", "clip_image_encoder."))}
     assert mine == ref
     # first-stage decoder slots (held under the reference's key names; the reference class itself needs `taming`)
     vae = {k: list(v.shape) for k, v in sd.items() if k.startswith(("first_stage_model.decoder.", "first_stage_model.post_quant_conv."))}
     assert vae == json.load(open(os.path.join(GOLD, "ref_vae_decoder_spec.json")))
+    clipk = {k: tuple(v.shape) for k, v in sd.items() if k.startswith("clip_image_encoder.")}
+    assert clipk == {k: tuple(v) for k, v in spec.clip_visual_spec().items()} and len(clipk) == 296
     enc = {k: list(v.shape) for k, v in sd.items() if k.startswith(("first_stage_model.encoder.", "first_stage_model.quant_conv."))}
     assert enc == json.load(open(os.path.join(GOLD, "ref_vae_encoder_spec.json")))
     assert SCHEDULE_BUFFERS <= set(sd)
