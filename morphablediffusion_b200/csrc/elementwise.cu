@@ -444,8 +444,8 @@ int launch_group_norm(const GroupNormArgs& a, cudaStream_t st) {
 // One warp per RPW consecutive rows: all RPW rows are requested before the first reduction (one memory round trip per
 // warp instead of one per row) and gamma / beta stay in registers.  Optional per-sample vector added first (and written
 // back when write_back != 0): x <- x + addvec[b].  MAXV = ceil(C / 128) float4 per lane.
-template <int MAXV, int RPW>
-__global__ void layer_norm_kernel(float* __restrict__ x, const float* __restrict__ addvec, int addvec_ld,
+template <int MAXV, int RPW, typename TX>
+__global__ void layer_norm_kernel(TX* __restrict__ x, const float* __restrict__ addvec, int addvec_ld,
                                   const float* __restrict__ gamma, const float* __restrict__ beta,
                                   __nv_bfloat16* __restrict__ out, size_t nrows, int rows_per_sample, int C, float eps,
                                   int write_back) {
@@ -524,14 +524,14 @@ __global__ void layer_norm_kernel(float* __restrict__ x, const float* __restrict
   }
 }
 
-template <int MAXV, int RPW>
-static int layer_norm_impl(float* x, const float* addvec, int addvec_ld, const float* gamma, const float* beta,
+template <int MAXV, int RPW, typename TX>
+static int layer_norm_impl(TX* x, const float* addvec, int addvec_ld, const float* gamma, const float* beta,
                            void* out_bf16, size_t nrows, int rows_per_sample, int C, float eps, int write_back,
                            cudaStream_t st) {
   const int threads = 256;
   const size_t warps = (nrows + RPW - 1) / RPW;
   const size_t blocks = (warps * 32 + threads - 1) / threads;
-  launch_pdl(layer_norm_kernel<MAXV, RPW>, dim3(static_cast<unsigned>(blocks)), dim3(threads), 0, st, x, addvec, addvec_ld,
+  launch_pdl(layer_norm_kernel<MAXV, RPW, TX>, dim3(static_cast<unsigned>(blocks)), dim3(threads), 0, st, x, addvec, addvec_ld,
              gamma, beta, static_cast<__nv_bfloat16*>(out_bf16), nrows, rows_per_sample, C, eps, write_back);
   return check_launch("layer_norm");
 }
@@ -540,9 +540,19 @@ int launch_layer_norm(float* x, const float* addvec, int addvec_ld, const float*
                       void* out_bf16, size_t nrows, int rows_per_sample, int C, float eps, cudaStream_t st,
                       int write_back) {
   if (C % 4 || C > 1280) return set_error("layer_norm: unsupported C=%d", C);
-  if (C <= 384) return layer_norm_impl<3, 4>(x, addvec, addvec_ld, gamma, beta, out_bf16, nrows, rows_per_sample, C, eps, write_back, st);
-  if (C <= 640) return layer_norm_impl<5, 2>(x, addvec, addvec_ld, gamma, beta, out_bf16, nrows, rows_per_sample, C, eps, write_back, st);
-  return layer_norm_impl<10, 1>(x, addvec, addvec_ld, gamma, beta, out_bf16, nrows, rows_per_sample, C, eps, write_back, st);
+  if (C <= 384) return layer_norm_impl<3, 4, float>(x, addvec, addvec_ld, gamma, beta, out_bf16, nrows, rows_per_sample, C, eps, write_back, st);
+  if (C <= 640) return layer_norm_impl<5, 2, float>(x, addvec, addvec_ld, gamma, beta, out_bf16, nrows, rows_per_sample, C, eps, write_back, st);
+  return layer_norm_impl<10, 1, float>(x, addvec, addvec_ld, gamma, beta, out_bf16, nrows, rows_per_sample, C, eps, write_back, st);
+}
+
+// bf16 input rows (the transformer block's internal stream); the optional per-sample vector is never written back
+int launch_layer_norm_bf16(const void* x_bf16, const float* addvec, int addvec_ld, const float* gamma, const float* beta,
+                           void* out_bf16, size_t nrows, int rows_per_sample, int C, float eps, cudaStream_t st) {
+  if (C % 4 || C > 1280) return set_error("layer_norm: unsupported C=%d", C);
+  __nv_bfloat16* x = const_cast<__nv_bfloat16*>(static_cast<const __nv_bfloat16*>(x_bf16));
+  if (C <= 384) return layer_norm_impl<3, 4, __nv_bfloat16>(x, addvec, addvec_ld, gamma, beta, out_bf16, nrows, rows_per_sample, C, eps, 0, st);
+  if (C <= 640) return layer_norm_impl<5, 2, __nv_bfloat16>(x, addvec, addvec_ld, gamma, beta, out_bf16, nrows, rows_per_sample, C, eps, 0, st);
+  return layer_norm_impl<10, 1, __nv_bfloat16>(x, addvec, addvec_ld, gamma, beta, out_bf16, nrows, rows_per_sample, C, eps, 0, st);
 }
 
 // ------------------------------------------------------------------------------------------------ small linear

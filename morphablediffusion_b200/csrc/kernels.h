@@ -32,6 +32,8 @@ int launch_group_norm(const GroupNormArgs& a, cudaStream_t st);
 int launch_layer_norm(float* x, const float* addvec, int addvec_ld, const float* gamma, const float* beta,
                       void* out_bf16, size_t nrows, int rows_per_sample, int C, float eps, cudaStream_t st,
                       int write_back = 1);
+int launch_layer_norm_bf16(const void* x_bf16, const float* addvec, int addvec_ld, const float* gamma, const float* beta,
+                           void* out_bf16, size_t nrows, int rows_per_sample, int C, float eps, cudaStream_t st);
 int launch_small_linear(const float* x, int ldx, const float* W, const float* bias, float* out, int ldo, int B, int K,
                         int N, int act_in, int act_out, int accumulate, cudaStream_t st);
 int launch_timestep_embedding(const float* t, float* out, int B, int dim, cudaStream_t st);

@@ -6,6 +6,7 @@
 #include "engine.h"
 
 #include <math.h>
+#include <stdlib.h>
 
 namespace md {
 
@@ -69,13 +70,14 @@ struct Fwd {
   }
   // plain GEMM over rows = nb * rows_per_sample tokens
   int gemm(const bf16* a_in, int nb, size_t rows_per_sample, const GemmW& w, const float* res_f32, float* out_f32,
-           bf16* out_bf16, bool stats, int act = ACT_NONE, const float* rowvec = nullptr, int rowvec_ld = 0) {
+           bf16* out_bf16, bool stats, int act = ACT_NONE, const float* rowvec = nullptr, int rowvec_ld = 0,
+           const bf16* res_bf16 = nullptr) {
     md_conv_gemm_args a;
     memset(&a, 0, sizeof(a));
     a.A = a_in; a.B = nb; a.D = 1; a.H = 1; a.W = static_cast<int>(rows_per_sample); a.Cin = w.K; a.Wt = w.w; a.N = w.N;
     a.ntaps = 1;
     a.bias = w.bias; a.res_f32 = res_f32; a.out_f32 = out_f32; a.out_bf16 = out_bf16; a.act = act;
-    a.rowvec = rowvec; a.rowvec_ld = rowvec_ld;
+    a.rowvec = rowvec; a.rowvec_ld = rowvec_ld; a.res_bf16 = res_bf16;
     const void* key = out_f32 ? static_cast<const void*>(out_f32) : static_cast<const void*>(out_bf16);
     if (stats && rows_per_sample >= 32 && rows_per_sample % 32 == 0) {
       a.col_stats = new_stats(key, nb, w.N);
@@ -144,28 +146,37 @@ struct Fwd {
     const size_t S = static_cast<size_t>(H) * W;
     const size_t rows = static_cast<size_t>(B) * S;
     const size_t m = A().mark();
+    // The block's internal stream x (proj_in output, += attn1, += feed-forward) is bf16: every consumer normalises or
+    // rounds it to bf16 anyway, and at level 0 each fp32 pass over it moved 42 MB (the 320-wide linears of the block
+    // are bound by exactly that traffic).  MD_ST_FP32=1 keeps it in fp32 (A/B switch).
+    static const bool x_fp32 = getenv("MD_ST_FP32") != nullptr;
     bf16* a = A().get<bf16>(rows * C);
-    float* x = A().get<float>(rows * C);
+    float* x = x_fp32 ? A().get<float>(rows * C) : nullptr;
+    bf16* xh = x_fp32 ? nullptr : A().get<bf16>(rows * C);
     bf16* ln = A().get<bf16>(rows * C);
     bf16* qkv = A().get<bf16>(rows * 3 * C);
     bf16* att = A().get<bf16>(rows * C);
     bf16* ff = A().get<bf16>(rows * 4 * C);
     bf16* xb = A().get<bf16>(rows * C);
     if (A().failed) return set_error("workspace exhausted (spatial transformer)");
-    MD_CHECK(gn(x_in, C, false, nullptr, 0, B, static_cast<int>(S), 32, 1e-6f, s.norm, ACT_NONE, a, nullptr));
-    MD_CHECK(gemm(a, B, S, s.proj_in, nullptr, x, nullptr, false));
+    const int Si = static_cast<int>(S);
+    const float* v2 = v2_all + s.v2_off;
+    const int v2_ld = c.unet.v2_total;
+    MD_CHECK(gn(x_in, C, false, nullptr, 0, B, Si, 32, 1e-6f, s.norm, ACT_NONE, a, nullptr));
+    MD_CHECK(gemm(a, B, S, s.proj_in, nullptr, x, xh, false));
     // attn1 (self-attention)
-    MD_CHECK(launch_layer_norm(x, nullptr, 0, s.ln1.g, s.ln1.b, ln, rows, static_cast<int>(S), C, 1e-5f, st));
+    if (x_fp32) MD_CHECK(launch_layer_norm(x, nullptr, 0, s.ln1.g, s.ln1.b, ln, rows, Si, C, 1e-5f, st));
+    else MD_CHECK(launch_layer_norm_bf16(xh, nullptr, 0, s.ln1.g, s.ln1.b, ln, rows, Si, C, 1e-5f, st));
     MD_CHECK(gemm(ln, B, S, s.qkv, nullptr, nullptr, qkv, false));
-    MD_CHECK(launch_self_attention(qkv, att, B, static_cast<int>(S), s.heads, C / s.heads, st));
-    MD_CHECK(gemm(att, B, S, s.o1, x, x, nullptr, false));
+    MD_CHECK(launch_self_attention(qkv, att, B, Si, s.heads, C / s.heads, st));
+    MD_CHECK(gemm(att, B, S, s.o1, x, x, xh, false, ACT_NONE, nullptr, 0, xh));
     // attn2: one context token => softmax == 1 => attn2(x) = to_out(to_v(ctx)) for every query (precomputed per
     // forward in v2_all): x2 = x + v2[b].  norm3 sees x2 without writing it back; the feed-forward's output GEMM adds
     // the vector again as its per-sample epilogue vector: xb = ff2(geglu(ff1(norm3(x2)))) + v2[b] + x
-    MD_CHECK(launch_layer_norm(x, v2_all + s.v2_off, c.unet.v2_total, s.ln3.g, s.ln3.b, ln, rows, static_cast<int>(S), C,
-                               1e-5f, st, /*write_back=*/0));
+    if (x_fp32) MD_CHECK(launch_layer_norm(x, v2, v2_ld, s.ln3.g, s.ln3.b, ln, rows, Si, C, 1e-5f, st, /*write_back=*/0));
+    else MD_CHECK(launch_layer_norm_bf16(xh, v2, v2_ld, s.ln3.g, s.ln3.b, ln, rows, Si, C, 1e-5f, st));
     MD_CHECK(gemm(ln, B, S, s.ff1, nullptr, nullptr, ff, false, ACT_GEGLU));
-    MD_CHECK(gemm(ff, B, S, s.ff2, x, nullptr, xb, false, ACT_NONE, v2_all + s.v2_off, c.unet.v2_total));
+    MD_CHECK(gemm(ff, B, S, s.ff2, x, nullptr, xb, false, ACT_NONE, v2, v2_ld, xh));
     MD_CHECK(gemm(xb, B, S, s.proj_out, x_in, out, out_b, true));
     A().release(m);
     return 0;
