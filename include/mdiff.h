@@ -70,6 +70,15 @@ typedef struct md_conv_gemm_args {
                                width 160 or 256, no split-K, at least one full wave of pairs), -1 = never */
   int Wpitch;               /* row pitch of Wt in elements (a weight matrix that is a column slice of a wider one,
                                e.g. the keys inside a fused q|k activation); 0 -> ntaps*Cin; multiple of 8 */
+  /* GroupNorm tail (needs col_stats, out_bf16 and the plain output geometry): after the last tile the whole grid waits on
+     gn_barrier (an int that is zero on entry), then normalises + activates the rows it produced into gn_out (bf16
+     [rows][N]) with the statistics of this launch: GroupNorm(groups, eps, gamma, beta) + gn_act (MD_ACT_NONE/SILU/RELU) */
+  void* gn_out;
+  const float* gn_gamma;
+  const float* gn_beta;
+  int gn_groups, gn_act;
+  float gn_eps;
+  int* gn_barrier;
   int tail_split;           /* last partial wave of tiles split along K: 0 = library default (on; MD_HYBRID=0 switches it
                                off), 1 = on, -1 = off */
 } md_conv_gemm_args;

@@ -56,6 +56,8 @@ class ConvGemmArgs(C.Structure):
         ("in_stride", C.c_int * 3),
         ("cta_pair", C.c_int),
         ("Wpitch", C.c_int),
+        ("gn_out", C.c_void_p), ("gn_gamma", C.c_void_p), ("gn_beta", C.c_void_p),
+        ("gn_groups", C.c_int), ("gn_act", C.c_int), ("gn_eps", C.c_float), ("gn_barrier", C.c_void_p),
         ("tail_split", C.c_int),
     ]
 
@@ -91,7 +93,7 @@ ACT = {"none": 0, "silu": 1, "relu": 2, "geglu": 3, "gelu": 4, "quickgelu": 5}
 
 def conv_gemm(A, Wt, *, B, D, H, W, Cin, N, taps, bias=None, rowvec=None, res_f32=None, res_bf16=None,
               out_f32=None, out_bf16=None, act="none", Cpitch=0, out_dims=None, os_=None, op=None, ldo=0,
-              out_scale=1.0, BN=0, col_stats=None, in_stride=None, ksplit=0, cta_pair=0, tail_split=0, Wpitch=0):
+              out_scale=1.0, BN=0, col_stats=None, in_stride=None, ksplit=0, cta_pair=0, tail_split=0, Wpitch=0, gn=None):
     a = ConvGemmArgs()
     a.A = (A.data_ptr() if Cpitch else ptr(A)); a.B, a.D, a.H, a.W = B, D, H, W
     a.Cin, a.Cpitch = Cin, Cpitch
@@ -119,6 +121,10 @@ def conv_gemm(A, Wt, *, B, D, H, W, Cin, N, taps, bias=None, rowvec=None, res_f3
     a.cta_pair = cta_pair
     a.tail_split = tail_split
     a.Wpitch = Wpitch
+    if gn is not None:   # dict(out=bf16 tensor, gamma, beta, groups, eps, act, barrier=zeroed int32 tensor)
+        a.gn_out = ptr(gn["out"]); a.gn_gamma = ptr(gn["gamma"]); a.gn_beta = ptr(gn["beta"])
+        a.gn_groups = gn["groups"]; a.gn_eps = gn["eps"]; a.gn_act = ACT[gn.get("act", "none")]
+        a.gn_barrier = ptr(gn["barrier"])
     if in_stride:
         for j in range(3):
             a.in_stride[j] = in_stride[j]

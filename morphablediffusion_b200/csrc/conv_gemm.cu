@@ -125,6 +125,18 @@ int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
     return set_error("conv_gemm: output of %lld elements exceeds the 32-bit row offsets of the epilogue",
                      static_cast<long long>(a.B) * p.OD * p.OH * p.OW * p.ldo);
   if (a.act == ACT_GEGLU && !a.out_bf16) return set_error("conv_gemm: GEGLU epilogue writes bf16 only");
+  if (a.gn_out) {
+    const bool plain = p.osx == 1 && p.osy == 1 && p.osz == 1 && p.opx == 0 && p.opy == 0 && p.opz == 0 && p.OW == p.W &&
+                       p.OH == p.H && p.OD == p.D;
+    if (!a.col_stats || !a.out_bf16 || !a.gn_gamma || !a.gn_beta || !a.gn_barrier || !plain || a.gn_groups < 1 ||
+        a.N % a.gn_groups || a.N % 4 || a.N > 1280 || p.ldo % 4)
+      return set_error("conv_gemm: the GroupNorm tail needs col_stats, out_bf16, gamma / beta, a barrier counter, the "
+                       "plain output geometry and N <= 1280 divisible by the groups (N=%d groups=%d)", a.N, a.gn_groups);
+    p.gn_out = static_cast<__nv_bfloat16*>(a.gn_out);
+    p.gn_gamma = a.gn_gamma; p.gn_beta = a.gn_beta; p.gn_groups = a.gn_groups; p.gn_act = a.gn_act; p.gn_eps = a.gn_eps;
+    p.gn_bar = a.gn_barrier;
+    p.gn_rows = p.W * p.H * p.D;
+  }
 
   // ---- tile N and split-K selection: minimise  waves x (per-tile MMA time ~ BN, divided by the K split)  plus a
   // reduction overhead for split tiles; prefer the wider tile on ties (fewer re-reads of the activation tile)

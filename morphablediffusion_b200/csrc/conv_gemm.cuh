@@ -97,6 +97,14 @@ struct ConvGemmParams {
   int epi_tma;  // 1: the output leaves through TMA stores of the per-warp staging tile (no fused statistics, one output,
                 // plain output geometry); qorg = position of an epilogue warp's 32 rows inside the tile box, per lane quarter
   int16_t qorg[4][4];
+  // GroupNorm tail (optional, needs col_stats and a bf16 output): after its last tile every CTA waits on a grid-wide
+  // counter, then the whole grid normalises + activates the rows it just produced into gn_out (bf16 [rows][N]) with the
+  // statistics its own epilogues accumulated: the GroupNorm between two convolutions costs no launch of its own
+  __nv_bfloat16* gn_out;
+  const float* gn_gamma; const float* gn_beta;
+  int gn_groups, gn_act, gn_rows;   // gn_rows = output rows per sample
+  float gn_eps;
+  int* gn_bar;                      // grid barrier counter, zero on entry
   int dbg;      // development only (MD_GEMM_DBG): 1 = skip the epilogue work, 2 = skip the MMAs, 4 = skip the TMA loads;
                 // results are garbage, the timings isolate which pipeline stage bounds a shape
   int cg2;      // 1: CTA-pair kernel; a work item is an (M-tile pair, N tile) and this CTA owns M tile 2*pair + rank
@@ -654,6 +662,110 @@ __device__ __forceinline__ void epilogue_loop(const ConvGemmParams& p, const CUt
   if (p.epi_tma && lane == 0) tma_store_wait_all();  // the CTA's shared memory must outlive its bulk stores
 }
 
+// GroupNorm tail of a statistics-carrying launch (p.gn_out != nullptr), run by all threads of every CTA after the tile loop.
+// 1. grid barrier: the CTA's output stores and statistics atomics are fenced, thread 0 arrives on p.gn_bar and spins until
+//    every CTA of the (fully resident: grid <= SMs, one CTA per SM) grid has arrived.  Only launches of the UNet's main
+//    stream use the tail, so a CTA that is still waiting for an SM is at most delayed by side-stream kernels, which
+//    never wait on anything of ours.
+// 2. the rows are split evenly over the CTAs; per sample a CTA touches, it reduces the per-channel sums to group
+//    mean / rstd (fp32 sums, double only for E[x^2] - mean^2, as gn_apply_fused_kernel), builds scale / shift in shared
+//    memory and streams its rows: 8-byte loads of the bf16 pre-norm tensor, normalise, activation, 8-byte stores.
+struct GnTailArgs {
+  const __nv_bfloat16* out_bf16; __nv_bfloat16* gn_out; const float* col_stats; const float* gn_gamma; const float* gn_beta;
+  int* gn_bar; int N, B, ldo, stats_ld, gn_groups, gn_act, gn_rows; float gn_eps;
+};
+static __device__ __noinline__ void gn_tail(const GnTailArgs p, uint8_t* smem) {
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    atomicAdd(p.gn_bar, 1);
+    const unsigned target = gridDim.x;
+    const long long t0 = clock64();
+    while (ld_acquire_gpu_u32(p.gn_bar) < target) {
+      __nanosleep(32);
+      if (clock64() - t0 > (1LL << 33)) break;   // ~4 s: never hang the device on a scheduling assumption gone wrong
+    }
+  }
+  __syncthreads();
+  const int C = p.N;
+  const int CQ = C >> 2;
+  const int G = p.gn_groups, cpg = C / G;
+  const int nthreads = blockDim.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = nthreads >> 5;
+  float* chs = reinterpret_cast<float*>(smem);          // [C][2] per-channel (sum, sum of squares) -> (scale, shift)
+  float* gsm = chs + 2 * C;                             // [G][2] mean, rstd
+  const long long rps = p.gn_rows;
+  const long long rows_total = static_cast<long long>(p.B) * rps;
+  const long long rpc = (rows_total + gridDim.x - 1) / gridDim.x;
+  const long long r0 = static_cast<long long>(blockIdx.x) * rpc;
+  const long long r1 = min(rows_total, r0 + rpc);
+  if (r0 >= r1) return;
+  const int R = nthreads / CQ;                          // row phases (C <= 1280 -> CQ <= 320 <= threads)
+  const int cq = threadIdx.x % CQ, rsub = threadIdx.x / CQ;
+  const double inv_n = 1.0 / (static_cast<double>(rps) * cpg);
+  for (long long b = r0 / rps; b * rps < r1; ++b) {
+    const long long s0 = max(r0, b * rps), s1 = min(r1, (b + 1) * rps);
+    for (int ch = threadIdx.x; ch < C; ch += nthreads) {
+      const float2 sq = __ldcg(reinterpret_cast<const float2*>(p.col_stats + (b * p.stats_ld + ch) * 2));
+      chs[2 * ch] = sq.x; chs[2 * ch + 1] = sq.y;
+    }
+    __syncthreads();
+    for (int g = warp; g < G; g += nwarps) {
+      float a = 0.f, q = 0.f;
+      for (int ch = g * cpg + lane; ch < (g + 1) * cpg; ch += 32) { a += chs[2 * ch]; q += chs[2 * ch + 1]; }
+#pragma unroll
+      for (int o = 16; o; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffff, a, o);
+        q += __shfl_xor_sync(0xffffffff, q, o);
+      }
+      if (lane == 0) {
+        const double mean = static_cast<double>(a) * inv_n;
+        double var = static_cast<double>(q) * inv_n - mean * mean;
+        if (var < 0.0) var = 0.0;
+        gsm[2 * g] = static_cast<float>(mean);
+        gsm[2 * g + 1] = rsqrtf(static_cast<float>(var) + p.gn_eps);
+      }
+    }
+    __syncthreads();
+    for (int ch = threadIdx.x; ch < C; ch += nthreads) {
+      const int g = ch / cpg;
+      const float sc = __ldg(p.gn_gamma + ch) * gsm[2 * g + 1];
+      chs[2 * ch] = sc;
+      chs[2 * ch + 1] = __ldg(p.gn_beta + ch) - gsm[2 * g] * sc;
+    }
+    __syncthreads();
+    if (rsub < R) {
+      const float4 s01 = *reinterpret_cast<const float4*>(chs + 8 * cq);       // sc0 sh0 sc1 sh1
+      const float4 s23 = *reinterpret_cast<const float4*>(chs + 8 * cq + 4);   // sc2 sh2 sc3 sh3
+      const __nv_bfloat16* src = p.out_bf16 + cq * 4;
+      __nv_bfloat16* dst = p.gn_out + cq * 4;
+      const int act = p.gn_act;
+      auto one = [&](const uint2 u) {
+        const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&u.x);
+        const __nv_bfloat162 hi = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+        float y0 = __low2float(lo) * s01.x + s01.y, y1 = __high2float(lo) * s01.z + s01.w;
+        float y2 = __low2float(hi) * s23.x + s23.y, y3 = __high2float(hi) * s23.z + s23.w;
+        if (act == ACT_SILU) { y0 = act_silu(y0); y1 = act_silu(y1); y2 = act_silu(y2); y3 = act_silu(y3); }
+        else if (act == ACT_RELU) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); y2 = fmaxf(y2, 0.f); y3 = fmaxf(y3, 0.f); }
+        __nv_bfloat162 a = __floats2bfloat162_rn(y0, y1), c2 = __floats2bfloat162_rn(y2, y3);
+        uint2 o;
+        o.x = *reinterpret_cast<uint32_t*>(&a); o.y = *reinterpret_cast<uint32_t*>(&c2);
+        return o;
+      };
+      long long r = s0 + rsub;
+      for (; r + 3 * R < s1; r += 4 * R) {   // four rows in flight per thread
+        uint2 u[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) u[k] = __ldcg(reinterpret_cast<const uint2*>(src + (r + k * R) * p.ldo));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) *reinterpret_cast<uint2*>(dst + (r + k * R) * C) = one(u[k]);
+      }
+      for (; r < s1; r += R) *reinterpret_cast<uint2*>(dst + r * C) = one(__ldcg(reinterpret_cast<const uint2*>(src + r * p.ldo)));
+    }
+    __syncthreads();
+  }
+}
+
 // RES: 0 none / 1 fp32 / 2 bf16 residual; RV: per-sample additive vector; STATS: fused GroupNorm statistics; ACTV: 0 no
 // activation / 1 SiLU, ReLU or GELU (p.act) / 2 GEGLU.  One kernel per combination keeps every instance a few thousand instructions, so the
 // cold instruction fetches of these short launches stay small.
@@ -805,6 +917,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tmem_dealloc(tmem_base, kTmemCols);
     KPROF(12, lane == 0);
   }
+  if constexpr (STATS) {
+    if (p.gn_out) {
+      const GnTailArgs ga{p.out_bf16, p.gn_out, p.col_stats, p.gn_gamma, p.gn_beta, p.gn_bar, p.N, p.B, p.ldo, p.stats_ld,
+                          p.gn_groups, p.gn_act, p.gn_rows, p.gn_eps};
+      gn_tail(ga, smem);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ CTA-pair variant
@@ -949,6 +1068,13 @@ conv_gemm_cg2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc_cg2(tmem_base, kTmemCols);
+  }
+  if constexpr (STATS) {
+    if (p.gn_out) {
+      const GnTailArgs ga{p.out_bf16, p.gn_out, p.col_stats, p.gn_gamma, p.gn_beta, p.gn_bar, p.N, p.B, p.ldo, p.stats_ld,
+                          p.gn_groups, p.gn_act, p.gn_rows, p.gn_eps};
+      gn_tail(ga, smem);
+    }
   }
 }
 

@@ -62,6 +62,12 @@ __device__ __forceinline__ void red_add_v4_f32(float* addr, float a, float b, fl
                : "memory");
 }
 
+__device__ __forceinline__ unsigned ld_acquire_gpu_u32(const int* addr) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(addr) : "memory");
+  return v;
+}
+
 // ---------------------------------------------------------------- programmatic dependent launch
 // Every kernel of the library starts with this: wait until the predecessor grid's writes are visible, then allow the
 // successor grid to begin launching (its own prologue overlaps our execution; it waits here in turn).

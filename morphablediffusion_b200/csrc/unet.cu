@@ -40,6 +40,29 @@ struct Fwd {
     return it == stats_of.end() ? nullptr : it->second;
   }
 
+  // GroupNorm applied by the producing GEMM itself (conv_gemm's tail phase): norm parameters + destination
+  struct GnTail { const NormW* n; int groups; float eps; int act; bf16* out; };
+  static bool gn_tail_enabled() {
+    static const bool on = getenv("MD_GN_TAIL") == nullptr || atoi(getenv("MD_GN_TAIL")) != 0;
+    return on;
+  }
+  // one grid-barrier counter per launch, taken from the statistics pool (zeroed once per forward)
+  int* new_barrier() {
+    if (spool_off + 4 > spool_cap) return nullptr;
+    int* b = reinterpret_cast<int*>(spool + spool_off);
+    spool_off += 4;   // keeps the statistics slabs behind it 16-byte aligned
+    return b;
+  }
+  int attach_tail(md_conv_gemm_args& a, const GnTail* t) {
+    if (!t) return 0;
+    if (!a.col_stats || !a.out_bf16) return set_error("GroupNorm tail without statistics / bf16 output");
+    a.gn_out = t->out; a.gn_gamma = t->n->g; a.gn_beta = t->n->b; a.gn_groups = t->groups; a.gn_eps = t->eps;
+    a.gn_act = t->act;
+    a.gn_barrier = new_barrier();
+    if (!a.gn_barrier) return set_error("statistics pool exhausted");
+    return 0;
+  }
+
   static void taps2d(md_conv_gemm_args& a) {
     a.ntaps = 9;
     for (int ky = 0; ky < 3; ++ky)
@@ -51,7 +74,8 @@ struct Fwd {
   // conv3x3 (pad 1) or 1x1 on a bf16 NHWC tensor of `nb` samples; `stats` = accumulate GroupNorm statistics of the
   // result (only possible when a warp's 32 output rows stay inside one sample)
   int conv(const bf16* a_in, int nb, int H, int W, const GemmW& w, const float* rowvec, int rowvec_ld,
-           const float* res_f32, float* out_f32, bf16* out_bf16, bool stats, int act = ACT_NONE) {
+           const float* res_f32, float* out_f32, bf16* out_bf16, bool stats, int act = ACT_NONE,
+           const GnTail* tail = nullptr) {
     md_conv_gemm_args a;
     memset(&a, 0, sizeof(a));
     a.A = a_in; a.B = nb; a.D = 1; a.H = H; a.W = W; a.Cin = w.K; a.Wt = w.w; a.N = w.N;
@@ -66,12 +90,15 @@ struct Fwd {
     } else {
       stats_of.erase(key);  // the arena recycles addresses: statistics of an earlier tensor must not outlive it
     }
+    MD_CHECK(attach_tail(a, tail));
     return launch_conv_gemm(a, st);
   }
+  // the GroupNorm of a GEMM's own output can ride on the producing launch when that launch carries statistics
+  static bool can_tail(int rows_per_sample) { return gn_tail_enabled() && rows_per_sample >= 32 && rows_per_sample % 32 == 0; }
   // plain GEMM over rows = nb * rows_per_sample tokens
   int gemm(const bf16* a_in, int nb, size_t rows_per_sample, const GemmW& w, const float* res_f32, float* out_f32,
            bf16* out_bf16, bool stats, int act = ACT_NONE, const float* rowvec = nullptr, int rowvec_ld = 0,
-           const bf16* res_bf16 = nullptr) {
+           const bf16* res_bf16 = nullptr, const GnTail* tail = nullptr) {
     md_conv_gemm_args a;
     memset(&a, 0, sizeof(a));
     a.A = a_in; a.B = nb; a.D = 1; a.H = 1; a.W = static_cast<int>(rows_per_sample); a.Cin = w.K; a.Wt = w.w; a.N = w.N;
@@ -85,6 +112,7 @@ struct Fwd {
     } else {
       stats_of.erase(key);
     }
+    MD_CHECK(attach_tail(a, tail));
     return launch_conv_gemm(a, st);
   }
 
@@ -126,8 +154,13 @@ struct Fwd {
     MD_CHECK(gn(x0, C0, false, x1, C1, B, H * W, 32, res_eps, r.n1, ACT_SILU, a1, raw));
     // per-sample time-embedding vector (UNet ResBlock); the first-stage ResnetBlock has none (temb is None)
     const float* rv = emb_all ? emb_all + r.emb_off : nullptr;
-    MD_CHECK(conv(a1, B, H, W, r.c1, rv, rv ? c.unet.emb_total : 0, nullptr, nullptr, h1, true));
-    MD_CHECK(gn(h1, r.cout, true, nullptr, 0, B, H * W, 32, res_eps, r.n2, ACT_SILU, a2, nullptr));
+    if (can_tail(H * W)) {   // GroupNorm + SiLU between the two convolutions rides on conv1's launch
+      const GnTail t{&r.n2, 32, res_eps, ACT_SILU, a2};
+      MD_CHECK(conv(a1, B, H, W, r.c1, rv, rv ? c.unet.emb_total : 0, nullptr, nullptr, h1, true, ACT_NONE, &t));
+    } else {
+      MD_CHECK(conv(a1, B, H, W, r.c1, rv, rv ? c.unet.emb_total : 0, nullptr, nullptr, h1, true));
+      MD_CHECK(gn(h1, r.cout, true, nullptr, 0, B, H * W, 32, res_eps, r.n2, ACT_SILU, a2, nullptr));
+    }
     const float* resid = x0;
     if (r.has_skip) {
       MD_CHECK(conv(raw, B, H, W, r.skip, nullptr, 0, nullptr, skip, nullptr, false));
@@ -202,8 +235,14 @@ struct Fwd {
     bf16* a2 = A().get<bf16>(rows * d.inner);
     if (A().failed) return set_error("workspace exhausted (depth transformer)");
     if (!x_in_b) MD_CHECK(launch_cast_bf16(x_in, xb, rows * d.dim, st));
-    MD_CHECK(gemm(x_in_b ? x_in_b : xb, B, S, d.proj_in, nullptr, nullptr, y, true));
-    MD_CHECK(gn(y, d.inner, true, nullptr, 0, B, static_cast<int>(S), 8, 1e-5f, d.gn_in, ACT_SILU, xq, nullptr));
+    const bool tail = can_tail(static_cast<int>(S));
+    if (tail) {
+      const GnTail t{&d.gn_in, 8, 1e-5f, ACT_SILU, xq};
+      MD_CHECK(gemm(x_in_b ? x_in_b : xb, B, S, d.proj_in, nullptr, nullptr, y, true, ACT_NONE, nullptr, 0, nullptr, &t));
+    } else {
+      MD_CHECK(gemm(x_in_b ? x_in_b : xb, B, S, d.proj_in, nullptr, nullptr, y, true));
+      MD_CHECK(gn(y, d.inner, true, nullptr, 0, B, static_cast<int>(S), 8, 1e-5f, d.gn_in, ACT_SILU, xq, nullptr));
+    }
     // queries mapped into context space (only the samples that own a volume)
     MD_CHECK(gemm(xq, n_ctx, S, d.wqk, nullptr, nullptr, qp, false));
     // context branch: proj_context conv -> GroupNorm statistics; the normalisation + ReLU is applied on read
@@ -212,10 +251,16 @@ struct Fwd {
     MD_CHECK(gn(c1, d.ctx, true, nullptr, 0, n_ctx, static_cast<int>(S * D), 8, 1e-5f, d.gn_ctx, ACT_RELU, nullptr, nullptr,
                 &ss_ctx));
     MD_CHECK(launch_depth_attention(qp, c1, ss_ctx, d.gn_ctx.b, cbar, n_ctx, B, D, static_cast<int>(S), d.ctx, st));
-    MD_CHECK(gemm(cbar, B, S, d.wov, nullptr, nullptr, y2, true));
-    MD_CHECK(gn(y2, d.inner, true, nullptr, 0, B, static_cast<int>(S), 8, 1e-5f, d.gn_o1, ACT_RELU, a1, nullptr));
-    MD_CHECK(conv(a1, B, H, W, d.conv1, nullptr, 0, nullptr, nullptr, y3, true));
-    MD_CHECK(gn(y3, d.inner, true, nullptr, 0, B, static_cast<int>(S), 8, 1e-5f, d.gn_o2, ACT_RELU, a2, nullptr));
+    if (tail) {
+      const GnTail t1{&d.gn_o1, 8, 1e-5f, ACT_RELU, a1}, t2{&d.gn_o2, 8, 1e-5f, ACT_RELU, a2};
+      MD_CHECK(gemm(cbar, B, S, d.wov, nullptr, nullptr, y2, true, ACT_NONE, nullptr, 0, nullptr, &t1));
+      MD_CHECK(conv(a1, B, H, W, d.conv1, nullptr, 0, nullptr, nullptr, y3, true, ACT_NONE, &t2));
+    } else {
+      MD_CHECK(gemm(cbar, B, S, d.wov, nullptr, nullptr, y2, true));
+      MD_CHECK(gn(y2, d.inner, true, nullptr, 0, B, static_cast<int>(S), 8, 1e-5f, d.gn_o1, ACT_RELU, a1, nullptr));
+      MD_CHECK(conv(a1, B, H, W, d.conv1, nullptr, 0, nullptr, nullptr, y3, true));
+      MD_CHECK(gn(y3, d.inner, true, nullptr, 0, B, static_cast<int>(S), 8, 1e-5f, d.gn_o2, ACT_RELU, a2, nullptr));
+    }
     MD_CHECK(conv(a2, B, H, W, d.conv2, nullptr, 0, x_in, out, nullptr, true));
     A().release(m);
     return 0;

@@ -322,6 +322,45 @@ def test_conv_gemm_tail_split(nat, case):
     assert rel(outs[1], outs[0]) < 1e-6 and rel(outs[2], outs[0]) < (4e-3 if o.dtype == torch.bfloat16 else 1e-6)
 
 
+@pytest.mark.parametrize("case", ["conv_l0", "linear_g8_relu", "pair"])
+def test_conv_gemm_group_norm_tail(nat, case):
+    """GroupNorm (+ activation) applied by the producing GEMM's own launch: after its last tile the grid meets on a
+    barrier counter and normalises the rows it wrote with the statistics its epilogues accumulated.  Against torch
+    group_norm of the (bf16-rounded) GEMM output; repeated launches need a fresh (zero) barrier counter each."""
+    torch.manual_seed(41)
+    taps9 = [(dx, dy, 0) for dy in (-1, 0, 1) for dx in (-1, 0, 1)]
+    if case == "conv_l0":
+        Bn, H, W, Cin, N, G, act, taps, kw = 6, 32, 32, 64, 320, 32, "silu", taps9, dict(cta_pair=-1)
+    elif case == "linear_g8_relu":
+        Bn, H, W, Cin, N, G, act, taps, kw = 5, 1, 256, 128, 64, 8, "relu", [(0, 0, 0)], dict(cta_pair=-1)
+    else:
+        Bn, H, W, Cin, N, G, act, taps, kw = 32, 32, 32, 192, 320, 32, "silu", taps9, dict(cta_pair=1, BN=160)
+    K = Cin * len(taps)
+    M = Bn * H * W
+    A = bf(torch.randn(Bn, H, W, Cin, device="cuda"))
+    Wt = bf(torch.randn(N, K, device="cuda") / K ** 0.5)
+    bias, rv = torch.randn(N, device="cuda"), torch.randn(Bn, N, device="cuda")
+    gamma, beta = 1 + 0.1 * torch.randn(N, device="cuda"), 0.1 * torch.randn(N, device="cuda")
+    if len(taps) == 9:
+        w4 = Wt.view(N, 3, 3, Cin).permute(0, 3, 1, 2).float()
+        y = F.conv2d(A.permute(0, 3, 1, 2).float(), w4, bias, padding=1).permute(0, 2, 3, 1).reshape(M, N)
+    else:
+        y = A.view(M, K).float() @ Wt.float().t() + bias
+    y = y + rv.repeat_interleave(H * W, 0)
+    ref = F.group_norm(y.view(Bn, H * W, N).permute(0, 2, 1), G, gamma, beta, 1e-5)
+    ref = (F.silu(ref) if act == "silu" else F.relu(ref)).permute(0, 2, 1).reshape(M, N)
+    for _ in range(2):
+        o = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16)
+        g_out = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16)
+        st = torch.zeros(Bn, N, 2, device="cuda")
+        bar = torch.zeros(1, device="cuda", dtype=torch.int32)
+        nat.conv_gemm(A, Wt, B=Bn, D=1, H=H, W=W, Cin=Cin, N=N, taps=taps, bias=bias, rowvec=rv, out_bf16=o, col_stats=st,
+                      gn=dict(out=g_out, gamma=gamma, beta=beta, groups=G, eps=1e-5, act=act, barrier=bar), **kw)
+        torch.cuda.synchronize()
+        assert rel(o, y) < 5e-3
+        assert rel(g_out, ref) < 1e-2, (case, rel(g_out, ref))
+
+
 # ----------------------------------------------------------------------------- norm / attention kernels
 @pytest.mark.parametrize("B,rows,C,G,act,bf16_in", [(3, 1024, 320, 32, 1, False), (2, 256, 1920, 32, 1, False),
                                                     (2, 16, 1280, 32, 0, False), (2, 6144, 128, 8, 1, True),
