@@ -144,7 +144,12 @@ int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
   auto auto_split = [&](long long tiles) {
     if (a.ksplit != 0 || a.act == ACT_GEGLU || !sw) return 1;
     if (tiles * 2 > num_sms() || kblocks_all < 8) return 1;
-    const long long ks = std::min<long long>(std::min<long long>(num_sms() / tiles, kblocks_all / 4), 16);
+    long long ks = std::min<long long>(std::min<long long>(num_sms() / tiles, kblocks_all / 4), 16);
+    // the partial-sum exchange is 5-10 us of pure latency (publish, ticket, read back: profiles/r02 phase stamps), about
+    // as long as `split_min_saved` K blocks: a split that shortens the K loop by less than that loses.  MD_SPLIT_MIN
+    // overrides the threshold (0 = the round-1 rule).
+    static const int split_min_saved = getenv("MD_SPLIT_MIN") ? atoi(getenv("MD_SPLIT_MIN")) : 28;
+    if (ks > 1 && kblocks_all - kblocks_all / ks < split_min_saved) ks = 1;
     return static_cast<int>(std::max<long long>(ks, 1));
   };
   int BN = a.BN;

@@ -300,6 +300,8 @@ if __name__ == "__main__":
         vae_decode_golden("vae_n2_lat8", 2, 8)
     if want("vae_n2_lat32"):
         vae_decode_golden("vae_n2_lat32", 2, 32)
+    if want("vae_n1_lat64"):          # BASELINE config 1's latent size (512x512 image)
+        vae_decode_golden("vae_n1_lat64", 1, 64)
     if want("vae_enc_n2_64"):         # §8f rank 2 (VAE half): encoder moments, small image (CPU test) and 256x256 (GPU test)
         vae_encode_golden("vae_enc_n2_64", 2, 64)
     if want("vae_enc_n2_256"):

@@ -39,7 +39,7 @@ def vae_engine(vae_state_dict):
     eng.close()
 
 
-@pytest.mark.parametrize("name", ["vae_n2_lat8", "vae_n2_lat32"])
+@pytest.mark.parametrize("name", ["vae_n2_lat8", "vae_n2_lat32", "vae_n1_lat64"])
 def test_vae_decode_vs_reference_golden(vae_engine, name):
     gold = np.load(os.path.join(GOLD, name + ".npz"))
     n, latent = int(gold["n_views"]), int(gold["latent"])
