@@ -190,9 +190,27 @@ class UNetWrapper(nn.Module):
     def get_trainable_parameters(self):
         return self.diffusion_model.get_trainable_parameters()
 
+    def drop(self, cond, mask):
+        """morphable_diffusion.py:74-82: zero a condition for the masked-out samples."""
+        shape = cond.shape
+        mask = mask.view(shape[0], *[1 for _ in range(len(shape) - 1)])
+        return cond * mask
+
+    def get_drop_scheme(self, B, device):
+        """morphable_diffusion.py:84-93."""
+        if self.drop_scheme != "default":
+            raise NotImplementedError
+        random = torch.rand(B, dtype=torch.float32, device=device)
+        return ((random > 0.15) & (random <= 0.2), (random > 0.1) & (random <= 0.15), (random > 0.05) & (random <= 0.1),
+                random <= 0.05)
+
     def forward(self, x, t, clip_embed, volume_feats, x_concat, is_train=False):
-        if self.drop_conditions and is_train:
-            raise NotImplementedError("condition dropout belongs to the training path (not built)")
+        if self.drop_conditions and is_train:       # :106-118 (host-side masks; the UNet itself runs in the library)
+            drop_clip, drop_volume, drop_concat, drop_all = self.get_drop_scheme(x.shape[0], x.device)
+            clip_embed = self.drop(clip_embed, 1.0 - (drop_clip | drop_all).float())
+            volume_mask = 1.0 - (drop_volume | drop_all).float()
+            volume_feats = {k: self.drop(v, volume_mask) for k, v in volume_feats.items()}
+            x_concat = self.drop(x_concat, 1.0 - (drop_concat | drop_all).float())
         xc = x_concat * 1.0
         if self.use_zero_123:
             xc[:, :4] = xc[:, :4] / 0.18215
@@ -463,10 +481,16 @@ class SyncMultiviewDiffusion(_Base):
         return eng.vae_decode(z)
 
     @torch.no_grad()
-    def prepare(self, batch):
+    def prepare(self, batch, encode_targets=False):
         """morphable_diffusion.py:473-489 with both frozen side models on the CUDA library: VAE encode of the input image
-        (md_vae_encode) and its CLIP embedding (md_clip_embed).  The reference's 16 target encodes are discarded at
-        inference (x is unused by sample) and are skipped here."""
+        (md_vae_encode) and its CLIP embedding (md_clip_embed).  The reference also encodes the N target images whenever
+        the batch carries them; sample() never reads that result, so it is computed only on request (training)."""
+        x = None
+        if encode_targets and "target_image" in batch:
+            image_target = batch["target_image"].permute(0, 1, 4, 2, 3)                # b,n,3,h,w
+            Bt, Nt = image_target.shape[:2]
+            z = self.encode_first_stage(image_target.reshape(Bt * Nt, *image_target.shape[2:]), True)
+            x = z.view(Bt, Nt, *z.shape[1:])
         image_input = batch["input_image"].permute(0, 3, 1, 2)
         x_input = self.encode_first_stage(image_input)
         input_info = {"image": image_input, "elevation": batch["input_elevation"][:, 0], "x": x_input}
@@ -477,7 +501,7 @@ class SyncMultiviewDiffusion(_Base):
             clip_embed = self.clip_image_encoder.encode(image_input)
         else:
             raise RuntimeError("the loaded state dict carries no clip_image_encoder.model.visual.* tensors")
-        return None, clip_embed, input_info
+        return x, clip_embed, input_info
 
     def sample(self, sampler, batch, cfg_scale, batch_view_num, return_inter_results=False, inter_interval=50,
                inter_view_interval=2):
@@ -538,9 +562,58 @@ class SyncMultiviewDiffusion(_Base):
         output_dir.mkdir(exist_ok=True, parents=True)
         self.log_image(x_sample, batch, batch_idx, output_dir=output_dir)
 
-    # -- training: signatures kept, not built (autograd for the CUDA kernels)
+    # -- training: the FORWARD half runs on the library; autograd for the CUDA kernels is not built
+    def add_noise(self, x_start, t):
+        """morphable_diffusion.py:551-565."""
+        B = x_start.shape[0]
+        noise = torch.randn_like(x_start)
+        shape = (B,) + (1,) * (x_start.dim() - 1)
+        x_noisy = self.sqrt_alphas_cumprod[t].view(shape) * x_start + self.sqrt_one_minus_alphas_cumprod[t].view(shape) * noise
+        return x_noisy, noise
+
+    @torch.no_grad()
+    def training_loss(self, batch, x=None, time_steps=None, noise=None, target_index=None, prepared=None):
+        """The forward half of training_step (morphable_diffusion.py:520-541): returns (loss, noise_predict).  The three
+        random draws can be passed in (tests); x = clean target latents [B,N,4,h,w] (default: VAE-encoded target images);
+        prepared = (clip_embed [B,1,768], input_info {'x': [B,4,h,w]}) skips prepare()."""
+        dev = self._device
+        B = batch["target_K"].shape[0]
+        if time_steps is None:
+            time_steps = torch.randint(0, self.num_timesteps, (B,), device=dev).long()
+        if prepared is None:
+            enc_x, clip_embed, input_info = self.prepare(batch, encode_targets=x is None)
+        else:
+            enc_x, (clip_embed, input_info) = None, prepared
+        x = enc_x if x is None else x.to(dev)
+        if noise is None:
+            x_noisy, noise = self.add_noise(x, time_steps)
+        else:
+            shape = (B,) + (1,) * (x.dim() - 1)
+            noise = noise.to(dev)
+            x_noisy = self.sqrt_alphas_cumprod[time_steps].view(shape) * x + \
+                self.sqrt_one_minus_alphas_cumprod[time_steps].view(shape) * noise
+        N = self.view_num
+        if target_index is None:
+            target_index = torch.randint(0, N, (B, 1), device=dev).long()
+        v_embed = self.get_viewpoint_embedding(batch)
+        t_embed = self.embed_time(time_steps)
+        spatial_volume = self.spatial_volume.construct_spatial_volume(x_noisy, t_embed, v_embed, batch)
+        clip_, volume_feats, x_concat = self.get_target_view_feats(input_info["x"], spatial_volume, clip_embed, t_embed,
+                                                                   v_embed, target_index, batch)
+        ar = torch.arange(B, device=dev)[:, None]
+        x_noisy_ = x_noisy[ar, target_index][:, 0]
+        noise_predict = self.model(x_noisy_, time_steps, clip_, volume_feats, x_concat, is_train=True)
+        noise_target = noise[ar, target_index][:, 0]
+        loss_simple = torch.nn.functional.mse_loss(noise_target, noise_predict, reduction="none")
+        return loss_simple.mean(), noise_predict
+
     def training_step(self, batch):
-        raise NotImplementedError("training path (autograd for the CUDA kernels) is not built yet")
+        """With gradients enabled this would need backward kernels (not built): it raises.  Under torch.no_grad() it
+        returns the training loss of one step (forward only), e.g. for a validation-loss curve."""
+        if torch.is_grad_enabled():
+            raise NotImplementedError("training path: the forward loss runs on the library (use torch.no_grad() or "
+                                      "training_loss()); autograd for the CUDA kernels is not built yet")
+        return self.training_loss(batch)[0]
 
     def configure_optimizers(self):
         raise NotImplementedError("training path is not built yet")

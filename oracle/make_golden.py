@@ -246,6 +246,35 @@ def clip_golden(name, n, size, seed=6033):
                         seed=seed, input_seed=seed + 79)
 
 
+def train_forward_golden(name, n_views=4, seed=6033):
+    """The forward half of the reference's training_step (morphable_diffusion.py:520-541), line by line through the
+    reference's own methods (add_noise with a seeded torch generator state, embed_time, construct_spatial_volume,
+    get_target_view_feats, UNetWrapper.forward(is_train=True)); the Lightning logging calls (:543-548) are left out."""
+    model, ns = ref_import.build_reference_model(view_num=n_views)
+    sd = load_synth(model, seed)
+    batch = synth.make_batch(n_views, "perspective", "flame", seed)
+    x_t, x_input, clip = synth.make_inputs(n_views, 32, seed)          # x_t doubles as the clean target latents
+    B = 1
+    time_steps = torch.tensor([437])
+    target_index = torch.tensor([[2]])
+    torch.manual_seed(seed + 80)
+    with torch.no_grad():
+        x_noisy, noise = model.add_noise(x_t, time_steps)
+        v_embed = model.get_viewpoint_embedding(batch)
+        t_embed = model.embed_time(time_steps)
+        vol = model.spatial_volume.construct_spatial_volume(x_noisy, t_embed, v_embed, batch)
+        clip_, feats, xc = model.get_target_view_feats(x_input, vol, clip, t_embed, v_embed, target_index, batch)
+        x_noisy_ = x_noisy[torch.arange(B)[:, None], target_index][:, 0]
+        pred = model.model(x_noisy_, time_steps, clip_, feats, xc, is_train=True)
+        target = noise[torch.arange(B)[:, None], target_index][:, 0]
+        loss = torch.nn.functional.mse_loss(target, pred, reduction="none").mean()
+        o_loss, o_pred = O.training_forward(sd, O.VolumeCfg("perspective", num_views=n_views), batch, x_t, x_input, clip,
+                                            time_steps, noise, target_index)
+    print(f"[{name}] loss ref {float(loss):.6f} oracle {float(o_loss):.6f}  pred err/max {maxerr(o_pred, pred)}", flush=True)
+    np.savez_compressed(GOLD / f"{name}.npz", n_views=n_views, seed=seed, time_step=437, target_index=2,
+                        noise_seed=seed + 80, noise=noise.numpy(), pred=pred.numpy(), loss=float(loss))
+
+
 def spec_dump():
     model, ns = ref_import.build_reference_model()
     skip = ("betas", "alphas", "alphas_cumprod", "sqrt_alphas_cumprod", "sqrt_one_minus_alphas_cumprod",
@@ -308,5 +337,7 @@ if __name__ == "__main__":
         vae_encode_golden("vae_enc_n2_256", 2, 256)
     if want("clip_n2_256"):           # §8f rank 2 (CLIP half): image embedding of two 256x256 images
         clip_golden("clip_n2_256", 2, 256)
+    if want("train_n4"):              # §8f rank 3, forward half: the training loss of one step
+        train_forward_golden("train_n4")
     if want("traj_n2_50"):            # a2: the 50-step sampler loop
         run_trajectory("traj_n2_50", 2, 50)

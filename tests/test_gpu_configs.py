@@ -182,6 +182,26 @@ def test_sampler_with_other_step_counts(state_dict):
     assert same < 1e-2 and moved > 3 * max(same, 3e-3), (same, moved)
 
 
+def test_training_forward_loss_vs_reference_golden(state_dict):
+    """SURVEY §8f rank 3, forward half: SyncMultiviewDiffusion.training_loss (the forward of training_step, morphable_
+    diffusion.py:520-541, composed of the library's stage calls) against the reference's own methods with the same
+    time step, noise and target view (tests/golden/train_n4.npz).  training_step itself refuses to run with gradients."""
+    from morphablediffusion_b200 import synth
+    gold = np.load(os.path.join(GOLD, "train_n4.npz"))
+    n, seed = int(gold["n_views"]), int(gold["seed"])
+    model = _shell(n, state_dict)
+    batch = {k: v.cuda() for k, v in synth.make_batch(n, "perspective", "flame", seed).items()}
+    x, x_input, clip = synth.make_inputs(n, 32, seed)
+    loss, pred = model.training_loss(batch, x=x.cuda(), time_steps=torch.tensor([int(gold["time_step"])], device="cuda"),
+                                     noise=torch.from_numpy(gold["noise"]).cuda(),
+                                     target_index=torch.tensor([[int(gold["target_index"])]], device="cuda"),
+                                     prepared=(clip.cuda(), {"x": x_input.cuda()}))
+    assert rel(pred, torch.from_numpy(gold["pred"])) < BF16_REL, rel(pred, torch.from_numpy(gold["pred"]))
+    assert abs(float(loss) - float(gold["loss"])) < 2e-2 * float(gold["loss"])
+    with pytest.raises(NotImplementedError):
+        model.training_step(batch)
+
+
 def test_sample_seeds_differ_between_calls_and_items(state_dict):
     """step noise is no longer one fixed Philox stream: it follows torch's generator per sample() call
     and differs between batch items; the same torch seed reproduces the same sample."""

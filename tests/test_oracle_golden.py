@@ -92,6 +92,20 @@ def test_clip_image_embedder_matches_independent_implementation(clip_state_dict)
     assert rel(emb, torch.from_numpy(gold["embed"])) < TOL
 
 
+def test_training_forward_matches_reference(state_dict):
+    """Forward half of training_step (loss of one step) vs the reference's own methods (tests/golden/train_n4.npz)."""
+    gold = np.load(os.path.join(GOLD, "train_n4.npz"))
+    n, seed = int(gold["n_views"]), int(gold["seed"])
+    batch = synth.make_batch(n, "perspective", "flame", seed)
+    x, x_input, clip = synth.make_inputs(n, 32, seed)
+    with torch.no_grad():
+        loss, pred = O.training_forward(state_dict, O.VolumeCfg("perspective", num_views=n), batch, x, x_input, clip,
+                                        torch.tensor([int(gold["time_step"])]), torch.from_numpy(gold["noise"]),
+                                        torch.tensor([[int(gold["target_index"])]]))
+    assert rel(pred, torch.from_numpy(gold["pred"])) < TOL
+    assert abs(float(loss) - float(gold["loss"])) < 1e-4 * float(gold["loss"])
+
+
 def test_schedule_constants():
     s = O.make_schedule()
     assert s["timesteps"][0] == 1 and s["timesteps"][-1] == 981 and len(s["timesteps"]) == 50
