@@ -202,6 +202,33 @@ def test_training_forward_loss_vs_reference_golden(state_dict):
         model.training_step(batch)
 
 
+def test_stage_methods_compose_like_the_reference(state_dict):
+    """The body of the reference's denoise_apply (morphable_diffusion.py:713-737) written against the drop-in classes' stage
+    methods — embed_time, construct_spatial_volume, get_target_view_feats, UNetWrapper.predict_with_unconditional_scale —
+    must give the reference's epsilon (tests/golden/step_n4_persp.npz)."""
+    from morphablediffusion_b200 import synth
+    gold = np.load(os.path.join(GOLD, "step_n4_persp.npz"))
+    n, seed, scale = int(gold["n_views"]), int(gold["seed"]), float(gold["cfg_scale"])
+    model = _shell(n, state_dict)
+    batch = {k: v.cuda() for k, v in synth.make_batch(n, "perspective", "flame", seed).items()}
+    x_t, x_input, clip = (a.cuda() for a in synth.make_inputs(n, 32, seed))
+    B, N, C, H, W = x_t.shape
+    t = torch.full((B,), int(gold["timestep"]), device="cuda", dtype=torch.long)
+    v_embed = model.get_viewpoint_embedding(batch)
+    t_embed = model.embed_time(t)
+    vol = model.spatial_volume.construct_spatial_volume(x_t, t_embed, v_embed, batch)
+    e_t = []
+    for ni in range(0, N, 2):                                             # batch_view_num = 2
+        xs = x_t[:, ni:ni + 2].reshape(B * 2, C, H, W)
+        ts = t.view(B, 1).repeat(1, 2).view(B * 2)
+        idx = torch.arange(N, device="cuda")[ni:ni + 2].unsqueeze(0).repeat(B, 1)
+        clip_, feats, xc = model.get_target_view_feats(x_input, vol, clip, t_embed, v_embed, idx, batch)
+        e = model.model.predict_with_unconditional_scale(xs, ts, clip_, feats, xc, scale)
+        e_t.append(e.view(B, 2, 4, H, W))
+    eps = torch.cat(e_t, 1)
+    assert rel(eps, torch.from_numpy(gold["eps"])) < BF16_REL, rel(eps, torch.from_numpy(gold["eps"]))
+
+
 def test_sample_seeds_differ_between_calls_and_items(state_dict):
     """step noise is no longer one fixed Philox stream: it follows torch's generator per sample() call
     and differs between batch items; the same torch seed reproduces the same sample."""
