@@ -69,9 +69,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __
   using L = AttSmem<NDB, NWG, STAGES>;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* q_full = reinterpret_cast<uint64_t*>(smem + L::kBar);
-  uint64_t* kv_full = q_full + 1;
-  uint64_t* kv_empty = kv_full + STAGES;
-  uint64_t* s_full = kv_empty + STAGES;   // [NWG] scores of the current key tile are in TMEM
+  // K and V tiles of a stage have their own barriers: the K half is free again as soon as Q K^T of its tile has run,
+  // long before the P V product that frees the V half, so the next key tile is already in flight while the softmax of
+  // the current one runs.  With one barrier per stage the load of tile j+1 could only start after P V of tile j-1, and
+  // the softmax warps waited for their scores every tile (14 % of all stall samples at that wait in the ncu source
+  // page, gpurun_out/r02ab): 135 -> 121 us on the level-0 launch.
+  uint64_t* k_full = q_full + 1;
+  uint64_t* k_empty = k_full + STAGES;
+  uint64_t* v_full = k_empty + STAGES;
+  uint64_t* v_empty = v_full + STAGES;
+  uint64_t* s_full = v_empty + STAGES;    // [NWG] scores of the current key tile are in TMEM
   uint64_t* s_free = s_full + NWG;        // [NWG] the warpgroup has read them into registers
   uint64_t* p_ready = s_free + NWG;       // [NWG] P tile written (and O rescaled if needed)
   uint64_t* pv_done = p_ready + NWG;      // [NWG] O += P V of the previous key tile has completed
@@ -87,7 +94,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmQKV);
     mbar_init(q_full, 1);
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
+    }
     for (int w = 0; w < NWG; ++w) {
       mbar_init(&s_full[w], 1);
       mbar_init(&s_free[w], 128);
@@ -120,16 +130,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __
     int s = 0;
     uint32_t ph = 0;
     for (int j = 0; j < nt; ++j) {
-      mbar_wait(&kv_empty[s], ph ^ 1);
       uint8_t* base = smem + L::kKV + s * L::kStageBytes;
+      mbar_wait(&k_empty[s], ph ^ 1);
       if (elect_one()) {
-        mbar_expect_tx(&kv_full[s], L::kStageBytes);
+        mbar_expect_tx(&k_full[s], NDB * kBox);
 #pragma unroll
         for (int db = 0; db < NDB; ++db)
-          tma_load_3d(base + db * kBox, &tmQKV, &kv_full[s], db * 64, heads + h, row0 + j * 128);
+          tma_load_3d(base + db * kBox, &tmQKV, &k_full[s], db * 64, heads + h, row0 + j * 128);
+      }
+      mbar_wait(&v_empty[s], ph ^ 1);
+      if (elect_one()) {
+        mbar_expect_tx(&v_full[s], NDB * kBox);
 #pragma unroll
         for (int db = 0; db < NDB; ++db)
-          tma_load_3d(base + (NDB + db) * kBox, &tmQKV, &kv_full[s], db * 64, 2 * heads + h, row0 + j * 128);
+          tma_load_3d(base + (NDB + db) * kBox, &tmQKV, &v_full[s], db * 64, 2 * heads + h, row0 + j * 128);
       }
       if (++s == STAGES) { s = 0; ph ^= 1; }
     }
@@ -143,7 +157,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __
     for (int j = 0; j <= nt; ++j) {
       if (j < nt) {
         const int s = j % STAGES;
-        mbar_wait(&kv_full[s], (j / STAGES) & 1);
+        mbar_wait(&k_full[s], (j / STAGES) & 1);
         tc_fence_after();
         const uint32_t kbase = smem_u32(smem + L::kKV + s * L::kStageBytes);
         for (int w = 0; w < NWG; ++w) {
@@ -162,11 +176,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __
             tc_commit(&s_full[w]);
           }
         }
+        if (elect_one()) tc_commit(&k_empty[s]);   // the K tile is free once every warpgroup's Q K^T has run
       }
       if (j > 0) {
         const int jp = j - 1;
         const int sp = jp % STAGES;
         const uint32_t vbase = smem_u32(smem + L::kKV + sp * L::kStageBytes + NDB * kBox);
+        mbar_wait(&v_full[sp], (jp / STAGES) & 1);
+        tc_fence_after();
         for (int w = 0; w < NWG; ++w) {
           mbar_wait(&p_ready[w], jp & 1);
           tc_fence_after();
@@ -182,7 +199,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __
             tc_commit(&pv_done[w]);
           }
         }
-        if (elect_one()) tc_commit(&kv_empty[sp]);
+        if (elect_one()) tc_commit(&v_empty[sp]);
       }
     }
     __syncwarp();
