@@ -149,8 +149,10 @@ def kernel_rooflines(dev, tensor_peak, hbm_peak):
     fl = 4.0 * B * heads * S * S * dh
     out.append({"kernel": "attention_tc_kernel", "shape": "32 x 8 heads x 1024 tokens x 40", "bound": "tensor",
                 "achieved": fl / t / 1e12, "peak": tensor_peak, "unit": "TFLOP/s", "frac": fl / t / 1e12 / tensor_peak,
-                "us": t * 1e6, "note": "exp-bound: 268 M ex2 per launch on 16 MUFU lanes/SM/clk = 60 us floor",
-                "traffic": 68.7e6, "traffic_source": "profiles/r01_attention_tc_full_v9.md (dram read + write, ncu --set full)"})
+                "us": t * 1e6, "note": "exp-bound: 268 M ex2 per launch on 16 MUFU lanes/SM/clk (measured, tools/ubench/mufu.cu) "
+                "= 58 us floor",
+                "traffic": 65.7e6, "traffic_source": "gpurun_out r02ag / profiles/r02_attention_stalls_by_opcode.txt run "
+                "(dram read + write of the persistent kernel, ncu --set full)"})
     # GroupNorm + SiLU apply (HBM-bound): fp32 [32][1024][320] -> bf16
     x = torch.randn(32, 1024, 320, device=dev)
     stats = torch.stack([x.sum(1), (x * x).sum(1)], dim=-1).contiguous()

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round-2 visit 26: source-level stall profile of the level-0 attention launch
-O=gpurun_out/r02ae; mkdir -p $O
+O=gpurun_out/r02af; mkdir -p $O
 timeout 300 ncu --profile-from-start off --set full --clock-control none --import-source on -o $O/att -f python tools/attn_one.py > $O/att.log 2>&1
 ncu -i $O/att.ncu-rep --page source --csv 2>> $O/att.log | python tools/ncu_source_top.py 60 > $O/att_source_top.txt 2>&1
 ncu -i $O/att.ncu-rep --page raw --csv 2>> $O/att.log > $O/att_raw.csv
