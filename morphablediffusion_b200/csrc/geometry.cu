@@ -677,11 +677,191 @@ __global__ void sparse_conv_quad_kernel(const float* __restrict__ in, const int3
   *reinterpret_cast<float4*>(out + static_cast<size_t>(r) * Cout + cq * 4) = o;
 }
 
+// Wide layers as a register-tiled gather GEMM: one CTA owns TM output rows x COUT channels.  Per kernel tap that is active
+// for at least one row of the tile, the gathered input rows ([row][ci], rows of inactive neighbours zero-filled) and the
+// tap's CIN x COUT weight block are copied into shared memory with cp.async through an NST-stage ring, so the gathers of
+// the next NST - 1 taps are in flight while the current one is multiplied.  Every thread accumulates an RPT x 4
+// micro-tile: per four input channels, RPT + 4 16-byte shared-memory loads feed 16 * RPT FMAs.  NGRP groups of 256
+// threads share the tile: the active taps are dealt round-robin to the groups, each with its own ring and named
+// barrier, and the partial sums meet in shared memory before the epilogue.
+// History (64 -> 64 layer of the FLAME mesh, 7 051 rows, ncu): one thread per (row, 4 channels) re-reading every weight
+// from L1 for 4 FMAs: 154 us (L1 bandwidth); tiles with weights through L1: 170 us (L2 latency of each tap's first
+// touch); weights staged one tap ahead, register-staged transposed gather: 76 us (one gather in flight per group,
+// issue slots 50 % busy); this version: see profiles/r02_sparse_conv.md.
+__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsrc, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void group_barrier(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+template <int CIN, int COUT, int TM>
+constexpr int sparse_stage_floats() { return TM * (CIN + 4) + CIN * COUT; }
+template <int CIN, int COUT, int TM, int NGRP, int NST>
+constexpr int sparse_tile_smem() { return 27 * TM * 4 + NGRP * NST * sparse_stage_floats<CIN, COUT, TM>() * 4; }
+
+template <int CIN, int COUT, int TM, int NGRP, int NST>
+__global__ void __launch_bounds__(256 * NGRP) sparse_conv_tile_kernel(const float* __restrict__ in, const int32_t* __restrict__ nbr,
+                                                                      const float* __restrict__ W, const float* __restrict__ scale,
+                                                                      const float* __restrict__ shift, float* __restrict__ out,
+                                                                      int n_rows) {
+  constexpr int CQ = COUT / 4;       // column quads
+  constexpr int RG = 256 / CQ;       // row groups
+  constexpr int RPT = TM / RG;       // rows per thread
+  constexpr int LDA = CIN + 4;       // padded row pitch: the row groups of one warp land on different banks
+  constexpr int NA = TM * CIN / 4;   // activation float4 per tap
+  constexpr int NWT = CIN * COUT / 4;  // weight float4 per tap
+  constexpr int STAGE = sparse_stage_floats<CIN, COUT, TM>();
+  constexpr int GRP_FLOATS = NST * STAGE;
+  static_assert(RPT == 2 || RPT == 4, "micro-tile is 2 or 4 rows");
+  static_assert(NA % 256 == 0, "gather mapping");
+  static_assert(NGRP == 1 || TM * COUT <= GRP_FLOATS, "partial sums reuse a group's ring");
+  extern __shared__ __align__(16) uint8_t sparse_smem[];
+  const int grp = threadIdx.x >> 8;
+  const int t = threadIdx.x & 255;
+  float* ring = reinterpret_cast<float*>(sparse_smem) + grp * GRP_FLOATS;
+  int (*s_nbr)[TM] = reinterpret_cast<int (*)[TM]>(reinterpret_cast<float*>(sparse_smem) + NGRP * GRP_FLOATS);
+  __shared__ unsigned s_mask;
+  const int row0 = blockIdx.x * TM;
+  if (threadIdx.x == 0) s_mask = 0u;
+  __syncthreads();
+  unsigned mine = 0u;
+  for (int i = threadIdx.x; i < 27 * TM; i += 256 * NGRP) {  // the rulebook is static (uploaded at bind): read it before the grid dependency
+    const int r = i / 27, k = i - r * 27;
+    const int j = (row0 + r < n_rows) ? __ldg(nbr + static_cast<size_t>(row0) * 27 + i) : -1;
+    s_nbr[k][r] = j;
+    if (j >= 0) mine |= 1u << k;
+  }
+  mine = __reduce_or_sync(0xffffffffu, mine);
+  if ((t & 31) == 0 && mine) atomicOr(&s_mask, mine);
+  __syncthreads();
+  unsigned mask = s_mask;
+  if (NGRP > 1) {  // keep every NGRP-th active tap, starting at this group's index
+    unsigned keep = 0u, rest = mask;
+    for (int i = 0; rest; ++i, rest &= rest - 1)
+      if (i % NGRP == grp) keep |= rest & (0u - rest);
+    mask = keep;
+  }
+  const int n_taps = __popc(mask);
+
+  const int cq = t % CQ, rg = t / CQ;
+  float acc[RPT][4];
+#pragma unroll
+  for (int r = 0; r < RPT; ++r) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f;
+
+  unsigned to_issue = mask;
+  auto issue_next = [&](int stage) {  // copies of the next unissued tap into ring slot `stage`; always commits a group
+    if (to_issue) {
+      const int k = __ffs(to_issue) - 1;
+      to_issue &= to_issue - 1;
+      float* sa = ring + stage * STAGE;
+      float* sw = sa + TM * LDA;
+      const float4* wsrc = reinterpret_cast<const float4*>(W + static_cast<size_t>(k) * CIN * COUT);
+#pragma unroll
+      for (int q = 0; q < (NWT + 255) / 256; ++q)
+        if (NWT % 256 == 0 || t + q * 256 < NWT) cp_async16_zfill(sw + (t + q * 256) * 4, wsrc + t + q * 256, 16);
+#pragma unroll
+      for (int q = 0; q < NA / 256; ++q) {
+        const int idx = t + q * 256;
+        const int r = idx / (CIN / 4), c4 = idx - r * (CIN / 4);
+        const int j = s_nbr[k][r];
+        cp_async16_zfill(sa + r * LDA + c4 * 4, in + (j >= 0 ? static_cast<size_t>(j) * CIN + c4 * 4 : 0), j >= 0 ? 16 : 0);
+      }
+    }
+    cp_async_commit();
+  };
+
+  pdl_grid_sync();
+#pragma unroll
+  for (int sidx = 0; sidx < NST - 1; ++sidx) issue_next(sidx);
+  for (int i = 0; i < n_taps; ++i) {
+    cp_async_wait<NST - 2>();         // this thread's copies of tap i have landed
+    group_barrier(1 + grp, 256);      // ... everyone's have, and everyone is past the multiply of tap i - 1
+    issue_next((i + NST - 1) % NST);  // refill the slot tap i - 1 used
+    const float* sa = ring + (i % NST) * STAGE + rg * RPT * LDA;
+    const float* sw = ring + (i % NST) * STAGE + TM * LDA + cq * 4;
+#pragma unroll 2
+    for (int c4 = 0; c4 < CIN / 4; ++c4) {
+      float4 av[RPT];
+#pragma unroll
+      for (int r = 0; r < RPT; ++r) av[r] = *reinterpret_cast<const float4*>(sa + r * LDA + c4 * 4);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float4 w = *reinterpret_cast<const float4*>(sw + (c4 * 4 + e) * COUT);
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) {
+          const float a = e == 0 ? av[r].x : e == 1 ? av[r].y : e == 2 ? av[r].z : av[r].w;
+          acc[r][0] += a * w.x; acc[r][1] += a * w.y; acc[r][2] += a * w.z; acc[r][3] += a * w.w;
+        }
+      }
+    }
+  }
+  cp_async_wait<0>();
+  if (NGRP > 1) {  // groups 1.. park their partial tiles in their own (now idle) ring; group 0 adds them
+    group_barrier(1 + grp, 256);  // the whole group is past its last multiply before the ring is overwritten
+    if (grp > 0) {
+      float4* part = reinterpret_cast<float4*>(ring);
+#pragma unroll
+      for (int r = 0; r < RPT; ++r) part[r * 256 + t] = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+    }
+    __syncthreads();
+    if (grp > 0) return;
+    for (int gi = 1; gi < NGRP; ++gi) {
+      const float4* other = reinterpret_cast<const float4*>(reinterpret_cast<float*>(sparse_smem) + gi * GRP_FLOATS);
+#pragma unroll
+      for (int r = 0; r < RPT; ++r) {
+        const float4 v = other[r * 256 + t];
+        acc[r][0] += v.x; acc[r][1] += v.y; acc[r][2] += v.z; acc[r][3] += v.w;
+      }
+    }
+  }
+  const float4 sc = *reinterpret_cast<const float4*>(scale + cq * 4);
+  const float4 sh = *reinterpret_cast<const float4*>(shift + cq * 4);
+#pragma unroll
+  for (int r = 0; r < RPT; ++r) {
+    const int row = row0 + rg * RPT + r;
+    if (row >= n_rows) continue;
+    float4 o;
+    o.x = fmaxf(acc[r][0] * sc.x + sh.x, 0.f); o.y = fmaxf(acc[r][1] * sc.y + sh.y, 0.f);
+    o.z = fmaxf(acc[r][2] * sc.z + sh.z, 0.f); o.w = fmaxf(acc[r][3] * sc.w + sh.w, 0.f);
+    *reinterpret_cast<float4*>(out + static_cast<size_t>(row) * COUT + cq * 4) = o;
+  }
+}
+
+template <int CIN, int COUT, int NGRP, int NST>
+static void launch_sparse_tile(const float* in, const int32_t* nbr, const float* W, const float* scale, const float* shift,
+                               float* out, int n_rows, cudaStream_t st) {
+  constexpr int TM = 64;
+  constexpr int smem = sparse_tile_smem<CIN, COUT, TM, NGRP, NST>();
+  static_assert(smem <= 227 * 1024, "shared memory per CTA");
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(sparse_conv_tile_kernel<CIN, COUT, TM, NGRP, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    configured = true;
+  }
+  launch_pdl(sparse_conv_tile_kernel<CIN, COUT, TM, NGRP, NST>, dim3((n_rows + TM - 1) / TM), dim3(256 * NGRP), smem, st, in,
+             nbr, W, scale, shift, out, n_rows);
+}
+
 int launch_sparse_conv(const float* in, const int32_t* nbr, const float* W, const float* scale, const float* shift,
                        float* out, int n_rows, int Cin, int Cout, cudaStream_t st) {
   if (n_rows == 0) return 0;
   const unsigned blocks = (static_cast<unsigned>(n_rows) * 32 + 127) / 128;
+  // MD_SPARSE_TILE: 0 = the one-warp-per-row / one-thread-per-quad kernels for every layer, 1 = tile kernel with one
+  // group of 256 threads, 2 (default) = two groups
+  static const int tile = getenv("MD_SPARSE_TILE") != nullptr ? atoi(getenv("MD_SPARSE_TILE")) : 2;
   if (Cin == 16 && Cout == 16) launch_pdl(sparse_conv_kernel<16, 16>, dim3(blocks), dim3(128), 0, st, in, nbr, W, scale, shift, out, n_rows);
+  else if (tile == 1 && Cin == 16 && Cout == 32) launch_sparse_tile<16, 32, 1, 4>(in, nbr, W, scale, shift, out, n_rows, st);
+  else if (tile == 1 && Cin == 32 && Cout == 32) launch_sparse_tile<32, 32, 1, 4>(in, nbr, W, scale, shift, out, n_rows, st);
+  else if (tile == 1 && Cin == 32 && Cout == 64) launch_sparse_tile<32, 64, 1, 4>(in, nbr, W, scale, shift, out, n_rows, st);
+  else if (tile == 1 && Cin == 64 && Cout == 64) launch_sparse_tile<64, 64, 1, 4>(in, nbr, W, scale, shift, out, n_rows, st);
+  else if (tile >= 2 && Cin == 16 && Cout == 32) launch_sparse_tile<16, 32, 2, 4>(in, nbr, W, scale, shift, out, n_rows, st);
+  else if (tile >= 2 && Cin == 32 && Cout == 32) launch_sparse_tile<32, 32, 2, 4>(in, nbr, W, scale, shift, out, n_rows, st);
+  else if (tile >= 2 && Cin == 32 && Cout == 64) launch_sparse_tile<32, 64, 2, 3>(in, nbr, W, scale, shift, out, n_rows, st);
+  else if (tile >= 2 && Cin == 64 && Cout == 64) launch_sparse_tile<64, 64, 2, 3>(in, nbr, W, scale, shift, out, n_rows, st);
   else if (Cin == 16 && Cout == 32) launch_pdl(sparse_conv_kernel<16, 32>, dim3(blocks), dim3(128), 0, st, in, nbr, W, scale, shift, out, n_rows);
   else if (Cin % 4 == 0 && Cout % 4 == 0)
     launch_pdl(sparse_conv_quad_kernel, dim3((n_rows * (Cout / 4) + 63) / 64), dim3(64), 0, st, in, nbr, W, scale, shift, out, n_rows, Cin, Cout);
