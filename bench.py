@@ -340,6 +340,8 @@ def run_ours(args):
         uid = [comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         eng.init_comm(rank, world, uid[0])
+        if os.environ.get("MD_PEER", "1") != "0":
+            eng.init_peer_exchange(dist)
     eng.bind(batch, proj, view0=view0, n_local=n_local)
 
     x0 = x_t[0, view0:view0 + n_local].contiguous()
@@ -418,6 +420,9 @@ def run_ours(args):
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": label, "views": N_VIEWS, "views_per_gpu": n_local, "views_per_unet_call": chunk,
                        "parallelism": f"view-shard x{world}",
+                       "exchange": ("none (single rank)" if world == 1 else
+                                    "NVLink peer-memory push of the vertex-feature sums, fused into the producer/consumer kernels"
+                                    if eng.peer_exchange_attached() else "NCCL all-reduce of the vertex-feature sums"),
                        "l2": "working set (1.8 GB weights + activations per step) >> 126 MB L2; no flush needed",
                        "accum": "bf16 operands, fp32 accumulate, fp32 residual stream"},
             "clocks": clocks,

@@ -241,6 +241,19 @@ MD_API int md_op_cfg_ddim(md_ctx* ctx, const float* eps, float* x, float* eps_ou
  * side (torch.distributed).  The only exchange per step is an all-reduce(sum) of the [nv][16] vertex features. */
 MD_API int md_comm_unique_id(void* id128);
 MD_API int md_comm_init(md_ctx* ctx, int rank, int world, const void* id128);
+/* NVLink peer exchange (after md_comm_init): with it attached, md_denoise_step no longer calls NCCL.  Every rank pushes
+ * its partial vertex-feature sums into its region of every peer's exchange buffer with plain stores over NVLink and
+ * raises a per-rank arrival flag; the kernel that consumes the sums (view mean + Conv1d + voxel scatter) waits for the
+ * flags in its own memory and adds the regions in rank order, so the exchange is fused into its producer / consumer
+ * kernels and the whole step is one CUDA graph on every rank.
+ *   md_peer_buffer : allocates this rank's buffer and writes its 64-byte cudaIpcMemHandle_t to ipc_handle64
+ *   md_peer_attach : ipc_handles = world x 64 bytes in rank order (gathered by the host side, e.g. all_gather_object);
+ *                    the caller runs a barrier over all ranks before the next md_denoise_step
+ * Every rank must then call md_denoise_step the same number of times (a missing rank is reported after ~2 s by the next
+ * call instead of hanging the device).  Meshes above 16 384 vertices keep the NCCL path. */
+MD_API int md_peer_buffer(md_ctx* ctx, int world, void* ipc_handle64);
+MD_API int md_peer_attach(md_ctx* ctx, int rank, int world, const void* ipc_handles);
+MD_API int md_peer_attached(md_ctx* ctx);
 
 #ifdef __cplusplus
 }

@@ -177,6 +177,11 @@ lib.md_clip_embed.argtypes = [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]
 lib.md_has_clip.argtypes = [_vp]
 lib.md_comm_unique_id.argtypes = [_vp]
 lib.md_comm_init.argtypes = [_vp, C.c_int, C.c_int, _vp]
+lib.md_peer_buffer.argtypes = [_vp, C.c_int, _vp]
+lib.md_peer_attach.argtypes = [_vp, C.c_int, C.c_int, _vp]
+lib.md_peer_attached.argtypes = [_vp]
+for _f in ("md_peer_buffer", "md_peer_attach", "md_peer_attached"):
+    getattr(lib, _f).restype = C.c_int
 for _f in ("md_embed_time", "md_create", "md_load_weights", "md_bind_sample", "md_voxelize", "md_spatial_volume", "md_frustum_feats",
            "md_unet_forward", "md_denoise_step", "md_ddim_timestep", "md_set_ddim", "md_ddim_steps", "md_comm_unique_id", "md_comm_init",
            "md_vae_decode", "md_has_vae", "md_vae_encode", "md_has_vae_encoder", "md_clip_embed", "md_has_clip"):

@@ -190,6 +190,24 @@ struct Ctx {
   // multi-GPU
   void* nccl_comm = nullptr;
   int rank = 0, world = 1;
+  // NVLink peer exchange of the vertex-feature sums (replaces the NCCL all-reduce inside the step; step.cu):
+  // every rank owns one IPC-exported buffer [2 slots][world][slot_floats] + [world] arrival flags.  A rank pushes its
+  // partial sums into its region of every peer's buffer and then stores the step's sequence number into the peers'
+  // flags; the consumer kernel (view mean + Conv1d + scatter) waits for its own flags and adds the world regions in rank
+  // order.  Slots alternate with the sequence number, which is enough: a rank can only reach step k+2's push after it
+  // has seen every peer's step-k+1 flag, which a peer raises after its own step-k consumer has finished.
+  struct PeerExchange {
+    bool on = false;
+    size_t slot_floats = 0;
+    float* base = nullptr;             // my buffer (device memory, IPC-exported)
+    void* peer_base[16] = {};          // peers' buffers mapped into this process (peer_base[rank] == base)
+    float** d_peer_data = nullptr;     // device copies of the pointer tables
+    unsigned** d_peer_flags = nullptr;
+    unsigned* d_seq = nullptr;         // [0] sequence number of the current step, [1] last-block ticket of the push kernel
+    unsigned seq = 0;                  // host-side counter (every rank calls md_denoise_step the same number of times)
+    int* h_err = nullptr;              // mapped pinned host word: the consumer sets it when a peer's flag never arrives
+    int* d_err = nullptr;
+  } px;
   std::string err;
 };
 
@@ -226,7 +244,7 @@ int bind_sample(Ctx& c, const float* K, const float* RT, const float* v_embed, c
 void free_binding(Ctx& c);
 int embed_time(Ctx& c, const float* t_dev, float* t_embed, cudaStream_t st);  // [1] -> [256]
 int vertex_feature_sum(Ctx& c, const float* x_local, const float* t_embed, float* vsum, cudaStream_t st);
-int spatial_volume_from_vsum(Ctx& c, const float* vsum, float* vol, cudaStream_t st);
+int spatial_volume_from_vsum(Ctx& c, const float* vsum, float* vol, cudaStream_t st, bool peer_exchange = false);
 int frustum_levels(Ctx& c, const float* vol, int lv0, int T, const float* t_embed, int alloc_samples, bf16* levels[4],
                    cudaStream_t st);
 

@@ -595,6 +595,86 @@ int launch_smpl_scatter(const float* vsum, float inv_views, const float* W, cons
   return check_launch("smpl_scatter");
 }
 
+// ---- cross-rank exchange of the vertex-feature sums over NVLink peer memory (Ctx::PeerExchange, engine.h) -----------------
+// Push: this rank's [n4] float4 partial sums go into region (seq & 1, rank) of EVERY rank's exchange buffer (plain remote
+// stores: fire and forget), each CTA fences at system scope, and the last CTA to finish raises this rank's flag in every
+// peer's buffer to the step's sequence number.
+__global__ void peer_push_kernel(const float4* __restrict__ vsum, int n4, float* const* __restrict__ peer_data,
+                                 unsigned* const* __restrict__ peer_flags, unsigned* __restrict__ seq_ticket, int rank,
+                                 int world, size_t slot_floats) {
+  pdl_grid_sync();
+  const unsigned seq = seq_ticket[0];
+  const size_t off4 = ((seq & 1u) * world + rank) * (slot_floats / 4);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+    const float4 v = vsum[i];
+    for (int p = 0; p < world; ++p) reinterpret_cast<float4*>(peer_data[p])[off4 + i] = v;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned t = atomicAdd(seq_ticket + 1, 1u);
+    if (t == gridDim.x - 1) {
+      seq_ticket[1] = 0u;  // every other CTA has taken its ticket: reset for the next step
+      __threadfence_system();
+      for (int p = 0; p < world; ++p) st_release_sys_u32(peer_flags[p] + rank, seq);
+    }
+  }
+}
+
+// Consume: SMPLFeatureExtractor + scatter as smpl_scatter_kernel, on the sum over ranks (added in rank order, so that
+// every rank builds bit-identical volumes).  Each CTA first waits until every rank's flag in THIS GPU's buffer has
+// reached the step's sequence number; the regions are read past L1 (__ldcg: peers write them through this GPU's L2).
+__global__ void smpl_scatter_peer_kernel(const float* __restrict__ slots, const unsigned* __restrict__ flags,
+                                         const unsigned* __restrict__ seq_ticket, int world, size_t slot_floats,
+                                         float inv_views, const float* __restrict__ W, const float* __restrict__ bias,
+                                         const int32_t* __restrict__ row_vertex, int n_rows, float* __restrict__ out,
+                                         int* __restrict__ err) {
+  pdl_grid_sync();
+  const unsigned seq = seq_ticket[0];
+  if (threadIdx.x < world) {
+    const long long t0 = clock64();
+    while (static_cast<int>(ld_acquire_sys_u32(flags + threadIdx.x) - seq) < 0) {
+      if (clock64() - t0 > (1LL << 32)) { *err = 1 + static_cast<int>(threadIdx.x); break; }  // ~2 s: report, never hang the device
+      __nanosleep(100);
+    }
+  }
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rows * 16) return;
+  const int co = i & 15, r = i >> 4;
+  const float* base = slots + (seq & 1u) * world * slot_floats + static_cast<size_t>(row_vertex[r]) * 16;
+  float f[16];
+#pragma unroll
+  for (int k4 = 0; k4 < 4; ++k4) {
+    float4 s4 = __ldcg(reinterpret_cast<const float4*>(base) + k4);
+    for (int p = 1; p < world; ++p) {
+      const float4 v = __ldcg(reinterpret_cast<const float4*>(base + p * slot_floats) + k4);
+      s4.x += v.x; s4.y += v.y; s4.z += v.z; s4.w += v.w;
+    }
+    f[k4 * 4] = s4.x; f[k4 * 4 + 1] = s4.y; f[k4 * 4 + 2] = s4.z; f[k4 * 4 + 3] = s4.w;
+  }
+  float a = 0.f;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) a += W[co * 16 + k] * (f[k] * inv_views);
+  out[i] = a + bias[co];
+}
+
+int launch_peer_push(const float* vsum, int n_floats, float* const* peer_data, unsigned* const* peer_flags,
+                     unsigned* seq_ticket, int rank, int world, size_t slot_floats, cudaStream_t st) {
+  const int n4 = n_floats / 4;
+  launch_pdl(peer_push_kernel, dim3(std::min((n4 + 255) / 256, 64)), dim3(256), 0, st, reinterpret_cast<const float4*>(vsum), n4,
+             peer_data, peer_flags, seq_ticket, rank, world, slot_floats);
+  return check_launch("peer_push");
+}
+
+int launch_smpl_scatter_peer(const float* slots, const unsigned* flags, const unsigned* seq_ticket, int world,
+                             size_t slot_floats, float inv_views, const float* W, const float* bias,
+                             const int32_t* row_vertex, int n_rows, float* out, int* err, cudaStream_t st) {
+  launch_pdl(smpl_scatter_peer_kernel, dim3((n_rows * 16 + 127) / 128), dim3(128), 0, st, slots, flags, seq_ticket, world,
+             slot_floats, inv_views, W, bias, row_vertex, n_rows, out, err);
+  return check_launch("smpl_scatter_peer");
+}
+
 // out[r][co] = relu( scale[co] * sum_{k,ci} W[k][ci][co] * in[nbr[r][k]][ci] + shift[co] ),  nbr < 0 = inactive.
 // One warp per output row: lane k < 27 owns kernel tap k (gathers its neighbour row and multiplies by W[k]), then the
 // 27 partial vectors are summed with a butterfly reduction.

@@ -24,6 +24,11 @@ int launch_vertex_features(const float* feats, const float* proj, int ortho, int
                            const float* vertices, int nv, int n_views, float* out, cudaStream_t st);
 int launch_smpl_scatter(const float* vsum, float inv_views, const float* W, const float* bias,
                         const int32_t* row_vertex, int n_rows, float* out, cudaStream_t st);
+int launch_peer_push(const float* vsum, int n_floats, float* const* peer_data, unsigned* const* peer_flags,
+                     unsigned* seq_ticket, int rank, int world, size_t slot_floats, cudaStream_t st);
+int launch_smpl_scatter_peer(const float* slots, const unsigned* flags, const unsigned* seq_ticket, int world,
+                             size_t slot_floats, float inv_views, const float* W, const float* bias,
+                             const int32_t* row_vertex, int n_rows, float* out, int* err, cudaStream_t st);
 int launch_sparse_conv(const float* in, const int32_t* nbr, const float* W, const float* scale, const float* shift,
                        float* out, int n_rows, int Cin, int Cout, cudaStream_t st);
 int launch_volume_resample(const float* feat, const int32_t* idx, const float* wgt, float* vol, int npts,

@@ -68,6 +68,16 @@ __device__ __forceinline__ unsigned ld_acquire_gpu_u32(const int* addr) {
   return v;
 }
 
+// system-scope flag traffic of the NVLink peer exchange (step.cu): the flag lives in this GPU's memory and is stored by a peer
+__device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned* addr) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys_u32(unsigned* addr, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(addr), "r"(v) : "memory");
+}
+
 // ---------------------------------------------------------------- programmatic dependent launch
 // Every kernel of the library starts with this: wait until the predecessor grid's writes are visible, then allow the
 // successor grid to begin launching (its own prologue overlaps our execution; it waits here in turn).

@@ -23,9 +23,10 @@ __global__ void fill_from_kernel(float* p, const float* src, int n) {
   if (i < n) p[i] = src[0];
 }
 __global__ void set_step_params_kernel(float* d, float tval, float a_t, float a_prev, float sigma, float s1m, int add_noise,
-                                       uint32_t index, uint64_t seed) {
+                                       uint32_t index, uint64_t seed, unsigned* xchg_seq, unsigned seq) {
   pdl_grid_sync();
   if (threadIdx.x == 0) {
+    if (xchg_seq) xchg_seq[0] = seq;  // sequence number of this step's peer exchange (read by the captured kernels)
     d[0] = tval; d[1] = a_t; d[2] = a_prev; d[3] = sigma; d[4] = s1m; d[5] = add_noise ? 1.f : 0.f;
     d[6] = __uint_as_float(index);
     d[7] = __uint_as_float(static_cast<uint32_t>(seed)); d[8] = __uint_as_float(static_cast<uint32_t>(seed >> 32));
@@ -126,6 +127,13 @@ static int allreduce_vsum(Ctx& c, cudaStream_t st) {
   return 0;
 }
 
+// The step's cross-rank exchange runs over NVLink peer memory (md_peer_attach) instead of NCCL when the exchange buffers
+// are attached and the mesh fits a region; MD_PEER=0 keeps the NCCL all-reduce between two graphs (A/B switch).
+static bool peer_exchange_active(const Ctx& c) {
+  static const bool env_on = !(getenv("MD_PEER") != nullptr && atoi(getenv("MD_PEER")) == 0);
+  return env_on && c.world > 1 && c.px.on && static_cast<size_t>(c.sb.nv) * 16 <= c.px.slot_floats;
+}
+
 // one denoise step for the local views (all chunks)
 static int denoise_step_impl(Ctx& c, float* x_local, const float* x_input, const float* clip, int index,
                              float cfg_scale, const float* noise, unsigned long long seed, float* eps_out,
@@ -160,14 +168,15 @@ static int denoise_step_impl(Ctx& c, float* x_local, const float* x_input, const
   // moves over (the encoder is one CTA per view: 0.25 ms during which the UNet would otherwise wait); with several
   // ranks the part before the cross-rank exchange stays on the main stream (it is captured as its own graph).
   const bool overlap = c.stream2 != nullptr && sb.n_local <= chunk && getenv("MD_NO_OVERLAP") == nullptr;
-  const bool vf_on_side = overlap && phase == 0 && c.world <= 1;
+  const bool peer = peer_exchange_active(c);  // then the step is one graph (phase 0) on every rank
+  const bool vf_on_side = overlap && phase == 0 && (c.world <= 1 || peer);
   if (phase != 2) {
     launch_pdl(fill_from_kernel, dim3((maxB + 63) / 64), dim3(64), 0, st, d_t, c.d_step, maxB);  // timestep of this index (d_step[0])
     MD_CHECK(check_launch("fill"));
     MD_CHECK(embed_time(c, d_t, t_embed, st));
     if (!vf_on_side) MD_CHECK(vertex_feature_sum(c, x_local, t_embed, vsum, st));
   }
-  if (phase == 0) MD_CHECK(allreduce_vsum(c, st));
+  if (phase == 0 && !peer) MD_CHECK(allreduce_vsum(c, st));
   if (phase == 1) return 0;
 
   const size_t m = A.mark();
@@ -185,7 +194,7 @@ static int denoise_step_impl(Ctx& c, float* x_local, const float* x_input, const
       {
         SplitScope side(&c.split_side);
         rc = vf_on_side ? vertex_feature_sum(c, x_local, t_embed, vsum, c.stream2) : 0;
-        if (rc == 0) rc = spatial_volume_from_vsum(c, vsum, vol, c.stream2);
+        if (rc == 0) rc = spatial_volume_from_vsum(c, vsum, vol, c.stream2, peer);
         if (rc == 0) rc = frustum_levels(c, vol, lv0, T, t_embed, T, levels, c.stream2);
       }
       std::swap(c.arena, c.arena2);
@@ -193,7 +202,7 @@ static int denoise_step_impl(Ctx& c, float* x_local, const float* x_input, const
       MD_CUDA(cudaEventRecord(c.ev_levels, c.stream2));
       c.levels_pending = true;
     } else {
-      if (lv0 == 0) MD_CHECK(spatial_volume_from_vsum(c, vsum, vol, st));
+      if (lv0 == 0) MD_CHECK(spatial_volume_from_vsum(c, vsum, vol, st, peer));
       MD_CHECK(frustum_levels(c, vol, lv0, T, t_embed, T, levels, st));
     }
     MD_CHECK(launch_unet_input(x_local + static_cast<size_t>(lv0) * 4 * HW, x_input, 0, x_in, T, HW, cfg, st));
@@ -300,6 +309,14 @@ void md_destroy(md_ctx* ctx) {
   free_binding(ctx->c);
   free_weights(ctx->c);
   if (ctx->c.nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->c.nccl_comm);
+  {
+    Ctx::PeerExchange& px = ctx->c.px;
+    for (int p = 0; p < 16; ++p)
+      if (px.peer_base[p] && px.peer_base[p] != px.base) cudaIpcCloseMemHandle(px.peer_base[p]);
+    cudaFree(px.d_peer_data); cudaFree(px.d_peer_flags); cudaFree(px.d_seq);
+    if (px.h_err) cudaFreeHost(px.h_err);
+    cudaFree(px.base);
+  }
   if (ctx->c.graph) cudaGraphExecDestroy(ctx->c.graph);
   if (ctx->c.graph_b) cudaGraphExecDestroy(ctx->c.graph_b);
   if (ctx->c.stream) cudaStreamDestroy(ctx->c.stream);
@@ -456,9 +473,16 @@ int md_denoise_step(md_ctx* ctx, float* x_local, const float* x_input, const flo
   // fence the caller's stream into the internal one (the legacy default stream cannot be captured)
   MD_CUDA(cudaEventRecord(c.ev_in, caller));
   MD_CUDA(cudaStreamWaitEvent(st, c.ev_in, 0));
+  const bool peer = peer_exchange_active(c);
+  if (peer) {
+    if (*c.px.h_err != 0)
+      return set_error("denoise_step: peer exchange timed out waiting for rank %d (a rank skipped a step, or died)", *c.px.h_err - 1);
+    ++c.px.seq;
+  }
   launch_pdl(set_step_params_kernel, dim3(1), dim3(32), 0, st, c.d_step, static_cast<float>(c.timesteps[index]), c.alphas[index],
                                            c.alphas_prev[index], c.sigmas[index], c.sqrt_1m_alphas[index], index != 0,
-                                           static_cast<uint32_t>(index), seed);
+                                           static_cast<uint32_t>(index), seed, peer ? c.px.d_seq : static_cast<unsigned*>(nullptr),
+                                           c.px.seq);
   MD_CHECK(check_launch("set_step_params"));
   const Ctx::GraphKey key{x_local, x_input, clip_embed, noise, eps_out, cfg_scale, c.bind_gen, c.weights_gen};
   const bool same = memcmp(&key, &c.gkey, sizeof(key)) == 0;
@@ -485,7 +509,7 @@ int md_denoise_step(md_ctx* ctx, float* x_local, const float* x_input, const flo
       c.graph_warm = 1;
     } else {                  // second call: capture, instantiate, launch
       const long long before = md_launch_count();
-      const bool split = c.world > 1;
+      const bool split = c.world > 1 && !peer;
       auto capture = [&](int phase, cudaGraphExec_t* out) -> int {
         cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed);
         if (e != cudaSuccess) return set_error("cudaStreamBeginCapture: %s", cudaGetErrorString(e));
@@ -663,6 +687,73 @@ int md_op_cfg_ddim(md_ctx* ctx, const float* eps, float* x, float* eps_out, cons
                          c.alphas_prev[index], c.sigmas[index], c.sqrt_1m_alphas[index], index != 0, seed,
                          static_cast<uint32_t>(index), view0, 1, nullptr, static_cast<cudaStream_t>(stream));
 }
+
+// ---- NVLink peer exchange (Ctx::PeerExchange): md_peer_buffer on every rank, exchange the 64-byte handles out of band
+// (torch.distributed all_gather_object in the Python binding), md_peer_attach with all of them, then a barrier.
+static const size_t kPeerSlotFloats = static_cast<size_t>(16384) * 16;  // vertices per region (FLAME 5 023, SMPL-X 10 475)
+
+int md_peer_buffer(md_ctx* ctx, int world, void* ipc_handle64) {
+  if (!ctx || !ipc_handle64) return set_error("md_peer_buffer: null argument");
+  if (world < 2 || world > 16) return set_error("md_peer_buffer: world=%d outside [2, 16]", world);
+  Ctx::PeerExchange& px = ctx->c.px;
+  if (px.base) return set_error("md_peer_buffer: already allocated");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size is part of the C ABI");
+  px.slot_floats = kPeerSlotFloats;
+  const size_t bytes = static_cast<size_t>(2) * world * px.slot_floats * sizeof(float) + 256;
+  MD_CUDA(cudaMalloc(reinterpret_cast<void**>(&px.base), bytes));
+  MD_CUDA(cudaMemset(px.base, 0, bytes));
+  MD_CUDA(cudaDeviceSynchronize());  // the flags are zero before any peer can learn the handle
+  cudaIpcMemHandle_t h;
+  MD_CUDA(cudaIpcGetMemHandle(&h, px.base));
+  memcpy(ipc_handle64, &h, sizeof(h));
+  return 0;
+}
+
+int md_peer_attach(md_ctx* ctx, int rank, int world, const void* ipc_handles) {
+  if (!ctx || !ipc_handles) return set_error("md_peer_attach: null argument");
+  Ctx& c = ctx->c;
+  Ctx::PeerExchange& px = c.px;
+  if (!px.base) return set_error("md_peer_attach: call md_peer_buffer first");
+  if (px.on) return set_error("md_peer_attach: already attached");
+  if (world < 2 || world > 16 || rank < 0 || rank >= world) return set_error("md_peer_attach: bad rank %d / world %d", rank, world);
+  if (c.world != world || c.rank != rank) return set_error("md_peer_attach: rank/world differ from md_comm_init (%d/%d)", c.rank, c.world);
+  const size_t flags_off = static_cast<size_t>(2) * world * px.slot_floats;
+  float* data[16];
+  unsigned* flags[16];
+  for (int p = 0; p < world; ++p) {
+    if (p == rank) {
+      px.peer_base[p] = px.base;
+    } else {
+      cudaIpcMemHandle_t h;
+      memcpy(&h, static_cast<const char*>(ipc_handles) + static_cast<size_t>(p) * sizeof(h), sizeof(h));
+      void* ptr = nullptr;
+      const cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) return set_error("md_peer_attach: cudaIpcOpenMemHandle(rank %d): %s", p, cudaGetErrorString(e));
+      px.peer_base[p] = ptr;
+    }
+    data[p] = static_cast<float*>(px.peer_base[p]);
+    flags[p] = reinterpret_cast<unsigned*>(data[p] + flags_off);
+  }
+  MD_CUDA(cudaMalloc(reinterpret_cast<void**>(&px.d_peer_data), sizeof(float*) * 16));
+  MD_CUDA(cudaMalloc(reinterpret_cast<void**>(&px.d_peer_flags), sizeof(unsigned*) * 16));
+  MD_CUDA(cudaMalloc(reinterpret_cast<void**>(&px.d_seq), 4 * sizeof(unsigned)));
+  MD_CUDA(cudaMemcpy(px.d_peer_data, data, sizeof(float*) * world, cudaMemcpyHostToDevice));
+  MD_CUDA(cudaMemcpy(px.d_peer_flags, flags, sizeof(unsigned*) * world, cudaMemcpyHostToDevice));
+  MD_CUDA(cudaMemset(px.d_seq, 0, 4 * sizeof(unsigned)));
+  MD_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&px.h_err), sizeof(int), cudaHostAllocMapped));
+  *px.h_err = 0;
+  MD_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&px.d_err), px.h_err, 0));
+  px.seq = 0;
+  px.on = true;
+  // the step's graph layout changes (one graph instead of two around the NCCL call): drop anything captured before
+  if (c.graph) { cudaGraphExecDestroy(c.graph); c.graph = nullptr; }
+  if (c.graph_b) { cudaGraphExecDestroy(c.graph_b); c.graph_b = nullptr; }
+  c.graph_warm = 0;
+  memset(&c.gkey, 0, sizeof(c.gkey));
+  return 0;
+}
+
+int md_peer_attached(md_ctx* ctx) { return ctx && ctx->c.px.on ? 1 : 0; }
 
 int md_comm_unique_id(void* id128) {
   MD_CHECK(nccl_load());

@@ -309,7 +309,9 @@ int vertex_feature_sum(Ctx& c, const float* x_local, const float* t_embed, float
 }
 
 // K4-K6: view-mean + Conv1d, sparse conv net, resample -> vol fp32 [V][V][V][64]
-int spatial_volume_from_vsum(Ctx& c, const float* vsum, float* vol, cudaStream_t st) {
+// peer_exchange: vsum holds this rank's partial sums only; they are pushed to every rank over NVLink and the scatter
+// kernel adds the world's contributions (otherwise vsum is already complete: single rank, or all-reduced by the caller)
+int spatial_volume_from_vsum(Ctx& c, const float* vsum, float* vol, cudaStream_t st, bool peer_exchange) {
   const SampleBinding& sb = c.sb;
   const md_config& mc = c.mcfg;
   Arena& A = c.arena;
@@ -319,8 +321,17 @@ int spatial_volume_from_vsum(Ctx& c, const float* vsum, float* vol, cudaStream_t
   float* bufB = A.get<float>(static_cast<size_t>(nmax) * 64);
   if (A.failed) return set_error("workspace exhausted (sparse conv)");
   const int ninv = mc.smpl_num_views > 0 ? mc.smpl_num_views : sb.n_views;
-  MD_CHECK(launch_smpl_scatter(vsum, 1.f / static_cast<float>(ninv), c.vol.smpl_w, c.vol.smpl_b, sb.row_vertex, sb.n0,
-                               bufA, st));
+  if (peer_exchange) {
+    const Ctx::PeerExchange& px = c.px;
+    const size_t flags_off = static_cast<size_t>(2) * c.world * px.slot_floats;
+    MD_CHECK(launch_peer_push(vsum, sb.nv * 16, px.d_peer_data, px.d_peer_flags, px.d_seq, c.rank, c.world, px.slot_floats, st));
+    MD_CHECK(launch_smpl_scatter_peer(px.base, reinterpret_cast<const unsigned*>(px.base + flags_off), px.d_seq, c.world,
+                                      px.slot_floats, 1.f / static_cast<float>(ninv), c.vol.smpl_w, c.vol.smpl_b,
+                                      sb.row_vertex, sb.n0, bufA, px.d_err, st));
+  } else {
+    MD_CHECK(launch_smpl_scatter(vsum, 1.f / static_cast<float>(ninv), c.vol.smpl_w, c.vol.smpl_b, sb.row_vertex, sb.n0,
+                                 bufA, st));
+  }
   const int rows[9] = {sb.n0, sb.n0, sb.n1, sb.n1, sb.n1, sb.n2, sb.n2, sb.n2, sb.n2};
   const int rule[9] = {0, 0, 1, 2, 2, 3, 4, 4, 4};
   float* in = bufA;

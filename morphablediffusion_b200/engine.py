@@ -200,6 +200,26 @@ class Engine:
     def init_comm(self, rank, world, unique_id_bytes):
         buf = C.create_string_buffer(bytes(unique_id_bytes), 128)
         nat.check(nat.lib.md_comm_init(self._h, rank, world, buf), "md_comm_init")
+        self._rank, self._world = rank, world
+
+    def init_peer_exchange(self, dist):
+        """NVLink peer exchange for the step's cross-rank sum (md_peer_buffer / md_peer_attach, include/mdiff.h): call on
+        every rank after init_comm; `dist` is an initialised torch.distributed (handles travel by all_gather_object,
+        a barrier closes the setup).  Afterwards denoise_step makes no NCCL call."""
+        rank, world = self._rank, self._world
+        if world <= 1:
+            return False
+        h = C.create_string_buffer(64)
+        nat.check(nat.lib.md_peer_buffer(self._h, world, h), "md_peer_buffer")
+        handles = [None] * world
+        dist.all_gather_object(handles, h.raw)
+        buf = C.create_string_buffer(b"".join(handles), 64 * world)
+        nat.check(nat.lib.md_peer_attach(self._h, rank, world, buf), "md_peer_attach")
+        dist.barrier()
+        return True
+
+    def peer_exchange_attached(self):
+        return bool(nat.lib.md_peer_attached(self._h))
 
 
 def comm_unique_id():

@@ -1,5 +1,5 @@
 """Multi-GPU parity against the REFERENCE golden: the 16 views of tests/golden/step_n16_persp.npz sharded over the
-ranks (one NCCL all-reduce of the vertex-feature sums per step), epsilon and x_{t-1} gathered and compared with what
+ranks (one exchange of the vertex-feature sums per step: NVLink peer push, or the NCCL all-reduce with MD_PEER=0), epsilon and x_{t-1} gathered and compared with what
 the real reference modules produced for the unsharded step.
     torchrun --nproc-per-node G --master-addr 127.0.0.1 tools/mgpu_check.py [out.json]"""
 import json
@@ -31,6 +31,8 @@ eng.load_state_dict(sd)
 uid = [comm_unique_id() if rank == 0 else None]
 dist.broadcast_object_list(uid, src=0)
 eng.init_comm(rank, world, uid[0])
+if os.environ.get("MD_PEER", "1") != "0":
+    eng.init_peer_exchange(dist)
 eng.bind(batch, str(gold["projection"]), view0=view0, n_local=n_local)
 xin, cl = x_input[0].cuda().contiguous(), clip[0, 0].cuda().contiguous()
 nz = noise[0, view0:view0 + n_local].cuda().contiguous()
@@ -62,6 +64,7 @@ if rank == 0:
     res["eps_rel_l2"] = rel(ge, torch.from_numpy(gold["eps"])[0])
 if rank == 0:
     res.update(world=world, views=N, views_per_gpu=n_local, tolerance=3e-2,
+               exchange="peer" if eng.peer_exchange_attached() else "nccl",
                ok=bool(max(v for k, v in res.items() if "rel_l2" in k) < 3e-2))
     line = json.dumps(res)
     print("MGPU " + line, flush=True)
