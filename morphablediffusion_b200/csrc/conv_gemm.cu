@@ -340,9 +340,11 @@ int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
   p.contig = contig ? 1 : 0;
   static const bool trace = getenv("MD_TRACE") != nullptr;
   if (trace)
-    fprintf(stderr, "conv_gemm B=%d D=%d H=%d W=%d Cin=%d taps=%d N=%d BN=%d tiles=%dx%d ks=%d split_tiles=%d cg2=%d act=%d f32=%d bf16=%d res=%d\n",
+    fprintf(stderr, "conv_gemm B=%d D=%d H=%d W=%d Cin=%d taps=%d N=%d BN=%d tiles=%dx%d ks=%d split_tiles=%d cg2=%d act=%d f32=%d bf16=%d res=%d "
+            "stats=%d rowvec=%d tail=%d stride=%d\n",
             a.B, a.D, a.H, a.W, a.Cin, a.ntaps, a.N, BN, p.m_tiles, p.n_tiles, p.ksplit, p.split_tiles, p.cg2, a.act, a.out_f32 != nullptr,
-            a.out_bf16 != nullptr, a.res_f32 != nullptr || a.res_bf16 != nullptr);
+            a.out_bf16 != nullptr, a.res_f32 != nullptr ? 1 : a.res_bf16 != nullptr ? 2 : 0, a.col_stats != nullptr, a.rowvec != nullptr,
+            a.gn_out != nullptr, a.in_stride[0] > 1 || a.os[0] > 1);
   if (p.cg2)
     return (BN == 160) ? launch_conv_gemm_cg2_bn160(tmA, tmB, tmO, p, grid, stream, nullptr)
                        : launch_conv_gemm_cg2_bn256(tmA, tmB, tmO, p, grid, stream, nullptr);
