@@ -144,7 +144,10 @@ int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
   auto auto_split = [&](long long tiles) {
     if (a.ksplit != 0 || a.act == ACT_GEGLU || !sw) return 1;
     if (tiles * 2 > num_sms() || kblocks_all < 8) return 1;
-    long long ks = std::min<long long>(std::min<long long>(num_sms() / tiles, kblocks_all / 4), 16);
+    // at least `split_div` K blocks per split (MD_SPLIT_DIV; the sweep in profiles/r02_gemm_autotune.md found 9-way splits
+    // of 36-block loops losing to 2-3-way ones)
+    static const int split_div = getenv("MD_SPLIT_DIV") ? std::max(1, atoi(getenv("MD_SPLIT_DIV"))) : 4;
+    long long ks = std::min<long long>(std::min<long long>(num_sms() / tiles, kblocks_all / split_div), 16);
     // the partial-sum exchange is 5-10 us of pure latency (publish, ticket, read back: profiles/r02 phase stamps), about
     // as long as `split_min_saved` K blocks: a split that shortens the K loop by less than that loses.  MD_SPLIT_MIN
     // overrides the threshold (0 = the round-1 rule).

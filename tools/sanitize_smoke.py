@@ -67,20 +67,21 @@ def depth(T, B, D, HW, ctx):
     print("depth_attention", T, B, D, HW, ctx, float(out.float().abs().mean()))
 
 
-attn(1, 256, 2, 40, 2)
-attn(1, 256, 2, 80, 2)
-attn(1, 128, 1, 64, 2)
-attn(1, 64, 2, 160, 1)
-gemm(128 * 151, 64, 320, 151, 1)
-gemm(1024, 320, 320, 4, -1)
-gn(2, 1024, 320, 32)
-gn(2, 16, 1280, 32)
-gn(2, 37, 64, 32)
-ln(130, 320)
-ln(67, 640)
-ln(33, 1280)
-depth(1, 2, 12, 64, 64)
-depth(1, 2, 6, 16, 512)
+if "--volume-only" not in sys.argv:
+    attn(1, 256, 2, 40, 2)
+    attn(1, 256, 2, 80, 2)
+    attn(1, 128, 1, 64, 2)
+    attn(1, 64, 2, 160, 1)
+    gemm(128 * 151, 64, 320, 151, 1)
+    gemm(1024, 320, 320, 4, -1)
+    gn(2, 1024, 320, 32)
+    gn(2, 16, 1280, 32)
+    gn(2, 37, 64, 32)
+    ln(130, 320)
+    ln(67, 640)
+    ln(33, 1280)
+    depth(1, 2, 12, 64, 64)
+    depth(1, 2, 6, 16, 512)
 
 
 def split_gemm(tail):
@@ -121,9 +122,30 @@ def batch_ops():
     print("batch ops", float(v.abs().mean()), int(u8.sum()))
 
 
+def volume_small():
+    """conditioning branch up to the spatial volume: target-view encoder, vertex features, the sparse-conv net (warp-per-row
+    layers and the cp.async-ring tile kernel with two tap groups), resample"""
+    from morphablediffusion_b200 import synth
+    from morphablediffusion_b200.engine import Engine
+    eng = Engine(max_views_per_call=2)
+    eng.load_state_dict(synth.make_state_dict())
+    eng.bind(synth.make_batch(2), "perspective")
+    x_t, _, _ = synth.make_inputs(2)
+    vol = eng.spatial_volume(x_t[0].cuda().contiguous(), 500.0)
+    torch.cuda.synchronize()
+    print("spatial volume", float(vol.abs().mean()))
+    eng.close()
+
+
+if "--volume-only" in sys.argv:
+    volume_small()
+    print("sanitize smoke done")
+    sys.exit(0)
 split_gemm(1)
 split_gemm(-1)
 batch_ops()
 if "--vae" in sys.argv:
     vae_small()
+if "--volume" in sys.argv:
+    volume_small()
 print("sanitize smoke done")
