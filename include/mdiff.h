@@ -254,6 +254,9 @@ MD_API int md_comm_init(md_ctx* ctx, int rank, int world, const void* id128);
 MD_API int md_peer_buffer(md_ctx* ctx, int world, void* ipc_handle64);
 MD_API int md_peer_attach(md_ctx* ctx, int rank, int world, const void* ipc_handles);
 MD_API int md_peer_attached(md_ctx* ctx);
+/* Back to the NCCL all-reduce (every rank must call it before its next md_denoise_step; used by the host side when
+ * md_peer_attach failed on some rank, e.g. a launcher that hides the peers' devices from each process). */
+MD_API int md_peer_detach(md_ctx* ctx);
 
 #ifdef __cplusplus
 }

@@ -180,7 +180,8 @@ lib.md_comm_init.argtypes = [_vp, C.c_int, C.c_int, _vp]
 lib.md_peer_buffer.argtypes = [_vp, C.c_int, _vp]
 lib.md_peer_attach.argtypes = [_vp, C.c_int, C.c_int, _vp]
 lib.md_peer_attached.argtypes = [_vp]
-for _f in ("md_peer_buffer", "md_peer_attach", "md_peer_attached"):
+lib.md_peer_detach.argtypes = [_vp]
+for _f in ("md_peer_buffer", "md_peer_attach", "md_peer_attached", "md_peer_detach"):
     getattr(lib, _f).restype = C.c_int
 for _f in ("md_embed_time", "md_create", "md_load_weights", "md_bind_sample", "md_voxelize", "md_spatial_volume", "md_frustum_feats",
            "md_unet_forward", "md_denoise_step", "md_ddim_timestep", "md_set_ddim", "md_ddim_steps", "md_comm_unique_id", "md_comm_init",

@@ -755,6 +755,20 @@ int md_peer_attach(md_ctx* ctx, int rank, int world, const void* ipc_handles) {
 
 int md_peer_attached(md_ctx* ctx) { return ctx && ctx->c.px.on ? 1 : 0; }
 
+int md_peer_detach(md_ctx* ctx) {
+  if (!ctx) return set_error("md_peer_detach: null context");
+  Ctx& c = ctx->c;
+  if (c.px.on) {  // back to the NCCL all-reduce between two graphs: drop the one-graph capture
+    MD_CUDA(cudaDeviceSynchronize());
+    c.px.on = false;
+    if (c.graph) { cudaGraphExecDestroy(c.graph); c.graph = nullptr; }
+    if (c.graph_b) { cudaGraphExecDestroy(c.graph_b); c.graph_b = nullptr; }
+    c.graph_warm = 0;
+    memset(&c.gkey, 0, sizeof(c.gkey));
+  }
+  return 0;
+}
+
 int md_comm_unique_id(void* id128) {
   MD_CHECK(nccl_load());
   const int r = g_nccl.GetUniqueId(id128);

@@ -210,13 +210,31 @@ class Engine:
         if world <= 1:
             return False
         h = C.create_string_buffer(64)
-        nat.check(nat.lib.md_peer_buffer(self._h, world, h), "md_peer_buffer")
+        err = None
+        try:
+            nat.check(nat.lib.md_peer_buffer(self._h, world, h), "md_peer_buffer")
+        except nat.MdiffError as e:
+            err = str(e)
         handles = [None] * world
-        dist.all_gather_object(handles, h.raw)
-        buf = C.create_string_buffer(b"".join(handles), 64 * world)
-        nat.check(nat.lib.md_peer_attach(self._h, rank, world, buf), "md_peer_attach")
+        dist.all_gather_object(handles, (h.raw, err))
+        if err is None and all(e is None for _, e in handles):
+            buf = C.create_string_buffer(b"".join(raw for raw, _ in handles), 64 * world)
+            try:
+                nat.check(nat.lib.md_peer_attach(self._h, rank, world, buf), "md_peer_attach")
+            except nat.MdiffError as e:
+                err = str(e)
+        # the exchange is collective: one rank that cannot map its peers (e.g. a launcher that hides the other devices
+        # from each process) sends everyone back to the NCCL all-reduce
+        errs = [None] * world
+        dist.all_gather_object(errs, err)
+        errs = [e for _, e in handles if e is not None] + [e for e in errs if e is not None]
+        if errs:
+            nat.check(nat.lib.md_peer_detach(self._h), "md_peer_detach")
+            if rank == 0:
+                import warnings
+                warnings.warn("NVLink peer exchange unavailable, using the NCCL all-reduce: " + errs[0])
         dist.barrier()
-        return True
+        return not errs
 
     def peer_exchange_attached(self):
         return bool(nat.lib.md_peer_attached(self._h))
