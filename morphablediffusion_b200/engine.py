@@ -4,6 +4,7 @@ Host-side glue only — tensors are torch CUDA tensors used as device memory; ev
 libmdiff.so.  The reference-shaped classes in morphablediffusion_b200/ldm_api.py are built on top of this handle.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -220,6 +221,8 @@ class Engine:
         if err is None and all(e is None for _, e in handles):
             buf = C.create_string_buffer(b"".join(raw for raw, _ in handles), 64 * world)
             try:
+                if os.environ.get("MD_PEER_TEST_FAIL") == str(rank):  # test hook: this rank pretends it cannot map its peers
+                    raise nat.MdiffError("md_peer_attach: simulated failure (MD_PEER_TEST_FAIL)")
                 nat.check(nat.lib.md_peer_attach(self._h, rank, world, buf), "md_peer_attach")
             except nat.MdiffError as e:
                 err = str(e)

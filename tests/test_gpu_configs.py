@@ -251,11 +251,12 @@ def test_sample_seeds_differ_between_calls_and_items(state_dict):
     assert rel(a, c) > 1e-2                 # next call draws new seeds
 
 
-@pytest.mark.parametrize("exchange", ["peer", "nccl"])
+@pytest.mark.parametrize("exchange", ["peer", "nccl", "peer_fallback"])
 def test_multi_gpu_sharded_step_vs_reference_golden(tmp_path, exchange):
     """BASELINE config 3: the 16 views sharded over 2 ranks reproduce the REFERENCE golden of the unsharded step —
     epsilon and x_{t-1}, for plain launches, graph capture and graph replay — with the vertex-feature sums exchanged
-    over NVLink peer memory inside the step's kernels (default) and through the NCCL all-reduce (MD_PEER=0).
+    over NVLink peer memory inside the step's kernels (default) and through the NCCL all-reduce (MD_PEER=0);
+    "peer_fallback": rank 1 pretends it cannot map its peers, and every rank must end up on the NCCL path.
     Needs two GPUs (gpurun --gpus 2); tools/mgpu_check.py is the worker."""
     import json
     import subprocess
@@ -264,13 +265,15 @@ def test_multi_gpu_sharded_step_vs_reference_golden(tmp_path, exchange):
         pytest.skip("needs 2 GPUs")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = tmp_path / "mgpu.json"
-    port = 29600 + os.getpid() % 300 + (0 if exchange == "peer" else 301)
-    env = dict(os.environ, MD_PEER="1" if exchange == "peer" else "0")
+    port = 29600 + os.getpid() % 300 + {"peer": 0, "nccl": 301, "peer_fallback": 602}[exchange]
+    env = dict(os.environ, MD_PEER="0" if exchange == "nccl" else "1")
+    if exchange == "peer_fallback":
+        env["MD_PEER_TEST_FAIL"] = "1"
     p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                         "--master-addr", "127.0.0.1", "--master-port", str(port),
                         os.path.join(root, "tools", "mgpu_check.py"), str(out)],
                        capture_output=True, text=True, timeout=900, cwd=root, env=env)
     assert p.returncode == 0, p.stderr[-3000:]
     res = json.loads(out.read_text())
-    assert res["exchange"] == exchange, res
+    assert res["exchange"] == ("peer" if exchange == "peer" else "nccl"), res
     assert res["ok"] and res["eps_rel_l2"] < BF16_REL, res
