@@ -25,6 +25,7 @@ class Engine:
         if not torch.cuda.is_available():
             raise nat.MdiffError("the Morphable Diffusion hot path needs a CUDA device (no CPU fallback)")
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self._rank, self._world = 0, 1   # set by init_comm
         ucfg = unet_config or UNetConfig()
         cfg = nat.MdConfig()
         nat.lib.md_default_config(C.byref(cfg))

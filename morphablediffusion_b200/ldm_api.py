@@ -338,6 +338,7 @@ class SyncMultiviewDiffusion(_Base):
         self._engine = None
         self._engine_version = None
         self._bound_key = None
+        self._shard = None   # (rank, world, dist) once enable_view_sharding() has been called
         if sample_type == "ddim":
             self.sampler = SyncDDIMSampler(self, sample_steps, "uniform", 1.0, latent_size=image_size // 8)
         else:
@@ -419,11 +420,46 @@ class SyncMultiviewDiffusion(_Base):
     _BOUND_KEYS = ("target_K", "target_RT", "vertices", "coord", "out_sh", "bounds", "target_elevation",
                    "target_azimuth", "input_elevation", "input_azimuth")
 
-    def _bound_engine(self, batch):
+    def enable_view_sharding(self, dist=None):
+        """Opt-in multi-GPU sampling (no counterpart in the reference, which samples on one GPU): with an initialised
+        torch.distributed job of G ranks, one process per GPU, every later SyncDDIMSampler.sample() steps only this
+        rank's N / G views of each sample — the step's one cross-rank quantity travels over NVLink peer memory inside the
+        library (Engine.init_peer_exchange; NCCL all-reduce as the fallback) — and returns the gathered latents on every
+        rank.  All ranks must call sample() with the same batch; x_T and the step-noise seed come from rank 0.  The
+        stage-level methods (construct_spatial_volume, get_target_view_feats, denoise_apply ...) bind all views and are
+        refused while sharding is on."""
+        import os
+
+        import torch.distributed as tdist
+        dist = dist or tdist
+        if self._shard is not None:
+            return True
+        if not dist.is_initialized():
+            raise RuntimeError("enable_view_sharding needs an initialised torch.distributed process group")
+        rank, world = dist.get_rank(), dist.get_world_size()
+        if world == 1:
+            return False
+        if self.view_num % world:
+            raise ValueError(f"view_num={self.view_num} is not divisible by the {world} ranks")
+        from .engine import comm_unique_id
+        eng = self._get_engine()
+        uid = [comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        eng.init_comm(rank, world, uid[0])
+        if os.environ.get("MD_PEER", "1") != "0":
+            eng.init_peer_exchange(dist)
+        self._shard = (rank, world, dist)
+        self._bound_key = None
+        return True
+
+    def _bound_engine(self, batch, shard=False):
         """Engine with `batch` (B = 1) bound.  The binding is keyed on tensor IDENTITY + in-place version of every
         bound tensor (the tensors are kept alive, so an id cannot be recycled by the allocator); tensors that are new
         objects are compared by CONTENT against the bound copies before a re-bind is skipped.  Addresses are never
-        part of the key: the caching allocator hands equal-shaped batches the same addresses."""
+        part of the key: the caching allocator hands equal-shaped batches the same addresses.
+        shard=True (sampler loop with enable_view_sharding): only this rank's view range is bound."""
+        if self._shard is not None and not shard:
+            raise RuntimeError("view sharding is enabled: this rank holds only its own views, use sample()")
         eng = self._get_engine()
         cur = tuple(batch[k] for k in self._BOUND_KEYS)
         ver = tuple(int(t._version) for t in cur)
@@ -437,7 +473,14 @@ class SyncMultiviewDiffusion(_Base):
                 return eng
         if batch["target_K"].shape[0] != 1:
             raise ValueError("bind one sample at a time")
-        eng.bind(batch, self.projection)
+        if self._shard is not None:
+            rank, world, _ = self._shard
+            n_views = batch["target_K"].shape[1]
+            if n_views % world:
+                raise ValueError(f"{n_views} views are not divisible by the {world} ranks")
+            eng.bind(batch, self.projection, view0=rank * (n_views // world), n_local=n_views // world)
+        else:
+            eng.bind(batch, self.projection)
         self._bound_key = (cur, ver, tuple(t.detach().clone() for t in cur))
         return eng
 
@@ -619,6 +662,21 @@ class SyncMultiviewDiffusion(_Base):
         raise NotImplementedError("training path is not built yet")
 
 
+def _dist_broadcast(dist, t):
+    """rank 0's tensor on every rank (gloo moves host tensors only)."""
+    buf = (t.cpu() if dist.get_backend() == "gloo" else t).contiguous()
+    dist.broadcast(buf, src=0)
+    return buf.to(t.device)
+
+
+def _dist_all_gather_cat(dist, t, dim):
+    """every rank's tensor, concatenated along `dim` in rank order, on every rank."""
+    buf = (t.cpu() if dist.get_backend() == "gloo" else t).contiguous()
+    parts = [torch.empty_like(buf) for _ in range(dist.get_world_size())]
+    dist.all_gather(parts, buf)
+    return torch.cat(parts, dim).to(t.device)
+
+
 class SyncDDIMSampler:
     """morphable_diffusion.py:648-776.  `sample` runs 50 fused CUDA steps; noise is Philox keyed by global view."""
 
@@ -644,10 +702,10 @@ class SyncDDIMSampler:
         self.ddim_sqrt_one_minus_alphas = torch.sqrt(1.0 - self.ddim_alphas).float()
         self.seed = None  # None: sample() draws a fresh seed from torch's generator per call (torch.manual_seed rules)
 
-    def _engine_for(self, batch_item):
+    def _engine_for(self, batch_item, shard=False):
         """Bound engine whose DDIM schedule is THIS sampler's (ddim_num_steps, eta); the library's schedule is checked
         against the sampler's own timestep table so a mismatch can never denoise at the wrong timestep silently."""
-        eng = self.model._bound_engine(batch_item)
+        eng = self.model._bound_engine(batch_item, shard=True) if shard else self.model._bound_engine(batch_item)
         eng.set_ddim(self.ddim_num_steps, self.eta)
         return eng
 
@@ -715,16 +773,29 @@ class SyncDDIMSampler:
         device = self.model._device
         x = torch.randn([B, N, C, H, W], device=device) if x_T is None else x_T.to(device, torch.float32).clone()
         self.seed = int(torch.randint(0, 2 ** 62, (1,)).item())  # step noise: Philox(seed ^ item, index, view, element)
+        shard = getattr(self.model, "_shard", None)
+        v0, n_loc = 0, N
+        if shard is not None:   # enable_view_sharding: this rank steps views [v0, v0 + n_loc); rank 0's x_T and seed rule
+            rank, world, dist = shard
+            if N % world:
+                raise ValueError(f"{N} views are not divisible by the {world} ranks")
+            n_loc = N // world
+            v0 = rank * n_loc
+            x = _dist_broadcast(dist, x)
+            self.seed = int(_dist_broadcast(dist, torch.tensor([self.seed], dtype=torch.int64, device=device)).item())
+            # the conditioning too: prepare() draws the input latent from the VAE posterior with each rank's own generator
+            input_info = dict(input_info, x=_dist_broadcast(dist, input_info["x"].detach().float()))
+            clip_embed = _dist_broadcast(dist, clip_embed.detach().float())
         total = self.ddim_timesteps.shape[0]
         logged = [index for index in range(total - 1, -1, -1) if index % log_every_t == 0 or index == total - 1]
         inter_items = []
         # Samples are independent, so the loop nest is (sample, step) instead of the reference's (step, sample): each
         # sample's cameras / mesh / sparse-conv rulebook are bound once and its 50 steps replay one CUDA graph.
         for bi in range(B):
-            eng = self._engine_for(_batch_item(batch, bi))
+            eng = self._engine_for(_batch_item(batch, bi), shard=shard is not None)
             # one work buffer per sample, stepped in place: the library sees the same pointers on all 50 steps, so the
             # whole step is captured once as a CUDA graph and replayed
-            xw = x[bi].detach().to(torch.float32).contiguous().clone()
+            xw = x[bi, v0:v0 + n_loc].detach().to(torch.float32).contiguous().clone()
             xin = input_info["x"][bi].detach().contiguous().float()
             clip = clip_embed[bi].detach().reshape(-1).contiguous().float()
             seed = self._step_seed(bi)
@@ -733,10 +804,13 @@ class SyncDDIMSampler:
             for i in range(total):
                 index = total - i - 1
                 if nz is not None:
-                    nz.copy_(step_noise[index, bi])
+                    nz.copy_(step_noise[index, bi, v0:v0 + n_loc])
                 eng.denoise_step(xw, xin, clip, index, unconditional_scale, noise=nz, seed=seed)
                 if index in logged:
                     snaps.append(xw.clone()[None])
+            if shard is not None:   # views back together, on every rank
+                xw = _dist_all_gather_cat(shard[2], xw, 0)
+                snaps = [_dist_all_gather_cat(shard[2], sn, 1) for sn in snaps]
             x[bi] = xw
             inter_items.append(snaps)
         inter = {"x_inter": [torch.cat([it[j] for it in inter_items], 0) for j in range(len(logged))]}

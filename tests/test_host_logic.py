@@ -117,6 +117,97 @@ def test_view_sharding_allreduce_equals_unsharded_sum():
     assert err < 1e-5
 
 
+# ----------------------------------------------------------------------------- N > 1: sampler loop with sharded views
+class _FakeEngine:
+    """Stands in for the CUDA engine in the sampler-loop test: one 'step' adds a value that depends on the GLOBAL view
+    index, the DDIM index and the seed, so a sharded run matches the unsharded one only if the view ranges, the seed
+    broadcast and the gather are right."""
+
+    def __init__(self):
+        self.view0, self.n_local = 0, None
+
+    def set_ddim(self, steps, eta):
+        pass
+
+    def denoise_step(self, x, xin, clip, index, scale, noise=None, seed=0):
+        n = x.shape[0]
+        assert self.n_local in (None, n)
+        g = torch.arange(self.view0, self.view0 + n, dtype=torch.float32).view(n, 1, 1, 1)
+        x.mul_(0.9).add_(0.01 * (g + 1.0) * (index + 1) + float(seed % 1000) * 1e-4)
+        if noise is not None:
+            x.add_(noise)
+
+
+class _FakeModel:
+    num_timesteps = 1000
+    view_num = 4
+    _device = torch.device("cpu")
+
+    def __init__(self, shard):
+        self.alphas_cumprod = torch.linspace(0.999, 0.01, 1000)
+        self._shard = shard
+        self.eng = _FakeEngine()
+
+    def _bound_engine(self, batch_item, shard=False):
+        assert shard == (self._shard is not None)
+        n = batch_item["target_K"].shape[1]
+        if shard:
+            rank, world, _ = self._shard
+            self.eng.view0, self.eng.n_local = rank * (n // world), n // world
+        else:
+            self.eng.view0, self.eng.n_local = 0, n
+        return self.eng
+
+
+def _sampler_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from morphablediffusion_b200.ldm_api import SyncDDIMSampler
+    B, N = 2, 4
+    batch = {"target_K": torch.zeros(B, N, 3, 3)}
+    info = {"x": torch.zeros(B, 4, 8, 8)}
+    clip = torch.zeros(B, 1, 768)
+    g = torch.Generator().manual_seed(3)
+    x_T = torch.randn(B, N, 4, 8, 8, generator=g)
+    noise = 0.1 * torch.randn(5, B, N, 4, 8, 8, generator=g)
+    sharded = SyncDDIMSampler(_FakeModel((rank, world, dist)), 5, latent_size=8)
+    torch.manual_seed(100 + rank)                       # ranks disagree on the seed (and would on x_T): rank 0 rules
+    xs, inter_s = sharded.sample(info, clip, 2.0, log_every_t=2, batch=batch, x_T=x_T, step_noise=noise)
+    seed_used = sharded.seed
+    torch.manual_seed(200 + rank)
+    xr, _ = sharded.sample(info, clip, 2.0, batch=batch)  # x_T drawn per rank, then broadcast
+    # unsharded loop with the seed rank 0 drew
+    plain = SyncDDIMSampler(_FakeModel(None), 5, latent_size=8)
+    torch.manual_seed(100)
+    xp, inter_p = plain.sample(info, clip, 2.0, log_every_t=2, batch=batch, x_T=x_T, step_noise=noise)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (xs, xr, seed_used))
+    if rank == 0:
+        same_on_ranks = all(torch.equal(gathered[0][0], o[0]) and torch.equal(gathered[0][1], o[1]) and gathered[0][2] == o[2]
+                            for o in gathered)
+        inter_ok = len(inter_s["x_inter"]) == len(inter_p["x_inter"]) and all(
+            torch.allclose(a, b) for a, b in zip(inter_s["x_inter"], inter_p["x_inter"]))
+        out.put((same_on_ranks, float((xs - xp).abs().max()), inter_ok, plain.seed == seed_used))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sampler_loop_with_sharded_views_matches_the_unsharded_loop():
+    """SyncDDIMSampler.sample under enable_view_sharding (host logic only, the engine is a stand-in): every rank steps
+    its own view range, x_T and the step seed come from rank 0, latents and logged intermediates are gathered on every rank."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_sampler_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    same_on_ranks, err, inter_ok, seed_ok = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert same_on_ranks and seed_ok and inter_ok and err < 1e-6
+
+
 def test_alignment_map_composes_the_reference_operations():
     """generate_face.py:203-213 as one affine map (batch.alignment_map) against the operation-by-operation oracle."""
     import numpy as np
